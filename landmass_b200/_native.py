@@ -1,0 +1,252 @@
+"""ctypes binding of the CUDA library (landmass_b200/csrc -> liblandmass_b200.so).
+
+This is the ONLY compute backend of the package.  If the shared library is
+missing or cannot be loaded (e.g. no CUDA driver), construction raises — there
+is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "liblandmass_b200.so")
+
+EXPORTED_SYMBOLS = [
+    "lmb_abi_version", "lmb_create", "lmb_destroy", "lmb_last_error", "lmb_navdata_upload",
+    "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
+    "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
+    "lmb_get_step_timings",
+]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"landmass_b200 native error {status}: {message}")
+        self.status = status
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    path = path or _LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"landmass_b200: CUDA library not built ({path}); run `python -c 'import "
+            "__graft_entry__ as g; g.build()'` — there is no CPU fallback")
+    lib = C.CDLL(path)
+    declare_prototypes(lib, "lmb_")
+    return lib
+
+
+def declare_prototypes(lib, prefix: str):
+    """Declares argument/return types shared by the lmb_* and (test-only) orc_* entry points."""
+    u32, i32, f32 = C.c_uint32, C.c_int32, C.c_float
+    vp = C.c_void_p
+
+    def fn(name, restype, argtypes):
+        f = getattr(lib, prefix + name, None)
+        if f is not None:
+            f.restype = restype
+            f.argtypes = argtypes
+
+    fn("navdata_upload", i32, [vp, C.POINTER(_abi.NavDataDesc)])
+    fn("step", i32, [vp, C.POINTER(_abi.AgentsIn), C.POINTER(_abi.CharactersIn),
+                     C.POINTER(_abi.Options), f32, C.POINTER(_abi.AgentsOut)])
+    fn("agents_upload", i32, [vp, C.POINTER(_abi.AgentsIn), C.POINTER(_abi.CharactersIn)])
+    fn("step_resident", i32, [vp, C.POINTER(_abi.Options), f32])
+    fn("agents_download", i32, [vp, C.POINTER(_abi.AgentsOut)])
+    fn("pathing_results", i32, [vp, C.POINTER(_abi.PathingResult), u32, C.POINTER(u32)])
+    fn("agent_path", i32, [vp, u32, _abi.u32p, _abi.u32p, u32, C.POINTER(u32)])
+    fn("sample_points", i32, [vp, u32, _abi.f32p, C.POINTER(_abi.Options), _abi.f32p, _abi.u32p])
+    fn("find_paths", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, _abi.f32p, _abi.u32p,
+                           _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.u32p,
+                           _abi.u32p, u32])
+    fn("get_step_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
+    if prefix == "lmb_":
+        lib.lmb_abi_version.restype = u32
+        lib.lmb_abi_version.argtypes = []
+        lib.lmb_create.restype = i32
+        lib.lmb_create.argtypes = [C.POINTER(_abi.Config), C.POINTER(vp)]
+        lib.lmb_destroy.restype = None
+        lib.lmb_destroy.argtypes = [vp]
+        lib.lmb_last_error.restype = C.c_char_p
+        lib.lmb_last_error.argtypes = [vp]
+
+
+class CBackend:
+    """Calls shared by the CUDA library and the test-only oracle (same signatures)."""
+
+    prefix = "lmb_"
+
+    def __init__(self):
+        self.lib = None
+        self.ctx = None
+
+    def _f(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def _check(self, status: int):
+        if status != 0:
+            msg = ""
+            if self.prefix == "lmb_":
+                raw = self.lib.lmb_last_error(self.ctx)
+                msg = raw.decode() if raw else ""
+            raise NativeError(status, msg)
+
+    def navdata_upload(self, flat: dict):
+        desc, keep = _abi.make_navdata_desc(flat)
+        self._check(self._f("navdata_upload")(self.ctx, C.byref(desc)))
+        self._n_polys = int(flat["n_polys"])
+        del keep
+
+    def step(self, ag: dict, ch: dict | None, options: _abi.Options, dt: float) -> dict:
+        a, ka = _abi.make_agents_in(ag)
+        c, kc = _abi.make_characters_in(ch)
+        o, out = _abi.make_agents_out(a.n)
+        self._check(self._f("step")(self.ctx, C.byref(a), C.byref(c), C.byref(options),
+                                    C.c_float(dt), C.byref(o)))
+        del ka, kc
+        return out
+
+    def pathing_results(self):
+        cap = 1024
+        while True:
+            buf = (_abi.PathingResult * cap)()
+            cnt = C.c_uint32(0)
+            st = self._f("pathing_results")(self.ctx, buf, cap, C.byref(cnt))
+            if st == _abi.ERR_CAPACITY:
+                cap = max(cnt.value, cap * 2)
+                continue
+            self._check(st)
+            return [(buf[i].agent, buf[i].success, buf[i].explored_nodes) for i in range(cnt.value)]
+
+    def pathing_results_array(self):
+        """Same as pathing_results but as an (n,3) uint32 array (for large batches)."""
+        cap = 1 << 16
+        while True:
+            buf = np.zeros((cap, 3), dtype=np.uint32)
+            cnt = C.c_uint32(0)
+            st = self._f("pathing_results")(
+                self.ctx, C.cast(buf.ctypes.data, C.POINTER(_abi.PathingResult)), cap, C.byref(cnt))
+            if st == _abi.ERR_CAPACITY:
+                cap = max(cnt.value, cap * 2)
+                continue
+            self._check(st)
+            return buf[:cnt.value]
+
+    def agent_path(self, slot: int):
+        cap = 256
+        while True:
+            nodes = np.zeros(cap, dtype=np.uint32)
+            portals = np.zeros(cap, dtype=np.uint32)
+            ln = C.c_uint32(0)
+            st = self._f("agent_path")(self.ctx, slot, _abi.ptr(nodes, _abi.u32p),
+                                       _abi.ptr(portals, _abi.u32p), cap, C.byref(ln))
+            if st == _abi.ERR_CAPACITY:
+                cap = max(ln.value, cap * 2)
+                continue
+            self._check(st)
+            return nodes[:ln.value], portals[:ln.value]
+
+    def sample_points(self, points, options: _abi.Options):
+        pts = _abi.as_f32(points).reshape(-1, 3)
+        n = len(pts)
+        out_p = np.zeros((max(n, 1), 3), dtype=np.float32)
+        out_n = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self._f("sample_points")(self.ctx, n, _abi.ptr(pts, _abi.f32p), C.byref(options),
+                                             _abi.ptr(out_p, _abi.f32p), _abi.ptr(out_n, _abi.u32p)))
+        return out_p[:n], out_n[:n]
+
+    def find_paths(self, start_node, start_point, end_node, end_point, overrides=None,
+                   path_capacity: int | None = None):
+        """overrides: list (per query) of dict{type: cost} or None."""
+        sn = _abi.as_u32(start_node)
+        en = _abi.as_u32(end_node)
+        sp = _abi.as_f32(start_point).reshape(-1, 3)
+        ep = _abi.as_f32(end_point).reshape(-1, 3)
+        n = len(sn)
+        ob = ot = oc = None
+        if overrides is not None:
+            ob = np.zeros(n + 1, dtype=np.uint32)
+            tl, cl = [], []
+            for i, ov in enumerate(overrides):
+                for t, c in sorted((ov or {}).items()):
+                    tl.append(t)
+                    cl.append(c)
+                ob[i + 1] = len(tl)
+            ot = np.array(tl + [0], dtype=np.uint32)
+            oc = np.array(cl + [0], dtype=np.float32)
+        cap = path_capacity or max(1024, 64 * n)
+        while True:
+            succ = np.zeros(max(n, 1), dtype=np.uint32)
+            expl = np.zeros(max(n, 1), dtype=np.uint32)
+            begin = np.zeros(n + 1, dtype=np.uint32)
+            nodes = np.zeros(cap, dtype=np.uint32)
+            portals = np.zeros(cap, dtype=np.uint32)
+            st = self._f("find_paths")(
+                self.ctx, n, _abi.ptr(sn, _abi.u32p), _abi.ptr(sp, _abi.f32p), _abi.ptr(en, _abi.u32p),
+                _abi.ptr(ep, _abi.f32p), _abi.ptr(ob, _abi.u32p), _abi.ptr(ot, _abi.u32p),
+                _abi.ptr(oc, _abi.f32p), _abi.ptr(succ, _abi.u32p), _abi.ptr(expl, _abi.u32p),
+                _abi.ptr(begin, _abi.u32p), _abi.ptr(nodes, _abi.u32p), _abi.ptr(portals, _abi.u32p), cap)
+            if st == _abi.ERR_CAPACITY:
+                cap = max(int(begin[n]), cap * 2)
+                continue
+            self._check(st)
+            return succ[:n], expl[:n], begin, nodes[:begin[n]], portals[:begin[n]]
+
+
+class NativeBackend(CBackend):
+    prefix = "lmb_"
+
+    def __init__(self, max_agents: int = 1024, device: int = 0, astar_slots: int = 0,
+                 scratch_bytes: int = 0, flags: int = 0, lib_path: str | None = None):
+        super().__init__()
+        self.lib = load_library(lib_path)
+        if self.lib.lmb_abi_version() != _abi.ABI_VERSION:
+            raise RuntimeError("landmass_b200: ABI version mismatch between header mirror and library")
+        cfg = _abi.Config()
+        cfg.struct_size = C.sizeof(_abi.Config)
+        cfg.device = device
+        cfg.max_agents = max_agents
+        cfg.astar_slots = astar_slots
+        cfg.scratch_bytes = scratch_bytes
+        cfg.flags = flags
+        ctx = C.c_void_p()
+        st = self.lib.lmb_create(C.byref(cfg), C.byref(ctx))
+        if st != 0:
+            raw = self.lib.lmb_last_error(None)
+            raise NativeError(st, raw.decode() if raw else "lmb_create failed")
+        self.ctx = ctx
+
+    # resident-input variants (bench `value` path)
+    def agents_upload(self, ag: dict, ch: dict | None):
+        a, ka = _abi.make_agents_in(ag)
+        c, kc = _abi.make_characters_in(ch)
+        self._check(self.lib.lmb_agents_upload(self.ctx, C.byref(a), C.byref(c)))
+        self._n_agents = a.n
+
+    def step_resident(self, options: _abi.Options, dt: float):
+        self._check(self.lib.lmb_step_resident(self.ctx, C.byref(options), C.c_float(dt)))
+
+    def agents_download(self) -> dict:
+        o, out = _abi.make_agents_out(self._n_agents)
+        self._check(self.lib.lmb_agents_download(self.ctx, C.byref(o)))
+        return out
+
+    def step_timings(self) -> _abi.StepTimings:
+        t = _abi.StepTimings()
+        self._check(self.lib.lmb_get_step_timings(self.ctx, C.byref(t)))
+        return t
+
+    def close(self):
+        if self.ctx is not None and self.lib is not None:
+            self.lib.lmb_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
