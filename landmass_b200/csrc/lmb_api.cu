@@ -1,0 +1,954 @@
+// landmass_b200 — C ABI implementation (include/landmass_b200.h): context, navdata
+// upload, and the orchestration of one `Archipelago::update` on the device.
+//
+// Step pipeline on one stream (reference lib.rs:270-534):
+//   H2D inputs -> k_sample_points (agents, targets, characters)      phase A / A'
+//              -> k_repath_decide (decision + repath queue)          phase B (decision)
+//              -> [sync: n_repath] -> k_astar (loop on overflow)     phase B (A*)
+//              -> k_follow                                           phase C
+//              -> avoidance kernels                                  phase D
+//              -> k_gather_outputs -> D2H outputs
+// There is no CPU fallback anywhere in this file: every phase is a kernel.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "lmb_context.h"
+
+static thread_local std::string g_create_error;
+
+
+// ---------------------------------------------------------------------------
+// host math mirroring the device (no FMA: compiled with -ffp-contract=off)
+// ---------------------------------------------------------------------------
+namespace {
+struct H3 {
+  float x, y, z;
+};
+inline H3 h_rotate_z(float s, float c, H3 v) {
+  volatile float b2 = (0.0f * 0.0f + 0.0f * 0.0f) + s * s;
+  volatile float k1 = c * c - b2;
+  volatile float vb = (v.x * 0.0f + v.y * 0.0f) + v.z * s;
+  volatile float k2 = vb * 2.0f;
+  volatile float k3 = c * 2.0f;
+  volatile float bx = 0.0f * v.z - v.y * s, by = s * v.x - v.z * 0.0f, bz = 0.0f * v.y - v.x * 0.0f;
+  volatile float x = (v.x * k1 + 0.0f * k2) + bx * k3;
+  volatile float y = (v.y * k1 + 0.0f * k2) + by * k3;
+  volatile float z = (v.z * k1 + s * k2) + bz * k3;
+  return {x, y, z};
+}
+inline H3 h_apply(const DevIsland& is, H3 p) {
+  H3 r = h_rotate_z(is.fs, is.fc, p);
+  volatile float x = r.x + is.tx, y = r.y + is.ty, z = r.z + is.tz;
+  return {x, y, z};
+}
+}  // namespace
+
+extern "C" {
+
+uint32_t lmb_abi_version(void) { return LMB_ABI_VERSION; }
+
+const char* lmb_last_error(const lmb_ctx* ctx) {
+  if (!ctx) return g_create_error.c_str();
+  return ctx->error.c_str();
+}
+
+int32_t lmb_create(const lmb_config* config, lmb_ctx** out_ctx) {
+  if (!config || !out_ctx || config->struct_size != sizeof(lmb_config)) {
+    g_create_error = "lmb_create: bad config (struct_size mismatch?)";
+    return LMB_ERR_INVALID_ARGUMENT;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("lmb_create: no CUDA device available (") + cudaGetErrorString(e) +
+                     "); landmass_b200 has no CPU fallback";
+    return LMB_ERR_CUDA;
+  }
+  if (config->device < 0 || config->device >= count) {
+    g_create_error = "lmb_create: device ordinal out of range";
+    return LMB_ERR_INVALID_ARGUMENT;
+  }
+  lmb_ctx* ctx = new lmb_ctx();
+  ctx->cfg = *config;
+  ctx->device = config->device;
+  if (ctx->cfg.max_agents == 0) ctx->cfg.max_agents = 1024;
+  e = cudaSetDevice(ctx->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 9 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, sizeof(AStarCounters));
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(uint32_t));
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, ctx->device);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("lmb_create: ") + cudaGetErrorString(e);
+    delete ctx;
+    return LMB_ERR_CUDA;
+  }
+  ctx->sm_count = (uint32_t)prop.multiProcessorCount;
+  const uint32_t m = ctx->cfg.max_agents;
+  cudaError_t es[] = {
+      ctx->d_slot_path_off.reserve(m), ctx->d_slot_path_len.reserve(m), ctx->d_scan_tmp.reserve(m + 1),
+      ctx->d_desired_move.reserve(3 * (size_t)m), ctx->d_reached_start.reserve(3 * (size_t)m),
+      ctx->d_reached_end.reserve(3 * (size_t)m), ctx->d_state.reserve(m),
+      ctx->d_reached_link_id.reserve(m), ctx->d_pool_cursor.reserve(1), ctx->d_counters.reserve(1),
+      ctx->d_queue_count.reserve(1), ctx->d_avoid_overflow.reserve(4), ctx->d_bounds_tmp.reserve(8)};
+  for (cudaError_t x : es)
+    if (x != cudaSuccess) {
+      g_create_error = std::string("lmb_create: ") + cudaGetErrorString(x);
+      delete ctx;
+      return LMB_ERR_CUDA;
+    }
+  cudaMemsetAsync(ctx->d_slot_path_len.p, 0, m * sizeof(uint32_t), ctx->stream);
+  cudaMemsetAsync(ctx->d_slot_path_off.p, 0, m * sizeof(uint32_t), ctx->stream);
+  cudaMemsetAsync(ctx->d_desired_move.p, 0, 3 * (size_t)m * sizeof(float), ctx->stream);
+  cudaMemsetAsync(ctx->d_state.p, 0, m * sizeof(uint32_t), ctx->stream);  // LMB_STATE_IDLE
+  cudaMemsetAsync(ctx->d_reached_link_id.p, 0xff, m * sizeof(uint32_t), ctx->stream);
+  cudaMemsetAsync(ctx->d_pool_cursor.p, 0, sizeof(unsigned long long), ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  *out_ctx = ctx;
+  return LMB_OK;
+}
+
+void lmb_destroy(lmb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  for (int i = 0; i < 9; i++)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  delete ctx;
+}
+
+// ---------------------------------------------------------------------------
+// navdata upload
+// ---------------------------------------------------------------------------
+static PathPool make_pool(lmb_ctx* ctx) {
+  PathPool p;
+  p.entries = ctx->d_pool[ctx->pool_cur].p;
+  p.cursor = ctx->d_pool_cursor.p;
+  p.capacity = ctx->pool_capacity;
+  p.slot_path_off = ctx->d_slot_path_off.p;
+  p.slot_path_len = ctx->d_slot_path_len.p;
+  return p;
+}
+
+static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
+  AStarArena& a = ctx->arena;
+  a.n_states = ctx->nav.n_edges + ctx->nav.n_links + 2;
+  a.node_cap = node_cap;
+  a.heap_cap = heap_cap;
+  size_t best_bytes = ((size_t)a.n_states * 4 + 255) & ~(size_t)255;
+  size_t node_bytes = ((size_t)node_cap * 16 + 255) & ~(size_t)255;
+  size_t heap_bytes = (((size_t)heap_cap + 2) * 16 + 255) & ~(size_t)255;
+  a.nodes_offset = best_bytes;
+  a.heap_offset = best_bytes + node_bytes;
+  a.slot_stride = best_bytes + node_bytes + heap_bytes;
+  a.n_slots = slots;
+  CUDA_TRY(ctx, ctx->d_arena.reserve(a.slot_stride * (size_t)slots));
+  a.base = ctx->d_arena.p;
+  launch_arena_init(a, ctx->stream);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return LMB_OK;
+}
+
+int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!d || d->struct_size != sizeof(lmb_navdata_desc))
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_navdata_upload: bad descriptor (struct_size)");
+  if (d->n_possible_links != 0)
+    return ctx->fail(LMB_ERR_UNSUPPORTED,
+                     "animation links (PossibleRegionLink) are not supported on the device path yet");
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  cudaStreamSynchronize(s);
+  DevNav& nav = ctx->nav;
+  nav = DevNav{};
+  nav.n_islands = d->n_islands;
+  nav.n_polys = d->n_polys;
+  nav.n_edges = d->n_edges;
+  nav.n_vertices = d->n_vertices;
+  nav.n_links = d->n_links;
+
+  // ---- dense type ids ----
+  std::map<uint32_t, uint32_t> type_dense;
+  for (uint32_t p = 0; p < d->n_polys; p++) type_dense[d->poly_type[p]] = 0;
+  for (uint32_t l = 0; l < d->n_links; l++) type_dense[d->link_dst_type[l]] = 0;
+  for (uint32_t t = 0; t < d->n_type_costs; t++) type_dense[d->type_cost_index[t]] = 0;
+  if (type_dense.empty()) type_dense[0] = 0;
+  if (type_dense.size() > LMB_MAX_TYPES)
+    return ctx->fail(LMB_ERR_UNSUPPORTED, "more than %u distinct node types", LMB_MAX_TYPES);
+  std::vector<uint32_t> type_raw;
+  for (auto& kv : type_dense) {
+    kv.second = (uint32_t)type_raw.size();
+    type_raw.push_back(kv.first);
+  }
+  nav.n_types = (uint32_t)type_raw.size();
+  std::vector<float> type_cost(nav.n_types, 1.0f);
+  std::vector<uint8_t> type_registered(nav.n_types, 0);
+  for (uint32_t t = 0; t < d->n_type_costs; t++) {
+    uint32_t k = type_dense[d->type_cost_index[t]];
+    type_cost[k] = d->type_cost_value[t];
+    type_registered[k] = 1;
+  }
+
+  // ---- islands, world vertices, sampling grids ----
+  std::vector<DevIsland> islands(d->n_islands);
+  std::vector<uint32_t> poly_island(d->n_polys), poly_type_dense(d->n_polys);
+  std::vector<float> verts_world((size_t)d->n_vertices * 3);
+  std::vector<uint32_t> cell_start, cell_polys;
+  bool any = false;
+  for (uint32_t i = 0; i < d->n_islands; i++) {
+    DevIsland& is = islands[i];
+    is.tx = d->island_translation[3 * i];
+    is.ty = d->island_translation[3 * i + 1];
+    is.tz = d->island_translation[3 * i + 2];
+    float rot = d->island_rotation[i];
+    volatile float hf = rot * 0.5f;
+    volatile float hi = (-rot) * 0.5f;
+    is.fs = sinf(hf);
+    is.fc = cosf(hf);
+    is.is = sinf(hi);
+    is.ic = cosf(hi);
+    for (int k = 0; k < 3; k++) {
+      is.bmin[k] = d->island_bounds[6 * i + k];
+      is.bmax[k] = d->island_bounds[6 * i + 3 + k];
+    }
+    is.bounds_empty = !(is.bmin[0] <= is.bmax[0]);
+    is.poly_begin = d->island_poly_begin[i];
+    is.poly_end = d->island_poly_begin[i + 1];
+    is.vert_begin = d->island_vert_begin[i];
+    is.vert_end = d->island_vert_begin[i + 1];
+    is.has_height = d->island_has_height ? d->island_has_height[i] : 0;
+    for (uint32_t p = is.poly_begin; p < is.poly_end; p++) poly_island[p] = i;
+    for (uint32_t v = is.vert_begin; v < is.vert_end; v++) {
+      H3 w = h_apply(is, {d->vertices[3 * (size_t)v], d->vertices[3 * (size_t)v + 1], d->vertices[3 * (size_t)v + 2]});
+      verts_world[3 * (size_t)v] = w.x;
+      verts_world[3 * (size_t)v + 1] = w.y;
+      verts_world[3 * (size_t)v + 2] = w.z;
+      if (!any) {
+        ctx->world_min[0] = ctx->world_max[0] = w.x;
+        ctx->world_min[1] = ctx->world_max[1] = w.y;
+        any = true;
+      } else {
+        ctx->world_min[0] = std::min(ctx->world_min[0], w.x);
+        ctx->world_max[0] = std::max(ctx->world_max[0], w.x);
+        ctx->world_min[1] = std::min(ctx->world_min[1], w.y);
+        ctx->world_max[1] = std::max(ctx->world_max[1], w.y);
+      }
+    }
+    // grid over polygon AABBs: ~1 polygon per cell, capped
+    uint32_t np = is.poly_end - is.poly_begin;
+    float ex = is.bounds_empty ? 1.0f : std::max(is.bmax[0] - is.bmin[0], 1e-3f);
+    float ey = is.bounds_empty ? 1.0f : std::max(is.bmax[1] - is.bmin[1], 1e-3f);
+    double target_cells = std::min<double>(std::max<double>(np, 1.0), 4.0e6);
+    float cell = (float)std::sqrt((double)ex * ey / target_cells);
+    if (!(cell > 0.0f) || !std::isfinite(cell)) cell = 1.0f;
+    is.gx0 = is.bounds_empty ? 0.0f : is.bmin[0];
+    is.gy0 = is.bounds_empty ? 0.0f : is.bmin[1];
+    is.ginv = 1.0f / cell;
+    is.gnx = (uint32_t)std::min<double>(std::max<double>(std::ceil(ex / cell), 1.0), 4096.0);
+    is.gny = (uint32_t)std::min<double>(std::max<double>(std::ceil(ey / cell), 1.0), 4096.0);
+    is.cell_begin = (uint32_t)cell_start.size();
+    size_t ncell = (size_t)is.gnx * is.gny;
+    std::vector<uint32_t> counts(ncell + 1, 0);
+    auto range = [&](uint32_t p, int32_t& x0, int32_t& x1, int32_t& y0, int32_t& y1) {
+      const float* b = d->poly_bounds + 6 * (size_t)p;
+      x0 = grid_cell(b[0], is.gx0, is.ginv, is.gnx);
+      x1 = grid_cell(b[3], is.gx0, is.ginv, is.gnx);
+      y0 = grid_cell(b[1], is.gy0, is.ginv, is.gny);
+      y1 = grid_cell(b[4], is.gy0, is.ginv, is.gny);
+    };
+    for (uint32_t p = is.poly_begin; p < is.poly_end; p++) {
+      const float* b = d->poly_bounds + 6 * (size_t)p;
+      if (!(b[0] <= b[3])) continue;
+      int32_t x0, x1, y0, y1;
+      range(p, x0, x1, y0, y1);
+      for (int32_t y = y0; y <= y1; y++)
+        for (int32_t x = x0; x <= x1; x++) counts[(size_t)y * is.gnx + x + 1]++;
+    }
+    for (size_t c = 0; c < ncell; c++) counts[c + 1] += counts[c];
+    size_t base = cell_polys.size();
+    cell_polys.resize(base + counts[ncell]);
+    std::vector<uint32_t> cursor(counts.begin(), counts.end() - 1);
+    for (uint32_t p = is.poly_begin; p < is.poly_end; p++) {  // ascending polygon order per cell
+      const float* b = d->poly_bounds + 6 * (size_t)p;
+      if (!(b[0] <= b[3])) continue;
+      int32_t x0, x1, y0, y1;
+      range(p, x0, x1, y0, y1);
+      for (int32_t y = y0; y <= y1; y++)
+        for (int32_t x = x0; x <= x1; x++) cell_polys[base + cursor[(size_t)y * is.gnx + x]++] = p;
+    }
+    for (size_t c = 0; c <= ncell; c++) cell_start.push_back((uint32_t)(base + counts[c]));
+  }
+  for (uint32_t p = 0; p < d->n_polys; p++) poly_type_dense[p] = type_dense[d->poly_type[p]];
+
+  // ---- node -> links CSR (may be absent) ----
+  std::vector<uint32_t> node_link_begin(d->n_polys + 1, 0), node_links;
+  if (d->node_link_begin && d->n_links) {
+    node_link_begin.assign(d->node_link_begin, d->node_link_begin + d->n_polys + 1);
+    node_links.assign(d->node_links, d->node_links + d->n_links);
+  }
+
+  // ---- edge records ----
+  std::vector<EdgeRec> edges(d->n_edges);
+  for (uint32_t p = 0; p < d->n_polys; p++) {
+    uint32_t eb = d->poly_edge_begin[p], ne = d->poly_edge_begin[p + 1] - eb;
+    if (ne > 255) return ctx->fail(LMB_ERR_UNSUPPORTED, "polygon %u has more than 255 edges", p);
+    const DevIsland& is = islands[poly_island[p]];
+    bool has_links = node_link_begin[p + 1] > node_link_begin[p];
+    for (uint32_t e = 0; e < ne; e++) {
+      EdgeRec& r = edges[eb + e];
+      uint32_t vi = d->edge_vertex[eb + (e == ne - 1 ? 0 : e + 1)];  // left  = vertex[e+1]
+      uint32_t vj = d->edge_vertex[eb + e];                           // right = vertex[e]
+      const float* a = d->vertices + 3 * (size_t)vi;
+      const float* b = d->vertices + 3 * (size_t)vj;
+      volatile float mx = (a[0] + b[0]) * 0.5f, my = (a[1] + b[1]) * 0.5f, mz = (a[2] + b[2]) * 0.5f;
+      H3 w = h_apply(is, {mx, my, mz});
+      r.mx = w.x;
+      r.my = w.y;
+      r.mz = w.z;
+      uint32_t nb = d->edge_neighbor[eb + e];
+      r.nbr_poly = nb;
+      r.twin = nb == LMB_NONE ? LMB_NONE : d->poly_edge_begin[nb] + d->edge_reverse[eb + e];
+      r.poly = p;
+      r.first_edge = eb;
+      uint32_t nbt = nb == LMB_NONE ? 0u : poly_type_dense[nb];
+      r.info = ne | (poly_type_dense[p] << 8) | (nbt << 16) | (has_links ? (1u << 24) : 0u);
+    }
+  }
+
+  std::vector<uint32_t> link_dst_type_dense(d->n_links);
+  for (uint32_t l = 0; l < d->n_links; l++) link_dst_type_dense[l] = type_dense[d->link_dst_type[l]];
+  std::vector<uint32_t> node_modified(d->n_polys, LMB_NONE);
+  for (uint32_t m = 0; m < d->n_modified; m++) node_modified[d->modified_node[m]] = m;
+  std::vector<uint32_t> node_region_number(d->n_polys, LMB_NONE);
+  if (d->node_region_number) node_region_number.assign(d->node_region_number, d->node_region_number + d->n_polys);
+
+#define UP(buf, ptr, n) CUDA_TRY(ctx, ctx->buf.upload(ptr, n, s))
+#define UPV(buf, vec) CUDA_TRY(ctx, ctx->buf.upload(vec, s))
+  UPV(d_islands, islands);
+  UP(d_verts_local, d->vertices, (size_t)d->n_vertices * 3);
+  UPV(d_verts_world, verts_world);
+  UP(d_poly_edge_begin, d->poly_edge_begin, (size_t)d->n_polys + 1);
+  UP(d_edge_vertex, d->edge_vertex, d->n_edges);
+  UP(d_edge_neighbor, d->edge_neighbor, d->n_edges);
+  UP(d_edge_reverse, d->edge_reverse, d->n_edges);
+  UP(d_poly_bounds, d->poly_bounds, (size_t)d->n_polys * 6);
+  UPV(d_poly_island, poly_island);
+  UP(d_poly_region, d->poly_region, d->n_polys);
+  UPV(d_poly_type_dense, poly_type_dense);
+  if (d->hpoly) {
+    UP(d_hpoly, d->hpoly, (size_t)d->n_polys * 4);
+    UP(d_hverts, d->hverts, (size_t)d->n_hverts * 3);
+    UP(d_htris, d->htris, (size_t)d->n_htris * 3);
+  }
+  UPV(d_cell_start, cell_start);
+  UPV(d_cell_polys, cell_polys);
+  UPV(d_edges, edges);
+  UPV(d_type_cost, type_cost);
+  UPV(d_type_registered, type_registered);
+  UPV(d_type_raw, type_raw);
+  UP(d_link_dst_node, d->link_dst_node, d->n_links);
+  UPV(d_link_dst_type_dense, link_dst_type_dense);
+  UP(d_link_portal, d->link_portal, (size_t)d->n_links * 6);
+  UP(d_link_kind, d->link_kind, d->n_links);
+  UP(d_link_reverse, d->link_reverse, d->n_links);
+  UP(d_link_dst_portal, d->link_dst_portal ? d->link_dst_portal : d->link_portal, (size_t)d->n_links * 6);
+  UP(d_link_cost, d->link_cost, d->n_links);
+  UP(d_link_anim_kind, d->link_anim_kind, d->n_links);
+  UP(d_link_anim_id, d->link_anim_id, d->n_links);
+  UPV(d_node_link_begin, node_link_begin);
+  UPV(d_node_links, node_links);
+  UPV(d_node_modified, node_modified);
+  UP(d_modified_edge_begin, d->modified_edge_begin, d->n_modified ? (size_t)d->n_modified + 1 : 0);
+  UP(d_modified_edges, d->modified_edges, d->n_modified ? 2 * (size_t)d->modified_edge_begin[d->n_modified] : 0);
+  UP(d_modified_vert_begin, d->modified_vert_begin, d->n_modified ? (size_t)d->n_modified + 1 : 0);
+  UP(d_modified_verts, d->modified_verts, d->n_modified ? 2 * (size_t)d->modified_vert_begin[d->n_modified] : 0);
+  UPV(d_node_region_number, node_region_number);
+  UP(d_region_root, d->region_root, d->n_region_numbers);
+#undef UP
+#undef UPV
+  nav.islands = ctx->d_islands.p;
+  nav.verts_local = ctx->d_verts_local.p;
+  nav.verts_world = ctx->d_verts_world.p;
+  nav.poly_edge_begin = ctx->d_poly_edge_begin.p;
+  nav.edge_vertex = ctx->d_edge_vertex.p;
+  nav.edge_neighbor = ctx->d_edge_neighbor.p;
+  nav.edge_reverse = ctx->d_edge_reverse.p;
+  nav.poly_bounds = ctx->d_poly_bounds.p;
+  nav.poly_island = ctx->d_poly_island.p;
+  nav.poly_region = ctx->d_poly_region.p;
+  nav.poly_type_dense = ctx->d_poly_type_dense.p;
+  nav.hpoly = ctx->d_hpoly.p;
+  nav.hverts = ctx->d_hverts.p;
+  nav.htris = ctx->d_htris.p;
+  nav.cell_start = ctx->d_cell_start.p;
+  nav.cell_polys = ctx->d_cell_polys.p;
+  nav.edges = ctx->d_edges.p;
+  nav.type_cost = ctx->d_type_cost.p;
+  nav.type_registered = ctx->d_type_registered.p;
+  nav.link_dst_node = ctx->d_link_dst_node.p;
+  nav.link_dst_type_dense = ctx->d_link_dst_type_dense.p;
+  nav.link_portal = ctx->d_link_portal.p;
+  nav.link_kind = ctx->d_link_kind.p;
+  nav.link_reverse = ctx->d_link_reverse.p;
+  nav.link_dst_portal = ctx->d_link_dst_portal.p;
+  nav.link_cost = ctx->d_link_cost.p;
+  nav.link_anim_kind = ctx->d_link_anim_kind.p;
+  nav.link_anim_id = ctx->d_link_anim_id.p;
+  nav.node_link_begin = ctx->d_node_link_begin.p;
+  nav.node_links = ctx->d_node_links.p;
+  nav.node_modified = ctx->d_node_modified.p;
+  nav.modified_edge_begin = ctx->d_modified_edge_begin.p;
+  nav.modified_edges = ctx->d_modified_edges.p;
+  nav.modified_vert_begin = ctx->d_modified_vert_begin.p;
+  nav.modified_verts = ctx->d_modified_verts.p;
+  nav.node_region_number = ctx->d_node_region_number.p;
+  nav.region_root = ctx->d_region_root.p;
+  nav.n_possible_links = 0;
+
+  // ---- A* arenas ----
+  uint32_t n_states = nav.n_edges + nav.n_links + 2;
+  uint32_t slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 16;
+  uint32_t node_cap = std::max<uint32_t>(n_states + 64, 256);
+  uint32_t heap_cap = std::max<uint32_t>(n_states / 4 + 64, 256);
+  size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)48 << 30);
+  size_t per_slot = (size_t)n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;
+  if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 32);
+  int32_t st = setup_arena(ctx, node_cap, heap_cap, slots);
+  if (st != LMB_OK) return st;
+
+  // ---- path pool: drop all paths ----
+  if (ctx->pool_capacity == 0) {
+    ctx->pool_capacity = std::max<unsigned long long>((unsigned long long)ctx->cfg.max_agents * 64ull, 1ull << 16);
+    CUDA_TRY(ctx, ctx->d_pool[0].reserve(ctx->pool_capacity));
+    ctx->pool_capacity = ctx->d_pool[0].cap;
+    ctx->pool_cur = 0;
+  }
+  launch_drop_all_paths(make_pool(ctx), ctx->cfg.max_agents, s);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  ctx->has_nav = true;
+  return LMB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// A* driver shared by lmb_step and lmb_find_paths
+// ---------------------------------------------------------------------------
+static int32_t grow_pool(lmb_ctx* ctx, unsigned long long min_capacity) {
+  cudaStream_t s = ctx->stream;
+  int other = 1 - ctx->pool_cur;
+  unsigned long long want = std::max(min_capacity, ctx->pool_capacity * 2);
+  CUDA_TRY(ctx, ctx->d_pool[other].reserve(want));
+  PathPool src = make_pool(ctx);
+  launch_pool_compact(src, ctx->d_pool[other].p, ctx->cfg.max_agents, ctx->d_scan_tmp.p, s);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  ctx->d_pool[ctx->pool_cur].release();
+  ctx->pool_cur = other;
+  ctx->pool_capacity = ctx->d_pool[other].cap;
+  return LMB_OK;
+}
+
+static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
+  cudaStream_t s = ctx->stream;
+  uint32_t n = q.n;
+  CUDA_TRY(ctx, cudaMemsetAsync(q.out_status, 0, n * sizeof(uint32_t), s));
+  const uint32_t* list = nullptr;
+  uint32_t n_run = n;
+  std::vector<uint32_t> h_status;
+  for (int iter = 0; iter < 24; iter++) {
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(AStarCounters), s));
+    AStarQueries qq = q;
+    qq.n = n_run;
+    qq.list = list;
+    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, s);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
+                                  cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    ctx->timings.explored_nodes += ctx->h_counters->explored_total;
+    ctx->timings.path_nodes += ctx->h_counters->path_nodes_total;
+    ctx->timings.kernel_launches += 1;
+    uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
+    if (ra == 0 && rp == 0) return LMB_OK;
+    // overflow: collect the retry list, grow what overflowed, run again
+    h_status.resize(n);
+    CUDA_TRY(ctx, cudaMemcpy(h_status.data(), q.out_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> retry;
+    for (uint32_t i = 0; i < n; i++)
+      if (h_status[i] == 2 || h_status[i] == 3) retry.push_back(i);
+    if (rp) {
+      int32_t st = grow_pool(ctx, ctx->pool_capacity * 2);
+      if (st != LMB_OK) return st;
+    }
+    if (ra) {
+      AStarArena& a = ctx->arena;
+      uint32_t node_cap = a.node_cap * 2, heap_cap = a.heap_cap * 2;
+      size_t per_slot = (size_t)a.n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;
+      size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)48 << 30);
+      uint32_t slots = a.n_slots;
+      if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 8);
+      int32_t st = setup_arena(ctx, node_cap, heap_cap, slots);
+      if (st != LMB_OK) return st;
+    }
+    CUDA_TRY(ctx, ctx->d_retry_list.upload(retry, s));
+    list = ctx->d_retry_list.p;
+    n_run = (uint32_t)retry.size();
+  }
+  return ctx->fail(LMB_ERR_CAPACITY, "A* scratch kept overflowing");
+}
+
+// ---------------------------------------------------------------------------
+// batched queries
+// ---------------------------------------------------------------------------
+int32_t lmb_sample_points(lmb_ctx* ctx, uint32_t n, const float* points, const lmb_options* options,
+                          float* out_points, uint32_t* out_nodes) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
+  if (!options || (n && (!points || !out_points || !out_nodes)))
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_sample_points: null argument");
+  if (n == 0) return LMB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(ctx, ctx->d_position.upload(points, 3 * (size_t)n, s));
+  CUDA_TRY(ctx, ctx->d_agent_point.reserve(3 * (size_t)n));
+  CUDA_TRY(ctx, ctx->d_agent_node.reserve(n));
+  launch_sample_points(ctx->nav, *options, n, ctx->d_position.p, nullptr, 0, 0, ctx->d_agent_point.p,
+                       ctx->d_agent_node.p, s);
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_points, ctx->d_agent_point.p, 3 * (size_t)n * sizeof(float),
+                                cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_nodes, ctx->d_agent_node.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return LMB_OK;
+}
+
+static int32_t reserve_queries(lmb_ctx* ctx, uint32_t n) {
+  size_t m = n ? n : 1;
+  CUDA_TRY(ctx, ctx->d_q_agent.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_slot.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_start_node.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_end_node.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_start_point.reserve(3 * m));
+  CUDA_TRY(ctx, ctx->d_q_end_point.reserve(3 * m));
+  CUDA_TRY(ctx, ctx->d_q_status.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_success.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_explored.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_path_off.reserve(m));
+  CUDA_TRY(ctx, ctx->d_q_path_len.reserve(m));
+  return LMB_OK;
+}
+
+static AStarQueries make_queries(lmb_ctx* ctx, uint32_t n) {
+  AStarQueries q{};
+  q.n = n;
+  q.start_node = ctx->d_q_start_node.p;
+  q.end_node = ctx->d_q_end_node.p;
+  q.start_point = ctx->d_q_start_point.p;
+  q.end_point = ctx->d_q_end_point.p;
+  q.out_status = ctx->d_q_status.p;
+  q.out_success = ctx->d_q_success.p;
+  q.out_explored = ctx->d_q_explored.p;
+  q.out_path_off = ctx->d_q_path_off.p;
+  q.out_path_len = ctx->d_q_path_len.p;
+  return q;
+}
+
+int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, const float* start_point,
+                       const uint32_t* end_node, const float* end_point,
+                       const uint32_t* override_begin, const uint32_t* override_type,
+                       const float* override_cost, uint32_t* out_success, uint32_t* out_explored,
+                       uint32_t* out_path_begin, uint32_t* out_nodes, uint32_t* out_portals,
+                       uint32_t path_capacity) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
+  if (!out_path_begin) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_paths: null argument");
+  out_path_begin[0] = 0;
+  if (n == 0) return LMB_OK;
+  if (!start_node || !start_point || !end_node || !end_point || !out_success || !out_explored)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_paths: null argument");
+  for (uint32_t i = 0; i < n; i++)
+    if (start_node[i] >= ctx->nav.n_polys || end_node[i] >= ctx->nav.n_polys)
+      return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_paths: node id out of range (query %u)", i);
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  int32_t st = reserve_queries(ctx, n);
+  if (st != LMB_OK) return st;
+  CUDA_TRY(ctx, ctx->d_q_start_node.upload(start_node, n, s));
+  CUDA_TRY(ctx, ctx->d_q_end_node.upload(end_node, n, s));
+  CUDA_TRY(ctx, ctx->d_q_start_point.upload(start_point, 3 * (size_t)n, s));
+  CUDA_TRY(ctx, ctx->d_q_end_point.upload(end_point, 3 * (size_t)n, s));
+  AStarQueries q = make_queries(ctx, n);
+  if (override_begin) {
+    CUDA_TRY(ctx, ctx->d_override_begin.upload(override_begin, (size_t)n + 1, s));
+    CUDA_TRY(ctx, ctx->d_override_type.upload(override_type, override_begin[n], s));
+    CUDA_TRY(ctx, ctx->d_override_cost.upload(override_cost, override_begin[n], s));
+    q.override_begin = ctx->d_override_begin.p;
+    q.override_type = ctx->d_override_type.p;
+    q.override_cost = ctx->d_override_cost.p;
+  }
+  // Paths of batch queries live in the pool only until they are copied out: remember the
+  // cursor and rewind afterwards (agent paths are never touched).
+  unsigned long long cursor0 = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&cursor0, ctx->d_pool_cursor.p, sizeof(cursor0), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  ctx->timings = lmb_step_timings{};
+  st = run_astar(ctx, q);
+  if (st != LMB_OK) return st;
+  std::vector<uint32_t> off(n), len(n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_success, q.out_success, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_explored, q.out_explored, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(off.data(), q.out_path_off, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(len.data(), q.out_path_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    out_path_begin[i] = (uint32_t)total;
+    total += out_success[i] ? len[i] : 0;
+  }
+  out_path_begin[n] = (uint32_t)total;
+  int32_t result = LMB_OK;
+  if (total > path_capacity) {
+    result = ctx->fail(LMB_ERR_CAPACITY, "lmb_find_paths: %llu path entries do not fit capacity %u",
+                       (unsigned long long)total, path_capacity);
+  } else if (total) {
+    if (!out_nodes || !out_portals) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_paths: null outputs");
+    std::vector<uint2> tmp;
+    const uint2* pool = ctx->d_pool[ctx->pool_cur].p;
+    for (uint32_t i = 0; i < n; i++) {
+      if (!out_success[i] || !len[i]) continue;
+      tmp.resize(len[i]);
+      CUDA_TRY(ctx, cudaMemcpy(tmp.data(), pool + off[i], len[i] * sizeof(uint2), cudaMemcpyDeviceToHost));
+      for (uint32_t k = 0; k < len[i]; k++) {
+        out_nodes[out_path_begin[i] + k] = tmp[k].x;
+        out_portals[out_path_begin[i] + k] = tmp[k].y;
+      }
+    }
+  }
+  // rewind the bump pointer only if no agent path was appended meanwhile (single-threaded use)
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pool_cursor.p, &cursor0, sizeof(cursor0), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return result;
+}
+
+// ---------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------
+int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* a, const lmb_characters_in* c) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!a) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_upload: null agents");
+  const uint32_t n = a->n;
+  if (n > ctx->cfg.max_agents)
+    return ctx->fail(LMB_ERR_CAPACITY, "%u agents exceed max_agents %u", n, ctx->cfg.max_agents);
+  if (n && (!a->slot || !a->flags || !a->position || !a->velocity || !a->radius || !a->desired_speed ||
+            !a->max_speed))
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_upload: null required array");
+  for (uint32_t i = 0; i < n; i++)
+    if (a->slot[i] >= ctx->cfg.max_agents)
+      return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "agent %u: slot %u >= max_agents %u", i, a->slot[i],
+                       ctx->cfg.max_agents);
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  cudaEventRecord(ctx->ev[0], s);
+  ctx->n_agents = n;
+  CUDA_TRY(ctx, ctx->d_slot.upload(a->slot, n, s));
+  CUDA_TRY(ctx, ctx->d_flags.upload(a->flags, n, s));
+  CUDA_TRY(ctx, ctx->d_position.upload(a->position, 3 * (size_t)n, s));
+  CUDA_TRY(ctx, ctx->d_velocity.upload(a->velocity, 3 * (size_t)n, s));
+  if (a->target) {
+    CUDA_TRY(ctx, ctx->d_target.upload(a->target, 3 * (size_t)n, s));
+  } else {
+    CUDA_TRY(ctx, ctx->d_target.reserve(3 * (size_t)n + 1));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_target.p, 0, 3 * (size_t)n * sizeof(float), s));
+  }
+  CUDA_TRY(ctx, ctx->d_radius.upload(a->radius, n, s));
+  CUDA_TRY(ctx, ctx->d_desired_speed.upload(a->desired_speed, n, s));
+  CUDA_TRY(ctx, ctx->d_max_speed.upload(a->max_speed, n, s));
+  ctx->has_reach_condition = a->reach_condition != nullptr;
+  if (a->reach_condition) CUDA_TRY(ctx, ctx->d_reach_condition.upload(a->reach_condition, n, s));
+  ctx->has_reach_distance = a->reach_distance != nullptr;
+  if (a->reach_distance) CUDA_TRY(ctx, ctx->d_reach_distance.upload(a->reach_distance, n, s));
+  ctx->has_anim_reach = a->anim_link_reach_distance != nullptr;
+  if (a->anim_link_reach_distance) CUDA_TRY(ctx, ctx->d_anim_reach.upload(a->anim_link_reach_distance, n, s));
+  ctx->has_overrides = a->override_begin != nullptr && n > 0 && a->override_begin[n] > 0;
+  if (ctx->has_overrides) {
+    CUDA_TRY(ctx, ctx->d_override_begin.upload(a->override_begin, (size_t)n + 1, s));
+    CUDA_TRY(ctx, ctx->d_override_type.upload(a->override_type, a->override_begin[n], s));
+    CUDA_TRY(ctx, ctx->d_override_cost.upload(a->override_cost, a->override_begin[n], s));
+  }
+  ctx->has_permitted = a->permitted_begin != nullptr && n > 0;
+  if (ctx->has_permitted) {
+    CUDA_TRY(ctx, ctx->d_permitted_begin.upload(a->permitted_begin, (size_t)n + 1, s));
+    CUDA_TRY(ctx, ctx->d_permitted_kind.upload(a->permitted_kind, a->permitted_begin[n], s));
+  }
+  ctx->n_chars = c ? c->n : 0;
+  if (ctx->n_chars) {
+    CUDA_TRY(ctx, ctx->d_char_position.upload(c->position, 3 * (size_t)c->n, s));
+    CUDA_TRY(ctx, ctx->d_char_velocity.upload(c->velocity, 3 * (size_t)c->n, s));
+    CUDA_TRY(ctx, ctx->d_char_radius.upload(c->radius, c->n, s));
+  }
+  cudaEventRecord(ctx->ev[1], s);
+  return LMB_OK;
+}
+
+static AgentArrays make_agent_arrays(lmb_ctx* ctx) {
+  AgentArrays ag{};
+  ag.n = ctx->n_agents;
+  ag.slot = ctx->d_slot.p;
+  ag.flags = ctx->d_flags.p;
+  ag.position = ctx->d_position.p;
+  ag.velocity = ctx->d_velocity.p;
+  ag.target = ctx->d_target.p;
+  ag.radius = ctx->d_radius.p;
+  ag.desired_speed = ctx->d_desired_speed.p;
+  ag.max_speed = ctx->d_max_speed.p;
+  ag.reach_condition = ctx->has_reach_condition ? ctx->d_reach_condition.p : nullptr;
+  ag.reach_distance = ctx->has_reach_distance ? ctx->d_reach_distance.p : nullptr;
+  ag.anim_link_reach_distance = ctx->has_anim_reach ? ctx->d_anim_reach.p : nullptr;
+  ag.agent_point = ctx->d_agent_point.p;
+  ag.agent_node = ctx->d_agent_node.p;
+  ag.target_point = ctx->d_target_point.p;
+  ag.target_node = ctx->d_target_node.p;
+  return ag;
+}
+
+static AgentPersist make_persist(lmb_ctx* ctx) {
+  AgentPersist p{};
+  p.desired_move = ctx->d_desired_move.p;
+  p.state = ctx->d_state.p;
+  p.reached_link_id = ctx->d_reached_link_id.p;
+  p.reached_link_start = ctx->d_reached_start.p;
+  p.reached_link_end = ctx->d_reached_end.p;
+  return p;
+}
+
+int32_t lmb_avoidance_phase(lmb_ctx* ctx, const lmb_options* o, float dt);  // lmb_avoid_host.cu
+
+int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
+  if (!o) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step: null options");
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = ctx->n_agents;
+  lmb_step_timings& T = ctx->timings;
+  float h2d = 0.0f;
+  if (cudaEventQuery(ctx->ev[1]) != cudaErrorInvalidResourceHandle) {
+    cudaEventSynchronize(ctx->ev[1]);
+    if (cudaEventElapsedTime(&h2d, ctx->ev[0], ctx->ev[1]) != cudaSuccess) h2d = 0.0f;
+    cudaGetLastError();
+  }
+  T = lmb_step_timings{};
+  T.h2d_ms = h2d;
+  size_t m = n ? n : 1;
+  CUDA_TRY(ctx, ctx->d_agent_point.reserve(3 * m));
+  CUDA_TRY(ctx, ctx->d_agent_node.reserve(m));
+  CUDA_TRY(ctx, ctx->d_target_point.reserve(3 * m));
+  CUDA_TRY(ctx, ctx->d_target_node.reserve(m));
+  CUDA_TRY(ctx, ctx->d_follow_start.reserve(m));
+  CUDA_TRY(ctx, ctx->d_follow_end.reserve(m));
+  CUDA_TRY(ctx, ctx->d_presult.reserve(m));
+  CUDA_TRY(ctx, ctx->d_query_of_agent.reserve(m));
+  CUDA_TRY(ctx, ctx->d_out_velocity.reserve(3 * m));
+  CUDA_TRY(ctx, ctx->d_out_state.reserve(m));
+  CUDA_TRY(ctx, ctx->d_out_link_id.reserve(m));
+  CUDA_TRY(ctx, ctx->d_out_link_start.reserve(3 * m));
+  CUDA_TRY(ctx, ctx->d_out_link_end.reserve(3 * m));
+  int32_t st = reserve_queries(ctx, n);
+  if (st != LMB_OK) return st;
+  if (ctx->n_chars) {
+    CUDA_TRY(ctx, ctx->d_char_point.reserve(3 * (size_t)ctx->n_chars));
+    CUDA_TRY(ctx, ctx->d_char_node.reserve(ctx->n_chars));
+  }
+  AgentArrays ag = make_agent_arrays(ctx);
+  AgentPersist persist = make_persist(ctx);
+
+  // keep the pool at most half full before the frame
+  {
+    unsigned long long cursor = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (cursor * 2 > ctx->pool_capacity) {
+      st = grow_pool(ctx, ctx->pool_capacity);  // compacts; capacity at least doubles
+      if (st != LMB_OK) return st;
+    }
+  }
+
+  cudaEventRecord(ctx->ev[2], s);
+  // phase A: sample agents (skipped when paused / using a link), targets, characters
+  launch_reset_slots(ag, persist, make_pool(ctx), s);
+  launch_sample_points(ctx->nav, *o, n, ag.position, ag.flags, LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK,
+                       0, ctx->d_agent_point.p, ctx->d_agent_node.p, s);
+  launch_sample_points(ctx->nav, *o, n, ag.target, ag.flags, LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK,
+                       LMB_AGENT_HAS_TARGET, ctx->d_target_point.p, ctx->d_target_node.p, s);
+  launch_sample_points(ctx->nav, *o, ctx->n_chars, ctx->d_char_position.p, nullptr, 0, 0, ctx->d_char_point.p,
+                       ctx->d_char_node.p, s);
+  T.kernel_launches += (n ? 3 : 0) + (ctx->n_chars ? 1 : 0);
+  cudaEventRecord(ctx->ev[3], s);
+
+  // phase B: decision
+  RepathQueue queue{};
+  queue.count = ctx->d_queue_count.p;
+  queue.agent = ctx->d_q_agent.p;
+  queue.slot = ctx->d_q_slot.p;
+  queue.start_node = ctx->d_q_start_node.p;
+  queue.end_node = ctx->d_q_end_node.p;
+  queue.start_point = ctx->d_q_start_point.p;
+  queue.end_point = ctx->d_q_end_point.p;
+  FollowScratch scratch{};
+  scratch.follow_start = ctx->d_follow_start.p;
+  scratch.follow_end = ctx->d_follow_end.p;
+  scratch.presult = ctx->d_presult.p;
+  scratch.query_of_agent = ctx->d_query_of_agent.p;
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue_count.p, 0, sizeof(uint32_t), s));
+  launch_repath_decide(ctx->nav, ag, persist, make_pool(ctx), queue, scratch, s);
+  T.kernel_launches += n ? 1 : 0;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small, ctx->d_queue_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(ctx->ev[4], s);
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  const uint32_t n_repath = ctx->h_small[0];
+  T.n_repath = n_repath;
+
+  // phase B: A*
+  AStarQueries q = make_queries(ctx, n_repath);
+  q.owner = ctx->d_q_agent.p;
+  q.slot = ctx->d_q_slot.p;
+  if (ctx->has_overrides) {
+    q.override_begin = ctx->d_override_begin.p;
+    q.override_type = ctx->d_override_type.p;
+    q.override_cost = ctx->d_override_cost.p;
+  }
+  q.owner_flags = ctx->d_flags.p;
+  if (ctx->has_permitted) {
+    q.permitted_begin = ctx->d_permitted_begin.p;
+    q.permitted_kind = ctx->d_permitted_kind.p;
+  }
+  if (n_repath) {
+    st = run_astar(ctx, q);
+    if (st != LMB_OK) return st;
+  }
+  cudaEventRecord(ctx->ev[5], s);
+
+  // phase C
+  launch_follow(ctx->nav, ag, persist, make_pool(ctx), q, scratch, s);
+  T.kernel_launches += n ? 1 : 0;
+  CUDA_TRY(ctx, cudaGetLastError());
+  cudaEventRecord(ctx->ev[6], s);
+
+  // phase D
+  if (!(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE)) {
+    st = lmb_avoidance_phase(ctx, o, dt);
+    if (st != LMB_OK) return st;
+  }
+  cudaEventRecord(ctx->ev[7], s);
+
+  launch_gather_outputs(ag, persist, ctx->d_out_velocity.p, ctx->d_out_state.p, ctx->d_out_link_id.p,
+                        ctx->d_out_link_start.p, ctx->d_out_link_end.p, s);
+  T.kernel_launches += n ? 1 : 0;
+  CUDA_TRY(ctx, cudaGetLastError());
+  cudaEventRecord(ctx->ev[8], s);
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  cudaEventElapsedTime(&T.sample_ms, ctx->ev[2], ctx->ev[3]);
+  cudaEventElapsedTime(&T.repath_decide_ms, ctx->ev[3], ctx->ev[4]);
+  cudaEventElapsedTime(&T.astar_ms, ctx->ev[4], ctx->ev[5]);
+  cudaEventElapsedTime(&T.follow_ms, ctx->ev[5], ctx->ev[6]);
+  cudaEventElapsedTime(&T.avoidance_ms, ctx->ev[6], ctx->ev[7]);
+  cudaEventElapsedTime(&T.total_ms, ctx->ev[2], ctx->ev[8]);
+  ctx->last_n_results = n;
+  return LMB_OK;
+}
+
+int32_t lmb_agents_download(lmb_ctx* ctx, const lmb_agents_out* out) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!out) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_download: null out");
+  const uint32_t n = ctx->n_agents;
+  if (n == 0) return LMB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  cudaEventRecord(ctx->ev[0], s);
+  if (out->desired_velocity)
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->desired_velocity, ctx->d_out_velocity.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out->state)
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->state, ctx->d_out_state.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (out->reached_link_id)
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->reached_link_id, ctx->d_out_link_id.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (out->reached_link_start)
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->reached_link_start, ctx->d_out_link_start.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out->reached_link_end)
+    CUDA_TRY(ctx, cudaMemcpyAsync(out->reached_link_end, ctx->d_out_link_end.p, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  cudaEventRecord(ctx->ev[1], s);
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  cudaEventElapsedTime(&ctx->timings.d2h_ms, ctx->ev[0], ctx->ev[1]);
+  return LMB_OK;
+}
+
+int32_t lmb_step(lmb_ctx* ctx, const lmb_agents_in* agents, const lmb_characters_in* characters,
+                 const lmb_options* options, float delta_time, const lmb_agents_out* out) {
+  int32_t st = lmb_agents_upload(ctx, agents, characters);
+  if (st != LMB_OK) return st;
+  st = lmb_step_resident(ctx, options, delta_time);
+  if (st != LMB_OK) return st;
+  float h2d = ctx->timings.h2d_ms;
+  st = lmb_agents_download(ctx, out);
+  ctx->timings.h2d_ms = h2d;
+  return st;
+}
+
+int32_t lmb_pathing_results(lmb_ctx* ctx, lmb_pathing_result* out, uint32_t capacity, uint32_t* out_count) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!out_count) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_pathing_results: null out_count");
+  *out_count = ctx->timings.n_repath;
+  if (ctx->timings.n_repath > capacity) return LMB_ERR_CAPACITY;
+  if (ctx->timings.n_repath == 0) return LMB_OK;
+  if (!out) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_pathing_results: null out");
+  cudaSetDevice(ctx->device);
+  const uint32_t n = ctx->last_n_results;
+  std::vector<uint32_t> pr(n);
+  CUDA_TRY(ctx, cudaMemcpy(pr.data(), ctx->d_presult.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  uint32_t k = 0;
+  for (uint32_t i = 0; i < n && k < capacity; i++)
+    if (pr[i] & 0x80000000u) out[k++] = {i, (pr[i] >> 30) & 1u, pr[i] & 0x3fffffffu};
+  *out_count = k;
+  return LMB_OK;
+}
+
+int32_t lmb_agent_path(lmb_ctx* ctx, uint32_t slot, uint32_t* out_nodes, uint32_t* out_portals,
+                       uint32_t capacity, uint32_t* out_len) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!out_len || slot >= ctx->cfg.max_agents)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_path: bad slot / null out_len");
+  cudaSetDevice(ctx->device);
+  uint32_t off = 0, len = 0;
+  CUDA_TRY(ctx, cudaMemcpy(&len, ctx->d_slot_path_len.p + slot, 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(&off, ctx->d_slot_path_off.p + slot, 4, cudaMemcpyDeviceToHost));
+  *out_len = len;
+  if (!len) return LMB_OK;
+  if (len > capacity) return LMB_ERR_CAPACITY;
+  std::vector<uint2> tmp(len);
+  CUDA_TRY(ctx, cudaMemcpy(tmp.data(), ctx->d_pool[ctx->pool_cur].p + off, len * sizeof(uint2), cudaMemcpyDeviceToHost));
+  for (uint32_t k = 0; k < len; k++) {
+    out_nodes[k] = tmp[k].x;
+    out_portals[k] = tmp[k].y;
+  }
+  return LMB_OK;
+}
+
+int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out) {
+  if (!ctx || !out) return LMB_ERR_INVALID_ARGUMENT;
+  *out = ctx->timings;
+  return LMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// landmass_b200 — host-callable kernel launchers (one translation unit per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lmb_device.cuh"
+
+namespace lmb {
+
+// ---- kernel 1: sampling (k_sample.cu) ----
+void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, const float* points,
+                          const uint32_t* flags, uint32_t skip_if_any, uint32_t require_all,
+                          float* out_points, uint32_t* out_nodes, cudaStream_t stream);
+
+// ---- kernel 2: batched A* (k_astar.cu) ----
+struct AStarArena {
+  uint8_t* base;          // device memory for all slots
+  size_t slot_stride;     // bytes per slot
+  uint32_t n_slots;       // concurrent queries (= warps launched)
+  uint32_t n_states;      // n_edges + n_links + 2
+  uint32_t node_cap;      // nodes per slot
+  uint32_t heap_cap;      // heap entries per slot
+  size_t nodes_offset;    // byte offset of the node array inside a slot
+  size_t heap_offset;     // byte offset of the heap array inside a slot
+};
+
+struct AStarQueries {
+  uint32_t n;
+  const uint32_t* list;        // optional indirection: query ids to run (retry list) or NULL
+  const uint32_t* start_node;  // [n]
+  const uint32_t* end_node;    // [n]
+  const float* start_point;    // [n*3]
+  const float* end_point;      // [n*3]
+  const uint32_t* owner;       // [n] index into the override / permitted CSR arrays, or NULL (= query id)
+  const uint32_t* override_begin;  // CSR by owner, or NULL
+  const uint32_t* override_type;   // raw type index
+  const float* override_cost;
+  const uint32_t* owner_flags;     // agent flags by owner (PERMIT_ALL) or NULL (= all permitted)
+  const uint32_t* permitted_begin;
+  const uint32_t* permitted_kind;
+  const uint32_t* slot;        // [n] agent slot to receive the path, or NULL
+  // outputs
+  uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool overflow)
+  uint32_t* out_success;       // [n]
+  uint32_t* out_explored;      // [n]
+  uint32_t* out_path_off;      // [n] offset into the path pool
+  uint32_t* out_path_len;      // [n]
+};
+
+struct PathPool {
+  uint2* entries;                   // (node id, portal code)
+  unsigned long long* cursor;       // device bump pointer
+  unsigned long long capacity;      // entries
+  uint32_t* slot_path_off;          // [max_agents]
+  uint32_t* slot_path_len;          // [max_agents] 0 = no path
+};
+
+struct AStarCounters {  // device-resident
+  unsigned int queue_head;
+  unsigned int n_retry_arena;
+  unsigned int n_retry_pool;
+  unsigned int n_done;
+  unsigned long long explored_total;
+  unsigned long long path_nodes_total;
+};
+
+void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
+void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
+
+// ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----
+struct AgentArrays {
+  uint32_t n;
+  const uint32_t* slot;
+  const uint32_t* flags;
+  const float* position;
+  const float* velocity;
+  const float* target;
+  const float* radius;
+  const float* desired_speed;
+  const float* max_speed;
+  const uint32_t* reach_condition;
+  const float* reach_distance;
+  const float* anim_link_reach_distance;
+  // sampled (phase A outputs)
+  const float* agent_point;
+  const uint32_t* agent_node;
+  const float* target_point;
+  const uint32_t* target_node;
+};
+
+struct AgentPersist {  // indexed by slot
+  float* desired_move;       // [max_agents*3]
+  uint32_t* state;           // [max_agents]
+  uint32_t* reached_link_id;
+  float* reached_link_start;
+  float* reached_link_end;
+};
+
+struct RepathQueue {
+  uint32_t* count;       // device counter
+  uint32_t* agent;       // [n] dense agent index of each query
+  uint32_t* start_node;
+  uint32_t* end_node;
+  float* start_point;
+  float* end_point;
+  uint32_t* slot;
+};
+
+// per-agent frame scratch
+struct FollowScratch {
+  uint32_t* follow_start;  // [n] flat path index of the agent node, LMB_NONE if no follow indices
+  uint32_t* follow_end;    // [n]
+  uint32_t* presult;       // [n] bit31 repathed this frame, bit30 success, low 30 bits explored
+  uint32_t* query_of_agent;  // [n] query id or LMB_NONE
+};
+
+void launch_reset_slots(const AgentArrays& ag, const AgentPersist& persist, const PathPool& pool,
+                        cudaStream_t stream);
+void launch_repath_decide(const DevNav& nav, const AgentArrays& ag, const AgentPersist& persist,
+                          const PathPool& pool, const RepathQueue& queue, const FollowScratch& scratch,
+                          cudaStream_t stream);
+void launch_follow(const DevNav& nav, const AgentArrays& ag, const AgentPersist& persist,
+                   const PathPool& pool, const AStarQueries& q, const FollowScratch& scratch,
+                   cudaStream_t stream);
+void launch_gather_outputs(const AgentArrays& ag, const AgentPersist& persist, float* out_velocity,
+                           uint32_t* out_state, uint32_t* out_link_id, float* out_link_start,
+                           float* out_link_end, cudaStream_t stream);
+void launch_drop_all_paths(const PathPool& pool, uint32_t max_agents, cudaStream_t stream);
+
+// path pool compaction
+void launch_pool_compact(const PathPool& src, uint2* dst_entries, uint32_t max_agents, uint32_t* scan_tmp,
+                         cudaStream_t stream);
+
+// ---- kernel 4: avoidance (k_avoid.cu) ----
+struct AvoidRecord {  // 32 B per sampled agent: the per-frame halo exchanged between GPUs
+  float px, py, pz;
+  float vx, vy;
+  float radius;
+  float responsibility;
+  uint32_t valid;
+};
+
+struct AvoidGrid {
+  float ox, oy, inv_cell;
+  uint32_t nx, ny;
+  uint32_t* cell_count;   // [nx*ny + 1]
+  uint32_t* cell_start;   // [nx*ny + 1]
+  uint32_t* sorted;       // [n_records] record indices grouped by cell
+  uint32_t capacity_cells;
+};
+
+struct AvoidScratch {
+  // per-agent variable-length scratch, sized by `per_agent_*`
+  uint8_t* base;
+  size_t per_agent_bytes;
+  uint32_t max_neighbours;
+  uint32_t max_lines;
+  uint32_t max_cones;
+  uint32_t max_border_edges;
+  uint32_t max_explore;
+  uint32_t* overflow;  // device flag
+};
+
+void launch_build_records(const AgentArrays& ag, const AgentPersist& persist, const lmb_options& o,
+                          AvoidRecord* records, cudaStream_t stream);
+void launch_character_records(uint32_t n, const float* velocity, const float* radius, const float* points,
+                              const uint32_t* nodes, AvoidRecord* records, cudaStream_t stream);
+void launch_avoidance(const DevNav& nav, const AgentArrays& ag, const AgentPersist& persist,
+                      const lmb_options& o, float delta_time, uint32_t first_agent_global,
+                      uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
+                      const AvoidRecord* char_records, AvoidGrid& grid, const AvoidScratch& scratch,
+                      float* bounds_tmp, cudaStream_t stream);
+
+// generic single-block exclusive scan (u32), in place allowed
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t stream);
+
+}  // namespace lmb

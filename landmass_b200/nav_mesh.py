@@ -114,19 +114,29 @@ class NavigationMesh:
         if self.height_mesh is not None:
             hm = _validate_height_mesh(self.height_mesh, n_polys, cs)
 
-        if len(self.vertices):
+        if isinstance(self.vertices, np.ndarray) and self.vertices.ndim == 2 and self.vertices.shape[1] == 3 \
+                and cs is XYZ:
+            vertices = np.ascontiguousarray(self.vertices, dtype=np.float32)
+        elif len(self.vertices):
             vertices = np.stack([cs.to_landmass(v) for v in self.vertices]).astype(np.float32)
         else:
             vertices = np.zeros((0, 3), dtype=np.float32)
         n_verts = len(vertices)
 
-        counts = np.array([len(p) for p in self.polygons], dtype=np.int64)
+        uniform = isinstance(self.polygons, np.ndarray) and self.polygons.ndim == 2
+        if uniform:
+            counts = np.full(n_polys, self.polygons.shape[1], dtype=np.int64)
+        else:
+            counts = np.array([len(p) for p in self.polygons], dtype=np.int64)
         if n_polys and counts.min() < 3:
             raise ValidationError("NotEnoughVerticesInPolygon", int(np.argmax(counts < 3)))
         begin = np.zeros(n_polys + 1, dtype=np.int64)
         np.cumsum(counts, out=begin[1:])
         n_edges = int(begin[-1])
-        if cs.FLIP_POLYGONS:
+        if uniform:
+            arr = self.polygons[:, ::-1] if cs.FLIP_POLYGONS else self.polygons
+            flat = np.ascontiguousarray(arr, dtype=np.int64).ravel()
+        elif cs.FLIP_POLYGONS:
             flat = np.fromiter((v for p in self.polygons for v in reversed(p)), dtype=np.int64,
                                count=n_edges)
         else:

@@ -1,0 +1,134 @@
+"""Synthetic navmeshes and agent populations for the BASELINE.json configs
+(SURVEY.md §8d).  Data only: deterministic generators shared by bench.py, smoke() and
+the parity tests, so the CUDA path and the CPU oracle see identical inputs.
+
+Common conventions (SURVEY.md §8d "Common inputs"): XYZ coordinates, z = 0, island
+rotation 0, unit cell = 1.0, quads CCW [v(x,y), v(x+1,y), v(x+1,y+1), v(x,y+1)],
+polygon index = row-major over open cells, seed 0x1A2B3C4D.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .nav_mesh import NavigationMesh, ValidNavigationMesh
+
+SEED = 0x1A2B3C4D
+
+
+def _quads_from_open(open_mask: np.ndarray, cell: float = 1.0, types=None) -> NavigationMesh:
+    """open_mask[y, x] -> one quad per open cell, shared vertices on the full lattice."""
+    h, w = open_mask.shape
+    ys, xs = np.nonzero(open_mask)  # row-major
+    vx, vy = np.meshgrid(np.arange(w + 1, dtype=np.float32), np.arange(h + 1, dtype=np.float32))
+    verts = np.stack([vx.ravel() * np.float32(cell), vy.ravel() * np.float32(cell),
+                      np.zeros((h + 1) * (w + 1), dtype=np.float32)], axis=1)
+    v00 = ys * (w + 1) + xs
+    polys = np.stack([v00, v00 + 1, v00 + (w + 1) + 1, v00 + (w + 1)], axis=1)
+    t = np.zeros(len(polys), dtype=np.int64) if types is None else np.asarray(types)[ys, xs]
+    return _FastQuadMesh(verts, polys, t)
+
+
+class _FastQuadMesh(NavigationMesh):
+    """NavigationMesh whose polygons are held as an (P,4) array (validate() accepts any
+    sequence of sequences; this just avoids building 500k Python lists)."""
+
+    def __init__(self, verts, polys, types):
+        super().__init__(vertices=verts, polygons=polys, polygon_type_indices=types)
+
+
+def grid_mesh(nx: int, ny: int, cell: float = 1.0, types=None) -> ValidNavigationMesh:
+    """Open nx x ny quad grid (configs 1, 3, 4)."""
+    return _quads_from_open(np.ones((ny, nx), dtype=bool), cell, types).validate()
+
+
+def maze_open_mask(rooms: int, seed: int = SEED) -> np.ndarray:
+    """Perfect maze with rooms x rooms rooms on a (2*rooms+1)^2 fine grid: rooms at odd
+    coordinates, walls carved by a randomised iterative DFS (configs 2, 5)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = 2 * rooms + 1
+    open_mask = np.zeros((g, g), dtype=bool)
+    visited = np.zeros((rooms, rooms), dtype=bool)
+    # pre-draw random direction orders in bulk for speed
+    perms = np.array([[0, 1, 2, 3], [0, 1, 3, 2], [0, 2, 1, 3], [0, 2, 3, 1], [0, 3, 1, 2], [0, 3, 2, 1],
+                      [1, 0, 2, 3], [1, 0, 3, 2], [1, 2, 0, 3], [1, 2, 3, 0], [1, 3, 0, 2], [1, 3, 2, 0],
+                      [2, 0, 1, 3], [2, 0, 3, 1], [2, 1, 0, 3], [2, 1, 3, 0], [2, 3, 0, 1], [2, 3, 1, 0],
+                      [3, 0, 1, 2], [3, 0, 2, 1], [3, 1, 0, 2], [3, 1, 2, 0], [3, 2, 0, 1], [3, 2, 1, 0]])
+    draws = rng.integers(0, 24, size=rooms * rooms * 2 + 16)
+    di = 0
+    dx = (1, -1, 0, 0)
+    dy = (0, 0, 1, -1)
+    stack = [(0, 0)]
+    visited[0, 0] = True
+    open_mask[1, 1] = True
+    while stack:
+        x, y = stack[-1]
+        moved = False
+        order = perms[draws[di % len(draws)]]
+        di += 1
+        for d in order:
+            nx_, ny_ = x + dx[d], y + dy[d]
+            if 0 <= nx_ < rooms and 0 <= ny_ < rooms and not visited[ny_, nx_]:
+                visited[ny_, nx_] = True
+                open_mask[2 * y + 1 + dy[d], 2 * x + 1 + dx[d]] = True
+                open_mask[2 * ny_ + 1, 2 * nx_ + 1] = True
+                stack.append((nx_, ny_))
+                moved = True
+                break
+        if not moved:
+            stack.pop()
+    return open_mask
+
+
+def maze_mesh(rooms: int, seed: int = SEED) -> ValidNavigationMesh:
+    return _quads_from_open(maze_open_mask(rooms, seed)).validate()
+
+
+def random_points_on_mesh(mesh: ValidNavigationMesh, n: int, rng, lo: float = 0.1, hi: float = 0.9):
+    """Uniform over polygons (axis-aligned quads): polygon min corner + uniform offset in
+    [lo, hi]^2 of its extent.  Returns (points (n,3) f32, polygon index (n,))."""
+    p = rng.integers(0, mesh.n_polys, size=n)
+    b = mesh.poly_bounds[p]
+    u = rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+    pts = np.zeros((n, 3), dtype=np.float32)
+    pts[:, 0] = b[:, 0] + (b[:, 3] - b[:, 0]) * u[:, 0]
+    pts[:, 1] = b[:, 1] + (b[:, 4] - b[:, 1]) * u[:, 1]
+    pts[:, 2] = b[:, 2]
+    return pts, p
+
+
+def make_agents(mesh: ValidNavigationMesh, n: int, seed: int = SEED, radius: float = 0.5,
+                desired_speed: float = 1.0, max_speed: float = 2.0, slot_base: int = 0) -> dict:
+    """Agent SoA (the `lmb_agents_in` arrays) with uniform positions and targets."""
+    from . import _abi
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pos, _ = random_points_on_mesh(mesh, n, rng)
+    tgt, _ = random_points_on_mesh(mesh, n, rng)
+    return {
+        "n": n,
+        "slot": np.arange(slot_base, slot_base + n, dtype=np.uint32),
+        "flags": np.full(n, _abi.AGENT_HAS_TARGET | _abi.AGENT_PERMIT_ALL_LINKS | _abi.AGENT_RESET,
+                         dtype=np.uint32),
+        "position": pos,
+        "velocity": np.zeros((n, 3), dtype=np.float32),
+        "target": tgt,
+        "radius": np.full(n, radius, dtype=np.float32),
+        "desired_speed": np.full(n, desired_speed, dtype=np.float32),
+        "max_speed": np.full(n, max_speed, dtype=np.float32),
+    }
+
+
+def single_island_flat(mesh: ValidNavigationMesh) -> dict:
+    """Flattened navdata (dict for _abi.make_navdata_desc) of one island at the origin."""
+    from .nav_data import Island, NavigationData, Transform
+
+    nd = NavigationData()
+    nd.add_island(Island(Transform(), mesh))
+    nd.update(0.01, 0.25)
+    return nd.flatten()
+
+
+def default_options(radius: float = 0.5):
+    from .archipelago import ArchipelagoOptions
+
+    return ArchipelagoOptions.from_agent_radius(radius).to_abi()

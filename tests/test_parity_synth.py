@@ -1,0 +1,111 @@
+"""CUDA-vs-oracle parity on seeded synthetic navmeshes (SURVEY.md §8d configs at sizes the
+oracle finishes in seconds), through the C ABI.  Bit-exact for node ids, corridors, portal
+edge indices, explored_nodes and states; sampled points bit-exact; velocities 1e-4 relative."""
+import numpy as np
+import pytest
+
+from landmass_b200 import _abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def backends(flat, max_agents=4096, flags=0):
+    from landmass_b200._native import NativeBackend
+    from oracle.oracle_py import OracleBackend
+
+    gpu = NativeBackend(max_agents=max_agents, flags=flags)
+    cpu = OracleBackend(flags=flags)
+    gpu.navdata_upload(flat)
+    cpu.navdata_upload(flat)
+    return gpu, cpu
+
+
+@pytest.mark.parametrize("mesh_kind", ["grid", "maze"])
+def test_sampling_bit_exact(mesh_kind):
+    mesh = synth.grid_mesh(64, 64) if mesh_kind == "grid" else synth.maze_mesh(24)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    rng = np.random.Generator(np.random.PCG64(7))
+    n = 20000
+    pts, _ = synth.random_points_on_mesh(mesh, n, rng, lo=-0.2, hi=1.2)  # some fall outside
+    pts[:, 2] = rng.uniform(-0.8, 0.6, size=n).astype(np.float32)
+    # lattice points exercise exact ties between neighbouring polygons
+    lattice = np.stack([rng.integers(0, 50, n // 10), rng.integers(0, 50, n // 10), np.zeros(n // 10)], axis=1)
+    pts = np.concatenate([pts, lattice.astype(np.float32)])
+    opts = synth.default_options()
+    gp, gn = gpu.sample_points(pts, opts)
+    cp, cn = cpu.sample_points(pts, opts)
+    assert np.array_equal(gn, cn)
+    assert np.array_equal(gp.view(np.uint32), cp.view(np.uint32))
+    assert (gn != _abi.NONE).sum() > n // 2 and (gn == _abi.NONE).sum() > 0
+
+
+@pytest.mark.parametrize("mesh_kind,nq", [("grid", 300), ("maze", 300)])
+def test_find_paths_bit_exact(mesh_kind, nq):
+    mesh = synth.grid_mesh(48, 48) if mesh_kind == "grid" else synth.maze_mesh(24)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    rng = np.random.Generator(np.random.PCG64(11))
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    g = gpu.find_paths(sn, sp, en, ep)
+    c = cpu.find_paths(sn, sp, en, ep)
+    for a, b, name in zip(g, c, ["success", "explored", "begin", "nodes", "portals"]):
+        assert np.array_equal(a, b), name
+    assert g[0].all()
+
+
+def run_frames(gpu, cpu, ag, opts, frames, dt=1.0 / 60.0, retarget=None):
+    n = ag["n"]
+    for frame in range(frames):
+        og = gpu.step(ag, None, opts, dt)
+        oc = cpu.step(ag, None, opts, dt)
+        assert np.array_equal(og["state"], oc["state"]), f"frame {frame}: states"
+        assert gpu.pathing_results() == cpu.pathing_results(), f"frame {frame}: pathing results"
+        np.testing.assert_allclose(og["desired_velocity"], oc["desired_velocity"], rtol=1e-4, atol=1e-6,
+                                   err_msg=f"frame {frame}")
+        for slot in range(0, n, max(1, n // 16)):
+            gp, cp = gpu.agent_path(slot), cpu.agent_path(slot)
+            assert np.array_equal(gp[0], cp[0]) and np.array_equal(gp[1], cp[1]), f"path of slot {slot}"
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["velocity"] = oc["desired_velocity"].copy()
+        ag["position"] = ag["position"] + oc["desired_velocity"] * np.float32(dt)
+        if retarget is not None:
+            retarget(frame, ag)
+    return og
+
+
+@pytest.mark.parametrize("mesh_kind", ["grid", "maze"])
+def test_step_without_avoidance(mesh_kind):
+    mesh = synth.grid_mesh(64, 64) if mesh_kind == "grid" else synth.maze_mesh(20)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat, flags=_abi.CONFIG_NO_AVOIDANCE)
+    ag = synth.make_agents(mesh, 600)
+    # a mix of agent situations: no target, paused, off-mesh agent, off-mesh target
+    ag["flags"][0:20] &= ~np.uint32(_abi.AGENT_HAS_TARGET)
+    ag["flags"][20:40] |= _abi.AGENT_PAUSED
+    ag["position"][40:60, 2] = 50.0
+    ag["target"][60:80, 0] = -100.0
+    ag["reach_condition"] = np.zeros(600, dtype=np.uint32)
+    ag["reach_condition"][100:200] = _abi.REACH_VISIBLE_AT_DISTANCE
+    ag["reach_condition"][200:300] = _abi.REACH_STRAIGHT_PATH_DISTANCE
+    ag["reach_distance"] = np.full(600, -1.0, dtype=np.float32)
+    ag["reach_distance"][250:300] = 3.0
+    opts = synth.default_options()
+    rng = np.random.Generator(np.random.PCG64(5))
+
+    def retarget(frame, a):
+        if frame == 2:  # some agents get new targets -> repath or path reuse
+            t, _ = synth.random_points_on_mesh(mesh, 100, rng)
+            a["target"][300:400] = t
+        if frame == 3:
+            a["flags"][20:30] &= ~np.uint32(_abi.AGENT_PAUSED)
+
+    og = run_frames(gpu, cpu, ag, opts, 6, dt=0.25, retarget=retarget)
+    assert (og["state"] == _abi_state("Moving")).sum() > 100
+
+
+def _abi_state(name):
+    from landmass_b200 import AgentState
+
+    return int(AgentState[name])
