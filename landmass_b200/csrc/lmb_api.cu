@@ -702,7 +702,8 @@ int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* a, const lmb_charac
   return LMB_OK;
 }
 
-static AgentArrays make_agent_arrays(lmb_ctx* ctx) {
+} // extern C
+AgentArrays lmb_make_agent_arrays(lmb_ctx* ctx) {
   AgentArrays ag{};
   ag.n = ctx->n_agents;
   ag.slot = ctx->d_slot.p;
@@ -723,7 +724,7 @@ static AgentArrays make_agent_arrays(lmb_ctx* ctx) {
   return ag;
 }
 
-static AgentPersist make_persist(lmb_ctx* ctx) {
+AgentPersist lmb_make_persist(lmb_ctx* ctx) {
   AgentPersist p{};
   p.desired_move = ctx->d_desired_move.p;
   p.state = ctx->d_state.p;
@@ -733,6 +734,7 @@ static AgentPersist make_persist(lmb_ctx* ctx) {
   return p;
 }
 
+extern "C" {
 int32_t lmb_avoidance_phase(lmb_ctx* ctx, const lmb_options* o, float dt);  // lmb_avoid_host.cu
 
 int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
@@ -771,8 +773,8 @@ int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
     CUDA_TRY(ctx, ctx->d_char_point.reserve(3 * (size_t)ctx->n_chars));
     CUDA_TRY(ctx, ctx->d_char_node.reserve(ctx->n_chars));
   }
-  AgentArrays ag = make_agent_arrays(ctx);
-  AgentPersist persist = make_persist(ctx);
+  AgentArrays ag = lmb_make_agent_arrays(ctx);
+  AgentPersist persist = lmb_make_persist(ctx);
 
   // keep the pool at most half full before the frame
   {

@@ -1,8 +1,114 @@
-// landmass_b200 — phase D host orchestration (placeholder until k_avoid.cu lands).
+// landmass_b200 — phase D host orchestration: records -> uniform grid -> per-agent
+// obstacle flood + ORCA (k_avoid.cu).  Split in two so that a multi-GPU caller can
+// all-gather the per-agent avoidance records between the halves.
+#include <algorithm>
+#include <cmath>
+
 #include "lmb_context.h"
 
+namespace lmb {
+size_t avoid_scratch_bytes_per_agent(const AvoidScratch& s);
+void launch_avoid_grid(uint32_t n_records, const AvoidRecord* records, AvoidGrid& grid, uint32_t* max_radius_bits,
+                       cudaStream_t stream);
+void launch_stage_moves(const AgentArrays& ag, const AgentPersist& persist, float* staged, cudaStream_t stream);
+void launch_commit_moves(const AgentArrays& ag, const AgentPersist& persist, const float* staged,
+                         cudaStream_t stream);
+void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_options& o, float delta_time,
+                            uint32_t first_agent_global, uint32_t chunk_begin, uint32_t chunk_n,
+                            uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
+                            const AvoidRecord* char_records, const AvoidGrid& grid, const AvoidScratch& scratch,
+                            const uint32_t* max_radius_bits, float* staged_moves, cudaStream_t stream);
+}  // namespace lmb
+
+AgentArrays lmb_make_agent_arrays(lmb_ctx* ctx);
+AgentPersist lmb_make_persist(lmb_ctx* ctx);
+
+// Builds this rank's avoidance records into ctx->d_records[first .. first + n_agents).
+int32_t lmb_avoidance_build_records(lmb_ctx* ctx, const lmb_options* o, uint32_t n_total, uint32_t first) {
+  cudaStream_t s = ctx->stream;
+  CUDA_TRY(ctx, ctx->d_records.reserve(n_total ? n_total : 1));
+  AgentArrays ag = lmb_make_agent_arrays(ctx);
+  launch_build_records(ag, lmb_make_persist(ctx), *o, ctx->d_records.p + first, s);
+  if (ctx->n_chars) {
+    CUDA_TRY(ctx, ctx->d_char_records.reserve(ctx->n_chars));
+    launch_character_records(ctx->n_chars, ctx->d_char_velocity.p, ctx->d_char_radius.p, ctx->d_char_point.p,
+                             ctx->d_char_node.p, ctx->d_char_records.p, s);
+  }
+  ctx->timings.kernel_launches += (ag.n ? 1 : 0) + (ctx->n_chars ? 1 : 0);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return LMB_OK;
+}
+
+// Runs avoidance for this rank's agents against all n_total records.
+int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first) {
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = ctx->n_agents;
+  if (n == 0) return LMB_OK;
+  AgentArrays ag = lmb_make_agent_arrays(ctx);
+  AgentPersist persist = lmb_make_persist(ctx);
+
+  // uniform grid over the navmesh's world xy bounds
+  AvoidGrid grid{};
+  float cell = std::max(o->neighbourhood * 0.5f, 1e-3f);
+  float ex = std::max(ctx->world_max[0] - ctx->world_min[0], 1e-3f) + 2.0f * cell;
+  float ey = std::max(ctx->world_max[1] - ctx->world_min[1], 1e-3f) + 2.0f * cell;
+  const double max_cells = 8.0e6;
+  if ((double)(ex / cell) * (double)(ey / cell) > max_cells) cell = (float)std::sqrt((double)ex * ey / max_cells);
+  grid.ox = ctx->world_min[0] - cell;
+  grid.oy = ctx->world_min[1] - cell;
+  grid.inv_cell = 1.0f / cell;
+  grid.nx = (uint32_t)std::ceil(ex / cell) + 1;
+  grid.ny = (uint32_t)std::ceil(ey / cell) + 1;
+  const size_t cells = (size_t)grid.nx * grid.ny;
+  CUDA_TRY(ctx, ctx->d_cell_count.reserve(cells + 2));
+  CUDA_TRY(ctx, ctx->d_cell_start2.reserve(cells + 2));
+  CUDA_TRY(ctx, ctx->d_sorted.reserve(n_total ? n_total : 1));
+  grid.cell_count = ctx->d_cell_count.p;
+  grid.cell_start = ctx->d_cell_start2.p;
+  grid.sorted = ctx->d_sorted.p;
+  uint32_t* max_radius_bits = ctx->d_avoid_overflow.p + 1;
+  launch_avoid_grid(n_total, ctx->d_records.p, grid, max_radius_bits, s);
+  ctx->timings.kernel_launches += 4;
+  CUDA_TRY(ctx, cudaGetLastError());
+
+  CUDA_TRY(ctx, ctx->d_out_velocity.reserve(3 * (size_t)n));
+  float* staged = ctx->d_out_velocity.p;  // reused as the staging buffer; gather overwrites it later
+
+  for (int attempt = 0; attempt < 8; attempt++) {
+    AvoidScratch sc{};
+    sc.max_neighbours = ctx->avoid_caps[0];
+    sc.max_explore = ctx->avoid_caps[1];
+    sc.max_border_edges = ctx->avoid_caps[2];
+    sc.max_cones = ctx->avoid_caps[3];
+    sc.max_lines = ctx->avoid_caps[4];
+    sc.per_agent_bytes = avoid_scratch_bytes_per_agent(sc);
+    const uint32_t chunk = std::min<uint32_t>(n, 131072u);
+    CUDA_TRY(ctx, ctx->d_avoid_scratch.reserve(sc.per_agent_bytes * (size_t)chunk));
+    sc.base = ctx->d_avoid_scratch.p;
+    sc.overflow = ctx->d_avoid_overflow.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(sc.overflow, 0, sizeof(uint32_t), s));
+    launch_stage_moves(ag, persist, staged, s);
+    for (uint32_t b = 0; b < n; b += chunk) {
+      launch_avoidance_chunk(ctx->nav, ag, *o, dt, first, b, std::min(chunk, n - b), n_total, ctx->d_records.p,
+                             ctx->n_chars, ctx->d_char_records.p, grid, sc, max_radius_bits, staged, s);
+      ctx->timings.kernel_launches += 1;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small + 8, sc.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (ctx->h_small[8] == 0) {
+      launch_commit_moves(ag, persist, staged, s);
+      ctx->timings.kernel_launches += 2;
+      CUDA_TRY(ctx, cudaGetLastError());
+      return LMB_OK;
+    }
+    for (int k = 0; k < 5; k++) ctx->avoid_caps[k] *= 2;  // scratch too small for some agent: grow, redo
+  }
+  return ctx->fail(LMB_ERR_CAPACITY, "avoidance scratch kept overflowing");
+}
+
 extern "C" int32_t lmb_avoidance_phase(lmb_ctx* ctx, const lmb_options* o, float dt) {
-  (void)o;
-  (void)dt;
-  return ctx->fail(LMB_ERR_UNSUPPORTED, "avoidance kernels not built yet");
+  int32_t st = lmb_avoidance_build_records(ctx, o, ctx->n_agents, 0);
+  if (st != LMB_OK) return st;
+  return lmb_avoidance_solve(ctx, o, dt, ctx->n_agents, 0);
 }

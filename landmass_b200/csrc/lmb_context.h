@@ -112,6 +112,7 @@ struct lmb_ctx {
   DevBuf<uint8_t> d_avoid_scratch;
   DevBuf<float> d_bounds_tmp;
   uint32_t last_n_results = 0;
+  uint32_t avoid_caps[5] = {64, 64, 128, 256, 256};  // neighbours, explore, border edges, cones, lines
 
   lmb_step_timings timings{};
   cudaEvent_t ev[9]{};

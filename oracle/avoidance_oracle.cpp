@@ -67,6 +67,7 @@ struct VisibilitySet {
   bool process_piece(V2 a, V2 b, float lo, float hi, int add_id, std::vector<Cone>* out) const {
     bool visible = false;
     float cur = lo;
+    bool tail_done = false;
     auto emit = [&](float l, float h, uint32_t line) {
       if (!out || !(l < h)) return;
       if (!out->empty() && out->back().line == line && out->back().hi == l)
@@ -76,8 +77,14 @@ struct VisibilitySet {
     };
     for (const Cone& c : cones) {
       if (!(c.hi > lo && c.lo < hi)) {
+        if (c.lo >= hi && !tail_done) {  // first cone past the span: the trailing gap goes before it
+          tail_done = true;
+          if (cur < hi) {
+            visible = true;
+            if (add_id >= 0) emit(cur, hi, (uint32_t)add_id);
+          }
+        }
         emit(c.lo, c.hi, c.line);
-        // a gap before a cone that starts at/after hi is handled after the loop
         continue;
       }
       if (c.lo > cur) {  // gap [cur, c.lo]
@@ -85,7 +92,7 @@ struct VisibilitySet {
         if (add_id >= 0) emit(cur, c.lo, (uint32_t)add_id);
         cur = c.lo;
       }
-      float olo = std::max(cur, c.lo), ohi = std::min(hi, c.hi);
+      float olo = std::fmax(cur, c.lo), ohi = std::fmin(hi, c.hi);
       if (c.lo < olo) emit(c.lo, olo, c.line);
       if (olo < ohi) {
         V2 d = pdir((olo + ohi) * 0.5f);
@@ -100,19 +107,9 @@ struct VisibilitySet {
       if (ohi < c.hi) emit(ohi, c.hi, c.line);
       if (c.hi > cur) cur = c.hi;
     }
-    if (cur < hi) {
+    if (!tail_done && cur < hi) {
       visible = true;
-      if (add_id >= 0 && out) {
-        // insert the trailing gap at its sorted position
-        Cone g{cur, hi, (uint32_t)add_id};
-        auto it = std::lower_bound(out->begin(), out->end(), g,
-                                   [](const Cone& x, const Cone& y) { return x.lo < y.lo; });
-        if (it != out->begin() && (it - 1)->line == g.line && (it - 1)->hi == g.lo) {
-          (it - 1)->hi = g.hi;
-        } else {
-          out->insert(it, g);
-        }
-      }
+      if (add_id >= 0) emit(cur, hi, (uint32_t)add_id);
     }
     return visible;
   }
@@ -120,39 +117,40 @@ struct VisibilitySet {
   bool process(V2 a, V2 b, bool add, uint32_t* out_id) {
     float det = perp_dot(a, b);
     if (det < 0.0f) std::swap(a, b);
-    if (!(det != 0.0f)) return false;  // zero angular width (or NaN)
+    if (!(det != 0.0f)) {
+      // The supporting line passes through the origin: zero angular width, so it can never
+      // occlude (not added); a portal is still "visible" when the origin lies ON the segment
+      // (agent standing on the portal, avoidance_test.rs:237-327).
+      return !add && det == 0.0f && dot(a, b) <= 0.0f;
+    }
     float lo = pangle(a), hi = pangle(b);
     if (lo == hi) return false;
-    int id = add ? (int)la.size() : -1;
-    bool visible;
-    if (lo < hi) {
-      std::vector<Cone> nc;
-      visible = process_piece(a, b, lo, hi, id, add ? &nc : nullptr);
-      if (add && visible) cones.swap(nc);
-    } else {
-      // span crosses the cut at pseudo-angle 0/4
-      if (!add) {
-        visible = process_piece(a, b, lo, 4.0f, -1, nullptr) || process_piece(a, b, 0.0f, hi, -1, nullptr);
-      } else {
-        // the line must be registered before the second piece is compared against it
-        std::vector<Cone> saved = cones, nc;
-        la.push_back(a);
-        lb.push_back(b);
-        bool v1 = process_piece(a, b, lo, 4.0f, id, &nc);
-        cones.swap(nc);
-        nc.clear();
-        bool v2 = process_piece(a, b, 0.0f, hi, id, &nc);
-        cones.swap(nc);
-        la.pop_back();
-        lb.pop_back();
-        visible = v1 || v2;
-        if (!visible) cones.swap(saved);
-      }
+    if (!add) {
+      if (lo < hi) return process_piece(a, b, lo, hi, -1, nullptr);
+      return process_piece(a, b, lo, 4.0f, -1, nullptr) || process_piece(a, b, 0.0f, hi, -1, nullptr);
     }
-    if (add && visible) {
-      la.push_back(a);
-      lb.push_back(b);
-      if (out_id) *out_id = (uint32_t)id;
+    int id = (int)la.size();
+    la.push_back(a);  // registered so that pieces can be compared against it
+    lb.push_back(b);
+    bool visible;
+    std::vector<Cone> nc;
+    if (lo < hi) {
+      visible = process_piece(a, b, lo, hi, id, &nc);
+      if (visible) cones.swap(nc);
+    } else {
+      // span crosses the cut at pseudo-angle 0/4: two pieces, each committed if visible
+      bool v1 = process_piece(a, b, lo, 4.0f, id, &nc);
+      if (v1) cones.swap(nc);
+      nc.clear();
+      bool v2 = process_piece(a, b, 0.0f, hi, id, &nc);
+      if (v2) cones.swap(nc);
+      visible = v1 || v2;
+    }
+    if (!visible) {
+      la.pop_back();
+      lb.pop_back();
+    } else if (out_id) {
+      *out_id = (uint32_t)id;
     }
     return visible;
   }

@@ -109,3 +109,32 @@ def _abi_state(name):
     from landmass_b200 import AgentState
 
     return int(AgentState[name])
+
+
+@pytest.mark.parametrize("mesh_kind,n", [("grid", 1500), ("maze", 800)])
+def test_full_step_with_avoidance(mesh_kind, n):
+    """All four phases.  Velocities within 1e-4 relative (north_star tolerance); states,
+    pathing results and paths exact.  ORCA parity is CUDA-vs-oracle (dodgy_2d source absent)."""
+    mesh = synth.grid_mesh(24, 24) if mesh_kind == "grid" else synth.maze_mesh(10)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    ag = synth.make_agents(mesh, n)   # dense: many neighbours per agent, borders nearby
+    opts = synth.default_options()
+    ch = {"n": 3,
+          "position": np.array([[5.5, 5.5, 0.0], [9.5, 3.5, 0.0], [100.0, 0.0, 0.0]], dtype=np.float32),
+          "velocity": np.array([[0.5, 0.0, 0.0], [0.0, -0.5, 0.0], [0.0, 0.0, 0.0]], dtype=np.float32),
+          "radius": np.array([0.6, 0.4, 1.0], dtype=np.float32)}
+    dt = 1.0 / 30.0
+    for frame in range(4):
+        og = gpu.step(ag, ch, opts, dt)
+        oc = cpu.step(ag, ch, opts, dt)
+        assert np.array_equal(og["state"], oc["state"]), f"frame {frame}: states"
+        assert gpu.pathing_results() == cpu.pathing_results()
+        err = np.abs(og["desired_velocity"] - oc["desired_velocity"]).max(axis=1)
+        scale = np.maximum(np.abs(oc["desired_velocity"]).max(axis=1), 1e-2)
+        assert (err <= 1e-4 * scale + 1e-6).all(), f"frame {frame}: max rel err {(err / scale).max()}"
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["velocity"] = oc["desired_velocity"].copy()
+        ag["position"] = ag["position"] + oc["desired_velocity"] * np.float32(dt)
+    moved = np.abs(oc["desired_velocity"]).max(axis=1) > 0
+    assert moved.sum() > n // 2
