@@ -279,6 +279,21 @@ int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* agents,
 int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* options, float delta_time);
 int32_t lmb_agents_download(lmb_ctx* ctx, const lmb_agents_out* out);
 
+/* Multi-GPU form of the step: agents are sharded over ranks by contiguous
+ * ranges of the global agent order, navigation data is replicated, and the only exchange is
+ * the per-agent avoidance record (32 bytes) between phase C and phase D.
+ *   lmb_step_begin : phases A-C for this rank's agents (those given to lmb_agents_upload),
+ *                    then writes their records at [first_agent, first_agent + n) of the halo
+ *                    buffer; returns after the stream is idle.
+ *   lmb_halo_buffer: device pointer / layout of the halo buffer (n_total records); the caller
+ *                    all-gathers it in place (e.g. ncclAllGather) and synchronises.
+ *   lmb_step_end   : phase D for this rank's agents against all n_total records, outputs.
+ * lmb_step_resident(ctx, o, dt) == begin(n, 0) + end. */
+int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* options, float delta_time,
+                       uint32_t n_total_agents, uint32_t first_agent);
+int32_t lmb_halo_buffer(lmb_ctx* ctx, void** device_ptr, uint64_t* record_bytes, uint64_t* n_records);
+int32_t lmb_step_end(lmb_ctx* ctx, const lmb_options* options, float delta_time);
+
 /* `Archipelago::get_pathing_results` (lib.rs:231-233): results of the last step in agent order. */
 int32_t lmb_pathing_results(lmb_ctx* ctx, lmb_pathing_result* out, uint32_t capacity,
                             uint32_t* out_count);

@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = [
     "lmb_abi_version", "lmb_create", "lmb_destroy", "lmb_last_error", "lmb_navdata_upload",
     "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
-    "lmb_get_step_timings",
+    "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
 ]
 
 
@@ -64,6 +64,9 @@ def declare_prototypes(lib, prefix: str):
                            _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.u32p,
                            _abi.u32p, u32])
     fn("get_step_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
+    fn("step_begin", i32, [vp, C.POINTER(_abi.Options), f32, u32, u32])
+    fn("halo_buffer", i32, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
+    fn("step_end", i32, [vp, C.POINTER(_abi.Options), f32])
     if prefix == "lmb_":
         lib.lmb_abi_version.restype = u32
         lib.lmb_abi_version.argtypes = []
@@ -229,6 +232,18 @@ class NativeBackend(CBackend):
 
     def step_resident(self, options: _abi.Options, dt: float):
         self._check(self.lib.lmb_step_resident(self.ctx, C.byref(options), C.c_float(dt)))
+
+    def step_begin(self, options: _abi.Options, dt: float, n_total: int, first: int):
+        self._check(self.lib.lmb_step_begin(self.ctx, C.byref(options), C.c_float(dt), n_total, first))
+
+    def halo_buffer(self):
+        """(device pointer, record bytes, n records) of the avoidance-record halo buffer."""
+        p, rb, nr = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.lmb_halo_buffer(self.ctx, C.byref(p), C.byref(rb), C.byref(nr)))
+        return p.value, rb.value, nr.value
+
+    def step_end(self, options: _abi.Options, dt: float):
+        self._check(self.lib.lmb_step_end(self.ctx, C.byref(options), C.c_float(dt)))
 
     def agents_download(self) -> dict:
         o, out = _abi.make_agents_out(self._n_agents)

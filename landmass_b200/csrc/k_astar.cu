@@ -29,6 +29,7 @@ constexpr float F_INF = __builtin_huge_valf();
 struct HeapEntry {
   float cost, estimate;
   uint32_t index;
+  uint32_t state;
 };
 
 // NodeRef::partial_cmp (astar.rs:67-77) as `a <= b`
@@ -41,15 +42,25 @@ __device__ __forceinline__ bool noderef_le(const HeapEntry& a, const HeapEntry& 
 // Reverse<T>::le(x, y) = y.0 <= x.0
 __device__ __forceinline__ bool rev_le(const HeapEntry& x, const HeapEntry& y) { return noderef_le(y, x); }
 
+// Open list.  Entries [0, SMEM_HEAP) live in shared memory (one private region per warp),
+// the rest spills to the slot's global arena.  Entry = {cost, estimate, node index, state}.
+constexpr uint32_t SMEM_HEAP = 384;
+
 struct Heap {
-  uint4* data;  // entry i lives at data[i + 1] so that child pairs share a 32-byte sector
+  uint4* sm;    // [SMEM_HEAP]
+  uint4* gm;    // global spill; entry i (>= SMEM_HEAP) at gm[i + 1]
   uint32_t len;
+  __device__ __forceinline__ uint4 raw(uint32_t i) const { return i < SMEM_HEAP ? sm[i] : gm[i + 1]; }
   __device__ __forceinline__ HeapEntry get(uint32_t i) const {
-    uint4 v = data[i + 1];
-    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z};
+    uint4 v = raw(i);
+    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w};
   }
   __device__ __forceinline__ void set(uint32_t i, const HeapEntry& e) {
-    data[i + 1] = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, 0u);
+    uint4 v = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, e.state);
+    if (i < SMEM_HEAP)
+      sm[i] = v;
+    else
+      gm[i + 1] = v;
   }
   __device__ __forceinline__ void sift_up(uint32_t start, uint32_t pos, const HeapEntry& hole) {
     while (pos > start) {
@@ -96,10 +107,13 @@ struct Query {
 
 }  // namespace
 
-__global__ void __launch_bounds__(64)
+constexpr uint32_t ASTAR_WARPS = 8;  // warps per block; 4 blocks/SM -> 32 concurrent queries per SM
+
+__global__ void __launch_bounds__(ASTAR_WARPS * 32, 4)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
-  __shared__ float s_cost[2][LMB_MAX_TYPES];
+  __shared__ float s_cost[ASTAR_WARPS][LMB_MAX_TYPES];
+  extern __shared__ uint4 s_heap[];  // [ASTAR_WARPS][SMEM_HEAP]
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp_in_block = threadIdx.x >> 5;
   const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -110,7 +124,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   float* best = reinterpret_cast<float*>(slot_base);
   uint4* nodes = reinterpret_cast<uint4*>(slot_base + arena.nodes_offset);  // cost, state, prev, depth
   Heap heap;
-  heap.data = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
+  heap.sm = s_heap + (size_t)warp_in_block * SMEM_HEAP;
+  heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
 
   const uint32_t ST_LINK0 = nav.n_edges;
   const uint32_t ST_START = nav.n_edges + nav.n_links;
@@ -175,36 +190,35 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           best[ST_START] = est;
           nodes[0] = make_uint4(__float_as_uint(0.0f), ST_START, LMB_NONE, 0u);
           n_nodes = 1;
-          heap.push({0.0f, est, 0u});
+          heap.push({0.0f, est, 0u, ST_START});
         }
       }
       uint32_t goal = LMB_NONE;
       while (heap.len > 0) {
         HeapEntry cur = heap.pop();
-        uint4 cn = nodes[cur.index];
-        const uint32_t s = cn.y;
-        if (best[s] < cur.estimate) continue;  // stale (astar.rs:172-176)
-        explored++;
-        if (s == ST_END) {
-          goal = cur.index;
-          break;
-        }
-        const float cur_cost_so_far = __uint_as_float(cn.x);
-        const uint32_t depth1 = cn.w + 1;
+        const uint32_t s = cur.state;
+        // Issue every load the expansion needs before the first use: best[s] (stale test) and
+        // the node record (depth) usually come from HBM, the edge records from L2.
+        const float best_s = best[s];
+        const uint32_t cur_depth = nodes[cur.index].w;
+        EdgeRec self_rec;
+        if (s < ST_LINK0) self_rec = nav.edges[s];
 
         // resolve (node, point, ignore step) — pathfinding.rs:93-143
         uint32_t poly, first, ne, cur_type, has_links;
         uint32_t ignore_edge = LMB_NONE, ignore_link = LMB_NONE;
         V3 point;
         if (s < ST_LINK0) {
-          const EdgeRec r = nav.edges[s];
-          poly = r.poly;
-          first = r.first_edge;
-          ne = r.info & 0xffu;
-          cur_type = (r.info >> 8) & 0xffu;
-          has_links = (r.info >> 24) & 1u;
-          point = {r.mx, r.my, r.mz};
+          poly = self_rec.poly;
+          first = self_rec.first_edge;
+          ne = self_rec.info & 0xffu;
+          cur_type = (self_rec.info >> 8) & 0xffu;
+          has_links = (self_rec.info >> 24) & 1u;
+          point = {self_rec.mx, self_rec.my, self_rec.mz};
           ignore_edge = s;
+        } else if (s == ST_END) {
+          poly = first = ne = cur_type = has_links = 0;
+          point = {0.0f, 0.0f, 0.0f};
         } else {
           if (s == ST_START) {
             poly = qu.start_node;
@@ -226,6 +240,19 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           cur_type = nav.poly_type_dense[poly];
           has_links = nav.node_link_begin[poly + 1] > nav.node_link_begin[poly];
         }
+        // first chunk of successor edge records, speculatively (before the stale test resolves)
+        EdgeRec succ_rec;
+        succ_rec.twin = LMB_NONE;
+        if (s != ST_END && poly != qu.end_node && lane < ne) succ_rec = nav.edges[first + lane];
+
+        if (best_s < cur.estimate) continue;  // stale (astar.rs:172-176)
+        explored++;
+        if (s == ST_END) {
+          goal = cur.index;
+          break;
+        }
+        const float cur_cost_so_far = cur.cost;
+        const uint32_t depth1 = cur_depth + 1;
         const float cur_type_cost = cost_tab[cur_type];
 
         bool overflow = false;
@@ -240,7 +267,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             } else {
               best[ST_END] = est;
               nodes[n_nodes] = make_uint4(__float_as_uint(ncost), ST_END, cur.index, depth1);
-              heap.push({ncost, est, n_nodes});
+              heap.push({ncost, est, n_nodes, ST_END});
               n_nodes++;
             }
           }
@@ -252,7 +279,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             float ncost = 0.0f, est = 0.0f;
             uint32_t nstate = LMB_NONE;
             if (e < ne) {
-              const EdgeRec r = nav.edges[first + e];
+              const EdgeRec r = e0 == 0 ? succ_rec : nav.edges[first + e];
               if (r.twin != LMB_NONE && first + e != ignore_edge &&
                   is_finite(cost_tab[(r.info >> 16) & 0xffu])) {
                 V3 mid{r.mx, r.my, r.mz};
@@ -276,7 +303,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               }
               best[s2] = e2;
               nodes[n_nodes] = make_uint4(__float_as_uint(c2), s2, cur.index, depth1);
-              heap.push({c2, e2, n_nodes});
+              heap.push({c2, e2, n_nodes, s2});
               n_nodes++;
             }
           }
@@ -317,7 +344,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               }
               best[s2] = est;
               nodes[n_nodes] = make_uint4(__float_as_uint(ncost), s2, cur.index, depth1);
-              heap.push({ncost, est, n_nodes});
+              heap.push({ncost, est, n_nodes, s2});
               n_nodes++;
             }
           }
@@ -413,12 +440,19 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                   AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   if (q.n == 0) return;
-  const uint32_t warps_per_block = 2;
+  const uint32_t warps_per_block = ASTAR_WARPS;
+  const size_t smem = (size_t)ASTAR_WARPS * SMEM_HEAP * sizeof(uint4);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
   uint32_t blocks = (slots + warps_per_block - 1) / warps_per_block;
   AStarArena a = arena;
   a.n_slots = blocks * warps_per_block <= arena.n_slots ? blocks * warps_per_block : arena.n_slots;
-  k_astar<<<blocks, warps_per_block * 32, 0, stream>>>(nav, a, q, pool, counters, type_raw);
+  k_astar<<<blocks, warps_per_block * 32, smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
 }  // namespace lmb

@@ -80,7 +80,7 @@ int32_t lmb_create(const lmb_config* config, lmb_ctx** out_ctx) {
   if (ctx->cfg.max_agents == 0) ctx->cfg.max_agents = 1024;
   e = cudaSetDevice(ctx->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 9 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 11 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, sizeof(AStarCounters));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(uint32_t));
   cudaDeviceProp prop;
@@ -122,7 +122,7 @@ void lmb_destroy(lmb_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
   }
-  for (int i = 0; i < 9; i++)
+  for (int i = 0; i < 11; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -419,10 +419,10 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
 
   // ---- A* arenas ----
   uint32_t n_states = nav.n_edges + nav.n_links + 2;
-  uint32_t slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 16;
+  uint32_t slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 32;
   uint32_t node_cap = std::max<uint32_t>(n_states + 64, 256);
   uint32_t heap_cap = std::max<uint32_t>(n_states / 4 + 64, 256);
-  size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)48 << 30);
+  size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)80 << 30);
   size_t per_slot = (size_t)n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;
   if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 32);
   int32_t st = setup_arena(ctx, node_cap, heap_cap, slots);
@@ -448,7 +448,9 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
 static int32_t grow_pool(lmb_ctx* ctx, unsigned long long min_capacity) {
   cudaStream_t s = ctx->stream;
   int other = 1 - ctx->pool_cur;
-  unsigned long long want = std::max(min_capacity, ctx->pool_capacity * 2);
+  // compacts the live paths into a fresh buffer of at least min_capacity entries
+  unsigned long long want = std::max<unsigned long long>(min_capacity, 1ull << 16);
+  ctx->d_pool[other].release();
   CUDA_TRY(ctx, ctx->d_pool[other].reserve(want));
   PathPool src = make_pool(ctx);
   launch_pool_compact(src, ctx->d_pool[other].p, ctx->cfg.max_agents, ctx->d_scan_tmp.p, s);
@@ -464,6 +466,21 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
   cudaStream_t s = ctx->stream;
   uint32_t n = q.n;
   CUDA_TRY(ctx, cudaMemsetAsync(q.out_status, 0, n * sizeof(uint32_t), s));
+  // Make room for the expected corridors up front: a query that finishes its search but
+  // cannot allocate its corridor has to be searched again.
+  {
+    unsigned long long cursor = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    double per_query = ctx->path_len_estimate > 0.0 ? ctx->path_len_estimate * 1.25 + 16.0
+                                                    : std::min(std::max(ctx->nav.n_polys / 8.0, 64.0), 65536.0);
+    unsigned long long want = cursor + (unsigned long long)(per_query * n) + 1024;
+    if (want > ctx->pool_capacity) {
+      int32_t st = grow_pool(ctx, want);
+      if (st != LMB_OK) return st;
+    }
+  }
+  unsigned long long done_total = 0, nodes_total = 0;
   const uint32_t* list = nullptr;
   uint32_t n_run = n;
   std::vector<uint32_t> h_status;
@@ -481,6 +498,9 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     ctx->timings.path_nodes += ctx->h_counters->path_nodes_total;
     ctx->timings.kernel_launches += 1;
     uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
+    done_total += ctx->h_counters->n_done;
+    nodes_total += ctx->h_counters->path_nodes_total;
+    if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
     if (ra == 0 && rp == 0) return LMB_OK;
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);
@@ -496,7 +516,7 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
       AStarArena& a = ctx->arena;
       uint32_t node_cap = a.node_cap * 2, heap_cap = a.heap_cap * 2;
       size_t per_slot = (size_t)a.n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;
-      size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)48 << 30);
+      size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)80 << 30);
       uint32_t slots = a.n_slots;
       if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 8);
       int32_t st = setup_arena(ctx, node_cap, heap_cap, slots);
@@ -734,10 +754,13 @@ AgentPersist lmb_make_persist(lmb_ctx* ctx) {
   return p;
 }
 
-extern "C" {
-int32_t lmb_avoidance_phase(lmb_ctx* ctx, const lmb_options* o, float dt);  // lmb_avoid_host.cu
+// lmb_avoid_host.cu
+int32_t lmb_avoidance_build_records(lmb_ctx* ctx, const lmb_options* o, uint32_t n_total, uint32_t first);
+int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first);
 
-int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
+extern "C" {
+
+int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
   if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
   if (!o) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step: null options");
@@ -776,20 +799,20 @@ int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
   AgentArrays ag = lmb_make_agent_arrays(ctx);
   AgentPersist persist = lmb_make_persist(ctx);
 
-  // keep the pool at most half full before the frame
+  cudaEventRecord(ctx->ev[2], s);
+  launch_reset_slots(ag, persist, make_pool(ctx), s);
+  // Bump allocation leaves dead corridors behind: once the cursor passes half the pool,
+  // compact the live ones (same capacity; run_astar grows it when more room is needed).
   {
     unsigned long long cursor = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     if (cursor * 2 > ctx->pool_capacity) {
-      st = grow_pool(ctx, ctx->pool_capacity);  // compacts; capacity at least doubles
+      st = grow_pool(ctx, ctx->pool_capacity);
       if (st != LMB_OK) return st;
     }
   }
-
-  cudaEventRecord(ctx->ev[2], s);
   // phase A: sample agents (skipped when paused / using a link), targets, characters
-  launch_reset_slots(ag, persist, make_pool(ctx), s);
   launch_sample_points(ctx->nav, *o, n, ag.position, ag.flags, LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK,
                        0, ctx->d_agent_point.p, ctx->d_agent_node.p, s);
   launch_sample_points(ctx->nav, *o, n, ag.target, ag.flags, LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK,
@@ -849,9 +872,47 @@ int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
   CUDA_TRY(ctx, cudaGetLastError());
   cudaEventRecord(ctx->ev[6], s);
 
-  // phase D
+  // phase D, first half: this rank's avoidance records into the halo buffer
+  if (first > n_total || n > n_total - first)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step_begin: agent range [%u,+%u) outside %u", first, n, n_total);
+  ctx->halo_total = n_total;
+  ctx->halo_first = first;
+  (void)dt;
   if (!(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE)) {
-    st = lmb_avoidance_phase(ctx, o, dt);
+    st = lmb_avoidance_build_records(ctx, o, n_total, first);
+    if (st != LMB_OK) return st;
+  }
+  cudaEventRecord(ctx->ev[10], s);
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the caller may now all-gather the halo buffer
+  ctx->step_open = true;
+  return LMB_OK;
+}
+
+int32_t lmb_halo_buffer(lmb_ctx* ctx, void** device_ptr, uint64_t* record_bytes, uint64_t* n_records) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->step_open) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_halo_buffer: no step in flight");
+  if (device_ptr) *device_ptr = ctx->d_records.p;
+  if (record_bytes) *record_bytes = sizeof(AvoidRecord);
+  if (n_records) *n_records = ctx->halo_total;
+  return LMB_OK;
+}
+
+int32_t lmb_step_end(lmb_ctx* ctx, const lmb_options* o, float dt) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->step_open) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step_end without lmb_step_begin");
+  if (!o) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step_end: null options");
+  ctx->step_open = false;
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  const uint32_t n = ctx->n_agents;
+  lmb_step_timings& T = ctx->timings;
+  AgentArrays ag = lmb_make_agent_arrays(ctx);
+  AgentPersist persist = lmb_make_persist(ctx);
+  int32_t st;
+  cudaEventRecord(ctx->ev[9], s);
+  // phase D, second half: grid over ALL records, ORCA for this rank's agents
+  if (!(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE)) {
+    st = lmb_avoidance_solve(ctx, o, dt, ctx->halo_total, ctx->halo_first);
     if (st != LMB_OK) return st;
   }
   cudaEventRecord(ctx->ev[7], s);
@@ -866,10 +927,24 @@ int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
   cudaEventElapsedTime(&T.repath_decide_ms, ctx->ev[3], ctx->ev[4]);
   cudaEventElapsedTime(&T.astar_ms, ctx->ev[4], ctx->ev[5]);
   cudaEventElapsedTime(&T.follow_ms, ctx->ev[5], ctx->ev[6]);
-  cudaEventElapsedTime(&T.avoidance_ms, ctx->ev[6], ctx->ev[7]);
-  cudaEventElapsedTime(&T.total_ms, ctx->ev[2], ctx->ev[8]);
+  float a1 = 0.0f, a2 = 0.0f;
+  cudaEventElapsedTime(&a1, ctx->ev[6], ctx->ev[10]);  // record building
+  cudaEventElapsedTime(&a2, ctx->ev[9], ctx->ev[7]);   // grid + solve
+  T.avoidance_ms = a1 + a2;
+  // device time of the step excluding whatever the caller did between begin and end (halo exchange)
+  float t1 = 0.0f, t2 = 0.0f;
+  cudaEventElapsedTime(&t1, ctx->ev[2], ctx->ev[10]);
+  cudaEventElapsedTime(&t2, ctx->ev[9], ctx->ev[8]);
+  T.total_ms = t1 + t2;
   ctx->last_n_results = n;
   return LMB_OK;
+}
+
+int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  int32_t st = lmb_step_begin(ctx, o, dt, ctx->n_agents, 0);
+  if (st != LMB_OK) return st;
+  return lmb_step_end(ctx, o, dt);
 }
 
 int32_t lmb_agents_download(lmb_ctx* ctx, const lmb_agents_out* out) {

@@ -107,8 +107,3 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
   return ctx->fail(LMB_ERR_CAPACITY, "avoidance scratch kept overflowing");
 }
 
-extern "C" int32_t lmb_avoidance_phase(lmb_ctx* ctx, const lmb_options* o, float dt) {
-  int32_t st = lmb_avoidance_build_records(ctx, o, ctx->n_agents, 0);
-  if (st != LMB_OK) return st;
-  return lmb_avoidance_solve(ctx, o, dt, ctx->n_agents, 0);
-}

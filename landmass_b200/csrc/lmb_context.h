@@ -115,7 +115,10 @@ struct lmb_ctx {
   uint32_t avoid_caps[5] = {64, 64, 128, 256, 256};  // neighbours, explore, border edges, cones, lines
 
   lmb_step_timings timings{};
-  cudaEvent_t ev[9]{};
+  cudaEvent_t ev[11]{};
+  uint32_t halo_total = 0, halo_first = 0;
+  bool step_open = false;
+  double path_len_estimate = 0.0;  // running mean corridor length, sizes the pool before A*
 
   int32_t fail(int32_t code, const char* fmt, ...) {
     char buf[512];
