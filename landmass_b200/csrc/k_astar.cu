@@ -46,18 +46,22 @@ __device__ __forceinline__ bool rev_le(const HeapEntry& x, const HeapEntry& y) {
 // the rest spills to the slot's global arena.  Entry = {cost, estimate, node index, state}.
 constexpr uint32_t SMEM_HEAP = 384;
 
+template <bool SPILL>
 struct Heap {
   uint4* sm;    // [SMEM_HEAP]
-  uint4* gm;    // global spill; entry i (>= SMEM_HEAP) at gm[i + 1]
+  uint4* gm;    // global spill (SPILL only); entry i (>= SMEM_HEAP) at gm[i + 1]
   uint32_t len;
-  __device__ __forceinline__ uint4 raw(uint32_t i) const { return i < SMEM_HEAP ? sm[i] : gm[i + 1]; }
   __device__ __forceinline__ HeapEntry get(uint32_t i) const {
-    uint4 v = raw(i);
+    uint4 v;
+    if (SPILL)
+      v = i < SMEM_HEAP ? sm[i] : gm[i + 1];
+    else
+      v = sm[i];
     return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w};
   }
   __device__ __forceinline__ void set(uint32_t i, const HeapEntry& e) {
     uint4 v = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, e.state);
-    if (i < SMEM_HEAP)
+    if (!SPILL || i < SMEM_HEAP)
       sm[i] = v;
     else
       gm[i + 1] = v;
@@ -109,6 +113,9 @@ struct Query {
 
 constexpr uint32_t ASTAR_WARPS = 8;  // warps per block; 4 blocks/SM -> 32 concurrent queries per SM
 
+// SPILL = false: the open list lives entirely in shared memory; a query whose open list
+// outgrows it is reported as status 4 and re-run by the SPILL = true variant.
+template <bool SPILL>
 __global__ void __launch_bounds__(ASTAR_WARPS * 32, 4)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
@@ -123,10 +130,11 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   uint8_t* slot_base = arena.base + (size_t)slot * arena.slot_stride;
   float* best = reinterpret_cast<float*>(slot_base);
   uint4* nodes = reinterpret_cast<uint4*>(slot_base + arena.nodes_offset);  // cost, state, prev, depth
-  Heap heap;
+  Heap<SPILL> heap;
   heap.sm = s_heap + (size_t)warp_in_block * SMEM_HEAP;
   heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
 
+  const uint32_t heap_cap = SPILL ? arena.heap_cap : SMEM_HEAP;
   const uint32_t ST_LINK0 = nav.n_edges;
   const uint32_t ST_START = nav.n_edges + nav.n_links;
   const uint32_t ST_END = ST_START + 1;
@@ -262,7 +270,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           float ncost = fadd(cur_cost_so_far, c);
           float est = fadd(ncost, 0.0f);
           if (!(best[ST_END] <= est)) {
-            if (n_nodes >= arena.node_cap || heap.len >= arena.heap_cap) {
+            if (n_nodes >= arena.node_cap || heap.len >= heap_cap) {
               overflow = true;
             } else {
               best[ST_END] = est;
@@ -297,7 +305,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               float c2 = __shfl_sync(0xffffffffu, ncost, src);
               float e2 = __shfl_sync(0xffffffffu, est, src);
               uint32_t s2 = __shfl_sync(0xffffffffu, nstate, src);
-              if (n_nodes >= arena.node_cap || heap.len >= arena.heap_cap) {
+              if (n_nodes >= arena.node_cap || heap.len >= heap_cap) {
                 overflow = true;
                 break;
               }
@@ -338,7 +346,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               float est = fadd(ncost, fmul(distance(hp, qu.end_point), cheapest));
               uint32_t s2 = ST_LINK0 + l;
               if (best[s2] <= est) continue;
-              if (n_nodes >= arena.node_cap || heap.len >= arena.heap_cap) {
+              if (n_nodes >= arena.node_cap || heap.len >= heap_cap) {
                 overflow = true;
                 break;
               }
@@ -350,7 +358,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           }
         }
         if (overflow) {
-          status = 2;
+          status = (!SPILL && n_nodes < arena.node_cap) ? 4 : 2;
           break;
         }
       }
@@ -417,6 +425,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         atomicAdd(&counters->path_nodes_total, (unsigned long long)path_len);
       } else if (status == 2) {
         atomicAdd(&counters->n_retry_arena, 1u);
+      } else if (status == 4) {
+        atomicAdd(&counters->n_retry_spill, 1u);
       } else {
         atomicAdd(&counters->n_retry_pool, 1u);
       }
@@ -438,21 +448,26 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
 }
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
+                  AStarCounters* counters, const uint32_t* type_raw, bool spill, cudaStream_t stream) {
   if (q.n == 0) return;
   const uint32_t warps_per_block = ASTAR_WARPS;
   const size_t smem = (size_t)ASTAR_WARPS * SMEM_HEAP * sizeof(uint4);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_astar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_astar<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
   uint32_t blocks = (slots + warps_per_block - 1) / warps_per_block;
   AStarArena a = arena;
   a.n_slots = blocks * warps_per_block <= arena.n_slots ? blocks * warps_per_block : arena.n_slots;
-  k_astar<<<blocks, warps_per_block * 32, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  if (spill)
+    k_astar<true><<<blocks, warps_per_block * 32, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  else
+    k_astar<false><<<blocks, warps_per_block * 32, smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
 }  // namespace lmb

@@ -483,13 +483,14 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
   unsigned long long done_total = 0, nodes_total = 0;
   const uint32_t* list = nullptr;
   uint32_t n_run = n;
+  bool spill = false;
   std::vector<uint32_t> h_status;
   for (int iter = 0; iter < 24; iter++) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(AStarCounters), s));
     AStarQueries qq = q;
     qq.n = n_run;
     qq.list = list;
-    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, s);
+    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, spill, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
@@ -498,16 +499,18 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     ctx->timings.path_nodes += ctx->h_counters->path_nodes_total;
     ctx->timings.kernel_launches += 1;
     uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
+    const uint32_t rs = ctx->h_counters->n_retry_spill;
     done_total += ctx->h_counters->n_done;
     nodes_total += ctx->h_counters->path_nodes_total;
     if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
-    if (ra == 0 && rp == 0) return LMB_OK;
+    if (ra == 0 && rp == 0 && rs == 0) return LMB_OK;
+    if (rs) spill = true;  // some open list outgrew shared memory: the retry uses the spilling variant
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);
     CUDA_TRY(ctx, cudaMemcpy(h_status.data(), q.out_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     std::vector<uint32_t> retry;
     for (uint32_t i = 0; i < n; i++)
-      if (h_status[i] == 2 || h_status[i] == 3) retry.push_back(i);
+      if (h_status[i] >= 2) retry.push_back(i);
     if (rp) {
       int32_t st = grow_pool(ctx, ctx->pool_capacity * 2);
       if (st != LMB_OK) return st;

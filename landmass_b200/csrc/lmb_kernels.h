@@ -40,7 +40,8 @@ struct AStarQueries {
   const uint32_t* permitted_kind;
   const uint32_t* slot;        // [n] agent slot to receive the path, or NULL
   // outputs
-  uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool overflow)
+  uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool
+                               //     overflow), 4 = retry with the spilling open list
   uint32_t* out_success;       // [n]
   uint32_t* out_explored;      // [n]
   uint32_t* out_path_off;      // [n] offset into the path pool
@@ -59,13 +60,14 @@ struct AStarCounters {  // device-resident
   unsigned int queue_head;
   unsigned int n_retry_arena;
   unsigned int n_retry_pool;
+  unsigned int n_retry_spill;
   unsigned int n_done;
   unsigned long long explored_total;
   unsigned long long path_nodes_total;
 };
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
+                  AStarCounters* counters, const uint32_t* type_raw, bool spill, cudaStream_t stream);
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
 // ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----

@@ -138,3 +138,24 @@ def test_full_step_with_avoidance(mesh_kind, n):
         ag["position"] = ag["position"] + oc["desired_velocity"] * np.float32(dt)
     moved = np.abs(oc["desired_velocity"]).max(axis=1) > 0
     assert moved.sum() > n // 2
+
+
+def test_find_paths_open_list_spills_shared_memory():
+    """Long queries on an open grid grow the open list past the shared-memory heap, so the
+    first pass reports them for the spilling kernel variant; results must still be exact."""
+    mesh = synth.grid_mesh(200, 200)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    rng = np.random.Generator(np.random.PCG64(3))
+    nq = 48
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    # force a few corner-to-corner queries
+    sp[:4] = [[0.5, 0.5, 0], [199.5, 0.5, 0], [0.5, 199.5, 0], [199.5, 199.5, 0]]
+    sn[:4] = [0, 199, 199 * 200, 200 * 200 - 1]
+    ep[:4] = sp[:4][::-1]
+    en[:4] = sn[:4][::-1]
+    g = gpu.find_paths(sn, sp, en, ep, path_capacity=1 << 20)
+    c = cpu.find_paths(sn, sp, en, ep, path_capacity=1 << 20)
+    for a, b, name in zip(g, c, ["success", "explored", "begin", "nodes", "portals"]):
+        assert np.array_equal(a, b), name
