@@ -732,26 +732,40 @@ struct KdTree3 {
 
 }  // namespace
 
-// apply_avoidance_to_agents (avoidance.rs:16-179)
-void apply_avoidance_to_agents(const NavData& nav, const std::vector<AgentIn>& agents,
+// Per-agent avoidance record: exactly what one agent contributes to every other agent's
+// avoidance (avoidance.rs:41-57).  Same 32-byte layout as the device halo record.
+void build_avoid_records(const std::vector<AgentIn>& agents, const std::vector<AgentPersist*>& persist,
+                         const std::vector<Sampled>& agent_node, const lmb_options& opt, AvoidRec* out) {
+  for (size_t i = 0; i < agents.size(); i++) {
+    AvoidRec r{};
+    r.valid = agent_node[i].valid ? 1u : 0u;
+    r.p = agent_node[i].point;
+    r.v = xy(agents[i].velocity);
+    r.radius = agents[i].radius;
+    r.responsibility = persist[i]->state == LMB_STATE_REACHED_TARGET
+                           ? opt.reached_destination_avoidance_responsibility
+                           : 1.0f;
+    out[i] = r;
+  }
+}
+
+// apply_avoidance_to_agents (avoidance.rs:16-179).  `records` holds ALL agents of the
+// archipelago (all ranks); this call solves for the agents [first, first + agents.size()).
+void apply_avoidance_to_agents(const NavData& nav, const std::vector<AvoidRec>& records, uint32_t first,
+                               const std::vector<AgentIn>& agents,
                                const std::vector<AgentPersist*>& persist,
                                const std::vector<Sampled>& agent_node,
                                const std::vector<CharacterIn>& characters, const lmb_options& opt,
                                float delta_time) {
   if (delta_time == 0.0f) delta_time = 1.0f;
   const size_t n = agents.size();
-  std::vector<DodgyAgent> dodgy(n);
   KdTree3 agent_tree, character_tree;
   float agent_max_radius = 0.0f;
-  for (size_t i = 0; i < n; i++) {
-    if (!agent_node[i].valid) continue;
-    V3 p = agent_node[i].point;
-    dodgy[i] = {xy(p), xy(agents[i].velocity), agents[i].radius,
-                persist[i]->state == LMB_STATE_REACHED_TARGET
-                    ? opt.reached_destination_avoidance_responsibility
-                    : 1.0f};
-    agent_tree.pts.push_back({{p.x, p.y, p.z}, (uint32_t)i});
-    agent_max_radius = std::fmax(agent_max_radius, agents[i].radius);
+  for (size_t g = 0; g < records.size(); g++) {
+    const AvoidRec& r = records[g];
+    if (!r.valid) continue;
+    agent_tree.pts.push_back({{r.p.x, r.p.y, r.p.z}, (uint32_t)g});
+    agent_max_radius = std::fmax(agent_max_radius, r.radius);
   }
   agent_tree.finish();
   std::vector<DodgyAgent> dodgy_chars(characters.size());
@@ -762,22 +776,24 @@ void apply_avoidance_to_agents(const NavData& nav, const std::vector<AgentIn>& a
     character_tree.pts.push_back({{p.x, p.y, p.z}, (uint32_t)i});
   }
   character_tree.finish();
+  auto dodgy_of = [&](uint32_t g) {
+    const AvoidRec& r = records[g];
+    return DodgyAgent{xy(r.p), r.v, r.radius, r.responsibility};
+  };
 
   float neighbourhood = agent_max_radius + opt.neighbourhood;
   float neighbourhood_squared = neighbourhood * neighbourhood;
-  // all agents see the same frame: results are written after the loop would be
-  // wrong — the reference writes current_desired_move in place, but no agent
-  // reads another agent's current_desired_move, so in-place is equivalent.
   for (size_t i = 0; i < n; i++) {
     if (!agent_node[i].valid) continue;
+    const uint32_t self_g = first + (uint32_t)i;
     V3 ap = agent_node[i].point;
     float q[3] = {ap.x, ap.y, ap.z};
     auto nearby_agents = agent_tree.within(q, neighbourhood_squared);
     auto nearby_chars = character_tree.within(q, neighbourhood_squared);
     std::vector<DodgyAgent> neighbours;
     for (auto& dn : nearby_agents) {
-      if (dn.second == i) continue;
-      const DodgyAgent& d = dodgy[dn.second];
+      if (dn.second == self_g) continue;
+      DodgyAgent d = dodgy_of(dn.second);
       float nh = opt.neighbourhood + d.radius;
       if (dn.first < nh * nh) neighbours.push_back(d);
     }
@@ -786,7 +802,7 @@ void apply_avoidance_to_agents(const NavData& nav, const std::vector<AgentIn>& a
     std::vector<Obstacle> obstacles =
         nav_mesh_borders_to_dodgy_obstacles(nav, ap, agent_node[i].node, opt.neighbourhood);
     V2 preferred = xy(persist[i]->desired_move);
-    V2 v = compute_avoiding_velocity(dodgy[i], neighbours, obstacles, preferred, agents[i].max_speed,
+    V2 v = compute_avoiding_velocity(dodgy_of(self_g), neighbours, obstacles, preferred, agents[i].max_speed,
                                      delta_time, 0.0f, opt.avoidance_time_horizon,
                                      opt.obstacle_avoidance_time_horizon);
     persist[i]->desired_move = {v.x, v.y, 0.0f};

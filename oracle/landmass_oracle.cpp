@@ -822,11 +822,12 @@ static bool has_reached_target(const AgentIn& a, const Path& path, const NavData
 // ---------------------------------------------------------------------------
 // Archipelago::update — lib.rs:270-534
 // ---------------------------------------------------------------------------
-void Ctx::step(const lmb_agents_in& in, const lmb_characters_in* chars, const lmb_options& opt,
-               float dt, const lmb_agents_out& out) {
+void Ctx::step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, const lmb_options& opt,
+                     float dt, uint32_t n_total, uint32_t first) {
   pathing_results.clear();
   const uint32_t n = in.n;
-  std::vector<AgentIn> ag(n);
+  f_agents.assign(n, AgentIn{});
+  std::vector<AgentIn>& ag = f_agents;
   for (uint32_t i = 0; i < n; i++) {
     AgentIn& a = ag[i];
     a.slot = in.slot[i];
@@ -852,7 +853,9 @@ void Ctx::step(const lmb_agents_in& in, const lmb_characters_in* chars, const lm
   auto st = [&](uint32_t i) -> AgentPersist& { return agent_state[ag[i].slot]; };
 
   // PHASE A: sample agents + targets (lib.rs:286-327)
-  std::vector<Sampled> agent_node(n), target_node(n);
+  f_agent_node.assign(n, Sampled{});
+  std::vector<Sampled>& agent_node = f_agent_node;
+  std::vector<Sampled> target_node(n);
   for (uint32_t i = 0; i < n; i++) {
     AgentPersist& s = st(i);
     if (ag[i].flags & LMB_AGENT_PAUSED) {
@@ -869,7 +872,8 @@ void Ctx::step(const lmb_agents_in& in, const lmb_characters_in* chars, const lm
       target_node[i].valid = nav.sample_point(ag[i].target, opt, target_node[i].point, target_node[i].node);
   }
   // PHASE A': characters (lib.rs:329-341)
-  std::vector<CharacterIn> ch(chars ? chars->n : 0);
+  f_chars.assign(chars ? chars->n : 0, CharacterIn{});
+  std::vector<CharacterIn>& ch = f_chars;
   for (uint32_t i = 0; i < ch.size(); i++) {
     ch[i].position = {chars->position[3 * i], chars->position[3 * i + 1], chars->position[3 * i + 2]};
     ch[i].velocity = {chars->velocity[3 * i], chars->velocity[3 * i + 1], chars->velocity[3 * i + 2]};
@@ -976,11 +980,23 @@ void Ctx::step(const lmb_agents_in& in, const lmb_characters_in* chars, const lm
     }
   }
 
-  // PHASE D: avoidance (lib.rs:525-533)
+  // PHASE D, first half: this rank's avoidance records into the halo buffer
+  halo.assign(n_total, AvoidRec{});
+  halo_first = first;
+  std::vector<AgentPersist*> persist(n);
+  for (uint32_t i = 0; i < n; i++) persist[i] = &st(i);
+  build_avoid_records(ag, persist, agent_node, opt, halo.data() + first);
+}
+
+void Ctx::step_end(const lmb_options& opt, float dt, const lmb_agents_out& out) {
+  std::vector<AgentIn>& ag = f_agents;
+  const uint32_t n = (uint32_t)ag.size();
+  auto st = [&](uint32_t i) -> AgentPersist& { return agent_state[ag[i].slot]; };
+  // PHASE D: avoidance (lib.rs:525-533) against every rank's records
   if (!(flags & LMB_CONFIG_NO_AVOIDANCE)) {
     std::vector<AgentPersist*> persist(n);
     for (uint32_t i = 0; i < n; i++) persist[i] = &st(i);
-    apply_avoidance_to_agents(nav, ag, persist, agent_node, ch, opt, dt);
+    apply_avoidance_to_agents(nav, halo, halo_first, ag, persist, f_agent_node, f_chars, opt, dt);
   }
 
   for (uint32_t i = 0; i < n; i++) {
@@ -1089,6 +1105,23 @@ int32_t orc_step(orc_ctx* h, const lmb_agents_in* agents, const lmb_characters_i
                  const lmb_options* options, float dt, const lmb_agents_out* out) {
   if (!h || !agents || !options || !out) return LMB_ERR_INVALID_ARGUMENT;
   h->c.step(*agents, characters, *options, dt, *out);
+  return LMB_OK;
+}
+int32_t orc_step_begin(orc_ctx* h, const lmb_agents_in* agents, const lmb_characters_in* characters,
+                       const lmb_options* options, float dt, uint32_t n_total, uint32_t first) {
+  if (!h || !agents || !options || first + agents->n > n_total) return LMB_ERR_INVALID_ARGUMENT;
+  h->c.step_begin(*agents, characters, *options, dt, n_total, first);
+  return LMB_OK;
+}
+int32_t orc_halo_buffer(orc_ctx* h, void** ptr, uint64_t* record_bytes, uint64_t* n_records) {
+  *ptr = h->c.halo.data();
+  *record_bytes = sizeof(orc::AvoidRec);
+  *n_records = h->c.halo.size();
+  return LMB_OK;
+}
+int32_t orc_step_end(orc_ctx* h, const lmb_options* options, float dt, const lmb_agents_out* out) {
+  if (!h || !options || !out) return LMB_ERR_INVALID_ARGUMENT;
+  h->c.step_end(*options, dt, *out);
   return LMB_OK;
 }
 int32_t orc_pathing_results(orc_ctx* h, lmb_pathing_result* out, uint32_t capacity,

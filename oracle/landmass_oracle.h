@@ -28,6 +28,12 @@ int32_t orc_find_paths(orc_ctx*, uint32_t n, const uint32_t* start_node, const f
 
 int32_t orc_step(orc_ctx*, const lmb_agents_in* agents, const lmb_characters_in* characters,
                  const lmb_options* options, float delta_time, const lmb_agents_out* out);
+/* multi-rank form of the step: begin (phases A-C + this rank's records) -> caller all-gathers the
+ * halo buffer (HOST memory here) -> end (phase D + outputs).  Same contract as lmb_step_begin/_end. */
+int32_t orc_step_begin(orc_ctx*, const lmb_agents_in* agents, const lmb_characters_in* characters,
+                       const lmb_options* options, float delta_time, uint32_t n_total, uint32_t first);
+int32_t orc_halo_buffer(orc_ctx*, void** host_ptr, uint64_t* record_bytes, uint64_t* n_records);
+int32_t orc_step_end(orc_ctx*, const lmb_options* options, float delta_time, const lmb_agents_out* out);
 int32_t orc_pathing_results(orc_ctx*, lmb_pathing_result* out, uint32_t capacity,
                             uint32_t* out_count);
 int32_t orc_agent_path(orc_ctx*, uint32_t slot, uint32_t* out_nodes, uint32_t* out_portals,

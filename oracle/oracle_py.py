@@ -45,6 +45,14 @@ def load():
         lib.orc_create.argtypes = [C.POINTER(_abi.NavDataDesc), C.c_uint32]
         lib.orc_destroy.restype = None
         lib.orc_destroy.argtypes = [C.c_void_p]
+        lib.orc_step_begin.restype = C.c_int32
+        lib.orc_step_begin.argtypes = [C.c_void_p, C.POINTER(_abi.AgentsIn), C.POINTER(_abi.CharactersIn),
+                                       C.POINTER(_abi.Options), C.c_float, C.c_uint32, C.c_uint32]
+        lib.orc_halo_buffer.restype = C.c_int32
+        lib.orc_halo_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_uint64)]
+        lib.orc_step_end.restype = C.c_int32
+        lib.orc_step_end.argtypes = [C.c_void_p, C.POINTER(_abi.Options), C.c_float, C.POINTER(_abi.AgentsOut)]
         lib.orc_astar_adjacency.restype = C.c_int32
         lib.orc_next_straight_point.restype = C.c_int32
         lib.orc_borders_to_obstacles.restype = C.c_int32
@@ -71,6 +79,26 @@ class OracleBackend(CBackend):
         else:
             self._check(self.lib.orc_navdata_upload(self.ctx, C.byref(desc)))
         del keep
+
+    # ---- multi-rank form (same contract as NativeBackend.step_begin / halo_buffer / step_end) ----
+    def step_begin_host(self, ag: dict, ch, options, dt: float, n_total: int, first: int):
+        a, self._ka = _abi.make_agents_in(ag)
+        c, self._kc = _abi.make_characters_in(ch)
+        self._n_local = a.n
+        self._check(self.lib.orc_step_begin(self.ctx, C.byref(a), C.byref(c), C.byref(options),
+                                            C.c_float(dt), C.c_uint32(n_total), C.c_uint32(first)))
+
+    def halo_numpy(self):
+        """The halo buffer as a writable (n_total, 8) float32 view of the oracle's host memory."""
+        p, rb, nr = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.orc_halo_buffer(self.ctx, C.byref(p), C.byref(rb), C.byref(nr)))
+        buf = (C.c_float * (nr.value * rb.value // 4)).from_address(p.value)
+        return np.ctypeslib.as_array(buf).reshape(nr.value, rb.value // 4)
+
+    def step_end_host(self, options, dt: float) -> dict:
+        o, out = _abi.make_agents_out(self._n_local)
+        self._check(self.lib.orc_step_end(self.ctx, C.byref(options), C.c_float(dt), C.byref(o)))
+        return out
 
     def next_straight_point(self, nodes, portals, start_index, start_point, end_index, end_point):
         nodes = _abi.as_u32(nodes)

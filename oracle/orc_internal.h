@@ -177,7 +177,16 @@ struct Obstacle {
 };
 std::vector<Obstacle> nav_mesh_borders_to_dodgy_obstacles(const NavData& nav, V3 agent_point,
                                                           uint32_t agent_node, float distance_limit);
-void apply_avoidance_to_agents(const NavData& nav, const std::vector<AgentIn>& agents,
+struct AvoidRec {  // 32 bytes, same layout as the device halo record
+  V3 p;
+  V2 v;
+  float radius, responsibility;
+  uint32_t valid;
+};
+void build_avoid_records(const std::vector<AgentIn>& agents, const std::vector<AgentPersist*>& persist,
+                         const std::vector<Sampled>& agent_node, const lmb_options& opt, AvoidRec* out);
+void apply_avoidance_to_agents(const NavData& nav, const std::vector<AvoidRec>& records, uint32_t first,
+                               const std::vector<AgentIn>& agents,
                                const std::vector<AgentPersist*>& persist,
                                const std::vector<Sampled>& agent_node,
                                const std::vector<CharacterIn>& characters, const lmb_options& opt,
@@ -188,8 +197,20 @@ struct Ctx {
   NavData nav;
   std::unordered_map<uint32_t, AgentPersist> agent_state;
   std::vector<lmb_pathing_result> pathing_results;
+  // frame state kept between step_begin and step_end (multi-rank form)
+  std::vector<AgentIn> f_agents;
+  std::vector<Sampled> f_agent_node;
+  std::vector<CharacterIn> f_chars;
+  std::vector<AvoidRec> halo;
+  uint32_t halo_first = 0;
+  void step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, const lmb_options& opt, float dt,
+                  uint32_t n_total, uint32_t first);
+  void step_end(const lmb_options& opt, float dt, const lmb_agents_out& out);
   void step(const lmb_agents_in& in, const lmb_characters_in* chars, const lmb_options& opt, float dt,
-            const lmb_agents_out& out);
+            const lmb_agents_out& out) {
+    step_begin(in, chars, opt, dt, in.n, 0);
+    step_end(opt, dt, out);
+  }
 };
 
 }  // namespace orc

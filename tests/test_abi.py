@@ -1,0 +1,81 @@
+"""The C-ABI library loads and exports every symbol include/landmass_b200.h declares, the ctypes
+mirror has the same struct layouts as the C header, and the product refuses to run without a GPU
+(no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+from landmass_b200 import _abi, _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "landmass_b200.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lmb_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_native._LIB_PATH), "run __graft_entry__.build() first"
+    lib = C.CDLL(_native._LIB_PATH)
+    declared = header_functions()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_native.EXPORTED_SYMBOLS) == set(declared)
+    lib.lmb_abi_version.restype = C.c_uint32
+    assert lib.lmb_abi_version() == _abi.ABI_VERSION
+
+
+def test_ctypes_layout_matches_header(tmp_path):
+    structs = {"lmb_options": _abi.Options, "lmb_navdata_desc": _abi.NavDataDesc,
+               "lmb_agents_in": _abi.AgentsIn, "lmb_characters_in": _abi.CharactersIn,
+               "lmb_agents_out": _abi.AgentsOut, "lmb_pathing_result": _abi.PathingResult,
+               "lmb_config": _abi.Config, "lmb_step_timings": _abi.StepTimings}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
+    for cname, py in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in py._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, py in structs.items():
+        assert int(out[cname]) == C.sizeof(py), cname
+        for fname, _ in py._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(py, fname).offset, f"{cname}.{fname}"
+
+
+def test_constants_match_header():
+    text = open(HEADER).read()
+    for name, value in [("LMB_ABI_VERSION", _abi.ABI_VERSION), ("LMB_AGENT_HAS_TARGET", _abi.AGENT_HAS_TARGET),
+                        ("LMB_AGENT_PAUSED", _abi.AGENT_PAUSED), ("LMB_AGENT_RESET", _abi.AGENT_RESET),
+                        ("LMB_AGENT_PERMIT_ALL_LINKS", _abi.AGENT_PERMIT_ALL_LINKS),
+                        ("LMB_CONFIG_NO_AVOIDANCE", _abi.CONFIG_NO_AVOIDANCE)]:
+        m = re.search(rf"#define {name} (\d+)u", text)
+        assert m and int(m.group(1)) == value, name
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_native.NativeError) as e:
+        _native.NativeBackend()
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_package_does_not_import_oracle():
+    code = "import sys; import landmass_b200, landmass_b200._native, landmass_b200.sharded, landmass_b200.synth; " \
+           "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported by the product'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
