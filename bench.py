@@ -186,6 +186,8 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
+    # keep stdout to the ONE JSON line: NCCL's banner / debug output goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch  # plumbing only: device selection, NCCL all-gather, barriers
 
     from landmass_b200 import _abi, synth
@@ -327,7 +329,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline(args)
         states = np.bincount(out["state"], minlength=9).tolist()
         line["state_histogram"] = states
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     gpu.close()
     if dist is not None:
         dist.barrier()
