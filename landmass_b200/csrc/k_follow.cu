@@ -489,10 +489,14 @@ __global__ void k_pool_set_cursor(PathPool pool, const uint32_t* new_off, uint32
     *pool.cursor = (unsigned long long)new_off[max_agents - 1] + pool.slot_path_len[max_agents - 1];
 }
 
-void launch_pool_compact(const PathPool& src, uint2* dst_entries, uint32_t max_agents, uint32_t* scan_tmp,
-                         cudaStream_t stream) {
+// step 1: new offsets (exclusive scan of the lengths) and the live total into *cursor
+void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, cudaStream_t stream) {
   launch_exclusive_scan(src.slot_path_len, scan_tmp, max_agents, stream);
   k_pool_set_cursor<<<1, 32, 0, stream>>>(src, scan_tmp, max_agents);
+}
+// step 2: copy every live path to its new offset in dst and update slot_path_off
+void launch_pool_copy(const PathPool& src, uint2* dst_entries, uint32_t max_agents, const uint32_t* scan_tmp,
+                      cudaStream_t stream) {
   uint32_t threads = 256, warps_per_block = threads / 32;
   k_pool_compact_copy<<<(max_agents + warps_per_block - 1) / warps_per_block, threads, 0, stream>>>(
       src, dst_entries, scan_tmp, max_agents);

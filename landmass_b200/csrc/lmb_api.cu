@@ -148,13 +148,15 @@ static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, u
   a.node_cap = node_cap;
   a.heap_cap = heap_cap;
   size_t best_bytes = ((size_t)a.n_states * 4 + 255) & ~(size_t)255;
+  size_t bits_bytes = ((((size_t)a.n_states + 31) / 32 + 1) * 4 + 255) & ~(size_t)255;
   size_t node_bytes = ((size_t)node_cap * 16 + 255) & ~(size_t)255;
   size_t heap_bytes = (((size_t)heap_cap + 2) * 16 + 255) & ~(size_t)255;
-  a.nodes_offset = best_bytes;
-  a.heap_offset = best_bytes + node_bytes;
-  a.slot_stride = best_bytes + node_bytes + heap_bytes;
+  a.bits_offset = best_bytes;
+  a.nodes_offset = best_bytes + bits_bytes;
+  a.heap_offset = best_bytes + bits_bytes + node_bytes;
+  a.slot_stride = best_bytes + bits_bytes + node_bytes + heap_bytes;
   a.n_slots = slots;
-  CUDA_TRY(ctx, ctx->d_arena.reserve(a.slot_stride * (size_t)slots));
+  CUDA_TRY(ctx, ctx->d_arena.reserve_exact(a.slot_stride * (size_t)slots));
   a.base = ctx->d_arena.p;
   launch_arena_init(a, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
@@ -431,8 +433,7 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   // ---- path pool: drop all paths ----
   if (ctx->pool_capacity == 0) {
     ctx->pool_capacity = std::max<unsigned long long>((unsigned long long)ctx->cfg.max_agents * 64ull, 1ull << 16);
-    CUDA_TRY(ctx, ctx->d_pool[0].reserve(ctx->pool_capacity));
-    ctx->pool_capacity = ctx->d_pool[0].cap;
+    CUDA_TRY(ctx, ctx->d_pool[0].reserve_exact(ctx->pool_capacity));
     ctx->pool_cur = 0;
   }
   launch_drop_all_paths(make_pool(ctx), ctx->cfg.max_agents, s);
@@ -445,20 +446,35 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
 // ---------------------------------------------------------------------------
 // A* driver shared by lmb_step and lmb_find_paths
 // ---------------------------------------------------------------------------
-static int32_t grow_pool(lmb_ctx* ctx, unsigned long long min_capacity) {
+// Path offsets are 32-bit: the pool never holds more than this many (node, portal) entries.
+static const unsigned long long POOL_MAX_ENTRIES = 0xFFFF0000ull;
+
+// Compacts the live corridors into a fresh buffer with room for `needed_free` more entries.
+// Bump allocation leaves dead corridors behind (dropped / replaced paths); this is the only
+// place they are reclaimed.  Exact-size allocation: the capacity does not creep.
+static int32_t compact_pool(lmb_ctx* ctx, unsigned long long needed_free) {
   cudaStream_t s = ctx->stream;
+  const uint32_t m = ctx->cfg.max_agents;
   int other = 1 - ctx->pool_cur;
-  // compacts the live paths into a fresh buffer of at least min_capacity entries
-  unsigned long long want = std::max<unsigned long long>(min_capacity, 1ull << 16);
-  ctx->d_pool[other].release();
-  CUDA_TRY(ctx, ctx->d_pool[other].reserve(want));
   PathPool src = make_pool(ctx);
-  launch_pool_compact(src, ctx->d_pool[other].p, ctx->cfg.max_agents, ctx->d_scan_tmp.p, s);
+  // live size = sum of path lengths (the scan also yields every path's new offset)
+  launch_pool_scan(src, m, ctx->d_scan_tmp.p, s);
+  unsigned long long live = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&live, ctx->d_pool_cursor.p, sizeof(live), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  unsigned long long want = std::max<unsigned long long>(live + needed_free, 1ull << 16);
+  if (want <= ctx->pool_capacity && live * 2 <= ctx->pool_capacity) want = ctx->pool_capacity;  // keep size
+  if (want > POOL_MAX_ENTRIES)
+    return ctx->fail(LMB_ERR_CAPACITY, "path pool would exceed %llu entries (live %llu + needed %llu)",
+                     POOL_MAX_ENTRIES, live, needed_free);
+  ctx->d_pool[other].release();
+  CUDA_TRY(ctx, ctx->d_pool[other].reserve_exact(want));
+  launch_pool_copy(src, ctx->d_pool[other].p, m, ctx->d_scan_tmp.p, s);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
   ctx->d_pool[ctx->pool_cur].release();
   ctx->pool_cur = other;
-  ctx->pool_capacity = ctx->d_pool[other].cap;
+  ctx->pool_capacity = want;
   return LMB_OK;
 }
 
@@ -468,15 +484,15 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
   CUDA_TRY(ctx, cudaMemsetAsync(q.out_status, 0, n * sizeof(uint32_t), s));
   // Make room for the expected corridors up front: a query that finishes its search but
   // cannot allocate its corridor has to be searched again.
+  double per_query = ctx->path_len_estimate > 0.0 ? ctx->path_len_estimate * 1.25 + 16.0
+                                                  : std::min(std::max(ctx->nav.n_polys / 4.0, 64.0), 131072.0);
+  unsigned long long needed = (unsigned long long)(per_query * n) + 1024;
   {
     unsigned long long cursor = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    double per_query = ctx->path_len_estimate > 0.0 ? ctx->path_len_estimate * 1.25 + 16.0
-                                                    : std::min(std::max(ctx->nav.n_polys / 8.0, 64.0), 65536.0);
-    unsigned long long want = cursor + (unsigned long long)(per_query * n) + 1024;
-    if (want > ctx->pool_capacity) {
-      int32_t st = grow_pool(ctx, want);
+    if (cursor + needed > ctx->pool_capacity) {
+      int32_t st = compact_pool(ctx, needed);
       if (st != LMB_OK) return st;
     }
   }
@@ -512,7 +528,8 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     for (uint32_t i = 0; i < n; i++)
       if (h_status[i] >= 2) retry.push_back(i);
     if (rp) {
-      int32_t st = grow_pool(ctx, ctx->pool_capacity * 2);
+      needed *= 2;
+      int32_t st = compact_pool(ctx, needed);
       if (st != LMB_OK) return st;
     }
     if (ra) {
@@ -804,17 +821,6 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
 
   cudaEventRecord(ctx->ev[2], s);
   launch_reset_slots(ag, persist, make_pool(ctx), s);
-  // Bump allocation leaves dead corridors behind: once the cursor passes half the pool,
-  // compact the live ones (same capacity; run_astar grows it when more room is needed).
-  {
-    unsigned long long cursor = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if (cursor * 2 > ctx->pool_capacity) {
-      st = grow_pool(ctx, ctx->pool_capacity);
-      if (st != LMB_OK) return st;
-    }
-  }
   // phase A: sample agents (skipped when paused / using a link), targets, characters
   launch_sample_points(ctx->nav, *o, n, ag.position, ag.flags, LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK,
                        0, ctx->d_agent_point.p, ctx->d_agent_node.p, s);

@@ -30,6 +30,15 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
+  cudaError_t reserve_exact(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
   cudaError_t upload(const T* host, size_t n, cudaStream_t s) {
     cudaError_t e = reserve(n ? n : 1);
     if (e != cudaSuccess) return e;

@@ -20,6 +20,7 @@ struct AStarArena {
   uint32_t n_states;      // n_edges + n_links + 2
   uint32_t node_cap;      // nodes per slot
   uint32_t heap_cap;      // heap entries per slot
+  size_t bits_offset;     // byte offset of the touched bitmap inside a slot
   size_t nodes_offset;    // byte offset of the node array inside a slot
   size_t heap_offset;     // byte offset of the heap array inside a slot
 };
@@ -131,8 +132,9 @@ void launch_gather_outputs(const AgentArrays& ag, const AgentPersist& persist, f
 void launch_drop_all_paths(const PathPool& pool, uint32_t max_agents, cudaStream_t stream);
 
 // path pool compaction
-void launch_pool_compact(const PathPool& src, uint2* dst_entries, uint32_t max_agents, uint32_t* scan_tmp,
-                         cudaStream_t stream);
+void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, cudaStream_t stream);
+void launch_pool_copy(const PathPool& src, uint2* dst_entries, uint32_t max_agents, const uint32_t* scan_tmp,
+                      cudaStream_t stream);
 
 // ---- kernel 4: avoidance (k_avoid.cu) ----
 struct AvoidRecord {  // 32 B per sampled agent: the per-frame halo exchanged between GPUs
