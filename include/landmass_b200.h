@@ -322,6 +322,19 @@ int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, con
                        uint32_t* out_path_begin, uint32_t* out_nodes, uint32_t* out_portals,
                        uint32_t path_capacity);
 
+/* Batched `Archipelago::find_path` of the query API (query.rs:185-273): A* followed by the
+ * full straight path (repeated funnel).  Steps of query i are
+ * [out_step_begin[i], out_step_begin[i+1]); the first step is the start point.  Per step:
+ * out_kind = 0 Waypoint / 1 AnimationLink, out_points = 6 floats (waypoint xyz twice, or link
+ * start xyz + link end xyz), out_link = animation link id or LMB_NONE.  A failed query
+ * (FindPathError::NoPathFound) has out_success = 0 and no steps. */
+int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node,
+                                const float* start_point, const uint32_t* end_node,
+                                const float* end_point, const uint32_t* override_begin,
+                                const uint32_t* override_type, const float* override_cost,
+                                uint32_t* out_success, uint32_t* out_step_begin, uint32_t* out_kind,
+                                float* out_points, uint32_t* out_link, uint32_t step_capacity);
+
 int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out);
 
 #ifdef __cplusplus

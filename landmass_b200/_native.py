@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
     "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
+    "lmb_find_straight_paths",
 ]
 
 
@@ -63,6 +64,9 @@ def declare_prototypes(lib, prefix: str):
     fn("find_paths", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, _abi.f32p, _abi.u32p,
                            _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.u32p,
                            _abi.u32p, u32])
+    fn("find_straight_paths", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, _abi.f32p, _abi.u32p,
+                                    _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.f32p,
+                                    _abi.u32p, u32])
     fn("get_step_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
     fn("step_begin", i32, [vp, C.POINTER(_abi.Options), f32, u32, u32])
     fn("halo_buffer", i32, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
@@ -198,6 +202,46 @@ class CBackend:
                 continue
             self._check(st)
             return succ[:n], expl[:n], begin, nodes[:begin[n]], portals[:begin[n]]
+
+
+    def _overrides_csr(self, overrides, n):
+        if overrides is None:
+            return None, None, None
+        ob = np.zeros(n + 1, dtype=np.uint32)
+        tl, cl = [], []
+        for i, ov in enumerate(overrides):
+            for t, c in sorted((ov or {}).items()):
+                tl.append(t)
+                cl.append(c)
+            ob[i + 1] = len(tl)
+        return ob, np.array(tl + [0], dtype=np.uint32), np.array(cl + [0], dtype=np.float32)
+
+    def find_straight_paths(self, start_node, start_point, end_node, end_point, overrides=None):
+        """Batched query-API find_path: returns (success, step_begin, kind, points (k,6), link)."""
+        sn = _abi.as_u32(start_node)
+        en = _abi.as_u32(end_node)
+        sp = _abi.as_f32(start_point).reshape(-1, 3)
+        ep = _abi.as_f32(end_point).reshape(-1, 3)
+        n = len(sn)
+        ob, ot, oc = self._overrides_csr(overrides, n)
+        cap = max(1024, 64 * n)
+        while True:
+            succ = np.zeros(max(n, 1), dtype=np.uint32)
+            begin = np.zeros(n + 1, dtype=np.uint32)
+            kind = np.zeros(cap, dtype=np.uint32)
+            pts = np.zeros((cap, 6), dtype=np.float32)
+            link = np.zeros(cap, dtype=np.uint32)
+            st = self._f("find_straight_paths")(
+                self.ctx, n, _abi.ptr(sn, _abi.u32p), _abi.ptr(sp, _abi.f32p), _abi.ptr(en, _abi.u32p),
+                _abi.ptr(ep, _abi.f32p), _abi.ptr(ob, _abi.u32p), _abi.ptr(ot, _abi.u32p),
+                _abi.ptr(oc, _abi.f32p), _abi.ptr(succ, _abi.u32p), _abi.ptr(begin, _abi.u32p),
+                _abi.ptr(kind, _abi.u32p), _abi.ptr(pts, _abi.f32p), _abi.ptr(link, _abi.u32p), cap)
+            if st == _abi.ERR_CAPACITY:
+                cap = max(int(begin[n]), cap * 2)
+                continue
+            self._check(st)
+            k = int(begin[n])
+            return succ[:n], begin, kind[:k], pts[:k], link[:k]
 
 
 class NativeBackend(CBackend):

@@ -382,7 +382,8 @@ __device__ void lines_for_obstacle(const DodgyAgent& self, const ObstacleView& o
                                    bool& overflow) {
   if (ob.n < 2) return;
   const Scratch& s = *ob.s;
-  const float radius = fadd(self.radius, margin);
+  // clearance from obstacle edges = obstacle margin alone (see oracle/avoidance_oracle.cpp)
+  const float radius = margin;
   const float inv_th = fdiv(1.0f, time_horizon);
   const uint32_t n_edges = ob.closed ? ob.n : ob.n - 1;
   uint32_t node = ob.tail;  // obstacle vertex 0 = last loop element

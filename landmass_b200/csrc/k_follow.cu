@@ -410,6 +410,70 @@ k_follow(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool, AStarQ
   dm[2] = 0.0f;
 }
 
+// Batched `Archipelago::find_path` straight path (query.rs:218-272): repeated funnel calls from
+// the start of the corridor to its end.  One thread per query; steps are written to
+// [step_begin[i], step_begin[i] + step_count[i]).
+__global__ void __launch_bounds__(128)
+k_straight_paths(DevNav nav, PathPool pool, AStarQueries q, const uint32_t* __restrict__ step_begin,
+                 uint32_t* __restrict__ step_count, uint32_t* __restrict__ out_kind,
+                 float* __restrict__ out_points, uint32_t* __restrict__ out_link) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= q.n) return;
+  step_count[i] = 0;
+  if (!q.out_success[i]) return;
+  const uint32_t cap = step_begin[i + 1] - step_begin[i];
+  uint32_t base = step_begin[i], count = 0;
+  auto emit = [&](uint32_t kind, V3 a, V3 b, uint32_t link) {
+    if (count < cap) {
+      uint32_t k = base + count;
+      out_kind[k] = kind;
+      out_points[6 * (size_t)k + 0] = a.x;
+      out_points[6 * (size_t)k + 1] = a.y;
+      out_points[6 * (size_t)k + 2] = a.z;
+      out_points[6 * (size_t)k + 3] = b.x;
+      out_points[6 * (size_t)k + 4] = b.y;
+      out_points[6 * (size_t)k + 5] = b.z;
+      out_link[k] = link;
+    }
+    count++;
+  };
+  PathView path{pool.entries + q.out_path_off[i], q.out_path_len[i]};
+  V3 current_point{q.start_point[3 * (size_t)i], q.start_point[3 * (size_t)i + 1], q.start_point[3 * (size_t)i + 2]};
+  const V3 last_point{q.end_point[3 * (size_t)i], q.end_point[3 * (size_t)i + 1], q.end_point[3 * (size_t)i + 2]};
+  uint32_t current_index = 0;
+  const uint32_t last_index = path.len - 1;
+  emit(0u, current_point, current_point, LMB_NONE);
+  if (current_index == last_index) {
+    emit(0u, last_point, last_point, LMB_NONE);
+    step_count[i] = count;
+    return;
+  }
+  bool last_was_link = false;
+  while ((current_index != last_index || last_was_link) && count < cap) {
+    Step next;
+    current_index = find_next_point_in_straight_path(nav, path, current_index, current_point, last_index,
+                                                     last_point, next);
+    if (!next.is_link) {
+      current_point = next.point;
+      emit(0u, next.point, next.point, LMB_NONE);
+      last_was_link = false;
+    } else {
+      current_point = next.end_point;
+      emit(1u, next.point, next.end_point, next.link_id);
+      last_was_link = true;
+    }
+  }
+  step_count[i] = count;
+}
+
+void launch_straight_paths(const DevNav& nav, const PathPool& pool, const AStarQueries& q,
+                           const uint32_t* step_begin, uint32_t* step_count, uint32_t* out_kind,
+                           float* out_points, uint32_t* out_link, cudaStream_t stream) {
+  if (q.n)
+    k_straight_paths<<<(q.n + 127) / 128, 128, 0, stream>>>(nav, pool, q, step_begin, step_count, out_kind,
+                                                            out_points, out_link);
+}
+
 __global__ void k_gather_outputs(AgentArrays ag, AgentPersist persist, float* out_velocity,
                                  uint32_t* out_state, uint32_t* out_link_id, float* out_link_start,
                                  float* out_link_end) {

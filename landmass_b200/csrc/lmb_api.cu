@@ -682,6 +682,99 @@ int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, con
   return result;
 }
 
+int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node,
+                                const float* start_point, const uint32_t* end_node,
+                                const float* end_point, const uint32_t* override_begin,
+                                const uint32_t* override_type, const float* override_cost,
+                                uint32_t* out_success, uint32_t* out_step_begin, uint32_t* out_kind,
+                                float* out_points, uint32_t* out_link, uint32_t step_capacity) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
+  if (!out_step_begin) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_straight_paths: null argument");
+  out_step_begin[0] = 0;
+  if (n == 0) return LMB_OK;
+  if (!start_node || !start_point || !end_node || !end_point || !out_success)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_straight_paths: null argument");
+  for (uint32_t i = 0; i < n; i++)
+    if (start_node[i] >= ctx->nav.n_polys || end_node[i] >= ctx->nav.n_polys)
+      return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_straight_paths: node id out of range (query %u)", i);
+  if (override_begin)
+    for (uint32_t k = 0; k < override_begin[n]; k++)
+      if (!(override_cost[k] > 0.0f))  // FindPathError::NonPositiveTypeIndexCost (query.rs:204-208)
+        return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "non-positive type index cost override %u -> %f",
+                         override_type[k], override_cost[k]);
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  int32_t st = reserve_queries(ctx, n);
+  if (st != LMB_OK) return st;
+  CUDA_TRY(ctx, ctx->d_q_start_node.upload(start_node, n, s));
+  CUDA_TRY(ctx, ctx->d_q_end_node.upload(end_node, n, s));
+  CUDA_TRY(ctx, ctx->d_q_start_point.upload(start_point, 3 * (size_t)n, s));
+  CUDA_TRY(ctx, ctx->d_q_end_point.upload(end_point, 3 * (size_t)n, s));
+  AStarQueries q = make_queries(ctx, n);
+  if (override_begin) {
+    CUDA_TRY(ctx, ctx->d_override_begin.upload(override_begin, (size_t)n + 1, s));
+    CUDA_TRY(ctx, ctx->d_override_type.upload(override_type, override_begin[n], s));
+    CUDA_TRY(ctx, ctx->d_override_cost.upload(override_cost, override_begin[n], s));
+    q.override_begin = ctx->d_override_begin.p;
+    q.override_type = ctx->d_override_type.p;
+    q.override_cost = ctx->d_override_cost.p;
+  }
+  unsigned long long cursor0 = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&cursor0, ctx->d_pool_cursor.p, sizeof(cursor0), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  ctx->timings = lmb_step_timings{};
+  st = run_astar(ctx, q);
+  if (st != LMB_OK) return st;
+  std::vector<uint32_t> len(n), begin(n + 1), count(n);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_success, q.out_success, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(len.data(), q.out_path_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  uint64_t total_cap = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    begin[i] = (uint32_t)total_cap;
+    total_cap += out_success[i] ? 2ull * len[i] + 2 : 0;  // generous bound on the number of steps
+  }
+  begin[n] = (uint32_t)total_cap;
+  DevBuf<uint32_t> d_begin, d_count, d_kind, d_link;
+  DevBuf<float> d_points;
+  CUDA_TRY(ctx, d_begin.upload(begin, s));
+  CUDA_TRY(ctx, d_count.reserve(n));
+  CUDA_TRY(ctx, d_kind.reserve(total_cap + 1));
+  CUDA_TRY(ctx, d_link.reserve(total_cap + 1));
+  CUDA_TRY(ctx, d_points.reserve(6 * total_cap + 6));
+  launch_straight_paths(ctx->nav, make_pool(ctx), q, d_begin.p, d_count.p, d_kind.p, d_points.p, d_link.p, s);
+  CUDA_TRY(ctx, cudaGetLastError());
+  std::vector<uint32_t> kind(total_cap + 1), link(total_cap + 1);
+  std::vector<float> points(6 * total_cap + 6);
+  CUDA_TRY(ctx, cudaMemcpyAsync(count.data(), d_count.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(kind.data(), d_kind.p, total_cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(link.data(), d_link.p, total_cap * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(points.data(), d_points.p, 6 * total_cap * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pool_cursor.p, &cursor0, sizeof(cursor0), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    out_step_begin[i] = (uint32_t)total;
+    if (count[i] > begin[i + 1] - begin[i]) return ctx->fail(LMB_ERR_INTERNAL, "straight path of query %u truncated", i);
+    total += count[i];
+  }
+  out_step_begin[n] = (uint32_t)total;
+  if (total > step_capacity)
+    return ctx->fail(LMB_ERR_CAPACITY, "lmb_find_straight_paths: %llu steps do not fit capacity %u",
+                     (unsigned long long)total, step_capacity);
+  if (total && (!out_kind || !out_points || !out_link))
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_straight_paths: null outputs");
+  for (uint32_t i = 0; i < n; i++)
+    for (uint32_t k = 0; k < count[i]; k++) {
+      uint32_t src = begin[i] + k, dst = out_step_begin[i] + k;
+      out_kind[dst] = kind[src];
+      out_link[dst] = link[src];
+      for (int c = 0; c < 6; c++) out_points[6 * (size_t)dst + c] = points[6 * (size_t)src + c];
+    }
+  return LMB_OK;
+}
+
 // ---------------------------------------------------------------------------
 // the step
 // ---------------------------------------------------------------------------

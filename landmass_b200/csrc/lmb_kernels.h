@@ -129,6 +129,9 @@ void launch_follow(const DevNav& nav, const AgentArrays& ag, const AgentPersist&
 void launch_gather_outputs(const AgentArrays& ag, const AgentPersist& persist, float* out_velocity,
                            uint32_t* out_state, uint32_t* out_link_id, float* out_link_start,
                            float* out_link_end, cudaStream_t stream);
+void launch_straight_paths(const DevNav& nav, const PathPool& pool, const AStarQueries& q,
+                           const uint32_t* step_begin, uint32_t* step_count, uint32_t* out_kind,
+                           float* out_points, uint32_t* out_link, cudaStream_t stream);
 void launch_drop_all_paths(const PathPool& pool, uint32_t max_agents, cudaStream_t stream);
 
 // path pool compaction

@@ -436,7 +436,12 @@ void lines_for_obstacle(const DodgyAgent& self, const Obstacle& ob, float margin
                         std::vector<Line>& lines) {
   size_t n = ob.vertices.size();
   if (n < 2) return;
-  float radius = self.radius + margin;
+  // Clearance from obstacle edges is the obstacle margin alone, NOT the agent radius: landmass
+  // passes obstacle_margin = 0 because "the nav mesh is the valid region" (avoidance.rs:143-146)
+  // — an agent centre may touch a border.  Pinned by lib_test.rs:156-423, where agents of radius
+  // 0.5 in a 1-wide corridor keep their full desired velocity (tolerance 1e-7).
+  (void)self.radius;
+  float radius = margin;
   float inv_th = 1.0f / time_horizon;
   std::vector<ObVertex> vs(n);
   for (size_t i = 0; i < n; i++) {

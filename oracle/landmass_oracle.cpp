@@ -1101,6 +1101,69 @@ int32_t orc_find_paths(orc_ctx* h, uint32_t n, const uint32_t* start_node, const
   return status;
 }
 
+int32_t orc_find_straight_paths(orc_ctx* h, uint32_t n, const uint32_t* start_node,
+                                const float* start_point, const uint32_t* end_node,
+                                const float* end_point, const uint32_t* override_begin,
+                                const uint32_t* override_type, const float* override_cost,
+                                uint32_t* out_success, uint32_t* out_step_begin, uint32_t* out_kind,
+                                float* out_points, uint32_t* out_link, uint32_t step_capacity) {
+  // query.rs:185-273
+  Permitted all;
+  all.all = true;
+  uint32_t cursor = 0;
+  int32_t status = LMB_OK;
+  auto emit = [&](uint32_t kind, V3 a, V3 b, uint32_t link) {
+    if (cursor < step_capacity) {
+      out_kind[cursor] = kind;
+      float* p = out_points + 6 * (size_t)cursor;
+      p[0] = a.x; p[1] = a.y; p[2] = a.z; p[3] = b.x; p[4] = b.y; p[5] = b.z;
+      out_link[cursor] = link;
+    } else {
+      status = LMB_ERR_CAPACITY;
+    }
+    cursor++;
+  };
+  for (uint32_t i = 0; i < n; i++) {
+    out_step_begin[i] = cursor;
+    std::unordered_map<uint32_t, float> ov;
+    if (override_begin)
+      for (uint32_t k = override_begin[i]; k < override_begin[i + 1]; k++) {
+        if (!(override_cost[k] > 0.0f)) return LMB_ERR_INVALID_ARGUMENT;
+        ov[override_type[k]] = override_cost[k];
+      }
+    V3 sp{start_point[3 * i], start_point[3 * i + 1], start_point[3 * i + 2]};
+    V3 ep{end_point[3 * i], end_point[3 * i + 1], end_point[3 * i + 2]};
+    PathResult pr = find_path(h->c.nav, start_node[i], sp, end_node[i], ep, ov, all);
+    out_success[i] = pr.path ? 1 : 0;
+    if (!pr.path) continue;
+    const Path& path = *pr.path;
+    PathIndex current_index{0, 0};
+    V3 current_point = sp;
+    PathIndex last_index = path.last_index();
+    emit(0, sp, sp, LMB_NONE);
+    if (current_index == last_index) {
+      emit(0, ep, ep, LMB_NONE);
+      continue;
+    }
+    bool last_was_link = false;
+    while (!(current_index == last_index) || last_was_link) {
+      auto r = path.find_next_point_in_straight_path(h->c.nav, current_index, current_point, last_index, ep);
+      current_index = r.first;
+      if (!r.second.is_link) {
+        current_point = r.second.point;
+        emit(0, r.second.point, r.second.point, LMB_NONE);
+        last_was_link = false;
+      } else {
+        current_point = r.second.end_point;
+        emit(1, r.second.point, r.second.end_point, r.second.link_id);
+        last_was_link = true;
+      }
+    }
+  }
+  out_step_begin[n] = cursor;
+  return status;
+}
+
 int32_t orc_step(orc_ctx* h, const lmb_agents_in* agents, const lmb_characters_in* characters,
                  const lmb_options* options, float dt, const lmb_agents_out* out) {
   if (!h || !agents || !options || !out) return LMB_ERR_INVALID_ARGUMENT;

@@ -1,0 +1,99 @@
+"""Funnel / straight-path known answers — transcribed from crates/landmass/src/path_test.rs:59-243
+(explicit corridors on rotated islands; oracle only, the C ABI takes no hand-made corridors) and
+query_test.rs:273-327 (`Archipelago::find_path` across three islands; oracle and CUDA)."""
+import math
+
+import numpy as np
+import pytest
+
+from landmass_b200 import XY, XYZ, Island, Transform, _abi
+from landmass_b200.nav_data import transform_apply
+from tests.golden import meshes
+from tests.helpers import new_archipelago, valid_mesh
+
+ZIGZAG = dict(
+    vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (1.0, 2.0), (0.0, 2.0), (1.0, 3.0), (0.0, 3.0),
+              (1.0, 4.0), (0.0, 4.0), (1.0, 5.0), (2.0, 4.0), (2.0, 5.0), (3.0, 4.0), (3.0, 5.0), (4.0, 4.0),
+              (4.0, 5.0), (5.0, 5.0), (5.0, 6.0), (4.0, 6.0), (5.0, 7.0), (4.0, 7.0), (4.0, 8.0), (-3.0, 8.0),
+              (-3.0, 7.0), (-4.0, 8.0), (-3.0, 15.0), (-4.0, 15.0)],
+    polygons=[[0, 1, 2, 3], [3, 2, 4, 5], [5, 4, 6, 7], [7, 6, 8, 9], [9, 8, 10], [10, 8, 11, 12],
+              [12, 11, 13, 14], [14, 13, 15, 16], [16, 15, 17], [16, 17, 18, 19], [19, 18, 20, 21],
+              [21, 20, 22], [21, 22, 23, 24], [24, 23, 25], [25, 23, 26, 27]],
+    polygon_type_indices=[0] * 15)
+
+
+def collect_straight_path(backend, nodes, portals, start, end, limit):
+    """path_test.rs:19-57"""
+    out = []
+    cur_index, cur_point = start
+    it = 0
+    while cur_index != end[0] and it < limit:
+        it += 1
+        idx, kind, pt = backend.next_straight_point(nodes, portals, cur_index, cur_point, end[0], end[1])
+        assert kind == 0
+        out.append((idx, pt[:3].copy()))
+        cur_index, cur_point = idx, pt[:3].copy()
+    return out
+
+
+@pytest.fixture
+def oracle_backend():
+    from oracle.oracle_py import OracleBackend
+
+    b = OracleBackend()
+    yield b
+    b.close()
+
+
+def test_finds_next_point_for_organic_map(oracle_backend):  # path_test.rs:59-134
+    t = np.array([5.0, 9.0, 7.0], dtype=np.float32)
+    rot = np.float32(math.pi) * np.float32(-0.35)
+    arch = new_archipelago(oracle_backend)
+    i = arch.add_island(Island(Transform(tuple(t), float(rot)), valid_mesh(meshes.ORGANIC)))
+    arch._sync_navdata()
+    ap = lambda p: transform_apply(t, rot, np.array(p, dtype=np.float32))
+    nodes = [arch.node_id(i, 0), arch.node_id(i, 1), arch.node_id(i, 2)]
+    portals = [4, 2, _abi.NONE]
+    got = collect_straight_path(oracle_backend, nodes, portals, (0, ap((3.0, 1.5, 0.0))),
+                                (2, ap((2.5, 4.5, 0.5))), 3)
+    exp = [(0, ap((2.0, 3.0, 0.0))), (1, ap((2.0, 4.0, 0.0))), (2, ap((2.5, 4.5, 0.5)))]
+    assert [g[0] for g in got] == [e[0] for e in exp]
+    for g, e in zip(got, exp):
+        np.testing.assert_allclose(g[1], e[1], rtol=0, atol=2e-6)
+
+
+def test_finds_next_point_in_zig_zag(oracle_backend):  # path_test.rs:136-243
+    t = np.array([-1.0, -3.0, 0.0], dtype=np.float32)
+    rot = np.float32(math.pi) * np.float32(-1.8)
+    arch = new_archipelago(oracle_backend, cs=XY)
+    i = arch.add_island(Island(Transform((-1.0, -3.0), float(rot)), valid_mesh(ZIGZAG, cs=XY)))
+    arch._sync_navdata()
+    ap = lambda p: transform_apply(t, rot, np.array(p, dtype=np.float32))
+    nodes = [arch.node_id(i, k) for k in range(15)]
+    portals = [2, 2, 2, 2, 1, 2, 2, 2, 2, 2, 2, 2, 2, 1, _abi.NONE]
+    got = collect_straight_path(oracle_backend, nodes, portals, (0, ap((0.5, 0.5, 0.0))),
+                                (14, ap((-3.5, 14.0, 0.0))), 5)
+    exp = [(4, ap((1.0, 4.0, 0.0))), (8, ap((4.0, 5.0, 0.0))), (11, ap((4.0, 7.0, 0.0))),
+           (13, ap((-3.0, 8.0, 0.0))), (14, ap((-3.5, 14.0, 0.0)))]
+    assert [g[0] for g in got] == [e[0] for e in exp]
+    for g, e in zip(got, exp):
+        np.testing.assert_allclose(g[1], e[1], rtol=0, atol=4e-6)
+
+
+def test_query_finds_path_across_islands(make_backend):  # query_test.rs:272-327
+    arch = new_archipelago(make_backend(), cs=XY)
+    mesh = valid_mesh(dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)],
+                           polygons=[[0, 1, 2, 3]], polygon_type_indices=[0]), cs=XY)
+    off = np.array([10.0, 10.0], dtype=np.float32)
+    arch.add_island(Island(Transform(tuple(off), 0.0), mesh))
+    arch.add_island(Island(Transform(tuple(off + np.float32([1.0, 0.0])), 0.0), mesh))
+    arch.add_island(Island(Transform(tuple(off + np.float32([2.0, 0.5])), 0.0), mesh))
+    start = arch.sample_point(tuple(off + np.float32([0.5, 0.5])), np.float32(1e-5))
+    end = arch.sample_point(tuple(off + np.float32([2.5, 1.25])), np.float32(1e-5))
+    assert start is not None and end is not None
+    sn, en = arch.node_id(*start[1]), arch.node_id(*end[1])
+    sp, ep = XY.to_landmass(start[0]), XY.to_landmass(end[0])
+    succ, begin, kind, pts, link = arch.backend.find_straight_paths([sn], [sp], [en], [ep])
+    assert succ[0] == 1 and list(kind) == [0, 0, 0]
+    got = [tuple(float(x) for x in p[:2]) for p in pts]
+    assert got == [(10.5, 10.5), (12.0, 11.0), (12.5, 11.25)]

@@ -159,3 +159,21 @@ def test_find_paths_open_list_spills_shared_memory():
     c = cpu.find_paths(sn, sp, en, ep, path_capacity=1 << 20)
     for a, b, name in zip(g, c, ["success", "explored", "begin", "nodes", "portals"]):
         assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("mesh_kind", ["grid", "maze"])
+def test_straight_paths_bit_exact(mesh_kind):
+    """Batched query-API find_path (A* + repeated funnel): every waypoint bitwise equal."""
+    mesh = synth.grid_mesh(40, 40) if mesh_kind == "grid" else synth.maze_mesh(16)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    rng = np.random.Generator(np.random.PCG64(21))
+    nq = 200
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    g = gpu.find_straight_paths(sn, sp, en, ep)
+    c = cpu.find_straight_paths(sn, sp, en, ep)
+    assert np.array_equal(g[0], c[0]) and np.array_equal(g[1], c[1]) and np.array_equal(g[2], c[2])
+    assert np.array_equal(g[3].view(np.uint32), c[3].view(np.uint32))
+    assert np.array_equal(g[4], c[4])
+    assert (np.diff(g[1].astype(np.int64)) >= 2).all()
