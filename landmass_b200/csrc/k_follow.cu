@@ -257,71 +257,79 @@ __global__ void k_reset_slots(AgentArrays ag, AgentPersist persist, PathPool poo
 }
 
 // Phase A state writes (lib.rs:286-297) + phase B decision (lib.rs:345-424 minus the A* call).
+// One WARP per agent: the two corridor searches of does_agent_need_repath are linear scans
+// (path.rs:403-446) over corridors that reach tens of thousands of nodes on maze meshes, so the
+// lanes scan 32 consecutive entries at a time (coalesced) with a ballot.
 __global__ void __launch_bounds__(128)
 k_repath_decide(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool, RepathQueue queue,
                 FollowScratch scratch) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
   if (i >= ag.n) return;
   const uint32_t s = ag.slot[i];
   const uint32_t flags = ag.flags[i];
-  scratch.follow_start[i] = LMB_NONE;
-  scratch.follow_end[i] = LMB_NONE;
+  const uint32_t plen = pool.slot_path_len[s];
+  // decision: 0 none/keep, 1 follow, 2 repath  (lane-uniform)
+  uint32_t new_state = LMB_NONE;
+  bool clear_path = false, follow = false, repath = false;
+  uint32_t ai = LMB_NONE, ti = LMB_NONE;
+  const uint32_t agent_node = ag.agent_node[i], target_node = ag.target_node[i];
+  if (flags & LMB_AGENT_PAUSED) {
+    new_state = LMB_STATE_PAUSED;  // paths are only invalidated by a navdata upload, which drops them
+  } else if (flags & LMB_AGENT_USING_ANIMATION_LINK) {
+    new_state = LMB_STATE_USING_ANIMATION_LINK;
+  } else if (!(flags & LMB_AGENT_HAS_TARGET)) {  // does_agent_need_repath (agent.rs:425-475)
+    if (plen) {  // ClearPathNoTarget; DoNothing leaves the state untouched
+      new_state = LMB_STATE_IDLE;
+      clear_path = true;
+    }
+  } else if (agent_node == LMB_NONE) {
+    new_state = LMB_STATE_AGENT_NOT_ON_NAV_MESH;
+    clear_path = true;
+  } else if (target_node == LMB_NONE) {
+    new_state = LMB_STATE_TARGET_NOT_ON_NAV_MESH;
+    clear_path = true;
+  } else {
+    repath = true;
+    if (plen) {
+      const uint2* e = pool.entries + pool.slot_path_off[s];
+      // find_index_of_node: first match from the front (path.rs:403-420)
+      for (uint32_t base = 0; base < plen; base += 32) {
+        uint32_t k = base + lane;
+        uint32_t hit = __ballot_sync(0xffffffffu, k < plen && e[k].x == agent_node);
+        if (hit) {
+          ai = base + (uint32_t)__ffs(hit) - 1;
+          break;
+        }
+      }
+      if (ai != LMB_NONE) {
+        // find_index_of_node_rev: first match from the back (path.rs:426-446)
+        for (uint32_t end = plen; end > 0;) {
+          uint32_t base = end >= 32 ? end - 32 : 0;
+          uint32_t k = base + lane;
+          uint32_t hit = __ballot_sync(0xffffffffu, k < end && e[k].x == target_node);
+          if (hit) {
+            ti = base + 31u - (uint32_t)__clz(hit);
+            break;
+          }
+          end = base;
+        }
+        if (ti != LMB_NONE && !(ai > ti)) {
+          follow = true;  // FollowPath
+          repath = false;
+        }
+      }
+    }
+  }
+  if (lane != 0) return;
+  scratch.follow_start[i] = follow ? ai : LMB_NONE;
+  scratch.follow_end[i] = follow ? ti : LMB_NONE;
   scratch.presult[i] = 0;
   scratch.query_of_agent[i] = LMB_NONE;
   persist.reached_link_id[s] = LMB_NONE;  // current_animation_link = None (lib.rs:348)
-  if (flags & LMB_AGENT_PAUSED) {
-    persist.state[s] = LMB_STATE_PAUSED;
-    return;  // paths are only invalidated by a navdata upload, which drops them all
-  }
-  if (flags & LMB_AGENT_USING_ANIMATION_LINK) {
-    persist.state[s] = LMB_STATE_USING_ANIMATION_LINK;
-    return;
-  }
-  const uint32_t plen = pool.slot_path_len[s];
-  // does_agent_need_repath (agent.rs:425-475)
-  if (!(flags & LMB_AGENT_HAS_TARGET)) {
-    if (plen) {  // ClearPathNoTarget
-      persist.state[s] = LMB_STATE_IDLE;
-      pool.slot_path_len[s] = 0;
-    }
-    return;  // DoNothing leaves the state untouched
-  }
-  const uint32_t agent_node = ag.agent_node[i];
-  if (agent_node == LMB_NONE) {
-    persist.state[s] = LMB_STATE_AGENT_NOT_ON_NAV_MESH;
-    pool.slot_path_len[s] = 0;
-    return;
-  }
-  const uint32_t target_node = ag.target_node[i];
-  if (target_node == LMB_NONE) {
-    persist.state[s] = LMB_STATE_TARGET_NOT_ON_NAV_MESH;
-    pool.slot_path_len[s] = 0;
-    return;
-  }
-  if (plen) {
-    const uint2* e = pool.entries + pool.slot_path_off[s];
-    // find_index_of_node: first match from the front (path.rs:403-420)
-    uint32_t ai = LMB_NONE;
-    for (uint32_t k = 0; k < plen; k++)
-      if (e[k].x == agent_node) {
-        ai = k;
-        break;
-      }
-    if (ai != LMB_NONE) {
-      // find_index_of_node_rev: first match from the back (path.rs:426-446)
-      uint32_t ti = LMB_NONE;
-      for (uint32_t k = plen; k-- > 0;)
-        if (e[k].x == target_node) {
-          ti = k;
-          break;
-        }
-      if (ti != LMB_NONE && !(ai > ti)) {
-        scratch.follow_start[i] = ai;  // FollowPath
-        scratch.follow_end[i] = ti;
-        return;
-      }
-    }
-  }
+  if (new_state != LMB_NONE) persist.state[s] = new_state;
+  if (clear_path) pool.slot_path_len[s] = 0;
+  if (!repath) return;
   // NeedsRepath
   pool.slot_path_len[s] = 0;
   uint32_t qi = atomicAdd(queue.count, 1u);
@@ -576,7 +584,7 @@ void launch_reset_slots(const AgentArrays& ag, const AgentPersist& persist, cons
 void launch_repath_decide(const DevNav& nav, const AgentArrays& ag, const AgentPersist& persist,
                           const PathPool& pool, const RepathQueue& queue, const FollowScratch& scratch,
                           cudaStream_t stream) {
-  if (ag.n) k_repath_decide<<<blocks_for(ag.n, 128), 128, 0, stream>>>(nav, ag, persist, pool, queue, scratch);
+  if (ag.n) k_repath_decide<<<blocks_for(ag.n, 4), 128, 0, stream>>>(nav, ag, persist, pool, queue, scratch);
 }
 void launch_follow(const DevNav& nav, const AgentArrays& ag, const AgentPersist& persist,
                    const PathPool& pool, const AStarQueries& q, const FollowScratch& scratch,

@@ -485,8 +485,9 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
   // Make room for the expected corridors up front: a query that finishes its search but
   // cannot allocate its corridor has to be searched again.
   double per_query = ctx->path_len_estimate > 0.0 ? ctx->path_len_estimate * 1.25 + 16.0
-                                                  : std::min(std::max(ctx->nav.n_polys / 4.0, 64.0), 131072.0);
+                                                  : std::min(std::max(2.0 * std::sqrt((double)ctx->nav.n_polys), 64.0), 65536.0);
   unsigned long long needed = (unsigned long long)(per_query * n) + 1024;
+  needed = std::min(needed, POOL_MAX_ENTRIES / 2);  // first guess only; overflow doubles it
   {
     unsigned long long cursor = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,130 @@
+"""Runs the non-headline BASELINE.json configs at full size on one GPU, checks size-independent
+properties of the outputs (the oracle cannot run these sizes in reasonable time) and prints
+per-phase device timings.  Usage: python scripts/run_configs.py [3] [5] [1]"""
+import json
+import sys
+import time
+
+sys.path.insert(0, ".")
+import numpy as np
+
+from landmass_b200 import _abi, synth
+from landmass_b200._native import NativeBackend
+
+
+def timings(gpu):
+    T = gpu.step_timings()
+    return {"total_ms": T.total_ms, "sample_ms": T.sample_ms, "decide_ms": T.repath_decide_ms,
+            "astar_ms": T.astar_ms, "follow_ms": T.follow_ms, "avoidance_ms": T.avoidance_ms,
+            "n_repath": T.n_repath, "explored": T.explored_nodes, "path_nodes": T.path_nodes,
+            "launches": T.kernel_launches}
+
+
+def check_paths(gpu, flat, slots):
+    """Every stored corridor is a chain of polygons connected through the recorded portal edges."""
+    peb, nb = flat["poly_edge_begin"], flat["edge_neighbor"]
+    for s in slots:
+        nodes, portals = gpu.agent_path(int(s))
+        assert len(nodes) > 0
+        assert portals[-1] == _abi.NONE
+        for k in range(len(nodes) - 1):
+            assert nb[peb[nodes[k]] + portals[k]] == nodes[k + 1], "corridor not connected"
+
+
+def config3(n=1_000_000, frames=4):
+    """Open field 2048 x 2048 m as 256 x 256 quads of 8 m, 1M agents, antipodal targets."""
+    mesh = synth.grid_mesh(256, 256, cell=8.0)
+    flat = synth.single_island_flat(mesh)
+    rng = np.random.Generator(np.random.PCG64(synth.SEED))
+    pos, _ = synth.random_points_on_mesh(mesh, n, rng)
+    ag = synth.make_agents(mesh, n)
+    ag["position"] = pos
+    ag["target"] = np.stack([2048.0 - pos[:, 0], 2048.0 - pos[:, 1], pos[:, 2]], axis=1).astype(np.float32)
+    opts = synth.default_options()
+    gpu = NativeBackend(max_agents=n)
+    gpu.navdata_upload(flat)
+    out_rows = []
+    dt = 1.0 / 60.0
+    for f in range(frames):
+        t0 = time.perf_counter()
+        out = gpu.step(ag, None, opts, dt)
+        wall = time.perf_counter() - t0
+        row = timings(gpu)
+        row["wall_ms"] = wall * 1e3
+        row["frame"] = f
+        out_rows.append(row)
+        speed = np.linalg.norm(out["desired_velocity"][:, :2], axis=1)
+        assert np.isfinite(out["desired_velocity"]).all()
+        # RVO2's 3-D LP fallback can lose the max-speed bound to float cancellation when two
+        # OVERLAPPING neighbours give near-antiparallel constraints (random initial overlaps only)
+        over = int((speed > 2.0 * (1 + 1e-4)).sum())
+        row["over_max_speed"] = over
+        assert over <= n // 100, f"{over} agents exceed max_speed"
+        assert (out["state"] == 4).mean() > 0.99, np.bincount(out["state"], minlength=9)
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["velocity"] = out["desired_velocity"].copy()
+        ag["position"] = ag["position"] + out["desired_velocity"] * np.float32(dt)
+    check_paths(gpu, flat, range(0, n, n // 50))
+    steady = out_rows[-1]
+    print(json.dumps({"config": 3, "agents": n, "polygons": mesh.n_polys, "frames": out_rows,
+                      "steady_agent_updates_per_s": n / (steady["total_ms"] * 1e-3),
+                      "mean_speed": float(speed.mean())}))
+    gpu.close()
+
+
+def config5(n=10_000, frames=3, rooms=512):
+    """Repath storm on the 512 x 512-room maze: every agent draws a new target every frame."""
+    mesh = synth.maze_mesh(rooms)
+    flat = synth.single_island_flat(mesh)
+    ag = synth.make_agents(mesh, n)
+    opts = synth.default_options()
+    gpu = NativeBackend(max_agents=n)
+    gpu.navdata_upload(flat)
+    rng = np.random.Generator(np.random.PCG64(99))
+    rows = []
+    for f in range(frames):
+        out = gpu.step(ag, None, opts, 1.0 / 60.0)
+        row = timings(gpu)
+        row["frame"] = f
+        row["astar_queries_per_s"] = row["n_repath"] / (row["astar_ms"] * 1e-3) if row["astar_ms"] else 0
+        row["explored_per_s"] = row["explored"] / (row["astar_ms"] * 1e-3) if row["astar_ms"] else 0
+        rows.append(row)
+        pr = gpu.pathing_results_array()
+        assert len(pr) == row["n_repath"] and (pr[:, 1] == 1).all(), "perfect maze: every query succeeds"
+        assert (out["state"] == 4).mean() > 0.99
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["target"], _ = synth.random_points_on_mesh(mesh, n, rng)  # retarget everyone
+    check_paths(gpu, flat, range(0, n, n // 25))
+    print(json.dumps({"config": 5, "agents": n, "polygons": mesh.n_polys, "frames": rows}))
+    gpu.close()
+
+
+def config1():
+    """64 x 64 quad grid, 100 agents (the reference's CPU-runnable case) — GPU vs oracle exact."""
+    from oracle.oracle_py import OracleBackend
+
+    mesh = synth.grid_mesh(64, 64)
+    flat = synth.single_island_flat(mesh)
+    ag = synth.make_agents(mesh, 100)
+    opts = synth.default_options()
+    gpu, cpu = NativeBackend(max_agents=100), OracleBackend()
+    gpu.navdata_upload(flat)
+    cpu.navdata_upload(flat)
+    t_cpu = t_gpu = 0.0
+    for f in range(20):
+        t0 = time.perf_counter(); og = gpu.step(ag, None, opts, 1 / 60); t1 = time.perf_counter()
+        oc = cpu.step(ag, None, opts, 1 / 60); t2 = time.perf_counter()
+        t_gpu += t1 - t0; t_cpu += t2 - t1
+        assert np.array_equal(og["state"], oc["state"]) and gpu.pathing_results() == cpu.pathing_results()
+        np.testing.assert_allclose(og["desired_velocity"], oc["desired_velocity"], rtol=1e-4, atol=1e-6)
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["velocity"] = oc["desired_velocity"].copy()
+        ag["position"] = ag["position"] + oc["desired_velocity"] * np.float32(1 / 60)
+    print(json.dumps({"config": 1, "agents": 100, "frames": 20, "gpu_ms_per_frame_e2e": t_gpu / 20 * 1e3,
+                      "cpu_oracle_ms_per_frame": t_cpu / 20 * 1e3}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["1", "3", "5"]
+    for w in which:
+        {"1": config1, "3": config3, "5": config5}[w]()
