@@ -8,13 +8,14 @@ sm_100a); importing this package never imports anything from oracle/.
 from .archipelago import (Agent, AgentState, Archipelago, ArchipelagoOptions, Character,
                           PathingResult, PermittedAnimationLinks, ReachedAnimationLink,
                           TargetReachedCondition)
+from .anim_links import AnimationLink
 from .coords import XY, XYZ, CorePointSampleDistance, PointSampleDistance3d
 from .nav_data import Island, NavigationData, SetTypeIndexCostError, Transform
 from .nav_mesh import (HeightNavigationMesh, HeightPolygon, NavigationMesh, ValidationError,
                        ValidNavigationMesh)
 
 __all__ = [
-    "Agent", "AgentState", "Archipelago", "ArchipelagoOptions", "Character", "PathingResult",
+    "Agent", "AgentState", "AnimationLink", "Archipelago", "ArchipelagoOptions", "Character", "PathingResult",
     "PermittedAnimationLinks", "ReachedAnimationLink", "TargetReachedCondition", "XY", "XYZ",
     "CorePointSampleDistance", "PointSampleDistance3d", "Island", "NavigationData",
     "SetTypeIndexCostError", "Transform", "HeightNavigationMesh", "HeightPolygon",

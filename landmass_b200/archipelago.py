@@ -270,6 +270,18 @@ class Archipelago:
     def get_island_ids(self):
         return self.nav_data.get_island_ids()
 
+    def add_animation_link(self, link) -> Key:
+        return self.nav_data.add_animation_link(link)
+
+    def remove_animation_link(self, link_id: Key):
+        self.nav_data.remove_animation_link(link_id)
+
+    def get_animation_link(self, link_id: Key):
+        return self.nav_data.get_animation_link(link_id)
+
+    def get_animation_link_ids(self):
+        return self.nav_data.get_animation_link_ids()
+
     def set_type_index_cost(self, type_index: int, cost: float):
         self.nav_data.set_type_index_cost(type_index, cost)
 

@@ -172,6 +172,15 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
     }
     for (int o = 16; o > 0; o >>= 1) cheapest = fminf(cheapest, __shfl_xor_sync(0xffffffffu, cheapest, o));
 
+    // PermittedAnimationLinks::is_permitted (agent.rs:178-186)
+    auto is_kind_permitted = [&](uint32_t kind) {
+      if (!q.owner_flags || (q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS)) return true;
+      if (q.permitted_begin)
+        for (uint32_t m = q.permitted_begin[owner]; m < q.permitted_begin[owner + 1]; m++)
+          if (q.permitted_kind[m] == kind) return true;
+      return false;
+    };
+
     // --- are_nodes_connected (nav_data.rs:1022-1087) ---
     bool connected;
     {
@@ -181,7 +190,33 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       } else {
         uint32_t r1 = nav.node_region_number[qu.start_node], r2 = nav.node_region_number[qu.end_node];
         connected = r1 != LMB_NONE && r2 != LMB_NONE && nav.region_root[r1] == nav.region_root[r2];
-        // PossibleRegionLink BFS (animation links) is rejected at upload (LMB_ERR_UNSUPPORTED).
+        if (!connected && r1 != LMB_NONE && r2 != LMB_NONE && nav.n_possible_links) {
+          // BFS over region numbers through the permitted PossibleRegionLinks
+          // (nav_data.rs:1056-1086).  seen[] / queue[] borrow the (still empty) node arena.
+          uint32_t* seen = reinterpret_cast<uint32_t*>(nodes);
+          uint32_t* queue = seen + nav.n_region_numbers;
+          for (uint32_t r = lane; r < nav.n_region_numbers; r += 32) seen[r] = 0u;
+          __syncwarp();
+          uint32_t head = 0, tail = 0;
+          seen[r1] = 1u;
+          queue[tail++] = r1;
+          while (head < tail) {
+            uint32_t r = queue[head++];
+            if (r == r2) {
+              connected = true;
+              break;
+            }
+            for (uint32_t k = 0; k < nav.n_possible_links; k++) {
+              if (nav.possible_link_src[k] != r) continue;
+              if (!is_kind_permitted(nav.possible_link_kind[k])) continue;
+              uint32_t dst = nav.possible_link_dst[k];
+              if (seen[dst]) continue;
+              seen[dst] = 1u;
+              queue[tail++] = dst;
+            }
+          }
+          __syncwarp();
+        }
       }
     }
 
@@ -323,14 +358,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               if (!is_finite(cost_tab[nav.link_dst_type_dense[l]])) continue;
               float link_cost = 0.0f;
               if (nav.link_kind[l] == LMB_LINK_ANIMATION) {
-                bool permitted = true;
-                if (q.owner_flags && !(q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS)) {
-                  permitted = false;
-                  if (q.permitted_begin)
-                    for (uint32_t m = q.permitted_begin[owner]; m < q.permitted_begin[owner + 1]; m++)
-                      if (q.permitted_kind[m] == nav.link_anim_kind[l]) permitted = true;
-                }
-                if (!permitted) continue;
+                if (!is_kind_permitted(nav.link_anim_kind[l])) continue;
                 link_cost = nav.link_cost[l];
               }
               const float* pp = nav.link_portal + 6 * (size_t)l;

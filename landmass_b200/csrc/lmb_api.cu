@@ -167,9 +167,6 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
   if (!d || d->struct_size != sizeof(lmb_navdata_desc))
     return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_navdata_upload: bad descriptor (struct_size)");
-  if (d->n_possible_links != 0)
-    return ctx->fail(LMB_ERR_UNSUPPORTED,
-                     "animation links (PossibleRegionLink) are not supported on the device path yet");
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   cudaStreamSynchronize(s);
@@ -378,6 +375,9 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   UP(d_modified_verts, d->modified_verts, d->n_modified ? 2 * (size_t)d->modified_vert_begin[d->n_modified] : 0);
   UPV(d_node_region_number, node_region_number);
   UP(d_region_root, d->region_root, d->n_region_numbers);
+  UP(d_possible_src, d->possible_link_src, d->n_possible_links);
+  UP(d_possible_dst, d->possible_link_dst, d->n_possible_links);
+  UP(d_possible_kind, d->possible_link_kind, d->n_possible_links);
 #undef UP
 #undef UPV
   nav.islands = ctx->d_islands.p;
@@ -417,12 +417,16 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   nav.modified_verts = ctx->d_modified_verts.p;
   nav.node_region_number = ctx->d_node_region_number.p;
   nav.region_root = ctx->d_region_root.p;
-  nav.n_possible_links = 0;
+  nav.n_possible_links = d->n_possible_links;
+  nav.n_region_numbers = d->n_region_numbers;
+  nav.possible_link_src = ctx->d_possible_src.p;
+  nav.possible_link_dst = ctx->d_possible_dst.p;
+  nav.possible_link_kind = ctx->d_possible_kind.p;
 
   // ---- A* arenas ----
   uint32_t n_states = nav.n_edges + nav.n_links + 2;
   uint32_t slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 32;
-  uint32_t node_cap = std::max<uint32_t>(n_states + 64, 256);
+  uint32_t node_cap = std::max<uint32_t>(std::max<uint32_t>(n_states + 64, 256), d->n_region_numbers / 2 + 64);
   uint32_t heap_cap = std::max<uint32_t>(n_states / 4 + 64, 256);
   size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)80 << 30);
   size_t per_slot = (size_t)n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;

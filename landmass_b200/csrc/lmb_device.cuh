@@ -165,7 +165,7 @@ struct DevNav {
   // regions
   const uint32_t* node_region_number;
   const uint32_t* region_root;
-  uint32_t n_possible_links;
+  uint32_t n_possible_links, n_region_numbers;
   const uint32_t* possible_link_src;
   const uint32_t* possible_link_dst;
   const uint32_t* possible_link_kind;

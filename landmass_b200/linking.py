@@ -96,7 +96,8 @@ def _boundary_world_edges(m, wv):
     return left, right
 
 
-def link_islands(nav_data, edge_link_distance):
+def link_islands(nav_data, edge_link_distance, animation_link_distance=1.0):
+    from .anim_links import create_animation_off_mesh_links
     from .nav_data import ModifiedNode, OffMeshLink
 
     d = f32(edge_link_distance)
@@ -158,12 +159,15 @@ def link_islands(nav_data, edge_link_distance):
         a._pair = b
         b._pair = a
         flat_links.extend([a, b])
+    for l in create_animation_off_mesh_links(nav_data, animation_link_distance):
+        l._pair = None
+        flat_links.append(l)
     order = sorted(range(len(flat_links)), key=lambda i: (dense[flat_links[i].src_island],
                                                           flat_links[i].src_polygon, i))
     out_links = [flat_links[i] for i in order]
     index_of = {id(l): i for i, l in enumerate(out_links)}
     for l in out_links:
-        l.reverse = index_of[id(l._pair)]
+        l.reverse = index_of[id(l._pair)] if l._pair is not None else -1
 
     modified = _modified_nodes(nav_data, items, world, out_links, d)
     regions = _update_regions(items, out_links)

@@ -114,6 +114,7 @@ class NavigationData:
     def __init__(self, cs=XYZ):
         self.cs = cs
         self.islands = DenseSlotMap()
+        self.animation_links = DenseSlotMap()
         self.type_index_to_cost: dict[int, float] = {}
         self.dirty = False
         self.links: list[OffMeshLink] = []
@@ -136,6 +137,20 @@ class NavigationData:
     def get_island_ids(self):
         return self.islands.keys()
 
+    def add_animation_link(self, link) -> Key:
+        self.dirty = True
+        return self.animation_links.insert(link)
+
+    def remove_animation_link(self, link_id: Key):
+        self.dirty = True
+        self.animation_links.remove(link_id)
+
+    def get_animation_link(self, link_id: Key):
+        return self.animation_links.get(link_id)
+
+    def get_animation_link_ids(self):
+        return self.animation_links.keys()
+
     def set_type_index_cost(self, type_index: int, cost: float):
         if cost <= 0.0:
             raise SetTypeIndexCostError(f"NonPositiveCost({cost})")
@@ -153,7 +168,8 @@ class NavigationData:
         self.dirty = False
         for island in self.islands.values():
             island.dirty = False
-        self.links, self.modified_nodes, self._regions = link_islands(self, edge_link_distance)
+        self.links, self.modified_nodes, self._regions = link_islands(self, edge_link_distance,
+                                                                      animation_link_distance)
         self.generation += 1
         return True
 
