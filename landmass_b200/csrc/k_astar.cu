@@ -1,4 +1,4 @@
-// Kernel 2 — batched A*, one query per warp.
+// Kernel 2 — batched A*, one query per THREAD, persistent lanes pulling from a queue.
 //
 // Replaces `pathfinding::find_path` + `ArchipelagoPathProblem` + `astar::find_path`
 // (crates/landmass/src/pathfinding.rs:19-382, astar.rs:126-206).
@@ -7,16 +7,32 @@
 // The open list is therefore NOT a bucketed queue: it is an exact emulation of Rust's
 // std `BinaryHeap<Reverse<NodeRef>>` (push = sift_up, pop = sift_down_to_bottom +
 // sift_up) with the reference's comparator, including the cost-vs-estimate quirk at
-// astar.rs:71.  What the warp parallelises is everything around
-// it: the successors of an expansion are evaluated one per lane (one 32-byte EdgeRec
-// sector per lane: midpoint, twin state, neighbour type), their `best_estimates`
-// probes are issued together, and accepted successors are pushed in ascending edge
-// order via a ballot.
+// astar.rs:71.
 //
-// State space (pathfinding.rs:55-69): NodeEdge{node, start_edge} = global edge id,
-// OffMeshLink(l) = n_edges + l, Start = n_edges + n_links, End = Start + 1.
-// `best_estimates` (a HashMap in the reference) is a dense f32 array per warp slot,
-// kept at +inf between queries and restored by walking the query's node list.
+// Why a thread per query: the search is a serial chain of dependent memory round trips
+// (pop -> best[s] / edge records -> best[successor] -> push), so the only parallelism is
+// ACROSS queries, and the number of queries in flight is what hides the latency.  A lane
+// owns a query; the 32 lanes of a warp run 32 independent searches in lock-step through
+// the same pop / expand / push code.  Each lane is a small state machine
+// (IDLE -> SEARCH -> WALK -> FINISH -> IDLE) so that a lane that found its goal walks its
+// back-pointers (one dependent load per iteration, issued before and consumed after the
+// other lanes' expansion so it adds no latency) while its neighbours keep searching.
+//
+// Memory:
+//   * open list: the first AT_HEAP_SM entries of every lane's heap live in shared memory,
+//     interleaved by thread (entry i of thread t at [i * AT_THREADS + t], conflict-free for
+//     128-bit accesses); deeper entries spill in place to the lane's arena slot.
+//   * `best_estimates` (a HashMap in the reference): dense f32 array per slot, +inf between
+//     queries; restored by a warp-cooperative memset (or a scatter over the node list when
+//     the query touched little).
+//   * node list {state, prev}: append-only, 8 B per node, per slot.
+//   * state ids: NodeEdge{node, start_edge} = edge-record id (CSR edge id, or
+//     `poly << kshift | local edge` when every polygon has <= 8 edges so that the records of
+//     a polygon are addressable from the state id alone), OffMeshLink(l) = n_ids + l,
+//     Start = n_ids + n_links, End = Start + 1.
+//   * the corridor is written into the path pool as raw (state, next state) pairs by the
+//     walk; `k_path_fixup` translates them to (node id, portal code) afterwards, fully
+//     parallel.
 #include "lmb_device.cuh"
 #include "lmb_kernels.h"
 
@@ -25,247 +41,342 @@ namespace lmb {
 namespace {
 
 constexpr float F_INF = __builtin_huge_valf();
+constexpr uint32_t FULL = 0xffffffffu;
 
 struct HeapEntry {
   float cost, estimate;
   uint32_t index;
   uint32_t state;
+  uint32_t depth;
 };
 
 // NodeRef::partial_cmp (astar.rs:67-77) as `a <= b`
 __device__ __forceinline__ bool noderef_le(const HeapEntry& a, const HeapEntry& b) {
-  if (a.estimate < b.estimate) return true;
-  if (a.estimate > b.estimate) return false;
-  if (a.estimate == b.estimate) return b.estimate <= a.cost;
-  return false;
+  // Less, or Equal-estimates with Reverse(a.cost) <= Reverse(b.estimate); unordered (NaN) -> false
+  return (a.estimate < b.estimate) | ((a.estimate == b.estimate) & (b.estimate <= a.cost));
 }
 // Reverse<T>::le(x, y) = y.0 <= x.0
 __device__ __forceinline__ bool rev_le(const HeapEntry& x, const HeapEntry& y) { return noderef_le(y, x); }
 
-// Open list.  Entries [0, SMEM_HEAP) live in shared memory (one private region per warp),
-// the rest spills to the slot's global arena.  Entry = {cost, estimate, node index, state}.
-constexpr uint32_t SMEM_HEAP = 384;
-
-template <bool SPILL>
+// Open list.  The SP = false members touch shared memory only (valid while every index they
+// can reach is < AT_HEAP_SM); SP = true adds the in-place spill to the slot's arena.  The
+// caller picks per operation from the current length, so the common case carries no
+// per-access branch.
 struct Heap {
-  uint4* sm;    // [SMEM_HEAP]
-  uint4* gm;    // global spill (SPILL only); entry i (>= SMEM_HEAP) at gm[i + 1]
+  uint4* sm;      // this thread's column: entry i at sm[i * AT_THREADS]
+  uint32_t* smd;  // depth column
+  uint4* gm;      // spill: entry i (>= AT_HEAP_SM) at gm[i - AT_HEAP_SM]
+  uint32_t* gmd;
   uint32_t len;
+  template <bool SP>
   __device__ __forceinline__ HeapEntry get(uint32_t i) const {
     uint4 v;
-    if (SPILL)
-      v = i < SMEM_HEAP ? sm[i] : gm[i + 1];
-    else
-      v = sm[i];
-    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w};
+    uint32_t d;
+    if (!SP || i < AT_HEAP_SM) {
+      v = sm[i * AT_THREADS];
+      d = smd[i * AT_THREADS];
+    } else {
+      v = gm[i - AT_HEAP_SM];
+      d = gmd[i - AT_HEAP_SM];
+    }
+    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w, d};
   }
+  template <bool SP>
   __device__ __forceinline__ void set(uint32_t i, const HeapEntry& e) {
     uint4 v = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, e.state);
-    if (!SPILL || i < SMEM_HEAP)
-      sm[i] = v;
-    else
-      gm[i + 1] = v;
+    if (!SP || i < AT_HEAP_SM) {
+      sm[i * AT_THREADS] = v;
+      smd[i * AT_THREADS] = e.depth;
+    } else {
+      gm[i - AT_HEAP_SM] = v;
+      gmd[i - AT_HEAP_SM] = e.depth;
+    }
   }
-  __device__ __forceinline__ void sift_up(uint32_t start, uint32_t pos, const HeapEntry& hole) {
-    while (pos > start) {
+  template <bool SP>
+  __device__ __forceinline__ void sift_up(uint32_t pos, const HeapEntry& hole) {
+    while (pos > 0) {
       uint32_t parent = (pos - 1) >> 1;
-      HeapEntry p = get(parent);
+      HeapEntry p = get<SP>(parent);
       if (rev_le(hole, p)) break;
-      set(pos, p);
+      set<SP>(pos, p);
       pos = parent;
     }
-    set(pos, hole);
+    set<SP>(pos, hole);
+  }
+  template <bool SP>
+  __device__ __forceinline__ void push_t(const HeapEntry& e) {
+    uint32_t old_len = len++;
+    sift_up<SP>(old_len, e);
   }
   __device__ __forceinline__ void push(const HeapEntry& e) {
-    uint32_t old_len = len++;
-    sift_up(0, old_len, e);
+    if (len < AT_HEAP_SM)
+      push_t<false>(e);
+    else
+      push_t<true>(e);
   }
-  __device__ __forceinline__ HeapEntry pop() {
-    HeapEntry item = get(--len);
+  template <bool SP>
+  __device__ __forceinline__ HeapEntry pop_t() {
+    HeapEntry item = get<SP>(--len);
     if (len > 0) {
-      HeapEntry top = get(0);
+      HeapEntry top = get<SP>(0);
       HeapEntry hole = item;  // swap(item, data[0]); the hole element is the old last
       item = top;
       uint32_t end = len, pos = 0, child = 1;
-      while (end >= 2 && child <= end - 2) {
-        HeapEntry a = get(child), b = get(child + 1);
+      while (child + 1 < end) {  // child <= end - 2
+        HeapEntry a = get<SP>(child), b = get<SP>(child + 1);
         bool right = rev_le(a, b);
-        set(pos, right ? b : a);
+        set<SP>(pos, right ? b : a);
         pos = child + (right ? 1u : 0u);
         child = 2 * pos + 1;
       }
-      if (child == end - 1) {
-        set(pos, get(child));
+      if (child + 1 == end) {
+        set<SP>(pos, get<SP>(child));
         pos = child;
       }
-      sift_up(0, pos, hole);
+      sift_up<SP>(pos, hole);
     }
     return item;
   }
+  __device__ __forceinline__ HeapEntry pop() {
+    if (len <= AT_HEAP_SM) return pop_t<false>();
+    return pop_t<true>();
+  }
 };
 
-struct Query {
-  uint32_t start_node, end_node;
-  V3 start_point, end_point;
-};
+template <class T>
+__device__ __forceinline__ T sel4(uint32_t j, T a0, T a1, T a2, T a3) {
+  return j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
+}
+
+__device__ __forceinline__ EdgeRec ld_rec(const EdgeRec* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  EdgeRec r;
+  r.mx = __uint_as_float(a.x);
+  r.my = __uint_as_float(a.y);
+  r.mz = __uint_as_float(a.z);
+  r.twin = a.w;
+  r.poly = b.x;
+  r.first_edge = b.y;
+  r.info = b.z;
+  r.aux = b.w;
+  return r;
+}
+
+enum : uint32_t { PH_IDLE = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINISH = 3, PH_EXIT = 4 };
 
 }  // namespace
 
-constexpr uint32_t ASTAR_WARPS = 8;  // warps per block; 4 blocks/SM -> 32 concurrent queries per SM
-
-// SPILL = false: the open list lives entirely in shared memory; a query whose open list
-// outgrows it is reported as status 4 and re-run by the SPILL = true variant.
-template <bool SPILL>
-__global__ void __launch_bounds__(ASTAR_WARPS * 32, 4)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
-  __shared__ float s_cost[ASTAR_WARPS][LMB_MAX_TYPES];
-  extern __shared__ uint4 s_heap[];  // [ASTAR_WARPS][SMEM_HEAP]
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp_in_block = threadIdx.x >> 5;
-  const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-  if (slot >= arena.n_slots) return;
-  float* cost_tab = s_cost[warp_in_block];
+  extern __shared__ uint4 s_heap[];  // [AT_HEAP_SM][AT_THREADS] uint4, then the same shape of u32 depths
+  __shared__ float s_cost[LMB_MAX_TYPES];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31;
+  const uint32_t slot = blockIdx.x * AT_THREADS + tid;
+  for (uint32_t t = tid; t < nav.n_types; t += AT_THREADS) s_cost[t] = nav.type_cost[t];
+  __syncthreads();
 
-  uint8_t* slot_base = arena.base + (size_t)slot * arena.slot_stride;
-  float* best = reinterpret_cast<float*>(slot_base);
-  uint4* nodes = reinterpret_cast<uint4*>(slot_base + arena.nodes_offset);  // cost, state, prev, depth
-  Heap<SPILL> heap;
-  heap.sm = s_heap + (size_t)warp_in_block * SMEM_HEAP;
+  const uint32_t slot_c = slot < arena.n_slots ? slot : 0;  // out-of-range lanes never touch memory
+  uint8_t* const slot_base = arena.base + (size_t)slot_c * arena.slot_stride;
+  float* const best = reinterpret_cast<float*>(slot_base);
+  uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
+  Heap heap;
+  heap.sm = s_heap + tid;
+  heap.smd = reinterpret_cast<uint32_t*>(s_heap + (size_t)AT_HEAP_SM * AT_THREADS) + tid;
   heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
+  heap.gmd = reinterpret_cast<uint32_t*>(slot_base + arena.heapd_offset);
+  heap.len = 0;
 
-  const uint32_t heap_cap = SPILL ? arena.heap_cap : SMEM_HEAP;
-  const uint32_t ST_LINK0 = nav.n_edges;
-  const uint32_t ST_START = nav.n_edges + nav.n_links;
+  const EdgeRec* __restrict__ recs = nav.edges;
+  const uint32_t heap_cap = arena.heap_cap;
+  const uint32_t node_cap = arena.node_cap;
+  const uint32_t kshift = arena.kshift;
+  const uint32_t kmask = (1u << kshift) - 1u;
+  const uint32_t ST_LINK0 = arena.n_ids;
+  const uint32_t ST_START = arena.n_ids + nav.n_links;
   const uint32_t ST_END = ST_START + 1;
 
+  // ---- lane state ----
+  uint32_t phase = slot < arena.n_slots ? PH_IDLE : PH_EXIT;
+  uint32_t qid = 0, owner = 0, start_node = 0, end_node = 0;
+  V3 end_point{0.0f, 0.0f, 0.0f};
+  float cheapest = 1.0f;
+  uint32_t ov_begin = 0, ov_end = 0;  // this query's cost overrides
+  bool permit_all = true;
+  uint32_t n_nodes = 0, explored = 0, status = 1, success = 0;
+  uint32_t path_off = 0, path_len = 0;
+  // walk
+  uint32_t w_node = 0, w_next = 0, w_pos = 0;
+
+  // type cost: override -> archipelago -> 1.0 (pathfinding.rs:73-77)
+  auto cost_of = [&](uint32_t t) -> float {
+    float c = s_cost[t];
+    if (ov_begin != ov_end) {
+      const uint32_t raw = type_raw[t];
+      for (uint32_t k = ov_begin; k < ov_end; k++)
+        if (q.override_type[k] == raw) c = q.override_cost[k];
+    }
+    return c;
+  };
+  // PermittedAnimationLinks::is_permitted (agent.rs:178-186)
+  auto is_kind_permitted = [&](uint32_t kind) -> bool {
+    if (permit_all) return true;
+    if (q.permitted_begin)
+      for (uint32_t m = q.permitted_begin[owner]; m < q.permitted_begin[owner + 1]; m++)
+        if (q.permitted_kind[m] == kind) return true;
+    return false;
+  };
+  // first edge record / record count of a polygon
+  auto poly_span = [&](uint32_t poly, uint32_t& first, uint32_t& cnt) {
+    if (kshift) {
+      first = poly << kshift;
+      cnt = kmask + 1u;
+    } else {
+      first = nav.poly_edge_begin[poly];
+      cnt = nav.poly_edge_begin[poly + 1] - first;
+    }
+  };
+
   for (;;) {
-    uint32_t qi = 0;
-    if (lane == 0) qi = atomicAdd(&counters->queue_head, 1u);
-    qi = __shfl_sync(0xffffffffu, qi, 0);
-    if (qi >= q.n) break;
-    const uint32_t qid = q.list ? q.list[qi] : qi;
-    Query qu;
-    qu.start_node = q.start_node[qid];
-    qu.end_node = q.end_node[qid];
-    qu.start_point = {q.start_point[3 * (size_t)qid], q.start_point[3 * (size_t)qid + 1], q.start_point[3 * (size_t)qid + 2]};
-    qu.end_point = {q.end_point[3 * (size_t)qid], q.end_point[3 * (size_t)qid + 1], q.end_point[3 * (size_t)qid + 2]};
-    const uint32_t owner = q.owner ? q.owner[qid] : qid;
-
-    // --- per-query type costs: override -> archipelago -> 1.0 (pathfinding.rs:73-77) ---
-    for (uint32_t t = lane; t < nav.n_types; t += 32) cost_tab[t] = nav.type_cost[t];
-    __syncwarp();
-    if (q.override_begin) {
-      uint32_t ob = q.override_begin[owner], oe = q.override_begin[owner + 1];
-      for (uint32_t k = ob + lane; k < oe; k += 32) {
-        uint32_t raw = q.override_type[k];
-        for (uint32_t t = 0; t < nav.n_types; t++)
-          if (type_raw[t] == raw) cost_tab[t] = q.override_cost[k];
-      }
-      __syncwarp();
-    }
-    // cheapest_type_index_cost (pathfinding.rs:300-314)
-    float cheapest = 1.0f;
-    for (uint32_t t = lane; t < nav.n_types; t += 32) {
-      float c = cost_tab[t];
-      if (nav.type_registered[t] && is_finite(c) && c < cheapest) cheapest = c;
-    }
-    for (int o = 16; o > 0; o >>= 1) cheapest = fminf(cheapest, __shfl_xor_sync(0xffffffffu, cheapest, o));
-
-    // PermittedAnimationLinks::is_permitted (agent.rs:178-186)
-    auto is_kind_permitted = [&](uint32_t kind) {
-      if (!q.owner_flags || (q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS)) return true;
-      if (q.permitted_begin)
-        for (uint32_t m = q.permitted_begin[owner]; m < q.permitted_begin[owner + 1]; m++)
-          if (q.permitted_kind[m] == kind) return true;
-      return false;
-    };
-
-    // --- are_nodes_connected (nav_data.rs:1022-1087) ---
-    bool connected;
-    {
-      uint32_t i1 = nav.poly_island[qu.start_node], i2 = nav.poly_island[qu.end_node];
-      if (i1 == i2 && nav.poly_region[qu.start_node] == nav.poly_region[qu.end_node]) {
-        connected = true;
+    // =========================== IDLE: fetch and set up a query ===========================
+    if (phase == PH_IDLE) {
+      const uint32_t qi = atomicAdd(&counters->queue_head, 1u);
+      if (qi >= q.n) {
+        phase = PH_EXIT;
       } else {
-        uint32_t r1 = nav.node_region_number[qu.start_node], r2 = nav.node_region_number[qu.end_node];
-        connected = r1 != LMB_NONE && r2 != LMB_NONE && nav.region_root[r1] == nav.region_root[r2];
-        if (!connected && r1 != LMB_NONE && r2 != LMB_NONE && nav.n_possible_links) {
-          // BFS over region numbers through the permitted PossibleRegionLinks
-          // (nav_data.rs:1056-1086).  seen[] / queue[] borrow the (still empty) node arena.
-          uint32_t* seen = reinterpret_cast<uint32_t*>(nodes);
-          uint32_t* queue = seen + nav.n_region_numbers;
-          for (uint32_t r = lane; r < nav.n_region_numbers; r += 32) seen[r] = 0u;
-          __syncwarp();
-          uint32_t head = 0, tail = 0;
-          seen[r1] = 1u;
-          queue[tail++] = r1;
-          while (head < tail) {
-            uint32_t r = queue[head++];
-            if (r == r2) {
-              connected = true;
-              break;
-            }
-            for (uint32_t k = 0; k < nav.n_possible_links; k++) {
-              if (nav.possible_link_src[k] != r) continue;
-              if (!is_kind_permitted(nav.possible_link_kind[k])) continue;
-              uint32_t dst = nav.possible_link_dst[k];
-              if (seen[dst]) continue;
-              seen[dst] = 1u;
-              queue[tail++] = dst;
+        qid = q.list ? q.list[qi] : qi;
+        start_node = q.start_node[qid];
+        end_node = q.end_node[qid];
+        const V3 start_point{q.start_point[3 * (size_t)qid], q.start_point[3 * (size_t)qid + 1],
+                             q.start_point[3 * (size_t)qid + 2]};
+        end_point = {q.end_point[3 * (size_t)qid], q.end_point[3 * (size_t)qid + 1],
+                     q.end_point[3 * (size_t)qid + 2]};
+        owner = q.owner ? q.owner[qid] : qid;
+        ov_begin = ov_end = 0;
+        if (q.override_begin) {
+          ov_begin = q.override_begin[owner];
+          ov_end = q.override_begin[owner + 1];
+        }
+        permit_all = !q.owner_flags || (q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS);
+        // cheapest_type_index_cost (pathfinding.rs:300-314)
+        cheapest = 1.0f;
+        for (uint32_t t = 0; t < nav.n_types; t++) {
+          float c = cost_of(t);
+          if (nav.type_registered[t] && is_finite(c) && c < cheapest) cheapest = c;
+        }
+        // are_nodes_connected (nav_data.rs:1022-1087)
+        bool connected;
+        {
+          uint32_t i1 = nav.poly_island[start_node], i2 = nav.poly_island[end_node];
+          if (i1 == i2 && nav.poly_region[start_node] == nav.poly_region[end_node]) {
+            connected = true;
+          } else {
+            uint32_t r1 = nav.node_region_number[start_node], r2 = nav.node_region_number[end_node];
+            connected = r1 != LMB_NONE && r2 != LMB_NONE && nav.region_root[r1] == nav.region_root[r2];
+            if (!connected && r1 != LMB_NONE && r2 != LMB_NONE && nav.n_possible_links) {
+              // BFS over region numbers through the permitted PossibleRegionLinks
+              // (nav_data.rs:1056-1086).  seen[] / queue[] borrow the (still empty) node list.
+              uint32_t* seen = reinterpret_cast<uint32_t*>(nodes);
+              uint32_t* queue = seen + nav.n_region_numbers;
+              for (uint32_t r = 0; r < nav.n_region_numbers; r++) seen[r] = 0u;
+              uint32_t head = 0, tail = 0;
+              seen[r1] = 1u;
+              queue[tail++] = r1;
+              while (head < tail) {
+                uint32_t r = queue[head++];
+                if (r == r2) {
+                  connected = true;
+                  break;
+                }
+                for (uint32_t k = 0; k < nav.n_possible_links; k++) {
+                  if (nav.possible_link_src[k] != r) continue;
+                  if (!is_kind_permitted(nav.possible_link_kind[k])) continue;
+                  uint32_t dst = nav.possible_link_dst[k];
+                  if (seen[dst]) continue;
+                  seen[dst] = 1u;
+                  queue[tail++] = dst;
+                }
+              }
             }
           }
-          __syncwarp();
+        }
+        explored = 0;
+        success = 0;
+        status = 1;
+        path_off = path_len = 0;
+        n_nodes = 0;
+        heap.len = 0;
+        phase = PH_FINISH;
+        if (connected) {
+          // try_add_node(Start)
+          float est = fadd(0.0f, fmul(distance(start_point, end_point), cheapest));
+          if (!(F_INF <= est)) {
+            best[ST_START] = est;
+            nodes[0] = make_uint2(ST_START, LMB_NONE);
+            n_nodes = 1;
+            heap.push({0.0f, est, 0u, ST_START, 0u});
+            phase = PH_SEARCH;
+          }
         }
       }
     }
+    if (__all_sync(FULL, phase == PH_EXIT)) break;
 
-    uint32_t explored = 0, success = 0, status = 1;
-    uint32_t path_off = 0, path_len = 0;
-    uint32_t n_nodes = 0;
-    heap.len = 0;
+    // ============ WALK (part 1): issue this iteration's back-pointer load early ============
+    uint2 w_rec = make_uint2(0u, 0u);
+    if (phase == PH_WALK) w_rec = nodes[w_node];
 
-    if (connected) {
-      // try_add_node(Start)
-      {
-        float est = fadd(0.0f, fmul(distance(qu.start_point, qu.end_point), cheapest));
-        if (!(F_INF <= est)) {
-          best[ST_START] = est;
-          nodes[0] = make_uint4(__float_as_uint(0.0f), ST_START, LMB_NONE, 0u);
-          n_nodes = 1;
-          heap.push({0.0f, est, 0u, ST_START});
+    // =============================== SEARCH: one pop ===============================
+    if (phase == PH_SEARCH) {
+      if (heap.len == 0) {
+        phase = PH_FINISH;  // no path
+      } else {
+        // ---- peek the root and issue this expansion's first loads BEFORE the pop's sift work:
+        //      best[s] (stale test, HBM) and, with padded ids, the polygon's edge records (L2) ----
+        const uint32_t s = heap.sm[0].w;
+        const float best_s = __ldcg(best + s);
+        const bool is_edge = s < ST_LINK0;
+        EdgeRec r[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) r[j].twin = LMB_NONE, r[j].info = 0, r[j].mx = r[j].my = r[j].mz = 0.0f;
+        EdgeRec self;
+        self.poly = self.first_edge = self.info = 0;
+        self.mx = self.my = self.mz = 0.0f;
+        uint32_t first = 0, cnt = 0;
+        const bool preloaded = is_edge && kshift;
+        if (is_edge) {
+          self = ld_rec(recs + s);
+          if (kshift) {
+            first = s & ~kmask;
+            cnt = kmask + 1u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) r[j] = ld_rec(recs + first + j);
+          }
         }
-      }
-      uint32_t goal = LMB_NONE;
-      while (heap.len > 0) {
-        HeapEntry cur = heap.pop();
-        const uint32_t s = cur.state;
-        // Issue every load the expansion needs before the first use: best[s] (stale test) and
-        // the node record (depth) usually come from HBM, the edge records from L2.
-        const float best_s = best[s];
-        const uint32_t cur_depth = nodes[cur.index].w;
-        EdgeRec self_rec;
-        if (s < ST_LINK0) self_rec = nav.edges[s];
 
-        // resolve (node, point, ignore step) — pathfinding.rs:93-143
-        uint32_t poly, first, ne, cur_type, has_links;
+        const HeapEntry cur = heap.pop();
+
+        // ---- resolve (node, point, ignore step) — pathfinding.rs:93-143 ----
+        uint32_t poly = 0, cur_type = 0, has_links = 0;
         uint32_t ignore_edge = LMB_NONE, ignore_link = LMB_NONE;
-        V3 point;
-        if (s < ST_LINK0) {
-          poly = self_rec.poly;
-          first = self_rec.first_edge;
-          ne = self_rec.info & 0xffu;
-          cur_type = (self_rec.info >> 8) & 0xffu;
-          has_links = (self_rec.info >> 24) & 1u;
-          point = {self_rec.mx, self_rec.my, self_rec.mz};
+        V3 point{0.0f, 0.0f, 0.0f};
+        if (is_edge) {
+          if (!kshift) {
+            first = self.first_edge;
+            cnt = self.info & 0xffu;
+          }
+          poly = self.poly;
+          cur_type = (self.info >> 8) & 0xffu;
+          has_links = (self.info >> 24) & 1u;
+          point = {self.mx, self.my, self.mz};
           ignore_edge = s;
-        } else if (s == ST_END) {
-          poly = first = ne = cur_type = has_links = 0;
-          point = {0.0f, 0.0f, 0.0f};
-        } else {
+        } else if (s != ST_END) {
           if (s == ST_START) {
-            poly = qu.start_node;
-            point = qu.start_point;
+            poly = start_node;
+            point = {q.start_point[3 * (size_t)qid], q.start_point[3 * (size_t)qid + 1],
+                     q.start_point[3 * (size_t)qid + 2]};
           } else {
             uint32_t l = s - ST_LINK0;
             poly = nav.link_dst_node[l];
@@ -278,165 +389,187 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             point = midpoint(V3{pp[0], pp[1], pp[2]}, V3{pp[3], pp[4], pp[5]});
           }
-          first = nav.poly_edge_begin[poly];
-          ne = nav.poly_edge_begin[poly + 1] - first;
+          poly_span(poly, first, cnt);
           cur_type = nav.poly_type_dense[poly];
           has_links = nav.node_link_begin[poly + 1] > nav.node_link_begin[poly];
         }
-        // first chunk of successor edge records, speculatively (before the stale test resolves)
-        EdgeRec succ_rec;
-        succ_rec.twin = LMB_NONE;
-        if (s != ST_END && poly != qu.end_node && lane < ne) succ_rec = nav.edges[first + lane];
+        const float cur_cost = cur.cost;
+        const uint32_t depth1 = cur.depth + 1;
+        const float cur_type_cost = cost_of(cur_type);
+        const bool to_end = poly == end_node;  // single successor GoToEnd (pathfinding.rs:152-155)
 
-        if (best_s < cur.estimate) continue;  // stale (astar.rs:172-176)
-        explored++;
-        if (s == ST_END) {
-          goal = cur.index;
-          break;
-        }
-        const float cur_cost_so_far = cur.cost;
-        const uint32_t depth1 = cur_depth + 1;
-        const float cur_type_cost = cost_tab[cur_type];
-
-        bool overflow = false;
-        if (poly == qu.end_node) {
-          // single successor: GoToEnd (pathfinding.rs:152-155); h(End) = 0
-          float c = fmul(distance(point, qu.end_point), cur_type_cost);
-          float ncost = fadd(cur_cost_so_far, c);
-          float est = fadd(ncost, 0.0f);
-          if (!(best[ST_END] <= est)) {
-            if (n_nodes >= arena.node_cap || heap.len >= heap_cap) {
+        // ---- node connections in ascending edge index, four records at a time.  Per chunk:
+        //      records (L2) -> `best` probes of every candidate issued together (HBM, speculative:
+        //      loads only) -> costs/estimates of all four evaluated unconditionally (independent
+        //      chains, no divergence) -> stale test -> accepted successors pushed in edge order ----
+        bool overflow = false, live = true;
+        for (uint32_t e0 = 0; (e0 < cnt && live && !overflow) || e0 == 0; e0 += 4) {
+          if (e0 > 0 || !preloaded) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              if (e0 + j < cnt && s != ST_END)
+                r[j] = ld_rec(recs + first + e0 + j);
+              else
+                r[j].twin = LMB_NONE;
+            }
+          }
+          float probe[4];
+          uint32_t cand = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const bool ok = r[j].twin != LMB_NONE && first + e0 + j != ignore_edge && !to_end;
+            probe[j] = ok ? __ldcg(best + r[j].twin) : 0.0f;
+            cand |= ok ? (1u << j) : 0u;
+          }
+          float nc[4], es[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (!is_finite(cost_of((r[j].info >> 16) & 0xffu))) cand &= ~(1u << j);
+            const V3 mid{r[j].mx, r[j].my, r[j].mz};
+            const float c = fmul(distance(point, mid), cur_type_cost);
+            nc[j] = fadd(cur_cost, c);
+            es[j] = fadd(nc[j], fmul(distance(mid, end_point), cheapest));
+          }
+          if (e0 == 0) {
+            if (best_s < cur.estimate) {  // stale (astar.rs:172-176)
+              live = false;
+              break;
+            }
+            explored++;
+            if (s == ST_END) {
+              // goal: allocate the corridor and start the walk (astar.rs:86-105)
+              const uint32_t L = cur.depth;  // number of corridor nodes (>= 1: Start)
+              const unsigned long long off = atomicAdd(pool.cursor, (unsigned long long)L);
+              if (off + L > pool.capacity) {
+                status = 3;
+                phase = PH_FINISH;
+              } else {
+                success = 1;
+                path_off = (uint32_t)off;
+                path_len = L;
+                w_node = cur.index;  // the End node; its record is loaded next iteration
+                w_next = ST_END;
+                w_pos = L;
+                phase = PH_WALK;
+              }
+              live = false;
+              break;
+            }
+            if (to_end) {
+              // h(End) = 0
+              float c = fmul(distance(point, end_point), cur_type_cost);
+              float ncost = fadd(cur_cost, c);
+              float est = fadd(ncost, 0.0f);
+              if (!(__ldcg(best + ST_END) <= est)) {
+                if (n_nodes >= node_cap || heap.len >= heap_cap) {
+                  overflow = true;
+                } else {
+                  best[ST_END] = est;
+                  nodes[n_nodes] = make_uint2(ST_END, cur.index);
+                  heap.push({ncost, est, n_nodes, ST_END, depth1});
+                  n_nodes++;
+                }
+              }
+              live = false;  // no other successor
+              break;
+            }
+          }
+          uint32_t acc = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc |= (!(probe[j] <= es[j])) ? (1u << j) : 0u;
+          acc &= cand;
+          // The lanes of the warp step through their k-th accepted successor together
+          // (ascending j = ascending edge index).
+          while (acc) {
+            const uint32_t j = __ffs(acc) - 1;
+            acc &= acc - 1;
+            if (n_nodes >= node_cap || heap.len >= heap_cap) {
               overflow = true;
-            } else {
-              best[ST_END] = est;
-              nodes[n_nodes] = make_uint4(__float_as_uint(ncost), ST_END, cur.index, depth1);
-              heap.push({ncost, est, n_nodes, ST_END});
-              n_nodes++;
+              break;
             }
+            const uint32_t s2 = sel4(j, r[0].twin, r[1].twin, r[2].twin, r[3].twin);
+            const float est = sel4(j, es[0], es[1], es[2], es[3]);
+            const float ncost = sel4(j, nc[0], nc[1], nc[2], nc[3]);
+            best[s2] = est;
+            nodes[n_nodes] = make_uint2(s2, cur.index);
+            heap.push({ncost, est, n_nodes, s2, depth1});
+            n_nodes++;
           }
-        } else {
-          // node connections, ascending edge index, one edge per lane
-          for (uint32_t e0 = 0; e0 < ne && !overflow; e0 += 32) {
-            uint32_t e = e0 + lane;
-            bool accept = false;
-            float ncost = 0.0f, est = 0.0f;
-            uint32_t nstate = LMB_NONE;
-            if (e < ne) {
-              const EdgeRec r = e0 == 0 ? succ_rec : nav.edges[first + e];
-              if (r.twin != LMB_NONE && first + e != ignore_edge &&
-                  is_finite(cost_tab[(r.info >> 16) & 0xffu])) {
-                V3 mid{r.mx, r.my, r.mz};
-                float c = fmul(distance(point, mid), cur_type_cost);
-                ncost = fadd(cur_cost_so_far, c);
-                est = fadd(ncost, fmul(distance(mid, qu.end_point), cheapest));
-                nstate = r.twin;
-                accept = !(best[nstate] <= est);
-              }
+        }
+        // ---- off-mesh links in ascending link index (canonical; pathfinding.rs:196-229) ----
+        if (live && has_links && !overflow) {
+          for (uint32_t k = nav.node_link_begin[poly]; k < nav.node_link_begin[poly + 1]; k++) {
+            uint32_t l = nav.node_links[k];
+            if (l == ignore_link) continue;
+            if (!is_finite(cost_of(nav.link_dst_type_dense[l]))) continue;
+            float link_cost = 0.0f;
+            if (nav.link_kind[l] == LMB_LINK_ANIMATION) {
+              if (!is_kind_permitted(nav.link_anim_kind[l])) continue;
+              link_cost = nav.link_cost[l];
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, accept);
-            while (mask) {
-              int src = __ffs(mask) - 1;
-              mask &= mask - 1;
-              float c2 = __shfl_sync(0xffffffffu, ncost, src);
-              float e2 = __shfl_sync(0xffffffffu, est, src);
-              uint32_t s2 = __shfl_sync(0xffffffffu, nstate, src);
-              if (n_nodes >= arena.node_cap || heap.len >= heap_cap) {
-                overflow = true;
-                break;
-              }
-              best[s2] = e2;
-              nodes[n_nodes] = make_uint4(__float_as_uint(c2), s2, cur.index, depth1);
-              heap.push({c2, e2, n_nodes, s2});
-              n_nodes++;
+            const float* pp = nav.link_portal + 6 * (size_t)l;
+            V3 pm = midpoint(V3{pp[0], pp[1], pp[2]}, V3{pp[3], pp[4], pp[5]});
+            float c = fadd(fmul(distance(point, pm), cur_type_cost), link_cost);
+            float ncost = fadd(cur_cost, c);
+            // heuristic of OffMeshLink state: portal (boundary) / destination portal (animation)
+            V3 hp = pm;
+            if (nav.link_kind[l] != LMB_LINK_BOUNDARY) {
+              const float* dp = nav.link_dst_portal + 6 * (size_t)l;
+              hp = midpoint(V3{dp[0], dp[1], dp[2]}, V3{dp[3], dp[4], dp[5]});
             }
-          }
-          // off-mesh links in ascending link index (canonical; pathfinding.rs:196-229)
-          if (has_links && !overflow) {
-            for (uint32_t k = nav.node_link_begin[poly]; k < nav.node_link_begin[poly + 1]; k++) {
-              uint32_t l = nav.node_links[k];
-              if (l == ignore_link) continue;
-              if (!is_finite(cost_tab[nav.link_dst_type_dense[l]])) continue;
-              float link_cost = 0.0f;
-              if (nav.link_kind[l] == LMB_LINK_ANIMATION) {
-                if (!is_kind_permitted(nav.link_anim_kind[l])) continue;
-                link_cost = nav.link_cost[l];
-              }
-              const float* pp = nav.link_portal + 6 * (size_t)l;
-              V3 pm = midpoint(V3{pp[0], pp[1], pp[2]}, V3{pp[3], pp[4], pp[5]});
-              float c = fadd(fmul(distance(point, pm), cur_type_cost), link_cost);
-              float ncost = fadd(cur_cost_so_far, c);
-              // heuristic of OffMeshLink state: portal (boundary) / destination portal (animation)
-              V3 hp = pm;
-              if (nav.link_kind[l] != LMB_LINK_BOUNDARY) {
-                const float* dp = nav.link_dst_portal + 6 * (size_t)l;
-                hp = midpoint(V3{dp[0], dp[1], dp[2]}, V3{dp[3], dp[4], dp[5]});
-              }
-              float est = fadd(ncost, fmul(distance(hp, qu.end_point), cheapest));
-              uint32_t s2 = ST_LINK0 + l;
-              if (best[s2] <= est) continue;
-              if (n_nodes >= arena.node_cap || heap.len >= heap_cap) {
-                overflow = true;
-                break;
-              }
-              best[s2] = est;
-              nodes[n_nodes] = make_uint4(__float_as_uint(ncost), s2, cur.index, depth1);
-              heap.push({ncost, est, n_nodes, s2});
-              n_nodes++;
+            float est = fadd(ncost, fmul(distance(hp, end_point), cheapest));
+            uint32_t s2 = ST_LINK0 + l;
+            if (__ldcg(best + s2) <= est) continue;
+            if (n_nodes >= node_cap || heap.len >= heap_cap) {
+              overflow = true;
+              break;
             }
+            best[s2] = est;
+            nodes[n_nodes] = make_uint2(s2, cur.index);
+            heap.push({ncost, est, n_nodes, s2, depth1});
+            n_nodes++;
           }
         }
         if (overflow) {
-          status = (!SPILL && n_nodes < arena.node_cap) ? 4 : 2;
-          break;
+          status = 2;
+          phase = PH_FINISH;
         }
       }
-
-      // --- recover the path (astar.rs:86-105, pathfinding.rs:324-381) into the pool ---
-      if (status == 1 && goal != LMB_NONE) {
-        const uint32_t L = nodes[goal].w;  // number of corridor nodes
-        unsigned long long off = 0;
-        if (lane == 0) off = atomicAdd(pool.cursor, (unsigned long long)L);
-        off = __shfl_sync(0xffffffffu, off, 0);
-        if (off + L > pool.capacity) {
-          status = 3;
-        } else {
-          uint32_t i = goal;
-          uint32_t next_state = ST_END;
-          for (uint32_t pos = L; pos-- > 0;) {
-            i = nodes[i].z;
-            uint32_t st = nodes[i].y;
-            uint32_t node_id;
-            if (st < ST_LINK0)
-              node_id = nav.edges[st].poly;
-            else if (st == ST_START)
-              node_id = qu.start_node;
-            else
-              node_id = nav.link_dst_node[st - ST_LINK0];
-            uint32_t portal;
-            if (next_state == ST_END) {
-              portal = LMB_NONE;
-            } else if (next_state < ST_LINK0) {
-              uint32_t tw = nav.edges[next_state].twin;  // the edge inside `node_id`
-              portal = tw - nav.edges[tw].first_edge;
-            } else {
-              portal = LMB_PORTAL_LINK | (next_state - ST_LINK0);
-            }
-            if (lane == 0) pool.entries[off + pos] = make_uint2(node_id, portal);
-            next_state = st;
-          }
-          success = 1;
-          path_off = (uint32_t)off;
-          path_len = L;
-        }
+    } else if (phase == PH_WALK) {
+      // ============ WALK (part 2): consume the back-pointer loaded above ============
+      // (astar.rs:86-105) one node per iteration, written backwards as (state, next state)
+      if (w_rec.x != ST_END) pool.entries[(size_t)path_off + w_pos] = make_uint2(w_rec.x, w_next);
+      w_next = w_rec.x;
+      if (w_rec.y == LMB_NONE) {
+        phase = PH_FINISH;  // wrote the Start node (position 0)
+      } else {
+        w_node = w_rec.y;
+        w_pos--;
       }
-
-      // --- restore best_estimates to +inf for the next query of this slot ---
-      __syncwarp();
-      for (uint32_t k = lane; k < n_nodes; k += 32) best[nodes[k].y] = F_INF;
-      __syncwarp();
     }
 
-    if (lane == 0) {
+    // ====== FINISH: restore best_estimates to +inf (warp-cooperative), publish results ======
+    uint32_t fin = __ballot_sync(FULL, phase == PH_FINISH);
+    while (fin) {
+      const int src = __ffs(fin) - 1;
+      fin &= fin - 1;
+      const uint32_t nn = __shfl_sync(FULL, n_nodes, src);
+      if (nn == 0) continue;
+      uint8_t* base = arena.base + (size_t)(slot - lane + src) * arena.slot_stride;
+      float* b = reinterpret_cast<float*>(base);
+      if ((size_t)nn * 16 >= arena.n_states) {
+        // dense restore: coalesced 16-byte stores over the whole array (padded to 16 B)
+        float4* b4 = reinterpret_cast<float4*>(b);
+        const uint32_t n4 = (arena.n_states + 3) >> 2;
+        const float4 inf4 = make_float4(F_INF, F_INF, F_INF, F_INF);
+        for (uint32_t k = lane; k < n4; k += 32) b4[k] = inf4;
+      } else {
+        const uint2* nd = reinterpret_cast<const uint2*>(base + arena.nodes_offset);
+        for (uint32_t k = lane; k < nn; k += 32) b[nd[k].x] = F_INF;
+      }
+    }
+    __syncwarp();
+    if (phase == PH_FINISH) {
       q.out_status[qid] = status;
       if (status == 1) {
         q.out_success[qid] = success;
@@ -453,11 +586,44 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         atomicAdd(&counters->path_nodes_total, (unsigned long long)path_len);
       } else if (status == 2) {
         atomicAdd(&counters->n_retry_arena, 1u);
-      } else if (status == 4) {
-        atomicAdd(&counters->n_retry_spill, 1u);
       } else {
         atomicAdd(&counters->n_retry_pool, 1u);
       }
+      n_nodes = 0;
+      phase = PH_IDLE;
+    }
+  }
+}
+
+// Translates the raw (state, next state) pairs the walk left in the pool into
+// (node id, portal code) — pathfinding.rs:324-381.  One warp per finished query.
+__global__ void k_path_fixup(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t ST_LINK0 = arena.n_ids;
+  const uint32_t ST_END = arena.n_ids + nav.n_links + 1;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < q.n; w += warps) {
+    const uint32_t qid = q.list ? q.list[w] : w;
+    if (q.out_status[qid] != 1 || !q.out_success[qid]) continue;
+    const uint32_t off = q.out_path_off[qid], L = q.out_path_len[qid];
+    const uint32_t start_node = q.start_node[qid];
+    for (uint32_t j = lane; j < L; j += 32) {
+      const uint2 raw = pool.entries[(size_t)off + j];
+      uint32_t node_id;
+      if (j == 0)
+        node_id = start_node;  // the Start state
+      else if (raw.x < ST_LINK0)
+        node_id = nav.edges[raw.x].poly;
+      else
+        node_id = nav.link_dst_node[raw.x - ST_LINK0];
+      uint32_t portal;
+      if (raw.y == ST_END)
+        portal = LMB_NONE;
+      else if (raw.y < ST_LINK0)
+        portal = nav.edges[raw.y].aux & 0xffu;  // index of the twin edge inside `node_id`
+      else
+        portal = LMB_PORTAL_LINK | (raw.y - ST_LINK0);
+      pool.entries[(size_t)off + j] = make_uint2(node_id, portal);
     }
   }
 }
@@ -476,26 +642,24 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
 }
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, bool spill, cudaStream_t stream) {
+                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   if (q.n == 0) return;
-  const uint32_t warps_per_block = ASTAR_WARPS;
-  const size_t smem = (size_t)ASTAR_WARPS * SMEM_HEAP * sizeof(uint4);
+  const size_t smem = (size_t)AT_HEAP_SM * AT_THREADS * (sizeof(uint4) + sizeof(uint32_t));
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_astar<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
-  uint32_t blocks = (slots + warps_per_block - 1) / warps_per_block;
+  uint32_t blocks = (slots + AT_THREADS - 1) / AT_THREADS;
   AStarArena a = arena;
-  a.n_slots = blocks * warps_per_block <= arena.n_slots ? blocks * warps_per_block : arena.n_slots;
-  if (spill)
-    k_astar<true><<<blocks, warps_per_block * 32, smem, stream>>>(nav, a, q, pool, counters, type_raw);
-  else
-    k_astar<false><<<blocks, warps_per_block * 32, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  a.n_slots = slots;
+  k_astar<<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  // corridors of the queries that finished in this launch: raw states -> (node, portal)
+  uint32_t fix_blocks = (q.n + 7) / 8;
+  if (fix_blocks > 148 * 16) fix_blocks = 148 * 16;
+  k_path_fixup<<<fix_blocks, 256, 0, stream>>>(nav, a, q, pool);
 }
 
 }  // namespace lmb

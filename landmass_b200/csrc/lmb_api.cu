@@ -142,25 +142,60 @@ static PathPool make_pool(lmb_ctx* ctx) {
   return p;
 }
 
+// (Re)allocates the A* arena: `slots` query slots of {best[n_states] f32, node list, open-list spill}.
 static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
   AStarArena& a = ctx->arena;
-  a.n_states = ctx->nav.n_edges + ctx->nav.n_links + 2;
+  a.n_ids = ctx->n_ids;
+  a.kshift = ctx->kshift;
+  a.n_states = ctx->n_ids + ctx->nav.n_links + 2;
   a.node_cap = node_cap;
   a.heap_cap = heap_cap;
+  const size_t spill = heap_cap > AT_HEAP_SM ? heap_cap - AT_HEAP_SM : 0;
   size_t best_bytes = ((size_t)a.n_states * 4 + 255) & ~(size_t)255;
-  size_t bits_bytes = ((((size_t)a.n_states + 31) / 32 + 1) * 4 + 255) & ~(size_t)255;
-  size_t node_bytes = ((size_t)node_cap * 16 + 255) & ~(size_t)255;
-  size_t heap_bytes = (((size_t)heap_cap + 2) * 16 + 255) & ~(size_t)255;
-  a.bits_offset = best_bytes;
-  a.nodes_offset = best_bytes + bits_bytes;
-  a.heap_offset = best_bytes + bits_bytes + node_bytes;
-  a.slot_stride = best_bytes + bits_bytes + node_bytes + heap_bytes;
+  size_t node_bytes = ((size_t)node_cap * 8 + 255) & ~(size_t)255;
+  size_t heap_bytes = (spill * 16 + 255) & ~(size_t)255;
+  size_t heapd_bytes = (spill * 4 + 255) & ~(size_t)255;
+  a.nodes_offset = best_bytes;
+  a.heap_offset = best_bytes + node_bytes;
+  a.heapd_offset = a.heap_offset + heap_bytes;
+  a.slot_stride = a.heapd_offset + heapd_bytes;
   a.n_slots = slots;
+  a.base = nullptr;
+  ctx->d_arena.release();
   CUDA_TRY(ctx, ctx->d_arena.reserve_exact(a.slot_stride * (size_t)slots));
   a.base = ctx->d_arena.p;
   launch_arena_init(a, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
   return LMB_OK;
+}
+
+static size_t arena_slot_bytes(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap) {
+  const size_t n_states = (size_t)ctx->n_ids + ctx->nav.n_links + 2;
+  return n_states * 4 + (size_t)node_cap * 8 + (size_t)heap_cap * 20 + 1024;
+}
+
+static size_t arena_budget(const lmb_ctx* ctx) {
+  if (ctx->cfg.scratch_bytes) return (size_t)ctx->cfg.scratch_bytes;
+  // auto: what is free now plus what the current arena already holds, minus head-room for the
+  // path pool (two copies during compaction) and the per-frame agent arrays
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)16 << 30;
+  free_b += ctx->d_arena.cap;
+  return std::min<size_t>((size_t)(free_b * 0.6), (size_t)110 << 30);
+}
+
+// Makes sure the arena can run `n_queries` concurrently (up to the slot limit / byte budget).
+static int32_t ensure_arena(lmb_ctx* ctx, uint32_t n_queries) {
+  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 2 * AT_THREADS;
+  uint32_t want = std::min<uint32_t>(max_slots, (n_queries + AT_THREADS - 1) / AT_THREADS * AT_THREADS);
+  want = std::max<uint32_t>(want, AT_THREADS);
+  if (ctx->arena.base && ctx->arena.n_slots >= want) return LMB_OK;
+  const size_t per_slot = arena_slot_bytes(ctx, ctx->arena_node_cap, ctx->arena_heap_cap);
+  const size_t budget = arena_budget(ctx);
+  uint32_t slots = want;
+  if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 32);
+  if (ctx->arena.base && ctx->arena.n_slots >= slots) return LMB_OK;
+  return setup_arena(ctx, ctx->arena_node_cap, ctx->arena_heap_cap, slots);
 }
 
 int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
@@ -298,15 +333,33 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
     node_links.assign(d->node_links, d->node_links + d->n_links);
   }
 
-  // ---- edge records ----
-  std::vector<EdgeRec> edges(d->n_edges);
+  // ---- edge records (= A* states) ----
+  // Record id space: padded (`poly << kshift | local edge`) when every polygon has <= 8 edges, so
+  // the kernel can address a polygon's records from a state id alone; CSR edge ids otherwise.
+  uint32_t max_ne = 0;
+  for (uint32_t p = 0; p < d->n_polys; p++)
+    max_ne = std::max(max_ne, d->poly_edge_begin[p + 1] - d->poly_edge_begin[p]);
+  if (max_ne > 255) return ctx->fail(LMB_ERR_UNSUPPORTED, "a polygon has more than 255 edges");
+  uint32_t kshift = max_ne <= 4 ? 2u : (max_ne <= 8 ? 3u : 0u);
+  if (kshift && ((uint64_t)d->n_polys << kshift) >= 0xF0000000ull) kshift = 0;
+  const uint32_t n_ids = kshift ? (d->n_polys << kshift) : d->n_edges;
+  ctx->kshift = kshift;
+  ctx->n_ids = n_ids;
+  auto rec_id = [&](uint32_t p, uint32_t e) { return kshift ? ((p << kshift) | e) : d->poly_edge_begin[p] + e; };
+  EdgeRec blank{};
+  blank.twin = LMB_NONE;
+  std::vector<EdgeRec> edges(std::max<uint32_t>(n_ids, 4u), blank);
   for (uint32_t p = 0; p < d->n_polys; p++) {
     uint32_t eb = d->poly_edge_begin[p], ne = d->poly_edge_begin[p + 1] - eb;
-    if (ne > 255) return ctx->fail(LMB_ERR_UNSUPPORTED, "polygon %u has more than 255 edges", p);
     const DevIsland& is = islands[poly_island[p]];
     bool has_links = node_link_begin[p + 1] > node_link_begin[p];
-    for (uint32_t e = 0; e < ne; e++) {
-      EdgeRec& r = edges[eb + e];
+    const uint32_t n_rec = kshift ? (1u << kshift) : ne;
+    for (uint32_t e = 0; e < n_rec; e++) {
+      EdgeRec& r = edges[rec_id(p, e)];
+      r.poly = p;
+      r.first_edge = rec_id(p, 0);
+      r.info = ne | (poly_type_dense[p] << 8) | (has_links ? (1u << 24) : 0u);
+      if (e >= ne) continue;  // padding record: twin stays LMB_NONE
       uint32_t vi = d->edge_vertex[eb + (e == ne - 1 ? 0 : e + 1)];  // left  = vertex[e+1]
       uint32_t vj = d->edge_vertex[eb + e];                           // right = vertex[e]
       const float* a = d->vertices + 3 * (size_t)vi;
@@ -317,12 +370,11 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
       r.my = w.y;
       r.mz = w.z;
       uint32_t nb = d->edge_neighbor[eb + e];
-      r.nbr_poly = nb;
-      r.twin = nb == LMB_NONE ? LMB_NONE : d->poly_edge_begin[nb] + d->edge_reverse[eb + e];
-      r.poly = p;
-      r.first_edge = eb;
-      uint32_t nbt = nb == LMB_NONE ? 0u : poly_type_dense[nb];
-      r.info = ne | (poly_type_dense[p] << 8) | (nbt << 16) | (has_links ? (1u << 24) : 0u);
+      if (nb != LMB_NONE) {
+        r.twin = rec_id(nb, d->edge_reverse[eb + e]);
+        r.aux = d->edge_reverse[eb + e] & 0xffu;
+        r.info |= poly_type_dense[nb] << 16;
+      }
     }
   }
 
@@ -423,16 +475,14 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   nav.possible_link_dst = ctx->d_possible_dst.p;
   nav.possible_link_kind = ctx->d_possible_kind.p;
 
-  // ---- A* arenas ----
-  uint32_t n_states = nav.n_edges + nav.n_links + 2;
-  uint32_t slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 32;
-  uint32_t node_cap = std::max<uint32_t>(std::max<uint32_t>(n_states + 64, 256), d->n_region_numbers / 2 + 64);
-  uint32_t heap_cap = std::max<uint32_t>(n_states / 4 + 64, 256);
-  size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)80 << 30);
-  size_t per_slot = (size_t)n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;
-  if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 32);
-  int32_t st = setup_arena(ctx, node_cap, heap_cap, slots);
-  if (st != LMB_OK) return st;
+  // ---- A* arena: sized lazily by the first batch of queries (ensure_arena) ----
+  {
+    const uint32_t n_states = ctx->n_ids + nav.n_links + 2;
+    ctx->arena_node_cap = std::max<uint32_t>(n_states / 4 + 1024, d->n_region_numbers + 64);
+    ctx->arena_heap_cap = AT_HEAP_SM + std::max<uint32_t>(1024, n_states / 64);
+    ctx->arena = AStarArena{};
+    ctx->d_arena.release();
+  }
 
   // ---- path pool: drop all paths ----
   if (ctx->pool_capacity == 0) {
@@ -501,31 +551,32 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
       if (st != LMB_OK) return st;
     }
   }
+  {
+    int32_t st = ensure_arena(ctx, n);
+    if (st != LMB_OK) return st;
+  }
   unsigned long long done_total = 0, nodes_total = 0;
   const uint32_t* list = nullptr;
   uint32_t n_run = n;
-  bool spill = false;
   std::vector<uint32_t> h_status;
   for (int iter = 0; iter < 24; iter++) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(AStarCounters), s));
     AStarQueries qq = q;
     qq.n = n_run;
     qq.list = list;
-    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, spill, s);
+    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     ctx->timings.explored_nodes += ctx->h_counters->explored_total;
     ctx->timings.path_nodes += ctx->h_counters->path_nodes_total;
-    ctx->timings.kernel_launches += 1;
+    ctx->timings.kernel_launches += 2;  // k_astar + k_path_fixup
     uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
-    const uint32_t rs = ctx->h_counters->n_retry_spill;
     done_total += ctx->h_counters->n_done;
     nodes_total += ctx->h_counters->path_nodes_total;
     if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
-    if (ra == 0 && rp == 0 && rs == 0) return LMB_OK;
-    if (rs) spill = true;  // some open list outgrew shared memory: the retry uses the spilling variant
+    if (ra == 0 && rp == 0) return LMB_OK;
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);
     CUDA_TRY(ctx, cudaMemcpy(h_status.data(), q.out_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -538,13 +589,14 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
       if (st != LMB_OK) return st;
     }
     if (ra) {
-      AStarArena& a = ctx->arena;
-      uint32_t node_cap = a.node_cap * 2, heap_cap = a.heap_cap * 2;
-      size_t per_slot = (size_t)a.n_states * 4 + (size_t)node_cap * 16 + (size_t)heap_cap * 16 + 1024;
-      size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes : ((size_t)80 << 30);
-      uint32_t slots = a.n_slots;
+      // node list or open-list spill too small: double both; the slot count follows the budget
+      ctx->arena_node_cap *= 2;
+      ctx->arena_heap_cap = AT_HEAP_SM + (ctx->arena_heap_cap - AT_HEAP_SM) * 2;
+      const size_t per_slot = arena_slot_bytes(ctx, ctx->arena_node_cap, ctx->arena_heap_cap);
+      const size_t budget = arena_budget(ctx);
+      uint32_t slots = ctx->arena.n_slots;
       if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 8);
-      int32_t st = setup_arena(ctx, node_cap, heap_cap, slots);
+      int32_t st = setup_arena(ctx, ctx->arena_node_cap, ctx->arena_heap_cap, slots);
       if (st != LMB_OK) return st;
     }
     CUDA_TRY(ctx, ctx->d_retry_list.upload(retry, s));

@@ -111,16 +111,19 @@ struct DevIsland {
   uint32_t cell_begin;       // offset into cell_start (gnx*gny+1 entries)
 };
 
-// One 32-byte record per polygon edge = one A* state "in polygon `poly`, standing on the
-// midpoint of this edge".  One sector per lane on expansion.
+// One 32-byte record (one sector) per polygon edge = one A* state "in polygon `poly`, standing
+// on the midpoint of this edge".  Record ids are the A* state ids: the CSR edge id, or — when
+// every polygon has <= 8 edges — `poly << kshift | local edge` (polygons padded to 4 or 8
+// records, padding has twin = LMB_NONE), so that a polygon's records are addressable from a
+// state id without first reading the state's own record.
 struct __align__(32) EdgeRec {
   float mx, my, mz;     // world midpoint: apply(midpoint(local v[e+1], v[e]))
-  uint32_t twin;        // edge id of the same edge inside the neighbour (= successor state) or LMB_NONE
+  uint32_t twin;        // record id of the same edge inside the neighbour (= successor state) or LMB_NONE
   uint32_t poly;        // node id owning this edge
-  uint32_t first_edge;  // first edge id of `poly`
+  uint32_t first_edge;  // record id of the first edge of `poly`
   uint32_t info;        // bits 0-7 n_edges of poly, 8-15 dense type of poly, 16-23 dense type of
                         // neighbour, bit 24 poly has off-mesh links
-  uint32_t nbr_poly;    // node id across the edge or LMB_NONE
+  uint32_t aux;         // bits 0-7 index of the twin edge inside the neighbour polygon
 };
 
 struct DevNav {

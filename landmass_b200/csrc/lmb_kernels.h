@@ -13,16 +13,21 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
                           float* out_points, uint32_t* out_nodes, cudaStream_t stream);
 
 // ---- kernel 2: batched A* (k_astar.cu) ----
+constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
+constexpr uint32_t AT_HEAP_SM = 40;   // open-list entries per query held in shared memory (20 B each)
+
 struct AStarArena {
   uint8_t* base;          // device memory for all slots
   size_t slot_stride;     // bytes per slot
-  uint32_t n_slots;       // concurrent queries (= warps launched)
-  uint32_t n_states;      // n_edges + n_links + 2
+  uint32_t n_slots;       // concurrent queries (= threads launched)
+  uint32_t n_ids;         // edge-record ids (CSR: n_edges; padded: n_polys << kshift)
+  uint32_t kshift;        // 0 = CSR ids; else a polygon's records are ids [poly << kshift, +1 << kshift)
+  uint32_t n_states;      // n_ids + n_links + 2
   uint32_t node_cap;      // nodes per slot
-  uint32_t heap_cap;      // heap entries per slot
-  size_t bits_offset;     // byte offset of the touched bitmap inside a slot
-  size_t nodes_offset;    // byte offset of the node array inside a slot
-  size_t heap_offset;     // byte offset of the heap array inside a slot
+  uint32_t heap_cap;      // open-list entries per query (shared memory + spill)
+  size_t nodes_offset;    // byte offset of the node list {state, prev} inside a slot
+  size_t heap_offset;     // byte offset of the open-list spill (16 B part) inside a slot
+  size_t heapd_offset;    // byte offset of the open-list spill (depth part) inside a slot
 };
 
 struct AStarQueries {
@@ -42,7 +47,7 @@ struct AStarQueries {
   const uint32_t* slot;        // [n] agent slot to receive the path, or NULL
   // outputs
   uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool
-                               //     overflow), 4 = retry with the spilling open list
+                               //     overflow)
   uint32_t* out_success;       // [n]
   uint32_t* out_explored;      // [n]
   uint32_t* out_path_off;      // [n] offset into the path pool
@@ -61,14 +66,13 @@ struct AStarCounters {  // device-resident
   unsigned int queue_head;
   unsigned int n_retry_arena;
   unsigned int n_retry_pool;
-  unsigned int n_retry_spill;
   unsigned int n_done;
   unsigned long long explored_total;
   unsigned long long path_nodes_total;
 };
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, bool spill, cudaStream_t stream);
+                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
 // ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----
