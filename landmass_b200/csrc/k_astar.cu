@@ -20,7 +20,7 @@
 //
 // Memory:
 //   * open list: the first AT_HEAP_SM entries of every lane's heap live in shared memory,
-//     interleaved by thread (entry i of thread t at [i * AT_THREADS + t], conflict-free for
+//     interleaved by thread (entry i of thread t at [i * STRIDE + t], conflict-free for
 //     128-bit accesses); deeper entries spill in place to the lane's arena slot.
 //   * `best_estimates` (a HashMap in the reference): dense f32 array per slot, +inf between
 //     queries; restored by a warp-cooperative memset (or a scatter over the node list when
@@ -33,148 +33,25 @@
 //   * the corridor is written into the path pool as raw (state, next state) pairs by the
 //     walk; `k_path_fixup` translates them to (node id, portal code) afterwards, fully
 //     parallel.
-#include "lmb_device.cuh"
-#include "lmb_kernels.h"
+#include <cstdlib>
+
+#include "k_astar_common.cuh"
 
 namespace lmb {
 
-namespace {
+using namespace astar_detail;
 
-constexpr float F_INF = __builtin_huge_valf();
-constexpr uint32_t FULL = 0xffffffffu;
-
-struct HeapEntry {
-  float cost, estimate;
-  uint32_t index;
-  uint32_t state;
-  uint32_t depth;
-};
-
-// NodeRef::partial_cmp (astar.rs:67-77) as `a <= b`
-__device__ __forceinline__ bool noderef_le(const HeapEntry& a, const HeapEntry& b) {
-  // Less, or Equal-estimates with Reverse(a.cost) <= Reverse(b.estimate); unordered (NaN) -> false
-  return (a.estimate < b.estimate) | ((a.estimate == b.estimate) & (b.estimate <= a.cost));
-}
-// Reverse<T>::le(x, y) = y.0 <= x.0
-__device__ __forceinline__ bool rev_le(const HeapEntry& x, const HeapEntry& y) { return noderef_le(y, x); }
-
-// Open list.  The SP = false members touch shared memory only (valid while every index they
-// can reach is < AT_HEAP_SM); SP = true adds the in-place spill to the slot's arena.  The
-// caller picks per operation from the current length, so the common case carries no
-// per-access branch.
-struct Heap {
-  uint4* sm;      // this thread's column: entry i at sm[i * AT_THREADS]
-  uint32_t* smd;  // depth column
-  uint4* gm;      // spill: entry i (>= AT_HEAP_SM) at gm[i - AT_HEAP_SM]
-  uint32_t* gmd;
-  uint32_t len;
-  template <bool SP>
-  __device__ __forceinline__ HeapEntry get(uint32_t i) const {
-    uint4 v;
-    uint32_t d;
-    if (!SP || i < AT_HEAP_SM) {
-      v = sm[i * AT_THREADS];
-      d = smd[i * AT_THREADS];
-    } else {
-      v = gm[i - AT_HEAP_SM];
-      d = gmd[i - AT_HEAP_SM];
-    }
-    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w, d};
-  }
-  template <bool SP>
-  __device__ __forceinline__ void set(uint32_t i, const HeapEntry& e) {
-    uint4 v = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, e.state);
-    if (!SP || i < AT_HEAP_SM) {
-      sm[i * AT_THREADS] = v;
-      smd[i * AT_THREADS] = e.depth;
-    } else {
-      gm[i - AT_HEAP_SM] = v;
-      gmd[i - AT_HEAP_SM] = e.depth;
-    }
-  }
-  template <bool SP>
-  __device__ __forceinline__ void sift_up(uint32_t pos, const HeapEntry& hole) {
-    while (pos > 0) {
-      uint32_t parent = (pos - 1) >> 1;
-      HeapEntry p = get<SP>(parent);
-      if (rev_le(hole, p)) break;
-      set<SP>(pos, p);
-      pos = parent;
-    }
-    set<SP>(pos, hole);
-  }
-  template <bool SP>
-  __device__ __forceinline__ void push_t(const HeapEntry& e) {
-    uint32_t old_len = len++;
-    sift_up<SP>(old_len, e);
-  }
-  __device__ __forceinline__ void push(const HeapEntry& e) {
-    if (len < AT_HEAP_SM)
-      push_t<false>(e);
-    else
-      push_t<true>(e);
-  }
-  template <bool SP>
-  __device__ __forceinline__ HeapEntry pop_t() {
-    HeapEntry item = get<SP>(--len);
-    if (len > 0) {
-      HeapEntry top = get<SP>(0);
-      HeapEntry hole = item;  // swap(item, data[0]); the hole element is the old last
-      item = top;
-      uint32_t end = len, pos = 0, child = 1;
-      while (child + 1 < end) {  // child <= end - 2
-        HeapEntry a = get<SP>(child), b = get<SP>(child + 1);
-        bool right = rev_le(a, b);
-        set<SP>(pos, right ? b : a);
-        pos = child + (right ? 1u : 0u);
-        child = 2 * pos + 1;
-      }
-      if (child + 1 == end) {
-        set<SP>(pos, get<SP>(child));
-        pos = child;
-      }
-      sift_up<SP>(pos, hole);
-    }
-    return item;
-  }
-  __device__ __forceinline__ HeapEntry pop() {
-    if (len <= AT_HEAP_SM) return pop_t<false>();
-    return pop_t<true>();
-  }
-};
-
-template <class T>
-__device__ __forceinline__ T sel4(uint32_t j, T a0, T a1, T a2, T a3) {
-  return j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
-}
-
-__device__ __forceinline__ EdgeRec ld_rec(const EdgeRec* p) {
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
-  EdgeRec r;
-  r.mx = __uint_as_float(a.x);
-  r.my = __uint_as_float(a.y);
-  r.mz = __uint_as_float(a.z);
-  r.twin = a.w;
-  r.poly = b.x;
-  r.first_edge = b.y;
-  r.info = b.z;
-  r.aux = b.w;
-  return r;
-}
-
-enum : uint32_t { PH_IDLE = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINISH = 3, PH_EXIT = 4 };
-
-}  // namespace
-
-__global__ void __launch_bounds__(AT_THREADS, 2)
+template <uint32_t QPW>  // queries per warp: lanes >= QPW idle (fewer searches in lock-step per warp)
+__global__ void __launch_bounds__(AT_THREADS, 64 / QPW)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
-  extern __shared__ uint4 s_heap[];  // [AT_HEAP_SM][AT_THREADS] uint4, then the same shape of u32 depths
+  constexpr uint32_t QPB = QPW * (AT_THREADS / 32);  // queries per block
+  extern __shared__ uint4 s_heap[];  // [AT_HEAP_SM][QPB] uint4, then the same shape of u32 depths
   __shared__ float s_cost[LMB_MAX_TYPES];
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31;
-  const uint32_t slot = blockIdx.x * AT_THREADS + tid;
+  const uint32_t qib = (tid >> 5) * QPW + (lane < QPW ? lane : 0);  // query index in block
+  const uint32_t slot = lane < QPW ? blockIdx.x * QPB + qib : 0xffffffffu;
   for (uint32_t t = tid; t < nav.n_types; t += AT_THREADS) s_cost[t] = nav.type_cost[t];
   __syncthreads();
 
@@ -182,9 +59,9 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   uint8_t* const slot_base = arena.base + (size_t)slot_c * arena.slot_stride;
   float* const best = reinterpret_cast<float*>(slot_base);
   uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
-  Heap heap;
-  heap.sm = s_heap + tid;
-  heap.smd = reinterpret_cast<uint32_t*>(s_heap + (size_t)AT_HEAP_SM * AT_THREADS) + tid;
+  Heap<QPB> heap;
+  heap.sm = s_heap + qib;
+  heap.smd = reinterpret_cast<uint32_t*>(s_heap + (size_t)AT_HEAP_SM * QPB) + qib;
   heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
   heap.gmd = reinterpret_cast<uint32_t*>(slot_base + arena.heapd_offset);
   heap.len = 0;
@@ -555,7 +432,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       fin &= fin - 1;
       const uint32_t nn = __shfl_sync(FULL, n_nodes, src);
       if (nn == 0) continue;
-      uint8_t* base = arena.base + (size_t)(slot - lane + src) * arena.slot_stride;
+      const uint32_t src_slot = __shfl_sync(FULL, slot, src);
+      uint8_t* base = arena.base + (size_t)src_slot * arena.slot_stride;
       float* b = reinterpret_cast<float*>(base);
       if ((size_t)nn * 16 >= arena.n_states) {
         // dense restore: coalesced 16-byte stores over the whole array (padded to 16 B)
@@ -641,21 +519,52 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
   k_arena_init<<<148 * 8, 256, 0, stream>>>(arena);
 }
 
-void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
-  if (q.n == 0) return;
-  const size_t smem = (size_t)AT_HEAP_SM * AT_THREADS * (sizeof(uint4) + sizeof(uint32_t));
+template <uint32_t QPW>
+static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                           AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
+  constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
+  const size_t smem = (size_t)AT_HEAP_SM * QPB * (sizeof(uint4) + sizeof(uint32_t));
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_astar<QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar<QPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
-  uint32_t blocks = (slots + AT_THREADS - 1) / AT_THREADS;
+  uint32_t blocks = (slots + QPB - 1) / QPB;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar<<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  k_astar<QPW><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+}
+
+// Kernel variant: LMB_ASTAR_MODE = "quad" (default: four lanes per query) or "thread" (one lane
+// per query; LMB_ASTAR_QPW = 32 | 16 | 8 queries per warp).
+static int astar_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* m = getenv("LMB_ASTAR_MODE");
+    const char* e = getenv("LMB_ASTAR_QPW");
+    int qpw = e ? atoi(e) : 16;
+    if (qpw != 8 && qpw != 16 && qpw != 32) qpw = 16;
+    mode = (m && m[0] == 't') ? qpw : 4;
+  }
+  return mode;
+}
+
+uint32_t astar_resident_queries_per_sm() {
+  return astar_mode() == 4 ? AQ_BLOCKS_PER_SM * 8 * (AT_THREADS / 32) : 2 * AT_THREADS;
+}
+
+void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
+  if (q.n == 0) return;
+  switch (astar_mode()) {
+    case 4: launch_astar_quad(nav, arena, q, pool, counters, type_raw, stream); break;
+    case 8: launch_astar_t<8>(nav, arena, q, pool, counters, type_raw, stream); break;
+    case 16: launch_astar_t<16>(nav, arena, q, pool, counters, type_raw, stream); break;
+    default: launch_astar_t<32>(nav, arena, q, pool, counters, type_raw, stream); break;
+  }
+  AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)
   uint32_t fix_blocks = (q.n + 7) / 8;
   if (fix_blocks > 148 * 16) fix_blocks = 148 * 16;

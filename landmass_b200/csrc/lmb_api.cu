@@ -186,7 +186,7 @@ static size_t arena_budget(const lmb_ctx* ctx) {
 
 // Makes sure the arena can run `n_queries` concurrently (up to the slot limit / byte budget).
 static int32_t ensure_arena(lmb_ctx* ctx, uint32_t n_queries) {
-  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * 2 * AT_THREADS;
+  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * astar_resident_queries_per_sm();
   uint32_t want = std::min<uint32_t>(max_slots, (n_queries + AT_THREADS - 1) / AT_THREADS * AT_THREADS);
   want = std::max<uint32_t>(want, AT_THREADS);
   if (ctx->arena.base && ctx->arena.n_slots >= want) return LMB_OK;

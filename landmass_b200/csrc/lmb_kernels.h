@@ -15,6 +15,7 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
 // ---- kernel 2: batched A* (k_astar.cu) ----
 constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
 constexpr uint32_t AT_HEAP_SM = 40;   // open-list entries per query held in shared memory (20 B each)
+constexpr uint32_t AQ_BLOCKS_PER_SM = 7;  // quad kernel: 7 blocks x 32 queries per SM
 
 struct AStarArena {
   uint8_t* base;          // device memory for all slots
@@ -73,6 +74,9 @@ struct AStarCounters {  // device-resident
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                   AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
+void launch_astar_quad(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                       AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
+uint32_t astar_resident_queries_per_sm();  // of the kernel variant in use
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
 // ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----

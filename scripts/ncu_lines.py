@@ -3,7 +3,10 @@
 `ncu --page source --csv` only exports the SASS view; this joins it (by instruction offset)
 with `nvdisasm -g` line info of the object file that holds the kernel.
 
-  python scripts/ncu_lines.py <report.ncu-rep> <object.o> <kernel-substring> [top]
+  python scripts/ncu_lines.py <report.ncu-rep> <object.o> <kernel-substring> [top] [mangled-substring]
+
+(the mangled substring selects the SASS section when the object holds several template
+instantiations, e.g. k_astarILj32E)
 """
 import csv
 import glob
@@ -15,6 +18,7 @@ import tempfile
 
 rep, obj, kern = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 50
+mangled = sys.argv[5] if len(sys.argv) > 5 else kern
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, capture_output=True)
@@ -28,7 +32,7 @@ cur = None
 for ln in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", ln)
     if m:
-        in_fn = kern in m.group(1)
+        in_fn = mangled in m.group(1)
         continue
     if not in_fn:
         continue
