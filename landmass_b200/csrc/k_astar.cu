@@ -41,7 +41,10 @@ namespace lmb {
 
 using namespace astar_detail;
 
-template <uint32_t QPW>  // queries per warp: lanes >= QPW idle (fewer searches in lock-step per warp)
+// QPW: queries per warp (lanes >= QPW idle: fewer searches in lock-step per warp).
+// KS: compile-time kshift (2 = every polygon has <= 4 edges: one chunk, no chunk loop), or 0 =
+//     use the run-time value (0 or 3).
+template <uint32_t QPW, uint32_t KS>
 __global__ void __launch_bounds__(AT_THREADS, 64 / QPW)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
@@ -69,8 +72,12 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   const EdgeRec* __restrict__ recs = nav.edges;
   const uint32_t heap_cap = arena.heap_cap;
   const uint32_t node_cap = arena.node_cap;
-  const uint32_t kshift = arena.kshift;
+  const uint32_t kshift = KS ? KS : arena.kshift;
   const uint32_t kmask = (1u << kshift) - 1u;
+  // one polygon type and no per-query overrides in this batch: every type cost is this value
+  const bool simple_cost = nav.n_types == 1 && !q.override_begin;
+  const float cost0 = s_cost[0];
+  const float4* __restrict__ edge_dist = reinterpret_cast<const float4*>(nav.edge_dist);
   const uint32_t ST_LINK0 = arena.n_ids;
   const uint32_t ST_START = arena.n_ids + nav.n_links;
   const uint32_t ST_END = ST_START + 1;
@@ -89,6 +96,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
 
   // type cost: override -> archipelago -> 1.0 (pathfinding.rs:73-77)
   auto cost_of = [&](uint32_t t) -> float {
+    if (simple_cost) return cost0;
     float c = s_cost[t];
     if (ov_begin != ov_end) {
       const uint32_t raw = type_raw[t];
@@ -223,6 +231,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         self.mx = self.my = self.mz = 0.0f;
         uint32_t first = 0, cnt = 0;
         const bool preloaded = is_edge && kshift;
+        float4 dtab = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // distances state midpoint -> edge midpoints
         if (is_edge) {
           self = ld_rec(recs + s);
           if (kshift) {
@@ -230,6 +239,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             cnt = kmask + 1u;
 #pragma unroll
             for (int j = 0; j < 4; j++) r[j] = ld_rec(recs + first + j);
+            dtab = __ldg(edge_dist + ((size_t)s << (kshift - 2)));
           }
         }
 
@@ -280,7 +290,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         //      loads only) -> costs/estimates of all four evaluated unconditionally (independent
         //      chains, no divergence) -> stale test -> accepted successors pushed in edge order ----
         bool overflow = false, live = true;
-        for (uint32_t e0 = 0; (e0 < cnt && live && !overflow) || e0 == 0; e0 += 4) {
+        for (uint32_t e0 = 0; e0 == 0 || (KS != 2 && e0 < cnt && live && !overflow); e0 += 4) {
           if (e0 > 0 || !preloaded) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -289,6 +299,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               else
                 r[j].twin = LMB_NONE;
             }
+            if (preloaded) dtab = __ldg(edge_dist + ((size_t)s << (kshift - 2)) + (e0 >> 2));
           }
           float probe[4];
           uint32_t cand = 0;
@@ -298,12 +309,21 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             probe[j] = ok ? __ldcg(best + r[j].twin) : 0.0f;
             cand |= ok ? (1u << j) : 0u;
           }
+          // distance(point, edge midpoint): a constant of the mesh for edge states (table built at
+          // upload with the same rounding sequence), computed here for Start / link states
+          float dj[4];
+          if (preloaded) {
+            dj[0] = dtab.x, dj[1] = dtab.y, dj[2] = dtab.z, dj[3] = dtab.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) dj[j] = distance(point, V3{r[j].mx, r[j].my, r[j].mz});
+          }
           float nc[4], es[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             if (!is_finite(cost_of((r[j].info >> 16) & 0xffu))) cand &= ~(1u << j);
             const V3 mid{r[j].mx, r[j].my, r[j].mz};
-            const float c = fmul(distance(point, mid), cur_type_cost);
+            const float c = fmul(dj[j], cur_type_cost);
             nc[j] = fadd(cur_cost, c);
             es[j] = fadd(nc[j], fmul(distance(mid, end_point), cheapest));
           }
@@ -458,6 +478,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           uint32_t sl = q.slot[qid];
           pool.slot_path_off[sl] = path_off;
           pool.slot_path_len[sl] = path_len;
+          pool.slot_cost_hint[sl] = explored;
         }
         atomicAdd(&counters->n_done, 1u);
         atomicAdd(&counters->explored_total, (unsigned long long)explored);
@@ -506,6 +527,65 @@ __global__ void k_path_fixup(DevNav nav, AStarArena arena, AStarQueries q, PathP
   }
 }
 
+// Longest-processing-time-first order of a batch.  A batch takes at least as long as its longest
+// search, and queries are handed to lanes in queue order, so searches expected to be long should
+// start first.  The only predictor available is the agent's previous search (a hint: the order
+// never changes a result).  Single block: 1024-bucket counting sort on a log scale.
+__global__ void __launch_bounds__(1024)
+k_order_queries(uint32_t n, const uint32_t* __restrict__ q_slot, const uint32_t* __restrict__ hint,
+                uint32_t unknown_hint, uint32_t* __restrict__ order) {
+  __shared__ uint32_t s_count[1024];
+  __shared__ uint32_t s_scan[1024];
+  const uint32_t t = threadIdx.x;
+  s_count[t] = 0;
+  __syncthreads();
+  auto bucket_of = [&](uint32_t i) -> uint32_t {
+    uint32_t h = hint[q_slot[i]];
+    if (h == 0) h = unknown_hint;
+    int b = (int)(log2f((float)h + 1.0f) * 40.0f);
+    b = b < 0 ? 0 : (b > 1023 ? 1023 : b);
+    return 1023u - (uint32_t)b;  // descending
+  };
+  for (uint32_t i = t; i < n; i += 1024) atomicAdd(&s_count[bucket_of(i)], 1u);
+  __syncthreads();
+  // exclusive scan of 1024 counters (Hillis-Steele)
+  uint32_t v = s_count[t];
+  s_scan[t] = v;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    uint32_t add = t >= off ? s_scan[t - off] : 0u;
+    __syncthreads();
+    s_scan[t] += add;
+    __syncthreads();
+  }
+  s_count[t] = s_scan[t] - v;  // start offset of bucket t
+  __syncthreads();
+  for (uint32_t i = t; i < n; i += 1024) order[atomicAdd(&s_count[bucket_of(i)], 1u)] = i;
+}
+
+void launch_order_queries(uint32_t n, const uint32_t* q_slot, const uint32_t* slot_cost_hint, uint32_t unknown_hint,
+                          uint32_t* order, cudaStream_t stream) {
+  if (n) k_order_queries<<<1, 1024, 0, stream>>>(n, q_slot, slot_cost_hint, unknown_hint, order);
+}
+
+// distance(midpoint of record s, midpoint of record j of the same polygon) for padded ids:
+// out[s * K + j].  Same device functions as the search, so the values are the ones the search
+// would compute (pathfinding.rs:178-182).
+__global__ void k_build_edge_dist(const EdgeRec* __restrict__ recs, uint32_t n_ids, uint32_t kshift, float* out) {
+  const uint32_t K = 1u << kshift;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)n_ids * K;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t s = (uint32_t)(i >> kshift), j = (uint32_t)(i & (K - 1));
+    const EdgeRec a = recs[s], b = recs[(s & ~(K - 1)) + j];
+    out[i] = distance(V3{a.mx, a.my, a.mz}, V3{b.mx, b.my, b.mz});
+  }
+}
+
+void launch_build_edge_dist(const EdgeRec* recs, uint32_t n_ids, uint32_t kshift, float* out, cudaStream_t stream) {
+  if (!kshift || !n_ids) return;
+  k_build_edge_dist<<<148 * 4, 256, 0, stream>>>(recs, n_ids, kshift, out);
+}
+
 __global__ void k_arena_init(AStarArena arena) {
   size_t total = (size_t)arena.n_slots * arena.n_states;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -519,50 +599,58 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
   k_arena_init<<<148 * 8, 256, 0, stream>>>(arena);
 }
 
-template <uint32_t QPW>
+template <uint32_t QPW, uint32_t KS>
 static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                            AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
   const size_t smem = (size_t)AT_HEAP_SM * QPB * (sizeof(uint4) + sizeof(uint32_t));
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar<QPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar<QPW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_astar<QPW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar<QPW, KS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
   uint32_t blocks = (slots + QPB - 1) / QPB;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar<QPW><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  k_astar<QPW, KS><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
-// Kernel variant: LMB_ASTAR_MODE = "quad" (default: four lanes per query) or "thread" (one lane
-// per query; LMB_ASTAR_QPW = 32 | 16 | 8 queries per warp).
-static int astar_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* m = getenv("LMB_ASTAR_MODE");
+// Queries per warp.  16 (default): only half of a warp's lanes own a query.  The search is bound by
+// the latency of one iteration with all lanes of a warp in lock-step, and the number of queries
+// in flight by HBM (one dense best[] array each), not by warp slots — so fewer queries per warp
+// (a warp waits for the slowest of 16 instead of 32 pops) costs nothing and measured 5-14 %
+// faster.  LMB_ASTAR_QPW=32|16|8 overrides (8 is register-starved, kept for experiments).
+static uint32_t astar_queries_per_warp() {
+  static int qpw = -1;
+  if (qpw < 0) {
     const char* e = getenv("LMB_ASTAR_QPW");
-    int qpw = e ? atoi(e) : 16;
+    qpw = e ? atoi(e) : 16;
     if (qpw != 8 && qpw != 16 && qpw != 32) qpw = 16;
-    mode = (m && m[0] == 't') ? qpw : 4;
   }
-  return mode;
+  return (uint32_t)qpw;
 }
 
-uint32_t astar_resident_queries_per_sm() {
-  return astar_mode() == 4 ? AQ_BLOCKS_PER_SM * 8 * (AT_THREADS / 32) : 2 * AT_THREADS;
-}
+uint32_t astar_resident_queries_per_sm() { return 2 * AT_THREADS; }
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                   AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   if (q.n == 0) return;
-  switch (astar_mode()) {
-    case 4: launch_astar_quad(nav, arena, q, pool, counters, type_raw, stream); break;
-    case 8: launch_astar_t<8>(nav, arena, q, pool, counters, type_raw, stream); break;
-    case 16: launch_astar_t<16>(nav, arena, q, pool, counters, type_raw, stream); break;
-    default: launch_astar_t<32>(nav, arena, q, pool, counters, type_raw, stream); break;
+  const bool k4 = arena.kshift == 2;
+  switch (astar_queries_per_warp()) {
+    case 8:
+      k4 ? launch_astar_t<8, 2>(nav, arena, q, pool, counters, type_raw, stream)
+         : launch_astar_t<8, 0>(nav, arena, q, pool, counters, type_raw, stream);
+      break;
+    case 16:
+      k4 ? launch_astar_t<16, 2>(nav, arena, q, pool, counters, type_raw, stream)
+         : launch_astar_t<16, 0>(nav, arena, q, pool, counters, type_raw, stream);
+      break;
+    default:
+      k4 ? launch_astar_t<32, 2>(nav, arena, q, pool, counters, type_raw, stream)
+         : launch_astar_t<32, 0>(nav, arena, q, pool, counters, type_raw, stream);
+      break;
   }
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <map>
@@ -93,7 +94,7 @@ int32_t lmb_create(const lmb_config* config, lmb_ctx** out_ctx) {
   ctx->sm_count = (uint32_t)prop.multiProcessorCount;
   const uint32_t m = ctx->cfg.max_agents;
   cudaError_t es[] = {
-      ctx->d_slot_path_off.reserve(m), ctx->d_slot_path_len.reserve(m), ctx->d_scan_tmp.reserve(m + 1),
+      ctx->d_slot_path_off.reserve(m), ctx->d_slot_path_len.reserve(m), ctx->d_slot_cost_hint.reserve(m), ctx->d_scan_tmp.reserve(m + 1),
       ctx->d_desired_move.reserve(3 * (size_t)m), ctx->d_reached_start.reserve(3 * (size_t)m),
       ctx->d_reached_end.reserve(3 * (size_t)m), ctx->d_state.reserve(m),
       ctx->d_reached_link_id.reserve(m), ctx->d_pool_cursor.reserve(1), ctx->d_counters.reserve(1),
@@ -106,6 +107,7 @@ int32_t lmb_create(const lmb_config* config, lmb_ctx** out_ctx) {
     }
   cudaMemsetAsync(ctx->d_slot_path_len.p, 0, m * sizeof(uint32_t), ctx->stream);
   cudaMemsetAsync(ctx->d_slot_path_off.p, 0, m * sizeof(uint32_t), ctx->stream);
+  cudaMemsetAsync(ctx->d_slot_cost_hint.p, 0, m * sizeof(uint32_t), ctx->stream);
   cudaMemsetAsync(ctx->d_desired_move.p, 0, 3 * (size_t)m * sizeof(float), ctx->stream);
   cudaMemsetAsync(ctx->d_state.p, 0, m * sizeof(uint32_t), ctx->stream);  // LMB_STATE_IDLE
   cudaMemsetAsync(ctx->d_reached_link_id.p, 0xff, m * sizeof(uint32_t), ctx->stream);
@@ -139,6 +141,7 @@ static PathPool make_pool(lmb_ctx* ctx) {
   p.capacity = ctx->pool_capacity;
   p.slot_path_off = ctx->d_slot_path_off.p;
   p.slot_path_len = ctx->d_slot_path_len.p;
+  p.slot_cost_hint = ctx->d_slot_cost_hint.p;
   return p;
 }
 
@@ -164,6 +167,9 @@ static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, u
   ctx->d_arena.release();
   CUDA_TRY(ctx, ctx->d_arena.reserve_exact(a.slot_stride * (size_t)slots));
   a.base = ctx->d_arena.p;
+  if (getenv("LMB_DEBUG"))
+    fprintf(stderr, "[lmb] A* arena: %u slots x %.2f MB (n_states %u, node_cap %u, heap_cap %u, kshift %u)\n", slots,
+            a.slot_stride / 1048576.0, a.n_states, node_cap, heap_cap, a.kshift);
   launch_arena_init(a, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
   return LMB_OK;
@@ -449,6 +455,13 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   nav.cell_start = ctx->d_cell_start.p;
   nav.cell_polys = ctx->d_cell_polys.p;
   nav.edges = ctx->d_edges.p;
+  nav.edge_dist = nullptr;
+  if (ctx->kshift) {
+    CUDA_TRY(ctx, ctx->d_edge_dist.reserve((size_t)ctx->n_ids << ctx->kshift));
+    launch_build_edge_dist(ctx->d_edges.p, ctx->n_ids, ctx->kshift, ctx->d_edge_dist.p, s);
+    CUDA_TRY(ctx, cudaGetLastError());
+    nav.edge_dist = ctx->d_edge_dist.p;
+  }
   nav.type_cost = ctx->d_type_cost.p;
   nav.type_registered = ctx->d_type_registered.p;
   nav.link_dst_node = ctx->d_link_dst_node.p;
@@ -491,6 +504,8 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
     ctx->pool_cur = 0;
   }
   launch_drop_all_paths(make_pool(ctx), ctx->cfg.max_agents, s);
+  CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_slot_cost_hint.p, 0, ctx->cfg.max_agents * sizeof(uint32_t), s));
+  ctx->explored_estimate = 0.0;
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
   ctx->has_nav = true;
@@ -555,9 +570,18 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     int32_t st = ensure_arena(ctx, n);
     if (st != LMB_OK) return st;
   }
-  unsigned long long done_total = 0, nodes_total = 0;
+  unsigned long long done_total = 0, nodes_total = 0, explored_total = 0;
   const uint32_t* list = nullptr;
   uint32_t n_run = n;
+  if (q.slot && n > ctx->arena.n_slots) {
+    // more queries than can run at once: start the (probably) longest searches first
+    CUDA_TRY(ctx, ctx->d_query_order.reserve(n));
+    launch_order_queries(n, q.slot, ctx->d_slot_cost_hint.p, (uint32_t)std::max(ctx->explored_estimate, 1.0),
+                         ctx->d_query_order.p, s);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timings.kernel_launches += 1;
+    list = ctx->d_query_order.p;
+  }
   std::vector<uint32_t> h_status;
   for (int iter = 0; iter < 24; iter++) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(AStarCounters), s));
@@ -575,7 +599,9 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
     done_total += ctx->h_counters->n_done;
     nodes_total += ctx->h_counters->path_nodes_total;
+    explored_total += ctx->h_counters->explored_total;
     if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
+    if (done_total) ctx->explored_estimate = (double)explored_total / (double)done_total;
     if (ra == 0 && rp == 0) return LMB_OK;
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);

@@ -76,6 +76,7 @@ struct lmb_ctx {
       d_possible_kind;
   DevBuf<uint8_t> d_htris, d_type_registered;
   DevBuf<EdgeRec> d_edges;
+  DevBuf<float> d_edge_dist;
   float world_min[2] = {0, 0}, world_max[2] = {0, 0};
 
   // --- A* ---
@@ -91,7 +92,7 @@ struct lmb_ctx {
   int pool_cur = 0;
   unsigned long long pool_capacity = 0;
   DevBuf<unsigned long long> d_pool_cursor;
-  DevBuf<uint32_t> d_slot_path_off, d_slot_path_len, d_scan_tmp;
+  DevBuf<uint32_t> d_slot_path_off, d_slot_path_len, d_slot_cost_hint, d_scan_tmp, d_query_order;
   DevBuf<float> d_desired_move, d_reached_start, d_reached_end;
   DevBuf<uint32_t> d_state, d_reached_link_id;
 
@@ -129,7 +130,8 @@ struct lmb_ctx {
   cudaEvent_t ev[11]{};
   uint32_t halo_total = 0, halo_first = 0;
   bool step_open = false;
-  double path_len_estimate = 0.0;  // running mean corridor length, sizes the pool before A*
+  double path_len_estimate = 0.0;
+  double explored_estimate = 0.0;  // running mean explored_nodes: the hint of an agent without history  // running mean corridor length, sizes the pool before A*
 
   int32_t fail(int32_t code, const char* fmt, ...) {
     char buf[512];

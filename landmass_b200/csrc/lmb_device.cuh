@@ -145,6 +145,7 @@ struct DevNav {
   const uint32_t* cell_start;  // per island blocks
   const uint32_t* cell_polys;
   const EdgeRec* edges;
+  const float* edge_dist;      // padded ids only: [n_ids * K] midpoint-to-midpoint distances inside a polygon
   const float* type_cost;      // [n_types] archipelago cost of each dense type (1.0 if unregistered)
   const uint8_t* type_registered;  // [n_types] 1 if present in nav_data.type_index_to_cost
   // links

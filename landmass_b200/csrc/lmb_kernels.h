@@ -15,7 +15,6 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
 // ---- kernel 2: batched A* (k_astar.cu) ----
 constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
 constexpr uint32_t AT_HEAP_SM = 40;   // open-list entries per query held in shared memory (20 B each)
-constexpr uint32_t AQ_BLOCKS_PER_SM = 7;  // quad kernel: 7 blocks x 32 queries per SM
 
 struct AStarArena {
   uint8_t* base;          // device memory for all slots
@@ -61,6 +60,8 @@ struct PathPool {
   unsigned long long capacity;      // entries
   uint32_t* slot_path_off;          // [max_agents]
   uint32_t* slot_path_len;          // [max_agents] 0 = no path
+  uint32_t* slot_cost_hint;         // [max_agents] explored_nodes of the slot's previous search (0 = none):
+                                    // a scheduling hint only (longest-first), never an input of a result
 };
 
 struct AStarCounters {  // device-resident
@@ -74,8 +75,10 @@ struct AStarCounters {  // device-resident
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                   AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
-void launch_astar_quad(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                       AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
+// order[] = query indices 0..n-1 sorted by descending cost hint of their agent slot (bucketed)
+void launch_order_queries(uint32_t n, const uint32_t* q_slot, const uint32_t* slot_cost_hint, uint32_t unknown_hint,
+                          uint32_t* order, cudaStream_t stream);
+void launch_build_edge_dist(const EdgeRec* recs, uint32_t n_ids, uint32_t kshift, float* out, cudaStream_t stream);
 uint32_t astar_resident_queries_per_sm();  // of the kernel variant in use
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
