@@ -41,15 +41,22 @@ namespace lmb {
 
 using namespace astar_detail;
 
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<false>&) { return 0u; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<true>& b) { return b.ovf_count; }
+__device__ __forceinline__ void ovf_clear(BestStore<false>&) {}
+__device__ __forceinline__ void ovf_clear(BestStore<true>& b) { b.ovf_count = 0; }
+
 // QPW: queries per warp (lanes >= QPW idle: fewer searches in lock-step per warp).
 // KS: compile-time kshift (2 = every polygon has <= 4 edges: one chunk, no chunk loop), or 0 =
 //     use the run-time value (0 or 3).
-template <uint32_t QPW, uint32_t KS>
-__global__ void __launch_bounds__(AT_THREADS, 64 / QPW)
+// COMPACT: best_estimates layout (k_astar_common.cuh).
+// HS: open-list entries per query in shared memory; BPS: blocks per SM the variant is sized for.
+template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, bool COMPACT>
+__global__ void __launch_bounds__(AT_THREADS, BPS)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);  // queries per block
-  extern __shared__ uint4 s_heap[];  // [AT_HEAP_SM][QPB] uint4, then the same shape of u32 depths
+  extern __shared__ uint4 s_heap[];  // [HS][QPB] uint4, then the same shape of u32 depths
   __shared__ float s_cost[LMB_MAX_TYPES];
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31;
@@ -60,11 +67,13 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
 
   const uint32_t slot_c = slot < arena.n_slots ? slot : 0;  // out-of-range lanes never touch memory
   uint8_t* const slot_base = arena.base + (size_t)slot_c * arena.slot_stride;
-  float* const best = reinterpret_cast<float*>(slot_base);
+  typedef typename BestStore<COMPACT>::Raw BestRaw;
+  BestStore<COMPACT> bs;
+  bs.init(slot_base, arena);
   uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
-  Heap<QPB> heap;
+  Heap<QPB, HS> heap;
   heap.sm = s_heap + qib;
-  heap.smd = reinterpret_cast<uint32_t*>(s_heap + (size_t)AT_HEAP_SM * QPB) + qib;
+  heap.smd = reinterpret_cast<uint32_t*>(s_heap + (size_t)HS * QPB) + qib;
   heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
   heap.gmd = reinterpret_cast<uint32_t*>(slot_base + arena.heapd_offset);
   heap.len = 0;
@@ -198,7 +207,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           // try_add_node(Start)
           float est = fadd(0.0f, fmul(distance(start_point, end_point), cheapest));
           if (!(F_INF <= est)) {
-            best[ST_START] = est;
+            bs.store(ST_START, bs.probe(ST_START), est);
             nodes[0] = make_uint2(ST_START, LMB_NONE);
             n_nodes = 1;
             heap.push({0.0f, est, 0u, ST_START, 0u});
@@ -221,7 +230,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         // ---- peek the root and issue this expansion's first loads BEFORE the pop's sift work:
         //      best[s] (stale test, HBM) and, with padded ids, the polygon's edge records (L2) ----
         const uint32_t s = heap.sm[0].w;
-        const float best_s = __ldcg(best + s);
+        const BestRaw raw_s = bs.probe(s);
         const bool is_edge = s < ST_LINK0;
         EdgeRec r[4];
 #pragma unroll
@@ -289,7 +298,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         //      records (L2) -> `best` probes of every candidate issued together (HBM, speculative:
         //      loads only) -> costs/estimates of all four evaluated unconditionally (independent
         //      chains, no divergence) -> stale test -> accepted successors pushed in edge order ----
-        bool overflow = false, live = true;
+        bool overflow = false, live = true, go_dense = false;
         for (uint32_t e0 = 0; e0 == 0 || (KS != 2 && e0 < cnt && live && !overflow); e0 += 4) {
           if (e0 > 0 || !preloaded) {
 #pragma unroll
@@ -301,12 +310,12 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             if (preloaded) dtab = __ldg(edge_dist + ((size_t)s << (kshift - 2)) + (e0 >> 2));
           }
-          float probe[4];
+          BestRaw praw[4];
           uint32_t cand = 0;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const bool ok = r[j].twin != LMB_NONE && first + e0 + j != ignore_edge && !to_end;
-            probe[j] = ok ? __ldcg(best + r[j].twin) : 0.0f;
+            praw[j] = ok ? bs.probe_edge(r[j].twin) : BestRaw{};
             cand |= ok ? (1u << j) : 0u;
           }
           // distance(point, edge midpoint): a constant of the mesh for edge states (table built at
@@ -328,7 +337,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             es[j] = fadd(nc[j], fmul(distance(mid, end_point), cheapest));
           }
           if (e0 == 0) {
-            if (best_s < cur.estimate) {  // stale (astar.rs:172-176)
+            if (bs.value(s, raw_s) < cur.estimate) {  // stale (astar.rs:172-176)
               live = false;
               break;
             }
@@ -357,11 +366,12 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               float c = fmul(distance(point, end_point), cur_type_cost);
               float ncost = fadd(cur_cost, c);
               float est = fadd(ncost, 0.0f);
-              if (!(__ldcg(best + ST_END) <= est)) {
+              const BestRaw raw_e = bs.probe(ST_END);
+              if (!(bs.value(ST_END, raw_e) <= est)) {
                 if (n_nodes >= node_cap || heap.len >= heap_cap) {
                   overflow = true;
                 } else {
-                  best[ST_END] = est;
+                  bs.store(ST_END, raw_e, est);
                   nodes[n_nodes] = make_uint2(ST_END, cur.index);
                   heap.push({ncost, est, n_nodes, ST_END, depth1});
                   n_nodes++;
@@ -373,8 +383,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           }
           uint32_t acc = 0;
 #pragma unroll
-          for (int j = 0; j < 4; j++) acc |= (!(probe[j] <= es[j])) ? (1u << j) : 0u;
-          acc &= cand;
+          for (int j = 0; j < 4; j++)
+            acc |= (((cand >> j) & 1u) && !(bs.value_edge(r[j].twin, praw[j]) <= es[j])) ? (1u << j) : 0u;
           // The lanes of the warp step through their k-th accepted successor together
           // (ascending j = ascending edge index).
           while (acc) {
@@ -387,14 +397,18 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             const uint32_t s2 = sel4(j, r[0].twin, r[1].twin, r[2].twin, r[3].twin);
             const float est = sel4(j, es[0], es[1], es[2], es[3]);
             const float ncost = sel4(j, nc[0], nc[1], nc[2], nc[3]);
-            best[s2] = est;
+            if (!bs.store(s2, sel4(j, praw[0], praw[1], praw[2], praw[3]), est)) {
+              go_dense = true;
+              break;
+            }
             nodes[n_nodes] = make_uint2(s2, cur.index);
             heap.push({ncost, est, n_nodes, s2, depth1});
             n_nodes++;
           }
+          if (go_dense) break;
         }
         // ---- off-mesh links in ascending link index (canonical; pathfinding.rs:196-229) ----
-        if (live && has_links && !overflow) {
+        if (live && has_links && !overflow && !go_dense) {
           for (uint32_t k = nav.node_link_begin[poly]; k < nav.node_link_begin[poly + 1]; k++) {
             uint32_t l = nav.node_links[k];
             if (l == ignore_link) continue;
@@ -416,19 +430,20 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             float est = fadd(ncost, fmul(distance(hp, end_point), cheapest));
             uint32_t s2 = ST_LINK0 + l;
-            if (__ldcg(best + s2) <= est) continue;
+            const BestRaw raw_l = bs.probe(s2);
+            if (bs.value(s2, raw_l) <= est) continue;
             if (n_nodes >= node_cap || heap.len >= heap_cap) {
               overflow = true;
               break;
             }
-            best[s2] = est;
+            bs.store(s2, raw_l, est);
             nodes[n_nodes] = make_uint2(s2, cur.index);
             heap.push({ncost, est, n_nodes, s2, depth1});
             n_nodes++;
           }
         }
-        if (overflow) {
-          status = 2;
+        if (overflow || go_dense) {
+          status = go_dense ? 5 : 2;
           phase = PH_FINISH;
         }
       }
@@ -454,16 +469,42 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       if (nn == 0) continue;
       const uint32_t src_slot = __shfl_sync(FULL, slot, src);
       uint8_t* base = arena.base + (size_t)src_slot * arena.slot_stride;
-      float* b = reinterpret_cast<float*>(base);
-      if ((size_t)nn * 16 >= arena.n_states) {
-        // dense restore: coalesced 16-byte stores over the whole array (padded to 16 B)
-        float4* b4 = reinterpret_cast<float4*>(b);
-        const uint32_t n4 = (arena.n_states + 3) >> 2;
-        const float4 inf4 = make_float4(F_INF, F_INF, F_INF, F_INF);
-        for (uint32_t k = lane; k < n4; k += 32) b4[k] = inf4;
+      const uint2* nd = reinterpret_cast<const uint2*>(base + arena.nodes_offset);
+      if (!COMPACT) {
+        float* b = reinterpret_cast<float*>(base);
+        if ((size_t)nn * 16 >= arena.n_states) {
+          // dense restore: coalesced 16-byte stores over the whole array (padded to 16 B)
+          float4* b4 = reinterpret_cast<float4*>(b);
+          const uint32_t n4 = (arena.n_states + 3) >> 2;
+          const float4 inf4 = make_float4(F_INF, F_INF, F_INF, F_INF);
+          for (uint32_t k = lane; k < n4; k += 32) b4[k] = inf4;
+        } else {
+          for (uint32_t k = lane; k < nn; k += 32) b[nd[k].x] = F_INF;
+        }
       } else {
-        const uint2* nd = reinterpret_cast<const uint2*>(base + arena.nodes_offset);
-        for (uint32_t k = lane; k < nn; k += 32) b[nd[k].x] = F_INF;
+        uint2* bp = reinterpret_cast<uint2*>(base);
+        float* sp = reinterpret_cast<float*>(base + arena.special_offset);
+        const uint32_t n_polys = arena.n_ids >> arena.kshift;
+        if ((size_t)nn * 8 >= n_polys) {
+          uint4* b4 = reinterpret_cast<uint4*>(base);
+          const uint32_t n4 = (n_polys + 1) >> 1;
+          const uint4 e4 = make_uint4(__float_as_uint(F_INF), BP_EMPTY, __float_as_uint(F_INF), BP_EMPTY);
+          for (uint32_t k = lane; k < n4; k += 32) b4[k] = e4;
+          for (uint32_t k = lane; k < arena.n_states - arena.n_ids; k += 32) sp[k] = F_INF;
+        } else {
+          for (uint32_t k = lane; k < nn; k += 32) {
+            const uint32_t st = nd[k].x;
+            if (st < arena.n_ids)
+              bp[st >> arena.kshift] = make_uint2(__float_as_uint(F_INF), BP_EMPTY);
+            else
+              sp[st - arena.n_ids] = F_INF;
+          }
+        }
+        if (__shfl_sync(FULL, ovf_used(bs), src)) {
+          uint4* o4 = reinterpret_cast<uint4*>(base + arena.ovf_offset);
+          const uint4 e4 = make_uint4(BP_EMPTY, 0u, BP_EMPTY, 0u);
+          for (uint32_t k = lane; k < arena.ovf_cap / 2; k += 32) o4[k] = e4;
+        }
       }
     }
     __syncwarp();
@@ -485,10 +526,13 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         atomicAdd(&counters->path_nodes_total, (unsigned long long)path_len);
       } else if (status == 2) {
         atomicAdd(&counters->n_retry_arena, 1u);
+      } else if (status == 5) {
+        atomicAdd(&counters->n_retry_dense, 1u);
       } else {
         atomicAdd(&counters->n_retry_pool, 1u);
       }
       n_nodes = 0;
+      ovf_clear(bs);
       phase = PH_IDLE;
     }
   }
@@ -587,11 +631,24 @@ void launch_build_edge_dist(const EdgeRec* recs, uint32_t n_ids, uint32_t kshift
 }
 
 __global__ void k_arena_init(AStarArena arena) {
-  size_t total = (size_t)arena.n_slots * arena.n_states;
+  // every slot: the best_estimates region to "absent", the overflow table (compact) to empty
+  const size_t words = arena.best_bytes / 4;
+  const size_t total = (size_t)arena.n_slots * words;
+  const uint32_t n_poly_words = arena.compact ? 2u * (arena.n_ids >> arena.kshift) : 0u;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
-    size_t slot = i / arena.n_states, k = i % arena.n_states;
-    reinterpret_cast<float*>(arena.base + slot * arena.slot_stride)[k] = F_INF;
+    const size_t slot = i / words, k = i % words;
+    uint32_t v = __float_as_uint(F_INF);
+    if (arena.compact && k < n_poly_words && (k & 1)) v = BP_EMPTY;
+    reinterpret_cast<uint32_t*>(arena.base + slot * arena.slot_stride)[k] = v;
+  }
+  if (arena.compact) {
+    const size_t ow = (size_t)arena.ovf_cap * 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)arena.n_slots * ow;
+         i += (size_t)gridDim.x * blockDim.x) {
+      const size_t slot = i / ow, k = i % ow;
+      reinterpret_cast<uint32_t*>(arena.base + slot * arena.slot_stride + arena.ovf_offset)[k] = (k & 1) ? 0u : BP_EMPTY;
+    }
   }
 }
 
@@ -599,58 +656,49 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
   k_arena_init<<<148 * 8, 256, 0, stream>>>(arena);
 }
 
-template <uint32_t QPW, uint32_t KS>
+template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, bool COMPACT>
 static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                            AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
-  const size_t smem = (size_t)AT_HEAP_SM * QPB * (sizeof(uint4) + sizeof(uint32_t));
+  const size_t smem = (size_t)HS * QPB * (sizeof(uint4) + sizeof(uint32_t));
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar<QPW, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar<QPW, KS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
   uint32_t blocks = (slots + QPB - 1) / QPB;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar<QPW, KS><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  k_astar<QPW, HS, BPS, KS, COMPACT><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
-// Queries per warp.  16 (default): only half of a warp's lanes own a query.  The search is bound by
-// the latency of one iteration with all lanes of a warp in lock-step, and the number of queries
-// in flight by HBM (one dense best[] array each), not by warp slots — so fewer queries per warp
-// (a warp waits for the slowest of 16 instead of 32 pops) costs nothing and measured 5-14 %
-// faster.  LMB_ASTAR_QPW=32|16|8 overrides (8 is register-starved, kept for experiments).
-static uint32_t astar_queries_per_warp() {
-  static int qpw = -1;
-  if (qpw < 0) {
-    const char* e = getenv("LMB_ASTAR_QPW");
-    qpw = e ? atoi(e) : 16;
-    if (qpw != 8 && qpw != 16 && qpw != 32) qpw = 16;
-  }
-  return (uint32_t)qpw;
-}
-
-uint32_t astar_resident_queries_per_sm() { return 2 * AT_THREADS; }
+// Launch shape: 256 queries per SM = 4 blocks x 4 warps x 16 queries, 40 open-list entries per
+// query in shared memory (205 KB per SM).  Only half the lanes of a warp own a query: the number
+// of queries in flight is bounded by HBM (the per-query arena slot) and the search by the
+// latency of one lock-step warp iteration, not by warp or issue slots — so a warp that waits
+// for the slowest of 16 instead of 32 pops costs nothing and measured 5-14 % faster.  (Measured
+// and rejected on the 256-maze, 100k queries: 32 queries per warp; 384 queries per SM with 28
+// shared-memory entries — the in-place spill then costs more than the extra slots give; a
+// 4-lanes-per-query variant — lower latency per query but issue-bound, no faster when loaded.)
+uint32_t astar_resident_queries_per_sm() { return 4 * 16 * (AT_THREADS / 32); }
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                   AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   if (q.n == 0) return;
   const bool k4 = arena.kshift == 2;
-  switch (astar_queries_per_warp()) {
-    case 8:
-      k4 ? launch_astar_t<8, 2>(nav, arena, q, pool, counters, type_raw, stream)
-         : launch_astar_t<8, 0>(nav, arena, q, pool, counters, type_raw, stream);
-      break;
-    case 16:
-      k4 ? launch_astar_t<16, 2>(nav, arena, q, pool, counters, type_raw, stream)
-         : launch_astar_t<16, 0>(nav, arena, q, pool, counters, type_raw, stream);
-      break;
-    default:
-      k4 ? launch_astar_t<32, 2>(nav, arena, q, pool, counters, type_raw, stream)
-         : launch_astar_t<32, 0>(nav, arena, q, pool, counters, type_raw, stream);
-      break;
+  if (arena.compact) {
+    if (k4)
+      launch_astar_t<16, 40, 4, 2, true>(nav, arena, q, pool, counters, type_raw, stream);
+    else
+      launch_astar_t<16, 40, 4, 0, true>(nav, arena, q, pool, counters, type_raw, stream);
+  } else {
+    if (k4)
+      launch_astar_t<16, 40, 4, 2, false>(nav, arena, q, pool, counters, type_raw, stream);
+    else
+      launch_astar_t<16, 40, 4, 0, false>(nav, arena, q, pool, counters, type_raw, stream);
   }
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)

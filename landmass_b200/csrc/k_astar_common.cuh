@@ -27,38 +27,38 @@ __device__ __forceinline__ bool noderef_le(const HeapEntry& a, const HeapEntry& 
 __device__ __forceinline__ bool rev_le(const HeapEntry& x, const HeapEntry& y) { return noderef_le(y, x); }
 
 // Open list.  The SP = false members touch shared memory only (valid while every index they
-// can reach is < AT_HEAP_SM); SP = true adds the in-place spill to the slot's arena.  The
+// can reach is < HS); SP = true adds the in-place spill to the slot's arena.  The
 // caller picks per operation from the current length, so the common case carries no
 // per-access branch.
-template <uint32_t STRIDE>
+template <uint32_t STRIDE, uint32_t HS>  // HS: entries held in shared memory
 struct Heap {
   uint4* sm;      // this query's column: entry i at sm[i * STRIDE]
   uint32_t* smd;  // depth column
-  uint4* gm;      // spill: entry i (>= AT_HEAP_SM) at gm[i - AT_HEAP_SM]
+  uint4* gm;      // spill: entry i (>= HS) at gm[i - HS]
   uint32_t* gmd;
   uint32_t len;
   template <bool SP>
   __device__ __forceinline__ HeapEntry get(uint32_t i) const {
     uint4 v;
     uint32_t d;
-    if (!SP || i < AT_HEAP_SM) {
+    if (!SP || i < HS) {
       v = sm[i * STRIDE];
       d = smd[i * STRIDE];
     } else {
-      v = gm[i - AT_HEAP_SM];
-      d = gmd[i - AT_HEAP_SM];
+      v = gm[i - HS];
+      d = gmd[i - HS];
     }
     return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w, d};
   }
   template <bool SP>
   __device__ __forceinline__ void set(uint32_t i, const HeapEntry& e) {
     uint4 v = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, e.state);
-    if (!SP || i < AT_HEAP_SM) {
+    if (!SP || i < HS) {
       sm[i * STRIDE] = v;
       smd[i * STRIDE] = e.depth;
     } else {
-      gm[i - AT_HEAP_SM] = v;
-      gmd[i - AT_HEAP_SM] = e.depth;
+      gm[i - HS] = v;
+      gmd[i - HS] = e.depth;
     }
   }
   template <bool SP>
@@ -78,7 +78,7 @@ struct Heap {
     sift_up<SP>(old_len, e);
   }
   __device__ __forceinline__ void push(const HeapEntry& e) {
-    if (len < AT_HEAP_SM)
+    if (len < HS)
       push_t<false>(e);
     else
       push_t<true>(e);
@@ -107,7 +107,7 @@ struct Heap {
     return item;
   }
   __device__ __forceinline__ HeapEntry pop() {
-    if (len <= AT_HEAP_SM) return pop_t<false>();
+    if (len <= HS) return pop_t<false>();
     return pop_t<true>();
   }
 };
@@ -131,6 +131,100 @@ __device__ __forceinline__ EdgeRec ld_rec(const EdgeRec* p) {
   r.aux = b.w;
   return r;
 }
+
+// ---------------------------------------------------------------------------------------------
+// `best_estimates` (HashMap<PathNode, f32> in the reference, astar.rs:131), two layouts per slot:
+//  * dense   — f32 best[n_states], +inf = absent.
+//  * compact — padded ids only.  One 8-byte entry per POLYGON {estimate, local edge of the one
+//    state tracked} (a search enters most polygons through a single edge: always in tree-like
+//    meshes), an f32 per special state (links, Start, End) and a small open-addressing overflow
+//    table {state, estimate} for further states of an already tracked polygon.  Half the bytes
+//    of the dense array (so more queries fit in HBM) and four polygons per 32-byte sector instead
+//    of two.  A query that fills the overflow table is re-run with the dense layout.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t BP_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t BP_SPECIAL = 0xFFFFFFFEu;
+
+template <bool COMPACT>
+struct BestStore;
+
+template <>
+struct BestStore<false> {
+  typedef float Raw;
+  float* b;
+  __device__ __forceinline__ void init(uint8_t* slot_base, const AStarArena&) { b = reinterpret_cast<float*>(slot_base); }
+  __device__ __forceinline__ Raw probe(uint32_t st) const { return __ldcg(b + st); }
+  __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return __ldcg(b + st); }
+  __device__ __forceinline__ float value(uint32_t, Raw r) const { return r; }
+  __device__ __forceinline__ float value_edge(uint32_t, Raw r) const { return r; }
+  __device__ __forceinline__ bool store(uint32_t st, Raw, float est) {
+    b[st] = est;
+    return true;
+  }
+};
+
+template <>
+struct BestStore<true> {
+  typedef uint2 Raw;
+  uint2* bp;    // [n_polys] {estimate bits, tracked local edge | BP_EMPTY}
+  float* sp;    // [n_links + 2]
+  uint2* ovf;   // [ovf_cap] {state | BP_EMPTY, estimate bits}
+  uint32_t n_ids, kshift, kmask, ovf_mask, ovf_count;
+  __device__ __forceinline__ void init(uint8_t* slot_base, const AStarArena& a) {
+    bp = reinterpret_cast<uint2*>(slot_base);
+    sp = reinterpret_cast<float*>(slot_base + a.special_offset);
+    ovf = reinterpret_cast<uint2*>(slot_base + a.ovf_offset);
+    n_ids = a.n_ids;
+    kshift = a.kshift;
+    kmask = (1u << a.kshift) - 1u;
+    ovf_mask = a.ovf_cap - 1u;
+    ovf_count = 0;
+  }
+  __device__ __forceinline__ Raw probe(uint32_t st) const {
+    if (st < n_ids) return __ldcg(bp + (st >> kshift));
+    return make_uint2(__float_as_uint(__ldcg(sp + (st - n_ids))), BP_SPECIAL);
+  }
+  __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return __ldcg(bp + (st >> kshift)); }
+  __device__ __forceinline__ uint32_t ovf_slot(uint32_t st) const { return (st * 2654435761u) >> 7; }
+  __device__ float ovf_get(uint32_t st) const {
+    for (uint32_t h = ovf_slot(st);; h++) {
+      const uint2 e = __ldcg(ovf + (h & ovf_mask));
+      if (e.x == st) return __uint_as_float(e.y);
+      if (e.x == BP_EMPTY) return __builtin_huge_valf();
+    }
+  }
+  __device__ bool ovf_set(uint32_t st, float est) {
+    for (uint32_t h = ovf_slot(st);; h++) {
+      const uint2 e = __ldcg(ovf + (h & ovf_mask));
+      if (e.x == st || e.x == BP_EMPTY) {
+        if (e.x == BP_EMPTY && ++ovf_count > (ovf_mask + 1u) / 2u) return false;  // too full: go dense
+        ovf[h & ovf_mask] = make_uint2(st, __float_as_uint(est));
+        return true;
+      }
+    }
+  }
+  __device__ __forceinline__ float value(uint32_t st, Raw r) const {
+    if (r.y == BP_SPECIAL || r.y == (st & kmask)) return __uint_as_float(r.x);
+    if (r.y == BP_EMPTY) return __builtin_huge_valf();
+    return ovf_get(st);
+  }
+  // edge states only (never BP_SPECIAL)
+  __device__ __forceinline__ float value_edge(uint32_t st, Raw r) const {
+    if (r.y == (st & kmask)) return __uint_as_float(r.x);
+    if (r.y == BP_EMPTY) return __builtin_huge_valf();
+    return ovf_get(st);
+  }
+  __device__ __forceinline__ bool store(uint32_t st, Raw r, float est) {
+    if (r.y == BP_SPECIAL) {
+      sp[st - n_ids] = est;
+    } else if (r.y == BP_EMPTY || r.y == (st & kmask)) {
+      bp[st >> kshift] = make_uint2(__float_as_uint(est), st & kmask);
+    } else {
+      return ovf_set(st, est);
+    }
+    return true;
+  }
+};
 
 enum : uint32_t { PH_IDLE = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINISH = 3, PH_EXIT = 4 };
 

@@ -145,39 +145,56 @@ static PathPool make_pool(lmb_ctx* ctx) {
   return p;
 }
 
-// (Re)allocates the A* arena: `slots` query slots of {best[n_states] f32, node list, open-list spill}.
-static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
-  AStarArena& a = ctx->arena;
+static const uint32_t OVF_CAP = 1024;  // compact layout: overflow-table entries per slot (power of two)
+
+// Byte layout of one arena slot: best_estimates region | node list | open-list spill (16 B part,
+// depth part) | overflow table (compact layout only).
+static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, bool compact, AStarArena& a) {
   a.n_ids = ctx->n_ids;
   a.kshift = ctx->kshift;
   a.n_states = ctx->n_ids + ctx->nav.n_links + 2;
   a.node_cap = node_cap;
   a.heap_cap = heap_cap;
+  a.compact = compact ? 1u : 0u;
+  a.ovf_cap = compact ? OVF_CAP : 0u;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t spill = heap_cap > AT_HEAP_SM ? heap_cap - AT_HEAP_SM : 0;
-  size_t best_bytes = ((size_t)a.n_states * 4 + 255) & ~(size_t)255;
-  size_t node_bytes = ((size_t)node_cap * 8 + 255) & ~(size_t)255;
-  size_t heap_bytes = (spill * 16 + 255) & ~(size_t)255;
-  size_t heapd_bytes = (spill * 4 + 255) & ~(size_t)255;
-  a.nodes_offset = best_bytes;
-  a.heap_offset = best_bytes + node_bytes;
-  a.heapd_offset = a.heap_offset + heap_bytes;
-  a.slot_stride = a.heapd_offset + heapd_bytes;
+  if (compact) {
+    const size_t n_polys = ctx->n_ids >> ctx->kshift;
+    a.special_offset = up(n_polys * 8);
+    a.best_bytes = a.special_offset + up((size_t)(ctx->nav.n_links + 2) * 4);
+  } else {
+    a.special_offset = 0;
+    a.best_bytes = up((size_t)a.n_states * 4);
+  }
+  a.nodes_offset = a.best_bytes;
+  a.heap_offset = a.nodes_offset + up((size_t)node_cap * 8);
+  a.heapd_offset = a.heap_offset + up(spill * 16);
+  a.ovf_offset = a.heapd_offset + up(spill * 4);
+  a.slot_stride = a.ovf_offset + up((size_t)a.ovf_cap * 8);
+}
+
+// (Re)allocates the A* arena: `slots` query slots.
+static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
+  AStarArena& a = ctx->arena;
+  arena_layout(ctx, node_cap, heap_cap, ctx->best_compact, a);
   a.n_slots = slots;
   a.base = nullptr;
   ctx->d_arena.release();
   CUDA_TRY(ctx, ctx->d_arena.reserve_exact(a.slot_stride * (size_t)slots));
   a.base = ctx->d_arena.p;
   if (getenv("LMB_DEBUG"))
-    fprintf(stderr, "[lmb] A* arena: %u slots x %.2f MB (n_states %u, node_cap %u, heap_cap %u, kshift %u)\n", slots,
-            a.slot_stride / 1048576.0, a.n_states, node_cap, heap_cap, a.kshift);
+    fprintf(stderr, "[lmb] A* arena: %u slots x %.2f MB (n_states %u, node_cap %u, heap_cap %u, kshift %u, %s best)\n",
+            slots, a.slot_stride / 1048576.0, a.n_states, node_cap, heap_cap, a.kshift, a.compact ? "compact" : "dense");
   launch_arena_init(a, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
   return LMB_OK;
 }
 
 static size_t arena_slot_bytes(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap) {
-  const size_t n_states = (size_t)ctx->n_ids + ctx->nav.n_links + 2;
-  return n_states * 4 + (size_t)node_cap * 8 + (size_t)heap_cap * 20 + 1024;
+  AStarArena a{};
+  arena_layout(ctx, node_cap, heap_cap, ctx->best_compact, a);
+  return a.slot_stride;
 }
 
 static size_t arena_budget(const lmb_ctx* ctx) {
@@ -493,6 +510,37 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
     const uint32_t n_states = ctx->n_ids + nav.n_links + 2;
     ctx->arena_node_cap = std::max<uint32_t>(n_states / 4 + 1024, d->n_region_numbers + 64);
     ctx->arena_heap_cap = AT_HEAP_SM + std::max<uint32_t>(1024, n_states / 64);
+    // best_estimates layout: compact (one entry per polygon) when the polygon graph — edges and
+    // off-mesh links — is a forest: a search then enters every polygon through one edge only.
+    // With a single cycle a search comes round both ways and enters whole regions twice, so
+    // anything else starts dense.  (A compact query that fills its overflow table is re-run
+    // dense and switches the context for good, see run_astar; LMB_ASTAR_COMPACT=1 forces compact
+    // as the starting layout for tests of that path, LMB_ASTAR_DENSE=1 forces dense.)
+    {
+      std::vector<uint32_t> parent(d->n_polys);
+      for (uint32_t p = 0; p < d->n_polys; p++) parent[p] = p;
+      auto find = [&](uint32_t x) {
+        while (parent[x] != x) x = parent[x] = parent[parent[x]];
+        return x;
+      };
+      uint64_t connections = 0, components = d->n_polys;
+      auto join = [&](uint32_t a, uint32_t b) {
+        connections++;
+        a = find(a), b = find(b);
+        if (a != b) parent[a] = b, components--;
+      };
+      for (uint32_t p = 0; p < d->n_polys; p++)
+        for (uint32_t e = d->poly_edge_begin[p]; e < d->poly_edge_begin[p + 1]; e++)
+          if (d->edge_neighbor[e] != LMB_NONE && d->edge_neighbor[e] > p) join(p, d->edge_neighbor[e]);
+      std::vector<uint32_t> link_src(d->n_links, LMB_NONE);
+      if (d->node_link_begin)
+        for (uint32_t p = 0; p < d->n_polys; p++)
+          for (uint32_t k = d->node_link_begin[p]; k < d->node_link_begin[p + 1]; k++) link_src[d->node_links[k]] = p;
+      for (uint32_t l = 0; l < d->n_links; l++)
+        if (link_src[l] != LMB_NONE) join(link_src[l], d->link_dst_node[l]);
+      const bool forest = connections + components == d->n_polys;
+      ctx->best_compact = ctx->kshift != 0 && (forest || getenv("LMB_ASTAR_COMPACT")) && !getenv("LMB_ASTAR_DENSE");
+    }
     ctx->arena = AStarArena{};
     ctx->d_arena.release();
   }
@@ -547,24 +595,57 @@ static int32_t compact_pool(lmb_ctx* ctx, unsigned long long needed_free) {
   return LMB_OK;
 }
 
-static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
+// Enlarges the pool keeping every entry where it is (offsets stay valid).  Used by the batch
+// query API, whose finished corridors are referenced by offset only — compaction, which keeps
+// the corridors owned by agent slots, would drop them.
+static int32_t grow_pool(lmb_ctx* ctx, unsigned long long needed_free) {
   cudaStream_t s = ctx->stream;
-  uint32_t n = q.n;
-  CUDA_TRY(ctx, cudaMemsetAsync(q.out_status, 0, n * sizeof(uint32_t), s));
-  // Make room for the expected corridors up front: a query that finishes its search but
-  // cannot allocate its corridor has to be searched again.
+  int other = 1 - ctx->pool_cur;
+  unsigned long long want = ctx->pool_capacity + needed_free;
+  if (want > POOL_MAX_ENTRIES)
+    return ctx->fail(LMB_ERR_CAPACITY, "path pool would exceed %llu entries", POOL_MAX_ENTRIES);
+  ctx->d_pool[other].release();
+  CUDA_TRY(ctx, ctx->d_pool[other].reserve_exact(want));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pool[other].p, ctx->d_pool[ctx->pool_cur].p,
+                                ctx->pool_capacity * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+  // allocations that failed still advanced the cursor: put it back at the old end
+  const unsigned long long cursor = ctx->pool_capacity;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pool_cursor.p, &cursor, sizeof(cursor), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  ctx->d_pool[ctx->pool_cur].release();
+  ctx->pool_cur = other;
+  ctx->pool_capacity = want;
+  return LMB_OK;
+}
+
+// Makes room for the corridors n queries are expected to produce (compacting dead corridors away
+// if needed).  A query that finishes its search but cannot allocate its corridor has to be
+// searched again, so this runs before the searches; returns the entry count reserved.
+static int32_t prepare_pool(lmb_ctx* ctx, uint32_t n, unsigned long long* needed_out) {
+  cudaStream_t s = ctx->stream;
   double per_query = ctx->path_len_estimate > 0.0 ? ctx->path_len_estimate * 1.25 + 16.0
                                                   : std::min(std::max(2.0 * std::sqrt((double)ctx->nav.n_polys), 64.0), 65536.0);
   unsigned long long needed = (unsigned long long)(per_query * n) + 1024;
   needed = std::min(needed, POOL_MAX_ENTRIES / 2);  // first guess only; overflow doubles it
+  unsigned long long cursor = 0;
+  CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  if (cursor + needed > ctx->pool_capacity) {
+    int32_t st = compact_pool(ctx, needed);
+    if (st != LMB_OK) return st;
+  }
+  if (needed_out) *needed_out = needed;
+  return LMB_OK;
+}
+
+static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
+  cudaStream_t s = ctx->stream;
+  uint32_t n = q.n;
+  CUDA_TRY(ctx, cudaMemsetAsync(q.out_status, 0, n * sizeof(uint32_t), s));
+  unsigned long long needed = 0;
   {
-    unsigned long long cursor = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(&cursor, ctx->d_pool_cursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if (cursor + needed > ctx->pool_capacity) {
-      int32_t st = compact_pool(ctx, needed);
-      if (st != LMB_OK) return st;
-    }
+    int32_t st = prepare_pool(ctx, n, &needed);
+    if (st != LMB_OK) return st;
   }
   {
     int32_t st = ensure_arena(ctx, n);
@@ -597,12 +678,13 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     ctx->timings.path_nodes += ctx->h_counters->path_nodes_total;
     ctx->timings.kernel_launches += 2;  // k_astar + k_path_fixup
     uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
+    const uint32_t rd = ctx->h_counters->n_retry_dense;
     done_total += ctx->h_counters->n_done;
     nodes_total += ctx->h_counters->path_nodes_total;
     explored_total += ctx->h_counters->explored_total;
     if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
     if (done_total) ctx->explored_estimate = (double)explored_total / (double)done_total;
-    if (ra == 0 && rp == 0) return LMB_OK;
+    if (ra == 0 && rp == 0 && rd == 0) return LMB_OK;
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);
     CUDA_TRY(ctx, cudaMemcpy(h_status.data(), q.out_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -611,13 +693,17 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
       if (h_status[i] >= 2) retry.push_back(i);
     if (rp) {
       needed *= 2;
-      int32_t st = compact_pool(ctx, needed);
+      // agent paths survive compaction through their slots; batch-query corridors only by offset
+      int32_t st = q.slot ? compact_pool(ctx, needed) : grow_pool(ctx, needed);
       if (st != LMB_OK) return st;
     }
-    if (ra) {
+    if (rd) ctx->best_compact = false;  // compact best_estimates overflowed: dense from now on
+    if (ra || rd) {
       // node list or open-list spill too small: double both; the slot count follows the budget
-      ctx->arena_node_cap *= 2;
-      ctx->arena_heap_cap = AT_HEAP_SM + (ctx->arena_heap_cap - AT_HEAP_SM) * 2;
+      if (ra) {
+        ctx->arena_node_cap *= 2;
+        ctx->arena_heap_cap = AT_HEAP_SM + (ctx->arena_heap_cap - AT_HEAP_SM) * 2;
+      }
       const size_t per_slot = arena_slot_bytes(ctx, ctx->arena_node_cap, ctx->arena_heap_cap);
       const size_t budget = arena_budget(ctx);
       uint32_t slots = ctx->arena.n_slots;
@@ -723,6 +809,8 @@ int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, con
   }
   // Paths of batch queries live in the pool only until they are copied out: remember the
   // cursor and rewind afterwards (agent paths are never touched).
+  st = prepare_pool(ctx, n, nullptr);  // may compact: do it before the cursor is remembered
+  if (st != LMB_OK) return st;
   unsigned long long cursor0 = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&cursor0, ctx->d_pool_cursor.p, sizeof(cursor0), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
@@ -803,6 +891,8 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
     q.override_type = ctx->d_override_type.p;
     q.override_cost = ctx->d_override_cost.p;
   }
+  st = prepare_pool(ctx, n, nullptr);  // may compact: do it before the cursor is remembered
+  if (st != LMB_OK) return st;
   unsigned long long cursor0 = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&cursor0, ctx->d_pool_cursor.p, sizeof(cursor0), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));

@@ -14,7 +14,8 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
 
 // ---- kernel 2: batched A* (k_astar.cu) ----
 constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
-constexpr uint32_t AT_HEAP_SM = 40;   // open-list entries per query held in shared memory (20 B each)
+constexpr uint32_t AT_HEAP_SM = 40;   // open-list entries per query held in shared memory (20 B each); the
+                                      // spill region of a slot holds heap_cap - AT_HEAP_SM
 
 struct AStarArena {
   uint8_t* base;          // device memory for all slots
@@ -28,6 +29,12 @@ struct AStarArena {
   size_t nodes_offset;    // byte offset of the node list {state, prev} inside a slot
   size_t heap_offset;     // byte offset of the open-list spill (16 B part) inside a slot
   size_t heapd_offset;    // byte offset of the open-list spill (depth part) inside a slot
+  // best_estimates layout (k_astar_common.cuh): dense f32[n_states] at offset 0, or compact
+  uint32_t compact;       // 1 = per-polygon entries + specials + overflow table
+  uint32_t ovf_cap;       // overflow-table entries (power of two)
+  size_t special_offset;  // compact: f32[n_links + 2]
+  size_t ovf_offset;      // compact: uint2[ovf_cap]
+  size_t best_bytes;      // bytes of the best_estimates region (dense array, or polygons + specials)
 };
 
 struct AStarQueries {
@@ -47,7 +54,7 @@ struct AStarQueries {
   const uint32_t* slot;        // [n] agent slot to receive the path, or NULL
   // outputs
   uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool
-                               //     overflow)
+                               //     overflow), 5 = retry with the dense best_estimates layout
   uint32_t* out_success;       // [n]
   uint32_t* out_explored;      // [n]
   uint32_t* out_path_off;      // [n] offset into the path pool
@@ -68,6 +75,7 @@ struct AStarCounters {  // device-resident
   unsigned int queue_head;
   unsigned int n_retry_arena;
   unsigned int n_retry_pool;
+  unsigned int n_retry_dense;
   unsigned int n_done;
   unsigned long long explored_total;
   unsigned long long path_nodes_total;
@@ -79,7 +87,7 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
 void launch_order_queries(uint32_t n, const uint32_t* q_slot, const uint32_t* slot_cost_hint, uint32_t unknown_hint,
                           uint32_t* order, cudaStream_t stream);
 void launch_build_edge_dist(const EdgeRec* recs, uint32_t n_ids, uint32_t kshift, float* out, cudaStream_t stream);
-uint32_t astar_resident_queries_per_sm();  // of the kernel variant in use
+uint32_t astar_resident_queries_per_sm();
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
 // ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----

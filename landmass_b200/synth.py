@@ -83,6 +83,39 @@ def maze_mesh(rooms: int, seed: int = SEED) -> ValidNavigationMesh:
     return _quads_from_open(maze_open_mask(rooms, seed)).validate()
 
 
+def loopy_maze_mesh(rooms: int, extra_openings: int, seed: int = SEED) -> ValidNavigationMesh:
+    """A perfect maze with `extra_openings` more walls removed (each closes one cycle), so a search
+    can enter some polygons through more than one edge."""
+    mask = maze_open_mask(rooms, seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    walls = [(2 * y + 1, 2 * x + 2) for y in range(rooms) for x in range(rooms - 1)]
+    walls += [(2 * y + 2, 2 * x + 1) for y in range(rooms - 1) for x in range(rooms)]
+    closed = [w for w in walls if not mask[w]]
+    for i in rng.permutation(len(closed))[:extra_openings]:
+        mask[closed[i]] = True
+    return _quads_from_open(mask).validate()
+
+
+def rosette_mesh(n_sides: int = 12, rings: int = 3) -> ValidNavigationMesh:
+    """A regular n-gon surrounded by `rings` rings of n quads (all convex, CCW): a polygon with more
+    than 8 edges forces the CSR state ids of the A* kernel."""
+    ang = 2.0 * np.pi * np.arange(n_sides) / n_sides
+    verts = []
+    for r in range(rings + 1):
+        rad = 2.0 + 2.0 * r
+        verts += [(rad * np.cos(a), rad * np.sin(a), 0.0) for a in ang]
+    polys = [list(range(n_sides))]
+    types = [0]
+    for r in range(rings):
+        a0, b0 = r * n_sides, (r + 1) * n_sides
+        for i in range(n_sides):
+            j = (i + 1) % n_sides
+            polys.append([a0 + i, b0 + i, b0 + j, a0 + j])
+            types.append(0)
+    return NavigationMesh(vertices=np.array(verts, dtype=np.float32), polygons=polys,
+                          polygon_type_indices=types).validate()
+
+
 def random_points_on_mesh(mesh: ValidNavigationMesh, n: int, rng, lo: float = 0.1, hi: float = 0.9):
     """Uniform over polygons (axis-aligned quads): polygon min corner + uniform offset in
     [lo, hi]^2 of its extent.  Returns (points (n,3) f32, polygon index (n,))."""

@@ -1,0 +1,160 @@
+"""CUDA-vs-oracle parity of the A* kernel's data-layout variants (k_astar.cu, k_astar_common.cuh):
+CSR vs padded state ids, dense vs compact best_estimates (incl. the overflow table and the
+fallback to dense), slot reuse (both restore paths), arena-overflow retries and the
+longest-first query order.  Everything here is bit-exact: corridors, portal edge indices,
+explored_nodes."""
+import numpy as np
+import pytest
+
+from landmass_b200 import _abi, synth
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["success", "explored", "begin", "nodes", "portals"]
+
+
+def backends(flat, max_agents=4096, flags=0, **kw):
+    from landmass_b200._native import NativeBackend
+    from oracle.oracle_py import OracleBackend
+
+    gpu = NativeBackend(max_agents=max_agents, flags=flags, **kw)
+    cpu = OracleBackend(flags=flags)
+    gpu.navdata_upload(flat)
+    cpu.navdata_upload(flat)
+    return gpu, cpu
+
+
+def assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=None):
+    g = gpu.find_paths(sn, sp, en, ep, path_capacity=cap)
+    c = cpu.find_paths(sn, sp, en, ep, path_capacity=cap)
+    for a, b, name in zip(g, c, NAMES):
+        assert np.array_equal(a, b), name
+    return g
+
+
+def centre_queries(mesh, pairs):
+    sn = np.array([a for a, _ in pairs], dtype=np.uint32)
+    en = np.array([b for _, b in pairs], dtype=np.uint32)
+    return sn, mesh.poly_center[sn].astype(np.float32), en, mesh.poly_center[en].astype(np.float32)
+
+
+def test_csr_state_ids_polygon_with_12_edges():
+    """A 12-gon makes max edges > 8: the kernel falls back to CSR edge ids (the state's own record
+    is read before the polygon's records can be addressed)."""
+    mesh = synth.rosette_mesh(12, 3)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    pairs = [(a, b) for a in range(mesh.n_polys) for b in range(mesh.n_polys)]
+    g = assert_same_paths(gpu, cpu, *centre_queries(mesh, pairs))
+    assert g[0].all()
+
+
+def test_padded_ids_with_8_record_polygons():
+    """Hexagon + ring: max edges in (4, 8] -> 8 records per polygon, two chunks per expansion."""
+    mesh = synth.rosette_mesh(7, 4)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    pairs = [(a, b) for a in range(mesh.n_polys) for b in range(mesh.n_polys)]
+    g = assert_same_paths(gpu, cpu, *centre_queries(mesh, pairs))
+    assert g[0].all()
+
+
+@pytest.mark.parametrize("extra", [0, 6, 40])
+def test_compact_best_with_overflow_and_slot_reuse(extra, capfd, monkeypatch):
+    """Perfect mazes (forests) use the compact best_estimates layout.  With extra openings the
+    layout is only used when forced; short searches then complete through the overflow table while
+    long ones fill it and are re-run dense.  128 slots for 1500 queries re-use every slot ~12
+    times (scatter and dense restore)."""
+    monkeypatch.setenv("LMB_DEBUG", "1")
+    monkeypatch.setenv("LMB_ASTAR_COMPACT", "1")
+    mesh = synth.loopy_maze_mesh(28, extra)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat, astar_slots=128)
+    rng = np.random.Generator(np.random.PCG64(17 + extra))
+    nq = 1500
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    # short queries (scatter restore) next to long ones (dense restore)
+    en[:300] = sn[:300]
+    ep[:300] = sp[:300] + np.float32(0.05)
+    g = assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
+    assert g[0].all()
+    err = capfd.readouterr().err
+    assert "compact best" in err and (extra > 0 or "dense best" not in err)
+
+
+def test_forest_detection_picks_layout(capfd, monkeypatch):
+    monkeypatch.setenv("LMB_DEBUG", "1")
+    for mesh, want in [(synth.maze_mesh(12), "compact best"), (synth.loopy_maze_mesh(12, 1), "dense best"),
+                       (synth.grid_mesh(8, 8), "dense best")]:
+        gpu, cpu = backends(synth.single_island_flat(mesh))
+        assert_same_paths(gpu, cpu, *centre_queries(mesh, [(0, mesh.n_polys - 1), (3, 5)]))
+        assert want in capfd.readouterr().err
+        gpu.close()
+
+
+def test_compact_best_falls_back_to_dense(capfd, monkeypatch):
+    """Compact layout forced on a maze with cycles: long searches enter more than 512 polygons a
+    second time, the overflow table fills, the queries are re-run and the context switches to the
+    dense layout — results unchanged."""
+    monkeypatch.setenv("LMB_DEBUG", "1")
+    monkeypatch.setenv("LMB_ASTAR_COMPACT", "1")
+    rooms = 64
+    base = synth.maze_mesh(rooms)
+    mesh = synth.loopy_maze_mesh(rooms, base.n_polys // 17)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    rng = np.random.Generator(np.random.PCG64(23))
+    nq = 200
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    g = assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
+    assert g[0].all()
+    err = capfd.readouterr().err
+    assert "compact best" in err and "dense best" in err
+    # and again on the now-dense context
+    assert_same_paths(gpu, cpu, sn[::-1].copy(), sp[::-1].copy(), en[::-1].copy(), ep[::-1].copy(), cap=1 << 21)
+
+
+def test_dense_best_slot_reuse_and_arena_retry(capfd, monkeypatch):
+    """Open grid (dense layout): corner-to-corner searches outgrow the initial node list
+    (n_states / 4) -> retry with a doubled arena; 64 slots re-used by 400 queries."""
+    monkeypatch.setenv("LMB_DEBUG", "1")
+    mesh = synth.grid_mesh(120, 120)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat, astar_slots=64)
+    rng = np.random.Generator(np.random.PCG64(29))
+    nq = 400
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    sp[:2] = [[0.5, 0.5, 0], [119.5, 0.5, 0]]
+    sn[:2] = [0, 119]
+    ep[:2] = [[119.5, 119.5, 0], [0.5, 119.5, 0]]
+    en[:2] = [120 * 120 - 1, 119 * 120]
+    en[100:200] = sn[100:200]
+    ep[100:200] = sp[100:200] + np.float32(0.05)
+    assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
+    err = capfd.readouterr().err
+    assert err.count("A* arena") >= 2 and "compact best" not in err
+
+
+def test_step_more_agents_than_slots_longest_first_order():
+    """The step orders a batch longest-first from the previous frame's explored_nodes when it has
+    more queries than slots.  The order must not change any result: every agent re-plans on
+    three consecutive frames (hints absent, then present) and matches the oracle each time."""
+    mesh = synth.maze_mesh(24)
+    flat = synth.single_island_flat(mesh)
+    n = 1200
+    gpu, cpu = backends(flat, flags=_abi.CONFIG_NO_AVOIDANCE, astar_slots=128)
+    ag = synth.make_agents(mesh, n)
+    opts = synth.default_options()
+    for frame in range(3):
+        og = gpu.step(ag, None, opts, 1.0 / 60.0)
+        oc = cpu.step(ag, None, opts, 1.0 / 60.0)
+        assert np.array_equal(og["state"], oc["state"])
+        assert gpu.pathing_results() == cpu.pathing_results()
+        assert len(gpu.pathing_results()) == n  # AGENT_RESET stays set: everyone re-plans
+        np.testing.assert_allclose(og["desired_velocity"], oc["desired_velocity"], rtol=1e-4, atol=1e-6)
+        for slot in range(0, n, 97):
+            gp, cp = gpu.agent_path(slot), cpu.agent_path(slot)
+            assert np.array_equal(gp[0], cp[0]) and np.array_equal(gp[1], cp[1])
