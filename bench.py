@@ -36,6 +36,10 @@ ROOMS = 256
 AGENTS_PER_GPU = 100_000
 DT = 1.0 / 60.0
 B_STEP = 240.0  # algorithmic bytes per steady agent-update
+# DRAM bytes per explored node of k_astar, from the one `ncu --set full` capture of a fully loaded
+# launch (profiles/r01_ncu_astar_loaded.md: dram read + write / explored nodes).  The bench-size
+# launch itself cannot be captured: kernel replay would have to save and restore its ~85 GB arena.
+NCU_DRAM_BYTES_PER_EXPLORED = 78.0
 
 
 def measured_peak_gbs():
@@ -154,7 +158,8 @@ def workload_config(args, n_gpus, sample_note=None):
                     "funnel, ORCA avoidance)",
         "agents_per_gpu": args.agents, "polygons": 2 * args.rooms * args.rooms - 1,
         "parallelism": f"agents sharded x{n_gpus}, navmesh replicated, NCCL all-gather of 32 B/agent",
-        "cache": "inputs and A* working set (per-warp arenas, GBs) far exceed the 126 MB L2; no flush needed",
+        "cache": "inputs and A* working set (one arena slot per query in flight, ~85 GB) far exceed the "
+                 "126 MB L2; no flush needed",
     }
     if sample_note:
         cfg["sample"] = sample_note
@@ -319,9 +324,15 @@ def main():
                          "astar": float(mean_phase[2]), "follow": float(mean_phase[3]),
                          "avoidance": float(mean_phase[4]), "wall_per_step": wall_ms},
             "roofline": {"bound": "hbm", "kernel": "k_astar", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "note": "latency/divergence-bound graph search over an L2-resident navmesh; "
-                                 "algorithmic bytes = 32/query + 8/corridor node + 96/explored node"},
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps,
+                         "traffic_source": "ncu dram bytes per explored node of a fully loaded smaller "
+                                           "launch (profiles/r01_ncu_astar_loaded.md) x explored nodes of this "
+                                           "launch; the bench-size launch is not capturable (85 GB arena)",
+                         "algorithmic_bytes": astar_bytes, "peak_source": peak_src,
+                         "note": "latency-bound graph search: one dependent chain per query (pop -> "
+                                 "records -> best[] probes -> push), random 32-byte sectors of a per-query "
+                                 "arena; algorithmic bytes = 32/query + 8/corridor node + 96/explored node"},
         }
         if e2e:
             line["e2e"] = e2e
