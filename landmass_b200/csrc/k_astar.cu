@@ -381,10 +381,23 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               break;
             }
           }
-          uint32_t acc = 0;
+          // accept = candidate and not (best <= estimate); the common cases of the probe (tracked /
+          // absent) are resolved without branches, the overflow table (compact layout) behind one
+          uint32_t acc = 0, slow = 0;
 #pragma unroll
-          for (int j = 0; j < 4; j++)
-            acc |= (((cand >> j) & 1u) && !(bs.value_edge(r[j].twin, praw[j]) <= es[j])) ? (1u << j) : 0u;
+          for (int j = 0; j < 4; j++) {
+            bool need_table = false;
+            const float bv = bs.value_fast(r[j].twin, praw[j], need_table);
+            acc |= !(bv <= es[j]) ? (1u << j) : 0u;
+            slow |= need_table ? (1u << j) : 0u;
+          }
+          acc &= cand;
+          slow &= cand;
+          if (slow) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (((slow >> j) & 1u) && bs.value_edge(r[j].twin, praw[j]) <= es[j]) acc &= ~(1u << j);
+          }
           // The lanes of the warp step through their k-th accepted successor together
           // (ascending j = ascending edge index).
           while (acc) {

@@ -157,6 +157,10 @@ struct BestStore<false> {
   __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return __ldcg(b + st); }
   __device__ __forceinline__ float value(uint32_t, Raw r) const { return r; }
   __device__ __forceinline__ float value_edge(uint32_t, Raw r) const { return r; }
+  __device__ __forceinline__ float value_fast(uint32_t, Raw r, bool& need_table) const {
+    need_table = false;
+    return r;
+  }
   __device__ __forceinline__ bool store(uint32_t st, Raw, float est) {
     b[st] = est;
     return true;
@@ -207,6 +211,12 @@ struct BestStore<true> {
     if (r.y == BP_SPECIAL || r.y == (st & kmask)) return __uint_as_float(r.x);
     if (r.y == BP_EMPTY) return __builtin_huge_valf();
     return ovf_get(st);
+  }
+  // edge states only: branch-free for "tracked" and "absent"; anything else is in the table
+  __device__ __forceinline__ float value_fast(uint32_t st, Raw r, bool& need_table) const {
+    const bool tracked = r.y == (st & kmask);
+    need_table = !tracked & (r.y != BP_EMPTY);
+    return tracked ? __uint_as_float(r.x) : __builtin_huge_valf();
   }
   // edge states only (never BP_SPECIAL)
   __device__ __forceinline__ float value_edge(uint32_t st, Raw r) const {
