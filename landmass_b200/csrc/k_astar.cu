@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(AT_THREADS, BPS)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);  // queries per block
-  extern __shared__ uint4 s_heap[];  // [HS][QPB] uint4, then the same shape of u32 depths
+  extern __shared__ uint4 s_heap[];  // [HS][QPB] open-list entries
   __shared__ float s_cost[LMB_MAX_TYPES];
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31;
@@ -73,9 +73,11 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
   Heap<QPB, HS> heap;
   heap.sm = s_heap + qib;
-  heap.smd = reinterpret_cast<uint32_t*>(s_heap + (size_t)HS * QPB) + qib;
   heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
-  heap.gmd = reinterpret_cast<uint32_t*>(slot_base + arena.heapd_offset);
+  // the finished search's corridor is staged in the slot's (no longer needed) best_estimates
+  // region as raw (state, next state) pairs, goal first, before it is copied to the path pool
+  uint2* const stage = reinterpret_cast<uint2*>(slot_base);
+  const uint32_t stage_cap = COMPACT ? (arena.n_ids >> arena.kshift) : arena.n_states / 2;
   heap.len = 0;
 
   const EdgeRec* __restrict__ recs = nav.edges;
@@ -210,7 +212,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             bs.store(ST_START, bs.probe(ST_START), est);
             nodes[0] = make_uint2(ST_START, LMB_NONE);
             n_nodes = 1;
-            heap.push({0.0f, est, 0u, ST_START, 0u});
+            heap.push({0.0f, est, 0u, ST_START});
             phase = PH_SEARCH;
           }
         }
@@ -290,7 +292,6 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           has_links = nav.node_link_begin[poly + 1] > nav.node_link_begin[poly];
         }
         const float cur_cost = cur.cost;
-        const uint32_t depth1 = cur.depth + 1;
         const float cur_type_cost = cost_of(cur_type);
         const bool to_end = poly == end_node;  // single successor GoToEnd (pathfinding.rs:152-155)
 
@@ -343,21 +344,12 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             explored++;
             if (s == ST_END) {
-              // goal: allocate the corridor and start the walk (astar.rs:86-105)
-              const uint32_t L = cur.depth;  // number of corridor nodes (>= 1: Start)
-              const unsigned long long off = atomicAdd(pool.cursor, (unsigned long long)L);
-              if (off + L > pool.capacity) {
-                status = 3;
-                phase = PH_FINISH;
-              } else {
-                success = 1;
-                path_off = (uint32_t)off;
-                path_len = L;
-                w_node = cur.index;  // the End node; its record is loaded next iteration
-                w_next = ST_END;
-                w_pos = L;
-                phase = PH_WALK;
-              }
+              // goal: walk the back-pointers (astar.rs:86-105); the End node's record is loaded
+              // next iteration
+              w_node = cur.index;
+              w_next = ST_END;
+              w_pos = 0;
+              phase = PH_WALK;
               live = false;
               break;
             }
@@ -373,7 +365,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
                 } else {
                   bs.store(ST_END, raw_e, est);
                   nodes[n_nodes] = make_uint2(ST_END, cur.index);
-                  heap.push({ncost, est, n_nodes, ST_END, depth1});
+                  heap.push({ncost, est, n_nodes, ST_END});
                   n_nodes++;
                 }
               }
@@ -415,7 +407,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               break;
             }
             nodes[n_nodes] = make_uint2(s2, cur.index);
-            heap.push({ncost, est, n_nodes, s2, depth1});
+            heap.push({ncost, est, n_nodes, s2});
             n_nodes++;
           }
           if (go_dense) break;
@@ -451,7 +443,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             bs.store(s2, raw_l, est);
             nodes[n_nodes] = make_uint2(s2, cur.index);
-            heap.push({ncost, est, n_nodes, s2, depth1});
+            heap.push({ncost, est, n_nodes, s2});
             n_nodes++;
           }
         }
@@ -462,14 +454,29 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       }
     } else if (phase == PH_WALK) {
       // ============ WALK (part 2): consume the back-pointer loaded above ============
-      // (astar.rs:86-105) one node per iteration, written backwards as (state, next state)
-      if (w_rec.x != ST_END) pool.entries[(size_t)path_off + w_pos] = make_uint2(w_rec.x, w_next);
+      // (astar.rs:86-105) one node per iteration, staged goal-first as (state, next state)
+      if (w_rec.x != ST_END) {
+        if (w_pos < stage_cap) stage[w_pos] = make_uint2(w_rec.x, w_next);
+        w_pos++;
+      }
       w_next = w_rec.x;
-      if (w_rec.y == LMB_NONE) {
-        phase = PH_FINISH;  // wrote the Start node (position 0)
-      } else {
+      if (w_rec.y != LMB_NONE) {
         w_node = w_rec.y;
-        w_pos--;
+      } else {
+        // reached the Start node: the corridor has w_pos nodes; allocate it in the pool
+        phase = PH_FINISH;
+        if (w_pos > stage_cap) {
+          status = 6;  // cannot happen for a simple path (corridor longer than the staging area)
+        } else {
+          const unsigned long long off = atomicAdd(pool.cursor, (unsigned long long)w_pos);
+          if (off + w_pos > pool.capacity) {
+            status = 3;
+          } else {
+            success = 1;
+            path_off = (uint32_t)off;
+            path_len = w_pos;
+          }
+        }
       }
     }
 
@@ -483,6 +490,18 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       const uint32_t src_slot = __shfl_sync(FULL, slot, src);
       uint8_t* base = arena.base + (size_t)src_slot * arena.slot_stride;
       const uint2* nd = reinterpret_cast<const uint2*>(base + arena.nodes_offset);
+      // corridor: staged goal-first in the best_estimates region -> path pool, start-first
+      const uint32_t cL = __shfl_sync(FULL, success ? path_len : 0u, src);
+      const uint32_t staged = __shfl_sync(FULL, phase == PH_FINISH && status != 2 && status != 5 ? w_pos : 0u, src);
+      if (cL) {
+        const uint32_t cOff = __shfl_sync(FULL, path_off, src);
+        const uint2* st = reinterpret_cast<const uint2*>(base);
+        for (uint32_t k = lane; k < cL; k += 32) pool.entries[(size_t)cOff + (cL - 1 - k)] = st[k];
+      } else {
+        (void)__shfl_sync(FULL, path_off, src);
+      }
+      __syncwarp();
+      const uint32_t n_staged = staged < stage_cap ? staged : stage_cap;
       if (!COMPACT) {
         float* b = reinterpret_cast<float*>(base);
         if ((size_t)nn * 16 >= arena.n_states) {
@@ -493,6 +512,9 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           for (uint32_t k = lane; k < n4; k += 32) b4[k] = inf4;
         } else {
           for (uint32_t k = lane; k < nn; k += 32) b[nd[k].x] = F_INF;
+          uint2* st = reinterpret_cast<uint2*>(base);
+          const uint2 e2 = make_uint2(__float_as_uint(F_INF), __float_as_uint(F_INF));
+          for (uint32_t k = lane; k < n_staged; k += 32) st[k] = e2;
         }
       } else {
         uint2* bp = reinterpret_cast<uint2*>(base);
@@ -512,6 +534,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             else
               sp[st - arena.n_ids] = F_INF;
           }
+          const uint2 e2 = make_uint2(__float_as_uint(F_INF), BP_EMPTY);
+          for (uint32_t k = lane; k < n_staged; k += 32) bp[k] = e2;
         }
         if (__shfl_sync(FULL, ovf_used(bs), src)) {
           uint4* o4 = reinterpret_cast<uint4*>(base + arena.ovf_offset);
@@ -541,10 +565,13 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         atomicAdd(&counters->n_retry_arena, 1u);
       } else if (status == 5) {
         atomicAdd(&counters->n_retry_dense, 1u);
+      } else if (status == 6) {
+        atomicAdd(&counters->n_failed, 1u);
       } else {
         atomicAdd(&counters->n_retry_pool, 1u);
       }
       n_nodes = 0;
+      w_pos = 0;
       ovf_clear(bs);
       phase = PH_IDLE;
     }
@@ -673,7 +700,7 @@ template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, bool COMPACT>
 static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                            AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
-  const size_t smem = (size_t)HS * QPB * (sizeof(uint4) + sizeof(uint32_t));
+  const size_t smem = (size_t)HS * QPB * sizeof(uint4);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -704,14 +731,14 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   const bool k4 = arena.kshift == 2;
   if (arena.compact) {
     if (k4)
-      launch_astar_t<16, 40, 4, 2, true>(nav, arena, q, pool, counters, type_raw, stream);
+      launch_astar_t<16, 48, 4, 2, true>(nav, arena, q, pool, counters, type_raw, stream);
     else
-      launch_astar_t<16, 40, 4, 0, true>(nav, arena, q, pool, counters, type_raw, stream);
+      launch_astar_t<16, 48, 4, 0, true>(nav, arena, q, pool, counters, type_raw, stream);
   } else {
     if (k4)
-      launch_astar_t<16, 40, 4, 2, false>(nav, arena, q, pool, counters, type_raw, stream);
+      launch_astar_t<16, 48, 4, 2, false>(nav, arena, q, pool, counters, type_raw, stream);
     else
-      launch_astar_t<16, 40, 4, 0, false>(nav, arena, q, pool, counters, type_raw, stream);
+      launch_astar_t<16, 48, 4, 0, false>(nav, arena, q, pool, counters, type_raw, stream);
   }
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)

@@ -11,11 +11,10 @@ namespace astar_detail {
 constexpr float F_INF = __builtin_huge_valf();
 constexpr uint32_t FULL = 0xffffffffu;
 
-struct HeapEntry {
+struct HeapEntry {  // 16 bytes: one 128-bit shared-memory access, half a sector when spilled
   float cost, estimate;
   uint32_t index;
   uint32_t state;
-  uint32_t depth;
 };
 
 // NodeRef::partial_cmp (astar.rs:67-77) as `a <= b`
@@ -30,36 +29,28 @@ __device__ __forceinline__ bool rev_le(const HeapEntry& x, const HeapEntry& y) {
 // can reach is < HS); SP = true adds the in-place spill to the slot's arena.  The
 // caller picks per operation from the current length, so the common case carries no
 // per-access branch.
-template <uint32_t STRIDE, uint32_t HS>  // HS: entries held in shared memory
+template <uint32_t STRIDE, uint32_t HS>  // HS: entries held in shared memory (even)
 struct Heap {
+  static_assert(HS % 2 == 0, "HS must be even: spilled sibling pairs (2k+1, 2k+2) then share a 32-byte sector");
   uint4* sm;      // this query's column: entry i at sm[i * STRIDE]
-  uint32_t* smd;  // depth column
-  uint4* gm;      // spill: entry i (>= HS) at gm[i - HS]
-  uint32_t* gmd;
+  uint4* gm;      // spill: entry i (>= HS) at gm[i - HS + 1]
   uint32_t len;
   template <bool SP>
   __device__ __forceinline__ HeapEntry get(uint32_t i) const {
     uint4 v;
-    uint32_t d;
-    if (!SP || i < HS) {
+    if (!SP || i < HS)
       v = sm[i * STRIDE];
-      d = smd[i * STRIDE];
-    } else {
-      v = gm[i - HS];
-      d = gmd[i - HS];
-    }
-    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w, d};
+    else
+      v = gm[i - HS + 1];
+    return {__uint_as_float(v.x), __uint_as_float(v.y), v.z, v.w};
   }
   template <bool SP>
   __device__ __forceinline__ void set(uint32_t i, const HeapEntry& e) {
     uint4 v = make_uint4(__float_as_uint(e.cost), __float_as_uint(e.estimate), e.index, e.state);
-    if (!SP || i < HS) {
+    if (!SP || i < HS)
       sm[i * STRIDE] = v;
-      smd[i * STRIDE] = e.depth;
-    } else {
-      gm[i - HS] = v;
-      gmd[i - HS] = e.depth;
-    }
+    else
+      gm[i - HS + 1] = v;
   }
   template <bool SP>
   __device__ __forceinline__ void sift_up(uint32_t pos, const HeapEntry& hole) {

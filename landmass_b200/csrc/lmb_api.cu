@@ -147,8 +147,8 @@ static PathPool make_pool(lmb_ctx* ctx) {
 
 static const uint32_t OVF_CAP = 1024;  // compact layout: overflow-table entries per slot (power of two)
 
-// Byte layout of one arena slot: best_estimates region | node list | open-list spill (16 B part,
-// depth part) | overflow table (compact layout only).
+// Byte layout of one arena slot: best_estimates region | node list | open-list spill |
+// overflow table (compact layout only).
 static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, bool compact, AStarArena& a) {
   a.n_ids = ctx->n_ids;
   a.kshift = ctx->kshift;
@@ -158,7 +158,7 @@ static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_ca
   a.compact = compact ? 1u : 0u;
   a.ovf_cap = compact ? OVF_CAP : 0u;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t spill = heap_cap > AT_HEAP_SM ? heap_cap - AT_HEAP_SM : 0;
+  const size_t spill = (heap_cap > AT_HEAP_SM ? heap_cap - AT_HEAP_SM : 0) + 2;
   if (compact) {
     const size_t n_polys = ctx->n_ids >> ctx->kshift;
     a.special_offset = up(n_polys * 8);
@@ -169,8 +169,7 @@ static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_ca
   }
   a.nodes_offset = a.best_bytes;
   a.heap_offset = a.nodes_offset + up((size_t)node_cap * 8);
-  a.heapd_offset = a.heap_offset + up(spill * 16);
-  a.ovf_offset = a.heapd_offset + up(spill * 4);
+  a.ovf_offset = a.heap_offset + up(spill * 16);
   a.slot_stride = a.ovf_offset + up((size_t)a.ovf_cap * 8);
 }
 
@@ -684,6 +683,8 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     explored_total += ctx->h_counters->explored_total;
     if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
     if (done_total) ctx->explored_estimate = (double)explored_total / (double)done_total;
+    if (ctx->h_counters->n_failed)
+      return ctx->fail(LMB_ERR_CAPACITY, "A*: a corridor did not fit the staging area (%u queries)", ctx->h_counters->n_failed);
     if (ra == 0 && rp == 0 && rd == 0) return LMB_OK;
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);

@@ -14,8 +14,8 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
 
 // ---- kernel 2: batched A* (k_astar.cu) ----
 constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
-constexpr uint32_t AT_HEAP_SM = 40;   // open-list entries per query held in shared memory (20 B each); the
-                                      // spill region of a slot holds heap_cap - AT_HEAP_SM
+constexpr uint32_t AT_HEAP_SM = 48;   // open-list entries per query held in shared memory (16 B each); the
+                                      // spill region of a slot holds heap_cap - AT_HEAP_SM + 1
 
 struct AStarArena {
   uint8_t* base;          // device memory for all slots
@@ -27,8 +27,7 @@ struct AStarArena {
   uint32_t node_cap;      // nodes per slot
   uint32_t heap_cap;      // open-list entries per query (shared memory + spill)
   size_t nodes_offset;    // byte offset of the node list {state, prev} inside a slot
-  size_t heap_offset;     // byte offset of the open-list spill (16 B part) inside a slot
-  size_t heapd_offset;    // byte offset of the open-list spill (depth part) inside a slot
+  size_t heap_offset;     // byte offset of the open-list spill inside a slot
   // best_estimates layout (k_astar_common.cuh): dense f32[n_states] at offset 0, or compact
   uint32_t compact;       // 1 = per-polygon entries + specials + overflow table
   uint32_t ovf_cap;       // overflow-table entries (power of two)
@@ -54,7 +53,7 @@ struct AStarQueries {
   const uint32_t* slot;        // [n] agent slot to receive the path, or NULL
   // outputs
   uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool
-                               //     overflow), 5 = retry with the dense best_estimates layout
+                               //     overflow), 5 = retry with the dense best_estimates layout, 6 = failed
   uint32_t* out_success;       // [n]
   uint32_t* out_explored;      // [n]
   uint32_t* out_path_off;      // [n] offset into the path pool
@@ -76,6 +75,7 @@ struct AStarCounters {  // device-resident
   unsigned int n_retry_arena;
   unsigned int n_retry_pool;
   unsigned int n_retry_dense;
+  unsigned int n_failed;
   unsigned int n_done;
   unsigned long long explored_total;
   unsigned long long path_nodes_total;
