@@ -104,6 +104,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   uint32_t path_off = 0, path_len = 0;
   // walk
   uint32_t w_node = 0, w_next = 0, w_pos = 0;
+  uint32_t hmax = 0;  // largest open list of this query (sizes the next batch's launch shape)
 
   // type cost: override -> archipelago -> 1.0 (pathfinding.rs:73-77)
   auto cost_of = [&](uint32_t t) -> float {
@@ -366,6 +367,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
                   bs.store(ST_END, raw_e, est);
                   nodes[n_nodes] = make_uint2(ST_END, cur.index);
                   heap.push({ncost, est, n_nodes, ST_END});
+                  hmax = max(hmax, heap.len);
                   n_nodes++;
                 }
               }
@@ -408,6 +410,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             nodes[n_nodes] = make_uint2(s2, cur.index);
             heap.push({ncost, est, n_nodes, s2});
+            hmax = max(hmax, heap.len);
             n_nodes++;
           }
           if (go_dense) break;
@@ -444,6 +447,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             bs.store(s2, raw_l, est);
             nodes[n_nodes] = make_uint2(s2, cur.index);
             heap.push({ncost, est, n_nodes, s2});
+            hmax = max(hmax, heap.len);
             n_nodes++;
           }
         }
@@ -561,6 +565,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         atomicAdd(&counters->n_done, 1u);
         atomicAdd(&counters->explored_total, (unsigned long long)explored);
         atomicAdd(&counters->path_nodes_total, (unsigned long long)path_len);
+        atomicAdd(&counters->heap_max_total, (unsigned long long)hmax);
       } else if (status == 2) {
         atomicAdd(&counters->n_retry_arena, 1u);
       } else if (status == 5) {
@@ -572,6 +577,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       }
       n_nodes = 0;
       w_pos = 0;
+      hmax = 0;
       ovf_clear(bs);
       phase = PH_IDLE;
     }
@@ -708,38 +714,56 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  // never more blocks than are resident at once: a block that starts late starts its (long) queries late
   uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
+  const uint32_t resident = (uint32_t)sm_count * BPS * QPB;
+  if (slots > resident) slots = resident;
   uint32_t blocks = (slots + QPB - 1) / QPB;
   AStarArena a = arena;
   a.n_slots = slots;
   k_astar<QPW, HS, BPS, KS, COMPACT><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
-// Launch shape: 256 queries per SM = 4 blocks x 4 warps x 16 queries, 40 open-list entries per
-// query in shared memory (205 KB per SM).  Only half the lanes of a warp own a query: the number
-// of queries in flight is bounded by HBM (the per-query arena slot) and the search by the
-// latency of one lock-step warp iteration, not by warp or issue slots — so a warp that waits
-// for the slowest of 16 instead of 32 pops costs nothing and measured 5-14 % faster.  (Measured
-// and rejected on the 256-maze, 100k queries: 32 queries per warp; 384 queries per SM with 28
-// shared-memory entries — the in-place spill then costs more than the extra slots give; a
-// 4-lanes-per-query variant — lower latency per query but issue-bound, no faster when loaded.)
-uint32_t astar_resident_queries_per_sm() { return 4 * 16 * (AT_THREADS / 32); }
+// Launch shapes.  Only half the lanes of a warp own a query (16 per warp): the number of queries
+// in flight is bounded by HBM (the per-query arena slot) and by shared memory (the open lists),
+// and the search by the latency of one lock-step warp iteration, not by warp or issue slots — a
+// warp that waits for the slowest of 16 instead of 32 pops measured 5-14 % faster.
+//  * small open lists (mazes: a few dozen open branches): 256 queries per SM = 4 blocks x 4 warps
+//    x 16, 48 open-list entries per query in shared memory;
+//  * large open lists (open fields: a wavefront of thousands): 128 queries per SM = 2 blocks, 96
+//    entries in shared memory.  Every spilled heap level is a dependent HBM round trip and these
+//    searches are bound by random-sector HBM traffic, so one more level on chip beats twice the
+//    queries in flight (open 256x256 field, 50k queries: 1.47 s -> 1.09 s).
+// (Measured and rejected: 32 queries per warp; 384 queries per SM with 28 shared-memory entries;
+// 64 / 192 / 384 entries at 192 / 64 / 32 queries per SM; a 4-lanes-per-query variant — lower
+// latency per query but issue-bound, no faster when loaded.)
+uint32_t astar_resident_queries_per_sm(bool big_heap) { return (big_heap ? 2 : 4) * 16 * (AT_THREADS / 32); }
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
+                  AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream) {
   if (q.n == 0) return;
   const bool k4 = arena.kshift == 2;
-  if (arena.compact) {
-    if (k4)
-      launch_astar_t<16, 48, 4, 2, true>(nav, arena, q, pool, counters, type_raw, stream);
-    else
-      launch_astar_t<16, 48, 4, 0, true>(nav, arena, q, pool, counters, type_raw, stream);
-  } else {
-    if (k4)
-      launch_astar_t<16, 48, 4, 2, false>(nav, arena, q, pool, counters, type_raw, stream);
-    else
-      launch_astar_t<16, 48, 4, 0, false>(nav, arena, q, pool, counters, type_raw, stream);
-  }
+#define LMB_ASTAR_LAUNCH(HS, BPS)                                                                       \
+  do {                                                                                                  \
+    if (arena.compact) {                                                                                \
+      if (k4) launch_astar_t<16, HS, BPS, 2, true>(nav, arena, q, pool, counters, type_raw, stream);      \
+      else launch_astar_t<16, HS, BPS, 0, true>(nav, arena, q, pool, counters, type_raw, stream);         \
+    } else {                                                                                            \
+      if (k4) launch_astar_t<16, HS, BPS, 2, false>(nav, arena, q, pool, counters, type_raw, stream);     \
+      else launch_astar_t<16, HS, BPS, 0, false>(nav, arena, q, pool, counters, type_raw, stream);        \
+    }                                                                                                   \
+  } while (0)
+  if (big_heap)
+    LMB_ASTAR_LAUNCH(96, 2);
+  else
+    LMB_ASTAR_LAUNCH(48, 4);
+#undef LMB_ASTAR_LAUNCH
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)
   uint32_t fix_blocks = (q.n + 7) / 8;

@@ -208,7 +208,7 @@ static size_t arena_budget(const lmb_ctx* ctx) {
 
 // Makes sure the arena can run `n_queries` concurrently (up to the slot limit / byte budget).
 static int32_t ensure_arena(lmb_ctx* ctx, uint32_t n_queries) {
-  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * astar_resident_queries_per_sm();
+  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * astar_resident_queries_per_sm(ctx->big_heap);
   uint32_t want = std::min<uint32_t>(max_slots, (n_queries + AT_THREADS - 1) / AT_THREADS * AT_THREADS);
   want = std::max<uint32_t>(want, AT_THREADS);
   if (ctx->arena.base && ctx->arena.n_slots >= want) return LMB_OK;
@@ -539,6 +539,7 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
         if (link_src[l] != LMB_NONE) join(link_src[l], d->link_dst_node[l]);
       const bool forest = connections + components == d->n_polys;
       ctx->best_compact = ctx->kshift != 0 && (forest || getenv("LMB_ASTAR_COMPACT")) && !getenv("LMB_ASTAR_DENSE");
+      ctx->big_heap = !forest;  // first guess: a wavefront; corrected from the first batch's open lists
     }
     ctx->arena = AStarArena{};
     ctx->d_arena.release();
@@ -650,7 +651,7 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     int32_t st = ensure_arena(ctx, n);
     if (st != LMB_OK) return st;
   }
-  unsigned long long done_total = 0, nodes_total = 0, explored_total = 0;
+  unsigned long long done_total = 0, nodes_total = 0, explored_total = 0, heap_max_total = 0;
   const uint32_t* list = nullptr;
   uint32_t n_run = n;
   if (q.slot && n > ctx->arena.n_slots) {
@@ -668,7 +669,7 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     AStarQueries qq = q;
     qq.n = n_run;
     qq.list = list;
-    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, s);
+    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, ctx->big_heap, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
@@ -683,9 +684,14 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     explored_total += ctx->h_counters->explored_total;
     if (done_total) ctx->path_len_estimate = (double)nodes_total / (double)done_total;
     if (done_total) ctx->explored_estimate = (double)explored_total / (double)done_total;
+    heap_max_total += ctx->h_counters->heap_max_total;
     if (ctx->h_counters->n_failed)
       return ctx->fail(LMB_ERR_CAPACITY, "A*: a corridor did not fit the staging area (%u queries)", ctx->h_counters->n_failed);
-    if (ra == 0 && rp == 0 && rd == 0) return LMB_OK;
+    if (ra == 0 && rp == 0 && rd == 0) {
+      // launch shape of the next batch: open lists that outgrow shared memory want the big-heap shape
+      if (done_total >= 16) ctx->big_heap = (double)heap_max_total / (double)done_total > 1.5 * AT_HEAP_SM;
+      return LMB_OK;
+    }
     // overflow: collect the retry list, grow what overflowed, run again
     h_status.resize(n);
     CUDA_TRY(ctx, cudaMemcpy(h_status.data(), q.out_status, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));

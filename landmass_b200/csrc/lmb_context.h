@@ -84,6 +84,7 @@ struct lmb_ctx {
   DevBuf<uint8_t> d_arena;
   uint32_t kshift = 0, n_ids = 0;              // edge-record id space (see EdgeRec)
   uint32_t arena_node_cap = 0, arena_heap_cap = 0;
+  bool big_heap = false;                       // launch shape for large open lists (k_astar.cu)
   bool best_compact = false;                   // best_estimates layout (k_astar_common.cuh)
   DevBuf<AStarCounters> d_counters;
   AStarCounters* h_counters = nullptr;  // pinned

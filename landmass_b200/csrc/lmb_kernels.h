@@ -79,15 +79,16 @@ struct AStarCounters {  // device-resident
   unsigned int n_done;
   unsigned long long explored_total;
   unsigned long long path_nodes_total;
+  unsigned long long heap_max_total;  // sum over finished queries of their largest open list
 };
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream);
+                  AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream);
 // order[] = query indices 0..n-1 sorted by descending cost hint of their agent slot (bucketed)
 void launch_order_queries(uint32_t n, const uint32_t* q_slot, const uint32_t* slot_cost_hint, uint32_t unknown_hint,
                           uint32_t* order, cudaStream_t stream);
 void launch_build_edge_dist(const EdgeRec* recs, uint32_t n_ids, uint32_t kshift, float* out, cudaStream_t stream);
-uint32_t astar_resident_queries_per_sm();
+uint32_t astar_resident_queries_per_sm(bool big_heap);
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
 // ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----

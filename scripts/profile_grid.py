@@ -14,7 +14,8 @@ ag = synth.make_agents(mesh, n)
 ag["position"] = pos
 ag["target"] = np.stack([2048.0 - pos[:, 0], 2048.0 - pos[:, 1], pos[:, 2]], axis=1).astype(np.float32)
 opts = synth.default_options()
-gpu = NativeBackend(max_agents=n)
+import os
+gpu = NativeBackend(max_agents=n, astar_slots=int(os.environ.get("SLOTS", "0")))
 gpu.navdata_upload(flat)
 gpu.agents_upload(ag, None)
 for step in range(2):
