@@ -191,8 +191,11 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
-    # keep stdout to the ONE JSON line: NCCL's banner / debug output goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # keep stdout to the ONE JSON line: everything else any library writes to fd 1 (NCCL prints its
+    # version banner there) goes to stderr; the JSON line is written to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch  # plumbing only: device selection, NCCL all-gather, barriers
 
     from landmass_b200 import _abi, synth
@@ -341,7 +344,7 @@ def main():
         states = np.bincount(out["state"], minlength=9).tolist()
         line["state_histogram"] = states
         sys.stdout.flush()
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     gpu.close()
     if dist is not None:
         dist.barrier()

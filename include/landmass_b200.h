@@ -233,8 +233,8 @@ typedef struct lmb_config {
   uint32_t struct_size;
   int32_t device;            /* CUDA device ordinal */
   uint32_t max_agents;       /* capacity of slot ids */
-  uint32_t astar_slots;      /* concurrent A* queries (warps); 0 = auto */
-  uint64_t scratch_bytes;    /* budget for A* arenas; 0 = auto */
+  uint32_t astar_slots;      /* A* arena slots = queries in flight; 0 = auto (up to 256 per SM) */
+  uint64_t scratch_bytes;    /* byte budget of the A* arena; 0 = auto (60 % of free HBM, <= 110 GB) */
   uint32_t flags;            /* LMB_CONFIG_* */
   uint32_t reserved;
 } lmb_config;
