@@ -268,12 +268,33 @@ def main():
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
+    print(f"[bench rank {rank}] per-step device ms: {[round(x, 1) for x in dev_ms]}", file=sys.stderr)
     out = gpu.agents_download()
     step_ms = float(np.mean(dev_ms)) if world == 1 else wall_ms  # multi-GPU: wall between barriers incl. all-gather
     red = torch.tensor([step_ms, float(np.mean(astar_ms))], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
     step_ms_max, astar_ms_max = float(red[0]), float(red[1])
+
+    # ---- context figure: steady frames of the same agents (no re-plan forced) ----
+    # Not the headline: the agents keep the corridors of the last timed step and only sample,
+    # check their corridor, follow it (funnel) and avoid each other.
+    steady = None
+    if world == 1:
+        ag_steady = dict(ag)
+        ag_steady["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        gpu.agents_upload(ag_steady, None)
+        gpu.step_resident(opts, DT)
+        s_ms, s_rep = [], 0
+        for _ in range(5):
+            gpu.step_resident(opts, DT)
+            T = gpu.step_timings()
+            s_ms.append(T.total_ms)
+            s_rep += T.n_repath
+        steady = {"value": n / (float(np.mean(s_ms)) * 1e-3), "unit": "agent-updates/s",
+                  "ms_per_step": float(np.mean(s_ms)), "repaths_per_step": s_rep / 5.0,
+                  "note": "same agents keeping their corridors: sample x2, corridor check, funnel, ORCA"}
+        gpu.agents_upload(ag, None)
 
     # ---- end-to-end timing through lmb_step with host buffers (`e2e`) ----
     e2e = None
@@ -339,6 +360,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if steady:
+            line["steady_state"] = steady
         if not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         states = np.bincount(out["state"], minlength=9).tolist()

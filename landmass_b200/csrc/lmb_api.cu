@@ -584,14 +584,21 @@ static int32_t compact_pool(lmb_ctx* ctx, unsigned long long needed_free) {
   if (want > POOL_MAX_ENTRIES)
     return ctx->fail(LMB_ERR_CAPACITY, "path pool would exceed %llu entries (live %llu + needed %llu)",
                      POOL_MAX_ENTRIES, live, needed_free);
-  ctx->d_pool[other].release();
-  CUDA_TRY(ctx, ctx->d_pool[other].reserve_exact(want));
+  if (live == 0 && want <= ctx->pool_capacity) {
+    // nothing to keep (every corridor was dropped or replaced): the scan already put the cursor at 0
+    return LMB_OK;
+  }
+  // The two buffers ping-pong and stay allocated: freeing and re-allocating tens of GB every time
+  // costs tens to hundreds of milliseconds of host time with the GPU idle.
+  if (ctx->d_pool[other].cap < want) {
+    ctx->d_pool[other].release();
+    CUDA_TRY(ctx, ctx->d_pool[other].reserve_exact(want));
+  }
   launch_pool_copy(src, ctx->d_pool[other].p, m, ctx->d_scan_tmp.p, s);
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  ctx->d_pool[ctx->pool_cur].release();
   ctx->pool_cur = other;
-  ctx->pool_capacity = want;
+  ctx->pool_capacity = ctx->d_pool[other].cap;
   return LMB_OK;
 }
 

@@ -1,6 +1,6 @@
 """Runs the non-headline BASELINE.json configs at full size on one GPU, checks size-independent
 properties of the outputs (the oracle cannot run these sizes in reasonable time) and prints
-per-phase device timings.  Usage: python scripts/run_configs.py [3] [5] [1]"""
+per-phase device timings.  Usage: python scripts/run_configs.py [3] [4] [5] [1]"""
 import json
 import sys
 import time
@@ -99,6 +99,67 @@ def config5(n=10_000, frames=3, rooms=512):
     gpu.close()
 
 
+def config4(n=100_000, frames=4, k=8, g=128):
+    """Multi-island archipelago: k x k islands of g x g unit quads tiled by translation (boundary
+    links at 0.01), polygon types (x/16 + y/16) mod 3 with costs {1, 2, 5}.  One GPU's share of the
+    4M-agent / 8-GPU configuration (the navmesh is replicated on every GPU)."""
+    from landmass_b200.nav_data import Island, NavigationData, Transform
+
+    types = ((np.arange(g)[None, :] // 16 + np.arange(g)[:, None] // 16) % 3)
+    mesh = synth.grid_mesh(g, g, types=types)
+    nd = NavigationData()
+    for iy in range(k):
+        for ix in range(k):
+            nd.add_island(Island(Transform(translation=(ix * g, iy * g, 0.0), rotation=0.0), mesh))
+    for t, c in ((0, 1.0), (1, 2.0), (2, 5.0)):
+        nd.set_type_index_cost(t, c)
+    nd.update(0.01, 0.25)
+    flat = nd.flatten()
+    n_links = len(flat["link_dst_node"])
+    rng = np.random.Generator(np.random.PCG64(synth.SEED))
+    span = float(k * g)
+    pos = np.zeros((n, 3), dtype=np.float32)
+    tgt = np.zeros((n, 3), dtype=np.float32)
+    pos[:, :2] = rng.uniform(0.1, span - 0.1, size=(n, 2))
+    # targets within ~1.5 islands of the agent: most paths cross at least one island border
+    tgt[:, :2] = np.clip(pos[:, :2] + rng.uniform(-1.5 * g, 1.5 * g, size=(n, 2)), 0.1, span - 0.1)
+    ag = synth.make_agents(mesh, n)
+    ag["position"], ag["target"] = pos, tgt
+    opts = synth.default_options()
+    gpu = NativeBackend(max_agents=n)
+    gpu.navdata_upload(flat)
+    rows = []
+    dt = 1.0 / 60.0
+    for f in range(frames):
+        out = gpu.step(ag, None, opts, dt)
+        row = timings(gpu)
+        row["frame"] = f
+        rows.append(row)
+        assert np.isfinite(out["desired_velocity"]).all()
+        if f == 0:
+            pr = gpu.pathing_results_array()
+            assert len(pr) == row["n_repath"] and (pr[:, 1] == 1).mean() > 0.999, "connected archipelago"
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["velocity"] = out["desired_velocity"].copy()
+        ag["position"] = ag["position"] + out["desired_velocity"] * np.float32(dt)
+    # corridors: consecutive nodes joined by the recorded portal (polygon edge or boundary link)
+    peb, nb = flat["poly_edge_begin"], flat["edge_neighbor"]
+    crossed = 0
+    for s_ in range(0, n, n // 50):
+        nodes, portals = gpu.agent_path(int(s_))
+        for i in range(len(nodes) - 1):
+            if int(portals[i]) & _abi.PORTAL_LINK:
+                crossed += 1
+                assert flat["link_dst_node"][int(portals[i]) & 0x7FFFFFFF] == nodes[i + 1], "link corridor broken"
+            else:
+                assert nb[peb[nodes[i]] + portals[i]] == nodes[i + 1], "corridor not connected"
+    assert crossed > 0, "no sampled corridor crosses an island border"
+    print(json.dumps({"config": 4, "agents": n, "islands": k * k, "polygons": int(len(flat["poly_type"])),
+                      "boundary_links": n_links, "sampled_link_crossings": crossed, "frames": rows,
+                      "steady_agent_updates_per_s": n / (rows[-1]["total_ms"] * 1e-3)}))
+    gpu.close()
+
+
 def config1():
     """64 x 64 quad grid, 100 agents (the reference's CPU-runnable case) — GPU vs oracle exact."""
     from oracle.oracle_py import OracleBackend
@@ -127,4 +188,4 @@ def config1():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["1", "3", "5"]
     for w in which:
-        {"1": config1, "3": config3, "5": config5}[w]()
+        {"1": config1, "3": config3, "4": config4, "5": config5}[w]()
