@@ -757,6 +757,11 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 //    entries in shared memory.  Every spilled heap level is a dependent HBM round trip and these
 //    searches are bound by random-sector HBM traffic, so one more level on chip beats twice the
 //    queries in flight (open 256x256 field, 50k queries: 1.47 s -> 1.09 s).
+//  * small batches run at the latency of their longest search, so they get the widest shapes the
+//    batch size allows: up to 32 queries per SM -> 4 queries per warp with 384 entries each, up to
+//    8 per SM -> one query per warp with 1536 entries (a lone lane is not held back by
+//    lock-step neighbours, and an open-field open list fits on chip); up to 128 per SM -> 8 queries
+//    per warp with 96 entries.
 // (Measured and rejected: 32 queries per warp; 384 queries per SM with 28 shared-memory entries;
 // 64 / 192 / 384 entries at 192 / 64 / 32 queries per SM; a 4-lanes-per-query variant — lower
 // latency per query but issue-bound, no faster when loaded.)
@@ -766,20 +771,29 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
                   AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream) {
   if (q.n == 0) return;
   const bool k4 = arena.kshift == 2;
-#define LMB_ASTAR_LAUNCH(HS, BPS)                                                                       \
+#define LMB_ASTAR_LAUNCH(QPW, HS, BPS)                                                                   \
   do {                                                                                                  \
     if (arena.compact) {                                                                                \
-      if (k4) launch_astar_t<16, HS, BPS, 2, true>(nav, arena, q, pool, counters, type_raw, stream);      \
-      else launch_astar_t<16, HS, BPS, 0, true>(nav, arena, q, pool, counters, type_raw, stream);         \
+      if (k4) launch_astar_t<QPW, HS, BPS, 2, true>(nav, arena, q, pool, counters, type_raw, stream);     \
+      else launch_astar_t<QPW, HS, BPS, 0, true>(nav, arena, q, pool, counters, type_raw, stream);        \
     } else {                                                                                            \
-      if (k4) launch_astar_t<16, HS, BPS, 2, false>(nav, arena, q, pool, counters, type_raw, stream);     \
-      else launch_astar_t<16, HS, BPS, 0, false>(nav, arena, q, pool, counters, type_raw, stream);        \
+      if (k4) launch_astar_t<QPW, HS, BPS, 2, false>(nav, arena, q, pool, counters, type_raw, stream);    \
+      else launch_astar_t<QPW, HS, BPS, 0, false>(nav, arena, q, pool, counters, type_raw, stream);       \
     }                                                                                                   \
   } while (0)
-  if (big_heap)
-    LMB_ASTAR_LAUNCH(96, 2);
+  int dev = 0, sm_count = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (q.n <= 8u * (uint32_t)sm_count)
+    LMB_ASTAR_LAUNCH(1, 1536, 2);  // few queries: one per warp, the whole open list on chip
+  else if (q.n <= 32u * (uint32_t)sm_count)
+    LMB_ASTAR_LAUNCH(4, 384, 2);
+  else if (q.n <= 128u * (uint32_t)sm_count)
+    LMB_ASTAR_LAUNCH(8, 96, 4);
+  else if (big_heap)
+    LMB_ASTAR_LAUNCH(16, 96, 2);
   else
-    LMB_ASTAR_LAUNCH(48, 4);
+    LMB_ASTAR_LAUNCH(16, 48, 4);
 #undef LMB_ASTAR_LAUNCH
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)
