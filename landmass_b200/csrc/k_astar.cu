@@ -41,17 +41,19 @@ namespace lmb {
 
 using namespace astar_detail;
 
-__device__ __forceinline__ uint32_t ovf_used(const BestStore<false>&) { return 0u; }
-__device__ __forceinline__ uint32_t ovf_used(const BestStore<true>& b) { return b.ovf_count; }
-__device__ __forceinline__ void ovf_clear(BestStore<false>&) {}
-__device__ __forceinline__ void ovf_clear(BestStore<true>& b) { b.ovf_count = 0; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<0>&) { return 0u; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<1>& b) { return b.ovf_count; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<2>&) { return 0u; }
+__device__ __forceinline__ void ovf_clear(BestStore<0>&) {}
+__device__ __forceinline__ void ovf_clear(BestStore<1>& b) { b.ovf_count = 0; }
+__device__ __forceinline__ void ovf_clear(BestStore<2>& b) { b.count = 0; }
 
 // QPW: queries per warp (lanes >= QPW idle: fewer searches in lock-step per warp).
 // KS: compile-time kshift (2 = every polygon has <= 4 edges: one chunk, no chunk loop), or 0 =
 //     use the run-time value (0 or 3).
-// COMPACT: best_estimates layout (k_astar_common.cuh).
+// LAYOUT: best_estimates layout (k_astar_common.cuh): 0 dense, 1 compact, 2 hashed.
 // HS: open-list entries per query in shared memory; BPS: blocks per SM the variant is sized for.
-template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, bool COMPACT>
+template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT>
 __global__ void __launch_bounds__(AT_THREADS, BPS)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
@@ -67,8 +69,9 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
 
   const uint32_t slot_c = slot < arena.n_slots ? slot : 0;  // out-of-range lanes never touch memory
   uint8_t* const slot_base = arena.base + (size_t)slot_c * arena.slot_stride;
-  typedef typename BestStore<COMPACT>::Raw BestRaw;
-  BestStore<COMPACT> bs;
+  constexpr bool COMPACT = LAYOUT == 1;
+  typedef typename BestStore<LAYOUT>::Raw BestRaw;
+  BestStore<LAYOUT> bs;
   bs.init(slot_base, arena);
   uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
   Heap<QPB, HS> heap;
@@ -77,7 +80,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   // the finished search's corridor is staged in the slot's (no longer needed) best_estimates
   // region as raw (state, next state) pairs, goal first, before it is copied to the path pool
   uint2* const stage = reinterpret_cast<uint2*>(slot_base);
-  const uint32_t stage_cap = COMPACT ? (arena.n_ids >> arena.kshift) : arena.n_states / 2;
+  const uint32_t stage_cap =
+      LAYOUT == 1 ? (arena.n_ids >> arena.kshift) : (LAYOUT == 2 ? arena.hash_cap : arena.n_states / 2);
   heap.len = 0;
 
   const EdgeRec* __restrict__ recs = nav.edges;
@@ -307,7 +311,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         //      records (L2) -> `best` probes of every candidate issued together (HBM, speculative:
         //      loads only) -> costs/estimates of all four evaluated unconditionally (independent
         //      chains, no divergence) -> stale test -> accepted successors pushed in edge order ----
-        bool overflow = false, live = true, go_dense = false;
+        bool overflow = false, live = true, go_dense = false, heap_full = false;
         for (uint32_t e0 = 0; e0 == 0 || (KS != 2 && e0 < cnt && live && !overflow); e0 += 4) {
           if (e0 > 0 || !preloaded) {
 #pragma unroll
@@ -369,13 +373,17 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
               const BestRaw raw_e = bs.probe(ST_END);
               if (!(bs.value(ST_END, raw_e) <= est)) {
                 if (n_nodes >= node_cap || heap.len >= heap_cap) {
+              heap_full = heap.len >= heap_cap;
                   overflow = true;
                 } else {
-                  bs.store(ST_END, raw_e, est);
-                  nodes[n_nodes] = make_uint2(ST_END, cur.index);
-                  heap.push({ncost, est, n_nodes, ST_END});
-                  hmax = max(hmax, heap.len);
-                  n_nodes++;
+                  if (!bs.store(ST_END, raw_e, est)) {
+                    go_dense = true;
+                  } else {
+                    nodes[n_nodes] = make_uint2(ST_END, cur.index);
+                    heap.push({ncost, est, n_nodes, ST_END});
+                    hmax = max(hmax, heap.len);
+                    n_nodes++;
+                  }
                 }
               }
               live = false;  // no other successor
@@ -405,6 +413,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             const uint32_t j = __ffs(acc) - 1;
             acc &= acc - 1;
             if (n_nodes >= node_cap || heap.len >= heap_cap) {
+              heap_full = heap.len >= heap_cap;
               overflow = true;
               break;
             }
@@ -448,10 +457,14 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             const BestRaw raw_l = bs.probe(s2);
             if (bs.value(s2, raw_l) <= est) continue;
             if (n_nodes >= node_cap || heap.len >= heap_cap) {
+              heap_full = heap.len >= heap_cap;
               overflow = true;
               break;
             }
-            bs.store(s2, raw_l, est);
+            if (!bs.store(s2, raw_l, est)) {
+              go_dense = true;
+              break;
+            }
             nodes[n_nodes] = make_uint2(s2, cur.index);
             heap.push({ncost, est, n_nodes, s2});
             hmax = max(hmax, heap.len);
@@ -459,7 +472,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           }
         }
         if (overflow || go_dense) {
-          status = go_dense ? 5 : 2;
+          // 5: compact layout's overflow table full; 7: open-list spill full; 2: node list (or hashed table) full
+          status = (go_dense && COMPACT) ? 5 : ((overflow && heap_full) ? 7 : 2);
           phase = PH_FINISH;
         }
       }
@@ -523,7 +537,12 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       }
       __syncwarp();
       const uint32_t n_staged = staged < stage_cap ? staged : stage_cap;
-      if (!COMPACT) {
+      if (LAYOUT == 2) {
+        // hashed: entries cannot be removed one by one (probe chains): clear the whole table
+        uint4* t4 = reinterpret_cast<uint4*>(base);
+        const uint4 e4 = make_uint4(BP_EMPTY, 0u, BP_EMPTY, 0u);
+        for (uint32_t k = lane; k < arena.hash_cap / 2; k += 32) t4[k] = e4;
+      } else if (LAYOUT == 0) {
         float* b = reinterpret_cast<float*>(base);
         if ((size_t)nn * 16 >= arena.n_states) {
           // dense restore: coalesced 16-byte stores over the whole array (padded to 16 B)
@@ -585,6 +604,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         atomicAdd(&counters->heap_max_total, (unsigned long long)hmax);
       } else if (status == 2) {
         atomicAdd(&counters->n_retry_arena, 1u);
+      } else if (status == 7) {
+        atomicAdd(&counters->n_retry_heap, 1u);
       } else if (status == 5) {
         atomicAdd(&counters->n_retry_dense, 1u);
       } else if (status == 6) {
@@ -697,15 +718,16 @@ __global__ void k_arena_init(AStarArena arena) {
   // every slot: the best_estimates region to "absent", the overflow table (compact) to empty
   const size_t words = arena.best_bytes / 4;
   const size_t total = (size_t)arena.n_slots * words;
-  const uint32_t n_poly_words = arena.compact ? 2u * (arena.n_ids >> arena.kshift) : 0u;
+  const uint32_t n_poly_words = arena.layout == 1 ? 2u * (arena.n_ids >> arena.kshift) : 0u;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const size_t slot = i / words, k = i % words;
     uint32_t v = __float_as_uint(F_INF);
-    if (arena.compact && k < n_poly_words && (k & 1)) v = BP_EMPTY;
+    if (arena.layout == 1 && k < n_poly_words && (k & 1)) v = BP_EMPTY;
+    if (arena.layout == 2) v = (k & 1) ? 0u : BP_EMPTY;
     reinterpret_cast<uint32_t*>(arena.base + slot * arena.slot_stride)[k] = v;
   }
-  if (arena.compact) {
+  if (arena.layout == 1) {
     const size_t ow = (size_t)arena.ovf_cap * 2;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)arena.n_slots * ow;
          i += (size_t)gridDim.x * blockDim.x) {
@@ -719,15 +741,15 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
   k_arena_init<<<148 * 8, 256, 0, stream>>>(arena);
 }
 
-template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, bool COMPACT>
+template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT>
 static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                            AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
   const size_t smem = (size_t)HS * QPB * sizeof(uint4);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, LAYOUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
@@ -744,7 +766,7 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
   uint32_t blocks = (slots + QPB - 1) / QPB;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar<QPW, HS, BPS, KS, COMPACT><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  k_astar<QPW, HS, BPS, KS, LAYOUT><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
 // Launch shapes.  Only half the lanes of a warp own a query (16 per warp): the number of queries
@@ -771,15 +793,16 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
                   AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream) {
   if (q.n == 0) return;
   const bool k4 = arena.kshift == 2;
-#define LMB_ASTAR_LAUNCH(QPW, HS, BPS)                                                                   \
-  do {                                                                                                  \
-    if (arena.compact) {                                                                                \
-      if (k4) launch_astar_t<QPW, HS, BPS, 2, true>(nav, arena, q, pool, counters, type_raw, stream);     \
-      else launch_astar_t<QPW, HS, BPS, 0, true>(nav, arena, q, pool, counters, type_raw, stream);        \
-    } else {                                                                                            \
-      if (k4) launch_astar_t<QPW, HS, BPS, 2, false>(nav, arena, q, pool, counters, type_raw, stream);    \
-      else launch_astar_t<QPW, HS, BPS, 0, false>(nav, arena, q, pool, counters, type_raw, stream);       \
-    }                                                                                                   \
+#define LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, L)                                                          \
+  do {                                                                                            \
+    if (k4) launch_astar_t<QPW, HS, BPS, 2, L>(nav, arena, q, pool, counters, type_raw, stream);   \
+    else launch_astar_t<QPW, HS, BPS, 0, L>(nav, arena, q, pool, counters, type_raw, stream);      \
+  } while (0)
+#define LMB_ASTAR_LAUNCH(QPW, HS, BPS)                                  \
+  do {                                                                  \
+    if (arena.layout == 1) LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 1);         \
+    else if (arena.layout == 2) LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 2);    \
+    else LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 0);                           \
   } while (0)
   int dev = 0, sm_count = 148;
   cudaGetDevice(&dev);
@@ -795,6 +818,7 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   else
     LMB_ASTAR_LAUNCH(16, 48, 4);
 #undef LMB_ASTAR_LAUNCH
+#undef LMB_ASTAR_LAUNCH_L
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)
   uint32_t fix_blocks = (q.n + 7) / 8;

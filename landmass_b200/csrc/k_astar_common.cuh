@@ -132,15 +132,19 @@ __device__ __forceinline__ EdgeRec ld_rec(const EdgeRec* p) {
 //    table {state, estimate} for further states of an already tracked polygon.  Half the bytes
 //    of the dense array (so more queries fit in HBM) and four polygons per 32-byte sector instead
 //    of two.  A query that fills the overflow table is re-run with the dense layout.
+//  * hashed  — for meshes so large that a search touches a small fraction of the states (1M
+//    polygons: ~1 %): an open-addressing table {state, estimate} (linear probing, power-of-two
+//    capacity >= 2 x node capacity, so at most half full: a query that would exceed that is re-run
+//    with a doubled arena).  16 bytes per touched state instead of 4 per existing state.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t BP_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t BP_SPECIAL = 0xFFFFFFFEu;
 
-template <bool COMPACT>
+template <int LAYOUT>  // 0 dense, 1 compact, 2 hashed
 struct BestStore;
 
 template <>
-struct BestStore<false> {
+struct BestStore<0> {
   typedef float Raw;
   float* b;
   __device__ __forceinline__ void init(uint8_t* slot_base, const AStarArena&) { b = reinterpret_cast<float*>(slot_base); }
@@ -159,7 +163,7 @@ struct BestStore<false> {
 };
 
 template <>
-struct BestStore<true> {
+struct BestStore<1> {
   typedef uint2 Raw;
   uint2* bp;    // [n_polys] {estimate bits, tracked local edge | BP_EMPTY}
   float* sp;    // [n_links + 2]
@@ -223,6 +227,53 @@ struct BestStore<true> {
     } else {
       return ovf_set(st, est);
     }
+    return true;
+  }
+};
+
+template <>
+struct BestStore<2> {
+  typedef uint2 Raw;  // the entry at the state's home slot {key, estimate bits}
+  uint2* tab;
+  uint32_t mask, count, limit;
+  __device__ __forceinline__ void init(uint8_t* slot_base, const AStarArena& a) {
+    tab = reinterpret_cast<uint2*>(slot_base);
+    mask = a.hash_cap - 1u;
+    count = 0;
+    limit = a.hash_cap / 2u;
+  }
+  __device__ __forceinline__ uint32_t home(uint32_t st) const { return (st * 2654435761u) >> 4; }
+  __device__ __forceinline__ Raw probe(uint32_t st) const { return __ldcg(tab + (home(st) & mask)); }
+  __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return probe(st); }
+  __device__ float find(uint32_t st) const {
+    for (uint32_t h = home(st) + 1;; h++) {
+      const uint2 e = __ldcg(tab + (h & mask));
+      if (e.x == st) return __uint_as_float(e.y);
+      if (e.x == BP_EMPTY) return __builtin_huge_valf();
+    }
+  }
+  __device__ __forceinline__ float value_fast(uint32_t st, Raw r, bool& need_table) const {
+    const bool here = r.x == st;
+    need_table = !here & (r.x != BP_EMPTY);
+    return here ? __uint_as_float(r.y) : __builtin_huge_valf();
+  }
+  __device__ __forceinline__ float value(uint32_t st, Raw r) const {
+    if (r.x == st) return __uint_as_float(r.y);
+    if (r.x == BP_EMPTY) return __builtin_huge_valf();
+    return find(st);
+  }
+  __device__ __forceinline__ float value_edge(uint32_t st, Raw r) const { return value(st, r); }
+  // false: the table would pass half full (the caller aborts the query: arena overflow)
+  __device__ bool store(uint32_t st, Raw r, float est) {
+    uint32_t h = home(st);
+    if (r.x != st && r.x != BP_EMPTY) {
+      for (h++;; h++) {
+        r = __ldcg(tab + (h & mask));
+        if (r.x == st || r.x == BP_EMPTY) break;
+      }
+    }
+    if (r.x == BP_EMPTY && ++count > limit) return false;
+    tab[h & mask] = make_uint2(st, __float_as_uint(est));
     return true;
   }
 };

@@ -149,22 +149,28 @@ static const uint32_t OVF_CAP = 1024;  // compact layout: overflow-table entries
 
 // Byte layout of one arena slot: best_estimates region | node list | open-list spill |
 // overflow table (compact layout only).
-static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, bool compact, AStarArena& a) {
+static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, int layout, AStarArena& a) {
   a.n_ids = ctx->n_ids;
   a.kshift = ctx->kshift;
   a.n_states = ctx->n_ids + ctx->nav.n_links + 2;
   a.node_cap = node_cap;
   a.heap_cap = heap_cap;
-  a.compact = compact ? 1u : 0u;
-  a.ovf_cap = compact ? OVF_CAP : 0u;
+  a.layout = (uint32_t)layout;
+  a.ovf_cap = layout == 1 ? OVF_CAP : 0u;
+  a.hash_cap = 0;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t spill = (heap_cap > AT_HEAP_SM ? heap_cap - AT_HEAP_SM : 0) + 2;
-  if (compact) {
+  a.special_offset = 0;
+  if (layout == 1) {
     const size_t n_polys = ctx->n_ids >> ctx->kshift;
     a.special_offset = up(n_polys * 8);
     a.best_bytes = a.special_offset + up((size_t)(ctx->nav.n_links + 2) * 4);
+  } else if (layout == 2) {
+    uint32_t cap = 1024;
+    while (cap < 2u * node_cap + 16u) cap <<= 1;  // every node adds at most one key: never more than half full
+    a.hash_cap = cap;
+    a.best_bytes = (size_t)cap * 8;
   } else {
-    a.special_offset = 0;
     a.best_bytes = up((size_t)a.n_states * 4);
   }
   a.nodes_offset = a.best_bytes;
@@ -173,26 +179,35 @@ static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_ca
   a.slot_stride = a.ovf_offset + up((size_t)a.ovf_cap * 8);
 }
 
-// (Re)allocates the A* arena: `slots` query slots.
-static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
-  AStarArena& a = ctx->arena;
-  arena_layout(ctx, node_cap, heap_cap, ctx->best_compact, a);
+// (Re)allocates an A* arena: `slots` query slots.
+static int32_t setup_arena_into(lmb_ctx* ctx, AStarArena& a, DevBuf<uint8_t>& buf, uint32_t node_cap,
+                                uint32_t heap_cap, uint32_t slots, const char* what) {
+  arena_layout(ctx, node_cap, heap_cap, ctx->best_layout, a);
   a.n_slots = slots;
   a.base = nullptr;
-  ctx->d_arena.release();
-  CUDA_TRY(ctx, ctx->d_arena.reserve_exact(a.slot_stride * (size_t)slots));
-  a.base = ctx->d_arena.p;
+  const size_t bytes = a.slot_stride * (size_t)slots;
+  if (buf.cap < bytes) {
+    buf.release();
+    CUDA_TRY(ctx, buf.reserve_exact(bytes));
+  }
+  a.base = buf.p;
   if (getenv("LMB_DEBUG"))
-    fprintf(stderr, "[lmb] A* arena: %u slots x %.2f MB (n_states %u, node_cap %u, heap_cap %u, kshift %u, %s best)\n",
-            slots, a.slot_stride / 1048576.0, a.n_states, node_cap, heap_cap, a.kshift, a.compact ? "compact" : "dense");
+    fprintf(stderr, "[lmb] A* %s: %u slots x %.2f MB (n_states %u, node_cap %u, heap_cap %u, kshift %u, %s best)\n",
+            what, slots, a.slot_stride / 1048576.0, a.n_states, node_cap, heap_cap, a.kshift,
+            a.layout == 1 ? "compact" : (a.layout == 2 ? "hashed" : "dense"));
   launch_arena_init(a, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
   return LMB_OK;
 }
 
+static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
+  ctx->d_arena.release();
+  return setup_arena_into(ctx, ctx->arena, ctx->d_arena, node_cap, heap_cap, slots, "arena");
+}
+
 static size_t arena_slot_bytes(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap) {
   AStarArena a{};
-  arena_layout(ctx, node_cap, heap_cap, ctx->best_compact, a);
+  arena_layout(ctx, node_cap, heap_cap, ctx->best_layout, a);
   return a.slot_stride;
 }
 
@@ -508,7 +523,7 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
   {
     const uint32_t n_states = ctx->n_ids + nav.n_links + 2;
     ctx->arena_node_cap = std::max<uint32_t>(n_states / 4 + 1024, d->n_region_numbers + 64);
-    ctx->arena_heap_cap = AT_HEAP_SM + std::max<uint32_t>(1024, n_states / 64);
+    ctx->arena_heap_cap = AT_HEAP_SM + std::min<uint32_t>(std::max<uint32_t>(1024, n_states / 64), 8192);
     // best_estimates layout: compact (one entry per polygon) when the polygon graph — edges and
     // off-mesh links — is a forest: a search then enters every polygon through one edge only.
     // With a single cycle a search comes round both ways and enters whole regions twice, so
@@ -538,7 +553,14 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
       for (uint32_t l = 0; l < d->n_links; l++)
         if (link_src[l] != LMB_NONE) join(link_src[l], d->link_dst_node[l]);
       const bool forest = connections + components == d->n_polys;
-      ctx->best_compact = ctx->kshift != 0 && (forest || getenv("LMB_ASTAR_COMPACT")) && !getenv("LMB_ASTAR_DENSE");
+      const uint32_t n_states = ctx->n_ids + nav.n_links + 2;
+      ctx->best_layout = 0;
+      if (ctx->kshift != 0 && (forest || getenv("LMB_ASTAR_COMPACT")) && !getenv("LMB_ASTAR_DENSE"))
+        ctx->best_layout = 1;
+      else if ((n_states > (1u << 21) || getenv("LMB_ASTAR_HASHED")) && !getenv("LMB_ASTAR_DENSE"))
+        ctx->best_layout = 2;  // a search touches a small part of a mesh this large: keep only what it touches
+      if (ctx->best_layout == 2) ctx->arena_node_cap = std::min<uint32_t>(ctx->arena_node_cap, 131072u);
+      if (getenv("LMB_ASTAR_HASHED")) ctx->arena_node_cap = std::min<uint32_t>(ctx->arena_node_cap, 2048u);
       ctx->big_heap = !forest;  // first guess: a wavefront; corrected from the first batch's open lists
     }
     ctx->arena = AStarArena{};
@@ -671,12 +693,13 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     list = ctx->d_query_order.p;
   }
   std::vector<uint32_t> h_status;
+  const AStarArena* cur = &ctx->arena;  // the arena of the next launch
   for (int iter = 0; iter < 24; iter++) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(AStarCounters), s));
     AStarQueries qq = q;
     qq.n = n_run;
     qq.list = list;
-    launch_astar(ctx->nav, ctx->arena, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, ctx->big_heap, s);
+    launch_astar(ctx->nav, *cur, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, ctx->big_heap, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
@@ -684,8 +707,8 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     ctx->timings.explored_nodes += ctx->h_counters->explored_total;
     ctx->timings.path_nodes += ctx->h_counters->path_nodes_total;
     ctx->timings.kernel_launches += 2;  // k_astar + k_path_fixup
-    uint32_t ra = ctx->h_counters->n_retry_arena, rp = ctx->h_counters->n_retry_pool;
-    const uint32_t rd = ctx->h_counters->n_retry_dense;
+    const uint32_t ra = ctx->h_counters->n_retry_arena, rh = ctx->h_counters->n_retry_heap;
+    const uint32_t rp = ctx->h_counters->n_retry_pool, rd = ctx->h_counters->n_retry_dense;
     done_total += ctx->h_counters->n_done;
     nodes_total += ctx->h_counters->path_nodes_total;
     explored_total += ctx->h_counters->explored_total;
@@ -694,7 +717,7 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     heap_max_total += ctx->h_counters->heap_max_total;
     if (ctx->h_counters->n_failed)
       return ctx->fail(LMB_ERR_CAPACITY, "A*: a corridor did not fit the staging area (%u queries)", ctx->h_counters->n_failed);
-    if (ra == 0 && rp == 0 && rd == 0) {
+    if (ra == 0 && rh == 0 && rp == 0 && rd == 0) {
       // launch shape of the next batch: open lists that outgrow shared memory want the big-heap shape
       if (done_total >= 16) ctx->big_heap = (double)heap_max_total / (double)done_total > 1.5 * AT_HEAP_SM;
       return LMB_OK;
@@ -711,19 +734,24 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
       int32_t st = q.slot ? compact_pool(ctx, needed) : grow_pool(ctx, needed);
       if (st != LMB_OK) return st;
     }
-    if (rd) ctx->best_compact = false;  // compact best_estimates overflowed: dense from now on
-    if (ra || rd) {
-      // node list or open-list spill too small: double both; the slot count follows the budget
-      if (ra) {
-        ctx->arena_node_cap *= 2;
-        ctx->arena_heap_cap = AT_HEAP_SM + (ctx->arena_heap_cap - AT_HEAP_SM) * 2;
-      }
+    if (rd) ctx->best_layout = 0;  // compact best_estimates overflowed: dense from now on
+    if (ra || rh || rd) {
+      // node list / hashed table (ra) or open-list spill (rh) too small: double what overflowed
+      uint32_t node_cap = cur->node_cap, heap_cap = cur->heap_cap;
+      if (ra) node_cap *= 2;
+      if (rh) heap_cap = AT_HEAP_SM + (heap_cap - AT_HEAP_SM) * 2;
+      // Resize the arena for good (the slot count follows the byte budget).  Measured alternative,
+      // rejected: a side arena of fat slots for the few searches that overflow, keeping the lean
+      // main arena — the same searches overflow again next frame and are then searched twice.
+      ctx->arena_node_cap = std::max(ctx->arena_node_cap, node_cap);
+      ctx->arena_heap_cap = std::max(ctx->arena_heap_cap, heap_cap);
       const size_t per_slot = arena_slot_bytes(ctx, ctx->arena_node_cap, ctx->arena_heap_cap);
       const size_t budget = arena_budget(ctx);
       uint32_t slots = ctx->arena.n_slots;
       if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 8);
       int32_t st = setup_arena(ctx, ctx->arena_node_cap, ctx->arena_heap_cap, slots);
       if (st != LMB_OK) return st;
+      cur = &ctx->arena;
     }
     CUDA_TRY(ctx, ctx->d_retry_list.upload(retry, s));
     list = ctx->d_retry_list.p;

@@ -85,7 +85,7 @@ struct lmb_ctx {
   uint32_t kshift = 0, n_ids = 0;              // edge-record id space (see EdgeRec)
   uint32_t arena_node_cap = 0, arena_heap_cap = 0;
   bool big_heap = false;                       // launch shape for large open lists (k_astar.cu)
-  bool best_compact = false;                   // best_estimates layout (k_astar_common.cuh)
+  int best_layout = 0;                         // best_estimates layout (k_astar_common.cuh): 0 dense, 1 compact, 2 hashed
   DevBuf<AStarCounters> d_counters;
   AStarCounters* h_counters = nullptr;  // pinned
 

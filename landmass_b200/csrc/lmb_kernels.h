@@ -29,7 +29,9 @@ struct AStarArena {
   size_t nodes_offset;    // byte offset of the node list {state, prev} inside a slot
   size_t heap_offset;     // byte offset of the open-list spill inside a slot
   // best_estimates layout (k_astar_common.cuh): dense f32[n_states] at offset 0, or compact
-  uint32_t compact;       // 1 = per-polygon entries + specials + overflow table
+  uint32_t layout;        // 0 = dense, 1 = compact (per-polygon entries + specials + overflow table),
+                          // 2 = hashed (open-addressing table)
+  uint32_t hash_cap;      // hashed: table entries (power of two, >= 2 x node_cap)
   uint32_t ovf_cap;       // overflow-table entries (power of two)
   size_t special_offset;  // compact: f32[n_links + 2]
   size_t ovf_offset;      // compact: uint2[ovf_cap]
@@ -53,7 +55,7 @@ struct AStarQueries {
   const uint32_t* slot;        // [n] agent slot to receive the path, or NULL
   // outputs
   uint32_t* out_status;        // [n] 0 = not run, 1 = done, 2 = retry (arena overflow), 3 = retry (pool
-                               //     overflow), 5 = retry with the dense best_estimates layout, 6 = failed
+                               //     overflow), 5 = retry with the dense best_estimates layout, 6 = failed, 7 = retry (open-list spill overflow)
   uint32_t* out_success;       // [n]
   uint32_t* out_explored;      // [n]
   uint32_t* out_path_off;      // [n] offset into the path pool
@@ -73,6 +75,7 @@ struct PathPool {
 struct AStarCounters {  // device-resident
   unsigned int queue_head;
   unsigned int n_retry_arena;
+  unsigned int n_retry_heap;
   unsigned int n_retry_pool;
   unsigned int n_retry_dense;
   unsigned int n_failed;

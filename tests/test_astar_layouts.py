@@ -116,6 +116,37 @@ def test_compact_best_falls_back_to_dense(capfd, monkeypatch):
     assert_same_paths(gpu, cpu, sn[::-1].copy(), sp[::-1].copy(), en[::-1].copy(), ep[::-1].copy(), cap=1 << 21)
 
 
+@pytest.mark.parametrize("mesh_kind", ["grid", "maze", "rosette"])
+def test_hashed_best_with_table_growth(mesh_kind, capfd, monkeypatch):
+    """Hashed best_estimates (chosen for meshes above 2M states; forced here, with a 2048-node
+    arena): probe chains, the half-full limit -> arena retry with a doubled table, slot re-use
+    (whole-table clear), CSR ids (rosette)."""
+    monkeypatch.setenv("LMB_DEBUG", "1")
+    monkeypatch.setenv("LMB_ASTAR_HASHED", "1")
+    monkeypatch.setenv("LMB_ASTAR_DENSE", "")  # unset below
+    monkeypatch.delenv("LMB_ASTAR_DENSE")
+    if mesh_kind == "rosette":
+        mesh = synth.rosette_mesh(12, 6)
+        pairs = [(a, b) for a in range(mesh.n_polys) for b in range(0, mesh.n_polys, 3)]
+        sn, sp, en, ep = centre_queries(mesh, pairs)
+    else:
+        mesh = synth.grid_mesh(90, 90) if mesh_kind == "grid" else synth.loopy_maze_mesh(40, 30)
+        rng = np.random.Generator(np.random.PCG64(41))
+        nq = 700
+        sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+        ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+        en[:100] = sn[:100]
+        ep[:100] = sp[:100] + np.float32(0.05)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat, astar_slots=96)
+    g = assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
+    assert g[0].all()
+    err = capfd.readouterr().err
+    assert "hashed best" in err
+    if mesh_kind != "rosette":
+        assert err.count("arena:") >= 2  # the 2048-node table overflowed at least once
+
+
 def test_dense_best_slot_reuse_and_arena_retry(capfd, monkeypatch):
     """Open grid (dense layout): corner-to-corner searches outgrow the initial node list
     (n_states / 4) -> retry with a doubled arena; 64 slots re-used by 400 queries."""
@@ -135,7 +166,7 @@ def test_dense_best_slot_reuse_and_arena_retry(capfd, monkeypatch):
     ep[100:200] = sp[100:200] + np.float32(0.05)
     assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
     err = capfd.readouterr().err
-    assert err.count("A* arena") >= 2 and "compact best" not in err
+    assert err.count("arena:") >= 2 and "compact best" not in err
 
 
 def test_step_more_agents_than_slots_longest_first_order():
