@@ -314,7 +314,9 @@ __device__ Line line_for_neighbour(const DodgyAgent& self, const DodgyAgent& oth
       inside_vo = w_length_sq < fmul(cutoff_radius, cutoff_radius);
     } else {
       float leg = fsqrt(fsub(dist_sq, combined_radius_sq));
-      if (perp_dot(relative_position, w) > 0.0f) {
+      // dodgy_2d: `determinant(..).signum()` — +0.0 is positive, an exactly symmetric approach takes the
+      // left leg (RVO2's `> 0` would go right); pinned by lib_test.rs:426-486
+      if (!signbit(perp_dot(relative_position, w))) {
         line.direction = V2{fsub(fmul(relative_position.x, leg), fmul(relative_position.y, combined_radius)),
                             fadd(fmul(relative_position.x, combined_radius), fmul(relative_position.y, leg))} /
                          dist_sq;

@@ -394,7 +394,10 @@ Line line_for_neighbour(const DodgyAgent& self, const DodgyAgent& other, float t
     } else {
       // project on the legs
       float leg = std::sqrt(dist_sq - combined_radius_sq);
-      if (det2(relative_position, w) > 0.0f) {
+      // dodgy_2d picks the leg by `determinant(..).signum()`: +0.0 counts as positive, so an exactly
+      // symmetric approach takes the LEFT leg (textbook RVO2 tests `> 0` and goes right) — pinned by
+      // lib_test.rs:426-486 (`agent_speeds_up_to_avoid_character`)
+      if (!std::signbit(det2(relative_position, w))) {
         line.direction = V2{relative_position.x * leg - relative_position.y * combined_radius,
                             relative_position.x * combined_radius + relative_position.y * leg} /
                          dist_sq;

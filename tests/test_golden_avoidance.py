@@ -137,3 +137,85 @@ def test_agent_avoids_character(make_backend):  # avoidance_test.rs:585-665
     v = _run_avoidance(make_backend, [((1.0, 1.0, 0.0), (1.0, 0.0, 0.0), 1.0, (12.5, 1.0, 0.0))],
                        [((11.0, 1.01, 0.0), (-1.0, 0.0, 0.0), 1.0)], 15.0, 15.0, 0.01)
     assert np.allclose(v[0], (np.sqrt(1.0 - 0.4 * 0.4), -0.4, 0.0), atol=0.05), v[0]
+
+
+def test_agent_speeds_up_to_avoid_character(make_backend):  # lib_test.rs:426-486
+    """An agent heading for the point a character is also heading for, from the same distance:
+    alone it moves at its desired speed (exact); with the character it speeds up (max_speed 2) to
+    pass first instead of braking."""
+    from landmass_b200 import XY, Agent, Character
+
+    square = dict(vertices=[(-10.0, -10.0), (10.0, -10.0), (10.0, 10.0), (-10.0, 10.0)], polygons=[[0, 1, 2, 3]],
+                  polygon_type_indices=[0])
+    arch = new_archipelago(make_backend(), cs=XY)
+    arch.archipelago_options.avoidance_time_horizon = 100.0
+    arch.archipelago_options.neighbourhood = 10.0
+    arch.add_island(Island(Transform(), valid_mesh(square, cs=XY)))
+    a = Agent.create((5.0, 0.0), (-1.0, 0.0), 0.5, 1.0, 2.0, cs=XY)
+    a.current_target = (-5.0, 0.0)
+    agent = arch.add_agent(a)
+    arch.update(0.01)
+    assert tuple(np.asarray(arch.get_agent(agent).get_desired_velocity(), dtype=np.float32)) == (-1.0, 0.0)
+    arch.add_character(Character((0.0, 5.0), (0.0, -1.0), 0.5))
+    arch.update(0.01)
+    v = np.asarray(arch.get_agent(agent).get_desired_velocity(), dtype=np.float32)
+    assert float(np.hypot(v[0], v[1])) > 1.1, v
+
+
+def test_agent_speeds_up_to_avoid_character_preset_move(make_backend):  # avoidance_test.rs:667-763
+    """The avoidance_test.rs variant: current velocity (-1, 0) but desired move (+1, 0) (here: a target
+    straight ahead in +x), time horizon 15.  Alone the desired move is kept exactly; with the
+    character on the symmetric collision course the result is faster than 1.1."""
+    from landmass_b200 import XY, Agent, Character
+
+    square = dict(vertices=[(-10.0, -10.0), (10.0, -10.0), (10.0, 10.0), (-10.0, 10.0)], polygons=[[0, 1, 2, 3]],
+                  polygon_type_indices=[0])
+
+    def run(with_character):
+        arch = new_archipelago(make_backend(), cs=XY)
+        arch.archipelago_options.neighbourhood = 15.0
+        arch.archipelago_options.avoidance_time_horizon = 15.0
+        arch.add_island(Island(Transform(), valid_mesh(square, cs=XY)))
+        a = Agent.create((5.0, 0.0), (-1.0, 0.0), 0.5, 1.0, 2.0, cs=XY)
+        a.current_target = (9.0, 0.0)
+        agent = arch.add_agent(a)
+        if with_character:
+            arch.add_character(Character((0.0, 5.0), (0.0, -1.0), 0.5))
+        arch.update(0.01)
+        return np.asarray(arch.get_agent(agent).get_desired_velocity(), dtype=np.float32)
+
+    assert tuple(run(False)) == (1.0, 0.0)
+    v = run(True)
+    assert float(np.hypot(v[0], v[1])) > 1.1, v
+
+
+def test_reached_target_agent_has_different_avoidance(make_backend):  # avoidance_test.rs:765-853
+    """35 frames of a moving agent passing one that has reached its target: with
+    reached_destination_avoidance_responsibility = 1/3 the standing agent takes 1/4 of the
+    avoidance and the moving one 3/4 (dodgy_2d's responsibility weighting)."""
+    from landmass_b200 import XY, Agent
+
+    square = dict(vertices=[(-10.0, -10.0), (10.0, -10.0), (10.0, 10.0), (-10.0, 10.0)], polygons=[[0, 1, 2, 3]],
+                  polygon_type_indices=[0])
+    arch = new_archipelago(make_backend(), cs=XY)
+    arch.add_island(Island(Transform(), valid_mesh(square, cs=XY)))
+    a1 = Agent.create((0.0, 0.0), (0.0, 0.0), 0.5, 1.0, 1.0, cs=XY)
+    a1.current_target = (0.0, 0.0)
+    a2 = Agent.create((0.0, -3.0), (0.0, 1.0), 0.5, 1.0, 1.0, cs=XY)
+    a2.current_target = (0.0, 3.0)
+    id1, id2 = arch.add_agent(a1), arch.add_agent(a2)
+    arch.archipelago_options.avoidance_time_horizon = 100.0
+    arch.archipelago_options.obstacle_avoidance_time_horizon = 0.1
+    arch.archipelago_options.reached_destination_avoidance_responsibility = 1.0 / 3.0
+    for _ in range(35):
+        arch.update(0.1)
+        for i in (id1, id2):
+            ag = arch.get_agent_mut(i)
+            ag.velocity = np.asarray(ag.get_desired_velocity(), dtype=np.float32)
+            ag.position = np.asarray(ag.position, dtype=np.float32) + ag.velocity * np.float32(0.1)
+    x1 = float(arch.get_agent(id1).position[0])
+    x2 = float(arch.get_agent(id2).position[0])
+    # the reference asserts one-sidedly: (x - expected) < 0.01
+    assert x1 - 0.25 < 0.01 and x2 - 0.75 < 0.01, (x1, x2)
+    # and both did move aside, the mover three times as far as the stander
+    assert abs(x1) > 0.1 and abs(x2) > 0.3 and abs(abs(x2) / abs(x1) - 3.0) < 0.5, (x1, x2)

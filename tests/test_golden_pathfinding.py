@@ -101,6 +101,25 @@ def test_detour_for_high_cost_path(make_backend):  # pathfinding_test.rs:592-669
         [seg(i, [0, 1, 2, 3, 4, 5, 6], [1, 2, 3, 2, 3, 2])], [])
 
 
+def test_detour_for_high_cost_path_across_boundary_links(make_backend):  # pathfinding_test.rs:671-777
+    mesh_1 = dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (2.0, 0.0), (2.0, 1.0), (3.0, 0.0), (3.0, 1.0)],
+                  polygons=[[0, 1, 2, 3], [2, 1, 4, 5], [5, 4, 6, 7]], polygon_type_indices=[0, 0, 0])
+    mesh_2 = dict(vertices=[(0.0, 2.0), (1.0, 2.0), (1.0, 3.0), (0.0, 3.0), (2.0, 2.0), (2.0, 3.0), (3.0, 2.0), (3.0, 3.0),
+                            (0.0, 1.0), (1.0, 1.0), (2.0, 1.0), (3.0, 1.0)],
+                  polygons=[[0, 1, 2, 3], [2, 1, 4, 5], [5, 4, 6, 7], [1, 0, 8, 9], [6, 4, 10, 11]],
+                  polygon_type_indices=[0, 0, 0, 1, 0])
+    arch = new_archipelago(make_backend(), cs=XY)
+    arch.set_type_index_cost(1, 5.1)
+    i1 = arch.add_island(Island(Transform(), valid_mesh(mesh_1, cs=XY)))
+    i2 = arch.add_island(Island(Transform(), valid_mesh(mesh_2, cs=XY)))
+    path, _ = find_path_between_nodes(arch, (i1, 0), (i2, 0))
+    # straight up through the expensive node (type 1, cost 5.1) would be shorter; the detour over the
+    # far boundary link is cheaper
+    segs, links = path
+    assert segs == [seg(i1, [0, 1, 2], [1, 2]), seg(i2, [4, 2, 1, 0], [0, 0, 0])]
+    assert len(links) == 1 and links[0][0] == (i1, 2) and links[0][1] == (i2, 4)
+
+
 def test_fast_path_not_ignored_by_heuristic(make_backend):  # pathfinding_test.rs:779-858
     arch, i = xy_arch(make_backend, meshes.ring(11, [1, 0, 0, 0, 0, 1, 1, 1]), [(1, 0.5)])
     assert find_path_between_nodes(arch, (i, 2), (i, 4))[0] == (
