@@ -80,6 +80,47 @@ def test_finds_next_point_in_zig_zag(oracle_backend):  # path_test.rs:136-243
         np.testing.assert_allclose(g[1], e[1], rtol=0, atol=4e-6)
 
 
+def test_starts_at_end_index_goes_to_end_point(oracle_backend):  # path_test.rs:261-310
+    arch = new_archipelago(oracle_backend)
+    i = arch.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), valid_mesh(dict(
+        vertices=[(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.0, 1.0, 0.0), (1.0, 2.0, 0.0), (0.0, 2.0, 0.0)],
+        polygons=[[0, 1, 2, 3], [3, 2, 4, 5]], polygon_type_indices=[0, 0]))))
+    arch._sync_navdata()
+    nodes, portals = [arch.node_id(i, 0), arch.node_id(i, 1)], [2, _abi.NONE]
+    idx, kind, pt = oracle_backend.next_straight_point(nodes, portals, 1, (0.25, 1.1, 0.0), 1, (0.75, 1.9, 0.0))
+    assert (idx, kind) == (1, 0) and tuple(pt[:3]) == tuple(np.float32([0.75, 1.9, 0.0]))
+
+
+def test_straight_path_includes_animation_link(oracle_backend):  # path_test.rs:312-427
+    """Two mesh chunks joined by an animation link: the funnel reports the link as its own step
+    (start point on the start edge straight ahead of the agent, end point on the end edge) and
+    resumes behind it."""
+    from landmass_b200 import AnimationLink
+
+    arch = new_archipelago(oracle_backend, cs=XY)
+    i = arch.add_island(Island(Transform((0.0, 0.0), 0.0), valid_mesh(dict(
+        vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (1.0, 2.0), (0.0, 2.0), (1.0, 3.0), (0.0, 3.0),
+                  (0.0, 5.0), (1.0, 5.0), (1.0, 6.0), (0.0, 6.0), (1.0, 7.0), (0.0, 7.0)],
+        polygons=[[0, 1, 2, 3], [3, 2, 4, 5], [5, 4, 6, 7], [8, 9, 10, 11], [11, 10, 12, 13]],
+        polygon_type_indices=[0] * 5), cs=XY)))
+    link_key = arch.add_animation_link(AnimationLink(start_edge=((0.0, 3.0), (1.0, 3.0)),
+                                                     end_edge=((0.0, 5.0), (1.0, 5.0)), cost=1.0, kind=0,
+                                                     bidirectional=False))
+    arch._sync_navdata()
+    f = arch._flat
+    links = [l for l in range(f["n_links"]) if f["link_kind"][l] == _abi.LINK_ANIMATION
+             and f["link_anim_id"][l] == link_key.idx]
+    assert len(links) == 1
+    nodes = [arch.node_id(i, k) for k in (0, 1, 2, 3, 4)]
+    portals = [2, 2, _abi.PORTAL_LINK | links[0], 2, _abi.NONE]
+    # PathIndex {segment 1, corridor 0} = flat index 3, {segment 1, corridor 1} = flat index 4
+    idx, kind, pt = oracle_backend.next_straight_point(nodes, portals, 0, (0.1, 0.1, 0.0), 4, (0.9, 6.9, 0.0))
+    assert (idx, kind) == (3, 1)
+    assert tuple(pt[:3]) == tuple(np.float32([0.1, 3.0, 0.0])) and tuple(pt[3:6]) == tuple(np.float32([0.1, 5.0, 0.0]))
+    idx, kind, pt = oracle_backend.next_straight_point(nodes, portals, 3, pt[3:6].copy(), 4, (0.9, 6.9, 0.0))
+    assert (idx, kind) == (4, 0) and tuple(pt[:3]) == tuple(np.float32([0.9, 6.9, 0.0]))
+
+
 def test_query_finds_path_across_islands(make_backend):  # query_test.rs:272-327
     arch = new_archipelago(make_backend(), cs=XY)
     mesh = valid_mesh(dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)],
