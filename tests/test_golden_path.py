@@ -121,6 +121,85 @@ def test_straight_path_includes_animation_link(oracle_backend):  # path_test.rs:
     assert (idx, kind) == (4, 0) and tuple(pt[:3]) == tuple(np.float32([0.9, 6.9, 0.0]))
 
 
+def collect_steps(backend, nodes, portals, start, end, limit):
+    """path_test.rs:19-57 incl. animation-link steps: [(flat index, kind, start/waypoint, end)]."""
+    out = []
+    cur_index, cur_point = start
+    it, force = 0, False
+    while (force or cur_index != end[0]) and it < limit:
+        force = False
+        it += 1
+        idx, kind, pt = backend.next_straight_point(nodes, portals, cur_index, cur_point, end[0], end[1])
+        if kind == 1:
+            out.append((idx, 1, tuple(float(x) for x in pt[:3]), tuple(float(x) for x in pt[3:6])))
+            cur_index, cur_point = idx, pt[3:6].copy()  # after the link we stand at its end point
+            force = True
+        else:
+            out.append((idx, 0, tuple(float(x) for x in pt[:3]), None))
+            cur_index, cur_point = idx, pt[:3].copy()
+    return out
+
+
+def link_arch(oracle_backend, vertices, polygons, links):
+    """One XY island + animation links [(start edge, end edge)]; returns (arch, node ids, off-mesh link ids)."""
+    from landmass_b200 import AnimationLink
+
+    arch = new_archipelago(oracle_backend, cs=XY)
+    i = arch.add_island(Island(Transform((0.0, 0.0), 0.0), valid_mesh(dict(
+        vertices=vertices, polygons=polygons, polygon_type_indices=[0] * len(polygons)), cs=XY)))
+    keys = [arch.add_animation_link(AnimationLink(start_edge=a, end_edge=b, cost=1.0, kind=0, bidirectional=False))
+            for a, b in links]
+    arch._sync_navdata()
+    f = arch._flat
+    ids = []
+    for k in keys:
+        hit = [l for l in range(f["n_links"]) if f["link_kind"][l] == _abi.LINK_ANIMATION
+               and f["link_anim_id"][l] == k.idx]
+        assert len(hit) == 1
+        ids.append(hit[0])
+    return arch, [arch.node_id(i, k) for k in range(len(polygons))], ids
+
+
+def test_multiple_animation_links_in_a_row(oracle_backend):  # path_test.rs:428-601
+    arch, n, l = link_arch(
+        oracle_backend,
+        [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (0.0, 2.0), (1.0, 2.0), (1.0, 3.0), (0.0, 3.0),
+         (0.0, 4.0), (1.0, 4.0), (1.0, 5.0), (0.0, 5.0), (0.0, 6.0), (1.0, 6.0), (1.0, 7.0), (0.0, 7.0),
+         (1.0, 8.0), (0.0, 8.0)],
+        [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12, 13, 14, 15], [15, 14, 16, 17]],
+        [(((0.0, 1.0), (1.0, 1.0)), ((0.0, 2.0), (1.0, 2.0))), (((0.0, 3.0), (1.0, 3.0)), ((0.0, 4.0), (1.0, 4.0))),
+         (((0.0, 5.0), (1.0, 5.0)), ((0.0, 6.0), (1.0, 6.0)))])
+    portals = [_abi.PORTAL_LINK | l[0], _abi.PORTAL_LINK | l[1], _abi.PORTAL_LINK | l[2], 2, _abi.NONE]
+    got = collect_steps(oracle_backend, n, portals, (0, (0.5, 0.5, 0.0)), (4, (0.5, 7.5, 0.0)), 10)
+    assert got == [(1, 1, (0.5, 1.0, 0.0), (0.5, 2.0, 0.0)), (2, 1, (0.5, 3.0, 0.0), (0.5, 4.0, 0.0)),
+                   (3, 1, (0.5, 5.0, 0.0), (0.5, 6.0, 0.0)), (4, 0, (0.5, 7.5, 0.0), None)]
+
+
+def test_obscured_animation_link_is_made_visible_by_straight_path(oracle_backend):  # path_test.rs:602-719
+    arch, n, l = link_arch(
+        oracle_backend,
+        [(0.0, 0.0), (7.0, 0.0), (7.0, 1.0), (6.0, 1.0), (8.0, 3.0), (0.0, 3.0), (0.0, 1.0), (0.0, 5.0),
+         (8.0, 5.0), (8.0, 6.0), (0.0, 6.0), (8.0, 7.0), (0.0, 7.0)],
+        [[0, 1, 2, 3, 6], [3, 4, 5, 6], [7, 8, 9, 10], [10, 9, 11, 12]],
+        [(((0.0, 3.0), (8.0, 3.0)), ((0.0, 5.0), (8.0, 5.0)))])
+    portals = [3, _abi.PORTAL_LINK | l[0], 2, _abi.NONE]
+    got = collect_steps(oracle_backend, n, portals, (0, (6.5, 0.5, 0.0)), (3, (0.1, 6.9, 0.0)), 10)
+    assert got == [(0, 0, (6.0, 1.0, 0.0), None), (2, 1, (6.0, 3.0, 0.0), (6.0, 5.0, 0.0)),
+                   (3, 0, (0.10000000149011612, 6.900000095367432, 0.0), None)]
+
+
+def test_end_point_after_animation_link_is_reported(oracle_backend):  # path_test.rs:720-840
+    arch, n, l = link_arch(
+        oracle_backend,
+        [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (0.0, 2.0), (1.0, 2.0), (1.0, 3.0), (0.0, 3.0),
+         (0.0, 4.0), (1.0, 4.0), (1.0, 5.0), (0.0, 5.0)],
+        [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11]],
+        [(((0.0, 1.0), (1.0, 1.0)), ((0.0, 2.0), (1.0, 2.0))), (((0.0, 3.0), (1.0, 3.0)), ((0.0, 4.0), (1.0, 4.0)))])
+    portals = [_abi.PORTAL_LINK | l[0], _abi.PORTAL_LINK | l[1], _abi.NONE]
+    got = collect_steps(oracle_backend, n, portals, (0, (0.5, 0.5, 0.0)), (1, (0.5, 2.5, 0.0)), 10)
+    assert got == [(1, 1, (0.5, 1.0, 0.0), (0.5, 2.0, 0.0)), (1, 0, (0.5, 2.5, 0.0), None)]
+
+
 def test_query_finds_path_across_islands(make_backend):  # query_test.rs:272-327
     arch = new_archipelago(make_backend(), cs=XY)
     mesh = valid_mesh(dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)],
