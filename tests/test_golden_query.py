@@ -1,7 +1,7 @@
 """Query-API known answers (query.rs:70-94, 185-273) — transcribed from
 crates/landmass/src/query_test.rs: `samples_point_on_nav_mesh_or_near_nav_mesh` (85-140), `no_path`
 (223-270), `finds_path_with_override_type_index_costs` (331-417), `start_and_end_in_same_node`
-(473-517).  Exact equality like the reference (`assert_eq!`), through the batched entry points."""
+(473-517), `one_animation_link_path` (519-599).  Exact equality like the reference (`assert_eq!`), through the batched entry points."""
 import numpy as np
 
 from landmass_b200 import XY, Archipelago, ArchipelagoOptions, Island, Transform
@@ -74,3 +74,28 @@ def test_start_and_end_in_same_node(make_backend):  # query_test.rs:473-517
     start = arch.sample_point((0.25, 0.25), np.float32(0.1))
     end = arch.sample_point((0.75, 0.75), np.float32(0.1))
     assert straight_path(arch, start, end) == [(0.25, 0.25), (0.75, 0.75)]
+
+
+def test_one_animation_link_path(make_backend):  # query_test.rs:519-599
+    """Start and end on two mesh chunks joined by an animation link: waypoint, link step (start and
+    end points on the link's edges straight ahead of the start), waypoint — exact."""
+    from landmass_b200 import AnimationLink, _abi
+
+    arch = new_arch(make_backend())
+    arch.add_island(Island(Transform(), valid_mesh(dict(
+        vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (0.0, 2.0), (1.0, 2.0), (1.0, 3.0), (0.0, 3.0)],
+        polygons=[[0, 1, 2, 3], [4, 5, 6, 7]], polygon_type_indices=[0, 0]), cs=XY)))
+    link_key = arch.add_animation_link(AnimationLink(start_edge=((0.0, 1.0), (1.0, 1.0)),
+                                                     end_edge=((0.0, 2.0), (1.0, 2.0)), cost=1.0, kind=0,
+                                                     bidirectional=False))
+    start = arch.sample_point((0.25, 0.25), np.float32(0.1))
+    end = arch.sample_point((0.75, 2.75), np.float32(0.1))
+    assert start is not None and end is not None
+    sn, en = arch.node_id(*start[1]), arch.node_id(*end[1])
+    succ, begin, kind, pts, link = arch.backend.find_straight_paths(
+        [sn], [XY.to_landmass(start[0])], [en], [XY.to_landmass(end[0])])
+    assert succ[0] == 1 and list(kind) == [0, 1, 0]
+    assert tuple(pts[0][:2]) == (0.25, 0.25)
+    assert tuple(pts[1][:2]) == (0.25, 1.0) and tuple(pts[1][3:5]) == (0.25, 2.0)
+    assert tuple(pts[2][:2]) == (0.75, 2.75)
+    assert int(link[1]) == link_key.idx  # the step names the animation link (link_id)
