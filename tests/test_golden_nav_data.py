@@ -1,0 +1,86 @@
+"""Island linking known answers (nav_data.rs:827-1011, host side: landmass_b200/linking.py) —
+transcribed from crates/landmass/src/nav_data_test.rs:178-505
+(`link_edges_between_islands_links_touching_islands`): two overlapping islands under the same
+rotated transform; every boundary link's source node, destination node, destination type and
+portal (rounded to 1e-5 like the reference), both for edge_link_distance 1e-5 and 1e-3."""
+import math
+
+import numpy as np
+import pytest
+
+from landmass_b200 import Island, Transform
+from landmass_b200.nav_data import NavigationData, transform_apply
+from tests.helpers import valid_mesh
+
+MESH_1 = dict(
+    vertices=[(1.0, 0.0, 1.0), (1.0, 1.0, 1.0), (-1.0, 1.0, 1.0), (-1.0, 0.0, 1.0), (-1.0, -1.0, 1.0), (1.0, -1.0, 1.0),
+              (2.0, 0.0, 1.0), (2.0, 2.0, 1.0), (-2.0, 2.0, 1.0), (-2.0, 0.0, 1.0), (-2.0, -2.0, 1.0), (2.0, -2.0, 1.0)],
+    polygons=[[0, 6, 7, 1], [1, 7, 8, 2], [2, 8, 9, 3], [10, 4, 3, 9], [10, 11, 5, 4], [6, 0, 5, 11]],
+    polygon_type_indices=[0, 1, 1, 1, 0, 0])
+MESH_2 = dict(
+    vertices=[(-1.0, -0.5, 1.0), (-0.5, -0.5, 1.0), (0.5, -0.5, 1.0), (1.0, -0.5, 1.0), (-1.0, 0.5, 1.0), (-0.5, 0.5, 1.0),
+              (0.5, 0.5, 1.0), (1.0, 0.5, 1.0), (-0.5, 1.0, 1.0), (0.5, 1.0, 1.0), (-0.5, -1.0, 1.0), (0.5, -1.0, 1.0)],
+    polygons=[[5, 4, 0, 1], [1, 2, 6, 5], [3, 7, 6, 2], [5, 6, 9, 8], [10, 11, 2, 1]],
+    polygon_type_indices=[0, 0, 0, 0, 2])
+
+T = np.array([1.0, 2.0, 3.0], dtype=np.float32)
+ROT = math.pi * -0.25
+
+# (source island, polygon) -> [(destination island, polygon, destination type, portal a, portal b)]
+EXPECTED = {
+    (1, 0): [(2, 2, 0, (1.0, 0.0, 1.0), (1.0, 0.5, 1.0))],
+    (1, 1): [(2, 3, 0, (0.5, 1.0, 1.0), (-0.5, 1.0, 1.0))],
+    (1, 2): [(2, 0, 0, (-1.0, 0.5, 1.0), (-1.0, 0.0, 1.0))],
+    (1, 3): [(2, 0, 0, (-1.0, 0.0, 1.0), (-1.0, -0.5, 1.0))],
+    (1, 4): [(2, 4, 2, (-0.5, -1.0, 1.0), (0.5, -1.0, 1.0))],
+    (1, 5): [(2, 2, 0, (1.0, -0.5, 1.0), (1.0, 0.0, 1.0))],
+    # reverse links
+    (2, 0): [(1, 2, 1, (-1.0, 0.0, 1.0), (-1.0, 0.5, 1.0)), (1, 3, 1, (-1.0, -0.5, 1.0), (-1.0, 0.0, 1.0))],
+    (2, 2): [(1, 0, 0, (1.0, 0.5, 1.0), (1.0, 0.0, 1.0)), (1, 5, 0, (1.0, 0.0, 1.0), (1.0, -0.5, 1.0))],
+    (2, 3): [(1, 1, 1, (-0.5, 1.0, 1.0), (0.5, 1.0, 1.0))],
+    (2, 4): [(1, 4, 0, (0.5, -1.0, 1.0), (-0.5, -1.0, 1.0))],
+}
+
+
+def rounded(p):
+    w = transform_apply(T, np.float32(ROT), np.array(p, dtype=np.float32)).astype(np.float64)
+    return tuple(np.round(w * 1e5) * 1e-5)
+
+
+@pytest.mark.parametrize("edge_link_distance,order", [(1e-5, (1, 2)), (1e-3, (2, 1))])
+def test_link_edges_between_islands_links_touching_islands(edge_link_distance, order):
+    meshes = {1: valid_mesh(MESH_1), 2: valid_mesh(MESH_2)}
+    nd = NavigationData()
+    keys = {}
+    for which in order:  # the reference links (1, 2) and then, separately, (2, 1): same links
+        keys[which] = nd.add_island(Island(Transform(tuple(T), ROT), meshes[which]))
+    nd.update(edge_link_distance, 0.25)
+    f = nd.flatten()
+    island_of = {f["_island_key_to_index"][k]: which for which, k in keys.items()}
+    begin = f["island_poly_begin"]
+
+    def node_ref(n):
+        i = int(np.searchsorted(begin, n, side="right") - 1)
+        return island_of[i], int(n - begin[i])
+
+    got = {}
+    for l in range(f["n_links"]):
+        src = node_ref(int(f["link_src_node"][l]))
+        dst = node_ref(int(f["link_dst_node"][l]))
+        portal = f["link_portal"][l].astype(np.float64)
+        a = tuple(np.round(portal[:3] * 1e5) * 1e-5)
+        b = tuple(np.round(portal[3:] * 1e5) * 1e-5)
+        got.setdefault(src, []).append((dst[0], dst[1], int(f["link_dst_type"][l]), a, b))
+    for v in got.values():
+        v.sort(key=lambda e: e[0] * 100 + e[1])
+    expected = {k: [(d, p, t, rounded(a), rounded(b)) for d, p, t, a, b in v] for k, v in EXPECTED.items()}
+    assert set(got) == set(expected)
+    for k in expected:
+        assert len(got[k]) == len(expected[k]), k
+        for g, e in zip(got[k], expected[k]):
+            assert g[:3] == e[:3], (k, g, e)
+            np.testing.assert_allclose(g[3], e[3], atol=1.5e-5, rtol=0, err_msg=str(k))
+            np.testing.assert_allclose(g[4], e[4], atol=1.5e-5, rtol=0, err_msg=str(k))
+    # every node that got a link has its boundary re-cut (modified_node_refs_to_update, nav_data_test.rs:456-476)
+    modified = {node_ref(int(n)) for n in f["modified_node"]} if f.get("n_modified", 0) else set()
+    assert modified == set(expected)
