@@ -84,3 +84,43 @@ def test_link_edges_between_islands_links_touching_islands(edge_link_distance, o
     # every node that got a link has its boundary re-cut (modified_node_refs_to_update, nav_data_test.rs:456-476)
     modified = {node_ref(int(n)) for n in f["modified_node"]} if f.get("n_modified", 0) else set()
     assert modified == set(expected)
+
+
+def test_modifies_node_boundaries_for_linked_islands():  # nav_data_test.rs:805-876
+    """Three islands touching along parts of their borders: the nodes with boundary links get a
+    `ModifiedNode` — the boundary edges that remain once the linked stretch is cut out, with the new
+    vertices the cut introduces (vertex index >= the mesh's vertex count = index into new_vertices)."""
+    mesh = valid_mesh(dict(
+        vertices=[(1.0, 1.0, 1.0), (2.0, 1.0, 1.0), (2.0, 2.0, 1.0), (1.0, 2.0, 1.0), (2.0, 3.0, 1.0), (1.0, 3.0, 1.0)],
+        polygons=[[0, 1, 2, 3], [3, 2, 4, 5]], polygon_type_indices=[0, 0]))
+    nd = NavigationData()
+    k1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    k2 = nd.add_island(Island(Transform((1.0, -1.0, 0.0), 0.0), mesh))
+    k3 = nd.add_island(Island(Transform((2.0, 3.5, 0.0), math.pi * -0.5), mesh))
+    nd.update(1e-6, 1e-6)
+    f = nd.flatten()
+    idx = {f["_island_key_to_index"][k]: n for n, k in ((1, k1), (2, k2), (3, k3))}
+    begin = f["island_poly_begin"]
+    n_mesh_vertices = 6
+    got = {}
+    for m in range(f["n_modified"]):
+        n = int(f["modified_node"][m])
+        i = int(np.searchsorted(begin, n, side="right") - 1)
+        verts = [tuple(np.round(v.astype(np.float64) / 1e-4) * 1e-4)
+                 for v in f["modified_verts"][f["modified_vert_begin"][m]:f["modified_vert_begin"][m + 1]]]
+        order = sorted(range(len(verts)), key=lambda a: verts[a])          # clone_sort_round_modified_nodes
+        rank = {old: new for new, old in enumerate(order)}
+        edges = []
+        for l, r in f["modified_edges"][f["modified_edge_begin"][m]:f["modified_edge_begin"][m + 1]]:
+            l, r = int(l), int(r)
+            if l >= n_mesh_vertices:
+                l = rank[l - n_mesh_vertices] + n_mesh_vertices
+            if r >= n_mesh_vertices:
+                r = rank[r - n_mesh_vertices] + n_mesh_vertices
+            edges.append((l, r))
+        got[(idx[i], int(n - begin[i]))] = (sorted(edges), [verts[a] for a in order])
+    assert got == {
+        (1, 0): ([(0, 1), (3, 0)], []),
+        (2, 1): ([(2, 6), (4, 5)], [(3.0, 1.5)]),
+        (3, 0): ([(0, 6), (1, 2), (3, 0)], [(3.0, 2.0)]),
+    }
