@@ -177,3 +177,32 @@ def test_clears_path_for_no_target_or_missing_nodes(make_backend):
         assert arch.get_agent(aid).state() == want
         assert arch.agent_path(aid) is None and not arch.get_pathing_results()
         assert tuple(arch.get_agent(aid).get_desired_velocity()) == (0.0, 0.0, 0.0)
+
+
+def test_agent_host_api():
+    """Host-side Agent bookkeeping, no update involved: agent_test.rs:20-64 (type-index cost
+    overrides; zero / negative costs are refused) and 775-799 (start / end of an animation link need
+    a reached link / a started link)."""
+    from landmass_b200 import XY
+    from landmass_b200.archipelago import (NotReachedAnimationLinkError, NotUsingAnimationLinkError,
+                                           ReachedAnimationLink)
+    agent = Agent.create((0.0, 0.0), (0.0, 0.0), 1.0, 1.0, 1.0, cs=XY)
+    assert agent.override_type_index_cost(1, 3.0) and agent.override_type_index_cost(2, 0.5)
+    assert sorted(agent.get_type_index_cost_overrides()) == [(1, 3.0), (2, 0.5)]
+    agent.override_type_index_cost(1, 5.0)
+    assert sorted(agent.get_type_index_cost_overrides()) == [(1, 5.0), (2, 0.5)]
+    assert not agent.override_type_index_cost(0, 0.0) and not agent.override_type_index_cost(0, -0.5)
+    assert agent.remove_overridden_type_index_cost(1) and not agent.remove_overridden_type_index_cost(1)
+
+    agent = Agent.create((0.0, 0.0), (0.0, 0.0), 0.5, 1.0, 2.0, cs=XY)
+    with pytest.raises(NotReachedAnimationLinkError):
+        agent.start_animation_link()
+    with pytest.raises(NotUsingAnimationLinkError):
+        agent.end_animation_link()
+    agent._current_animation_link = ReachedAnimationLink((0.0, 0.0), (1.0, 0.0), None)
+    with pytest.raises(NotUsingAnimationLinkError):
+        agent.end_animation_link()
+    agent.start_animation_link()
+    assert agent.is_using_animation_link()
+    agent.end_animation_link()
+    assert not agent.is_using_animation_link()
