@@ -115,3 +115,44 @@ def test_height_mesh_errors():  # nav_mesh_test.rs:884-1081
 def test_no_error_on_concave_height_polygon_with_flipped_coordinate_system():  # nav_mesh_test.rs:1083-1106
     NavigationMesh(TRIANGLE, [[2, 1, 0]], [0], height_mesh=create_height_mesh(TRIANGLE, [[[2, 1, 0]]]),
                    cs=FlippedXYZ).validate()
+
+
+# --- ValidNavigationMesh::sample_edge (feeds animation-link creation) — nav_mesh_test.rs:1164-1345 ---
+
+def sampled(mesh, a, b, max_vertical_distance):
+    from landmass_b200.anim_links import sample_edge
+    edge = (np.array(a, dtype=np.float32), np.array(b, dtype=np.float32))
+    return sorted((node, (float(t0), float(t1))) for node, (t0, t1) in sample_edge(mesh, edge, max_vertical_distance))
+
+
+F32 = lambda x: float(np.float32(x))
+
+
+def test_samples_edge_on_square():  # nav_mesh_test.rs:1164-1214
+    m = NavigationMesh(TRIANGLE + [(0.0, 1.0, 0.0)], [[0, 1, 2, 3]], [0]).validate()
+    assert sampled(m, (0.5, 0.0, 0.0), (1.0, 0.5, 0.0), 1.0) == [(0, (0.0, 1.0))]
+    assert sampled(m, (0.0, 0.5, 0.0), (2.0, 0.5, 0.0), 1.0) == [(0, (0.0, 0.5))]
+    assert sampled(m, (-1.0, 0.5, 0.0), (3.0, 0.5, 0.0), 1.0) == [(0, (0.25, 0.5))]
+    assert sampled(m, (1.0, 0.5, 0.0), (2.0, 0.5, 0.0), 1.0) == []
+
+
+def test_samples_edge_for_multiple_nodes():  # nav_mesh_test.rs:1216-1256
+    from landmass_b200 import XY
+    m = NavigationMesh([(0.0, 0.0), (1.0, 0.0), (2.0, 0.0), (0.0, 1.0), (1.0, 1.0), (2.0, 1.0), (0.0, 2.0), (1.0, 2.0),
+                        (2.0, 2.0)], [[0, 1, 4, 3], [1, 2, 5, 4], [3, 4, 7, 6], [4, 5, 8, 7]], [0] * 4, cs=XY).validate()
+    assert sampled(m, (0.75, 0.5, 0.0), (1.5, 1.25, 0.0), 1.0) == [
+        (0, (0.0, F32(0.33333334))), (1, (F32(0.33333334), F32(0.6666667))), (3, (F32(0.6666667), 1.0))]
+
+
+def test_samples_edge_for_multiple_floors():  # nav_mesh_test.rs:1258-1297
+    m = NavigationMesh(TRIANGLE + [(0.0, 1.0, 0.0), (0.0, 0.0, 2.0), (1.0, 0.0, 2.0), (1.0, 1.0, 2.0), (0.0, 1.0, 2.0)],
+                       [[0, 1, 2, 3], [4, 5, 6, 7]], [0] * 2).validate()
+    assert sampled(m, (0.0, 0.1, 0.5), (1.0, 0.1, 0.5), 1.0) == [(0, (0.0, 1.0))]
+    assert sampled(m, (0.0, 0.1, 1.5), (1.0, 0.1, 1.5), 1.0) == [(1, (0.0, 1.0))]
+
+
+def test_samples_edge_along_stairs():  # nav_mesh_test.rs:1299-1345
+    m = NavigationMesh(TRIANGLE + [(0.0, 1.0, 0.0), (0.0, 2.0, 2.0), (1.0, 2.0, 2.0), (0.0, 3.0, 2.0), (1.0, 3.0, 2.0)],
+                       [[0, 1, 2, 3], [3, 2, 5, 4], [4, 5, 7, 6]], [0] * 3).validate()
+    assert sampled(m, (0.5, 0.5, 1.0), (0.5, 2.5, 1.0), 0.5) == [(1, (0.375, 0.625))]
+    assert sampled(m, (0.5, 0.5, 1.0), (0.5, 2.5, 1.0), 1.1) == [(0, (0.0, 0.25)), (1, (0.25, 0.75)), (2, (0.75, 1.0))]
