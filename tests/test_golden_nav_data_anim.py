@@ -1,0 +1,134 @@
+"""Animation links -> off-mesh links on the host (landmass_b200/anim_links.py), transcribed from
+crates/landmass/src/nav_data_test.rs:1262 onwards.  The reference keeps per-link start/end
+`NodePortal`s and patches the off-mesh links incrementally; here every `update` rebuilds them from
+scratch, so the tests compare the state AFTER each update: the node portals each link edge samples
+(`world_portal_to_node_portals`) and the off-mesh links per node (destination, portals, cost, kind,
+owning animation link)."""
+import numpy as np
+import pytest
+
+from landmass_b200 import XYZ, AnimationLink, Island, NavigationMesh, Transform, _abi
+from landmass_b200.anim_links import world_portal_to_node_portals
+from landmass_b200.nav_data import NavigationData
+
+f32 = np.float32
+
+
+def P(*pts):
+    return tuple(tuple(float(f32(c)) for c in p) for p in pts)
+
+
+def rect_mesh(w, h, z):
+    return NavigationMesh([(0.0, 0.0, z), (w, 0.0, z), (w, h, z), (0.0, h, z)], [[0, 1, 2, 3]], [0]).validate()
+
+
+def node_portals(nd, edge, distance=1.0):
+    cs = nd.cs
+    portal = (cs.to_landmass(edge[0]), cs.to_landmass(edge[1]))
+    return sorted(((k, int(p)), (float(iv[0]), float(iv[1])))
+                  for k, p, iv in world_portal_to_node_portals(portal, nd.islands.items(), cs, distance))
+
+
+def link_portals(nd, link_id, distance=1.0):
+    link = nd.get_animation_link(link_id)
+    return node_portals(nd, link.start_edge, distance), node_portals(nd, link.end_edge, distance)
+
+
+def off_mesh_links(nd):
+    """{(island key, polygon): [(destination node, destination type, portal, destination portal, cost, kind,
+    animation link key index)]} over the animation off-mesh links (node_to_off_mesh_link_ids)."""
+    out = {}
+    for l in nd.links:
+        if l.kind != _abi.LINK_ANIMATION:
+            continue
+        out.setdefault((l.src_island, l.src_polygon), []).append(
+            ((l.dst_island, l.dst_polygon), l.dst_type, P(*l.portal), P(*l.dst_portal), l.cost, l.anim_kind, l.anim_id))
+    return {k: sorted(v, key=repr) for k, v in out.items()}
+
+
+def link(start, end, kind=0, cost=1.0, bidirectional=False):
+    return AnimationLink(start_edge=start, end_edge=end, cost=cost, kind=kind, bidirectional=bidirectional)
+
+
+def update(nd):
+    nd.update(1e-5, 1.0)
+
+
+def test_generates_animation_links():  # nav_data_test.rs:1262-1428
+    mesh = rect_mesh(1.0, 1.0, 13.0)
+    nd = NavigationData(XYZ)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    i3 = nd.add_island(Island(Transform((-2.0, 0.0, 0.0), 0.0), mesh))
+    i4 = nd.add_island(Island(Transform((0.0, 4.0, 0.0), 0.0), mesh))
+    e1 = (((0.1, 0.9, 13.0), (0.9, 0.9, 13.0)), ((0.1, 4.1, 13.0), (0.9, 4.1, 13.0)))
+    e2 = (((0.9, 0.1, 13.0), (0.9, 0.9, 13.0)), ((2.1, 0.1, 13.0), (2.1, 0.9, 13.0)))
+    e3 = (((-1.1, 0.1, 13.0), (-1.1, 0.9, 13.0)), ((0.1, 0.1, 13.0), (0.1, 0.9, 13.0)))
+    l1 = nd.add_animation_link(link(*e1, kind=0))
+    l2 = nd.add_animation_link(link(*e2, kind=1))
+    l3 = nd.add_animation_link(link(*e3, kind=2))
+    update(nd)
+    whole = (0.0, 1.0)
+    assert link_portals(nd, l1) == ([((i1, 0), whole)], [((i4, 0), whole)])
+    assert link_portals(nd, l2) == ([((i1, 0), whole)], [((i2, 0), whole)])
+    assert link_portals(nd, l3) == ([((i3, 0), whole)], [((i1, 0), whole)])
+    assert off_mesh_links(nd) == {
+        (i1, 0): sorted([((i4, 0), 0, P(*e1[0]), P(*e1[1]), 1.0, 0, l1.idx),
+                         ((i2, 0), 0, P(*e2[0]), P(*e2[1]), 1.0, 1, l2.idx)], key=repr),
+        (i3, 0): [((i1, 0), 0, P(*e3[0]), P(*e3[1]), 1.0, 2, l3.idx)],
+    }
+
+
+E_12 = (((0.9, 0.1, 7.0), (0.9, 0.9, 7.0)), ((2.1, 0.1, 7.0), (2.1, 0.9, 7.0)))
+E_21 = (((2.1, 1.1, 7.0), (2.1, 1.9, 7.0)), ((0.9, 1.1, 7.0), (0.9, 1.9, 7.0)))
+
+
+def test_removing_animation_link_removes_off_mesh_links():  # nav_data_test.rs:1430-1603
+    mesh = rect_mesh(1.0, 2.0, 7.0)
+    nd = NavigationData(XYZ)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    update(nd)  # the islands are not brand new any more
+    l1 = nd.add_animation_link(link(*E_12, kind=0))
+    l2 = nd.add_animation_link(link(*E_21, kind=1))
+    update(nd)
+    whole = (0.0, 1.0)
+    assert link_portals(nd, l1) == ([((i1, 0), whole)], [((i2, 0), whole)])
+    assert link_portals(nd, l2) == ([((i2, 0), whole)], [((i1, 0), whole)])
+    assert off_mesh_links(nd) == {
+        (i1, 0): [((i2, 0), 0, P(*E_12[0]), P(*E_12[1]), 1.0, 0, l1.idx)],
+        (i2, 0): [((i1, 0), 0, P(*E_21[0]), P(*E_21[1]), 1.0, 1, l2.idx)],
+    }
+    nd.remove_animation_link(l1)
+    update(nd)
+    links = off_mesh_links(nd)
+    assert list(links) == [(i2, 0)] and len(links[(i2, 0)]) == 1
+    nd.add_animation_link(link(*E_12, kind=0))
+    update(nd)
+    links = off_mesh_links(nd)
+    assert sorted(links, key=repr) == sorted([(i1, 0), (i2, 0)], key=repr)
+    assert len(links[(i1, 0)]) == 1 and len(links[(i2, 0)]) == 1
+
+
+def test_existing_animation_link_is_linked_for_new_island():  # nav_data_test.rs:1605-1769
+    mesh = rect_mesh(1.0, 2.0, 7.0)
+    nd = NavigationData(XYZ)
+    l1 = nd.add_animation_link(link(*E_12, kind=0))
+    l2 = nd.add_animation_link(link(*E_21, kind=1))
+    update(nd)  # no islands yet: no portals, no off-mesh links
+    assert link_portals(nd, l1) == ([], []) and link_portals(nd, l2) == ([], [])
+    assert off_mesh_links(nd) == {} and nd.links == []
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    update(nd)  # one end each: still no off-mesh links
+    whole = (0.0, 1.0)
+    assert link_portals(nd, l1) == ([((i1, 0), whole)], [])
+    assert link_portals(nd, l2) == ([], [((i1, 0), whole)])
+    assert off_mesh_links(nd) == {}
+    i2 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    update(nd)
+    assert link_portals(nd, l1) == ([((i1, 0), whole)], [((i2, 0), whole)])
+    assert link_portals(nd, l2) == ([((i2, 0), whole)], [((i1, 0), whole)])
+    assert off_mesh_links(nd) == {
+        (i1, 0): [((i2, 0), 0, P(*E_12[0]), P(*E_12[1]), 1.0, 0, l1.idx)],
+        (i2, 0): [((i1, 0), 0, P(*E_21[0]), P(*E_21[1]), 1.0, 1, l2.idx)],
+    }
