@@ -279,6 +279,20 @@ def _vec_lerp(a, b, s):  # glam Vec3::lerp
     return (a * f32(f32(1.0) - s) + b * s).astype(f32)
 
 
+def effective_link_edges(link, cs):
+    """The (start, end) world portals a link is sampled with: a point start edge turns the end edge
+    into its midpoint, and for bidirectional links a point end edge does the same to the start."""
+    start = (cs.to_landmass(link.start_edge[0]), cs.to_landmass(link.start_edge[1]))
+    end = (cs.to_landmass(link.end_edge[0]), cs.to_landmass(link.end_edge[1]))
+    if (start[0] == start[1]).all():
+        mid = ((end[0] + end[1]) * f32(0.5)).astype(f32)
+        end = (mid, mid)
+    elif link.bidirectional and (end[0] == end[1]).all():
+        mid = ((start[0] + start[1]) * f32(0.5)).astype(f32)
+        start = (mid, mid)
+    return start, end
+
+
 def create_animation_off_mesh_links(nav_data, max_vertical_distance):
     """create_off_mesh_links_for_animation_links (nav_data.rs:516-825), rebuilt from scratch:
     for every animation link, every (start portal, end portal) pair with overlapping intervals."""
@@ -289,14 +303,7 @@ def create_animation_off_mesh_links(nav_data, max_vertical_distance):
     key_to_island = dict(islands)
     links = []
     for link_key, link in nav_data.animation_links.items():
-        start = (cs.to_landmass(link.start_edge[0]), cs.to_landmass(link.start_edge[1]))
-        end = (cs.to_landmass(link.end_edge[0]), cs.to_landmass(link.end_edge[1]))
-        if (start[0] == start[1]).all():
-            mid = ((end[0] + end[1]) * f32(0.5)).astype(f32)
-            end = (mid, mid)
-        elif link.bidirectional and (end[0] == end[1]).all():
-            mid = ((start[0] + start[1]) * f32(0.5)).astype(f32)
-            start = (mid, mid)
+        start, end = effective_link_edges(link, cs)
         start_portals = world_portal_to_node_portals(start, islands, cs, max_vertical_distance)
         if not start_portals:
             continue

@@ -22,16 +22,12 @@ def rect_mesh(w, h, z):
     return NavigationMesh([(0.0, 0.0, z), (w, 0.0, z), (w, h, z), (0.0, h, z)], [[0, 1, 2, 3]], [0]).validate()
 
 
-def node_portals(nd, edge, distance=1.0):
-    cs = nd.cs
-    portal = (cs.to_landmass(edge[0]), cs.to_landmass(edge[1]))
-    return sorted(((k, int(p)), (float(iv[0]), float(iv[1])))
-                  for k, p, iv in world_portal_to_node_portals(portal, nd.islands.items(), cs, distance))
-
-
 def link_portals(nd, link_id, distance=1.0):
-    link = nd.get_animation_link(link_id)
-    return node_portals(nd, link.start_edge, distance), node_portals(nd, link.end_edge, distance)
+    from landmass_b200.anim_links import effective_link_edges
+    start, end = effective_link_edges(nd.get_animation_link(link_id), nd.cs)
+    return tuple(sorted(((k, int(p)), (float(iv[0]), float(iv[1])))
+                        for k, p, iv in world_portal_to_node_portals(e, nd.islands.items(), nd.cs, distance))
+                 for e in (start, end))
 
 
 def off_mesh_links(nd):
@@ -132,3 +128,73 @@ def test_existing_animation_link_is_linked_for_new_island():  # nav_data_test.rs
         (i1, 0): [((i2, 0), 0, P(*E_12[0]), P(*E_12[1]), 1.0, 0, l1.idx)],
         (i2, 0): [((i1, 0), 0, P(*E_21[0]), P(*E_21[1]), 1.0, 1, l2.idx)],
     }
+
+
+def test_added_island_mixes_new_and_old_portals():  # nav_data_test.rs:1771-2002
+    mesh = rect_mesh(1.0, 1.0, 7.0)
+    nd = NavigationData(XYZ)
+    i00 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i11 = nd.add_island(Island(Transform((2.0, 2.0, 0.0), 0.0), mesh))
+    bottom, top = ((0.5, 0.5, 7.0), (2.5, 0.5, 7.0)), ((0.5, 2.5, 7.0), (2.5, 2.5, 7.0))
+    l1 = nd.add_animation_link(link(bottom, top, kind=0))
+    l2 = nd.add_animation_link(link(top, bottom, kind=1))
+    update(nd)
+    lo, hi = (0.0, 0.25), (0.75, 1.0)
+    assert link_portals(nd, l1) == ([((i00, 0), lo)], [((i11, 0), hi)])
+    assert link_portals(nd, l2) == ([((i11, 0), hi)], [((i00, 0), lo)])
+    assert off_mesh_links(nd) == {}  # the intervals do not overlap
+    i01 = nd.add_island(Island(Transform((0.0, 2.0, 0.0), 0.0), mesh))
+    i10 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    update(nd)
+    by_key = lambda ps: sorted(ps, key=lambda p: p[1])
+    assert tuple(map(by_key, link_portals(nd, l1))) == ([((i00, 0), lo), ((i10, 0), hi)], [((i01, 0), lo), ((i11, 0), hi)])
+    assert tuple(map(by_key, link_portals(nd, l2))) == ([((i01, 0), lo), ((i11, 0), hi)], [((i00, 0), lo), ((i10, 0), hi)])
+    assert off_mesh_links(nd) == {
+        (i00, 0): [((i01, 0), 0, P((0.5, 0.5, 7.0), (1.0, 0.5, 7.0)), P((0.5, 2.5, 7.0), (1.0, 2.5, 7.0)), 1.0, 0, l1.idx)],
+        (i10, 0): [((i11, 0), 0, P((2.0, 0.5, 7.0), (2.5, 0.5, 7.0)), P((2.0, 2.5, 7.0), (2.5, 2.5, 7.0)), 1.0, 0, l1.idx)],
+        (i01, 0): [((i00, 0), 0, P((0.5, 2.5, 7.0), (1.0, 2.5, 7.0)), P((0.5, 0.5, 7.0), (1.0, 0.5, 7.0)), 1.0, 1, l2.idx)],
+        (i11, 0): [((i10, 0), 0, P((2.0, 2.5, 7.0), (2.5, 2.5, 7.0)), P((2.0, 0.5, 7.0), (2.5, 0.5, 7.0)), 1.0, 1, l2.idx)],
+    }
+
+
+def test_same_island_animation_link():  # nav_data_test.rs:2004-2076
+    from landmass_b200 import XY
+    mesh = NavigationMesh([(0.0, 0.0), (1.0, 0.0), (1.0, 2.0), (0.0, 2.0)], [[0, 1, 2, 3]], [0], cs=XY).validate()
+    nd = NavigationData(XY)
+    i = nd.add_island(Island(Transform((0.0, 0.0), 0.0), mesh))
+    l = nd.add_animation_link(link(((0.1, 0.5), (0.9, 0.5)), ((0.1, 1.5), (0.9, 1.5))))
+    update(nd)
+    assert link_portals(nd, l) == ([((i, 0), (0.0, 1.0))], [((i, 0), (0.0, 1.0))])
+    assert off_mesh_links(nd) == {
+        (i, 0): [((i, 0), 0, P((0.1, 0.5, 0.0), (0.9, 0.5, 0.0)), P((0.1, 1.5, 0.0), (0.9, 1.5, 0.0)), 1.0, 0, l.idx)]}
+
+
+TWO_SQUARES = dict(vertices=[(0.0, 0.0, 7.0), (1.0, 0.0, 7.0), (1.0, 1.0, 7.0), (0.0, 1.0, 7.0),
+                             (0.0, 3.0, 7.0), (1.0, 3.0, 7.0), (1.0, 4.0, 7.0), (0.0, 4.0, 7.0)],
+                   polygons=[[0, 1, 2, 3], [4, 5, 6, 7]], polygon_type_indices=[0, 0])
+
+
+@pytest.mark.parametrize("links_first", [False, True])
+def test_point_animation_links_are_connected(links_first):  # nav_data_test.rs:2078-2203, 2205-2336
+    """A point end edge receives the whole start edge; a point start edge collapses the end edge to its
+    midpoint.  Second variant: the links exist (and have been updated once) before the island does."""
+    mesh = NavigationMesh(**TWO_SQUARES).validate()
+    nd = NavigationData(XYZ)
+    if not links_first:
+        i = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    edge, point = ((0.0, 0.5, 7.0), (1.0, 0.5, 7.0)), ((0.5, 3.5, 7.0), (0.5, 3.5, 7.0))
+    l1 = nd.add_animation_link(link(edge, point, kind=0))
+    l2 = nd.add_animation_link(link(point, edge, kind=1))
+    if links_first:
+        update(nd)
+        i = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    update(nd)
+    whole = (0.0, 1.0)
+    assert link_portals(nd, l1) == ([((i, 0), whole)], [((i, 1), whole)])
+    assert link_portals(nd, l2) == ([((i, 1), whole)], [((i, 0), whole)])
+    mid = ((0.5, 0.5, 7.0), (0.5, 0.5, 7.0))
+    assert off_mesh_links(nd) == {
+        (i, 0): [((i, 1), 0, P(*edge), P(*point), 1.0, 0, l1.idx)],
+        (i, 1): [((i, 0), 0, P(*point), P(*mid), 1.0, 1, l2.idx)],
+    }
+    assert len(nd.links) == 2
