@@ -198,3 +198,112 @@ def test_point_animation_links_are_connected(links_first):  # nav_data_test.rs:2
         (i, 1): [((i, 0), 0, P(*point), P(*mid), 1.0, 1, l2.idx)],
     }
     assert len(nd.links) == 2
+
+
+def test_changing_island_does_not_cause_duplicate_off_mesh_links():  # nav_data_test.rs:2338-2543
+    mesh = rect_mesh(1.0, 1.0, 7.0)
+    nd = NavigationData(XYZ)
+    i00 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i10 = nd.add_island(Island(Transform((3.5, 0.0, 0.0), 0.0), mesh))
+    i11 = nd.add_island(Island(Transform((3.0, 3.0, 0.0), 0.0), mesh))
+    i01 = nd.add_island(Island(Transform((-0.5, 3.0, 0.0), 0.0), mesh))
+    l = nd.add_animation_link(link(((0.0, 0.5, 7.0), (4.0, 0.5, 7.0)), ((0.0, 3.5, 7.0), (4.0, 3.5, 7.0))))
+    update(nd)
+    by_iv = lambda ps: sorted(ps, key=lambda p: p[1])
+    assert tuple(map(by_iv, link_portals(nd, l))) == (
+        [((i00, 0), (0.0, 0.25)), ((i10, 0), (0.875, 1.0))], [((i01, 0), (0.0, 0.125)), ((i11, 0), (0.75, 1.0))])
+    assert off_mesh_links(nd) == {
+        (i00, 0): [((i01, 0), 0, P((0.0, 0.5, 7.0), (0.5, 0.5, 7.0)), P((0.0, 3.5, 7.0), (0.5, 3.5, 7.0)), 1.0, 0, l.idx)],
+        (i10, 0): [((i11, 0), 0, P((3.5, 0.5, 7.0), (4.0, 0.5, 7.0)), P((3.5, 3.5, 7.0), (4.0, 3.5, 7.0)), 1.0, 0, l.idx)],
+    }
+    assert len(nd.links) == 2
+    nd.get_island(i01).set_transform(Transform((0.0, 3.0, 0.0), 0.0))
+    nd.get_island(i10).set_transform(Transform((3.0, 0.0, 0.0), 0.0))
+    update(nd)
+    assert tuple(map(by_iv, link_portals(nd, l))) == (
+        [((i00, 0), (0.0, 0.25)), ((i10, 0), (0.75, 1.0))], [((i01, 0), (0.0, 0.25)), ((i11, 0), (0.75, 1.0))])
+    assert off_mesh_links(nd) == {
+        (i00, 0): [((i01, 0), 0, P((0.0, 0.5, 7.0), (1.0, 0.5, 7.0)), P((0.0, 3.5, 7.0), (1.0, 3.5, 7.0)), 1.0, 0, l.idx)],
+        (i10, 0): [((i11, 0), 0, P((3.0, 0.5, 7.0), (4.0, 0.5, 7.0)), P((3.0, 3.5, 7.0), (4.0, 3.5, 7.0)), 1.0, 0, l.idx)],
+    }
+    assert len(nd.links) == 2
+
+
+def test_changing_island_does_not_cause_duplicate_off_mesh_links_for_point_links():  # nav_data_test.rs:2545-2765
+    mesh = rect_mesh(1.0, 1.0, 7.0)
+    nd = NavigationData(XYZ)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((0.0, 2.0, 0.0), 0.0), mesh))
+    p1, p2 = (0.25, 0.5, 7.0), (0.75, 0.5, 7.0)
+    l1 = nd.add_animation_link(link((p1, p1), ((0.0, 2.5, 7.0), (0.5, 2.5, 7.0)), kind=0))
+    l2 = nd.add_animation_link(link(((0.5, 2.5, 7.0), (1.0, 2.5, 7.0)), (p2, p2), kind=1))
+    want = {
+        (i1, 0): [((i2, 0), 0, P(p1, p1), P((0.25, 2.5, 7.0), (0.25, 2.5, 7.0)), 1.0, 0, l1.idx)],
+        (i2, 0): [((i1, 0), 0, P((0.5, 2.5, 7.0), (1.0, 2.5, 7.0)), P(p2, p2), 1.0, 1, l2.idx)],
+    }
+    whole = (0.0, 1.0)
+    for moved in (False, True):
+        if moved:
+            nd.get_island(i2).set_transform(Transform((0.1, 2.0, 0.0), 0.0))
+        update(nd)
+        assert link_portals(nd, l1) == ([((i1, 0), whole)], [((i2, 0), whole)])
+        assert link_portals(nd, l2) == ([((i2, 0), whole)], [((i1, 0), whole)])
+        assert off_mesh_links(nd) == want and len(nd.links) == 2
+
+
+TWO_FLOORS = [(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)]
+
+
+@pytest.mark.parametrize("use_height_mesh", [False, True])
+def test_generates_animation_links_at_correct_height(use_height_mesh):  # nav_data_test.rs:2767-2864, 2866-2991
+    """Two floors at z = 5 and z = 10.  Link edges 0.9 above / below a floor are sampled, 1.1 are not.
+    Second variant: the polygons lie at z = -100 / +100 and only the height mesh has the real floors."""
+    from landmass_b200 import HeightNavigationMesh, HeightPolygon
+    floor = lambda z: [(x, y, z) for x, y in TWO_FLOORS]
+    hm = None
+    zs = (5.0, 10.0)
+    if use_height_mesh:
+        hm = HeightNavigationMesh(vertices=floor(5.0) + floor(10.0),
+                                  triangles=[[0, 1, 2], [2, 3, 0], [0, 1, 2], [2, 3, 0]],
+                                  polygons=[HeightPolygon(0, 4, 0, 2), HeightPolygon(4, 4, 2, 2)])
+        zs = (-100.0, 100.0)
+    mesh = NavigationMesh(floor(zs[0]) + floor(zs[1]), [[0, 1, 2, 3], [4, 5, 6, 7]], [0, 0], height_mesh=hm).validate()
+    nd = NavigationData(XYZ)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    inside = (((0.9, 0.1, 4.1), (0.9, 0.9, 4.1)), ((2.1, 0.1, 10.9), (2.1, 0.9, 10.9)))
+    outside = (((0.9, 0.1, 3.9), (0.9, 0.9, 3.9)), ((2.1, 0.1, 11.1), (2.1, 0.9, 11.1)))
+    l1 = nd.add_animation_link(link(*inside, kind=0))
+    l2 = nd.add_animation_link(link(*outside, kind=0 if use_height_mesh else 1))
+    update(nd)
+    assert link_portals(nd, l1) == ([((i1, 0), (0.0, 1.0))], [((i2, 1), (0.0, 1.0))])
+    assert link_portals(nd, l2) == ([], [])
+    assert off_mesh_links(nd) == {(i1, 0): [((i2, 1), 0, P(*inside[0]), P(*inside[1]), 1.0, 0, l1.idx)]}
+    assert len(nd.links) == 1
+
+
+def test_animation_link_along_angled_surface():  # nav_data_test.rs:2993-3186
+    """A ramp between two flat squares; the link edge runs along it at half height.  With a vertical
+    distance of 0.4 only the middle of the ramp is close enough; with 0.6 all three polygons are."""
+    mesh = NavigationMesh(
+        [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.0, 1.0, 0.0), (1.0, 2.0, 1.0), (0.0, 2.0, 1.0),
+         (1.0, 3.0, 1.0), (0.0, 3.0, 1.0)], [[0, 1, 2, 3], [3, 2, 4, 5], [5, 4, 6, 7]], [0] * 3).validate()
+    nd = NavigationData(XYZ)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    edges = (((0.5, 0.5, 0.5), (0.5, 2.5, 0.5)), ((2.5, 0.5, 0.5), (2.5, 2.5, 0.5)))
+    l = nd.add_animation_link(link(*edges))
+    nd.update(0.01, 0.4)
+    iv = (float(f32(0.3)), float(f32(0.7)))
+    assert link_portals(nd, l, 0.4) == ([((i1, 1), iv)], [((i2, 1), iv)])
+    assert off_mesh_links(nd) == {
+        (i1, 1): [((i2, 1), 0, P((0.5, 1.1, 0.5), (0.5, 1.9, 0.5)), P((2.5, 1.1, 0.5), (2.5, 1.9, 0.5)), 1.0, 0, l.idx)]}
+    nd.remove_animation_link(l)
+    l = nd.add_animation_link(link(*edges))
+    nd.update(0.01, 0.6)
+    ivs = [(0.0, 0.25), (0.25, 0.75), (0.75, 1.0)]
+    assert link_portals(nd, l, 0.6) == ([((i1, p), ivs[p]) for p in range(3)], [((i2, p), ivs[p]) for p in range(3)])
+    ys = [(0.5, 1.0), (1.0, 2.0), (2.0, 2.5)]
+    assert off_mesh_links(nd) == {
+        (i1, p): [((i2, p), 0, P((0.5, ys[p][0], 0.5), (0.5, ys[p][1], 0.5)),
+                   P((2.5, ys[p][0], 0.5), (2.5, ys[p][1], 0.5)), 1.0, 0, l.idx)] for p in range(3)}
