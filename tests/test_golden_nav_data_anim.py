@@ -307,3 +307,78 @@ def test_animation_link_along_angled_surface():  # nav_data_test.rs:2993-3186
     assert off_mesh_links(nd) == {
         (i1, p): [((i2, p), 0, P((0.5, ys[p][0], 0.5), (0.5, ys[p][1], 0.5)),
                    P((2.5, ys[p][0], 0.5), (2.5, ys[p][1], 0.5)), 1.0, 0, l.idx)] for p in range(3)}
+
+
+def test_generates_bidirectional_animation_links():  # nav_data_test.rs:3188-3409
+    mesh = rect_mesh(1.0, 1.0, 13.0)
+    nd = NavigationData(XYZ)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((2.0, 0.0, 0.0), 0.0), mesh))
+    i3 = nd.add_island(Island(Transform((-2.0, 0.0, 0.0), 0.0), mesh))
+    i4 = nd.add_island(Island(Transform((0.0, 4.0, 0.0), 0.0), mesh))
+    e1 = (((0.1, 0.9, 13.0), (0.9, 0.9, 13.0)), ((0.1, 4.1, 13.0), (0.9, 4.1, 13.0)))
+    e2 = (((0.9, 0.1, 13.0), (0.9, 0.9, 13.0)), ((2.1, 0.1, 13.0), (2.1, 0.9, 13.0)))
+    e3 = (((-1.1, 0.1, 13.0), (-1.1, 0.9, 13.0)), ((0.1, 0.1, 13.0), (0.1, 0.9, 13.0)))
+    l1 = nd.add_animation_link(link(*e1, kind=0, bidirectional=True))
+    l2 = nd.add_animation_link(link(*e2, kind=1, bidirectional=True))
+    l3 = nd.add_animation_link(link(*e3, kind=2, bidirectional=True))
+    update(nd)
+    whole = (0.0, 1.0)
+    assert link_portals(nd, l1) == ([((i1, 0), whole)], [((i4, 0), whole)])
+    assert link_portals(nd, l2) == ([((i1, 0), whole)], [((i2, 0), whole)])
+    assert link_portals(nd, l3) == ([((i3, 0), whole)], [((i1, 0), whole)])
+    assert off_mesh_links(nd) == {
+        (i1, 0): sorted([((i4, 0), 0, P(*e1[0]), P(*e1[1]), 1.0, 0, l1.idx),
+                         ((i2, 0), 0, P(*e2[0]), P(*e2[1]), 1.0, 1, l2.idx),
+                         ((i3, 0), 0, P(*e3[1]), P(*e3[0]), 1.0, 2, l3.idx)], key=repr),
+        (i2, 0): [((i1, 0), 0, P(*e2[1]), P(*e2[0]), 1.0, 1, l2.idx)],
+        (i3, 0): [((i1, 0), 0, P(*e3[0]), P(*e3[1]), 1.0, 2, l3.idx)],
+        (i4, 0): [((i1, 0), 0, P(*e1[1]), P(*e1[0]), 1.0, 0, l1.idx)],
+    }
+
+
+def test_bidirectional_links_collapse_either_end():  # nav_data_test.rs:3411-3644
+    mesh = NavigationMesh(**TWO_SQUARES).validate()
+    nd = NavigationData(XYZ)
+    i = nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    a, b = (0.25, 3.5, 7.0), (0.75, 3.5, 7.0)
+    l1 = nd.add_animation_link(link(((0.0, 0.5, 7.0), (0.5, 0.5, 7.0)), (a, a), kind=0, bidirectional=True))
+    l2 = nd.add_animation_link(link((b, b), ((0.5, 0.5, 7.0), (1.0, 0.5, 7.0)), kind=1, bidirectional=True))
+    a0, b0 = (0.25, 0.5, 7.0), (0.75, 0.5, 7.0)
+    whole = (0.0, 1.0)
+    want = {
+        (i, 0): sorted([((i, 1), 0, P(a0, a0), P(a, a), 1.0, 0, l1.idx), ((i, 1), 0, P(b0, b0), P(b, b), 1.0, 1, l2.idx)],
+                       key=repr),
+        (i, 1): sorted([((i, 0), 0, P(a, a), P(a0, a0), 1.0, 0, l1.idx), ((i, 0), 0, P(b, b), P(b0, b0), 1.0, 1, l2.idx)],
+                       key=repr),
+    }
+    for step in ("first", "moved away", "moved back"):
+        if step == "moved away":
+            nd.get_island(i).set_transform(Transform((100.0, 100.0, 100.0), 0.0))
+        elif step == "moved back":
+            nd.get_island(i).set_transform(Transform((0.0, 0.0, 0.0), 0.0))
+        update(nd)
+        if step == "moved away":
+            assert link_portals(nd, l1) == ([], []) and link_portals(nd, l2) == ([], [])
+            assert off_mesh_links(nd) == {} and nd.links == []
+        else:
+            assert link_portals(nd, l1) == ([((i, 0), whole)], [((i, 1), whole)])
+            assert link_portals(nd, l2) == ([((i, 1), whole)], [((i, 0), whole)])
+            assert off_mesh_links(nd) == want and len(nd.links) == 4
+
+
+def test_bidirectional_links_use_correct_indices():  # nav_data_test.rs:3646-3748
+    from landmass_b200 import XY
+    mesh = NavigationMesh([(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0), (2.0, 0.0), (2.0, 1.0)],
+                          [[0, 1, 2, 3], [2, 1, 4, 5]], [0, 1], cs=XY).validate()
+    nd = NavigationData(XY)
+    i1 = nd.add_island(Island(Transform((0.0, 0.0), 0.0), mesh))
+    i2 = nd.add_island(Island(Transform((-3.0, 0.0), 0.0), mesh))
+    l = nd.add_animation_link(link(((0.1, 0.1), (0.1, 0.9)), ((-1.1, 0.1), (-1.1, 0.9)), bidirectional=True))
+    update(nd)
+    assert link_portals(nd, l) == ([((i1, 0), (0.0, 1.0))], [((i2, 1), (0.0, 1.0))])
+    s, e = ((0.1, 0.1, 0.0), (0.1, 0.9, 0.0)), ((-1.1, 0.1, 0.0), (-1.1, 0.9, 0.0))
+    assert off_mesh_links(nd) == {
+        (i1, 0): [((i2, 1), 1, P(*s), P(*e), 1.0, 0, l.idx)],   # destination type index of (island_2, node 1)
+        (i2, 1): [((i1, 0), 0, P(*e), P(*s), 1.0, 0, l.idx)],
+    }
