@@ -124,3 +124,49 @@ def test_modifies_node_boundaries_for_linked_islands():  # nav_data_test.rs:805-
         (2, 1): ([(2, 6), (4, 5)], [(3.0, 1.5)]),
         (3, 0): ([(0, 6), (1, 2), (3, 0)], [(3.0, 2.0)]),
     }
+
+
+def boundary_links(nd, names, digits=6):
+    """{(island name, polygon): [(destination name, polygon, destination type, portal a, portal b)]} over the
+    boundary links, portals rounded like clone_sort_round_links (nav_data_test.rs:134-176)."""
+    from landmass_b200 import _abi
+    rnd = lambda p: tuple(float(x) + 0.0 for x in np.round(np.asarray(p, dtype=np.float64), digits))
+    out = {}
+    for l in nd.links:
+        if l.kind != _abi.LINK_BOUNDARY:
+            continue
+        out.setdefault((names[l.src_island], l.src_polygon), []).append(
+            (names[l.dst_island], l.dst_polygon, l.dst_type, rnd(l.portal[0]), rnd(l.portal[1])))
+    return {k: sorted(v) for k, v in out.items()}
+
+
+def test_update_links_islands_and_unlinks_on_delete():  # nav_data_test.rs:506-733
+    mesh = valid_mesh(dict(
+        vertices=[(1.0, 0.0, 1.0), (2.0, 0.0, 1.0), (2.0, 2.0, 1.0), (0.0, 2.0, 1.0), (0.0, 1.0, 1.0), (1.0, 1.0, 1.0)],
+        polygons=[[0, 1, 2, 5], [4, 5, 2, 3]], polygon_type_indices=[0, 0]))
+    nd = NavigationData()
+    pi = math.pi
+    keys = [nd.add_island(Island(Transform(t, r), mesh)) for t, r in [
+        ((0.0, 0.0, 0.0), 0.0), ((0.0, 0.0, 0.0), pi * 0.5), ((0.0, 0.0, 0.0), pi), ((3.0, 0.0, 0.0), pi),
+        ((2.0, 3.0, 0.0), pi * -0.5)]]
+    names = {k: n + 1 for n, k in enumerate(keys)}
+    nd.update(0.01, 0.01)
+    assert boundary_links(nd, names) == {
+        (1, 0): [(4, 0, 0, (2.0, 0.0, 1.0), (1.0, 0.0, 1.0)), (5, 0, 0, (2.0, 2.0, 1.0), (2.0, 1.0, 1.0))],
+        (1, 1): [(2, 0, 0, (0.0, 1.0, 1.0), (0.0, 2.0, 1.0))],
+        (2, 0): [(1, 1, 0, (0.0, 2.0, 1.0), (0.0, 1.0, 1.0))],
+        (2, 1): [(3, 0, 0, (-1.0, 0.0, 1.0), (-2.0, 0.0, 1.0))],
+        (3, 0): [(2, 1, 0, (-2.0, 0.0, 1.0), (-1.0, 0.0, 1.0))],
+        (4, 0): [(1, 0, 0, (1.0, 0.0, 1.0), (2.0, 0.0, 1.0))],
+        (5, 0): [(1, 0, 0, (2.0, 1.0, 1.0), (2.0, 2.0, 1.0))],
+    }
+    nd.remove_island(keys[1])
+    nd.remove_island(keys[3])
+    nd.get_island(keys[4]).set_transform(Transform((0.0, 0.0, 0.0), pi * 0.5))  # island 5 takes island 2's place
+    nd.update(0.01, 0.01)
+    assert boundary_links(nd, names) == {
+        (1, 1): [(5, 0, 0, (0.0, 1.0, 1.0), (0.0, 2.0, 1.0))],
+        (3, 0): [(5, 1, 0, (-2.0, 0.0, 1.0), (-1.0, 0.0, 1.0))],
+        (5, 0): [(1, 1, 0, (0.0, 2.0, 1.0), (0.0, 1.0, 1.0))],
+        (5, 1): [(3, 0, 0, (-1.0, 0.0, 1.0), (-2.0, 0.0, 1.0))],
+    }
