@@ -170,3 +170,121 @@ def test_update_links_islands_and_unlinks_on_delete():  # nav_data_test.rs:506-7
         (5, 0): [(1, 1, 0, (0.0, 2.0, 1.0), (0.0, 1.0, 1.0))],
         (5, 1): [(3, 0, 0, (-1.0, 0.0, 1.0), (-2.0, 0.0, 1.0))],
     }
+
+
+SQUARE_2D = dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 1.0), (0.0, 1.0)], polygons=[[0, 1, 2, 3]],
+                 polygon_type_indices=[0])
+
+
+def test_stale_modified_nodes_are_removed():  # nav_data_test.rs:877-922
+    mesh = valid_mesh(dict(
+        vertices=[(1.0, 1.0, 1.0), (2.0, 1.0, 1.0), (2.0, 2.0, 1.0), (1.0, 2.0, 1.0), (2.0, 3.0, 1.0), (1.0, 3.0, 1.0)],
+        polygons=[[0, 1, 2, 3], [3, 2, 4, 5]], polygon_type_indices=[0, 0]))
+    nd = NavigationData()
+    nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    k2 = nd.add_island(Island(Transform((1.0, -1.0, 0.0), 0.0), mesh))
+    nd.update(1e-6, 1e-6)
+    assert len(nd.modified_nodes) == 2
+    nd.remove_island(k2)
+    nd.update(1e-6, 1e-6)
+    assert len(nd.modified_nodes) == 0
+
+
+def test_modified_node_is_removed_for_no_boundary_links():  # nav_data_test.rs:924-987
+    from landmass_b200 import XY, AnimationLink
+    mesh = valid_mesh(SQUARE_2D, cs=XY)
+    nd = NavigationData(XY)
+    k1 = nd.add_island(Island(Transform((0.0, 0.0), 0.0), mesh))
+    k2 = nd.add_island(Island(Transform((1.0, 0.0), 0.0), mesh))
+    nd.add_island(Island(Transform((-2.0, 0.0), 0.0), mesh))
+    nd.add_animation_link(AnimationLink(start_edge=((0.1, 0.1), (0.1, 0.9)), end_edge=((-1.1, 0.1), (-1.1, 0.9)),
+                                        cost=1.0, kind=0, bidirectional=False))
+    nd.update(1e-5, 1e-5)
+    assert any(m.island == k1 and m.polygon == 0 for m in nd.modified_nodes)
+    nd.remove_island(k2)  # the animation link stays, the boundary links go
+    nd.update(1e-5, 1e-5)
+    assert not any(m.island == k1 and m.polygon == 0 for m in nd.modified_nodes)
+
+
+def test_empty_navigation_mesh_is_safe():  # nav_data_test.rs:989-1027
+    nd = NavigationData()
+    nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), valid_mesh(dict(
+        vertices=[(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.0, 1.0, 0.0)], polygons=[[0, 1, 2, 3]],
+        polygon_type_indices=[0]))))
+    nd.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), valid_mesh(dict(vertices=[], polygons=[],
+                                                                          polygon_type_indices=[]))))
+    nd.update(1e-6, 1e-6)
+    nd.flatten()
+
+
+def test_error_on_set_zero_or_negative_type_index_cost(make_backend):  # nav_data_test.rs:1029-1041
+    from landmass_b200 import XY, Archipelago, ArchipelagoOptions
+    from landmass_b200.nav_data import SetTypeIndexCostError
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5, cs=XY), cs=XY, backend=make_backend())
+    for cost in (0.0, -1.0):
+        with pytest.raises(SetTypeIndexCostError):
+            arch.set_type_index_cost(0, cost)
+
+
+def connected(arch, agent_kwargs=None):
+    """`are_nodes_connected(island_1 node 0, island_2 node 0)` as one whole update sees it: an agent on
+    island 1 with a target on island 2 either gets a path or — unconnected regions — fails without
+    exploring a single node (pathfinding.rs:237-245)."""
+    from landmass_b200 import XY, Agent, AgentState
+    a = Agent.create((0.5, 0.5), (0.0, 0.0), 0.25, 1.0, 1.0, cs=XY)
+    a.current_target = (0.5, arch._island_2_y + 0.5)
+    for k, v in (agent_kwargs or {}).items():
+        setattr(a, k, v)
+    aid = arch.add_agent(a)
+    arch.update(0.01)
+    (result,) = arch.get_pathing_results()
+    state = arch.get_agent(aid).state()
+    arch.remove_agent(aid)
+    if result.success:
+        assert state == AgentState.Moving
+        return True
+    assert state == AgentState.NoPath and result.explored_nodes == 0
+    return False
+
+
+def two_squares_arch(make_backend):
+    from landmass_b200 import XY, Archipelago, ArchipelagoOptions
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5, cs=XY), cs=XY, backend=make_backend())
+    mesh = valid_mesh(SQUARE_2D, cs=XY)
+    arch.add_island(Island(Transform((0.0, 0.0), 0.0), mesh))
+    k2 = arch.add_island(Island(Transform((0.0, 2.0), 0.0), mesh))
+    arch._island_2_y = 2.0
+    return arch, k2
+
+
+def test_changed_island_rebuilds_region_connectivity(make_backend):  # nav_data_test.rs:1043-1108
+    arch, k2 = two_squares_arch(make_backend)
+    assert not connected(arch)
+    arch.get_island_mut(k2).set_transform(Transform((0.0, 1.0), 0.0))
+    arch._island_2_y = 1.0
+    assert connected(arch)
+    arch.get_island_mut(k2).set_transform(Transform((0.0, 2.0), 0.0))
+    arch._island_2_y = 2.0
+    assert not connected(arch)
+
+
+def test_changed_animation_link_rebuilds_region_connectivity(make_backend):  # nav_data_test.rs:1110-1175
+    from landmass_b200 import AnimationLink
+    arch, _ = two_squares_arch(make_backend)
+    assert not connected(arch)
+    l = arch.add_animation_link(AnimationLink(start_edge=((0.1, 0.9), (0.9, 0.9)), end_edge=((0.1, 2.1), (0.9, 2.1)),
+                                              cost=1.0, kind=0, bidirectional=False))
+    assert connected(arch)
+    arch.remove_animation_link(l)
+    assert not connected(arch)
+
+
+def test_permitted_animation_link_blocks_region_connectivity(make_backend):  # nav_data_test.rs:1177-1245
+    from landmass_b200 import AnimationLink, PermittedAnimationLinks
+    arch, _ = two_squares_arch(make_backend)
+    for kind in (0, 1):
+        arch.add_animation_link(AnimationLink(start_edge=((0.0, 0.9), (1.0, 0.9)), end_edge=((0.0, 2.1), (1.0, 2.1)),
+                                              kind=kind, cost=1.0, bidirectional=False))
+    assert connected(arch)
+    for kinds, want in [({0}, True), ({1}, True), ({2}, False)]:
+        assert connected(arch, dict(permitted_animation_links=PermittedAnimationLinks(frozenset(kinds)))) == want
