@@ -182,3 +182,43 @@ def test_agent_could_not_find_path(make_backend):  # lib_test.rs:1206-1232
     arch.update(1.0)
     assert arch.agent_path(agent) is None
     assert arch.get_agent(agent).state() == AgentState.NoPath
+
+
+def test_add_and_remove_agents_characters_islands():
+    """lib_test.rs:22-94 (agents), 96-153 (characters), 488-526 (islands), 528-563 (island dirty flag):
+    slot-map bookkeeping on the host; no backend is needed until `update`."""
+    from landmass_b200 import Character
+    from landmass_b200.archipelago import Archipelago, ArchipelagoOptions
+    from oracle.oracle_py import OracleBackend
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5), backend=OracleBackend())
+    zero = (0.0, 0.0, 0.0)
+    for add, get, ids, remove, make in [
+        (arch.add_agent, arch.get_agent, arch.get_agent_ids, arch.remove_agent,
+         lambda r: Agent.create(zero, zero, r, 0.0, 0.0)),
+        (arch.add_character, arch.get_character, arch.get_character_ids, arch.remove_character,
+         lambda r: Character(position=zero, velocity=zero, radius=r)),
+    ]:
+        k1, k2, k3 = add(make(1.0)), add(make(2.0)), add(make(3.0))
+        assert sorted(ids(), key=repr) == sorted([k1, k2, k3], key=repr)
+        assert [get(k).radius for k in (k1, k2, k3)] == [1.0, 2.0, 3.0]
+        remove(k2)
+        assert sorted(ids(), key=repr) == sorted([k1, k3], key=repr)
+        assert [get(k).radius for k in (k1, k3)] == [1.0, 3.0]
+        remove(k3)
+        assert list(ids()) == [k1] and get(k1).radius == 1.0
+        remove(k1)
+        assert list(ids()) == []
+
+    empty = valid_mesh(dict(vertices=[], polygons=[], polygon_type_indices=[]))
+    i1, i2, i3 = (arch.add_island(Island(Transform(zero, 0.0), empty)) for _ in range(3))
+    assert sorted(arch.get_island_ids(), key=repr) == sorted([i1, i2, i3], key=repr)
+    arch.remove_island(i2)
+    assert sorted(arch.get_island_ids(), key=repr) == sorted([i1, i3], key=repr)
+
+    assert arch.get_island(i1).dirty
+    arch.update(0.01)
+    assert not arch.get_island(i1).dirty
+    arch.get_island_mut(i1).set_transform(Transform(zero, 0.0))
+    assert arch.get_island(i1).dirty
+    arch.update(0.01)
+    assert not arch.get_island(i1).dirty
