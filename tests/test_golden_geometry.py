@@ -118,3 +118,43 @@ def test_clips_edge_part_way_estimating_triangle_height():  # geometry_test.rs:5
 
 def test_clips_edge_height_correctly_when_extending_line():  # geometry_test.rs:528-545
     assert clip(((0, 0, 2), (1, 0, 2), (1, 1, 2)), (0, 0.1, 1.5), (0.5, 0.1, 1.5), 1.0) == F(0.20000005, 1.0)
+
+
+# --- util_test.rs: the two BoundingBox operations the host-side link sampling uses ---
+
+def test_bounding_box_detects_ray_segment_intersection():  # util_test.rs:182-237
+    from landmass_b200.anim_links import intersects_ray_segment
+    bmin, bmax = V(-1, -2, -3), V(5, 4, 3)
+
+    def check(v0, v1, expected):
+        assert intersects_ray_segment(bmin, bmax, V(*v0), V(*v1)) == expected
+        assert intersects_ray_segment(bmin, bmax, V(*v1), V(*v0)) == expected
+
+    for axis in range(3):
+        def on_axis(t):
+            p = [2.0, 2.0, 2.0]
+            p[axis] = t
+            return tuple(p)
+        # the reference's six cases per axis: inside, through, entering, leaving, before, after
+        for a, b, expected in [(2, 4, True), (-3, 6, True), (-10, 2, True), (2, 10, True), (-10, -3, False),
+                               (6, 10, False)]:
+            check(on_axis(a), on_axis(b), expected)
+    check((-2, -3, -4), (6, 5, 4), True)
+    check((6, -3, -4), (-2, 5, 4), True)
+    check((-2, 5, -4), (6, -3, 4), True)
+    check((-2, -3, 4), (6, 5, -4), True)
+    check((8, -13, -4), (-12, 7, -4), False)
+    check((16, -5, 4), (-4, 15, 4), False)
+
+
+def test_transforms_bounds():  # util_test.rs:239-270
+    import math
+    from types import SimpleNamespace
+    from landmass_b200.anim_links import transformed_bounds
+    t, r = V(1, 2, 3), f32(0.75)
+    assert transformed_bounds(SimpleNamespace(mesh_bounds=None), t, r) is None  # Empty stays Empty
+    mesh = SimpleNamespace(mesh_bounds=np.array([1, 3, 2, 6, 4, 5], dtype=f32))
+    mn, mx = transformed_bounds(mesh, V(-4, 1, -3), f32(math.pi * -0.75))
+    root_2 = math.sqrt(2.0)
+    np.testing.assert_allclose(mn, (-3.0 / root_2 - 4.0, -10.0 / root_2 + 1.0, -1.0), atol=1e-6)
+    np.testing.assert_allclose(mx, (3.0 / root_2 - 4.0, -4.0 / root_2 + 1.0, 2.0), atol=1e-6)
