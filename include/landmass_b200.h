@@ -264,8 +264,30 @@ void lmb_destroy(lmb_ctx* ctx);
 const char* lmb_last_error(const lmb_ctx* ctx);
 
 /* Replaces the navigation data.  Call when `nav_data.update()` (nav_data.rs:1158-1180)
- * reports a change.  All device-side paths are dropped (agents with a target repath). */
+ * reports a change.  All device-side paths are dropped (agents with a target repath) —
+ * i.e. every island counts as invalidated; use lmb_navdata_update to keep the others. */
 int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* desc);
+
+/* What `NavigationData::update` returns (nav_data.rs:326-350: dropped off-mesh links, changed
+ * islands), expressed against the PREVIOUS upload's flattening so that stored paths can be
+ * carried over: node ids and link indices change whenever an island or link is added or removed. */
+typedef struct lmb_nav_remap {
+  uint32_t struct_size;
+  uint32_t n_old_islands;     /* n_islands of the previous upload */
+  const uint32_t* island_map; /* [n_old_islands] index of the same, UNCHANGED island in `desc`, or
+                                 LMB_NONE when it was removed or dirty (invalidated_islands) */
+  uint32_t n_old_links;       /* n_links of the previous upload */
+  const uint32_t* link_map;   /* [n_old_links] index of the same off-mesh link in `desc`, or LMB_NONE
+                                 when it was dropped (invalidated_off_mesh_links) */
+} lmb_nav_remap;
+
+/* lmb_navdata_upload that keeps the paths `Path::is_valid` (path.rs:381-400) keeps: a stored path
+ * survives when none of its island segments lies on an invalidated island and none of its off-mesh
+ * link segments uses a dropped link; its node ids / link indices are rewritten to the new
+ * flattening.  Every other path is marked invalid and handled by the next step exactly like the
+ * reference (lib.rs:350-358, agent.rs:454-456): paused agents lose it, agents with a target
+ * re-plan.  remap == NULL is lmb_navdata_upload. */
+int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* desc, const lmb_nav_remap* remap);
 
 /* One `Archipelago::update(delta_time)` (lib.rs:270-534) with HOST buffers:
  * H2D of inputs, phases A-D on the device, D2H of outputs; synchronous. */

@@ -157,6 +157,30 @@ class AgentsOut(C.Structure):
     ]
 
 
+class NavRemap(C.Structure):
+    """lmb_nav_remap: the previous upload's islands / links -> the new flattening (NONE = invalidated)."""
+
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("n_old_islands", C.c_uint32),
+        ("island_map", u32p),
+        ("n_old_links", C.c_uint32),
+        ("link_map", u32p),
+    ]
+
+
+def make_nav_remap(remap: dict):
+    """remap: {"island_map": uint32[n_old_islands], "link_map": uint32[n_old_links]} -> (NavRemap, keepalive)."""
+    im, lm = as_u32(remap["island_map"]), as_u32(remap["link_map"])
+    r = NavRemap()
+    r.struct_size = C.sizeof(NavRemap)
+    r.n_old_islands = len(im)
+    r.island_map = im.ctypes.data_as(u32p)
+    r.n_old_links = len(lm)
+    r.link_map = lm.ctypes.data_as(u32p)
+    return r, (im, lm)
+
+
 class PathingResult(C.Structure):
     _fields_ = [
         ("agent", C.c_uint32),

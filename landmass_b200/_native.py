@@ -17,6 +17,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 
 EXPORTED_SYMBOLS = [
     "lmb_abi_version", "lmb_create", "lmb_destroy", "lmb_last_error", "lmb_navdata_upload",
+    "lmb_navdata_update",
     "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
     "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
@@ -53,6 +54,7 @@ def declare_prototypes(lib, prefix: str):
             f.argtypes = argtypes
 
     fn("navdata_upload", i32, [vp, C.POINTER(_abi.NavDataDesc)])
+    fn("navdata_update", i32, [vp, C.POINTER(_abi.NavDataDesc), C.POINTER(_abi.NavRemap)])
     fn("step", i32, [vp, C.POINTER(_abi.AgentsIn), C.POINTER(_abi.CharactersIn),
                      C.POINTER(_abi.Options), f32, C.POINTER(_abi.AgentsOut)])
     fn("agents_upload", i32, [vp, C.POINTER(_abi.AgentsIn), C.POINTER(_abi.CharactersIn)])
@@ -102,9 +104,16 @@ class CBackend:
                 msg = raw.decode() if raw else ""
             raise NativeError(status, msg)
 
-    def navdata_upload(self, flat: dict):
+    def navdata_upload(self, flat: dict, remap: dict | None = None):
+        """remap (see _abi.make_nav_remap) keeps the stored paths the reference's `Path::is_valid`
+        keeps; without it every path is dropped."""
         desc, keep = _abi.make_navdata_desc(flat)
-        self._check(self._f("navdata_upload")(self.ctx, C.byref(desc)))
+        if remap is None:
+            self._check(self._f("navdata_upload")(self.ctx, C.byref(desc)))
+        else:
+            r, keep_r = _abi.make_nav_remap(remap)
+            self._check(self._f("navdata_update")(self.ctx, C.byref(desc), C.byref(r)))
+            del keep_r
         self._n_polys = int(flat["n_polys"])
         del keep
 

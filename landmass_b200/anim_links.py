@@ -319,9 +319,9 @@ def create_animation_off_mesh_links(nav_data, max_vertical_distance):
                 e_edge = np.stack([_vec_lerp(end[0], end[1], lo), _vec_lerp(end[0], end[1], hi)])
                 links.append(OffMeshLink(sk, sp, ek, ep, int(key_to_island[ek].nav_mesh.poly_type[ep]), s_edge,
                                          _abi.LINK_ANIMATION, -1, e_edge, float(link.cost), int(link.kind),
-                                         int(link_key.idx)))
+                                         int(link_key.idx), link_key))
                 if link.bidirectional:
                     links.append(OffMeshLink(ek, ep, sk, sp, int(key_to_island[sk].nav_mesh.poly_type[sp]),
                                              e_edge, _abi.LINK_ANIMATION, -1, s_edge, float(link.cost),
-                                             int(link.kind), int(link_key.idx)))
+                                             int(link.kind), int(link_key.idx), link_key))
     return links

@@ -212,6 +212,7 @@ class Archipelago:
         self.characters = DenseSlotMap()
         self._pathing_results: list[PathingResult] = []
         self._uploaded_generation = -1
+        self._flat = None
         self._device_versions: dict[int, int] = {}
         if backend is None:
             from ._native import NativeBackend  # raises loudly if the CUDA library is missing
@@ -311,9 +312,26 @@ class Archipelago:
         self.nav_data.update(0.01, animation_link_max_vertical_distance(
             self.archipelago_options.point_sample_distance))
         if self._uploaded_generation != self.nav_data.generation:
-            self._flat = self.nav_data.flatten()
-            self.backend.navdata_upload(self._flat)
+            flat = self.nav_data.flatten()
+            self.backend.navdata_upload(flat, self._nav_remap(self._flat, flat))
+            self._flat = flat
             self._uploaded_generation = self.nav_data.generation
+
+    def _nav_remap(self, old, new):
+        """What `NavigationData::update` hands `Archipelago::update` (lib.rs:274-281; nav_data.rs:326-403)
+        — the invalidated islands (deleted or dirty) and the dropped off-mesh links (an end on such an
+        island, or their animation link deleted) — expressed as maps from the previous upload's island /
+        link indices to the new ones, so the backend can keep every path `Path::is_valid` keeps."""
+        changed = self.nav_data.take_changed_islands()
+        if old is None:
+            return None
+        new_index = new["_island_key_to_index"]
+        island_map = np.array([new_index[k] if (k in new_index and k not in changed) else _abi.NONE
+                               for k in old["_island_keys"]], dtype=np.uint32)
+        new_link = {ident: i for i, ident in enumerate(new["_link_identity"])}
+        link_map = np.array([new_link.get(ident, _abi.NONE) if (ident[0] not in changed and ident[2] not in changed)
+                             else _abi.NONE for ident in old["_link_identity"]], dtype=np.uint32)
+        return {"island_map": island_map, "link_map": link_map}
 
     def sample_point(self, point, point_sample_distance=None):
         """query.rs:70-94 through the batched device entry point.

@@ -274,10 +274,14 @@ k_repath_decide(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool,
   bool clear_path = false, follow = false, repath = false;
   uint32_t ai = LMB_NONE, ti = LMB_NONE;
   const uint32_t agent_node = ag.agent_node[i], target_node = ag.target_node[i];
+  // a path invalidated by the last navdata update is the marker entry (k_remap_paths)
+  const bool invalid = plen && pool.entries[pool.slot_path_off[s]].x == LMB_NONE;
   if (flags & LMB_AGENT_PAUSED) {
-    new_state = LMB_STATE_PAUSED;  // paths are only invalidated by a navdata upload, which drops them
+    new_state = LMB_STATE_PAUSED;
+    clear_path = invalid;  // lib.rs:350-358
   } else if (flags & LMB_AGENT_USING_ANIMATION_LINK) {
     new_state = LMB_STATE_USING_ANIMATION_LINK;
+    clear_path = invalid;
   } else if (!(flags & LMB_AGENT_HAS_TARGET)) {  // does_agent_need_repath (agent.rs:425-475)
     if (plen) {  // ClearPathNoTarget; DoNothing leaves the state untouched
       new_state = LMB_STATE_IDLE;
@@ -291,7 +295,7 @@ k_repath_decide(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool,
     clear_path = true;
   } else {
     repath = true;
-    if (plen) {
+    if (plen && !invalid) {  // agent.rs:449-456
       const uint2* e = pool.entries + pool.slot_path_off[s];
       // find_index_of_node: first match from the front (path.rs:403-420)
       for (uint32_t base = 0; base < plen; base += 32) {
@@ -504,6 +508,57 @@ __global__ void k_drop_all_paths(PathPool pool, uint32_t max_agents) {
   if (i == 0) *pool.cursor = 0ull;
 }
 
+// Carries stored paths over a navdata replacement (`Path::is_valid`, path.rs:381-400, against the
+// sets `NavigationData::update` returns).  One warp per slot.  A path none of whose nodes lies on
+// an invalidated island and none of whose off-mesh links was dropped gets its node ids and link
+// indices rewritten to the new flattening; any other path becomes the one-entry marker
+// (LMB_NONE, LMB_NONE), which k_repath_decide treats as "has a path, path invalid".
+__global__ void __launch_bounds__(128)
+k_remap_paths(PathPool pool, uint32_t max_agents, const uint32_t* __restrict__ old_begin, uint32_t n_old_islands,
+              const uint32_t* __restrict__ new_begin_of_old, const uint32_t* __restrict__ link_map,
+              uint32_t n_old_links) {
+  const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (slot >= max_agents) return;
+  const uint32_t len = pool.slot_path_len[slot];
+  if (!len) return;
+  uint2* e = pool.entries + pool.slot_path_off[slot];
+  bool bad = false;
+  for (uint32_t k = lane; k < len; k += 32) {
+    uint2 v = e[k];
+    if (v.x == LMB_NONE) {
+      bad = true;
+      break;
+    }
+    uint32_t lo = 0, hi = n_old_islands;  // last island whose first node id is <= v.x
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (old_begin[mid] <= v.x) lo = mid; else hi = mid;
+    }
+    const uint32_t nb = new_begin_of_old[lo];
+    if (nb == LMB_NONE || v.x >= old_begin[lo + 1]) {
+      bad = true;
+      break;
+    }
+    v.x = nb + (v.x - old_begin[lo]);
+    if (v.y != LMB_NONE && (v.y & LMB_PORTAL_LINK)) {
+      const uint32_t l = v.y & ~LMB_PORTAL_LINK;
+      const uint32_t nl = l < n_old_links ? link_map[l] : LMB_NONE;
+      if (nl == LMB_NONE) {
+        bad = true;
+        break;
+      }
+      v.y = LMB_PORTAL_LINK | nl;
+    }
+    e[k] = v;
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  if (bad && lane == 0) {
+    e[0] = make_uint2(LMB_NONE, LMB_NONE);
+    pool.slot_path_len[slot] = 1;
+  }
+}
+
 // ---- single-block exclusive scan ------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n) {
   __shared__ uint32_t warp_sums[32];
@@ -600,6 +655,13 @@ void launch_gather_outputs(const AgentArrays& ag, const AgentPersist& persist, f
 }
 void launch_drop_all_paths(const PathPool& pool, uint32_t max_agents, cudaStream_t stream) {
   k_drop_all_paths<<<blocks_for(max_agents ? max_agents : 1, 256), 256, 0, stream>>>(pool, max_agents);
+}
+void launch_remap_paths(const PathPool& pool, uint32_t max_agents, const uint32_t* old_begin, uint32_t n_old_islands,
+                        const uint32_t* new_begin_of_old, const uint32_t* link_map, uint32_t n_old_links,
+                        cudaStream_t stream) {
+  if (max_agents && n_old_islands)
+    k_remap_paths<<<blocks_for(max_agents, 4), 128, 0, stream>>>(pool, max_agents, old_begin, n_old_islands,
+                                                                 new_begin_of_old, link_map, n_old_links);
 }
 
 }  // namespace lmb

@@ -235,10 +235,33 @@ static int32_t ensure_arena(lmb_ctx* ctx, uint32_t n_queries) {
   return setup_arena(ctx, ctx->arena_node_cap, ctx->arena_heap_cap, slots);
 }
 
-int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
+int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) { return lmb_navdata_update(ctx, d, nullptr); }
+
+int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_nav_remap* remap) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
   if (!d || d->struct_size != sizeof(lmb_navdata_desc))
     return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_navdata_upload: bad descriptor (struct_size)");
+  if (remap && ctx->has_nav) {
+    if (remap->struct_size != sizeof(lmb_nav_remap) || remap->n_old_islands + 1 != ctx->h_island_poly_begin.size() ||
+        remap->n_old_links != ctx->nav.n_links || (remap->n_old_islands && !remap->island_map) ||
+        (remap->n_old_links && !remap->link_map))
+      return ctx->fail(LMB_ERR_INVALID_ARGUMENT,
+                       "lmb_navdata_update: remap does not describe the previous upload (%u islands, %u links)",
+                       (unsigned)(ctx->h_island_poly_begin.size() - 1), ctx->nav.n_links);
+    for (uint32_t i = 0; i < remap->n_old_islands; i++) {
+      const uint32_t j = remap->island_map[i];
+      if (j == LMB_NONE) continue;
+      if (j >= d->n_islands || d->island_poly_begin[j + 1] - d->island_poly_begin[j] !=
+                                   ctx->h_island_poly_begin[i + 1] - ctx->h_island_poly_begin[i])
+        return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_navdata_update: island_map[%u] = %u is not the same island", i, j);
+    }
+    for (uint32_t l = 0; l < remap->n_old_links; l++)
+      if (remap->link_map[l] != LMB_NONE && remap->link_map[l] >= d->n_links)
+        return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_navdata_update: link_map[%u] out of range", l);
+  }
+  const bool carry_paths = remap && ctx->has_nav;
+  const std::vector<uint32_t> old_island_poly_begin = ctx->h_island_poly_begin;
+  const uint32_t n_old_links = ctx->nav.n_links;
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   cudaStreamSynchronize(s);
@@ -573,7 +596,21 @@ int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) {
     CUDA_TRY(ctx, ctx->d_pool[0].reserve_exact(ctx->pool_capacity));
     ctx->pool_cur = 0;
   }
-  launch_drop_all_paths(make_pool(ctx), ctx->cfg.max_agents, s);
+  ctx->h_island_poly_begin.assign(d->island_poly_begin, d->island_poly_begin + d->n_islands + 1);
+  DevBuf<uint32_t> d_old_begin, d_new_begin, d_link_map;
+  if (carry_paths) {
+    // Path::is_valid against (invalidated_off_mesh_links, invalidated_islands), then re-index
+    std::vector<uint32_t> new_begin(remap->n_old_islands);
+    for (uint32_t i = 0; i < remap->n_old_islands; i++)
+      new_begin[i] = remap->island_map[i] == LMB_NONE ? LMB_NONE : d->island_poly_begin[remap->island_map[i]];
+    CUDA_TRY(ctx, d_old_begin.upload(old_island_poly_begin.data(), old_island_poly_begin.size(), s));
+    CUDA_TRY(ctx, d_new_begin.upload(new_begin.data(), new_begin.size(), s));
+    CUDA_TRY(ctx, d_link_map.upload(remap->link_map, n_old_links, s));
+    launch_remap_paths(make_pool(ctx), ctx->cfg.max_agents, d_old_begin.p, remap->n_old_islands, d_new_begin.p,
+                       d_link_map.p, n_old_links, s);
+  } else {
+    launch_drop_all_paths(make_pool(ctx), ctx->cfg.max_agents, s);
+  }
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_slot_cost_hint.p, 0, ctx->cfg.max_agents * sizeof(uint32_t), s));
   ctx->explored_estimate = 0.0;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -1332,6 +1369,10 @@ int32_t lmb_agent_path(lmb_ctx* ctx, uint32_t slot, uint32_t* out_nodes, uint32_
   if (len > capacity) return LMB_ERR_CAPACITY;
   std::vector<uint2> tmp(len);
   CUDA_TRY(ctx, cudaMemcpy(tmp.data(), ctx->d_pool[ctx->pool_cur].p + off, len * sizeof(uint2), cudaMemcpyDeviceToHost));
+  if (tmp[0].x == LMB_NONE) {  // invalidated by the last lmb_navdata_update, not yet seen by a step
+    *out_len = 0;
+    return LMB_OK;
+  }
   for (uint32_t k = 0; k < len; k++) {
     out_nodes[k] = tmp[k].x;
     out_portals[k] = tmp[k].y;

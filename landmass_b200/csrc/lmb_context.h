@@ -61,6 +61,7 @@ struct lmb_ctx {
   cudaStream_t stream = nullptr;
   std::string error;
   bool has_nav = false;
+  std::vector<uint32_t> h_island_poly_begin;  // of the current navdata: node id -> island for lmb_navdata_update
   uint32_t sm_count = 148;
 
   // --- navdata ---

@@ -156,6 +156,9 @@ void launch_straight_paths(const DevNav& nav, const PathPool& pool, const AStarQ
                            const uint32_t* step_begin, uint32_t* step_count, uint32_t* out_kind,
                            float* out_points, uint32_t* out_link, cudaStream_t stream);
 void launch_drop_all_paths(const PathPool& pool, uint32_t max_agents, cudaStream_t stream);
+void launch_remap_paths(const PathPool& pool, uint32_t max_agents, const uint32_t* old_begin, uint32_t n_old_islands,
+                        const uint32_t* new_begin_of_old, const uint32_t* link_map, uint32_t n_old_links,
+                        cudaStream_t stream);
 
 // path pool compaction
 void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, cudaStream_t stream);

@@ -98,6 +98,14 @@ class OffMeshLink:
     cost: float = 0.0
     anim_kind: int = 0
     anim_id: int = 0
+    anim_key: Key | None = None   # slot-map key of the AnimationLink (anim_id is its index)
+
+    def identity(self):
+        """What makes this the same link after a rebuild (the reference keeps the OffMeshLinkId of a
+        link whose islands and animation link did not change: nav_data.rs:352-403)."""
+        return (self.src_island, int(self.src_polygon), self.dst_island, int(self.dst_polygon), int(self.kind),
+                self.anim_key, np.asarray(self.portal, dtype=np.float32).tobytes(),
+                None if self.dst_portal is None else np.asarray(self.dst_portal, dtype=np.float32).tobytes())
 
 
 @dataclass
@@ -120,6 +128,9 @@ class NavigationData:
         self.links: list[OffMeshLink] = []
         self.modified_nodes: list[ModifiedNode] = []
         self.generation = 0  # bumped whenever the flattened data must be re-uploaded
+        # `changed_islands` of nav_data.rs:326-344 (deleted + dirty), accumulated until a consumer
+        # (Archipelago._sync_navdata) takes them to decide which stored paths survive
+        self._changed_islands: set = set()
 
     # --- mutation (all mark dirty) ---
     def add_island(self, island: Island) -> Key:
@@ -130,6 +141,7 @@ class NavigationData:
         self.dirty = True
         if self.islands.remove(island_id) is None:
             raise KeyError("Island should be present in the Archipelago")
+        self._changed_islands.add(island_id)
 
     def get_island(self, island_id: Key):
         return self.islands.get(island_id)
@@ -166,12 +178,19 @@ class NavigationData:
         if not self.dirty and not any(i.dirty for i in self.islands.values()):
             return False
         self.dirty = False
-        for island in self.islands.values():
+        for key, island in self.islands.items():
+            if island.dirty:
+                self._changed_islands.add(key)
             island.dirty = False
         self.links, self.modified_nodes, self._regions = link_islands(self, edge_link_distance,
                                                                       animation_link_distance)
         self.generation += 1
         return True
+
+    def take_changed_islands(self) -> set:
+        """Keys of the islands deleted or dirty since the last call (`invalidated_islands`, lib.rs:274)."""
+        out, self._changed_islands = self._changed_islands, set()
+        return out
 
     # --- flattening ---
     def flatten(self) -> dict:
@@ -337,4 +356,6 @@ class NavigationData:
             f["possible_link_kind"] = np.zeros(0, dtype=np.uint32)
         f["node_region_number"] = nrn
         f["_island_key_to_index"] = key_to_index
+        f["_island_keys"] = [key for key, _ in islands]
+        f["_link_identity"] = [l.identity() for l in links]
         return f

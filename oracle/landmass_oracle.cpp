@@ -882,14 +882,19 @@ void Ctx::step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, co
     ch[i].valid = nav.sample_point(ch[i].position, opt, ch[i].point, node);
   }
 
-  // PHASE B: repath decision + A* (lib.rs:343-424).  Paths are all valid here:
-  // invalidation is handled by navdata upload dropping paths.
+  // PHASE B: repath decision + A* (lib.rs:343-424).  `path_invalid` is this frame's
+  // `!path.is_valid(..)`, computed by orc_navdata_update.
   std::vector<std::pair<PathIndex, PathIndex>> follow(n);
   std::vector<bool> has_follow(n, false);
   for (uint32_t i = 0; i < n; i++) {
     AgentPersist& s = st(i);
     s.reached_link_id = LMB_NONE;  // current_animation_link = None (lib.rs:348)
-    if (ag[i].flags & (LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK)) continue;
+    const bool path_invalid = s.path_invalid;
+    s.path_invalid = false;
+    if (ag[i].flags & (LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK)) {
+      if (s.path && path_invalid) s.path.reset();  // lib.rs:350-358
+      continue;
+    }
     // does_agent_need_repath (agent.rs:425-475)
     if (!(ag[i].flags & LMB_AGENT_HAS_TARGET)) {
       if (s.path) {
@@ -909,7 +914,7 @@ void Ctx::step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, co
       continue;
     }
     bool repath = true;
-    if (s.path) {
+    if (s.path && !path_invalid) {  // agent.rs:449-456
       auto ai = s.path->find_index_of_node(nav, agent_node[i].node);
       if (ai) {
         auto ti = s.path->find_index_of_node_rev(nav, target_node[i].node);
@@ -1037,13 +1042,61 @@ orc_ctx* orc_create(const lmb_navdata_desc* desc, uint32_t flags) {
   orc_ctx* h = new orc_ctx();
   h->c.flags = flags;
   h->c.nav.load(*desc);
+  h->c.has_nav = true;
   return h;
 }
 void orc_destroy(orc_ctx* h) { delete h; }
-int32_t orc_navdata_upload(orc_ctx* h, const lmb_navdata_desc* desc) {
+int32_t orc_navdata_upload(orc_ctx* h, const lmb_navdata_desc* desc) { return orc_navdata_update(h, desc, nullptr); }
+
+// Path::is_valid (path.rs:381-400): no island segment on an invalidated island, no off-mesh link
+// segment over an invalidated link.
+bool Path::is_valid(const uint32_t* island_map, const uint32_t* link_map) const {
+  for (const IslandSegment& seg : island_segments)
+    if (island_map[seg.island] == LMB_NONE) return false;
+  for (const OffMeshLinkSegment& seg : off_mesh_link_segments)
+    if (link_map[seg.link] == LMB_NONE) return false;
+  return true;
+}
+
+int32_t orc_navdata_update(orc_ctx* h, const lmb_navdata_desc* desc, const lmb_nav_remap* remap) {
   if (!h || !desc || desc->struct_size != sizeof(lmb_navdata_desc)) return LMB_ERR_INVALID_ARGUMENT;
-  h->c.nav.load(*desc);
-  for (auto& kv : h->c.agent_state) kv.second.path.reset();
+  NavData& nav = h->c.nav;
+  if (!remap || !h->c.has_nav) {
+    nav.load(*desc);
+    h->c.has_nav = true;
+    for (auto& kv : h->c.agent_state) kv.second.path.reset();
+    return LMB_OK;
+  }
+  if (remap->struct_size != sizeof(lmb_nav_remap) || remap->n_old_islands != nav.islands.size() ||
+      remap->n_old_links != nav.link_dst_node.size())
+    return LMB_ERR_INVALID_ARGUMENT;
+  // `invalidated_islands` / `invalidated_off_mesh_links` (nav_data.rs:326-350) are the entries
+  // mapped to LMB_NONE.  Valid paths are re-expressed in the new flattening's ids.
+  std::vector<uint32_t> old_begin(nav.islands.size());
+  for (size_t i = 0; i < nav.islands.size(); i++) old_begin[i] = nav.islands[i].poly_begin;
+  for (auto& kv : h->c.agent_state) {
+    AgentPersist& s = kv.second;
+    if (!s.path) continue;
+    if (s.path_invalid || !s.path->is_valid(remap->island_map, remap->link_map)) {
+      s.path_invalid = true;
+      continue;
+    }
+    for (IslandSegment& seg : s.path->island_segments) {
+      const uint32_t ni = remap->island_map[seg.island];
+      for (uint32_t& node : seg.corridor) node = desc->island_poly_begin[ni] + (node - old_begin[seg.island]);
+      seg.island = ni;
+    }
+    for (OffMeshLinkSegment& seg : s.path->off_mesh_link_segments) {
+      auto renode = [&](uint32_t node) {
+        const uint32_t oi = nav.poly_island[node];
+        return desc->island_poly_begin[remap->island_map[oi]] + (node - old_begin[oi]);
+      };
+      seg.starting_node = renode(seg.starting_node);
+      seg.end_node = renode(seg.end_node);
+      seg.link = remap->link_map[seg.link];
+    }
+  }
+  nav.load(*desc);
   return LMB_OK;
 }
 
@@ -1198,7 +1251,7 @@ int32_t orc_agent_path(orc_ctx* h, uint32_t slot, uint32_t* out_nodes, uint32_t*
                        uint32_t capacity, uint32_t* out_len) {
   *out_len = 0;
   auto it = h->c.agent_state.find(slot);
-  if (it == h->c.agent_state.end() || !it->second.path) return LMB_OK;
+  if (it == h->c.agent_state.end() || !it->second.path || it->second.path_invalid) return LMB_OK;
   std::vector<uint32_t> nodes, portals;
   it->second.path->flatten(nodes, portals);
   *out_len = (uint32_t)nodes.size();

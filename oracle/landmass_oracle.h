@@ -15,6 +15,7 @@ orc_ctx* orc_create(const lmb_navdata_desc* desc, uint32_t flags /* LMB_CONFIG_*
 void orc_destroy(orc_ctx*);
 /* replaces nav data, drops all paths (same contract as lmb_navdata_upload) */
 int32_t orc_navdata_upload(orc_ctx*, const lmb_navdata_desc* desc);
+int32_t orc_navdata_update(orc_ctx*, const lmb_navdata_desc* desc, const lmb_nav_remap* remap);
 
 int32_t orc_sample_points(orc_ctx*, uint32_t n, const float* points, const lmb_options* options,
                           float* out_points, uint32_t* out_nodes);

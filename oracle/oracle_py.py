@@ -70,14 +70,18 @@ class OracleBackend(CBackend):
         self.flags = flags
         self.ctx = None
 
-    def navdata_upload(self, flat: dict):
+    def navdata_upload(self, flat: dict, remap: dict | None = None):
         desc, keep = _abi.make_navdata_desc(flat)
         if self.ctx is None:
             self.ctx = C.c_void_p(self.lib.orc_create(C.byref(desc), self.flags))
             if not self.ctx:
                 raise RuntimeError("orc_create failed")
-        else:
+        elif remap is None:
             self._check(self.lib.orc_navdata_upload(self.ctx, C.byref(desc)))
+        else:
+            r, keep_r = _abi.make_nav_remap(remap)
+            self._check(self.lib.orc_navdata_update(self.ctx, C.byref(desc), C.byref(r)))
+            del keep_r
         del keep
 
     # ---- multi-rank form (same contract as NativeBackend.step_begin / halo_buffer / step_end) ----

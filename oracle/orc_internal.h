@@ -123,6 +123,8 @@ struct Path {
   std::vector<OffMeshLinkSegment> off_mesh_link_segments;
   V3 start_point, end_point;
   PathIndex last_index() const;
+  // path.rs:381-400 against the sets of an lmb_nav_remap (indices of the flattening the path is in)
+  bool is_valid(const uint32_t* island_map, const uint32_t* link_map) const;
   std::optional<PathIndex> find_index_of_node(const NavData& nav, uint32_t node) const;
   std::optional<PathIndex> find_index_of_node_rev(const NavData& nav, uint32_t node) const;
   std::pair<PathIndex, StraightPathStep> find_next_point_in_straight_path(
@@ -164,6 +166,9 @@ struct Sampled {
 };
 struct AgentPersist {  // private Agent fields (agent.rs:93-104)
   std::optional<Path> path;
+  // `!path.is_valid(invalidated_off_mesh_links, invalidated_islands)` of the navdata update that
+  // precedes the next step (the sets only exist for that one frame: lib.rs:274-281)
+  bool path_invalid = false;
   V3 desired_move{0, 0, 0};
   uint32_t state = LMB_STATE_IDLE;
   uint32_t reached_link_id = LMB_NONE;
@@ -195,6 +200,7 @@ void apply_avoidance_to_agents(const NavData& nav, const std::vector<AvoidRec>& 
 struct Ctx {
   uint32_t flags = 0;
   NavData nav;
+  bool has_nav = false;
   std::unordered_map<uint32_t, AgentPersist> agent_state;
   std::vector<lmb_pathing_result> pathing_results;
   // frame state kept between step_begin and step_end (multi-rank form)
