@@ -206,3 +206,48 @@ def test_agent_host_api():
     assert agent.is_using_animation_link()
     agent.end_animation_link()
     assert not agent.is_using_animation_link()
+
+
+@pytest.mark.parametrize("condition", [TargetReachedCondition.Distance(2.0),
+                                       TargetReachedCondition.StraightPathDistance(2.0),
+                                       TargetReachedCondition.VisibleAtDistance(2.0)])
+@pytest.mark.parametrize("target,reached", [((2.5, 1.0), True), ((3.5, 1.0), False), ((2.0, 2.0), True),
+                                            ((2.5, 2.5), False)])
+def test_has_reached_target_at_end_node(make_backend, condition, target, reached):
+    """agent_test.rs:70-154: agent and target in the same node, so the next waypoint IS the target and
+    all three conditions reduce to the distance (1.5, 2.5, sqrt 2, 2.12 against 2.0).  The reference
+    test moves the waypoint in x/z over an empty mesh; here the same offsets lie in the plane of one
+    5x5 polygon on the reference test's transformed island."""
+    tr, rot = (2.0, 3.0, 4.0), math.pi * 0.85
+
+    def world(p):
+        c, s = math.cos(rot), math.sin(rot)
+        return (c * p[0] - s * p[1] + tr[0], s * p[0] + c * p[1] + tr[1], tr[2])
+
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5), backend=make_backend())
+    arch.add_island(Island(Transform(tr, rot), valid_mesh(dict(
+        vertices=[(0.0, 0.0, 0.0), (5.0, 0.0, 0.0), (5.0, 5.0, 0.0), (0.0, 5.0, 0.0)], polygons=[[0, 1, 2, 3]],
+        polygon_type_indices=[0]))))
+    agent = arch.add_agent(Agent.create(world((1.0, 1.0)), (0, 0, 0), 0.0, 0.0, 0.0))
+    arch.get_agent_mut(agent).current_target = world(target)
+    arch.get_agent_mut(agent).target_reached_condition = condition
+    arch.update(0.01)
+    assert arch.get_agent(agent).state() == (AgentState.ReachedTarget if reached else AgentState.Moving)
+
+
+def test_uses_sampled_point_for_reaching_target(make_backend):
+    """agent_test.rs:546-591: the distance is taken from the agent's SAMPLED point.  An agent hovering
+    0.45 above the mesh is 0.54 from a target 0.3 away on the ground, but its sampled point is 0.3
+    from it: reached at Distance(0.5).  From 0.6 away horizontally it is not."""
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5), backend=make_backend())
+    arch.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), valid_mesh(dict(
+        vertices=[(0.0, 0.0, 0.0), (5.0, 0.0, 0.0), (5.0, 5.0, 0.0), (0.0, 5.0, 0.0)], polygons=[[0, 1, 2, 3]],
+        polygon_type_indices=[0]))))
+    near = arch.add_agent(Agent.create((1.0, 1.0, 0.45), (0, 0, 0), 0.0, 0.0, 0.0))
+    far = arch.add_agent(Agent.create((1.0, 1.0, 0.45), (0, 0, 0), 0.0, 0.0, 0.0))
+    for key, tx in ((near, 1.3), (far, 1.6)):
+        arch.get_agent_mut(key).current_target = (tx, 1.0, 0.0)
+        arch.get_agent_mut(key).target_reached_condition = TargetReachedCondition.Distance(0.5)
+    arch.update(0.01)
+    assert arch.get_agent(near).state() == AgentState.ReachedTarget
+    assert arch.get_agent(far).state() == AgentState.Moving
