@@ -332,8 +332,10 @@ int32_t lmb_sample_points(lmb_ctx* ctx, uint32_t n, const float* points, const l
                           float* out_points, uint32_t* out_nodes);
 
 /* Batched `pathfinding::find_path` (pathfinding.rs:277-382).  Query i goes from
- * (start_node[i], start_point[i]) to (end_node[i], end_point[i]).  Overrides /
- * permitted kinds are CSR per query (NULL = none / all permitted).
+ * (start_node[i], start_point[i]) to (end_node[i], end_point[i]).  Overrides are CSR per query
+ * (NULL = none).  permitted_animation_links per query: permit_all[i] != 0 is
+ * PermittedAnimationLinks::All, otherwise Kinds = row i of the permitted CSR; permit_all == NULL
+ * means All for every query (the CSR is then ignored and may be NULL).
  * Output corridor i = out_nodes/out_portals[out_path_begin[i] .. out_path_begin[i+1]);
  * out_success[i] = 0 leaves an empty corridor.  path_capacity is the size of
  * out_nodes/out_portals; LMB_ERR_CAPACITY if the paths do not fit. */
@@ -342,7 +344,8 @@ int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, con
                        const uint32_t* override_begin, const uint32_t* override_type,
                        const float* override_cost, uint32_t* out_success, uint32_t* out_explored,
                        uint32_t* out_path_begin, uint32_t* out_nodes, uint32_t* out_portals,
-                       uint32_t path_capacity);
+                       uint32_t path_capacity, const uint32_t* permit_all, const uint32_t* permitted_begin,
+                       const uint32_t* permitted_kind);
 
 /* Batched `Archipelago::find_path` of the query API (query.rs:185-273): A* followed by the
  * full straight path (repeated funnel).  Steps of query i are
@@ -355,7 +358,9 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
                                 const float* end_point, const uint32_t* override_begin,
                                 const uint32_t* override_type, const float* override_cost,
                                 uint32_t* out_success, uint32_t* out_step_begin, uint32_t* out_kind,
-                                float* out_points, uint32_t* out_link, uint32_t step_capacity);
+                                float* out_points, uint32_t* out_link, uint32_t step_capacity,
+                                const uint32_t* permit_all, const uint32_t* permitted_begin,
+                                const uint32_t* permitted_kind);
 
 int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out);
 

@@ -5,9 +5,9 @@ Host-side mirror of the reference's public API for ONE hot path,
 in include/landmass_b200.h.  The compute lives in landmass_b200/csrc (CUDA,
 sm_100a); importing this package never imports anything from oracle/.
 """
-from .archipelago import (Agent, AgentState, Archipelago, ArchipelagoOptions, Character,
-                          PathingResult, PermittedAnimationLinks, ReachedAnimationLink,
-                          TargetReachedCondition)
+from .archipelago import (Agent, AgentState, Archipelago, ArchipelagoOptions, Character, FindPathError,
+                          PathingResult, PathStep, PermittedAnimationLinks, ReachedAnimationLink,
+                          SampledPoint, SamplePointError, TargetReachedCondition)
 from .anim_links import AnimationLink
 from .coords import XY, XYZ, CorePointSampleDistance, PointSampleDistance3d
 from .nav_data import Island, NavigationData, SetTypeIndexCostError, Transform
@@ -15,8 +15,9 @@ from .nav_mesh import (HeightNavigationMesh, HeightPolygon, NavigationMesh, Vali
                        ValidNavigationMesh)
 
 __all__ = [
-    "Agent", "AgentState", "AnimationLink", "Archipelago", "ArchipelagoOptions", "Character", "PathingResult",
-    "PermittedAnimationLinks", "ReachedAnimationLink", "TargetReachedCondition", "XY", "XYZ",
+    "Agent", "AgentState", "AnimationLink", "Archipelago", "ArchipelagoOptions", "Character", "FindPathError",
+    "PathingResult", "PathStep", "PermittedAnimationLinks", "ReachedAnimationLink", "SampledPoint",
+    "SamplePointError", "TargetReachedCondition", "XY", "XYZ",
     "CorePointSampleDistance", "PointSampleDistance3d", "Island", "NavigationData",
     "SetTypeIndexCostError", "Transform", "HeightNavigationMesh", "HeightPolygon",
     "NavigationMesh", "ValidationError", "ValidNavigationMesh",

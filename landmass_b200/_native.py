@@ -65,10 +65,10 @@ def declare_prototypes(lib, prefix: str):
     fn("sample_points", i32, [vp, u32, _abi.f32p, C.POINTER(_abi.Options), _abi.f32p, _abi.u32p])
     fn("find_paths", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, _abi.f32p, _abi.u32p,
                            _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.u32p,
-                           _abi.u32p, u32])
+                           _abi.u32p, u32, _abi.u32p, _abi.u32p, _abi.u32p])
     fn("find_straight_paths", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, _abi.f32p, _abi.u32p,
                                     _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.f32p,
-                                    _abi.u32p, u32])
+                                    _abi.u32p, u32, _abi.u32p, _abi.u32p, _abi.u32p])
     fn("get_step_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
     fn("step_begin", i32, [vp, C.POINTER(_abi.Options), f32, u32, u32])
     fn("halo_buffer", i32, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
@@ -176,24 +176,16 @@ class CBackend:
         return out_p[:n], out_n[:n]
 
     def find_paths(self, start_node, start_point, end_node, end_point, overrides=None,
-                   path_capacity: int | None = None):
-        """overrides: list (per query) of dict{type: cost} or None."""
+                   path_capacity: int | None = None, permitted=None):
+        """overrides: list (per query) of dict{type: cost} or None.
+        permitted: list (per query) of None (= All) or an iterable of permitted link kinds; None = All."""
         sn = _abi.as_u32(start_node)
         en = _abi.as_u32(end_node)
         sp = _abi.as_f32(start_point).reshape(-1, 3)
         ep = _abi.as_f32(end_point).reshape(-1, 3)
         n = len(sn)
-        ob = ot = oc = None
-        if overrides is not None:
-            ob = np.zeros(n + 1, dtype=np.uint32)
-            tl, cl = [], []
-            for i, ov in enumerate(overrides):
-                for t, c in sorted((ov or {}).items()):
-                    tl.append(t)
-                    cl.append(c)
-                ob[i + 1] = len(tl)
-            ot = np.array(tl + [0], dtype=np.uint32)
-            oc = np.array(cl + [0], dtype=np.float32)
+        ob, ot, oc = self._overrides_csr(overrides, n)
+        pa, pb, pk = self._permitted_csr(permitted, n)
         cap = path_capacity or max(1024, 64 * n)
         while True:
             succ = np.zeros(max(n, 1), dtype=np.uint32)
@@ -205,7 +197,8 @@ class CBackend:
                 self.ctx, n, _abi.ptr(sn, _abi.u32p), _abi.ptr(sp, _abi.f32p), _abi.ptr(en, _abi.u32p),
                 _abi.ptr(ep, _abi.f32p), _abi.ptr(ob, _abi.u32p), _abi.ptr(ot, _abi.u32p),
                 _abi.ptr(oc, _abi.f32p), _abi.ptr(succ, _abi.u32p), _abi.ptr(expl, _abi.u32p),
-                _abi.ptr(begin, _abi.u32p), _abi.ptr(nodes, _abi.u32p), _abi.ptr(portals, _abi.u32p), cap)
+                _abi.ptr(begin, _abi.u32p), _abi.ptr(nodes, _abi.u32p), _abi.ptr(portals, _abi.u32p), cap,
+                _abi.ptr(pa, _abi.u32p), _abi.ptr(pb, _abi.u32p), _abi.ptr(pk, _abi.u32p))
             if st == _abi.ERR_CAPACITY:
                 cap = max(int(begin[n]), cap * 2)
                 continue
@@ -225,7 +218,18 @@ class CBackend:
             ob[i + 1] = len(tl)
         return ob, np.array(tl + [0], dtype=np.uint32), np.array(cl + [0], dtype=np.float32)
 
-    def find_straight_paths(self, start_node, start_point, end_node, end_point, overrides=None):
+    def _permitted_csr(self, permitted, n):
+        if permitted is None:
+            return None, None, None
+        pa = np.array([1 if p is None else 0 for p in permitted], dtype=np.uint32)
+        pb = np.zeros(n + 1, dtype=np.uint32)
+        kinds = []
+        for i, p in enumerate(permitted):
+            kinds.extend(sorted(p or ()))
+            pb[i + 1] = len(kinds)
+        return pa, pb, np.array(kinds + [0], dtype=np.uint32)
+
+    def find_straight_paths(self, start_node, start_point, end_node, end_point, overrides=None, permitted=None):
         """Batched query-API find_path: returns (success, step_begin, kind, points (k,6), link)."""
         sn = _abi.as_u32(start_node)
         en = _abi.as_u32(end_node)
@@ -233,6 +237,7 @@ class CBackend:
         ep = _abi.as_f32(end_point).reshape(-1, 3)
         n = len(sn)
         ob, ot, oc = self._overrides_csr(overrides, n)
+        pa, pb, pk = self._permitted_csr(permitted, n)
         cap = max(1024, 64 * n)
         while True:
             succ = np.zeros(max(n, 1), dtype=np.uint32)
@@ -244,7 +249,8 @@ class CBackend:
                 self.ctx, n, _abi.ptr(sn, _abi.u32p), _abi.ptr(sp, _abi.f32p), _abi.ptr(en, _abi.u32p),
                 _abi.ptr(ep, _abi.f32p), _abi.ptr(ob, _abi.u32p), _abi.ptr(ot, _abi.u32p),
                 _abi.ptr(oc, _abi.f32p), _abi.ptr(succ, _abi.u32p), _abi.ptr(begin, _abi.u32p),
-                _abi.ptr(kind, _abi.u32p), _abi.ptr(pts, _abi.f32p), _abi.ptr(link, _abi.u32p), cap)
+                _abi.ptr(kind, _abi.u32p), _abi.ptr(pts, _abi.f32p), _abi.ptr(link, _abi.u32p), cap,
+                _abi.ptr(pa, _abi.u32p), _abi.ptr(pb, _abi.u32p), _abi.ptr(pk, _abi.u32p))
             if st == _abi.ERR_CAPACITY:
                 cap = max(int(begin[n]), cap * 2)
                 continue

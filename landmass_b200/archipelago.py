@@ -191,6 +191,79 @@ class ArchipelagoOptions:
         return o
 
 
+class SamplePointError(Exception):
+    """query.rs:57-66: kind is "OutOfRange" or "NavDataDirty"."""
+
+    def __init__(self, kind: str):
+        super().__init__(kind)
+        self.kind = kind
+
+    def __eq__(self, other):
+        return isinstance(other, SamplePointError) and other.kind == self.kind
+
+    __hash__ = Exception.__hash__
+
+
+class FindPathError(Exception):
+    """query.rs:96-103: ("NonPositiveTypeIndexCost", type_index, cost) or ("NoPathFound",)."""
+
+    def __init__(self, kind: str, *args):
+        super().__init__(kind, *args)
+        self.kind = kind
+        self.args_ = args
+
+    def __eq__(self, other):
+        return isinstance(other, FindPathError) and (other.kind, other.args_) == (self.kind, self.args_)
+
+    __hash__ = Exception.__hash__
+
+
+class SampledPoint:
+    """query.rs:15-55: a point on the navigation meshes."""
+
+    def __init__(self, point, node_ref, type_index, landmass_point):
+        self._point = point
+        self._node_ref = node_ref          # (island key, polygon index)
+        self._type_index = type_index
+        self._landmass_point = landmass_point
+
+    def point(self):
+        return self._point.copy()
+
+    def island(self) -> Key:
+        return self._node_ref[0]
+
+    def type_index(self) -> int:
+        return self._type_index
+
+
+class PathStep:
+    """query.rs:105-123: `Waypoint(point)` or `AnimationLink{start_point, end_point, link_id}`."""
+
+    def __init__(self, kind, point=None, start_point=None, end_point=None, link_id=None):
+        self.kind, self.point, self.start_point, self.end_point, self.link_id = kind, point, start_point, end_point, link_id
+
+    @classmethod
+    def Waypoint(cls, point):
+        return cls("Waypoint", point=np.asarray(point, dtype=np.float32))
+
+    @classmethod
+    def AnimationLink(cls, start_point, end_point, link_id):
+        return cls("AnimationLink", start_point=np.asarray(start_point, dtype=np.float32),
+                   end_point=np.asarray(end_point, dtype=np.float32), link_id=link_id)
+
+    def _key(self):
+        t = lambda v: None if v is None else tuple(float(x) for x in v)
+        return self.kind, t(self.point), t(self.start_point), t(self.end_point), self.link_id
+
+    def __eq__(self, other):
+        return isinstance(other, PathStep) and self._key() == other._key()
+
+    def __repr__(self):
+        k = self._key()
+        return f"Waypoint({k[1]})" if self.kind == "Waypoint" else f"AnimationLink({k[2]} -> {k[3]}, {k[4]})"
+
+
 @dataclass
 class PathingResult:
     """lib.rs:538-547."""
@@ -333,9 +406,12 @@ class Archipelago:
                              else _abi.NONE for ident in old["_link_identity"]], dtype=np.uint32)
         return {"island_map": island_map, "link_map": link_map}
 
-    def sample_point(self, point, point_sample_distance=None):
-        """query.rs:70-94 through the batched device entry point.
-        Returns (point, (island key, polygon)) or None."""
+    def sample_point(self, point, point_sample_distance=None) -> "SampledPoint":
+        """`Archipelago::sample_point` (lib.rs:235-246, query.rs:70-94) through the batched device entry
+        point.  Raises SamplePointError("NavDataDirty") when the navigation data was mutated since the last
+        `update`, SamplePointError("OutOfRange") when no node is within the sample distance."""
+        if self.nav_data.dirty or any(i.dirty for i in self.nav_data.islands.values()):
+            raise SamplePointError("NavDataDirty")
         self._sync_navdata()
         opts = self.archipelago_options.to_abi()
         if point_sample_distance is not None:
@@ -347,8 +423,39 @@ class Archipelago:
         pts, nodes = self.backend.sample_points(
             self.cs.to_landmass(point).reshape(1, 3), opts)
         if nodes[0] == _abi.NONE:
-            return None
-        return self.cs.from_landmass(pts[0]), self.node_ref(int(nodes[0]))
+            raise SamplePointError("OutOfRange")
+        island, polygon = self.node_ref(int(nodes[0]))
+        return SampledPoint(self.cs.from_landmass(pts[0]), (island, polygon),
+                            int(self.nav_data.get_island(island).nav_mesh.poly_type[polygon]), pts[0].copy())
+
+    def find_path(self, start_point: "SampledPoint", end_point: "SampledPoint", override_type_index_costs=None,
+                  permitted_animation_links: PermittedAnimationLinks | None = None):
+        """`Archipelago::find_path` (lib.rs:248-268, query.rs:185-273): the straight path between two
+        sampled points as a list of `PathStep`.  Raises FindPathError("NonPositiveTypeIndexCost", type, cost)
+        or FindPathError("NoPathFound")."""
+        assert not (self.nav_data.dirty or any(i.dirty for i in self.nav_data.islands.values())), \
+            "The navigation data has been mutated, but we have SampledPoints, so this should be impossible."
+        overrides = dict(override_type_index_costs or {})
+        for type_index, cost in overrides.items():
+            if cost <= 0.0:
+                raise FindPathError("NonPositiveTypeIndexCost", type_index, cost)
+        self._sync_navdata()
+        kinds = None if permitted_animation_links is None else permitted_animation_links.kinds
+        succ, begin, kind, pts, link = self.backend.find_straight_paths(
+            [self.node_id(*start_point._node_ref)], [start_point._landmass_point],
+            [self.node_id(*end_point._node_ref)], [end_point._landmass_point], [overrides], [kinds])
+        if not succ[0]:
+            raise FindPathError("NoPathFound")
+        link_keys = {k.idx: k for k in self.nav_data.get_animation_link_ids()}
+        steps = []
+        for k in range(int(begin[0]), int(begin[1])):
+            a, b = self.cs.from_landmass(pts[k, :3]), self.cs.from_landmass(pts[k, 3:])
+            steps.append(PathStep.Waypoint(a) if kind[k] == 0 else PathStep.AnimationLink(a, b, link_keys[int(link[k])]))
+        # the sampled points are returned as given (query.rs:224, 227), not after a to/from_landmass round trip
+        steps[0] = PathStep.Waypoint(start_point.point())
+        if steps[-1].kind == "Waypoint":
+            steps[-1] = PathStep.Waypoint(end_point.point())
+        return steps
 
     # --- the hot path ---
     def update(self, delta_time: float):

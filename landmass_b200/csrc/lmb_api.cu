@@ -853,12 +853,48 @@ static AStarQueries make_queries(lmb_ctx* ctx, uint32_t n) {
   return q;
 }
 
+// override_type_index_costs / permitted_animation_links of the batched queries (query.rs:185-191).
+// They go to buffers of their own: the agents' copies (lmb_agents_upload) must survive a query
+// made between two resident steps.  permit_all[i] plays the part of the agent flag
+// LMB_AGENT_PERMIT_ALL_LINKS (AStarQueries::owner_flags).
+static int32_t upload_query_filters(lmb_ctx* ctx, AStarQueries& q, uint32_t n, const uint32_t* override_begin,
+                                    const uint32_t* override_type, const float* override_cost,
+                                    const uint32_t* permit_all, const uint32_t* permitted_begin,
+                                    const uint32_t* permitted_kind) {
+  cudaStream_t s = ctx->stream;
+  if (override_begin) {
+    if (override_begin[n] && (!override_type || !override_cost))
+      return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "override arrays are null but the CSR is not empty");
+    CUDA_TRY(ctx, ctx->d_qf_override_begin.upload(override_begin, (size_t)n + 1, s));
+    CUDA_TRY(ctx, ctx->d_qf_override_type.upload(override_type, override_begin[n], s));
+    CUDA_TRY(ctx, ctx->d_qf_override_cost.upload(override_cost, override_begin[n], s));
+    q.override_begin = ctx->d_qf_override_begin.p;
+    q.override_type = ctx->d_qf_override_type.p;
+    q.override_cost = ctx->d_qf_override_cost.p;
+  }
+  if (!permit_all) return LMB_OK;  // PermittedAnimationLinks::All for every query
+  std::vector<uint32_t> flags(n), begin(n + 1, 0);
+  for (uint32_t i = 0; i < n; i++) flags[i] = permit_all[i] ? LMB_AGENT_PERMIT_ALL_LINKS : 0u;
+  if (permitted_begin) begin.assign(permitted_begin, permitted_begin + n + 1);
+  if (begin[n] && !permitted_kind)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "permitted_kind is null but the CSR is not empty");
+  CUDA_TRY(ctx, ctx->d_qf_flags.upload(flags.data(), n, s));
+  CUDA_TRY(ctx, ctx->d_qf_permitted_begin.upload(begin.data(), (size_t)n + 1, s));
+  CUDA_TRY(ctx, ctx->d_qf_permitted_kind.upload(permitted_kind, begin[n], s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));  // flags / begin are locals
+  q.owner_flags = ctx->d_qf_flags.p;
+  q.permitted_begin = ctx->d_qf_permitted_begin.p;
+  q.permitted_kind = ctx->d_qf_permitted_kind.p;
+  return LMB_OK;
+}
+
 int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, const float* start_point,
                        const uint32_t* end_node, const float* end_point,
                        const uint32_t* override_begin, const uint32_t* override_type,
                        const float* override_cost, uint32_t* out_success, uint32_t* out_explored,
                        uint32_t* out_path_begin, uint32_t* out_nodes, uint32_t* out_portals,
-                       uint32_t path_capacity) {
+                       uint32_t path_capacity, const uint32_t* permit_all, const uint32_t* permitted_begin,
+                       const uint32_t* permitted_kind) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
   if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
   if (!out_path_begin) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_paths: null argument");
@@ -878,14 +914,9 @@ int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, con
   CUDA_TRY(ctx, ctx->d_q_start_point.upload(start_point, 3 * (size_t)n, s));
   CUDA_TRY(ctx, ctx->d_q_end_point.upload(end_point, 3 * (size_t)n, s));
   AStarQueries q = make_queries(ctx, n);
-  if (override_begin) {
-    CUDA_TRY(ctx, ctx->d_override_begin.upload(override_begin, (size_t)n + 1, s));
-    CUDA_TRY(ctx, ctx->d_override_type.upload(override_type, override_begin[n], s));
-    CUDA_TRY(ctx, ctx->d_override_cost.upload(override_cost, override_begin[n], s));
-    q.override_begin = ctx->d_override_begin.p;
-    q.override_type = ctx->d_override_type.p;
-    q.override_cost = ctx->d_override_cost.p;
-  }
+  st = upload_query_filters(ctx, q, n, override_begin, override_type, override_cost, permit_all, permitted_begin,
+                            permitted_kind);
+  if (st != LMB_OK) return st;
   // Paths of batch queries live in the pool only until they are copied out: remember the
   // cursor and rewind afterwards (agent paths are never touched).
   st = prepare_pool(ctx, n, nullptr);  // may compact: do it before the cursor is remembered
@@ -937,7 +968,9 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
                                 const float* end_point, const uint32_t* override_begin,
                                 const uint32_t* override_type, const float* override_cost,
                                 uint32_t* out_success, uint32_t* out_step_begin, uint32_t* out_kind,
-                                float* out_points, uint32_t* out_link, uint32_t step_capacity) {
+                                float* out_points, uint32_t* out_link, uint32_t step_capacity,
+                                const uint32_t* permit_all, const uint32_t* permitted_begin,
+                                const uint32_t* permitted_kind) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
   if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
   if (!out_step_begin) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_find_straight_paths: null argument");
@@ -962,14 +995,9 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
   CUDA_TRY(ctx, ctx->d_q_start_point.upload(start_point, 3 * (size_t)n, s));
   CUDA_TRY(ctx, ctx->d_q_end_point.upload(end_point, 3 * (size_t)n, s));
   AStarQueries q = make_queries(ctx, n);
-  if (override_begin) {
-    CUDA_TRY(ctx, ctx->d_override_begin.upload(override_begin, (size_t)n + 1, s));
-    CUDA_TRY(ctx, ctx->d_override_type.upload(override_type, override_begin[n], s));
-    CUDA_TRY(ctx, ctx->d_override_cost.upload(override_cost, override_begin[n], s));
-    q.override_begin = ctx->d_override_begin.p;
-    q.override_type = ctx->d_override_type.p;
-    q.override_cost = ctx->d_override_cost.p;
-  }
+  st = upload_query_filters(ctx, q, n, override_begin, override_type, override_cost, permit_all, permitted_begin,
+                            permitted_kind);
+  if (st != LMB_OK) return st;
   st = prepare_pool(ctx, n, nullptr);  // may compact: do it before the cursor is remembered
   if (st != LMB_OK) return st;
   unsigned long long cursor0 = 0;

@@ -103,6 +103,9 @@ struct lmb_ctx {
   uint32_t n_agents = 0, n_chars = 0;
   DevBuf<uint32_t> d_slot, d_flags, d_reach_condition, d_override_begin, d_override_type,
       d_permitted_begin, d_permitted_kind;
+  // per-query filters of lmb_find_paths / lmb_find_straight_paths
+  DevBuf<uint32_t> d_qf_override_begin, d_qf_override_type, d_qf_flags, d_qf_permitted_begin, d_qf_permitted_kind;
+  DevBuf<float> d_qf_override_cost;
   DevBuf<float> d_position, d_velocity, d_target, d_radius, d_desired_speed, d_max_speed,
       d_reach_distance, d_anim_reach, d_override_cost;
   bool has_reach_condition = false, has_reach_distance = false, has_anim_reach = false,

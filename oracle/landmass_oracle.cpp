@@ -1117,15 +1117,24 @@ int32_t orc_sample_points(orc_ctx* h, uint32_t n, const float* points, const lmb
   return LMB_OK;
 }
 
+// permitted_animation_links of query i of a batched query (see lmb_find_paths)
+static Permitted query_permitted(uint32_t i, const uint32_t* permit_all, const uint32_t* permitted_begin,
+                                 const uint32_t* permitted_kind) {
+  Permitted p;
+  p.all = !permit_all || permit_all[i] != 0;
+  if (!p.all && permitted_begin)
+    for (uint32_t k = permitted_begin[i]; k < permitted_begin[i + 1]; k++) p.kinds.insert(permitted_kind[k]);
+  return p;
+}
+
 int32_t orc_find_paths(orc_ctx* h, uint32_t n, const uint32_t* start_node, const float* start_point,
                        const uint32_t* end_node, const float* end_point,
                        const uint32_t* override_begin, const uint32_t* override_type,
                        const float* override_cost, uint32_t* out_success, uint32_t* out_explored,
                        uint32_t* out_path_begin, uint32_t* out_nodes, uint32_t* out_portals,
-                       uint32_t path_capacity) {
+                       uint32_t path_capacity, const uint32_t* permit_all, const uint32_t* permitted_begin,
+                       const uint32_t* permitted_kind) {
   uint32_t cursor = 0;
-  Permitted all;
-  all.all = true;
   std::vector<uint32_t> nodes, portals;
   int32_t status = LMB_OK;
   for (uint32_t i = 0; i < n; i++) {
@@ -1135,7 +1144,8 @@ int32_t orc_find_paths(orc_ctx* h, uint32_t n, const uint32_t* start_node, const
         ov[override_type[k]] = override_cost[k];
     V3 sp{start_point[3 * i], start_point[3 * i + 1], start_point[3 * i + 2]};
     V3 ep{end_point[3 * i], end_point[3 * i + 1], end_point[3 * i + 2]};
-    PathResult pr = find_path(h->c.nav, start_node[i], sp, end_node[i], ep, ov, all);
+    PathResult pr = find_path(h->c.nav, start_node[i], sp, end_node[i], ep, ov,
+                              query_permitted(i, permit_all, permitted_begin, permitted_kind));
     out_success[i] = pr.path ? 1 : 0;
     out_explored[i] = pr.explored_nodes;
     out_path_begin[i] = cursor;
@@ -1159,10 +1169,10 @@ int32_t orc_find_straight_paths(orc_ctx* h, uint32_t n, const uint32_t* start_no
                                 const float* end_point, const uint32_t* override_begin,
                                 const uint32_t* override_type, const float* override_cost,
                                 uint32_t* out_success, uint32_t* out_step_begin, uint32_t* out_kind,
-                                float* out_points, uint32_t* out_link, uint32_t step_capacity) {
+                                float* out_points, uint32_t* out_link, uint32_t step_capacity,
+                                const uint32_t* permit_all, const uint32_t* permitted_begin,
+                                const uint32_t* permitted_kind) {
   // query.rs:185-273
-  Permitted all;
-  all.all = true;
   uint32_t cursor = 0;
   int32_t status = LMB_OK;
   auto emit = [&](uint32_t kind, V3 a, V3 b, uint32_t link) {
@@ -1186,7 +1196,8 @@ int32_t orc_find_straight_paths(orc_ctx* h, uint32_t n, const uint32_t* start_no
       }
     V3 sp{start_point[3 * i], start_point[3 * i + 1], start_point[3 * i + 2]};
     V3 ep{end_point[3 * i], end_point[3 * i + 1], end_point[3 * i + 2]};
-    PathResult pr = find_path(h->c.nav, start_node[i], sp, end_node[i], ep, ov, all);
+    PathResult pr = find_path(h->c.nav, start_node[i], sp, end_node[i], ep, ov,
+                              query_permitted(i, permit_all, permitted_begin, permitted_kind));
     out_success[i] = pr.path ? 1 : 0;
     if (!pr.path) continue;
     const Path& path = *pr.path;

@@ -25,14 +25,16 @@ int32_t orc_find_paths(orc_ctx*, uint32_t n, const uint32_t* start_node, const f
                        const uint32_t* override_begin, const uint32_t* override_type,
                        const float* override_cost, uint32_t* out_success, uint32_t* out_explored,
                        uint32_t* out_path_begin, uint32_t* out_nodes, uint32_t* out_portals,
-                       uint32_t path_capacity);
+                       uint32_t path_capacity, const uint32_t* permit_all, const uint32_t* permitted_begin,
+                       const uint32_t* permitted_kind);
 
 int32_t orc_find_straight_paths(orc_ctx*, uint32_t n, const uint32_t* start_node, const float* start_point,
                                 const uint32_t* end_node, const float* end_point,
                                 const uint32_t* override_begin, const uint32_t* override_type,
                                 const float* override_cost, uint32_t* out_success,
                                 uint32_t* out_step_begin, uint32_t* out_kind, float* out_points,
-                                uint32_t* out_link, uint32_t step_capacity);
+                                uint32_t* out_link, uint32_t step_capacity, const uint32_t* permit_all,
+                                const uint32_t* permitted_begin, const uint32_t* permitted_kind);
 
 int32_t orc_step(orc_ctx*, const lmb_agents_in* agents, const lmb_characters_in* characters,
                  const lmb_options* options, float delta_time, const lmb_agents_out* out);

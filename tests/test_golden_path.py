@@ -208,11 +208,11 @@ def test_query_finds_path_across_islands(make_backend):  # query_test.rs:272-327
     arch.add_island(Island(Transform(tuple(off), 0.0), mesh))
     arch.add_island(Island(Transform(tuple(off + np.float32([1.0, 0.0])), 0.0), mesh))
     arch.add_island(Island(Transform(tuple(off + np.float32([2.0, 0.5])), 0.0), mesh))
+    arch.update(1.0)
     start = arch.sample_point(tuple(off + np.float32([0.5, 0.5])), np.float32(1e-5))
     end = arch.sample_point(tuple(off + np.float32([2.5, 1.25])), np.float32(1e-5))
-    assert start is not None and end is not None
-    sn, en = arch.node_id(*start[1]), arch.node_id(*end[1])
-    sp, ep = XY.to_landmass(start[0]), XY.to_landmass(end[0])
+    sn, en = arch.node_id(*start._node_ref), arch.node_id(*end._node_ref)
+    sp, ep = XY.to_landmass(start.point()), XY.to_landmass(end.point())
     succ, begin, kind, pts, link = arch.backend.find_straight_paths([sn], [sp], [en], [ep])
     assert succ[0] == 1 and list(kind) == [0, 0, 0]
     got = [tuple(float(x) for x in p[:2]) for p in pts]

@@ -177,3 +177,47 @@ def test_straight_paths_bit_exact(mesh_kind):
     assert np.array_equal(g[3].view(np.uint32), c[3].view(np.uint32))
     assert np.array_equal(g[4], c[4])
     assert (np.diff(g[1].astype(np.int64)) >= 2).all()
+
+
+@pytest.mark.gpu
+def test_queries_between_resident_steps_leave_the_agents_alone():
+    """lmb_find_paths / lmb_find_straight_paths carry their own override and permitted-kind arrays;
+    the copies lmb_agents_upload left on the device (used by every lmb_step_resident until the next
+    upload) must not change when a query with different filters runs in between."""
+    from landmass_b200._native import NativeBackend
+
+    types = (np.add.outer(np.arange(24) // 4, np.arange(24) // 4) % 3).astype(np.uint32).ravel()
+    mesh = synth.grid_mesh(24, 24, types=types)
+    flat = synth.single_island_flat(mesh)
+    flat["n_type_costs"] = 3
+    flat["type_cost_index"] = np.array([0, 1, 2], dtype=np.uint32)
+    flat["type_cost_value"] = np.array([1.0, 2.0, 5.0], dtype=np.float32)
+    n = 200
+    ag = synth.make_agents(mesh, n)
+    ag["override_begin"] = np.arange(n + 1, dtype=np.uint32)
+    ag["override_type"] = np.full(n, 2, dtype=np.uint32)
+    ag["override_cost"] = np.full(n, 0.25, dtype=np.float32)   # type 2 becomes the cheapest
+    opts = synth.default_options()
+
+    def run(with_query):
+        gpu = NativeBackend(max_agents=n, flags=_abi.CONFIG_NO_AVOIDANCE)
+        gpu.navdata_upload(flat)
+        gpu.agents_upload(ag, None)
+        if with_query:
+            sn = np.arange(50, dtype=np.uint32)
+            en = np.arange(500, 550, dtype=np.uint32)
+            gpu.find_paths(sn, mesh.poly_center[sn], en, mesh.poly_center[en], overrides=[{1: 9.0, 0: 3.0}] * 50,
+                           permitted=[[7]] * 50)
+            gpu.find_straight_paths(sn, mesh.poly_center[sn], en, mesh.poly_center[en], overrides=[{2: 40.0}] * 50)
+        gpu.step_resident(opts, 1.0 / 60.0)
+        out = gpu.agents_download()
+        res = gpu.pathing_results_array().copy()
+        paths = [gpu.agent_path(s) for s in range(0, n, 17)]
+        gpu.close()
+        return out, res, paths
+
+    (o1, r1, p1), (o2, r2, p2) = run(False), run(True)
+    assert np.array_equal(r1, r2)
+    assert np.array_equal(o1["desired_velocity"], o2["desired_velocity"])
+    for a, b in zip(p1, p2):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
