@@ -186,7 +186,7 @@ def test_queries_between_resident_steps_leave_the_agents_alone():
     upload) must not change when a query with different filters runs in between."""
     from landmass_b200._native import NativeBackend
 
-    types = (np.add.outer(np.arange(24) // 4, np.arange(24) // 4) % 3).astype(np.uint32).ravel()
+    types = (np.add.outer(np.arange(24) // 4, np.arange(24) // 4) % 3).astype(np.uint32)
     mesh = synth.grid_mesh(24, 24, types=types)
     flat = synth.single_island_flat(mesh)
     flat["n_type_costs"] = 3
