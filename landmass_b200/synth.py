@@ -116,6 +116,62 @@ def rosette_mesh(n_sides: int = 12, rings: int = 3) -> ValidNavigationMesh:
                           polygon_type_indices=types).validate()
 
 
+def irregular_mesh(nx: int, ny: int, seed: int = SEED, jitter: float = 0.2, hole_fraction: float = 0.08,
+                   relief: float = 0.6, straight_border: bool = False) -> ValidNavigationMesh:
+    """A mesh none of whose arithmetic is exact: an nx x ny lattice with every vertex moved by up to
+    `jitter` cells, heights from a smooth bump field (up to `relief`), about `hole_fraction` of the
+    cells removed, the others kept as quads or cut into two triangles along a random diagonal, and
+    polygon types 0..2 in blotches.  With `straight_border` the outer ring of vertices is not moved
+    (and lies at z = 0), so copies of the mesh tile with coinciding borders."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    gx, gy = np.meshgrid(np.arange(nx + 1, dtype=np.float64), np.arange(ny + 1, dtype=np.float64))
+    dx = rng.uniform(-jitter, jitter, size=gx.shape)
+    dy = rng.uniform(-jitter, jitter, size=gx.shape)
+    z = relief * 0.5 * (np.sin(gx * 0.37 + 0.3) * np.cos(gy * 0.29 - 0.2) + 0.35 * np.sin(gx * 0.9 + gy * 0.7))
+    if straight_border:
+        edge = (gx == 0) | (gx == nx) | (gy == 0) | (gy == ny)
+        dx[edge] = dy[edge] = 0.0
+        z[edge] = 0.0
+    verts = np.stack([(gx + dx).ravel(), (gy + dy).ravel(), z.ravel()], axis=1).astype(np.float32)
+    hole = rng.uniform(size=(ny, nx)) < hole_fraction
+    hole[0, :] = hole[-1, :] = hole[:, 0] = hole[:, -1] = False
+    cut = rng.integers(0, 3, size=(ny, nx))  # 0 quad, 1 / 2 the two diagonals
+    blotch = (np.floor(gx[:-1, :-1] / 3.0) + 2 * np.floor(gy[:-1, :-1] / 4.0)).astype(np.int64) % 3
+    polys, types = [], []
+    for y in range(ny):
+        for x in range(nx):
+            if hole[y, x]:
+                continue
+            v00 = y * (nx + 1) + x
+            a, b, c, d = v00, v00 + 1, v00 + (nx + 1) + 1, v00 + (nx + 1)
+            t = int(blotch[y, x])
+            if cut[y, x] == 0:
+                polys.append([a, b, c, d])
+                types.append(t)
+            elif cut[y, x] == 1:
+                polys.extend([[a, b, c], [a, c, d]])
+                types.extend([t, t])
+            else:
+                polys.extend([[a, b, d], [b, c, d]])
+                types.extend([t, t])
+    return NavigationMesh(vertices=verts, polygons=polys, polygon_type_indices=types).validate()
+
+
+def random_points_in_polygons(mesh: ValidNavigationMesh, n: int, rng, lift: float = 0.0):
+    """Uniform over polygons of any shape: a random convex combination of the polygon's first
+    triangle fan, `lift` above the surface.  Returns (points (n,3) f32, polygon index (n,))."""
+    p = rng.integers(0, mesh.n_polys, size=n)
+    pts = np.zeros((n, 3), dtype=np.float32)
+    for i, poly in enumerate(p):
+        v = mesh.vertices[mesh.polygon_vertices(int(poly))]
+        k = int(rng.integers(1, len(v) - 1))
+        w = rng.dirichlet([1.0, 1.0, 1.0])
+        w = 0.9 * w + 0.1 / 3.0  # stay off the edges
+        pts[i] = (w[0] * v[0] + w[1] * v[k] + w[2] * v[k + 1]).astype(np.float32)
+    pts[:, 2] += np.float32(lift)
+    return pts, p
+
+
 def random_points_on_mesh(mesh: ValidNavigationMesh, n: int, rng, lo: float = 0.1, hi: float = 0.9):
     """Uniform over polygons (axis-aligned quads): polygon min corner + uniform offset in
     [lo, hi]^2 of its extent.  Returns (points (n,3) f32, polygon index (n,))."""
