@@ -362,6 +362,17 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
                                 const uint32_t* permit_all, const uint32_t* permitted_begin,
                                 const uint32_t* permitted_kind);
 
+/* Read-backs for `debug::draw_archipelago_debug` (debug.rs:89-413), both cold:
+ * the start and end point of the path stored for `slot` (Path.start_point / end_point,
+ * path.rs:24-27; meaningful while lmb_agent_path reports a path), and, for every agent of the last
+ * step in its order, the next step of the straight path that step computed (debug.rs:386-412):
+ * out_kind LMB_NONE = none (no path, paused, using a link), 0 = Waypoint, 1 = AnimationLink;
+ * out_points = 6 floats (waypoint xyz twice, or link start xyz + link end xyz); out_link = the
+ * animation link id of an AnimationLink step. */
+int32_t lmb_agent_path_endpoints(lmb_ctx* ctx, uint32_t slot, float* out_start_point, float* out_end_point);
+int32_t lmb_agent_waypoints(lmb_ctx* ctx, uint32_t capacity, uint32_t* out_kind, float* out_points,
+                            uint32_t* out_link, uint32_t* out_count);
+
 int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out);
 
 #ifdef __cplusplus

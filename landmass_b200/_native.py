@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "li
 
 EXPORTED_SYMBOLS = [
     "lmb_abi_version", "lmb_create", "lmb_destroy", "lmb_last_error", "lmb_navdata_upload",
-    "lmb_navdata_update",
+    "lmb_navdata_update", "lmb_agent_path_endpoints", "lmb_agent_waypoints",
     "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
     "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
@@ -69,6 +69,8 @@ def declare_prototypes(lib, prefix: str):
     fn("find_straight_paths", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, _abi.f32p, _abi.u32p,
                                     _abi.u32p, _abi.f32p, _abi.u32p, _abi.u32p, _abi.u32p, _abi.f32p,
                                     _abi.u32p, u32, _abi.u32p, _abi.u32p, _abi.u32p])
+    fn("agent_path_endpoints", i32, [vp, u32, _abi.f32p, _abi.f32p])
+    fn("agent_waypoints", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, C.POINTER(u32)])
     fn("get_step_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
     fn("step_begin", i32, [vp, C.POINTER(_abi.Options), f32, u32, u32])
     fn("halo_buffer", i32, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
@@ -165,6 +167,28 @@ class CBackend:
                 continue
             self._check(st)
             return nodes[:ln.value], portals[:ln.value]
+
+    def agent_path_endpoints(self, slot: int):
+        """(Path.start_point, Path.end_point) of the path stored for `slot` (see lmb_agent_path_endpoints)."""
+        a, b = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        self._check(self._f("agent_path_endpoints")(self.ctx, slot, _abi.ptr(a, _abi.f32p), _abi.ptr(b, _abi.f32p)))
+        return a, b
+
+    def agent_waypoints(self):
+        """Per agent of the last step: (kind, points (n,6), link) — see lmb_agent_waypoints."""
+        cap = 1024
+        while True:
+            kind = np.zeros(cap, dtype=np.uint32)
+            pts = np.zeros((cap, 6), dtype=np.float32)
+            link = np.zeros(cap, dtype=np.uint32)
+            cnt = C.c_uint32(0)
+            st = self._f("agent_waypoints")(self.ctx, cap, _abi.ptr(kind, _abi.u32p), _abi.ptr(pts, _abi.f32p),
+                                            _abi.ptr(link, _abi.u32p), C.byref(cnt))
+            if st == _abi.ERR_CAPACITY:
+                cap = cnt.value
+                continue
+            self._check(st)
+            return kind[:cnt.value], pts[:cnt.value], link[:cnt.value]
 
     def sample_points(self, points, options: _abi.Options):
         pts = _abi.as_f32(points).reshape(-1, 3)

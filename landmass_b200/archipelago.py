@@ -286,6 +286,7 @@ class Archipelago:
         self._pathing_results: list[PathingResult] = []
         self._uploaded_generation = -1
         self._flat = None
+        self._last_step_keys = []
         self._device_versions: dict[int, int] = {}
         if backend is None:
             from ._native import NativeBackend  # raises loudly if the CUDA library is missing
@@ -517,6 +518,7 @@ class Archipelago:
                 ov_cost.append(c)
             ov_begin[i + 1] = len(ov_type)
         self._device_versions = live_slots
+        self._last_step_keys = [key for key, _ in items]
         ag["override_begin"] = ov_begin
         ag["override_type"] = np.array(ov_type, dtype=np.uint32)
         ag["override_cost"] = np.array(ov_cost, dtype=np.float32)

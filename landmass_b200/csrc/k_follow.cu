@@ -330,6 +330,7 @@ k_repath_decide(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool,
   scratch.follow_end[i] = follow ? ti : LMB_NONE;
   scratch.presult[i] = 0;
   scratch.query_of_agent[i] = LMB_NONE;
+  scratch.waypoint_kind[i] = LMB_NONE;
   persist.reached_link_id[s] = LMB_NONE;  // current_animation_link = None (lib.rs:348)
   if (new_state != LMB_NONE) persist.state[s] = new_state;
   if (clear_path) pool.slot_path_len[s] = 0;
@@ -365,6 +366,11 @@ k_follow(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool, AStarQ
     } else {
       follow_start = 0;                        // PathIndex::from_corridor_index(0, 0)
       follow_end = q.out_path_len[qi] - 1;     // new_path.last_index()
+      float* ends = persist.path_endpoints + 6 * (size_t)s;  // Path { start_point, end_point }
+      for (int k = 0; k < 3; k++) {
+        ends[k] = q.start_point[3 * (size_t)qi + k];
+        ends[3 + k] = q.end_point[3 * (size_t)qi + k];
+      }
     }
   }
   const uint32_t plen = pool.slot_path_len[s];
@@ -382,6 +388,14 @@ k_follow(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool, AStarQ
   Step next;
   uint32_t next_index =
       find_next_point_in_straight_path(nav, path, follow_start, agent_point, follow_end, target_point, next);
+  {
+    scratch.waypoint_kind[i] = next.is_link ? 1u : 0u;
+    scratch.waypoint_link[i] = next.is_link ? next.link_id : LMB_NONE;
+    float* w = scratch.waypoint_points + 6 * (size_t)i;
+    w[0] = next.point.x; w[1] = next.point.y; w[2] = next.point.z;
+    const V3 e = next.is_link ? next.end_point : next.point;
+    w[3] = e.x; w[4] = e.y; w[5] = e.z;
+  }
   const float radius = ag.radius[i];
   const uint32_t cond = ag.reach_condition ? ag.reach_condition[i] : LMB_REACH_DISTANCE;
   const float rd = reach_distance_or_radius(ag.reach_distance ? ag.reach_distance[i] : -1.0f, radius);

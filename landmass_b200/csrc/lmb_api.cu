@@ -97,7 +97,7 @@ int32_t lmb_create(const lmb_config* config, lmb_ctx** out_ctx) {
       ctx->d_slot_path_off.reserve(m), ctx->d_slot_path_len.reserve(m), ctx->d_slot_cost_hint.reserve(m), ctx->d_scan_tmp.reserve(m + 1),
       ctx->d_desired_move.reserve(3 * (size_t)m), ctx->d_reached_start.reserve(3 * (size_t)m),
       ctx->d_reached_end.reserve(3 * (size_t)m), ctx->d_state.reserve(m),
-      ctx->d_reached_link_id.reserve(m), ctx->d_pool_cursor.reserve(1), ctx->d_counters.reserve(1),
+      ctx->d_reached_link_id.reserve(m), ctx->d_path_endpoints.reserve(6 * (size_t)m), ctx->d_pool_cursor.reserve(1), ctx->d_counters.reserve(1),
       ctx->d_queue_count.reserve(1), ctx->d_avoid_overflow.reserve(4), ctx->d_bounds_tmp.reserve(8)};
   for (cudaError_t x : es)
     if (x != cudaSuccess) {
@@ -1144,6 +1144,7 @@ AgentPersist lmb_make_persist(lmb_ctx* ctx) {
   p.reached_link_id = ctx->d_reached_link_id.p;
   p.reached_link_start = ctx->d_reached_start.p;
   p.reached_link_end = ctx->d_reached_end.p;
+  p.path_endpoints = ctx->d_path_endpoints.p;
   return p;
 }
 
@@ -1178,6 +1179,9 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
   CUDA_TRY(ctx, ctx->d_follow_end.reserve(m));
   CUDA_TRY(ctx, ctx->d_presult.reserve(m));
   CUDA_TRY(ctx, ctx->d_query_of_agent.reserve(m));
+  CUDA_TRY(ctx, ctx->d_waypoint_kind.reserve(m));
+  CUDA_TRY(ctx, ctx->d_waypoint_link.reserve(m));
+  CUDA_TRY(ctx, ctx->d_waypoint_points.reserve(6 * m));
   CUDA_TRY(ctx, ctx->d_out_velocity.reserve(3 * m));
   CUDA_TRY(ctx, ctx->d_out_state.reserve(m));
   CUDA_TRY(ctx, ctx->d_out_link_id.reserve(m));
@@ -1218,6 +1222,9 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
   scratch.follow_end = ctx->d_follow_end.p;
   scratch.presult = ctx->d_presult.p;
   scratch.query_of_agent = ctx->d_query_of_agent.p;
+  scratch.waypoint_kind = ctx->d_waypoint_kind.p;
+  scratch.waypoint_link = ctx->d_waypoint_link.p;
+  scratch.waypoint_points = ctx->d_waypoint_points.p;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue_count.p, 0, sizeof(uint32_t), s));
   launch_repath_decide(ctx->nav, ag, persist, make_pool(ctx), queue, scratch, s);
   T.kernel_launches += n ? 1 : 0;
@@ -1405,6 +1412,37 @@ int32_t lmb_agent_path(lmb_ctx* ctx, uint32_t slot, uint32_t* out_nodes, uint32_
     out_nodes[k] = tmp[k].x;
     out_portals[k] = tmp[k].y;
   }
+  return LMB_OK;
+}
+
+int32_t lmb_agent_path_endpoints(lmb_ctx* ctx, uint32_t slot, float* out_start_point, float* out_end_point) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!out_start_point || !out_end_point || slot >= ctx->cfg.max_agents)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_path_endpoints: bad slot / null output");
+  cudaSetDevice(ctx->device);
+  float ends[6];
+  CUDA_TRY(ctx, cudaMemcpy(ends, ctx->d_path_endpoints.p + 6 * (size_t)slot, sizeof(ends), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 3; k++) {
+    out_start_point[k] = ends[k];
+    out_end_point[k] = ends[3 + k];
+  }
+  return LMB_OK;
+}
+
+int32_t lmb_agent_waypoints(lmb_ctx* ctx, uint32_t capacity, uint32_t* out_kind, float* out_points,
+                            uint32_t* out_link, uint32_t* out_count) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!out_count) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_waypoints: null out_count");
+  const uint32_t n = ctx->n_agents;
+  *out_count = n;
+  if (n > capacity) return LMB_ERR_CAPACITY;
+  if (n == 0) return LMB_OK;
+  if (!out_kind || !out_points || !out_link)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_waypoints: null output");
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaMemcpy(out_kind, ctx->d_waypoint_kind.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(out_link, ctx->d_waypoint_link.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CUDA_TRY(ctx, cudaMemcpy(out_points, ctx->d_waypoint_points.p, 6 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
   return LMB_OK;
 }
 

@@ -119,7 +119,8 @@ struct lmb_ctx {
   DevBuf<uint32_t> d_queue_count, d_q_agent, d_q_slot, d_q_start_node, d_q_end_node, d_q_status,
       d_q_success, d_q_explored, d_q_path_off, d_q_path_len, d_retry_list;
   DevBuf<float> d_q_start_point, d_q_end_point;
-  DevBuf<uint32_t> d_follow_start, d_follow_end, d_presult, d_query_of_agent;
+  DevBuf<uint32_t> d_follow_start, d_follow_end, d_presult, d_query_of_agent, d_waypoint_kind, d_waypoint_link;
+  DevBuf<float> d_waypoint_points, d_path_endpoints;
   uint32_t* h_small = nullptr;  // pinned scratch (n_repath etc.)
   // outputs (device)
   DevBuf<float> d_out_velocity, d_out_link_start, d_out_link_end;

@@ -121,6 +121,7 @@ struct AgentPersist {  // indexed by slot
   uint32_t* reached_link_id;
   float* reached_link_start;
   float* reached_link_end;
+  float* path_endpoints;     // [max_agents*6] Path.start_point, Path.end_point (path.rs:24-27) of the stored path
 };
 
 struct RepathQueue {
@@ -139,6 +140,11 @@ struct FollowScratch {
   uint32_t* follow_end;    // [n]
   uint32_t* presult;       // [n] bit31 repathed this frame, bit30 success, low 30 bits explored
   uint32_t* query_of_agent;  // [n] query id or LMB_NONE
+  // the frame's next step of the straight path per agent (what debug drawing shows, debug.rs:386-412):
+  // kind LMB_NONE = none this frame, 0 = Waypoint, 1 = AnimationLink
+  uint32_t* waypoint_kind;   // [n]
+  uint32_t* waypoint_link;   // [n] animation link id of an AnimationLink step
+  float* waypoint_points;    // [n*6] point (or link start point) xyz, link end point xyz
 };
 
 void launch_reset_slots(const AgentArrays& ag, const AgentPersist& persist, const PathPool& pool,

@@ -940,6 +940,7 @@ void Ctx::step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, co
   }
 
   // PHASE C: follow path (lib.rs:426-523)
+  f_waypoints.assign(n, Waypoint{});
   for (uint32_t i = 0; i < n; i++) {
     AgentPersist& s = st(i);
     if (!s.path) {
@@ -951,6 +952,13 @@ void Ctx::step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, co
     V3 target_point = target_node[i].point;
     auto next_waypoint = s.path->find_next_point_in_straight_path(nav, follow[i].first, agent_point,
                                                                   follow[i].second, target_point);
+    {
+      const StraightPathStep& w = next_waypoint.second;
+      f_waypoints[i].kind = w.is_link ? 1u : 0u;
+      f_waypoints[i].link = w.is_link ? w.link_id : LMB_NONE;
+      f_waypoints[i].point = w.point;
+      f_waypoints[i].end_point = w.is_link ? w.end_point : w.point;
+    }
     if (has_reached_target(ag[i], *s.path, nav, agent_point, next_waypoint,
                            {follow[i].second, target_point})) {
       s.desired_move = {0, 0, 0};
@@ -1269,6 +1277,29 @@ int32_t orc_agent_path(orc_ctx* h, uint32_t slot, uint32_t* out_nodes, uint32_t*
   if (nodes.size() > capacity) return LMB_ERR_CAPACITY;
   std::copy(nodes.begin(), nodes.end(), out_nodes);
   std::copy(portals.begin(), portals.end(), out_portals);
+  return LMB_OK;
+}
+
+int32_t orc_agent_path_endpoints(orc_ctx* h, uint32_t slot, float* out_start_point, float* out_end_point) {
+  auto it = h->c.agent_state.find(slot);
+  if (it == h->c.agent_state.end() || !it->second.path) return LMB_ERR_INVALID_ARGUMENT;
+  const Path& p = *it->second.path;
+  out_start_point[0] = p.start_point.x; out_start_point[1] = p.start_point.y; out_start_point[2] = p.start_point.z;
+  out_end_point[0] = p.end_point.x; out_end_point[1] = p.end_point.y; out_end_point[2] = p.end_point.z;
+  return LMB_OK;
+}
+int32_t orc_agent_waypoints(orc_ctx* h, uint32_t capacity, uint32_t* out_kind, float* out_points,
+                            uint32_t* out_link, uint32_t* out_count) {
+  const auto& w = h->c.f_waypoints;
+  *out_count = (uint32_t)w.size();
+  if (w.size() > capacity) return LMB_ERR_CAPACITY;
+  for (size_t i = 0; i < w.size(); i++) {
+    out_kind[i] = w[i].kind;
+    out_link[i] = w[i].link;
+    float* p = out_points + 6 * i;
+    p[0] = w[i].point.x; p[1] = w[i].point.y; p[2] = w[i].point.z;
+    p[3] = w[i].end_point.x; p[4] = w[i].end_point.y; p[5] = w[i].end_point.z;
+  }
   return LMB_OK;
 }
 

@@ -208,6 +208,12 @@ struct Ctx {
   std::vector<Sampled> f_agent_node;
   std::vector<CharacterIn> f_chars;
   std::vector<AvoidRec> halo;
+  // the frame's next step of the straight path per agent (debug.rs:386-412); kind LMB_NONE = none
+  struct Waypoint {
+    uint32_t kind = LMB_NONE, link = LMB_NONE;
+    V3 point{0, 0, 0}, end_point{0, 0, 0};
+  };
+  std::vector<Waypoint> f_waypoints;
   uint32_t halo_first = 0;
   void step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, const lmb_options& opt, float dt,
                   uint32_t n_total, uint32_t first);
