@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LMB_ABI_VERSION 1u
+#define LMB_ABI_VERSION 2u
 #define LMB_NONE 0xFFFFFFFFu
 
 typedef enum lmb_status {

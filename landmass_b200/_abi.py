@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NONE = 0xFFFFFFFF
 PORTAL_LINK = 0x80000000
 

@@ -37,7 +37,7 @@ def test_ctypes_layout_matches_header(tmp_path):
     structs = {"lmb_options": _abi.Options, "lmb_navdata_desc": _abi.NavDataDesc,
                "lmb_agents_in": _abi.AgentsIn, "lmb_characters_in": _abi.CharactersIn,
                "lmb_agents_out": _abi.AgentsOut, "lmb_pathing_result": _abi.PathingResult,
-               "lmb_config": _abi.Config, "lmb_step_timings": _abi.StepTimings}
+               "lmb_config": _abi.Config, "lmb_step_timings": _abi.StepTimings, "lmb_nav_remap": _abi.NavRemap}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void) {"]
     for cname, py in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
@@ -79,3 +79,35 @@ def test_package_does_not_import_oracle():
     code = "import sys; import landmass_b200, landmass_b200._native, landmass_b200.sharded, landmass_b200.synth; " \
            "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported by the product'"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+@pytest.mark.gpu
+def test_error_paths_of_the_newer_entry_points():
+    """lmb_navdata_update refuses a remap that does not describe the previous upload; the read-backs
+    refuse bad slots; every failure leaves a message in lmb_last_error."""
+    import numpy as np
+
+    from landmass_b200 import synth
+
+    mesh = synth.grid_mesh(4, 4)
+    flat = synth.single_island_flat(mesh)
+    gpu = _native.NativeBackend(max_agents=8)
+    # before any upload a remap is ignored (there is nothing to carry over)
+    gpu.navdata_upload(flat, {"island_map": np.zeros(0, dtype=np.uint32), "link_map": np.zeros(0, dtype=np.uint32)})
+    for remap, what in [
+        ({"island_map": np.zeros(3, dtype=np.uint32), "link_map": np.zeros(0, dtype=np.uint32)}, "previous upload"),
+        ({"island_map": np.array([5], dtype=np.uint32), "link_map": np.zeros(0, dtype=np.uint32)}, "not the same island"),
+    ]:
+        with pytest.raises(_native.NativeError) as e:
+            gpu.navdata_upload(flat, remap)
+        assert e.value.status == _abi.ERR_INVALID_ARGUMENT and what in str(e.value)
+    gpu.navdata_upload(flat, {"island_map": np.array([0], dtype=np.uint32), "link_map": np.zeros(0, dtype=np.uint32)})
+    with pytest.raises(_native.NativeError):
+        gpu.agent_path_endpoints(8)
+    kind, pts, link = gpu.agent_waypoints()
+    assert len(kind) == 0
+    ag = synth.make_agents(mesh, 4)
+    gpu.step(ag, None, synth.default_options(), 0.1)
+    kind, pts, link = gpu.agent_waypoints()
+    assert len(kind) == 4 and set(kind.tolist()) <= {0, _abi.NONE}
+    gpu.close()
