@@ -773,8 +773,11 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 // in flight is bounded by HBM (the per-query arena slot) and by shared memory (the open lists),
 // and the search by the latency of one lock-step warp iteration, not by warp or issue slots — a
 // warp that waits for the slowest of 16 instead of 32 pops measured 5-14 % faster.
-//  * small open lists (mazes: a few dozen open branches): 256 queries per SM = 4 blocks x 4 warps
-//    x 16, 48 open-list entries per query in shared memory;
+//  * small open lists (mazes: a few dozen open branches): 320 queries per SM = 5 blocks x 4 warps
+//    x 16, 40 open-list entries per query in shared memory.  __launch_bounds__(128, 5) holds the
+//    kernel to 96 registers without a spill (113 at 4 blocks); the fifth block is worth 7 % on the
+//    bench (822 -> 765 ms).  A sixth (32 entries, 80 registers, 68 bytes spilled) is slower than
+//    four;
 //  * large open lists (open fields: a wavefront of thousands): 128 queries per SM = 2 blocks, 96
 //    entries in shared memory.  Every spilled heap level is a dependent HBM round trip and these
 //    searches are bound by random-sector HBM traffic, so one more level on chip beats twice the
@@ -787,7 +790,7 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 // (Measured and rejected: 32 queries per warp; 384 queries per SM with 28 shared-memory entries;
 // 64 / 192 / 384 entries at 192 / 64 / 32 queries per SM; a 4-lanes-per-query variant — lower
 // latency per query but issue-bound, no faster when loaded.)
-uint32_t astar_resident_queries_per_sm(bool big_heap) { return (big_heap ? 2 : 4) * 16 * (AT_THREADS / 32); }
+uint32_t astar_resident_queries_per_sm(bool big_heap) { return (big_heap ? 2 : 5) * 16 * (AT_THREADS / 32); }
 
 void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                   AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream) {
@@ -816,7 +819,7 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   else if (big_heap)
     LMB_ASTAR_LAUNCH(16, 96, 2);
   else
-    LMB_ASTAR_LAUNCH(16, 48, 4);
+    LMB_ASTAR_LAUNCH(16, 40, 5);
 #undef LMB_ASTAR_LAUNCH
 #undef LMB_ASTAR_LAUNCH_L
   AStarArena a = arena;
