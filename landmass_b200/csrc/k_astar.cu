@@ -778,10 +778,12 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 //    kernel to 96 registers without a spill (113 at 4 blocks); the fifth block is worth 7 % on the
 //    bench (822 -> 765 ms).  A sixth (32 entries, 80 registers, 68 bytes spilled) is slower than
 //    four;
-//  * large open lists (open fields: a wavefront of thousands): 128 queries per SM = 2 blocks, 96
-//    entries in shared memory.  Every spilled heap level is a dependent HBM round trip and these
-//    searches are bound by random-sector HBM traffic, so one more level on chip beats twice the
-//    queries in flight (open 256x256 field, 50k queries: 1.47 s -> 1.09 s).
+//  * large open lists (open fields: a wavefront of thousands): 128 queries per SM with 96 entries in
+//    shared memory.  Every spilled heap level is a dependent HBM round trip and these searches are
+//    bound by random-sector HBM traffic, so one more level on chip beats twice the queries in
+//    flight (open 256x256 field, 50k queries: 1.47 s -> 1.06 s), and the same 128 queries as 16
+//    warps of 8 instead of 8 warps of 16 hide more of those round trips (-> 0.92 s; 160 queries
+//    with 80 entries: 0.97 s, 80 with 160: 1.01 s, 64 with 192: 1.15 s).
 //  * small batches run at the latency of their longest search, so they get the widest shapes the
 //    batch size allows: up to 32 queries per SM -> 4 queries per warp with 384 entries each, up to
 //    8 per SM -> one query per warp with 1536 entries (a lone lane is not held back by
@@ -817,7 +819,7 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   else if (q.n <= 128u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(8, 96, 4);
   else if (big_heap)
-    LMB_ASTAR_LAUNCH(16, 96, 2);
+    LMB_ASTAR_LAUNCH(8, 96, 4);
   else
     LMB_ASTAR_LAUNCH(16, 40, 5);
 #undef LMB_ASTAR_LAUNCH
