@@ -38,8 +38,8 @@ DT = 1.0 / 60.0
 B_STEP = 240.0  # algorithmic bytes per steady agent-update
 # DRAM bytes per explored node of k_astar, from the one `ncu --set full` capture of a fully loaded
 # launch (profiles/r01_ncu_astar_loaded.md: dram read + write / explored nodes).  The bench-size
-# launch itself cannot be captured: kernel replay would have to save and restore its ~85 GB arena.
-NCU_DRAM_BYTES_PER_EXPLORED = 85.7
+# launch itself cannot be captured: kernel replay would have to save and restore its ~100 GB arena.
+NCU_DRAM_BYTES_PER_EXPLORED = 113.9
 
 
 def measured_peak_gbs():
@@ -158,7 +158,7 @@ def workload_config(args, n_gpus, sample_note=None):
                     "funnel, ORCA avoidance)",
         "agents_per_gpu": args.agents, "polygons": 2 * args.rooms * args.rooms - 1,
         "parallelism": f"agents sharded x{n_gpus}, navmesh replicated, NCCL all-gather of 32 B/agent",
-        "cache": "inputs and A* working set (one arena slot per query in flight, ~85 GB) far exceed the "
+        "cache": "inputs and A* working set (one arena slot per query in flight, ~100 GB) far exceed the "
                  "126 MB L2; no flush needed",
     }
     if sample_note:
@@ -352,7 +352,7 @@ def main():
                          "traffic": NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps,
                          "traffic_source": "ncu dram bytes per explored node of a fully loaded smaller "
                                            "launch (profiles/r01_ncu_astar_loaded.md) x explored nodes of this "
-                                           "launch; the bench-size launch is not capturable (85 GB arena)",
+                                           "launch; the bench-size launch is not capturable (~100 GB arena)",
                          "algorithmic_bytes": astar_bytes, "peak_source": peak_src,
                          "note": "latency-bound graph search: one dependent chain per query (pop -> "
                                  "records -> best[] probes -> push), random 32-byte sectors of a per-query "
