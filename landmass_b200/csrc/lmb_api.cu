@@ -262,6 +262,7 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
   const bool carry_paths = remap && ctx->has_nav;
   const std::vector<uint32_t> old_island_poly_begin = ctx->h_island_poly_begin;
   const uint32_t n_old_links = ctx->nav.n_links;
+  ctx->has_nav = false;  // a failure below leaves the context without navigation data, not with half of it
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   cudaStreamSynchronize(s);
