@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LMB_ABI_VERSION 2u
+#define LMB_ABI_VERSION 3u
 #define LMB_NONE 0xFFFFFFFFu
 
 typedef enum lmb_status {
@@ -66,6 +66,7 @@ typedef enum lmb_agent_state {
 #define LMB_AGENT_USING_ANIMATION_LINK 4u  /* agent.using_animation_link */
 #define LMB_AGENT_RESET 8u                 /* slot was (re)created: drop the device-side path/state */
 #define LMB_AGENT_PERMIT_ALL_LINKS 16u     /* PermittedAnimationLinks::All */
+#define LMB_AGENT_KEEP_AVOIDANCE_DATA 32u  /* agent.keep_avoidance_data (agent.rs:87-90, feature debug-avoidance) */
 
 /* Off-mesh link kinds — reference nav_data.rs:96-117. */
 #define LMB_LINK_BOUNDARY 0u
@@ -372,6 +373,19 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
 int32_t lmb_agent_path_endpoints(lmb_ctx* ctx, uint32_t slot, float* out_start_point, float* out_end_point);
 int32_t lmb_agent_waypoints(lmb_ctx* ctx, uint32_t capacity, uint32_t* out_kind, float* out_points,
                             uint32_t* out_link, uint32_t* out_count);
+
+/* `debug::draw_avoidance_data` (debug.rs:415-503, feature `debug-avoidance`): the velocity-space
+ * constraint lines the last step's avoidance built for the agent at `agent_index` of that step's
+ * arrays — what `agent.avoidance_data` holds after avoidance.rs:161-172.  Only agents uploaded with
+ * LMB_AGENT_KEEP_AVOIDANCE_DATA have any.  out_lines = [capacity][4] {point.xy, direction.xy} in
+ * dodgy_2d's Line convention (ConstraintLine.normal = (-direction.y, direction.x)):
+ * *out_n_original lines of DebugData::{Satisfied.constraints, Fallback.original_constraints}
+ * (obstacle lines first, then one per neighbour) followed by *out_n_fallback lines of
+ * Fallback.fallback_constraints (the projected set of the last 3-D re-solve).  *out_ran = 1:
+ * DebugData::Satisfied, 2: DebugData::Fallback, 0: the step skipped avoidance for this agent (not
+ * sampled, paused ...: the reference then leaves agent.avoidance_data as it was).  LMB_ERR_CAPACITY with the counts set if capacity is too small. */
+int32_t lmb_agent_avoidance_constraints(lmb_ctx* ctx, uint32_t agent_index, uint32_t capacity, float* out_lines,
+                                        uint32_t* out_n_original, uint32_t* out_n_fallback, uint32_t* out_ran);
 
 int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out);
 

@@ -9,8 +9,8 @@ from .archipelago import (Agent, AgentState, Archipelago, ArchipelagoOptions, Ch
                           PathingResult, PathStep, PermittedAnimationLinks, ReachedAnimationLink,
                           SampledPoint, SamplePointError, TargetReachedCondition)
 from .anim_links import AnimationLink
-from .debug import (DebugDrawError, DebugDrawer, LineType, PointType, TriangleType,  # noqa: F401
-                    draw_archipelago_debug)
+from .debug import (AvoidanceDrawer, ConstraintKind, ConstraintLine, DebugDrawError, DebugDrawer,  # noqa: F401
+                    LineType, PointType, TriangleType, draw_archipelago_debug, draw_avoidance_data)
 from .coords import XY, XYZ, CorePointSampleDistance, PointSampleDistance3d
 from .nav_data import Island, NavigationData, SetTypeIndexCostError, Transform
 from .nav_mesh import (HeightNavigationMesh, HeightPolygon, NavigationMesh, ValidationError,

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 NONE = 0xFFFFFFFF
 PORTAL_LINK = 0x80000000
 
@@ -29,6 +29,7 @@ AGENT_PAUSED = 2
 AGENT_USING_ANIMATION_LINK = 4
 AGENT_RESET = 8
 AGENT_PERMIT_ALL_LINKS = 16
+AGENT_KEEP_AVOIDANCE_DATA = 32
 
 REACH_DISTANCE = 0
 REACH_VISIBLE_AT_DISTANCE = 1

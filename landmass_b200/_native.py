@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
     "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
-    "lmb_find_straight_paths",
+    "lmb_find_straight_paths", "lmb_agent_avoidance_constraints",
 ]
 
 
@@ -71,6 +71,7 @@ def declare_prototypes(lib, prefix: str):
                                     _abi.u32p, u32, _abi.u32p, _abi.u32p, _abi.u32p])
     fn("agent_path_endpoints", i32, [vp, u32, _abi.f32p, _abi.f32p])
     fn("agent_waypoints", i32, [vp, u32, _abi.u32p, _abi.f32p, _abi.u32p, C.POINTER(u32)])
+    fn("agent_avoidance_constraints", i32, [vp, u32, u32, _abi.f32p, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)])
     fn("get_step_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
     fn("step_begin", i32, [vp, C.POINTER(_abi.Options), f32, u32, u32])
     fn("halo_buffer", i32, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
@@ -189,6 +190,22 @@ class CBackend:
                 continue
             self._check(st)
             return kind[:cnt.value], pts[:cnt.value], link[:cnt.value]
+
+    def agent_avoidance_constraints(self, agent_index: int):
+        """(ran, original (n,4), fallback (m,4), fell_back) of the agent at `agent_index` of the last step; lines
+        are {point.xy, direction.xy} — see lmb_agent_avoidance_constraints."""
+        cap = 64
+        while True:
+            lines = np.zeros((cap, 4), dtype=np.float32)
+            n_o, n_f, ran = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+            st = self._f("agent_avoidance_constraints")(self.ctx, agent_index, cap, _abi.ptr(lines, _abi.f32p),
+                                                        C.byref(n_o), C.byref(n_f), C.byref(ran))
+            if st == _abi.ERR_CAPACITY:
+                cap = n_o.value + n_f.value
+                continue
+            self._check(st)
+            return (ran.value != 0, lines[:n_o.value].copy(), lines[n_o.value:n_o.value + n_f.value].copy(),
+                    ran.value == 2)
 
     def sample_points(self, points, options: _abi.Options):
         pts = _abi.as_f32(points).reshape(-1, 3)

@@ -102,6 +102,9 @@ class Agent:
         self.animation_link_reached_distance = None
         self.permitted_animation_links = PermittedAnimationLinks()
         self.paused = False
+        # feature `debug-avoidance` (agent.rs:87-90, 105-108): keep the avoidance constraints of each update
+        self.keep_avoidance_data = False
+        self._avoidance_data = None  # ("Satisfied", constraints) | ("Fallback", original, fallback); lines (n, 4)
         self._override_type_index_to_cost: dict[int, float] = {}
         self._current_desired_move = cs.from_landmass(np.zeros(3, dtype=np.float32))
         self._state = AgentState.Idle
@@ -500,6 +503,9 @@ class Archipelago:
                 flags |= _abi.AGENT_PERMIT_ALL_LINKS
             else:
                 pm_kind.extend(sorted(a.permitted_animation_links.kinds))
+            if a.keep_avoidance_data or a._avoidance_data is not None:
+                # (an agent that stopped asking still needs to learn whether avoidance ran, to drop its old data)
+                flags |= _abi.AGENT_KEEP_AVOIDANCE_DATA
             pm_begin[i + 1] = len(pm_kind)
             ag["slot"][i] = key.idx
             ag["flags"][i] = flags
@@ -544,6 +550,17 @@ class Archipelago:
                     cs.from_landmass(out["reached_link_end"][i]))
             else:
                 a._current_animation_link = None
+            if a.keep_avoidance_data or a._avoidance_data is not None:
+                # agent.avoidance_data = agent.keep_avoidance_data.then_some(debug_data), only for the agents
+                # avoidance visited (avoidance.rs:83-87, 161-172)
+                ran, original, fallback, fell_back = self.backend.agent_avoidance_constraints(i)
+                if ran:
+                    if not a.keep_avoidance_data:
+                        a._avoidance_data = None
+                    elif fell_back:
+                        a._avoidance_data = ("Fallback", original, fallback)
+                    else:
+                        a._avoidance_data = ("Satisfied", original)
         self._pathing_results = [
             PathingResult(items[int(r[0])][0], bool(r[1]), int(r[2]))
             for r in self.backend.pathing_results()

@@ -587,9 +587,12 @@ __device__ uint32_t linear_program_2(const Line* lines, uint32_t n, float radius
   return n;
 }
 
-__device__ void linear_program_3(const Line* lines, uint32_t n, uint32_t num_obst_lines, uint32_t begin_line,
-                                 float radius, V2& result, Line* proj) {
+// Returns the size of the last projected constraint set left in `proj` (the fallback constraints
+// the debug-avoidance export reports, debug.rs:470-481).
+__device__ uint32_t linear_program_3(const Line* lines, uint32_t n, uint32_t num_obst_lines, uint32_t begin_line,
+                                     float radius, V2& result, Line* proj) {
   float distance_ = 0.0f;
+  uint32_t last_np = 0;
   for (uint32_t i = begin_line; i < n; i++) {
     Line li = lines[i];
     if (perp_dot(li.direction, li.point - result) > distance_) {
@@ -611,8 +614,10 @@ __device__ void linear_program_3(const Line* lines, uint32_t n, uint32_t num_obs
       V2 temp = result;
       if (linear_program_2(proj, np, radius, V2{-li.direction.y, li.direction.x}, true, result) < np) result = temp;
       distance_ = perp_dot(li.direction, li.point - result);
+      last_np = np;
     }
   }
+  return last_np;
 }
 
 }  // namespace
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(64)
 k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_t first_agent_global,
             uint32_t chunk_begin, uint32_t chunk_n, uint32_t n_records, const AvoidRecord* records,
             uint32_t n_characters, const AvoidRecord* char_records, AvoidGrid grid, AvoidScratch scratch,
-            const uint32_t* max_radius_bits, float* out_move) {
+            const uint32_t* max_radius_bits, float* out_move, AvoidDebug dbg) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= chunk_n) return;
   const uint32_t i = chunk_begin + t;        // local dense agent index
@@ -974,7 +979,27 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
   V2 preferred{out_move[3 * (size_t)i], out_move[3 * (size_t)i + 1]};
   V2 result;
   uint32_t fail = linear_program_2(s.lines, n_lines, ag.max_speed[i], preferred, false, result);
-  if (fail < n_lines) linear_program_3(s.lines, n_lines, obstacle_line_count, fail, ag.max_speed[i], result, s.proj);
+  uint32_t n_fallback = 0;
+  if (fail < n_lines)
+    n_fallback = linear_program_3(s.lines, n_lines, obstacle_line_count, fail, ag.max_speed[i], result, s.proj);
+  if (dbg.row_of) {
+    // debug-avoidance export (avoidance.rs:161-172): the constraint lines of agents that asked for them
+    const uint32_t row = dbg.row_of[i];
+    if (row != LMB_NONE) {
+      uint32_t* h = dbg.header + 4 * (size_t)row;
+      float4* out = dbg.lines + (size_t)row * dbg.lines_per_row;
+      const uint32_t no = n_lines < dbg.lines_per_row ? n_lines : dbg.lines_per_row;
+      const uint32_t nf = n_fallback < dbg.lines_per_row - no ? n_fallback : dbg.lines_per_row - no;
+      for (uint32_t k = 0; k < no; k++)
+        out[k] = make_float4(s.lines[k].point.x, s.lines[k].point.y, s.lines[k].direction.x, s.lines[k].direction.y);
+      for (uint32_t k = 0; k < nf; k++)
+        out[no + k] = make_float4(s.proj[k].point.x, s.proj[k].point.y, s.proj[k].direction.x, s.proj[k].direction.y);
+      h[0] = 1u;  // avoidance ran for this agent in this step
+      h[1] = no;
+      h[2] = nf;
+      h[3] = fail < n_lines ? 1u : 0u;  // DebugData::Fallback
+    }
+  }
   out_move[3 * (size_t)i] = result.x;
   out_move[3 * (size_t)i + 1] = result.y;
   out_move[3 * (size_t)i + 2] = 0.0f;
@@ -1049,11 +1074,12 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             uint32_t first_agent_global, uint32_t chunk_begin, uint32_t chunk_n,
                             uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
                             const AvoidRecord* char_records, const AvoidGrid& grid, const AvoidScratch& scratch,
-                            const uint32_t* max_radius_bits, float* staged_moves, cudaStream_t stream) {
+                            const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
+                            cudaStream_t stream) {
   if (!chunk_n) return;
   k_avoidance<<<blocks_for(chunk_n, 64), 64, 0, stream>>>(nav, ag, o, delta_time, first_agent_global, chunk_begin,
                                                           chunk_n, n_records, records, n_characters, char_records,
-                                                          grid, scratch, max_radius_bits, staged_moves);
+                                                          grid, scratch, max_radius_bits, staged_moves, dbg);
 }
 
 }  // namespace lmb

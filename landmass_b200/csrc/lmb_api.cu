@@ -1078,6 +1078,15 @@ int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* a, const lmb_charac
   ctx->n_agents = n;
   CUDA_TRY(ctx, ctx->d_slot.upload(a->slot, n, s));
   CUDA_TRY(ctx, ctx->d_flags.upload(a->flags, n, s));
+  // rows of the debug-avoidance export, in agent order
+  ctx->dbg_rows = 0;
+  ctx->h_dbg_row_of.clear();
+  for (uint32_t i = 0; i < n; i++) {
+    if (!(a->flags[i] & LMB_AGENT_KEEP_AVOIDANCE_DATA)) continue;
+    if (ctx->h_dbg_row_of.empty()) ctx->h_dbg_row_of.assign(n, LMB_NONE);
+    ctx->h_dbg_row_of[i] = ctx->dbg_rows++;
+  }
+  if (ctx->dbg_rows) CUDA_TRY(ctx, ctx->d_dbg_row_of.upload(ctx->h_dbg_row_of, s));
   CUDA_TRY(ctx, ctx->d_position.upload(a->position, 3 * (size_t)n, s));
   CUDA_TRY(ctx, ctx->d_velocity.upload(a->velocity, 3 * (size_t)n, s));
   if (a->target) {
@@ -1444,6 +1453,34 @@ int32_t lmb_agent_waypoints(lmb_ctx* ctx, uint32_t capacity, uint32_t* out_kind,
   CUDA_TRY(ctx, cudaMemcpy(out_kind, ctx->d_waypoint_kind.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   CUDA_TRY(ctx, cudaMemcpy(out_link, ctx->d_waypoint_link.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   CUDA_TRY(ctx, cudaMemcpy(out_points, ctx->d_waypoint_points.p, 6 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+  return LMB_OK;
+}
+
+int32_t lmb_agent_avoidance_constraints(lmb_ctx* ctx, uint32_t agent_index, uint32_t capacity, float* out_lines,
+                                        uint32_t* out_n_original, uint32_t* out_n_fallback, uint32_t* out_ran) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (!out_n_original || !out_n_fallback || !out_ran)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_avoidance_constraints: null output");
+  if (agent_index >= ctx->n_agents)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_avoidance_constraints: agent %u of %u", agent_index,
+                     ctx->n_agents);
+  *out_n_original = *out_n_fallback = *out_ran = 0;
+  if (ctx->h_dbg_row_of.empty() || ctx->h_dbg_row_of[agent_index] == LMB_NONE || !ctx->dbg_lines_per_row)
+    return LMB_OK;  // the agent did not ask for its avoidance data (or no step ran since the upload)
+  const uint32_t row = ctx->h_dbg_row_of[agent_index];
+  cudaSetDevice(ctx->device);
+  uint32_t h[4];
+  CUDA_TRY(ctx, cudaMemcpy(h, ctx->d_dbg_header.p + 4 * (size_t)row, sizeof(h), cudaMemcpyDeviceToHost));
+  *out_ran = h[0] ? 1u + h[3] : 0u;
+  *out_n_original = h[1];
+  *out_n_fallback = h[2];
+  const uint32_t total = h[1] + h[2];
+  if (total > capacity) return LMB_ERR_CAPACITY;
+  if (total) {
+    if (!out_lines) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agent_avoidance_constraints: null out_lines");
+    CUDA_TRY(ctx, cudaMemcpy(out_lines, ctx->d_dbg_lines.p + (size_t)row * ctx->dbg_lines_per_row,
+                             (size_t)total * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+  }
   return LMB_OK;
 }
 

@@ -17,7 +17,8 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             uint32_t first_agent_global, uint32_t chunk_begin, uint32_t chunk_n,
                             uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
                             const AvoidRecord* char_records, const AvoidGrid& grid, const AvoidScratch& scratch,
-                            const uint32_t* max_radius_bits, float* staged_moves, cudaStream_t stream);
+                            const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
+                            cudaStream_t stream);
 }  // namespace lmb
 
 AgentArrays lmb_make_agent_arrays(lmb_ctx* ctx);
@@ -87,10 +88,23 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
     sc.base = ctx->d_avoid_scratch.p;
     sc.overflow = ctx->d_avoid_overflow.p;
     CUDA_TRY(ctx, cudaMemsetAsync(sc.overflow, 0, sizeof(uint32_t), s));
+    // debug-avoidance export: one row of 2 x max_lines per asking agent, "did not run" until written
+    AvoidDebug dbg{};
+    ctx->dbg_lines_per_row = 0;
+    if (ctx->dbg_rows) {
+      ctx->dbg_lines_per_row = 2 * sc.max_lines;
+      CUDA_TRY(ctx, ctx->d_dbg_header.reserve(4 * (size_t)ctx->dbg_rows));
+      CUDA_TRY(ctx, ctx->d_dbg_lines.reserve((size_t)ctx->dbg_rows * ctx->dbg_lines_per_row));
+      CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_dbg_header.p, 0, 4 * (size_t)ctx->dbg_rows * sizeof(uint32_t), s));
+      dbg.row_of = ctx->d_dbg_row_of.p;
+      dbg.header = ctx->d_dbg_header.p;
+      dbg.lines = ctx->d_dbg_lines.p;
+      dbg.lines_per_row = ctx->dbg_lines_per_row;
+    }
     launch_stage_moves(ag, persist, staged, s);
     for (uint32_t b = 0; b < n; b += chunk) {
       launch_avoidance_chunk(ctx->nav, ag, *o, dt, first, b, std::min(chunk, n - b), n_total, ctx->d_records.p,
-                             ctx->n_chars, ctx->d_char_records.p, grid, sc, max_radius_bits, staged, s);
+                             ctx->n_chars, ctx->d_char_records.p, grid, sc, max_radius_bits, staged, dbg, s);
       ctx->timings.kernel_launches += 1;
     }
     CUDA_TRY(ctx, cudaGetLastError());

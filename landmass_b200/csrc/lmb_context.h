@@ -129,6 +129,11 @@ struct lmb_ctx {
   DevBuf<AvoidRecord> d_records, d_char_records;
   DevBuf<uint32_t> d_cell_count, d_cell_start2, d_sorted, d_avoid_overflow;
   DevBuf<uint8_t> d_avoid_scratch;
+  // debug-avoidance export: agents that set LMB_AGENT_KEEP_AVOIDANCE_DATA (in upload order)
+  std::vector<uint32_t> h_dbg_row_of;  // [n_agents] row or LMB_NONE; empty = nobody asked
+  uint32_t dbg_rows = 0, dbg_lines_per_row = 0;
+  DevBuf<uint32_t> d_dbg_row_of, d_dbg_header;
+  DevBuf<float4> d_dbg_lines;
   DevBuf<float> d_bounds_tmp;
   uint32_t last_n_results = 0;
   uint32_t avoid_caps[5] = {64, 64, 128, 256, 256};  // neighbours, explore, border edges, cones, lines

@@ -201,6 +201,15 @@ struct AvoidScratch {
   uint32_t* overflow;  // device flag
 };
 
+// debug-avoidance export (debug.rs:415-503): the ORCA constraint lines of the agents that set
+// LMB_AGENT_KEEP_AVOIDANCE_DATA, one row per such agent.  row_of == nullptr: nobody asked.
+struct AvoidDebug {
+  const uint32_t* row_of;  // [n_agents] row of the agent or LMB_NONE
+  uint32_t* header;        // [rows][4] {ran this step, n original, n fallback, fell back}
+  float4* lines;           // [rows][lines_per_row] {point.xy, direction.xy}: originals, then fallbacks
+  uint32_t lines_per_row;
+};
+
 void launch_build_records(const AgentArrays& ag, const AgentPersist& persist, const lmb_options& o,
                           AvoidRecord* records, cudaStream_t stream);
 void launch_character_records(uint32_t n, const float* velocity, const float* radius, const float* points,

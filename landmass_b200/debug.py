@@ -4,8 +4,8 @@ Cold path: everything about the navigation data is drawn from the host copy (`Na
 per-agent parts come from three read-backs of the device state (`lmb_agent_path`,
 `lmb_agent_path_endpoints`, `lmb_agent_waypoints`).  Point / line / triangle types are plain tuples
 whose first element is the Rust variant name, e.g. `LineType.AgentCorridor(agent_id)` ==
-("AgentCorridor", agent_id).  The `debug-avoidance` feature (constraint export, debug.rs:415-503) is
-not mirrored.
+("AgentCorridor", agent_id).  The `debug-avoidance` feature (debug.rs:415-503) is mirrored by
+`draw_avoidance_data` over the read-back `lmb_agent_avoidance_constraints`.
 """
 from __future__ import annotations
 
@@ -197,3 +197,50 @@ def _draw_path(archipelago, debug_drawer, agent_id, position, path, index, waypo
                               [cs.from_landmass(points[index, :3]), cs.from_landmass(points[index, 3:])])
     debug_drawer.add_line(LineType.Waypoint(agent_id), [position, cs.from_landmass(waypoint)])
     debug_drawer.add_point(PointType.Waypoint(agent_id), cs.from_landmass(waypoint))
+
+
+# --- feature `debug-avoidance` (debug.rs:415-503) ---------------------------------------------------
+class ConstraintLine:
+    """debug.rs:415-426: a half-plane of valid velocities; `normal` points towards the valid side."""
+
+    __slots__ = ("point", "normal")
+
+    def __init__(self, point, normal):
+        self.point = np.asarray(point, dtype=f32)
+        self.normal = np.asarray(normal, dtype=f32)
+
+    @classmethod
+    def from_dodgy(cls, line):
+        """debug.rs:453-460: line = (point.x, point.y, direction.x, direction.y)."""
+        return cls((line[0], line[1]), (-line[3], line[2]))
+
+    def __repr__(self):
+        return f"ConstraintLine(point={self.point.tolist()}, normal={self.normal.tolist()})"
+
+
+class ConstraintKind:
+    """debug.rs:428-439."""
+
+    Original = "Original"
+    Fallback = "Fallback"
+
+
+class AvoidanceDrawer:
+    """debug.rs:441-451."""
+
+    def add_constraint(self, agent, constraint: ConstraintLine, kind):
+        raise NotImplementedError
+
+
+def draw_avoidance_data(archipelago, avoidance_drawer):
+    """debug.rs:462-503: reports the constraints of every agent that kept its avoidance data."""
+    for agent_id, agent in archipelago.agents.items():
+        data = agent._avoidance_data
+        if data is None:
+            continue
+        original = data[1]
+        fallback = data[2] if data[0] == "Fallback" else ()
+        for line in original:
+            avoidance_drawer.add_constraint(agent_id, ConstraintLine.from_dodgy(line), ConstraintKind.Original)
+        for line in fallback:
+            avoidance_drawer.add_constraint(agent_id, ConstraintLine.from_dodgy(line), ConstraintKind.Fallback)

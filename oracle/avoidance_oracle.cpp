@@ -645,8 +645,10 @@ size_t linear_program_2(const std::vector<Line>& lines, float radius, V2 opt_vel
   return lines.size();
 }
 
+// `last_proj` (optional) receives the projected constraint set of the last re-solve: the
+// Fallback.fallback_constraints of the debug-avoidance export (debug.rs:470-481).
 void linear_program_3(const std::vector<Line>& lines, size_t num_obst_lines, size_t begin_line,
-                      float radius, V2& result) {
+                      float radius, V2& result, std::vector<Line>* last_proj = nullptr) {
   float distance_ = 0.0f;
   for (size_t i = begin_line; i < lines.size(); i++) {
     if (det2(lines[i].direction, lines[i].point - result) > distance_) {
@@ -670,6 +672,7 @@ void linear_program_3(const std::vector<Line>& lines, size_t num_obst_lines, siz
                            result) < proj.size())
         result = temp;
       distance_ = det2(lines[i].direction, lines[i].point - result);
+      if (last_proj) *last_proj = proj;
     }
   }
 }
@@ -677,7 +680,8 @@ void linear_program_3(const std::vector<Line>& lines, size_t num_obst_lines, siz
 V2 compute_avoiding_velocity(const DodgyAgent& self, const std::vector<DodgyAgent>& neighbours,
                              const std::vector<Obstacle>& obstacles, V2 preferred_velocity,
                              float max_speed, float time_step, float obstacle_margin,
-                             float time_horizon, float obstacle_time_horizon) {
+                             float time_horizon, float obstacle_time_horizon,
+                             AvoidDebugData* debug = nullptr) {
   std::vector<Line> lines;
   for (const Obstacle& ob : obstacles)
     lines_for_obstacle(self, ob, obstacle_margin, obstacle_time_horizon, lines);
@@ -686,7 +690,18 @@ V2 compute_avoiding_velocity(const DodgyAgent& self, const std::vector<DodgyAgen
     lines.push_back(line_for_neighbour(self, nb, time_horizon, time_step));
   V2 result;
   size_t fail = linear_program_2(lines, max_speed, preferred_velocity, false, result);
-  if (fail < lines.size()) linear_program_3(lines, obstacle_line_count, fail, max_speed, result);
+  std::vector<Line> last_proj;
+  if (fail < lines.size())
+    linear_program_3(lines, obstacle_line_count, fail, max_speed, result, debug ? &last_proj : nullptr);
+  if (debug) {
+    // compute_avoiding_velocity_with_debug (avoidance.rs:163-171)
+    debug->ran = true;
+    debug->fell_back = fail < lines.size();
+    debug->original.clear();
+    debug->fallback.clear();
+    for (const Line& l : lines) debug->original.push_back({l.point.x, l.point.y, l.direction.x, l.direction.y});
+    for (const Line& l : last_proj) debug->fallback.push_back({l.point.x, l.point.y, l.direction.x, l.direction.y});
+  }
   return result;
 }
 
@@ -764,7 +779,7 @@ void apply_avoidance_to_agents(const NavData& nav, const std::vector<AvoidRec>& 
                                const std::vector<AgentPersist*>& persist,
                                const std::vector<Sampled>& agent_node,
                                const std::vector<CharacterIn>& characters, const lmb_options& opt,
-                               float delta_time) {
+                               float delta_time, std::vector<AvoidDebugData>* debug) {
   if (delta_time == 0.0f) delta_time = 1.0f;
   const size_t n = agents.size();
   KdTree3 agent_tree, character_tree;
@@ -812,7 +827,8 @@ void apply_avoidance_to_agents(const NavData& nav, const std::vector<AvoidRec>& 
     V2 preferred = xy(persist[i]->desired_move);
     V2 v = compute_avoiding_velocity(dodgy_of(self_g), neighbours, obstacles, preferred, agents[i].max_speed,
                                      delta_time, 0.0f, opt.avoidance_time_horizon,
-                                     opt.obstacle_avoidance_time_horizon);
+                                     opt.obstacle_avoidance_time_horizon,
+                                     debug && (agents[i].flags & LMB_AGENT_KEEP_AVOIDANCE_DATA) ? &(*debug)[i] : nullptr);
     persist[i]->desired_move = {v.x, v.y, 0.0f};
   }
 }

@@ -1009,7 +1009,8 @@ void Ctx::step_end(const lmb_options& opt, float dt, const lmb_agents_out& out) 
   if (!(flags & LMB_CONFIG_NO_AVOIDANCE)) {
     std::vector<AgentPersist*> persist(n);
     for (uint32_t i = 0; i < n; i++) persist[i] = &st(i);
-    apply_avoidance_to_agents(nav, halo, halo_first, ag, persist, f_agent_node, f_chars, opt, dt);
+    f_avoid_debug.assign(n, AvoidDebugData{});
+    apply_avoidance_to_agents(nav, halo, halo_first, ag, persist, f_agent_node, f_chars, opt, dt, &f_avoid_debug);
   }
 
   for (uint32_t i = 0; i < n; i++) {
@@ -1300,6 +1301,22 @@ int32_t orc_agent_waypoints(orc_ctx* h, uint32_t capacity, uint32_t* out_kind, f
     p[0] = w[i].point.x; p[1] = w[i].point.y; p[2] = w[i].point.z;
     p[3] = w[i].end_point.x; p[4] = w[i].end_point.y; p[5] = w[i].end_point.z;
   }
+  return LMB_OK;
+}
+
+int32_t orc_agent_avoidance_constraints(orc_ctx* h, uint32_t agent_index, uint32_t capacity, float* out_lines,
+                                        uint32_t* out_n_original, uint32_t* out_n_fallback, uint32_t* out_ran) {
+  *out_n_original = *out_n_fallback = *out_ran = 0;
+  if (agent_index >= h->c.f_agents.size()) return LMB_ERR_INVALID_ARGUMENT;
+  if (agent_index >= h->c.f_avoid_debug.size()) return LMB_OK;
+  const AvoidDebugData& d = h->c.f_avoid_debug[agent_index];
+  *out_ran = d.ran ? (d.fell_back ? 2 : 1) : 0;
+  *out_n_original = (uint32_t)d.original.size();
+  *out_n_fallback = (uint32_t)d.fallback.size();
+  if (d.original.size() + d.fallback.size() > capacity) return LMB_ERR_CAPACITY;
+  size_t k = 0;
+  for (const auto& l : d.original) { for (int c = 0; c < 4; c++) out_lines[4 * k + c] = l[c]; k++; }
+  for (const auto& l : d.fallback) { for (int c = 0; c < 4; c++) out_lines[4 * k + c] = l[c]; k++; }
   return LMB_OK;
 }
 

@@ -15,6 +15,8 @@ orc_ctx* orc_create(const lmb_navdata_desc* desc, uint32_t flags /* LMB_CONFIG_*
 void orc_destroy(orc_ctx*);
 /* replaces nav data, drops all paths (same contract as lmb_navdata_upload) */
 int32_t orc_agent_path_endpoints(orc_ctx*, uint32_t slot, float* out_start_point, float* out_end_point);
+int32_t orc_agent_avoidance_constraints(orc_ctx*, uint32_t agent_index, uint32_t capacity, float* out_lines,
+                                        uint32_t* out_n_original, uint32_t* out_n_fallback, uint32_t* out_ran);
 int32_t orc_agent_waypoints(orc_ctx*, uint32_t capacity, uint32_t* out_kind, float* out_points, uint32_t* out_link,
                             uint32_t* out_count);
 int32_t orc_navdata_upload(orc_ctx*, const lmb_navdata_desc* desc);

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE — internal types of the CPU oracle (see oracle/README.md).
 #pragma once
+#include <array>
 #include <cstdint>
 #include <map>
 #include <optional>
@@ -190,12 +191,17 @@ struct AvoidRec {  // 32 bytes, same layout as the device halo record
 };
 void build_avoid_records(const std::vector<AgentIn>& agents, const std::vector<AgentPersist*>& persist,
                          const std::vector<Sampled>& agent_node, const lmb_options& opt, AvoidRec* out);
+// debug-avoidance export (debug.rs:415-503): lines as {point.xy, direction.xy}
+struct AvoidDebugData {
+  bool ran = false, fell_back = false;
+  std::vector<std::array<float, 4>> original, fallback;
+};
 void apply_avoidance_to_agents(const NavData& nav, const std::vector<AvoidRec>& records, uint32_t first,
                                const std::vector<AgentIn>& agents,
                                const std::vector<AgentPersist*>& persist,
                                const std::vector<Sampled>& agent_node,
                                const std::vector<CharacterIn>& characters, const lmb_options& opt,
-                               float delta_time);
+                               float delta_time, std::vector<AvoidDebugData>* debug = nullptr);
 
 struct Ctx {
   uint32_t flags = 0;
@@ -214,6 +220,7 @@ struct Ctx {
     V3 point{0, 0, 0}, end_point{0, 0, 0};
   };
   std::vector<Waypoint> f_waypoints;
+  std::vector<AvoidDebugData> f_avoid_debug;  // per agent of the last step
   uint32_t halo_first = 0;
   void step_begin(const lmb_agents_in& in, const lmb_characters_in* chars, const lmb_options& opt, float dt,
                   uint32_t n_total, uint32_t first);

@@ -60,6 +60,7 @@ def test_constants_match_header():
     for name, value in [("LMB_ABI_VERSION", _abi.ABI_VERSION), ("LMB_AGENT_HAS_TARGET", _abi.AGENT_HAS_TARGET),
                         ("LMB_AGENT_PAUSED", _abi.AGENT_PAUSED), ("LMB_AGENT_RESET", _abi.AGENT_RESET),
                         ("LMB_AGENT_PERMIT_ALL_LINKS", _abi.AGENT_PERMIT_ALL_LINKS),
+                        ("LMB_AGENT_KEEP_AVOIDANCE_DATA", _abi.AGENT_KEEP_AVOIDANCE_DATA),
                         ("LMB_CONFIG_NO_AVOIDANCE", _abi.CONFIG_NO_AVOIDANCE)]:
         m = re.search(rf"#define {name} (\d+)u", text)
         assert m and int(m.group(1)) == value, name

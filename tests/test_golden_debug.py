@@ -3,11 +3,13 @@ draws_island_meshes_and_agents (44-393), draws_boundary_links (395-467), draws_a
 (469-547), draws_height_mesh (549-704), fails_to_draw_dirty_archipelago (706-751).  The per-agent
 lines come from the device read-backs (`lmb_agent_path`, `lmb_agent_path_endpoints`,
 `lmb_agent_waypoints`), so each test runs on the oracle and on the CUDA library.  The
-feature-gated draws_avoidance_data_when_requested (753-) has no counterpart."""
+feature-gated draws_avoidance_data_when_requested (753-909) reads `lmb_agent_avoidance_constraints`;
+it is the one reference golden that pins individual ORCA constraint lines (obstacle lines and a
+neighbour line, to 1e-3)."""
 import numpy as np
 import pytest
 
-from landmass_b200 import (Agent, AnimationLink, Archipelago, ArchipelagoOptions, DebugDrawError, HeightNavigationMesh,
+from landmass_b200 import (Agent, AnimationLink, ConstraintKind, ConstraintLine, draw_avoidance_data, Archipelago, ArchipelagoOptions, DebugDrawError, HeightNavigationMesh,
                            HeightPolygon, Island, LineType, PointType, Transform, TriangleType,
                            draw_archipelago_debug)
 from tests.helpers import valid_mesh
@@ -202,3 +204,67 @@ def test_fails_to_draw_dirty_archipelago(make_backend):  # debug_test.rs:706-751
     with pytest.raises(DebugDrawError) as e:
         draw_archipelago_debug(arch, d)
     assert e.value == DebugDrawError("NavDataDirty")
+
+
+def _equiv_line(expected: ConstraintLine, actual: ConstraintLine) -> bool:  # debug_test.rs:842-853
+    e, a = expected.normal.astype(np.float64), actual.normal.astype(np.float64)
+    angle = np.arctan2(e[0] * a[1] - e[1] * a[0], e[0] * a[0] + e[1] * a[1])  # Vec2::angle_to
+    if abs(angle) >= 1e-3:
+        return False
+    return abs(float(np.dot(expected.point.astype(np.float64) - actual.point.astype(np.float64), a))) < 1e-3
+
+
+def test_draws_avoidance_data_when_requested(make_backend):  # debug_test.rs:753-909
+    mesh = valid_mesh(dict(vertices=[(1.0, 1.0, 1.0), (11.0, 1.0, 1.0), (11.0, 11.0, 1.0), (1.0, 11.0, 1.0)],
+                           polygons=[[0, 1, 2, 3]], polygon_type_indices=[0]))
+    opts = ArchipelagoOptions.from_agent_radius(0.5)
+    opts.neighbourhood = 100.0
+    opts.avoidance_time_horizon = 100.0
+    opts.obstacle_avoidance_time_horizon = 100.0
+    arch = Archipelago(opts, backend=make_backend())
+    arch.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    a1 = Agent.create((6.0, 2.0, 1.0), (1.0, 1.0, 0.0), 0.5, 1.0, 1.0)
+    a1.current_target = (6.0, 10.0, 1.0)
+    a1.keep_avoidance_data = True
+    agent_1 = arch.add_agent(a1)
+    a2 = Agent.create((6.0, 10.0, 1.0), (0.0, 0.0, 0.0), 0.5, 1.0, 1.0)
+    a2.current_target = (6.0, 2.0, 1.0)
+    agent_2 = arch.add_agent(a2)
+    arch.update(1.0)
+
+    drawn = {}
+
+    class FakeAvoidanceDrawer:
+        def add_constraint(self, agent, constraint, kind):
+            drawn.setdefault(agent, {}).setdefault(kind, []).append(constraint)
+
+    draw_avoidance_data(arch, FakeAvoidanceDrawer())
+    # only one of the agents was rendered, with original constraints only
+    assert list(drawn.keys()) == [agent_1]
+    assert list(drawn[agent_1].keys()) == [ConstraintKind.Original]
+    actual = drawn[agent_1][ConstraintKind.Original]
+    nb = np.array([1.007905, 8.0], dtype=np.float64)
+    nb /= np.linalg.norm(nb)
+    expected = [
+        # lines for the edges of the nav mesh
+        ConstraintLine((0.05, 0.0), (-1.0, 0.0)), ConstraintLine((0.0, -0.01), (0.0, 1.0)),
+        ConstraintLine((-0.05, 0.0), (1.0, 0.0)), ConstraintLine((0.0, 0.09), (0.0, -1.0)),
+        # line for the other agent: normal = -normalize(1.007905, 8).perp(), perp(x, y) = (-y, x)
+        ConstraintLine((0.0, 0.0), (nb[1], -nb[0])),
+    ]
+    assert len(actual) == len(expected), actual
+    unmatched = list(actual)
+    for e in expected:  # unordered_elements_are!
+        hit = next((a for a in unmatched if _equiv_line(e, a)), None)
+        assert hit is not None, (e, actual)
+        unmatched.remove(hit)
+
+    # agent.avoidance_data = keep_avoidance_data.then_some(..) (avoidance.rs:172): asking later starts the
+    # export, no longer asking drops the data at the next update that runs avoidance for the agent
+    arch.get_agent(agent_2).keep_avoidance_data = True
+    arch.get_agent(agent_1).keep_avoidance_data = False
+    arch.update(1.0)
+    drawn.clear()
+    draw_avoidance_data(arch, FakeAvoidanceDrawer())
+    assert list(drawn.keys()) == [agent_2]
+    assert len(drawn[agent_2][ConstraintKind.Original]) == 5

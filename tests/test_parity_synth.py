@@ -221,3 +221,43 @@ def test_queries_between_resident_steps_leave_the_agents_alone():
     assert np.array_equal(o1["desired_velocity"], o2["desired_velocity"])
     for a, b in zip(p1, p2):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_avoidance_constraints_export():
+    """`lmb_agent_avoidance_constraints` (debug.rs:415-503): constraint lines of a dense crowd, CUDA vs
+    oracle — counts and Satisfied/Fallback exact, lines within 1e-4 — for two agents in three (the others
+    did not ask and report nothing)."""
+    mesh = synth.grid_mesh(12, 12)
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat)
+    n = 90  # dense enough that the 2-D program fails for about half of the agents (Fallback)
+    ag = synth.make_agents(mesh, n)
+    asked = np.arange(n) % 3 != 1
+    ag["flags"] = ag["flags"] | np.where(asked, np.uint32(_abi.AGENT_KEEP_AVOIDANCE_DATA), np.uint32(0))
+    opts = synth.default_options()
+    dt = 1.0 / 30.0
+    n_fallback = n_lines = 0
+    for frame in range(2):
+        og = gpu.step(ag, None, opts, dt)
+        oc = cpu.step(ag, None, opts, dt)
+        assert np.array_equal(og["state"], oc["state"])
+        for i in range(n):
+            ran_g, orig_g, fb_g, fell_g = gpu.agent_avoidance_constraints(i)
+            ran_c, orig_c, fb_c, fell_c = cpu.agent_avoidance_constraints(i)
+            if not asked[i]:
+                assert not ran_g and len(orig_g) == 0 and len(fb_g) == 0
+                continue
+            assert (ran_g, fell_g) == (ran_c, fell_c), f"agent {i}"
+            assert orig_g.shape == orig_c.shape and fb_g.shape == fb_c.shape, f"agent {i}"
+            for g, c in ((orig_g, orig_c), (fb_g, fb_c)):
+                if len(c):
+                    scale = np.maximum(np.abs(c).max(axis=1, keepdims=True), 1e-2)
+                    assert (np.abs(g - c) <= 1e-4 * scale + 1e-6).all(), f"agent {i}: {np.abs(g - c).max()}"
+            n_fallback += int(fell_c)
+            n_lines += len(orig_c)
+        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+        ag["velocity"] = oc["desired_velocity"].copy()
+        ag["position"] = ag["position"] + oc["desired_velocity"] * np.float32(dt)
+    assert 0 < n_fallback < 2 * asked.sum() and n_lines > 10 * asked.sum()
+    gpu.close()
+    cpu.close()
