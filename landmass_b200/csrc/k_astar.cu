@@ -53,7 +53,11 @@ __device__ __forceinline__ void ovf_clear(BestStore<2>& b) { b.count = 0; }
 //     use the run-time value (0 or 3).
 // LAYOUT: best_estimates layout (k_astar_common.cuh): 0 dense, 1 compact, 2 hashed.
 // HS: open-list entries per query in shared memory; BPS: blocks per SM the variant is sized for.
-template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT>
+// SIMPLE: one polygon type and no per-query cost overrides in this batch (the host checks), so
+//     every type cost is one value: no cost-table or override loads anywhere in the search.  Those
+//     loads share hardware scoreboards with the best[] probes, and their (never taken) paths made
+//     the first cost test wait for the probes it was meant to overlap (ncu: 15 % of stall samples).
+template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT, bool SIMPLE>
 __global__ void __launch_bounds__(AT_THREADS, BPS)
 k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
         const uint32_t* __restrict__ type_raw) {
@@ -71,6 +75,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   uint8_t* const slot_base = arena.base + (size_t)slot_c * arena.slot_stride;
   constexpr bool COMPACT = LAYOUT == 1;
   typedef typename BestStore<LAYOUT>::Raw BestRaw;
+  typedef typename BestStore<LAYOUT>::RootRaw BestRootRaw;
   BestStore<LAYOUT> bs;
   bs.init(slot_base, arena);
   uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
@@ -90,7 +95,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   const uint32_t kshift = KS ? KS : arena.kshift;
   const uint32_t kmask = (1u << kshift) - 1u;
   // one polygon type and no per-query overrides in this batch: every type cost is this value
-  const bool simple_cost = nav.n_types == 1 && !q.override_begin;
+  constexpr bool simple_cost = SIMPLE;
   const float cost0 = s_cost[0];
   const float4* __restrict__ edge_dist = reinterpret_cast<const float4*>(nav.edge_dist);
   const uint32_t ST_LINK0 = arena.n_ids;
@@ -99,13 +104,11 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
 
   // ---- lane state ----
   uint32_t phase = slot < arena.n_slots ? PH_IDLE : PH_EXIT;
-  uint32_t qid = 0, owner = 0, start_node = 0, end_node = 0;
+  uint32_t qid = 0, end_node = 0;
   V3 end_point{0.0f, 0.0f, 0.0f};
   float cheapest = 1.0f;
   uint32_t ov_begin = 0, ov_end = 0;  // this query's cost overrides
-  bool permit_all = true;
-  uint32_t n_nodes = 0, explored = 0, status = 1, success = 0;
-  uint32_t path_off = 0, path_len = 0;
+  uint32_t n_nodes = 0, explored = 0;
   // walk
   uint32_t w_node = 0, w_next = 0, w_pos = 0;
   uint32_t hmax = 0;  // largest open list of this query (sizes the next batch's launch shape)
@@ -122,8 +125,11 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
     return c;
   };
   // PermittedAnimationLinks::is_permitted (agent.rs:178-186)
+  // (owner and its permit-all flag are looked up here, in the rare link paths, instead of being carried
+  // in registers through every iteration: the kernel is at its register limit)
   auto is_kind_permitted = [&](uint32_t kind) -> bool {
-    if (permit_all) return true;
+    const uint32_t owner = q.owner ? q.owner[qid] : qid;
+    if (!q.owner_flags || (q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS)) return true;
     if (q.permitted_begin)
       for (uint32_t m = q.permitted_begin[owner]; m < q.permitted_begin[owner + 1]; m++)
         if (q.permitted_kind[m] == kind) return true;
@@ -141,6 +147,9 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   };
 
   for (;;) {
+    // results of a query that finishes in this iteration (every path into FINISH sets them in the
+    // iteration that publishes them, so they are not carried across iterations)
+    uint32_t status = 1, success = 0, path_off = 0, path_len = 0;
     // =========================== IDLE: fetch and set up a query ===========================
     if (phase == PH_IDLE) {
       const uint32_t qi = atomicAdd(&counters->queue_head, 1u);
@@ -148,19 +157,18 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         phase = PH_EXIT;
       } else {
         qid = q.list ? q.list[qi] : qi;
-        start_node = q.start_node[qid];
+        const uint32_t start_node = q.start_node[qid];
         end_node = q.end_node[qid];
         const V3 start_point{q.start_point[3 * (size_t)qid], q.start_point[3 * (size_t)qid + 1],
                              q.start_point[3 * (size_t)qid + 2]};
         end_point = {q.end_point[3 * (size_t)qid], q.end_point[3 * (size_t)qid + 1],
                      q.end_point[3 * (size_t)qid + 2]};
-        owner = q.owner ? q.owner[qid] : qid;
+        const uint32_t owner = q.owner ? q.owner[qid] : qid;
         ov_begin = ov_end = 0;
-        if (q.override_begin) {
+        if (!SIMPLE && q.override_begin) {
           ov_begin = q.override_begin[owner];
           ov_end = q.override_begin[owner + 1];
         }
-        permit_all = !q.owner_flags || (q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS);
         // cheapest_type_index_cost (pathfinding.rs:300-314)
         cheapest = 1.0f;
         for (uint32_t t = 0; t < nav.n_types; t++) {
@@ -204,9 +212,6 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           }
         }
         explored = 0;
-        success = 0;
-        status = 1;
-        path_off = path_len = 0;
         n_nodes = 0;
         heap.len = 0;
         phase = PH_FINISH;
@@ -244,7 +249,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         // ---- peek the root and issue this expansion's first loads BEFORE the pop's sift work:
         //      best[s] (stale test, HBM) and, with padded ids, the polygon's edge records (L2) ----
         const uint32_t s = heap.sm[0].w;
-        const BestRaw raw_s = bs.probe(s);
+        const BestRootRaw raw_s = bs.probe_root(s);
         const bool is_edge = s < ST_LINK0;
         EdgeRec r[4];
 #pragma unroll
@@ -256,7 +261,11 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         const bool preloaded = is_edge && kshift;
         float4 dtab = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // distances state midpoint -> edge midpoints
         if (is_edge) {
-          self = ld_rec(recs + s);
+          // KS == 2: the state's own record is one of the four loaded below, so it is not fetched on its
+          // own: a separate load costs a wait in FRONT of the pop (its `info` word was consumed at once, and
+          // the register of its unused `twin` word was recycled inside the pop's sift loop — a write that
+          // has to wait for the load), which is exactly the latency the early issue is there to hide.
+          if (KS != 2) self = ld_rec(recs + s);
           if (kshift) {
             first = s & ~kmask;
             cnt = kmask + 1u;
@@ -267,24 +276,43 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         }
 
         const HeapEntry cur = heap.pop();
+        // Nothing that consumes the loads above may be scheduled before the pop (the compiler does not
+        // know the sift is long and hoists e.g. the has-links test right behind its load, which then
+        // waits a full round trip in front of the pop): pass the loaded registers through an opaque
+        // statement the pop's shared-memory traffic cannot move across.
+        if (KS == 2) {
+          asm volatile(""
+                       : "+r"(r[0].twin), "+r"(r[1].twin), "+r"(r[2].twin), "+r"(r[3].twin), "+r"(r[0].info),
+                         "+r"(r[1].info), "+r"(r[2].info), "+r"(r[3].info)
+                       :
+                       : "memory");
+        }
 
         // ---- resolve (node, point, ignore step) — pathfinding.rs:93-143 ----
         uint32_t poly = 0, cur_type = 0, has_links = 0;
         uint32_t ignore_edge = LMB_NONE, ignore_link = LMB_NONE;
         V3 point{0.0f, 0.0f, 0.0f};
         if (is_edge) {
-          if (!kshift) {
-            first = self.first_edge;
-            cnt = self.info & 0xffu;
+          if (KS == 2) {
+            // own type / has-links are the same in every record of the polygon; `point` (the state's own
+            // midpoint) is only needed by the rare branches below, which pick it out of r[] themselves
+            poly = s >> 2;
+            cur_type = (r[0].info >> 8) & 0xffu;
+            has_links = (r[0].info >> 24) & 1u;
+          } else {
+            if (!kshift) {
+              first = self.first_edge;
+              cnt = self.info & 0xffu;
+            }
+            poly = self.poly;
+            cur_type = (self.info >> 8) & 0xffu;
+            has_links = (self.info >> 24) & 1u;
+            point = {self.mx, self.my, self.mz};
           }
-          poly = self.poly;
-          cur_type = (self.info >> 8) & 0xffu;
-          has_links = (self.info >> 24) & 1u;
-          point = {self.mx, self.my, self.mz};
           ignore_edge = s;
         } else if (s != ST_END) {
           if (s == ST_START) {
-            poly = start_node;
+            poly = q.start_node[qid];
             point = {q.start_point[3 * (size_t)qid], q.start_point[3 * (size_t)qid + 1],
                      q.start_point[3 * (size_t)qid + 2]};
           } else {
@@ -323,11 +351,17 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             if (preloaded) dtab = __ldg(edge_dist + ((size_t)s << (kshift - 2)) + (e0 >> 2));
           }
+          // type costs of the four neighbours first: whatever these read (cost table, overrides) is
+          // consumed before the probes are in flight
+          uint32_t passable = 0;
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (is_finite(cost_of((r[j].info >> 16) & 0xffu))) passable |= 1u << j;
           BestRaw praw[4];
           uint32_t cand = 0;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const bool ok = r[j].twin != LMB_NONE && first + e0 + j != ignore_edge && !to_end;
+            const bool ok = r[j].twin != LMB_NONE && first + e0 + j != ignore_edge && !to_end && ((passable >> j) & 1u);
             praw[j] = ok ? bs.probe_edge(r[j].twin) : BestRaw{};
             cand |= ok ? (1u << j) : 0u;
           }
@@ -343,14 +377,14 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           float nc[4], es[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            if (!is_finite(cost_of((r[j].info >> 16) & 0xffu))) cand &= ~(1u << j);
             const V3 mid{r[j].mx, r[j].my, r[j].mz};
             const float c = fmul(dj[j], cur_type_cost);
             nc[j] = fadd(cur_cost, c);
             es[j] = fadd(nc[j], fmul(distance(mid, end_point), cheapest));
           }
           if (e0 == 0) {
-            if (bs.value(s, raw_s) < cur.estimate) {  // stale (astar.rs:172-176)
+            // (cur.state == s: naming the popped entry keeps this use behind the pop)
+            if (bs.root_value(cur.state, raw_s) < cur.estimate) {  // stale (astar.rs:172-176)
               live = false;
               break;
             }
@@ -367,6 +401,9 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             }
             if (to_end) {
               // h(End) = 0
+              if (KS == 2 && is_edge)
+                point = {sel4(s & 3u, r[0].mx, r[1].mx, r[2].mx, r[3].mx), sel4(s & 3u, r[0].my, r[1].my, r[2].my, r[3].my),
+                         sel4(s & 3u, r[0].mz, r[1].mz, r[2].mz, r[3].mz)};
               float c = fmul(distance(point, end_point), cur_type_cost);
               float ncost = fadd(cur_cost, c);
               float est = fadd(ncost, 0.0f);
@@ -433,6 +470,10 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         }
         // ---- off-mesh links in ascending link index (canonical; pathfinding.rs:196-229) ----
         if (live && has_links && !overflow && !go_dense) {
+          if (KS == 2 && is_edge) {  // rare: re-read the own midpoint rather than keep r[] alive across the pushes
+            const EdgeRec own = ld_rec(recs + s);
+            point = {own.mx, own.my, own.mz};
+          }
           for (uint32_t k = nav.node_link_begin[poly]; k < nav.node_link_begin[poly + 1]; k++) {
             uint32_t l = nav.node_links[k];
             if (l == ignore_link) continue;
@@ -741,15 +782,22 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
   k_arena_init<<<148 * 8, 256, 0, stream>>>(arena);
 }
 
-template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT>
+template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT, bool SIMPLE>
 static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                            AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
+  if constexpr (!SIMPLE && BPS == 5) {
+    // with cost tables / overrides in play the kernel does not fit 96 registers without spilling (and
+    // spill reloads miss the shared-memory-sized L1): four blocks per SM at 113 registers instead
+    launch_astar_t<QPW, 48, 4, KS, LAYOUT, false>(nav, arena, q, pool, counters, type_raw, stream);
+    return;
+  } else {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
   const size_t smem = (size_t)HS * QPB * sizeof(uint4);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, LAYOUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, LAYOUT, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    cudaFuncSetAttribute(k_astar<QPW, HS, BPS, KS, LAYOUT, SIMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
@@ -766,7 +814,8 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
   uint32_t blocks = (slots + QPB - 1) / QPB;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar<QPW, HS, BPS, KS, LAYOUT><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  k_astar<QPW, HS, BPS, KS, LAYOUT, SIMPLE><<<blocks, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw);
+  }
 }
 
 // Launch shapes.  Only half the lanes of a warp own a query (16 per warp): the number of queries
@@ -798,10 +847,16 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
                   AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream) {
   if (q.n == 0) return;
   const bool k4 = arena.kshift == 2;
-#define LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, L)                                                          \
-  do {                                                                                            \
-    if (k4) launch_astar_t<QPW, HS, BPS, 2, L>(nav, arena, q, pool, counters, type_raw, stream);   \
-    else launch_astar_t<QPW, HS, BPS, 0, L>(nav, arena, q, pool, counters, type_raw, stream);      \
+  const bool simple = nav.n_types == 1 && !q.override_begin;  // the kernel's SIMPLE flag
+#define LMB_ASTAR_LAUNCH_S(QPW, HS, BPS, K, L)                                                             \
+  do {                                                                                                    \
+    if (simple) launch_astar_t<QPW, HS, BPS, K, L, true>(nav, arena, q, pool, counters, type_raw, stream);  \
+    else launch_astar_t<QPW, HS, BPS, K, L, false>(nav, arena, q, pool, counters, type_raw, stream);        \
+  } while (0)
+#define LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, L)           \
+  do {                                               \
+    if (k4) LMB_ASTAR_LAUNCH_S(QPW, HS, BPS, 2, L);   \
+    else LMB_ASTAR_LAUNCH_S(QPW, HS, BPS, 0, L);      \
   } while (0)
 #define LMB_ASTAR_LAUNCH(QPW, HS, BPS)                                  \
   do {                                                                  \
@@ -824,6 +879,7 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
     LMB_ASTAR_LAUNCH(16, 40, 5);
 #undef LMB_ASTAR_LAUNCH
 #undef LMB_ASTAR_LAUNCH_L
+#undef LMB_ASTAR_LAUNCH_S
   AStarArena a = arena;
   // corridors of the queries that finished in this launch: raw states -> (node, portal)
   uint32_t fix_blocks = (q.n + 7) / 8;

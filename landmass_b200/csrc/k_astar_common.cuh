@@ -150,6 +150,9 @@ struct BestStore<0> {
   __device__ __forceinline__ void init(uint8_t* slot_base, const AStarArena&) { b = reinterpret_cast<float*>(slot_base); }
   __device__ __forceinline__ Raw probe(uint32_t st) const { return __ldcg(b + st); }
   __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return __ldcg(b + st); }
+  typedef Raw RootRaw;
+  __device__ __forceinline__ RootRaw probe_root(uint32_t st) const { return probe(st); }
+  __device__ __forceinline__ float root_value(uint32_t, RootRaw r) const { return r; }
   __device__ __forceinline__ float value(uint32_t, Raw r) const { return r; }
   __device__ __forceinline__ float value_edge(uint32_t, Raw r) const { return r; }
   __device__ __forceinline__ float value_fast(uint32_t, Raw r, bool& need_table) const {
@@ -184,6 +187,27 @@ struct BestStore<1> {
     return make_uint2(__float_as_uint(__ldcg(sp + (st - n_ids))), BP_SPECIAL);
   }
   __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return __ldcg(bp + (st >> kshift)); }
+  // Probe of the open list's root, issued before the pop and consumed after it.  Two loads into
+  // separate registers and no write to either before the consumer: `probe()` patches .y of a
+  // special state's result right behind the (predicated-off) 64-bit load of the same register
+  // pair, and that write waits for the load — the whole memory latency, in front of the pop
+  // it was issued early to overlap with (ncu: 13.8 % of the kernel's stall samples).
+  struct RootRaw {
+    uint2 e;
+    float special;
+  };
+  __device__ __forceinline__ RootRaw probe_root(uint32_t st) const {
+    const bool edge = st < n_ids;
+    RootRaw r;
+    r.e = __ldcg(bp + (edge ? st >> kshift : 0u));
+    r.special = 0.0f;
+    if (!edge) r.special = __ldcg(sp + (st - n_ids));
+    return r;
+  }
+  __device__ __forceinline__ float root_value(uint32_t st, const RootRaw& r) const {
+    if (st >= n_ids) return r.special;
+    return value_edge(st, r.e);
+  }
   __device__ __forceinline__ uint32_t ovf_slot(uint32_t st) const { return (st * 2654435761u) >> 7; }
   __device__ float ovf_get(uint32_t st) const {
     for (uint32_t h = ovf_slot(st);; h++) {
@@ -245,6 +269,9 @@ struct BestStore<2> {
   __device__ __forceinline__ uint32_t home(uint32_t st) const { return (st * 2654435761u) >> 4; }
   __device__ __forceinline__ Raw probe(uint32_t st) const { return __ldcg(tab + (home(st) & mask)); }
   __device__ __forceinline__ Raw probe_edge(uint32_t st) const { return probe(st); }
+  typedef Raw RootRaw;
+  __device__ __forceinline__ RootRaw probe_root(uint32_t st) const { return probe(st); }
+  __device__ __forceinline__ float root_value(uint32_t st, RootRaw r) const { return value(st, r); }
   __device__ float find(uint32_t st) const {
     for (uint32_t h = home(st) + 1;; h++) {
       const uint2 e = __ldcg(tab + (h & mask));
