@@ -39,7 +39,7 @@ B_STEP = 240.0  # algorithmic bytes per steady agent-update
 # DRAM bytes per explored node of k_astar, from the one `ncu --set full` capture of a fully loaded
 # launch (profiles/r01_ncu_astar_loaded.md: dram read + write / explored nodes).  The bench-size
 # launch itself cannot be captured: kernel replay would have to save and restore its ~100 GB arena.
-NCU_DRAM_BYTES_PER_EXPLORED = 113.9
+NCU_DRAM_BYTES_PER_EXPLORED = 114.4
 
 
 def measured_peak_gbs():
