@@ -867,7 +867,13 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   int dev = 0, sm_count = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  if (q.n <= 8u * (uint32_t)sm_count)
+  // LMB_ASTAR_SHAPE=large: tests run the large-batch shapes (the benchmarked ones) at sizes the oracle can check
+  const char* shape_env = getenv("LMB_ASTAR_SHAPE");  // (read per launch: a test sets it for its own launches only)
+  const bool force_large = shape_env && shape_env[0] == 'l';
+  if (force_large) {
+    if (big_heap) LMB_ASTAR_LAUNCH(8, 96, 4);
+    else LMB_ASTAR_LAUNCH(16, 40, 5);
+  } else if (q.n <= 8u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(1, 1536, 2);  // few queries: one per warp, the whole open list on chip
   else if (q.n <= 32u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(4, 384, 2);

@@ -189,3 +189,43 @@ def test_step_more_agents_than_slots_longest_first_order():
         for slot in range(0, n, 97):
             gp, cp = gpu.agent_path(slot), cpu.agent_path(slot)
             assert np.array_equal(gp[0], cp[0]) and np.array_equal(gp[1], cp[1])
+
+
+@pytest.mark.parametrize("case", ["maze_simple", "maze_overrides", "grid_simple", "grid_types", "loopy_maze_types"])
+def test_large_batch_shapes_against_the_oracle(case, monkeypatch):
+    """The launch shapes of large batches — `<16, 40, 5, SIMPLE>` (the benchmarked kernel: one polygon
+    type, no overrides), `<16, 48, 4>` (cost tables / per-query overrides in play) and `<8, 96, 4>` (large
+    open lists) — only run above ~19 000 queries, which the oracle cannot check in seconds.
+    LMB_ASTAR_SHAPE=large forces them here: 2 500 queries on 192 slots, bit-exact."""
+    monkeypatch.setenv("LMB_ASTAR_SHAPE", "large")
+    rng = np.random.Generator(np.random.PCG64(4242))
+    nq = 2500
+    overrides = None
+    if case.startswith("maze"):
+        types = None
+        mesh = synth.maze_mesh(20)
+        if case == "loopy_maze_types":
+            mesh = synth.loopy_maze_mesh(20, 60)   # cycles: dense layout, larger open lists
+    else:  # (not a forest: the first batch takes the large-open-list shape)
+        types = (np.add.outer(np.arange(24) // 4, np.arange(24) // 4) % 3).astype(np.uint32)
+        mesh = synth.grid_mesh(24, 24, types=types if case == "grid_types" else None)
+    flat = synth.single_island_flat(mesh)
+    if case in ("grid_types", "loopy_maze_types"):
+        flat = dict(flat)
+        if case == "loopy_maze_types":
+            flat["poly_type"] = (np.arange(mesh.n_polys) % 3).astype(np.uint32)
+        flat["n_type_costs"] = 3
+        flat["type_cost_index"] = np.array([0, 1, 2], dtype=np.uint32)
+        flat["type_cost_value"] = np.array([1.0, 2.5, 0.5], dtype=np.float32)
+    gpu, cpu = backends(flat, astar_slots=192)
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    if case == "maze_overrides":
+        overrides = [({0: float(1.0 + (i % 5))} if i % 2 else None) for i in range(nq)]
+    g = gpu.find_paths(sn, sp, en, ep, overrides=overrides, path_capacity=1 << 21)
+    c = cpu.find_paths(sn, sp, en, ep, overrides=overrides, path_capacity=1 << 21)
+    for a, b, name in zip(g, c, NAMES):
+        assert np.array_equal(a, b), name
+    assert g[0].all()
+    gpu.close()
+    cpu.close()
