@@ -785,10 +785,11 @@ void launch_arena_init(const AStarArena& arena, cudaStream_t stream) {
 template <uint32_t QPW, uint32_t HS, uint32_t BPS, uint32_t KS, int LAYOUT, bool SIMPLE>
 static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                            AStarCounters* counters, const uint32_t* type_raw, cudaStream_t stream) {
-  if constexpr (!SIMPLE && BPS == 5) {
-    // with cost tables / overrides in play the kernel does not fit 96 registers without spilling (and
-    // spill reloads miss the shared-memory-sized L1): four blocks per SM at 113 registers instead
-    launch_astar_t<QPW, 48, 4, KS, LAYOUT, false>(nav, arena, q, pool, counters, type_raw, stream);
+  if constexpr ((!SIMPLE || KS != 2) && BPS == 5) {
+    // with cost tables / overrides in play (or without the quad specialisation) the kernel does not fit 96
+    // registers without spilling (and spill reloads miss the shared-memory-sized L1): four blocks per SM at
+    // 113 registers instead
+    launch_astar_t<QPW, 48, 4, KS, LAYOUT, SIMPLE>(nav, arena, q, pool, counters, type_raw, stream);
     return;
   } else {
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
