@@ -1341,6 +1341,29 @@ int32_t orc_next_straight_point(orc_ctx* h, uint32_t path_len, const uint32_t* n
   return LMB_OK;
 }
 
+// Path::find_index_of_node / find_index_of_node_rev (path.rs:402-446) on a hand-made corridor, as a flat index.
+int32_t orc_path_find_index_of_node(orc_ctx* h, uint32_t path_len, const uint32_t* nodes, const uint32_t* portals,
+                                    uint32_t node, uint32_t reverse, uint32_t* out_found, uint32_t* out_index) {
+  Path path = Path::from_flat(h->c.nav, path_len, nodes, portals);
+  if (node >= h->c.nav.n_polys) return LMB_ERR_INVALID_ARGUMENT;
+  auto r = reverse ? path.find_index_of_node_rev(h->c.nav, node) : path.find_index_of_node(h->c.nav, node);
+  *out_found = r ? 1 : 0;
+  *out_index = r ? path.flat_index(*r) : LMB_NONE;
+  return LMB_OK;
+}
+
+// geometry.rs:176-189
+int32_t orc_project_point_to_line_segment(const float* point, const float* start, const float* end,
+                                          float* out_point, float* out_fraction) {
+  auto r = project_point_to_line_segment({point[0], point[1], point[2]}, {start[0], start[1], start[2]},
+                                         {end[0], end[1], end[2]});
+  out_point[0] = r.first.x;
+  out_point[1] = r.first.y;
+  out_point[2] = r.first.z;
+  *out_fraction = r.second;
+  return LMB_OK;
+}
+
 int32_t orc_astar_adjacency(uint32_t n_states, const uint32_t* adj_begin, const float* adj_cost,
                             const int32_t* adj_action, const uint32_t* adj_state,
                             const float* heuristic, uint32_t start, uint32_t end,

@@ -57,6 +57,10 @@ int32_t orc_agent_path(orc_ctx*, uint32_t slot, uint32_t* out_nodes, uint32_t* o
 /* Funnel (path.rs:227-368) on an explicit flattened path; returns the next
  * waypoint from (start_index,start_point) to (end_index,end_point).
  * out_kind: 0 = Waypoint, 1 = AnimationLink. */
+int32_t orc_path_find_index_of_node(orc_ctx*, uint32_t path_len, const uint32_t* nodes, const uint32_t* portals,
+                                    uint32_t node, uint32_t reverse, uint32_t* out_found, uint32_t* out_index);
+int32_t orc_project_point_to_line_segment(const float* point, const float* start, const float* end,
+                                          float* out_point, float* out_fraction);
 int32_t orc_next_straight_point(orc_ctx*, uint32_t path_len, const uint32_t* nodes,
                                 const uint32_t* portals, uint32_t start_index,
                                 const float* start_point, uint32_t end_index, const float* end_point,

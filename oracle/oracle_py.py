@@ -118,6 +118,28 @@ class OracleBackend(CBackend):
             _abi.ptr(ep, _abi.f32p), C.byref(oi), C.byref(ok), _abi.ptr(op, _abi.f32p)))
         return oi.value, ok.value, op
 
+    def path_find_index_of_node(self, nodes, portals, node, reverse=False):
+        """Path::find_index_of_node[_rev] (path.rs:402-446) on a hand-made corridor: flat index or None."""
+        nodes = _abi.as_u32(nodes)
+        portals = _abi.as_u32(portals)
+        found, idx = C.c_uint32(), C.c_uint32()
+        self.lib.orc_path_find_index_of_node.restype = C.c_int32
+        self._check(self.lib.orc_path_find_index_of_node(
+            self.ctx, C.c_uint32(len(nodes)), _abi.ptr(nodes, _abi.u32p), _abi.ptr(portals, _abi.u32p),
+            C.c_uint32(node), C.c_uint32(1 if reverse else 0), C.byref(found), C.byref(idx)))
+        return idx.value if found.value else None
+
+    @staticmethod
+    def project_point_to_line_segment(point, start, end):
+        """geometry.rs:176-189 -> (point (3,), fraction)."""
+        lib = load()
+        lib.orc_project_point_to_line_segment.restype = C.c_int32
+        p, a, b = _abi.as_f32(point), _abi.as_f32(start), _abi.as_f32(end)
+        out, frac = np.zeros(3, dtype=np.float32), C.c_float()
+        lib.orc_project_point_to_line_segment(_abi.ptr(p, _abi.f32p), _abi.ptr(a, _abi.f32p), _abi.ptr(b, _abi.f32p),
+                                              _abi.ptr(out, _abi.f32p), C.byref(frac))
+        return out, frac.value
+
     def borders_to_obstacles(self, point, node, distance_limit):
         p = _abi.as_f32(point)
         cap_o, cap_v = 256, 8192

@@ -219,3 +219,27 @@ def test_reached_target_agent_has_different_avoidance(make_backend):  # avoidanc
     assert x1 - 0.25 < 0.01 and x2 - 0.75 < 0.01, (x1, x2)
     # and both did move aside, the mover three times as far as the stander
     assert abs(x1) > 0.1 and abs(x2) > 0.3 and abs(abs(x2) / abs(x1) - 3.0) < 0.5, (x1, x2)
+
+
+def test_switching_nav_mesh_to_fewer_vertices_does_not_result_in_panic(make_backend):  # avoidance_test.rs:855-925
+    """Two copies of a hexagon with redundant vertices, the second shifted so that its border is slightly
+    misaligned (the boundary link clips new vertices into both nodes: `ModifiedNode`s, which avoidance walks);
+    then the first island's mesh is replaced by one with fewer vertices and the archipelago updated again."""
+    from landmass_b200 import XY, Agent
+
+    redundant = valid_mesh(dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 2.0), (0.0, 2.0), (0.0, 0.6), (0.0, 0.2)],
+                                polygons=[[0, 1, 2, 3, 4, 5]], polygon_type_indices=[0]), cs=XY)
+    simplified = valid_mesh(dict(vertices=[(0.0, 0.0), (1.0, 0.0), (1.0, 2.0), (0.0, 2.0)],
+                                 polygons=[[0, 1, 2, 3]], polygon_type_indices=[0]), cs=XY)
+    arch = new_archipelago(make_backend(), cs=XY)
+    island_1 = arch.add_island(Island(Transform((0.0, 0.0), 0.0), redundant))
+    arch.add_island(Island(Transform((1.0, 0.25), 0.0), redundant))
+    a = Agent.create((0.5, 1.25), (0.0, 0.0), 0.5, 1.0, 1.0, cs=XY)
+    a.current_target = (1.5, 1.25)
+    agent = arch.add_agent(a)
+    arch.update(0.01)
+    # "ensures that pathing + avoidance is running"
+    assert tuple(np.asarray(arch.get_agent(agent).get_desired_velocity())) == (1.0, 0.0)
+    arch.get_island_mut(island_1).set_nav_mesh(simplified)
+    arch.update(0.01)
+    assert tuple(np.asarray(arch.get_agent(agent).get_desired_velocity())) == (1.0, 0.0)

@@ -1,5 +1,7 @@
 """Funnel / straight-path known answers — transcribed from crates/landmass/src/path_test.rs:59-243
-(explicit corridors on rotated islands; oracle only, the C ABI takes no hand-made corridors) and
+(explicit corridors on rotated islands; oracle only, the C ABI takes no hand-made corridors),
+path_test.rs:919-1089 (`find_index_of_node[_rev]` on a corridor across three islands), geometry_test.rs:547-589
+(`project_point_to_line_segment`, the funnel's projection onto an animation link's start edge) and
 query_test.rs:273-327 (`Archipelago::find_path` across three islands; oracle and CUDA)."""
 import math
 
@@ -217,3 +219,59 @@ def test_query_finds_path_across_islands(make_backend):  # query_test.rs:272-327
     assert succ[0] == 1 and list(kind) == [0, 0, 0]
     got = [tuple(float(x) for x in p[:2]) for p in pts]
     assert got == [(10.5, 10.5), (12.0, 11.0), (12.5, 11.25)]
+
+
+def _three_island_corridor(oracle_backend):
+    """path_test.rs:919-975: corridor [island 1: 3] -link-> [island 2: 2, 1] -link-> [island 3: 0], a fourth
+    island that is not on the path.  The reference builds the `Path` by hand; here the islands are real (five
+    quads each, far apart) and the two off-mesh links are animation links, so that the flat corridor is one the
+    oracle can turn back into segments."""
+    from landmass_b200 import AnimationLink
+
+    arch = new_archipelago(oracle_backend, cs=XY)
+    strip = dict(vertices=[(float(x), float(y)) for x in range(6) for y in (0, 1)],
+                 polygons=[[2 * k, 2 * k + 2, 2 * k + 3, 2 * k + 1] for k in range(5)], polygon_type_indices=[0] * 5)
+    islands = [arch.add_island(Island(Transform((0.0, 10.0 * k), 0.0), valid_mesh(strip, cs=XY))) for k in range(4)]
+    # island 1 polygon 3 -> island 2 polygon 2, island 2 polygon 1 -> island 3 polygon 0
+    keys = [arch.add_animation_link(AnimationLink(start_edge=((3.2, 0.5), (3.8, 0.5)), end_edge=((2.2, 10.5), (2.8, 10.5)),
+                                                  cost=1.0, kind=0, bidirectional=False)),
+            arch.add_animation_link(AnimationLink(start_edge=((1.2, 10.5), (1.8, 10.5)), end_edge=((0.2, 20.5), (0.8, 20.5)),
+                                                  cost=1.0, kind=0, bidirectional=False))]
+    arch._sync_navdata()
+    f = arch._flat
+    link_of = {}
+    for l in range(f["n_links"]):
+        if f["link_kind"][l] == _abi.LINK_ANIMATION:
+            link_of[int(f["link_anim_id"][l])] = l
+    node = lambda isl, poly: arch.node_id(islands[isl - 1], poly)  # noqa: E731
+    nodes = [node(1, 3), node(2, 2), node(2, 1), node(3, 0)]
+    assert f["link_dst_node"][link_of[keys[0].idx]] == node(2, 2) and f["link_dst_node"][link_of[keys[1].idx]] == node(3, 0)
+    portals = [_abi.PORTAL_LINK | link_of[keys[0].idx], 0, _abi.PORTAL_LINK | link_of[keys[1].idx], _abi.NONE]
+    return nodes, portals, node
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+def test_indices_in_path_are_found(oracle_backend, reverse):  # path_test.rs:919-1003 / 1005-1089
+    nodes, portals, node = _three_island_corridor(oracle_backend)
+    find = lambda isl, poly: oracle_backend.path_find_index_of_node(nodes, portals, node(isl, poly), reverse)  # noqa: E731
+    # PathIndex {segment, portal} as a flat index: {2, 0} = 3, {0, 0} = 0, {1, 1} = 2
+    assert find(3, 0) == 3
+    assert find(1, 3) == 0
+    assert find(2, 1) == 2
+    # missing NodeRefs
+    assert find(3, 3) is None
+    assert find(1, 1) is None
+    assert find(4, 4) is None
+
+
+def test_project_point_to_line_segment():  # geometry_test.rs:547-589
+    from oracle.oracle_py import OracleBackend
+
+    proj = OracleBackend.project_point_to_line_segment
+    for point, seg, want_p, want_f in [
+            ((0.0, 0.0, 0.0), ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0)), (0.5, 0.5, 0.0), 0.5),
+            ((2.0, -2.0, 0.0), ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0)), (1.0, 0.0, 0.0), 0.0),
+            ((-2.0, 2.0, 0.0), ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0)), (0.0, 1.0, 0.0), 1.0),
+            ((-2.0, 2.0, 0.0), ((10.0, 3.0, 0.0), (10.0, 3.0, 0.0)), (10.0, 3.0, 0.0), 0.0)]:
+        p, f = proj(point, seg[0], seg[1])
+        assert tuple(p) == tuple(np.float32(want_p)) and f == want_f
