@@ -1080,6 +1080,7 @@ int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* a, const lmb_charac
   CUDA_TRY(ctx, ctx->d_flags.upload(a->flags, n, s));
   // rows of the debug-avoidance export, in agent order
   ctx->dbg_rows = 0;
+  ctx->dbg_lines_per_row = 0;  // no avoidance has run for these agents yet: nothing to report
   ctx->h_dbg_row_of.clear();
   for (uint32_t i = 0; i < n; i++) {
     if (!(a->flags[i] & LMB_AGENT_KEEP_AVOIDANCE_DATA)) continue;

@@ -111,4 +111,15 @@ def test_error_paths_of_the_newer_entry_points():
     gpu.step(ag, None, synth.default_options(), 0.1)
     kind, pts, link = gpu.agent_waypoints()
     assert len(kind) == 4 and set(kind.tolist()) <= {0, _abi.NONE}
+    # lmb_agent_avoidance_constraints: nobody asked -> nothing; out of range -> error; asked but no step
+    # since the upload -> "did not run"; after a step -> the lines
+    assert gpu.agent_avoidance_constraints(0)[0] is False
+    with pytest.raises(_native.NativeError):
+        gpu.agent_avoidance_constraints(4)
+    ag["flags"] = ag["flags"] | np.uint32(_abi.AGENT_KEEP_AVOIDANCE_DATA)
+    gpu.agents_upload(ag, None)
+    assert gpu.agent_avoidance_constraints(1)[0] is False
+    gpu.step_resident(synth.default_options(), 0.1)
+    ran, original, fallback, fell_back = gpu.agent_avoidance_constraints(1)
+    assert ran and original.shape[1] == 4 and len(original) >= 3
     gpu.close()
