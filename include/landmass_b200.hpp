@@ -1,0 +1,459 @@
+// landmass_b200.hpp — C++17 host mirror of the reference's per-frame surface, over the C ABI.
+//
+// The reference is a Rust crate; this image has no Rust toolchain, so the host side that sits above
+// include/landmass_b200.h exists twice: the complete mirror in Python (landmass_b200/*.py: validation,
+// island linking, animation links, queries, debug drawing — what the parity tests drive) and this
+// header, which covers the part of the API a game loop touches every frame, in the compiled language
+// a maintainer would port to Rust line by line:
+//
+//   Archipelago<..>::{add,remove,get}_{agent,character}, update(dt), get_pathing_results   lib.rs:96-268, 270-534
+//   Agent (pub fields + state accessors), AgentState, TargetReachedCondition,              agent.rs:24-310
+//   PermittedAnimationLinks, ReachedAnimationLink
+//   Character                                                                              character.rs:14-31
+//   ArchipelagoOptions::from_agent_radius                                                  lib.rs:63-93, coords.rs:148-158
+//   DenseSlotMap (iteration = dense order, swap-remove, versioned keys)                     slotmap 1.0.7
+//
+// What `update` does here is what `Archipelago::update` keeps on the host: pack the
+// agents in DenseSlotMap order, one lmb_step, scatter desired velocity / state / reached link back,
+// translate `PathingResult.agent` from an index to the AgentId.  Navigation data enters as the
+// flattened `lmb_navdata_desc` (the output of `NavigationData::flatten`, produced by the Python mirror
+// or by the caller's own port of nav_data.rs) — validation and island linking are NOT mirrored here.
+//
+// Coordinates are landmass-internal (XYZ, z up): `CoordinateSystem::to_landmass` stays with the caller.
+// The entry points are reached through a table of function pointers so that the same code runs on the
+// CUDA library (`cuda_backend()`, the only product backend — there is no CPU fallback) and, in tests
+// only, on the CPU oracle, whose step functions have the same signatures.
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "landmass_b200.h"
+
+namespace landmass_b200 {
+
+using Vec3 = std::array<float, 3>;
+
+// agent.rs:24-47 (same order as the Rust enum and as lmb_agent_state)
+enum class AgentState : uint32_t {
+  Idle = LMB_STATE_IDLE,
+  ReachedTarget = LMB_STATE_REACHED_TARGET,
+  ReachedAnimationLink = LMB_STATE_REACHED_ANIMATION_LINK,
+  UsingAnimationLink = LMB_STATE_USING_ANIMATION_LINK,
+  Moving = LMB_STATE_MOVING,
+  AgentNotOnNavMesh = LMB_STATE_AGENT_NOT_ON_NAV_MESH,
+  TargetNotOnNavMesh = LMB_STATE_TARGET_NOT_ON_NAV_MESH,
+  NoPath = LMB_STATE_NO_PATH,
+  Paused = LMB_STATE_PAUSED,
+};
+
+// agent.rs:136-160
+struct TargetReachedCondition {
+  uint32_t kind = LMB_REACH_DISTANCE;
+  std::optional<float> distance;  // None = the agent's radius
+  static TargetReachedCondition Distance(std::optional<float> d = std::nullopt) { return {LMB_REACH_DISTANCE, d}; }
+  static TargetReachedCondition VisibleAtDistance(std::optional<float> d = std::nullopt) {
+    return {LMB_REACH_VISIBLE_AT_DISTANCE, d};
+  }
+  static TargetReachedCondition StraightPathDistance(std::optional<float> d = std::nullopt) {
+    return {LMB_REACH_STRAIGHT_PATH_DISTANCE, d};
+  }
+};
+
+// agent.rs:170-187
+struct PermittedAnimationLinks {
+  bool all = true;
+  std::vector<uint32_t> kinds;  // used when !all; kept ascending when packed
+};
+
+// agent.rs:112-119
+struct ReachedAnimationLink {
+  uint32_t link_id;
+  Vec3 start_point, end_point;
+};
+
+struct NotReachedAnimationLinkError : std::runtime_error {  // agent.rs:477-487
+  NotReachedAnimationLinkError() : std::runtime_error("the agent has not reached an animation link") {}
+};
+struct NotUsingAnimationLinkError : std::runtime_error {
+  NotUsingAnimationLinkError() : std::runtime_error("the agent is not using an animation link") {}
+};
+
+// agent.rs:50-310
+class Agent {
+ public:
+  Vec3 position{}, velocity{};
+  float radius = 0.0f, desired_speed = 0.0f, max_speed = 0.0f;
+  std::optional<Vec3> current_target;
+  TargetReachedCondition target_reached_condition = TargetReachedCondition::Distance();
+  std::optional<float> animation_link_reached_distance;
+  PermittedAnimationLinks permitted_animation_links;
+  bool paused = false;
+  bool keep_avoidance_data = false;  // feature `debug-avoidance`; read back with lmb_agent_avoidance_constraints
+
+  static Agent create(Vec3 position, Vec3 velocity, float radius, float desired_speed, float max_speed) {
+    Agent a;
+    a.position = position;
+    a.velocity = velocity;
+    a.radius = radius;
+    a.desired_speed = desired_speed;
+    a.max_speed = max_speed;
+    return a;
+  }
+  // agent.rs:232-262: costs must be positive; returns whether the override was taken / existed
+  bool override_type_index_cost(uint32_t type_index, float cost) {
+    if (!(cost > 0.0f)) return false;
+    for (auto& kv : overrides_)
+      if (kv.first == type_index) {
+        kv.second = cost;
+        return true;
+      }
+    overrides_.emplace_back(type_index, cost);
+    return true;
+  }
+  bool remove_overridden_type_index_cost(uint32_t type_index) {
+    for (size_t i = 0; i < overrides_.size(); i++)
+      if (overrides_[i].first == type_index) {
+        overrides_.erase(overrides_.begin() + (long)i);
+        return true;
+      }
+    return false;
+  }
+  const std::vector<std::pair<uint32_t, float>>& get_type_index_cost_overrides() const { return overrides_; }
+  const Vec3& get_desired_velocity() const { return current_desired_move_; }
+  AgentState state() const { return state_; }
+  const std::optional<ReachedAnimationLink>& reached_animation_link() const { return current_animation_link_; }
+  void start_animation_link() {  // agent.rs:277-286
+    if (!current_animation_link_) throw NotReachedAnimationLinkError();
+    using_animation_link_ = true;
+  }
+  void end_animation_link() {  // agent.rs:290-299
+    if (!using_animation_link_) throw NotUsingAnimationLinkError();
+    using_animation_link_ = false;
+  }
+  bool is_using_animation_link() const { return using_animation_link_; }
+
+ private:
+  template <class B>
+  friend class BasicArchipelago;
+  std::vector<std::pair<uint32_t, float>> overrides_;
+  Vec3 current_desired_move_{};
+  AgentState state_ = AgentState::Idle;
+  std::optional<ReachedAnimationLink> current_animation_link_;
+  bool using_animation_link_ = false;
+};
+
+// character.rs:14-31
+struct Character {
+  Vec3 position{}, velocity{};
+  float radius = 0.0f;
+};
+
+// lib.rs:63-93 with PointSampleDistance3d::from_agent_radius (coords.rs:148-158) already folded into
+// CorePointSampleDistance (coords.rs:209-226)
+struct ArchipelagoOptions {
+  lmb_options abi{};
+  static ArchipelagoOptions from_agent_radius(float radius) {
+    ArchipelagoOptions o;
+    o.abi.horizontal_distance = 0.2f * radius;
+    o.abi.distance_above = 0.5f * radius;
+    o.abi.distance_below = radius;
+    o.abi.vertical_preference_ratio = 2.0f;
+    o.abi.neighbourhood = 10.0f * radius;
+    o.abi.avoidance_time_horizon = 0.5f;
+    o.abi.obstacle_avoidance_time_horizon = 0.25f;
+    o.abi.reached_destination_avoidance_responsibility = 0.1f;
+    return o;
+  }
+};
+
+// slotmap::KeyData: index + version (occupied versions are odd)
+struct Key {
+  uint32_t idx = 0, version = 0;
+  bool operator==(const Key& o) const { return idx == o.idx && version == o.version; }
+  bool operator!=(const Key& o) const { return !(*this == o); }
+};
+using AgentId = Key;
+using CharacterId = Key;
+
+// slotmap::DenseSlotMap: iteration order = dense storage order, removal swaps the last element in.
+// This order is the agent order of the step, of `pathing_results` and of avoidance's tie-breaks.
+template <class T>
+class DenseSlotMap {
+ public:
+  DenseSlotMap() { slots_.push_back({0u, 0u}); }  // slot 0 is slotmap's sentinel
+  Key insert(T value) {
+    const uint32_t dense = (uint32_t)keys_.size();
+    const uint32_t idx = free_head_;
+    if (idx < slots_.size()) {
+      free_head_ = slots_[idx].dense_or_next;
+      slots_[idx].version |= 1u;
+      slots_[idx].dense_or_next = dense;
+    } else {
+      slots_.push_back({1u, dense});
+      free_head_ = (uint32_t)slots_.size();
+    }
+    const Key key{idx, slots_[idx].version};
+    keys_.push_back(key);
+    values_.push_back(std::move(value));
+    return key;
+  }
+  std::optional<T> remove(Key key) {
+    const int64_t d = dense_index(key);
+    if (d < 0) return std::nullopt;
+    slots_[key.idx].version += 1u;  // even = vacant
+    slots_[key.idx].dense_or_next = free_head_;
+    free_head_ = key.idx;
+    T value = std::move(values_[(size_t)d]);
+    const Key last = keys_.back();
+    keys_[(size_t)d] = last;
+    values_[(size_t)d] = std::move(values_.back());
+    keys_.pop_back();
+    values_.pop_back();
+    if ((size_t)d < keys_.size()) slots_[last.idx].dense_or_next = (uint32_t)d;
+    return value;
+  }
+  T* get(Key key) {
+    const int64_t d = dense_index(key);
+    return d < 0 ? nullptr : &values_[(size_t)d];
+  }
+  const T* get(Key key) const {
+    const int64_t d = dense_index(key);
+    return d < 0 ? nullptr : &values_[(size_t)d];
+  }
+  int64_t dense_index(Key key) const {
+    if (key.idx >= slots_.size() || slots_[key.idx].version != key.version) return -1;
+    return (int64_t)slots_[key.idx].dense_or_next;
+  }
+  size_t size() const { return keys_.size(); }
+  const std::vector<Key>& keys() const { return keys_; }
+  std::vector<T>& values() { return values_; }
+  const std::vector<T>& values() const { return values_; }
+
+ private:
+  struct Slot {
+    uint32_t version, dense_or_next;
+  };
+  std::vector<Slot> slots_;
+  std::vector<Key> keys_;
+  std::vector<T> values_;
+  uint32_t free_head_ = 1;
+};
+
+// lib.rs:538-547
+struct PathingResult {
+  AgentId agent;
+  bool success;
+  uint32_t explored_nodes;
+};
+
+struct Error : std::runtime_error {
+  int32_t status;
+  Error(int32_t st, const std::string& what) : std::runtime_error(what), status(st) {}
+};
+
+// The entry points `update` needs.  `Ctx` is the backend's opaque context type.
+struct CudaBackend {
+  using Ctx = lmb_ctx;
+  static int32_t navdata_upload(Ctx* c, const lmb_navdata_desc* d) { return lmb_navdata_upload(c, d); }
+  static int32_t step(Ctx* c, const lmb_agents_in* a, const lmb_characters_in* ch, const lmb_options* o, float dt,
+                      const lmb_agents_out* out) {
+    return lmb_step(c, a, ch, o, dt, out);
+  }
+  static int32_t pathing_results(Ctx* c, lmb_pathing_result* out, uint32_t cap, uint32_t* n) {
+    return lmb_pathing_results(c, out, cap, n);
+  }
+  static std::string last_error(Ctx* c) {
+    const char* e = lmb_last_error(c);
+    return e ? e : "";
+  }
+};
+
+// `Archipelago` (lib.rs:49-61) over a context the caller created (lmb_create) and destroys.
+template <class Backend>
+class BasicArchipelago {
+ public:
+  ArchipelagoOptions archipelago_options;
+
+  BasicArchipelago(typename Backend::Ctx* ctx, ArchipelagoOptions options, uint32_t max_agents)
+      : archipelago_options(options), ctx_(ctx), max_agents_(max_agents) {}
+
+  // the flattened navigation data (NavigationData::flatten); every island counts as changed
+  void set_navigation_data(const lmb_navdata_desc& desc) { check(Backend::navdata_upload(ctx_, &desc), "lmb_navdata_upload"); }
+
+  AgentId add_agent(Agent agent) {  // lib.rs:96-101
+    const AgentId id = agents_.insert(std::move(agent));
+    if (id.idx >= max_agents_) {
+      agents_.remove(id);
+      throw Error(LMB_ERR_CAPACITY, "more live agents than the context's max_agents");
+    }
+    return id;
+  }
+  void remove_agent(AgentId id) {  // lib.rs:103-108: panics on a stale id
+    if (!agents_.remove(id)) throw std::out_of_range("Agent should be present in the archipelago");
+  }
+  Agent* get_agent_mut(AgentId id) { return agents_.get(id); }
+  const Agent* get_agent(AgentId id) const { return agents_.get(id); }
+  const std::vector<AgentId>& get_agent_ids() const { return agents_.keys(); }
+
+  CharacterId add_character(Character c) { return characters_.insert(c); }  // lib.rs:125-128
+  void remove_character(CharacterId id) {
+    if (!characters_.remove(id)) throw std::out_of_range("Character should be present in the archipelago");
+  }
+  Character* get_character_mut(CharacterId id) { return characters_.get(id); }
+  const std::vector<CharacterId>& get_character_ids() const { return characters_.keys(); }
+
+  const std::vector<PathingResult>& get_pathing_results() const { return pathing_results_; }  // lib.rs:233-236
+
+  // `Archipelago::update` (lib.rs:270-534): pack -> lmb_step -> scatter
+  void update(float delta_time) {
+    const std::vector<AgentId>& keys = agents_.keys();
+    std::vector<Agent>& ag = agents_.values();
+    const uint32_t n = (uint32_t)ag.size();
+    slot_.resize(n), flags_.resize(n), radius_.resize(n), desired_speed_.resize(n), max_speed_.resize(n);
+    reach_condition_.resize(n), reach_distance_.resize(n), anim_reach_.resize(n);
+    position_.resize(3 * (size_t)n), velocity_.resize(3 * (size_t)n), target_.assign(3 * (size_t)n, 0.0f);
+    override_begin_.assign((size_t)n + 1, 0u), permitted_begin_.assign((size_t)n + 1, 0u);
+    override_type_.clear(), override_cost_.clear(), permitted_kind_.clear();
+    if (device_version_.size() < max_agents_) device_version_.assign(max_agents_, 0u);
+    std::vector<uint32_t> live(n);
+    for (uint32_t i = 0; i < n; i++) {
+      const Agent& a = ag[i];
+      uint32_t f = 0;
+      // a slot that was vacated and re-used carries another agent's corridor on the device
+      if (device_version_[keys[i].idx] != keys[i].version) f |= LMB_AGENT_RESET;
+      live[i] = keys[i].idx;
+      if (a.current_target) {
+        f |= LMB_AGENT_HAS_TARGET;
+        for (int k = 0; k < 3; k++) target_[3 * (size_t)i + k] = (*a.current_target)[k];
+      }
+      if (a.paused) f |= LMB_AGENT_PAUSED;
+      if (a.using_animation_link_) f |= LMB_AGENT_USING_ANIMATION_LINK;
+      if (a.keep_avoidance_data) f |= LMB_AGENT_KEEP_AVOIDANCE_DATA;
+      if (a.permitted_animation_links.all) {
+        f |= LMB_AGENT_PERMIT_ALL_LINKS;
+      } else {
+        std::vector<uint32_t> kinds = a.permitted_animation_links.kinds;
+        sort_unique(kinds);
+        permitted_kind_.insert(permitted_kind_.end(), kinds.begin(), kinds.end());
+      }
+      permitted_begin_[i + 1] = (uint32_t)permitted_kind_.size();
+      slot_[i] = keys[i].idx;
+      flags_[i] = f;
+      for (int k = 0; k < 3; k++) {
+        position_[3 * (size_t)i + k] = a.position[k];
+        velocity_[3 * (size_t)i + k] = a.velocity[k];
+      }
+      radius_[i] = a.radius;
+      desired_speed_[i] = a.desired_speed;
+      max_speed_[i] = a.max_speed;
+      reach_condition_[i] = a.target_reached_condition.kind;
+      reach_distance_[i] = a.target_reached_condition.distance ? *a.target_reached_condition.distance : -1.0f;
+      anim_reach_[i] = a.animation_link_reached_distance ? *a.animation_link_reached_distance : -1.0f;
+      // HashMap in the reference: ascending type index is the canonical order of the ABI
+      std::vector<std::pair<uint32_t, float>> ov = a.overrides_;
+      for (size_t x = 1; x < ov.size(); x++)
+        for (size_t y = x; y > 0 && ov[y].first < ov[y - 1].first; y--) std::swap(ov[y], ov[y - 1]);
+      for (const auto& kv : ov) {
+        override_type_.push_back(kv.first);
+        override_cost_.push_back(kv.second);
+      }
+      override_begin_[i + 1] = (uint32_t)override_type_.size();
+    }
+    // versions of the slots that are alive now; everything else is forgotten (a later re-use resets)
+    std::vector<uint32_t> versions(max_agents_, 0u);
+    for (uint32_t i = 0; i < n; i++) versions[live[i]] = keys[i].version;
+    device_version_.swap(versions);
+
+    const std::vector<Character>& ch = characters_.values();
+    const uint32_t nc = (uint32_t)ch.size();
+    char_position_.resize(3 * (size_t)nc), char_velocity_.resize(3 * (size_t)nc), char_radius_.resize(nc);
+    for (uint32_t i = 0; i < nc; i++) {
+      for (int k = 0; k < 3; k++) {
+        char_position_[3 * (size_t)i + k] = ch[i].position[k];
+        char_velocity_[3 * (size_t)i + k] = ch[i].velocity[k];
+      }
+      char_radius_[i] = ch[i].radius;
+    }
+
+    lmb_agents_in in{};
+    in.n = n;
+    in.slot = slot_.data(), in.flags = flags_.data();
+    in.position = position_.data(), in.velocity = velocity_.data(), in.target = target_.data();
+    in.radius = radius_.data(), in.desired_speed = desired_speed_.data(), in.max_speed = max_speed_.data();
+    in.reach_condition = reach_condition_.data(), in.reach_distance = reach_distance_.data();
+    in.anim_link_reach_distance = anim_reach_.data();
+    in.override_begin = override_begin_.data(), in.override_type = override_type_.data();
+    in.override_cost = override_cost_.data();
+    in.permitted_begin = permitted_begin_.data(), in.permitted_kind = permitted_kind_.data();
+    lmb_characters_in cin{};
+    cin.n = nc;
+    cin.position = char_position_.data(), cin.velocity = char_velocity_.data(), cin.radius = char_radius_.data();
+    out_velocity_.resize(3 * (size_t)n + 1), out_state_.resize((size_t)n + 1), out_link_id_.resize((size_t)n + 1);
+    out_link_start_.resize(3 * (size_t)n + 1), out_link_end_.resize(3 * (size_t)n + 1);
+    lmb_agents_out out{};
+    out.desired_velocity = out_velocity_.data(), out.state = out_state_.data();
+    out.reached_link_id = out_link_id_.data(), out.reached_link_start = out_link_start_.data();
+    out.reached_link_end = out_link_end_.data();
+    check(Backend::step(ctx_, &in, &cin, &archipelago_options.abi, delta_time, &out), "lmb_step");
+
+    for (uint32_t i = 0; i < n; i++) {
+      Agent& a = ag[i];
+      a.current_desired_move_ = {out_velocity_[3 * (size_t)i], out_velocity_[3 * (size_t)i + 1],
+                                 out_velocity_[3 * (size_t)i + 2]};
+      a.state_ = (AgentState)out_state_[i];
+      if (out_link_id_[i] != LMB_NONE) {
+        ReachedAnimationLink r;
+        r.link_id = out_link_id_[i];
+        for (int k = 0; k < 3; k++) {
+          r.start_point[k] = out_link_start_[3 * (size_t)i + k];
+          r.end_point[k] = out_link_end_[3 * (size_t)i + k];
+        }
+        a.current_animation_link_ = r;
+      } else {
+        a.current_animation_link_.reset();
+      }
+    }
+    // lib.rs:406-410: one result per agent that re-planned, in agent order
+    std::vector<lmb_pathing_result> raw((size_t)n + 1);
+    uint32_t n_results = 0;
+    check(Backend::pathing_results(ctx_, raw.data(), (uint32_t)raw.size(), &n_results), "lmb_pathing_results");
+    pathing_results_.clear();
+    for (uint32_t k = 0; k < n_results; k++)
+      pathing_results_.push_back({keys[raw[k].agent], raw[k].success != 0, raw[k].explored_nodes});
+  }
+
+ private:
+  static void sort_unique(std::vector<uint32_t>& v) {
+    for (size_t x = 1; x < v.size(); x++)
+      for (size_t y = x; y > 0 && v[y] < v[y - 1]; y--) std::swap(v[y], v[y - 1]);
+    size_t w = 0;
+    for (size_t x = 0; x < v.size(); x++)
+      if (w == 0 || v[x] != v[w - 1]) v[w++] = v[x];
+    v.resize(w);
+  }
+  void check(int32_t st, const char* what) {
+    if (st != LMB_OK) throw Error(st, std::string(what) + ": " + Backend::last_error(ctx_));
+  }
+
+  typename Backend::Ctx* ctx_;
+  uint32_t max_agents_;
+  DenseSlotMap<Agent> agents_;
+  DenseSlotMap<Character> characters_;
+  std::vector<PathingResult> pathing_results_;
+  std::vector<uint32_t> device_version_;
+  // packed per-frame arrays (kept between frames: no allocation in steady state)
+  std::vector<uint32_t> slot_, flags_, reach_condition_, override_begin_, override_type_, permitted_begin_,
+      permitted_kind_, out_state_, out_link_id_;
+  std::vector<float> position_, velocity_, target_, radius_, desired_speed_, max_speed_, reach_distance_, anim_reach_,
+      override_cost_, char_position_, char_velocity_, char_radius_, out_velocity_, out_link_start_, out_link_end_;
+};
+
+using Archipelago = BasicArchipelago<CudaBackend>;
+
+}  // namespace landmass_b200

@@ -1,0 +1,109 @@
+// Test harness for include/landmass_b200.hpp (the C++ host mirror): runs a scripted game loop through
+// `BasicArchipelago` on a backend bound at run time (function pointers handed in by the Python test: the
+// CPU oracle here, the CUDA library on a GPU box) and records a per-frame trace that the test compares with
+// the Python mirror running the same script.  TEST INFRASTRUCTURE.
+#include <cstdint>
+#include <cstring>
+
+#include "landmass_b200.hpp"
+
+namespace lb = landmass_b200;
+
+struct FnBackend {
+  using Ctx = void;
+  static inline int32_t (*p_upload)(void*, const lmb_navdata_desc*) = nullptr;
+  static inline int32_t (*p_step)(void*, const lmb_agents_in*, const lmb_characters_in*, const lmb_options*, float,
+                                  const lmb_agents_out*) = nullptr;
+  static inline int32_t (*p_results)(void*, lmb_pathing_result*, uint32_t, uint32_t*) = nullptr;
+  static int32_t navdata_upload(Ctx* c, const lmb_navdata_desc* d) { return p_upload(c, d); }
+  static int32_t step(Ctx* c, const lmb_agents_in* a, const lmb_characters_in* ch, const lmb_options* o, float dt,
+                      const lmb_agents_out* out) {
+    return p_step(c, a, ch, o, dt, out);
+  }
+  static int32_t pathing_results(Ctx* c, lmb_pathing_result* out, uint32_t cap, uint32_t* n) {
+    return p_results(c, out, cap, n);
+  }
+  static std::string last_error(Ctx*) { return ""; }
+};
+
+extern "C" {
+
+// The script (mirrored line by line in tests/test_host_mirror_cpp.py):
+//   agents A (1,1)->(11,1.1) r=1, B (11,1.1)->(1,1) r=1, C (6,8)->(6,2) r=0.5 with a cost override and
+//   StraightPathDistance(0.25); one character at (6,4) drifting in +x.  Frame 10: A is removed; frame 12: D is
+//   added (re-uses A's slot index with a new version); frames 20-24: B is paused.
+// Trace per frame: [4 agents][position xyz, desired velocity xyz, state] (absent: -1000 / 99), then the number
+// of pathing results and the sum of their explored nodes, then for each result its agent key idx + version.
+int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_results, const lmb_navdata_desc* desc,
+                      uint32_t max_agents, uint32_t frames, float dt, float* trace_f, uint32_t* trace_u,
+                      char* error, uint32_t error_cap) {
+  FnBackend::p_upload = reinterpret_cast<decltype(FnBackend::p_upload)>(fn_upload);
+  FnBackend::p_step = reinterpret_cast<decltype(FnBackend::p_step)>(fn_step);
+  FnBackend::p_results = reinterpret_cast<decltype(FnBackend::p_results)>(fn_results);
+  try {
+    lb::BasicArchipelago<FnBackend> arch(ctx, lb::ArchipelagoOptions::from_agent_radius(0.5f), max_agents);
+    arch.set_navigation_data(*desc);
+    auto make = [](lb::Vec3 pos, lb::Vec3 target, float radius) {
+      lb::Agent a = lb::Agent::create(pos, {0.0f, 0.0f, 0.0f}, radius, 1.0f, 2.0f);
+      a.current_target = target;
+      a.target_reached_condition = lb::TargetReachedCondition::Distance(0.01f);
+      return a;
+    };
+    lb::AgentId ids[4];
+    bool alive[4] = {true, true, true, false};
+    ids[0] = arch.add_agent(make({1.0f, 1.0f, 0.0f}, {11.0f, 1.1f, 0.0f}, 1.0f));
+    ids[1] = arch.add_agent(make({11.0f, 1.1f, 0.0f}, {1.0f, 1.0f, 0.0f}, 1.0f));
+    {
+      lb::Agent c = make({6.0f, 8.0f, 0.0f}, {6.0f, 2.0f, 0.0f}, 0.5f);
+      c.target_reached_condition = lb::TargetReachedCondition::StraightPathDistance(0.25f);
+      c.override_type_index_cost(0, 3.0f);
+      ids[2] = arch.add_agent(c);
+    }
+    lb::CharacterId ch = arch.add_character({{6.0f, 4.0f, 0.0f}, {0.2f, 0.0f, 0.0f}, 0.5f});
+    for (uint32_t f = 0; f < frames; f++) {
+      if (f == 10) {
+        arch.remove_agent(ids[0]);
+        alive[0] = false;
+      }
+      if (f == 12) {
+        ids[3] = arch.add_agent(make({2.0f, 12.0f, 0.0f}, {12.0f, 12.0f, 0.0f}, 0.5f));
+        alive[3] = true;
+      }
+      if (f == 20) arch.get_agent_mut(ids[1])->paused = true;
+      if (f == 25) arch.get_agent_mut(ids[1])->paused = false;
+      arch.update(dt);
+      float* tf = trace_f + (size_t)f * 4 * 6;
+      uint32_t* tu = trace_u + (size_t)f * (4 + 2 + 2 * 4);
+      for (int k = 0; k < 4; k++) {
+        if (!alive[k]) {
+          for (int c = 0; c < 6; c++) tf[6 * k + c] = -1000.0f;
+          tu[k] = 99u;
+          continue;
+        }
+        lb::Agent* a = arch.get_agent_mut(ids[k]);
+        a->velocity = a->get_desired_velocity();
+        for (int c = 0; c < 3; c++) a->position[c] = a->position[c] + a->velocity[c] * dt;
+        for (int c = 0; c < 3; c++) tf[6 * k + c] = a->position[c], tf[6 * k + 3 + c] = a->velocity[c];
+        tu[k] = (uint32_t)a->state();
+      }
+      lb::Character* c = arch.get_character_mut(ch);
+      for (int k = 0; k < 3; k++) c->position[k] = c->position[k] + c->velocity[k] * dt;
+      const auto& pr = arch.get_pathing_results();
+      uint32_t explored = 0;
+      for (const auto& r : pr) explored += r.explored_nodes;
+      tu[4] = (uint32_t)pr.size();
+      tu[5] = explored;
+      for (int k = 0; k < 4; k++) {
+        tu[6 + 2 * k] = k < (int)pr.size() ? pr[(size_t)k].agent.idx : 0u;
+        tu[7 + 2 * k] = k < (int)pr.size() ? pr[(size_t)k].agent.version : 0u;
+      }
+    }
+  } catch (const std::exception& e) {
+    std::strncpy(error, e.what(), error_cap - 1);
+    error[error_cap - 1] = 0;
+    return -1;
+  }
+  return 0;
+}
+
+}  // extern "C"
