@@ -12,12 +12,14 @@
 //   Character                                                                              character.rs:14-31
 //   ArchipelagoOptions::from_agent_radius                                                  lib.rs:63-93, coords.rs:148-158
 //   DenseSlotMap (iteration = dense order, swap-remove, versioned keys)                     slotmap 1.0.7
+//   NavigationMesh::validate -> ValidNavigationMesh, ValidationError, Transform              nav_mesh.rs:19-35, 131-407
 //
 // What `update` does here is what `Archipelago::update` keeps on the host: pack the
 // agents in DenseSlotMap order, one lmb_step, scatter desired velocity / state / reached link back,
 // translate `PathingResult.agent` from an index to the AgentId.  Navigation data enters as the
-// flattened `lmb_navdata_desc` (the output of `NavigationData::flatten`, produced by the Python mirror
-// or by the caller's own port of nav_data.rs) — validation and island linking are NOT mirrored here.
+// flattened `lmb_navdata_desc`: `NavigationMesh::validate` and a single-island `NavigationData` are
+// mirrored below (SingleIslandNavigationData); worlds of several linked islands, animation links and
+// height meshes bring the descriptor the Python mirror (or the caller's port of nav_data.rs) flattens.
 //
 // Coordinates are landmass-internal (XYZ, z up): `CoordinateSystem::to_landmass` stays with the caller.
 // The entry points are reached through a table of function pointers so that the same code runs on the
@@ -243,6 +245,232 @@ class DenseSlotMap {
   std::vector<Key> keys_;
   std::vector<T> values_;
   uint32_t free_head_ = 1;
+};
+
+// ---------------------------------------------------------------------------------------------
+// NavigationMesh::validate (nav_mesh.rs:19-35, 187-407) and a single-island NavigationData.
+// Island LINKING (boundary links, modified nodes, animation links: nav_data.rs:326-1180) is mirrored in
+// Python only; a world of one island — or one whose flattened descriptor the caller brings — is what this
+// header can feed on its own.  Height meshes are not mirrored here either.
+// ---------------------------------------------------------------------------------------------
+struct ValidationError : std::runtime_error {  // nav_mesh.rs:131-162
+  enum Kind {
+    TypeIndicesHaveWrongLength,
+    NotEnoughVerticesInPolygon,
+    InvalidVertexIndexInPolygon,
+    DegenerateEdgeInPolygon,
+    DoublyConnectedEdge,
+    ConcavePolygon
+  } kind;
+  size_t a, b;  // the variant's payload (polygon index / the two vertex indices / the two lengths)
+  ValidationError(Kind k, size_t a_, size_t b_ = 0)
+      : std::runtime_error("invalid navigation mesh (ValidationError kind " + std::to_string((int)k) + ")"),
+        kind(k), a(a_), b(b_) {}
+};
+
+// nav_mesh.rs:483-583 as flat arrays (island-local, landmass coordinates), the layout lmb_navdata_desc takes
+struct ValidNavigationMesh {
+  std::vector<float> vertices;              // [V*3]
+  std::vector<uint32_t> poly_edge_begin;    // [P+1]
+  std::vector<uint32_t> poly_verts;         // [E] vertex of edge e's start (edge e runs vertex[e] -> vertex[e+1])
+  std::vector<uint32_t> edge_neighbor;      // [E] polygon across the edge or LMB_NONE
+  std::vector<uint32_t> edge_reverse;       // [E] index of the same edge inside the neighbour
+  std::vector<uint32_t> poly_type, poly_region;  // [P]
+  std::vector<float> poly_bounds;           // [P*6]
+  std::vector<float> poly_center;           // [P*3]
+  bool bounds_empty = true;
+  std::array<float, 6> mesh_bounds{};       // min xyz, max xyz
+  std::vector<std::pair<uint32_t, uint32_t>> boundary_edges;  // (polygon, edge), ascending
+  size_t n_polys() const { return poly_type.size(); }
+};
+
+struct NavigationMesh {  // nav_mesh.rs:19-35 (vertices already in landmass coordinates; polygons counter-clockwise)
+  std::vector<Vec3> vertices;
+  std::vector<std::vector<uint32_t>> polygons;
+  std::vector<uint32_t> polygon_type_indices;
+
+  ValidNavigationMesh validate() const {
+    using VE = ValidationError;
+    const size_t P = polygons.size(), V = vertices.size();
+    if (P != polygon_type_indices.size()) throw VE(VE::TypeIndicesHaveWrongLength, P, polygon_type_indices.size());
+    ValidNavigationMesh m;
+    for (const Vec3& v : vertices) m.vertices.insert(m.vertices.end(), v.begin(), v.end());
+    m.poly_edge_begin.assign(P + 1, 0u);
+    // the reference discovers errors polygon by polygon: size, vertex range, then per edge degenerate /
+    // doubly connected / concave (nav_mesh.rs:246-319)
+    struct EdgeUse {
+      uint32_t polygon, edge;
+    };
+    struct EdgeSlot {
+      uint64_t key;
+      EdgeUse first;
+      bool has_second = false;
+      EdgeUse second{};
+    };
+    std::vector<EdgeSlot> table;  // open addressing on the (lo, hi) vertex pair
+    size_t total_edges = 0;
+    for (const auto& poly : polygons) total_edges += poly.size();
+    size_t cap = 16;
+    while (cap < 2 * total_edges + 2) cap <<= 1;
+    table.assign(cap, EdgeSlot{~0ull, {0, 0}, false, {0, 0}});
+    auto slot_of = [&](uint64_t key) -> EdgeSlot& {
+      size_t h = (size_t)((key * 0x9E3779B97F4A7C15ull) >> 17) & (cap - 1);
+      while (table[h].key != ~0ull && table[h].key != key) h = (h + 1) & (cap - 1);
+      return table[h];
+    };
+    for (size_t p = 0; p < P; p++) {
+      const auto& poly = polygons[p];
+      const size_t n = poly.size();
+      if (n < 3) throw VE(VE::NotEnoughVerticesInPolygon, p);
+      for (uint32_t v : poly)
+        if (v >= V) throw VE(VE::InvalidVertexIndexInPolygon, p);
+      for (size_t e = 0; e < n; e++) {
+        const uint32_t a = poly[e], b = poly[(e + 1) % n], l = poly[(e + n - 1) % n];
+        if (a == b) throw VE(VE::DegenerateEdgeInPolygon, p);
+        const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+        EdgeSlot& s = slot_of(((uint64_t)lo << 32) | hi);
+        if (s.key == ~0ull) {
+          s.key = ((uint64_t)lo << 32) | hi;
+          s.first = {(uint32_t)p, (uint32_t)e};
+        } else if (!s.has_second) {
+          s.has_second = true;
+          s.second = {(uint32_t)p, (uint32_t)e};
+        } else {
+          throw VE(VE::DoublyConnectedEdge, lo, hi);
+        }
+        // convexity at vertex a (nav_mesh.rs:300-319), f32
+        const float lx = vertices[l][0] - vertices[a][0], ly = vertices[l][1] - vertices[a][1];
+        const float rx = vertices[b][0] - vertices[a][0], ry = vertices[b][1] - vertices[a][1];
+        const float pd = rx * ly - ry * lx, dt = rx * lx + ry * ly;
+        if (!(pd > 0.0f || (pd == 0.0f && dt < 0.0f))) throw VE(VE::ConcavePolygon, p);
+      }
+      m.poly_edge_begin[p + 1] = m.poly_edge_begin[p] + (uint32_t)n;
+      m.poly_verts.insert(m.poly_verts.end(), poly.begin(), poly.end());
+    }
+    const size_t E = m.poly_verts.size();
+    m.edge_neighbor.assign(E, LMB_NONE);
+    m.edge_reverse.assign(E, 0u);
+    for (const EdgeSlot& s : table) {
+      if (s.key == ~0ull || !s.has_second) continue;
+      const uint32_t e1 = m.poly_edge_begin[s.first.polygon] + s.first.edge;
+      const uint32_t e2 = m.poly_edge_begin[s.second.polygon] + s.second.edge;
+      m.edge_neighbor[e1] = s.second.polygon, m.edge_reverse[e1] = s.second.edge;
+      m.edge_neighbor[e2] = s.first.polygon, m.edge_reverse[e2] = s.first.edge;
+    }
+    // regions: connected components numbered by first appearance (nav_mesh.rs:354-364)
+    m.poly_region.assign(P, LMB_NONE);
+    m.poly_type = polygon_type_indices;
+    uint32_t next_region = 0;
+    std::vector<uint32_t> stack;
+    for (size_t p = 0; p < P; p++) {
+      if (m.poly_region[p] != LMB_NONE) continue;
+      m.poly_region[p] = next_region;
+      stack.push_back((uint32_t)p);
+      while (!stack.empty()) {
+        const uint32_t q = stack.back();
+        stack.pop_back();
+        for (uint32_t e = m.poly_edge_begin[q]; e < m.poly_edge_begin[q + 1]; e++) {
+          const uint32_t nb = m.edge_neighbor[e];
+          if (nb != LMB_NONE && m.poly_region[nb] == LMB_NONE) {
+            m.poly_region[nb] = next_region;
+            stack.push_back(nb);
+          }
+        }
+      }
+      next_region++;
+    }
+    // bounds and centres (nav_mesh.rs:321-352): centre = (sum of the vertices in order) / n, f32
+    m.poly_bounds.resize(P * 6), m.poly_center.resize(P * 3);
+    for (size_t p = 0; p < P; p++) {
+      float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, sum[3] = {0, 0, 0};
+      for (uint32_t v : polygons[p])
+        for (int k = 0; k < 3; k++) {
+          lo[k] = std::fmin(lo[k], vertices[v][k]);
+          hi[k] = std::fmax(hi[k], vertices[v][k]);
+          sum[k] = sum[k] + vertices[v][k];
+        }
+      for (int k = 0; k < 3; k++) {
+        m.poly_bounds[6 * p + k] = lo[k];
+        m.poly_bounds[6 * p + 3 + k] = hi[k];
+        m.poly_center[3 * p + k] = sum[k] / (float)polygons[p].size();
+      }
+    }
+    m.bounds_empty = V == 0;
+    if (V) {
+      for (int k = 0; k < 3; k++) m.mesh_bounds[k] = INFINITY, m.mesh_bounds[3 + k] = -INFINITY;
+      for (const Vec3& v : vertices)
+        for (int k = 0; k < 3; k++) {
+          m.mesh_bounds[k] = std::fmin(m.mesh_bounds[k], v[k]);
+          m.mesh_bounds[3 + k] = std::fmax(m.mesh_bounds[3 + k], v[k]);
+        }
+    }
+    for (size_t p = 0; p < P; p++)
+      for (uint32_t e = m.poly_edge_begin[p]; e < m.poly_edge_begin[p + 1]; e++)
+        if (m.edge_neighbor[e] == LMB_NONE) m.boundary_edges.emplace_back((uint32_t)p, e - m.poly_edge_begin[p]);
+    return m;
+  }
+};
+
+// util.rs:315-368 / island.rs:16-27: one island = a transform and a validated mesh
+struct Transform {
+  Vec3 translation{};
+  float rotation = 0.0f;
+};
+
+// The flattened navigation data of ONE island (no links, no modified nodes, no region numbers: exactly what
+// NavigationData::flatten yields for such a world).  Owns the arrays `desc` points into.
+class SingleIslandNavigationData {
+ public:
+  SingleIslandNavigationData(Transform transform, ValidNavigationMesh mesh,
+                             std::vector<std::pair<uint32_t, float>> type_index_costs = {})
+      : mesh_(std::move(mesh)) {
+    translation_ = transform.translation;
+    rotation_ = transform.rotation;
+    const uint32_t P = (uint32_t)mesh_.n_polys(), V = (uint32_t)(mesh_.vertices.size() / 3);
+    if (mesh_.bounds_empty)
+      bounds_ = {1.0f, 1.0f, 1.0f, 0.0f, 0.0f, 0.0f};
+    else
+      bounds_ = mesh_.mesh_bounds;
+    poly_begin_[0] = 0, poly_begin_[1] = P, vert_begin_[0] = 0, vert_begin_[1] = V;
+    for (size_t x = 1; x < type_index_costs.size(); x++)  // ascending type index
+      for (size_t y = x; y > 0 && type_index_costs[y].first < type_index_costs[y - 1].first; y--)
+        std::swap(type_index_costs[y], type_index_costs[y - 1]);
+    for (const auto& kv : type_index_costs) cost_index_.push_back(kv.first), cost_value_.push_back(kv.second);
+    node_link_begin_.assign((size_t)P + 1, 0u);
+    node_region_number_.assign(P, LMB_NONE);
+    lmb_navdata_desc& d = desc_;
+    d = lmb_navdata_desc{};
+    d.struct_size = (uint32_t)sizeof(lmb_navdata_desc);
+    d.n_islands = 1;
+    d.island_translation = translation_.data(), d.island_rotation = &rotation_, d.island_bounds = bounds_.data();
+    d.island_poly_begin = poly_begin_, d.island_vert_begin = vert_begin_;
+    d.n_vertices = V, d.vertices = mesh_.vertices.data();
+    d.n_polys = P, d.poly_edge_begin = mesh_.poly_edge_begin.data();
+    d.n_edges = (uint32_t)mesh_.poly_verts.size();
+    d.edge_vertex = mesh_.poly_verts.data(), d.edge_neighbor = mesh_.edge_neighbor.data();
+    d.edge_reverse = mesh_.edge_reverse.data();
+    d.poly_type = mesh_.poly_type.data(), d.poly_region = mesh_.poly_region.data();
+    d.poly_bounds = mesh_.poly_bounds.data(), d.poly_center = mesh_.poly_center.data();
+    d.n_type_costs = (uint32_t)cost_index_.size();
+    d.type_cost_index = cost_index_.data(), d.type_cost_value = cost_value_.data();
+    d.node_link_begin = node_link_begin_.data();
+    d.modified_edge_begin = zero2_, d.modified_vert_begin = zero2_;
+    d.node_region_number = node_region_number_.data();
+  }
+  SingleIslandNavigationData(const SingleIslandNavigationData&) = delete;
+  SingleIslandNavigationData& operator=(const SingleIslandNavigationData&) = delete;
+  const lmb_navdata_desc& desc() const { return desc_; }
+  const ValidNavigationMesh& mesh() const { return mesh_; }
+
+ private:
+  ValidNavigationMesh mesh_;
+  Vec3 translation_{};
+  float rotation_ = 0.0f;
+  std::array<float, 6> bounds_{};
+  uint32_t poly_begin_[2]{}, vert_begin_[2]{}, zero2_[2] = {0u, 0u};
+  std::vector<uint32_t> cost_index_, node_link_begin_, node_region_number_;
+  std::vector<float> cost_value_;
+  lmb_navdata_desc desc_{};
 };
 
 // lib.rs:538-547

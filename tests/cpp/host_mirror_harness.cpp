@@ -42,7 +42,13 @@ int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_result
   FnBackend::p_results = reinterpret_cast<decltype(FnBackend::p_results)>(fn_results);
   try {
     lb::BasicArchipelago<FnBackend> arch(ctx, lb::ArchipelagoOptions::from_agent_radius(0.5f), max_agents);
-    arch.set_navigation_data(*desc);
+    // desc == nullptr: the 15 x 15 room is validated and flattened by the C++ mirror itself
+    lb::NavigationMesh room;
+    room.vertices = {{0.0f, 0.0f, 0.0f}, {15.0f, 0.0f, 0.0f}, {15.0f, 15.0f, 0.0f}, {0.0f, 15.0f, 0.0f}};
+    room.polygons = {{0, 1, 2, 3}};
+    room.polygon_type_indices = {0};
+    lb::SingleIslandNavigationData own(lb::Transform{}, room.validate());
+    arch.set_navigation_data(desc ? *desc : own.desc());
     auto make = [](lb::Vec3 pos, lb::Vec3 target, float radius) {
       lb::Agent a = lb::Agent::create(pos, {0.0f, 0.0f, 0.0f}, radius, 1.0f, 2.0f);
       a.current_target = target;
@@ -104,6 +110,50 @@ int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_result
     return -1;
   }
   return 0;
+}
+
+// NavigationMesh::validate + SingleIslandNavigationData on caller-provided input; the flattened arrays are
+// copied out for comparison with the Python mirror.  Returns 0, or 1 + ValidationError::Kind with the
+// payload in out_err[0..1].
+int32_t hm_validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t n_polys, const uint32_t* poly_begin,
+                            const uint32_t* poly_verts, uint32_t n_types, const uint32_t* types,
+                            const float* translation, float rotation, uint64_t* out_err, uint32_t* out_u32,
+                            float* out_f32, float* out_island) {
+  lb::NavigationMesh mesh;
+  for (uint32_t v = 0; v < n_vertices; v++) mesh.vertices.push_back({vertices[3 * v], vertices[3 * v + 1], vertices[3 * v + 2]});
+  for (uint32_t p = 0; p < n_polys; p++)
+    mesh.polygons.emplace_back(poly_verts + poly_begin[p], poly_verts + poly_begin[p + 1]);
+  mesh.polygon_type_indices.assign(types, types + n_types);
+  try {
+    lb::SingleIslandNavigationData nd(lb::Transform{{translation[0], translation[1], translation[2]}, rotation},
+                                      mesh.validate());
+    const lmb_navdata_desc& d = nd.desc();
+    // u32: poly_edge_begin [P+1] | edge_vertex [E] | edge_neighbor [E] | edge_reverse [E] | poly_type [P] |
+    //      poly_region [P] | node_link_begin [P+1] | node_region_number [P] | island_poly_begin[2] | island_vert_begin[2]
+    uint32_t* u = out_u32;
+    auto put = [&](const uint32_t* src, size_t n) {
+      std::memcpy(u, src, n * sizeof(uint32_t));
+      u += n;
+    };
+    put(d.poly_edge_begin, d.n_polys + 1), put(d.edge_vertex, d.n_edges), put(d.edge_neighbor, d.n_edges);
+    put(d.edge_reverse, d.n_edges), put(d.poly_type, d.n_polys), put(d.poly_region, d.n_polys);
+    put(d.node_link_begin, d.n_polys + 1), put(d.node_region_number, d.n_polys);
+    put(d.island_poly_begin, 2), put(d.island_vert_begin, 2);
+    // f32: vertices [V*3] | poly_bounds [P*6] | poly_center [P*3]
+    float* f = out_f32;
+    std::memcpy(f, d.vertices, (size_t)d.n_vertices * 3 * sizeof(float)), f += (size_t)d.n_vertices * 3;
+    std::memcpy(f, d.poly_bounds, (size_t)d.n_polys * 6 * sizeof(float)), f += (size_t)d.n_polys * 6;
+    std::memcpy(f, d.poly_center, (size_t)d.n_polys * 3 * sizeof(float));
+    // island: translation xyz, rotation, bounds[6]
+    std::memcpy(out_island, d.island_translation, 3 * sizeof(float));
+    out_island[3] = d.island_rotation[0];
+    std::memcpy(out_island + 4, d.island_bounds, 6 * sizeof(float));
+    out_err[0] = d.n_edges, out_err[1] = d.n_links + d.n_modified + d.n_region_numbers + d.n_possible_links;
+    return 0;
+  } catch (const lb::ValidationError& e) {
+    out_err[0] = e.a, out_err[1] = e.b;
+    return 1 + (int32_t)e.kind;
+  }
 }
 
 }  // extern "C"

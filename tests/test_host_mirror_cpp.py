@@ -95,7 +95,8 @@ def cpp_trace(harness, ctx, fns, desc):
     trace_f = np.zeros((FRAMES, 4, 6), dtype=np.float32)
     trace_u = np.zeros((FRAMES, 14), dtype=np.uint32)
     err = C.create_string_buffer(512)
-    st = harness.hm_run_script(ctx, *[C.cast(f, C.c_void_p) for f in fns], C.byref(desc), C.c_uint32(MAX_AGENTS),
+    st = harness.hm_run_script(ctx, *[C.cast(f, C.c_void_p) for f in fns],
+                               C.byref(desc) if desc is not None else None, C.c_uint32(MAX_AGENTS),
                                C.c_uint32(FRAMES), C.c_float(DT), trace_f.ctypes.data_as(C.c_void_p),
                                trace_u.ctypes.data_as(C.c_void_p), err, C.c_uint32(512))
     assert st == 0, err.value.decode()
@@ -110,6 +111,113 @@ def check(py, cpp):
     assert (states[:12, 3] == 99).all() and (states[12:, 3] != 99).all()      # D added at frame 12 ...
     assert py[1][12, 4] >= 1 and (py[1][12, 6:8] == py[1][0, 6:8] + [0, 2]).all()  # ... in A's slot, next version
     assert (states[20:25, 1] == 8).all() and (states[25:, 1] != 8).all()      # B paused for five frames
+
+
+KINDS = ["TypeIndicesHaveWrongLength", "NotEnoughVerticesInPolygon", "InvalidVertexIndexInPolygon",
+         "DegenerateEdgeInPolygon", "DoublyConnectedEdge", "ConcavePolygon"]
+
+
+def cpp_validate_flatten(harness, vertices, polygons, types, translation=(0.0, 0.0, 0.0), rotation=0.0):
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    begin = np.zeros(len(polygons) + 1, dtype=np.uint32)
+    begin[1:] = np.cumsum([len(p) for p in polygons])
+    pv = np.array([x for p in polygons for x in p], dtype=np.uint32)
+    t = np.asarray(types, dtype=np.uint32)
+    P, E, V = len(polygons), len(pv), len(v)
+    out_u = np.zeros(7 * P + 3 * E + 8, dtype=np.uint32)
+    out_f = np.zeros(3 * V + 9 * P + 1, dtype=np.float32)
+    out_i = np.zeros(10, dtype=np.float32)
+    err = np.zeros(2, dtype=np.uint64)
+    tr = np.asarray(translation, dtype=np.float32)
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = harness.hm_validate_flatten(C.c_uint32(V), p_(v), C.c_uint32(P), p_(begin), p_(pv), C.c_uint32(len(t)), p_(t),
+                                     p_(tr), C.c_float(rotation), p_(err), p_(out_u), p_(out_f), p_(out_i))
+    if st != 0:
+        return KINDS[st - 1], int(err[0]), int(err[1])
+    u = iter(np.split(out_u[:5 * P + 3 * E + 6], np.cumsum([P + 1, E, E, E, P, P, P + 1, P, 2, 2])[:-1]))
+    f = iter(np.split(out_f[:3 * V + 9 * P], np.cumsum([3 * V, 6 * P])))
+    return dict(poly_edge_begin=next(u), edge_vertex=next(u), edge_neighbor=next(u), edge_reverse=next(u),
+                poly_type=next(u), poly_region=next(u), node_link_begin=next(u), node_region_number=next(u),
+                island_poly_begin=next(u), island_vert_begin=next(u), vertices=next(f).reshape(-1, 3),
+                poly_bounds=next(f).reshape(-1, 6), poly_center=next(f).reshape(-1, 3), island=out_i,
+                n_edges=int(err[0]), n_other=int(err[1]))
+
+
+@pytest.mark.parametrize("mesh_kind", ["grid", "maze", "irregular", "rosette12", "two_regions"])
+def test_cpp_validate_and_flatten_match_the_python_mirror(harness, mesh_kind):
+    """`NavigationMesh::validate` + the single-island flatten of the C++ mirror against landmass_b200.nav_mesh /
+    nav_data.flatten: every array of the descriptor, bit for bit."""
+    from landmass_b200 import synth
+
+    if mesh_kind == "two_regions":
+        quad = lambda x: [(x, 0.0, 0.0), (x + 1.0, 0.0, 0.5), (x + 1.0, 1.0, 0.0), (x, 1.0, 0.25)]  # noqa: E731
+        mesh = valid_mesh(dict(vertices=quad(0.0) + quad(1.0)[1:3] + quad(5.0),
+                               polygons=[[0, 1, 2, 3], [1, 4, 5, 2], [6, 7, 8, 9]], polygon_type_indices=[0, 2, 1]))
+    else:
+        mesh = {"grid": lambda: synth.grid_mesh(9, 7, types=(np.arange(63).reshape(7, 9) % 3).astype(np.uint32)),
+                "maze": lambda: synth.maze_mesh(9), "irregular": lambda: synth.irregular_mesh(10, 8),
+                "rosette12": lambda: synth.rosette_mesh(12, 3)}[mesh_kind]()
+    polygons = [mesh.polygon_vertices(p).tolist() for p in range(mesh.n_polys)]
+    translation, rotation = (3.0, -2.0, 0.5), 0.7
+    from landmass_b200.nav_data import NavigationData
+
+    nd = NavigationData()
+    nd.add_island(Island(Transform(translation, rotation), mesh))
+    nd.update(0.01, 0.25)
+    flat = nd.flatten()
+    got = cpp_validate_flatten(harness, mesh.vertices, polygons, mesh.poly_type, translation, rotation)
+    assert isinstance(got, dict), got
+    for name in ["poly_edge_begin", "edge_vertex", "edge_neighbor", "edge_reverse", "poly_type", "poly_region",
+                 "node_link_begin", "node_region_number", "island_poly_begin", "island_vert_begin"]:
+        assert np.array_equal(got[name], np.asarray(flat[name], dtype=np.uint32)), name
+    for name in ["vertices", "poly_bounds", "poly_center"]:
+        assert np.array_equal(got[name].view(np.uint32), np.asarray(flat[name], dtype=np.float32).view(np.uint32)), name
+    want_island = np.concatenate([flat["island_translation"][0], flat["island_rotation"][:1], flat["island_bounds"][0]])
+    assert np.array_equal(got["island"], want_island.astype(np.float32))
+    assert got["n_edges"] == flat["n_edges"] and got["n_other"] == 0
+    assert flat["n_links"] == 0 and flat["n_modified"] == 0 and flat["n_region_numbers"] == 0
+
+
+def test_cpp_validation_errors_match_the_python_mirror(harness):
+    """Every ValidationError of nav_mesh.rs:131-162 that does not involve a height mesh, same variant and payload."""
+    from landmass_b200 import NavigationMesh, ValidationError
+
+    sq = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 1.0, 0.0), (0.0, 1.0, 0.0), (2.0, 0.0, 0.0), (2.0, 1.0, 0.0),
+          (0.5, 0.5, 0.0)]
+    cases = [
+        (sq, [[0, 1, 2, 3]], [0, 1]),                            # TypeIndicesHaveWrongLength
+        (sq, [[0, 1, 2, 3], [1, 4]], [0, 0]),                    # NotEnoughVerticesInPolygon
+        (sq, [[0, 1, 2, 3], [1, 4, 9]], [0, 0]),                 # InvalidVertexIndexInPolygon
+        (sq, [[0, 1, 2, 3], [1, 4, 4, 5, 2]], [0, 0]),           # DegenerateEdgeInPolygon
+        (sq, [[0, 1, 2, 3], [1, 4, 5, 2], [2, 1, 6]], [0, 0, 0]),  # DoublyConnectedEdge
+        (sq, [[0, 1, 6, 2, 3]], [0]),                            # ConcavePolygon
+        (sq, [[0, 3, 2, 1]], [0]),                               # clockwise: ConcavePolygon
+    ]
+    seen = set()
+    for vertices, polygons, types in cases:
+        with pytest.raises(ValidationError) as e:
+            NavigationMesh(vertices=vertices, polygons=polygons, polygon_type_indices=types).validate()
+        got = cpp_validate_flatten(harness, vertices, polygons, types)
+        assert isinstance(got, tuple), (polygons, got)
+        want_args = tuple(int(a) for a in e.value.args_) + (0,) * (2 - len(e.value.args_))
+        assert got == (e.value.kind,) + want_args, (polygons, got, e.value)
+        seen.add(got[0])
+    assert seen == set(KINDS)
+
+
+def test_cpp_host_mirror_builds_its_own_navigation_data(harness):
+    """The scripted game loop again, but with the room validated and flattened by the C++ mirror."""
+    from oracle import oracle_py
+    from oracle.oracle_py import OracleBackend
+
+    py = python_trace(OracleBackend())
+    desc, keep = _abi.make_navdata_desc(py[2])
+    lib = oracle_py.load()
+    lib.orc_create.restype = C.c_void_p
+    ctx = C.c_void_p(lib.orc_create(C.byref(desc), C.c_uint32(0)))
+    cpp = cpp_trace(harness, ctx, (lib.orc_navdata_upload, lib.orc_step, lib.orc_pathing_results), None)
+    check(py, cpp)
+    del keep
 
 
 def test_cpp_host_mirror_matches_python_mirror_on_the_oracle(harness):
