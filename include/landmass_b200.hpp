@@ -6,7 +6,8 @@
 // header, which covers the part of the API a game loop touches every frame, in the compiled language
 // a maintainer would port to Rust line by line:
 //
-//   Archipelago<..>::{add,remove,get}_{agent,character}, update(dt), get_pathing_results   lib.rs:96-268, 270-534
+//   Archipelago<..>::{add,remove,get}_{agent,character}, update(dt), get_pathing_results,  lib.rs:96-268, 270-534
+//   sample_point, find_path (SampledPoint, PathStep)                                       query.rs:19-127, 185-273
 //   Agent (pub fields + state accessors), AgentState, TargetReachedCondition,              agent.rs:24-310
 //   PermittedAnimationLinks, ReachedAnimationLink
 //   Character                                                                              character.rs:14-31
@@ -473,6 +474,25 @@ class SingleIslandNavigationData {
   lmb_navdata_desc desc_{};
 };
 
+// query.rs:19-55: a point on the navigation meshes (`node` is the global node id of the C ABI)
+struct SampledPoint {
+  Vec3 point;
+  uint32_t node;
+};
+// query.rs:105-127
+struct PathStep {
+  bool is_animation_link = false;
+  Vec3 point{};      // Waypoint, or the animation link's start point
+  Vec3 end_point{};  // the animation link's end point
+  uint32_t link_id = LMB_NONE;
+};
+struct FindPathError : std::runtime_error {  // query.rs:97-103 (NoPathFound is reported as an empty optional)
+  uint32_t type_index;
+  float cost;
+  FindPathError(uint32_t t, float c)
+      : std::runtime_error("NonPositiveTypeIndexCost"), type_index(t), cost(c) {}
+};
+
 // lib.rs:538-547
 struct PathingResult {
   AgentId agent;
@@ -495,6 +515,16 @@ struct CudaBackend {
   }
   static int32_t pathing_results(Ctx* c, lmb_pathing_result* out, uint32_t cap, uint32_t* n) {
     return lmb_pathing_results(c, out, cap, n);
+  }
+  static int32_t sample_points(Ctx* c, uint32_t n, const float* points, const lmb_options* o, float* out_points,
+                               uint32_t* out_nodes) {
+    return lmb_sample_points(c, n, points, o, out_points, out_nodes);
+  }
+  static int32_t find_straight_paths(Ctx* c, uint32_t n, const uint32_t* sn, const float* sp, const uint32_t* en,
+                                     const float* ep, const uint32_t* ob, const uint32_t* ot, const float* oc,
+                                     uint32_t* succ, uint32_t* begin, uint32_t* kind, float* pts, uint32_t* link,
+                                     uint32_t cap, const uint32_t* pa, const uint32_t* pb, const uint32_t* pk) {
+    return lmb_find_straight_paths(c, n, sn, sp, en, ep, ob, ot, oc, succ, begin, kind, pts, link, cap, pa, pb, pk);
   }
   static std::string last_error(Ctx* c) {
     const char* e = lmb_last_error(c);
@@ -537,6 +567,69 @@ class BasicArchipelago {
   const std::vector<CharacterId>& get_character_ids() const { return characters_.keys(); }
 
   const std::vector<PathingResult>& get_pathing_results() const { return pathing_results_; }  // lib.rs:233-236
+
+  // `Archipelago::sample_point` (lib.rs:235-246, query.rs:70-94); an empty optional is SamplePointError::OutOfRange.
+  // `distances` replaces the archipelago's point_sample_distance for this call (only its first four fields are read).
+  std::optional<SampledPoint> sample_point(Vec3 point, const lmb_options* distances = nullptr) {
+    lmb_options o = archipelago_options.abi;
+    if (distances) {
+      o.horizontal_distance = distances->horizontal_distance, o.distance_above = distances->distance_above;
+      o.distance_below = distances->distance_below, o.vertical_preference_ratio = distances->vertical_preference_ratio;
+    }
+    float out_point[3];
+    uint32_t node = LMB_NONE;
+    check(Backend::sample_points(ctx_, 1, point.data(), &o, out_point, &node), "lmb_sample_points");
+    if (node == LMB_NONE) return std::nullopt;
+    return SampledPoint{{out_point[0], out_point[1], out_point[2]}, node};
+  }
+
+  // `Archipelago::find_path` (lib.rs:248-268, query.rs:185-273): the straight path between two sampled points;
+  // an empty optional is FindPathError::NoPathFound.
+  std::optional<std::vector<PathStep>> find_path(const SampledPoint& start, const SampledPoint& end,
+                                                 std::vector<std::pair<uint32_t, float>> override_type_index_costs = {},
+                                                 const PermittedAnimationLinks& permitted = {}) {
+    for (const auto& kv : override_type_index_costs)
+      if (!(kv.second > 0.0f)) throw FindPathError(kv.first, kv.second);
+    for (size_t x = 1; x < override_type_index_costs.size(); x++)
+      for (size_t y = x; y > 0 && override_type_index_costs[y].first < override_type_index_costs[y - 1].first; y--)
+        std::swap(override_type_index_costs[y], override_type_index_costs[y - 1]);
+    std::vector<uint32_t> ot, kinds = permitted.kinds;
+    std::vector<float> oc;
+    for (const auto& kv : override_type_index_costs) ot.push_back(kv.first), oc.push_back(kv.second);
+    sort_unique(kinds);
+    const uint32_t ob[2] = {0u, (uint32_t)ot.size()}, pb[2] = {0u, (uint32_t)kinds.size()};
+    const uint32_t permit_all = permitted.all ? 1u : 0u;
+    uint32_t cap = 256;
+    for (;;) {
+      std::vector<uint32_t> kind(cap), link(cap);
+      std::vector<float> pts(6 * (size_t)cap);
+      uint32_t success = 0, begin[2] = {0, 0};
+      const int32_t st = Backend::find_straight_paths(ctx_, 1, &start.node, start.point.data(), &end.node,
+                                                      end.point.data(), ob, ot.data(), oc.data(), &success, begin,
+                                                      kind.data(), pts.data(), link.data(), cap, &permit_all, pb,
+                                                      kinds.data());
+      if (st == LMB_ERR_CAPACITY) {
+        cap = begin[1] > cap ? begin[1] : cap * 2;
+        continue;
+      }
+      check(st, "lmb_find_straight_paths");
+      if (!success) return std::nullopt;
+      std::vector<PathStep> steps;
+      for (uint32_t k = begin[0]; k < begin[1]; k++) {
+        PathStep ps;
+        ps.is_animation_link = kind[k] == 1;
+        for (int c = 0; c < 3; c++) ps.point[c] = pts[6 * (size_t)k + c], ps.end_point[c] = pts[6 * (size_t)k + 3 + c];
+        ps.link_id = ps.is_animation_link ? link[k] : LMB_NONE;
+        steps.push_back(ps);
+      }
+      // the sampled points are returned as given (query.rs:224, 227)
+      if (!steps.empty()) {
+        steps.front().point = start.point;
+        if (!steps.back().is_animation_link) steps.back().point = end.point;
+      }
+      return steps;
+    }
+  }
 
   // `Archipelago::update` (lib.rs:270-534): pack -> lmb_step -> scatter
   void update(float delta_time) {

@@ -23,6 +23,21 @@ struct FnBackend {
   static int32_t pathing_results(Ctx* c, lmb_pathing_result* out, uint32_t cap, uint32_t* n) {
     return p_results(c, out, cap, n);
   }
+  static inline int32_t (*p_sample)(void*, uint32_t, const float*, const lmb_options*, float*, uint32_t*) = nullptr;
+  static inline int32_t (*p_straight)(void*, uint32_t, const uint32_t*, const float*, const uint32_t*, const float*,
+                                      const uint32_t*, const uint32_t*, const float*, uint32_t*, uint32_t*, uint32_t*,
+                                      float*, uint32_t*, uint32_t, const uint32_t*, const uint32_t*,
+                                      const uint32_t*) = nullptr;
+  static int32_t sample_points(Ctx* c, uint32_t n, const float* points, const lmb_options* o, float* out_points,
+                               uint32_t* out_nodes) {
+    return p_sample(c, n, points, o, out_points, out_nodes);
+  }
+  static int32_t find_straight_paths(Ctx* c, uint32_t n, const uint32_t* sn, const float* sp, const uint32_t* en,
+                                     const float* ep, const uint32_t* ob, const uint32_t* ot, const float* oc,
+                                     uint32_t* succ, uint32_t* begin, uint32_t* kind, float* pts, uint32_t* link,
+                                     uint32_t cap, const uint32_t* pa, const uint32_t* pb, const uint32_t* pk) {
+    return p_straight(c, n, sn, sp, en, ep, ob, ot, oc, succ, begin, kind, pts, link, cap, pa, pb, pk);
+  }
   static std::string last_error(Ctx*) { return ""; }
 };
 
@@ -102,6 +117,49 @@ int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_result
       for (int k = 0; k < 4; k++) {
         tu[6 + 2 * k] = k < (int)pr.size() ? pr[(size_t)k].agent.idx : 0u;
         tu[7 + 2 * k] = k < (int)pr.size() ? pr[(size_t)k].agent.version : 0u;
+      }
+    }
+  } catch (const std::exception& e) {
+    std::strncpy(error, e.what(), error_cap - 1);
+    error[error_cap - 1] = 0;
+    return -1;
+  }
+  return 0;
+}
+
+// `sample_point` + `find_path` for n (start, end) pairs; query q with override cost `override_cost[q]` on type 0
+// when that is > 0.  out_n_steps[q] = number of steps, or -1 / -2 (start / end OutOfRange), -3 (NoPathFound);
+// steps are appended to out_steps as 7 floats (is_link, point xyz, end point xyz), at most step_cap of them.
+int32_t hm_queries(void* ctx, void* fn_upload, void* fn_sample, void* fn_straight, const lmb_navdata_desc* desc,
+                   uint32_t n, const float* starts, const float* ends, const float* override_cost, int32_t* out_n_steps,
+                   float* out_steps, uint32_t step_cap, char* error, uint32_t error_cap) {
+  FnBackend::p_upload = reinterpret_cast<decltype(FnBackend::p_upload)>(fn_upload);
+  FnBackend::p_sample = reinterpret_cast<decltype(FnBackend::p_sample)>(fn_sample);
+  FnBackend::p_straight = reinterpret_cast<decltype(FnBackend::p_straight)>(fn_straight);
+  try {
+    lb::BasicArchipelago<FnBackend> arch(ctx, lb::ArchipelagoOptions::from_agent_radius(0.5f), 4);
+    arch.set_navigation_data(*desc);
+    uint32_t used = 0;
+    for (uint32_t q = 0; q < n; q++) {
+      auto a = arch.sample_point({starts[3 * q], starts[3 * q + 1], starts[3 * q + 2]});
+      auto b = arch.sample_point({ends[3 * q], ends[3 * q + 1], ends[3 * q + 2]});
+      if (!a || !b) {
+        out_n_steps[q] = !a ? -1 : -2;
+        continue;
+      }
+      std::vector<std::pair<uint32_t, float>> ov;
+      if (override_cost[q] > 0.0f) ov.emplace_back(0u, override_cost[q]);
+      auto steps = arch.find_path(*a, *b, ov);
+      if (!steps) {
+        out_n_steps[q] = -3;
+        continue;
+      }
+      out_n_steps[q] = (int32_t)steps->size();
+      for (const lb::PathStep& st : *steps) {
+        if (used >= step_cap) throw std::runtime_error("step capacity");
+        float* o = out_steps + 7 * (size_t)used++;
+        o[0] = st.is_animation_link ? 1.0f : 0.0f;
+        for (int c = 0; c < 3; c++) o[1 + c] = st.point[c], o[4 + c] = st.is_animation_link ? st.end_point[c] : 0.0f;
       }
     }
   } catch (const std::exception& e) {

@@ -27,6 +27,8 @@ def harness(tmp_path_factory):
                     "-o", out], check=True)
     lib = C.CDLL(out)
     lib.hm_run_script.restype = C.c_int32
+    lib.hm_queries.restype = C.c_int32
+    lib.hm_validate_flatten.restype = C.c_int32
     return lib
 
 
@@ -217,6 +219,95 @@ def test_cpp_host_mirror_builds_its_own_navigation_data(harness):
     ctx = C.c_void_p(lib.orc_create(C.byref(desc), C.c_uint32(0)))
     cpp = cpp_trace(harness, ctx, (lib.orc_navdata_upload, lib.orc_step, lib.orc_pathing_results), None)
     check(py, cpp)
+    del keep
+
+
+def _query_case(backend):
+    """A maze island and 40 (start, end) pairs: most on the mesh, some off it, some with a cost override."""
+    from landmass_b200 import FindPathError, SamplePointError, synth
+
+    mesh = synth.maze_mesh(8)
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5), backend=backend)
+    arch.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), mesh))
+    arch.update(0.1)
+    rng = np.random.Generator(np.random.PCG64(5))
+    n = 40
+    starts, _ = synth.random_points_on_mesh(mesh, n, rng)
+    ends, _ = synth.random_points_on_mesh(mesh, n, rng)
+    starts[3] = (-5.0, -5.0, 0.0)   # off the mesh
+    ends[7] = (100.0, 3.0, 0.0)
+    cost = np.where(np.arange(n) % 4 == 1, 2.5, 0.0).astype(np.float32)
+    want_n, want_steps = [], []
+    for q in range(n):
+        try:
+            a = arch.sample_point(tuple(starts[q]))
+        except SamplePointError:
+            want_n.append(-1)
+            continue
+        try:
+            b = arch.sample_point(tuple(ends[q]))
+        except SamplePointError:
+            want_n.append(-2)
+            continue
+        try:
+            steps = arch.find_path(a, b, {0: float(cost[q])} if cost[q] > 0 else None)
+        except FindPathError:
+            want_n.append(-3)
+            continue
+        want_n.append(len(steps))
+        for st in steps:
+            assert st.kind == "Waypoint"
+            want_steps.append([0.0] + [float(x) for x in np.asarray(st.point, dtype=np.float32)] + [0.0, 0.0, 0.0])
+    arch._sync_navdata()
+    return arch._flat, starts, ends, cost, np.array(want_n, dtype=np.int32), np.array(want_steps, dtype=np.float32)
+
+
+def _cpp_queries(harness, ctx, fns, desc, starts, ends, cost):
+    n = len(starts)
+    out_n = np.zeros(n, dtype=np.int32)
+    out_steps = np.zeros((4096, 7), dtype=np.float32)
+    err = C.create_string_buffer(512)
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = harness.hm_queries(ctx, *[C.cast(f, C.c_void_p) for f in fns], C.byref(desc), C.c_uint32(n),
+                            p_(np.ascontiguousarray(starts, dtype=np.float32)),
+                            p_(np.ascontiguousarray(ends, dtype=np.float32)), p_(cost), p_(out_n), p_(out_steps),
+                            C.c_uint32(4096), err, C.c_uint32(512))
+    assert st == 0, err.value.decode()
+    return out_n, out_steps[:int(out_n[out_n > 0].sum())]
+
+
+def test_cpp_queries_match_the_python_mirror_on_the_oracle(harness):
+    """`Archipelago::sample_point` / `find_path` of the C++ mirror (query.rs:70-94, 185-273) against the Python
+    mirror: same OutOfRange cases, same straight paths, bit for bit."""
+    from oracle import oracle_py
+    from oracle.oracle_py import OracleBackend
+
+    flat, starts, ends, cost, want_n, want_steps = _query_case(OracleBackend())
+    desc, keep = _abi.make_navdata_desc(flat)
+    lib = oracle_py.load()
+    lib.orc_create.restype = C.c_void_p
+    ctx = C.c_void_p(lib.orc_create(C.byref(desc), C.c_uint32(0)))
+    got_n, got_steps = _cpp_queries(harness, ctx, (lib.orc_navdata_upload, lib.orc_sample_points,
+                                                   lib.orc_find_straight_paths), desc, starts, ends, cost)
+    assert np.array_equal(got_n, want_n) and (want_n == -1).sum() == 1 and (want_n == -2).sum() == 1
+    assert (want_n > 2).sum() > 10
+    assert np.array_equal(got_steps.view(np.uint32), want_steps.view(np.uint32))
+    del keep
+
+
+@pytest.mark.gpu
+def test_cpp_queries_match_the_python_mirror_on_cuda(harness):
+    from landmass_b200._native import NativeBackend
+
+    flat, starts, ends, cost, want_n, want_steps = _query_case(NativeBackend(max_agents=MAX_AGENTS))
+    desc, keep = _abi.make_navdata_desc(flat)
+    gpu = NativeBackend(max_agents=MAX_AGENTS)
+    lib = gpu.lib
+    got_n, got_steps = _cpp_queries(harness, gpu.ctx, (lib.lmb_navdata_upload, lib.lmb_sample_points,
+                                                       lib.lmb_find_straight_paths), desc, starts, ends, cost)
+    assert np.array_equal(got_n, want_n)
+    assert np.array_equal(got_steps.view(np.uint32), want_steps.view(np.uint32))
+    gpu.close()
     del keep
 
 
