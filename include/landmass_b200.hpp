@@ -23,8 +23,8 @@
 // height meshes bring the descriptor the Python mirror (or the caller's port of nav_data.rs) flattens.
 //
 // Coordinates are landmass-internal (XYZ, z up): `CoordinateSystem::to_landmass` stays with the caller.
-// The entry points are reached through a table of function pointers so that the same code runs on the
-// CUDA library (`cuda_backend()`, the only product backend — there is no CPU fallback) and, in tests
+// The entry points are reached through a `Backend` policy class so that the same code runs on the
+// CUDA library (`CudaBackend`, the only product backend — there is no CPU fallback) and, in tests
 // only, on the CPU oracle, whose step functions have the same signatures.
 #pragma once
 #include <array>

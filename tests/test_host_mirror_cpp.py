@@ -338,3 +338,23 @@ def test_cpp_host_mirror_matches_python_mirror_on_cuda(harness):
     check(py, cpp)
     gpu.close()
     del keep
+
+
+def test_cpp_mirror_links_against_the_cuda_library(tmp_path):
+    """`landmass_b200::Archipelago` (= BasicArchipelago<CudaBackend>) compiles and every lmb_* entry point it
+    calls resolves against liblandmass_b200.so.  Without a GPU the program can only report the ABI version, and
+    `--run` fails at lmb_create: the library has no CPU fallback."""
+    import torch
+
+    csrc = os.path.join(ROOT, "landmass_b200", "csrc")
+    exe = str(tmp_path / "link_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "link_check.cpp"), "-o", exe, "-L" + csrc, "-llandmass_b200",
+                    "-Wl,-rpath," + csrc], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == f"abi {_abi.ABI_VERSION}"
+    run = subprocess.run([exe, "--run"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "pathing result(s)" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 1
