@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "landmass_b200.hpp"
+#include "landmass_b200_linking.hpp"
 
 namespace lb = landmass_b200;
 
@@ -212,6 +213,63 @@ int32_t hm_validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t
     out_err[0] = e.a, out_err[1] = e.b;
     return 1 + (int32_t)e.kind;
   }
+}
+
+// Several islands -> validate each -> link (boundary links, modified nodes, regions) -> flatten, all in the C++
+// mirror; the descriptor's arrays are streamed out in a fixed order for comparison with nav_data.flatten.
+// Island i owns vertices [vert_begin[i], vert_begin[i+1]) and polygons [poly_begin[i], poly_begin[i+1]) whose vertex
+// indices are island-local.  Returns 0 or -1 (error text in `error`); *n_u / *n_f = words written.
+int32_t hm_link_flatten(uint32_t n_islands, const uint32_t* vert_begin, const float* vertices, const uint32_t* poly_begin,
+                        const uint32_t* poly_edge_begin, const uint32_t* poly_verts, const uint32_t* types,
+                        const float* translations, const float* rotations, uint32_t* out_u, uint32_t cap_u,
+                        float* out_f, uint32_t cap_f, uint32_t* n_u, uint32_t* n_f, char* error, uint32_t error_cap) {
+  try {
+    std::vector<lb::Island> islands;
+    for (uint32_t i = 0; i < n_islands; i++) {
+      lb::NavigationMesh mesh;
+      for (uint32_t v = vert_begin[i]; v < vert_begin[i + 1]; v++)
+        mesh.vertices.push_back({vertices[3 * v], vertices[3 * v + 1], vertices[3 * v + 2]});
+      for (uint32_t p = poly_begin[i]; p < poly_begin[i + 1]; p++) {
+        mesh.polygons.emplace_back(poly_verts + poly_edge_begin[p], poly_verts + poly_edge_begin[p + 1]);
+        mesh.polygon_type_indices.push_back(types[p]);
+      }
+      islands.push_back({lb::Transform{{translations[3 * i], translations[3 * i + 1], translations[3 * i + 2]}, rotations[i]},
+                         mesh.validate()});
+    }
+    lb::NavigationData nd(std::move(islands));
+    const lmb_navdata_desc& d = nd.desc();
+    uint32_t wu = 0, wf = 0;
+    auto pu = [&](const uint32_t* src, size_t n) {
+      if (wu + n > cap_u) throw std::runtime_error("u32 capacity");
+      if (n) std::memcpy(out_u + wu, src, n * sizeof(uint32_t));
+      wu += (uint32_t)n;
+    };
+    auto pf = [&](const float* src, size_t n) {
+      if (wf + n > cap_f) throw std::runtime_error("f32 capacity");
+      if (n) std::memcpy(out_f + wf, src, n * sizeof(float));
+      wf += (uint32_t)n;
+    };
+    const uint32_t head[6] = {d.n_polys, d.n_edges, d.n_links, d.n_modified, d.n_region_numbers, d.n_vertices};
+    pu(head, 6);
+    pu(d.island_poly_begin, d.n_islands + 1), pu(d.island_vert_begin, d.n_islands + 1);
+    pu(d.poly_edge_begin, d.n_polys + 1), pu(d.edge_vertex, d.n_edges), pu(d.edge_neighbor, d.n_edges);
+    pu(d.edge_reverse, d.n_edges), pu(d.poly_type, d.n_polys), pu(d.poly_region, d.n_polys);
+    pu(d.link_dst_node, d.n_links), pu(d.link_dst_type, d.n_links), pu(d.link_kind, d.n_links);
+    pu(d.link_reverse, d.n_links), pu(d.node_link_begin, d.n_polys + 1), pu(d.node_links, d.n_links);
+    pu(d.modified_node, d.n_modified), pu(d.modified_edge_begin, d.n_modified + 1);
+    pu(d.modified_edges, 2 * (size_t)d.modified_edge_begin[d.n_modified]);
+    pu(d.modified_vert_begin, d.n_modified + 1);
+    pu(d.node_region_number, d.n_polys), pu(d.region_root, d.n_region_numbers);
+    pf(d.vertices, 3 * (size_t)d.n_vertices), pf(d.poly_bounds, 6 * (size_t)d.n_polys);
+    pf(d.poly_center, 3 * (size_t)d.n_polys), pf(d.island_bounds, 6 * (size_t)d.n_islands);
+    pf(d.link_portal, 6 * (size_t)d.n_links), pf(d.modified_verts, 2 * (size_t)d.modified_vert_begin[d.n_modified]);
+    *n_u = wu, *n_f = wf;
+  } catch (const std::exception& e) {
+    std::strncpy(error, e.what(), error_cap - 1);
+    error[error_cap - 1] = 0;
+    return -1;
+  }
+  return 0;
 }
 
 }  // extern "C"

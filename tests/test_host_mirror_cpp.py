@@ -29,6 +29,7 @@ def harness(tmp_path_factory):
     lib.hm_run_script.restype = C.c_int32
     lib.hm_queries.restype = C.c_int32
     lib.hm_validate_flatten.restype = C.c_int32
+    lib.hm_link_flatten.restype = C.c_int32
     return lib
 
 
@@ -220,6 +221,108 @@ def test_cpp_host_mirror_builds_its_own_navigation_data(harness):
     cpp = cpp_trace(harness, ctx, (lib.orc_navdata_upload, lib.orc_step, lib.orc_pathing_results), None)
     check(py, cpp)
     del keep
+
+
+def _cpp_link_flatten(harness, islands):
+    """islands: [(translation, rotation, ValidNavigationMesh)] -> dict of the descriptor arrays the C++ mirror
+    (include/landmass_b200_linking.hpp) builds."""
+    vb, pb, peb, verts, pv, types = [0], [0], [0], [], [], []
+    for _, _, m in islands:
+        verts.append(m.vertices)
+        vb.append(vb[-1] + len(m.vertices))
+        pb.append(pb[-1] + m.n_polys)
+        for p in range(m.n_polys):
+            v = m.polygon_vertices(p)
+            pv.extend(v.tolist())
+            peb.append(peb[-1] + len(v))
+        types.extend(m.poly_type.tolist())
+    arr = lambda x, dt: np.ascontiguousarray(x, dtype=dt)  # noqa: E731
+    vb, pb, peb, pv, types = (arr(x, np.uint32) for x in (vb, pb, peb, pv, types))
+    verts = arr(np.concatenate(verts), np.float32)
+    tr = arr([i[0] for i in islands], np.float32)
+    rot = arr([i[1] for i in islands], np.float32)
+    ou, of = np.zeros(1 << 20, dtype=np.uint32), np.zeros(1 << 20, dtype=np.float32)
+    nu, nf, err = C.c_uint32(), C.c_uint32(), C.create_string_buffer(256)
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    st = harness.hm_link_flatten(C.c_uint32(len(islands)), p_(vb), p_(verts), p_(pb), p_(peb), p_(pv), p_(types), p_(tr),
+                                 p_(rot), p_(ou), C.c_uint32(len(ou)), p_(of), C.c_uint32(len(of)), C.byref(nu),
+                                 C.byref(nf), err, C.c_uint32(256))
+    assert st == 0, err.value.decode()
+    ou, of = ou[:nu.value], of[:nf.value]
+    P, E, L, M, R, V = (int(x) for x in ou[:6])
+    out, pos = dict(n_polys=P, n_edges=E, n_links=L, n_modified=M, n_region_numbers=R, n_vertices=V), 6
+    n_isl = len(islands)
+    for name, n in [("island_poly_begin", n_isl + 1), ("island_vert_begin", n_isl + 1), ("poly_edge_begin", P + 1),
+                    ("edge_vertex", E), ("edge_neighbor", E), ("edge_reverse", E), ("poly_type", P), ("poly_region", P),
+                    ("link_dst_node", L), ("link_dst_type", L), ("link_kind", L), ("link_reverse", L),
+                    ("node_link_begin", P + 1), ("node_links", L), ("modified_node", M), ("modified_edge_begin", M + 1)]:
+        out[name] = ou[pos:pos + n]
+        pos += n
+    ne = int(out["modified_edge_begin"][-1])
+    out["modified_edges"] = ou[pos:pos + 2 * ne]
+    pos += 2 * ne
+    out["modified_vert_begin"] = ou[pos:pos + M + 1]
+    pos += M + 1
+    out["node_region_number"] = ou[pos:pos + P]
+    pos += P
+    out["region_root"] = ou[pos:pos + R]
+    assert pos + R == len(ou)
+    fp = 0
+    for name, n in [("vertices", 3 * V), ("poly_bounds", 6 * P), ("poly_center", 3 * P), ("island_bounds", 6 * n_isl),
+                    ("link_portal", 6 * L), ("modified_verts", 2 * int(out["modified_vert_begin"][-1]))]:
+        out[name] = of[fp:fp + n]
+        fp += n
+    assert fp == len(of)
+    return out
+
+
+@pytest.mark.parametrize("world", ["misaligned_pair", "tiling_3x3", "apart", "rotated_pi", "rotated_half_pi"])
+def test_cpp_island_linking_matches_the_python_mirror(harness, world):
+    """include/landmass_b200_linking.hpp — boundary links (`edge_intersection`, link order and reverse indices),
+    modified nodes (clipped boundaries, new vertices), region numbers / roots and the multi-island flatten — against
+    landmass_b200.linking + nav_data.flatten: every array of the descriptor, floats bit for bit."""
+    from landmass_b200 import synth
+    from landmass_b200.nav_data import NavigationData
+
+    types = (np.add.outer(np.arange(8) // 2, np.arange(8) // 2) % 3).astype(np.uint32)
+    grid = synth.grid_mesh(8, 8, types=types)
+    if world == "misaligned_pair":   # avoidance_test.rs:855-925: redundant vertices, clipped borders
+        red = valid_mesh(dict(vertices=[(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (1.0, 2.0, 0.0), (0.0, 2.0, 0.0),
+                                        (0.0, 0.6, 0.0), (0.0, 0.2, 0.0)],
+                              polygons=[[0, 1, 2, 3, 4, 5]], polygon_type_indices=[0]))
+        islands = [((0.0, 0.0, 0.0), 0.0, red), ((1.0, 0.25, 0.0), 0.0, red)]
+    elif world == "tiling_3x3":      # BASELINE config 4 in small: typed grids tiled by pure translations
+        islands = [((8.0 * x, 8.0 * y, 0.0), 0.0, grid) for y in range(3) for x in range(3)]
+    elif world == "apart":
+        islands = [((0.0, 0.0, 0.0), 0.0, synth.maze_mesh(5)), ((40.0, 0.0, 0.0), 0.0, grid)]
+    elif world == "rotated_pi":
+        islands = [((0.0, 0.0, 0.0), 0.0, grid), ((16.0, 8.0, 0.0), float(np.pi), grid)]
+    else:
+        islands = [((0.0, 0.0, 0.0), 0.0, grid), ((16.0, 0.0, 0.0), float(np.pi / 2), grid)]
+    nd = NavigationData()
+    for t, r, m in islands:
+        nd.add_island(Island(Transform(t, r), m))
+    nd.update(0.01, 0.25)
+    flat = nd.flatten()
+    got = _cpp_link_flatten(harness, islands)
+    for name in ["n_polys", "n_edges", "n_links", "n_modified", "n_region_numbers", "n_vertices"]:
+        assert got[name] == flat[name], name
+    for name, value in got.items():
+        if isinstance(value, int):
+            continue
+        want = np.asarray(flat[name]).ravel()
+        assert len(value) == len(want), name
+        if value.dtype == np.float32:
+            assert np.array_equal(value.view(np.uint32), want.astype(np.float32).view(np.uint32)), name
+        else:
+            assert np.array_equal(value, want.astype(np.uint32)), name
+    if world == "tiling_3x3":
+        assert got["n_links"] == 192 and got["n_modified"] == 176 and got["n_region_numbers"] == 9
+        assert len(set(got["region_root"].tolist())) == 1          # one connected archipelago
+    if world == "apart":
+        assert got["n_links"] == 0 and (got["node_region_number"] == _abi.NONE).all()
+    if world == "misaligned_pair":
+        assert got["n_links"] == 6 and len(got["modified_verts"]) > 0
 
 
 def _query_case(backend):
