@@ -509,6 +509,9 @@ struct Error : std::runtime_error {
 struct CudaBackend {
   using Ctx = lmb_ctx;
   static int32_t navdata_upload(Ctx* c, const lmb_navdata_desc* d) { return lmb_navdata_upload(c, d); }
+  static int32_t navdata_update(Ctx* c, const lmb_navdata_desc* d, const lmb_nav_remap* r) {
+    return lmb_navdata_update(c, d, r);
+  }
   static int32_t step(Ctx* c, const lmb_agents_in* a, const lmb_characters_in* ch, const lmb_options* o, float dt,
                       const lmb_agents_out* out) {
     return lmb_step(c, a, ch, o, dt, out);

@@ -10,7 +10,9 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
+#include <memory>
 #include <utility>
 #include <vector>
 
@@ -43,6 +45,16 @@ class NavigationData {
   const lmb_navdata_desc& desc() const { return desc_; }
   uint32_t node_id(uint32_t island, uint32_t polygon) const { return poly_begin_[island] + polygon; }
   size_t n_links() const { return links_.size(); }
+  // what identifies a link across rebuilds (the reference keeps the OffMeshLinkId of a link whose islands did not
+  // change, nav_data.rs:352-403): its end nodes as (island index, polygon) and its portal
+  struct LinkInfo {
+    uint32_t src_island, src_polygon, dst_island, dst_polygon;
+    std::array<float, 6> portal;
+  };
+  LinkInfo link_info(size_t l) const {
+    const Link& k = links_[l];
+    return {k.src_island, k.src_polygon, k.dst_island, k.dst_polygon, {k.p0.x, k.p0.y, k.p0.z, k.p1.x, k.p1.y, k.p1.z}};
+  }
 
  private:
   struct V3d {
@@ -429,5 +441,116 @@ class NavigationData {
       node_region_number_;
   lmb_navdata_desc desc_{};
 };
+
+using IslandId = Key;
+
+// `Archipelago` with its islands (lib.rs:139-175, 270-281): islands live in a DenseSlotMap, a change marks the
+// navigation data dirty, and `update` re-links and re-uploads it first — through lmb_navdata_update with the map
+// from the previous flattening's islands / links to the new one, so that exactly the paths `Path::is_valid`
+// keeps survive (the islands deleted or touched since the last update are the invalidated ones).
+template <class Backend>
+class BasicIslandArchipelago : public BasicArchipelago<Backend> {
+  using Base = BasicArchipelago<Backend>;
+
+ public:
+  BasicIslandArchipelago(typename Backend::Ctx* ctx, ArchipelagoOptions options, uint32_t max_agents)
+      : Base(ctx, options, max_agents), ctx_(ctx) {}
+
+  IslandId add_island(Island island) {  // lib.rs:139-146
+    dirty_ = true;
+    return islands_.insert(std::move(island));
+  }
+  void remove_island(IslandId id) {  // lib.rs:161-167
+    if (!islands_.remove(id)) throw std::out_of_range("Island should be present in the Archipelago");
+    dirty_ = true;
+    changed_.push_back(id);
+  }
+  const Island* get_island(IslandId id) const { return islands_.get(id); }
+  // IslandMut (nav_data.rs:1193-1223): handing out mutable access marks the island dirty
+  Island* get_island_mut(IslandId id) {
+    Island* is = islands_.get(id);
+    if (is) {
+      dirty_ = true;
+      changed_.push_back(id);
+    }
+    return is;
+  }
+  const std::vector<IslandId>& get_island_ids() const { return islands_.keys(); }
+  bool set_type_index_cost(uint32_t type_index, float cost) {  // nav_data.rs:229-241: SetTypeIndexCostError on cost <= 0
+    if (!(cost > 0.0f)) return false;
+    for (auto& kv : costs_)
+      if (kv.first == type_index) {
+        kv.second = cost;
+        costs_dirty_ = true;
+        return true;
+      }
+    costs_.emplace_back(type_index, cost);
+    costs_dirty_ = true;
+    return true;
+  }
+  const NavigationData* navigation_data() const { return nav_.get(); }
+
+  void update(float delta_time) {
+    sync_navigation_data();
+    Base::update(delta_time);
+  }
+
+  void sync_navigation_data() {
+    if (nav_ && !dirty_ && !costs_dirty_) return;
+    std::vector<Island> list(islands_.values().begin(), islands_.values().end());
+    const std::vector<IslandId> keys = islands_.keys();
+    auto nav = std::make_unique<NavigationData>(std::move(list), costs_, 0.01f);  // edge_link_distance, lib.rs:273-276
+    if (!nav_) {
+      check(Backend::navdata_upload(ctx_, &nav->desc()));
+    } else {
+      auto is_changed = [&](IslandId k) { return std::find(changed_.begin(), changed_.end(), k) != changed_.end(); };
+      auto new_index = [&](IslandId k) -> uint32_t {
+        for (size_t i = 0; i < keys.size(); i++)
+          if (keys[i] == k) return (uint32_t)i;
+        return LMB_NONE;
+      };
+      std::vector<uint32_t> island_map(keys_.size() + 1, LMB_NONE), link_map(nav_->n_links() + 1, LMB_NONE);
+      for (size_t i = 0; i < keys_.size(); i++)
+        if (!is_changed(keys_[i])) island_map[i] = new_index(keys_[i]);
+      for (size_t l = 0; l < nav_->n_links(); l++) {
+        const NavigationData::LinkInfo o = nav_->link_info(l);
+        const IslandId ks = keys_[o.src_island], kd = keys_[o.dst_island];
+        if (is_changed(ks) || is_changed(kd)) continue;
+        const uint32_t ns = new_index(ks), ndst = new_index(kd);
+        if (ns == LMB_NONE || ndst == LMB_NONE) continue;
+        for (size_t m = 0; m < nav->n_links(); m++) {
+          const NavigationData::LinkInfo c = nav->link_info(m);
+          if (c.src_island == ns && c.dst_island == ndst && c.src_polygon == o.src_polygon &&
+              c.dst_polygon == o.dst_polygon && std::memcmp(c.portal.data(), o.portal.data(), sizeof(float) * 6) == 0) {
+            link_map[l] = (uint32_t)m;
+            break;
+          }
+        }
+      }
+      lmb_nav_remap remap{};
+      remap.struct_size = (uint32_t)sizeof(remap);
+      remap.n_old_islands = (uint32_t)keys_.size(), remap.island_map = island_map.data();
+      remap.n_old_links = (uint32_t)nav_->n_links(), remap.link_map = link_map.data();
+      check(Backend::navdata_update(ctx_, &nav->desc(), &remap));
+    }
+    nav_ = std::move(nav);
+    keys_ = keys;
+    changed_.clear();
+    dirty_ = costs_dirty_ = false;
+  }
+
+ private:
+  void check(int32_t st) {
+    if (st != LMB_OK) throw Error(st, "lmb_navdata_update: " + Backend::last_error(ctx_));
+  }
+  typename Backend::Ctx* ctx_;
+  DenseSlotMap<Island> islands_;
+  std::vector<std::pair<uint32_t, float>> costs_;
+  std::unique_ptr<NavigationData> nav_;
+  std::vector<IslandId> keys_, changed_;  // island order of the uploaded flattening; islands invalidated since
+  bool dirty_ = true, costs_dirty_ = false;
+};
+
+using IslandArchipelago = BasicIslandArchipelago<CudaBackend>;
 
 }  // namespace landmass_b200

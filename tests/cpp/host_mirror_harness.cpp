@@ -16,7 +16,9 @@ struct FnBackend {
   static inline int32_t (*p_step)(void*, const lmb_agents_in*, const lmb_characters_in*, const lmb_options*, float,
                                   const lmb_agents_out*) = nullptr;
   static inline int32_t (*p_results)(void*, lmb_pathing_result*, uint32_t, uint32_t*) = nullptr;
+  static inline int32_t (*p_update)(void*, const lmb_navdata_desc*, const lmb_nav_remap*) = nullptr;
   static int32_t navdata_upload(Ctx* c, const lmb_navdata_desc* d) { return p_upload(c, d); }
+  static int32_t navdata_update(Ctx* c, const lmb_navdata_desc* d, const lmb_nav_remap* r) { return p_update(c, d, r); }
   static int32_t step(Ctx* c, const lmb_agents_in* a, const lmb_characters_in* ch, const lmb_options* o, float dt,
                       const lmb_agents_out* out) {
     return p_step(c, a, ch, o, dt, out);
@@ -213,6 +215,73 @@ int32_t hm_validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t
     out_err[0] = e.a, out_err[1] = e.b;
     return 1 + (int32_t)e.kind;
   }
+}
+
+// A changing world through BasicIslandArchipelago (mirrored line by line in tests/test_host_mirror_cpp.py): three 6 x 6
+// grid islands in a row, A B C; agents 0-2 walk from A to C, agent 3 from C to A.  Frame 8: island D is added above
+// B; frame 14: C is removed; frame 18: B is touched (same mesh set again: its paths are invalidated); frame 22: a
+// new island takes C's place; frame 25: type 0 gets cost 2.  Trace per frame: [4 agents][position xyz, velocity xyz]
+// and [4 states, number of pathing results, sum of explored nodes, number of links].
+int32_t hm_run_world_script(void* ctx, void* fn_upload, void* fn_update, void* fn_step, void* fn_results,
+                            uint32_t frames, float dt, float* trace_f, uint32_t* trace_u, char* error,
+                            uint32_t error_cap) {
+  FnBackend::p_upload = reinterpret_cast<decltype(FnBackend::p_upload)>(fn_upload);
+  FnBackend::p_update = reinterpret_cast<decltype(FnBackend::p_update)>(fn_update);
+  FnBackend::p_step = reinterpret_cast<decltype(FnBackend::p_step)>(fn_step);
+  FnBackend::p_results = reinterpret_cast<decltype(FnBackend::p_results)>(fn_results);
+  try {
+    lb::NavigationMesh grid;
+    for (int y = 0; y <= 6; y++)
+      for (int x = 0; x <= 6; x++) grid.vertices.push_back({(float)x, (float)y, 0.0f});
+    for (uint32_t y = 0; y < 6; y++)
+      for (uint32_t x = 0; x < 6; x++) {
+        const uint32_t v = y * 7 + x;
+        grid.polygons.push_back({v, v + 1, v + 8, v + 7});
+        grid.polygon_type_indices.push_back(0);
+      }
+    const lb::ValidNavigationMesh mesh = grid.validate();
+    auto island_at = [&](float x, float y) { return lb::Island{lb::Transform{{x, y, 0.0f}, 0.0f}, mesh}; };
+    lb::BasicIslandArchipelago<FnBackend> arch(ctx, lb::ArchipelagoOptions::from_agent_radius(0.5f), 16);
+    arch.add_island(island_at(0.0f, 0.0f));
+    const lb::IslandId b = arch.add_island(island_at(6.0f, 0.0f));
+    lb::IslandId c = arch.add_island(island_at(12.0f, 0.0f));
+    auto make = [](lb::Vec3 pos, lb::Vec3 target) {
+      lb::Agent a = lb::Agent::create(pos, {0.0f, 0.0f, 0.0f}, 0.4f, 2.0f, 3.0f);
+      a.current_target = target;
+      return a;
+    };
+    lb::AgentId ids[4] = {arch.add_agent(make({0.7f, 0.8f, 0.0f}, {17.2f, 5.1f, 0.0f})),
+                          arch.add_agent(make({1.5f, 3.1f, 0.0f}, {16.5f, 2.2f, 0.0f})),
+                          arch.add_agent(make({0.9f, 5.2f, 0.0f}, {13.4f, 0.8f, 0.0f})),
+                          arch.add_agent(make({16.8f, 3.3f, 0.0f}, {0.6f, 2.9f, 0.0f}))};
+    for (uint32_t f = 0; f < frames; f++) {
+      if (f == 8) arch.add_island(island_at(6.0f, 6.0f));
+      if (f == 14) arch.remove_island(c);
+      if (f == 18) arch.get_island_mut(b)->mesh = mesh;
+      if (f == 22) c = arch.add_island(island_at(12.0f, 0.0f));
+      if (f == 25) arch.set_type_index_cost(0, 2.0f);
+      arch.update(dt);
+      float* tf = trace_f + (size_t)f * 4 * 6;
+      uint32_t* tu = trace_u + (size_t)f * 7;
+      for (int k = 0; k < 4; k++) {
+        lb::Agent* a = arch.get_agent_mut(ids[k]);
+        a->velocity = a->get_desired_velocity();
+        for (int x = 0; x < 3; x++) a->position[x] = a->position[x] + a->velocity[x] * dt;
+        for (int x = 0; x < 3; x++) tf[6 * k + x] = a->position[x], tf[6 * k + 3 + x] = a->velocity[x];
+        tu[k] = (uint32_t)a->state();
+      }
+      uint32_t explored = 0;
+      for (const auto& r : arch.get_pathing_results()) explored += r.explored_nodes;
+      tu[4] = (uint32_t)arch.get_pathing_results().size();
+      tu[5] = explored;
+      tu[6] = (uint32_t)arch.navigation_data()->n_links();
+    }
+  } catch (const std::exception& e) {
+    std::strncpy(error, e.what(), error_cap - 1);
+    error[error_cap - 1] = 0;
+    return -1;
+  }
+  return 0;
 }
 
 // Several islands -> validate each -> link (boundary links, modified nodes, regions) -> flatten, all in the C++

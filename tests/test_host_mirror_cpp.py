@@ -30,6 +30,7 @@ def harness(tmp_path_factory):
     lib.hm_queries.restype = C.c_int32
     lib.hm_validate_flatten.restype = C.c_int32
     lib.hm_link_flatten.restype = C.c_int32
+    lib.hm_run_world_script.restype = C.c_int32
     return lib
 
 
@@ -323,6 +324,100 @@ def test_cpp_island_linking_matches_the_python_mirror(harness, world):
         assert got["n_links"] == 0 and (got["node_region_number"] == _abi.NONE).all()
     if world == "misaligned_pair":
         assert got["n_links"] == 6 and len(got["modified_verts"]) > 0
+
+
+WORLD_FRAMES, WORLD_DT = 30, 0.25
+
+
+def _python_world_trace(backend):
+    """The script of hm_run_world_script on the Python mirror."""
+    from landmass_b200 import synth
+
+    mesh = synth.grid_mesh(6, 6)
+    arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5), backend=backend)
+    island_at = lambda x, y: Island(Transform((x, y, 0.0), 0.0), mesh)  # noqa: E731
+    arch.add_island(island_at(0.0, 0.0))
+    b = arch.add_island(island_at(6.0, 0.0))
+    c = arch.add_island(island_at(12.0, 0.0))
+
+    def make(pos, target):
+        a = Agent.create(np.array(pos, dtype=np.float32), np.zeros(3, dtype=np.float32), 0.4, 2.0, 3.0)
+        a.current_target = target
+        return a
+
+    ids = [arch.add_agent(make((0.7, 0.8, 0.0), (17.2, 5.1, 0.0))), arch.add_agent(make((1.5, 3.1, 0.0), (16.5, 2.2, 0.0))),
+           arch.add_agent(make((0.9, 5.2, 0.0), (13.4, 0.8, 0.0))), arch.add_agent(make((16.8, 3.3, 0.0), (0.6, 2.9, 0.0)))]
+    dt = np.float32(WORLD_DT)
+    trace_f = np.zeros((WORLD_FRAMES, 4, 6), dtype=np.float32)
+    trace_u = np.zeros((WORLD_FRAMES, 7), dtype=np.uint32)
+    for f in range(WORLD_FRAMES):
+        if f == 8:
+            arch.add_island(island_at(6.0, 6.0))
+        if f == 14:
+            arch.remove_island(c)
+        if f == 18:
+            arch.get_island_mut(b).set_nav_mesh(mesh)
+        if f == 22:
+            c = arch.add_island(island_at(12.0, 0.0))
+        if f == 25:
+            arch.set_type_index_cost(0, 2.0)
+        arch.update(float(dt))
+        for k in range(4):
+            a = arch.get_agent_mut(ids[k])
+            a.velocity = np.asarray(a.get_desired_velocity(), dtype=np.float32).copy()
+            a.position = (np.asarray(a.position, dtype=np.float32) + a.velocity * dt).astype(np.float32)
+            trace_f[f, k, :3] = a.position
+            trace_f[f, k, 3:] = a.velocity
+            trace_u[f, k] = int(a.state())
+        pr = arch.get_pathing_results()
+        trace_u[f, 4] = len(pr)
+        trace_u[f, 5] = sum(r.explored_nodes for r in pr)
+        trace_u[f, 6] = arch._flat["n_links"]
+    return trace_f, trace_u
+
+
+def _cpp_world_trace(harness, ctx, fns):
+    trace_f = np.zeros((WORLD_FRAMES, 4, 6), dtype=np.float32)
+    trace_u = np.zeros((WORLD_FRAMES, 7), dtype=np.uint32)
+    err = C.create_string_buffer(512)
+    st = harness.hm_run_world_script(ctx, *[C.cast(f, C.c_void_p) for f in fns], C.c_uint32(WORLD_FRAMES),
+                                     C.c_float(WORLD_DT), trace_f.ctypes.data_as(C.c_void_p),
+                                     trace_u.ctypes.data_as(C.c_void_p), err, C.c_uint32(512))
+    assert st == 0, err.value.decode()
+    return trace_f, trace_u
+
+
+def _check_world(py, cpp):
+    assert np.array_equal(py[1], cpp[1]), "states / pathing results / link counts differ"
+    assert np.array_equal(py[0].view(np.uint32), cpp[0].view(np.uint32)), "positions / velocities differ"
+    links = py[1][:, 6]
+    assert links[0] == 24 and links[8] == 36 and links[14] == 24 and links[22] == 36   # 6 edges x 2 per border
+    n_results = py[1][:, 4]
+    assert n_results[0] == 4                       # everybody plans in the first frame
+    assert n_results[8] == 0                       # a new island invalidates nothing
+    assert n_results[14] >= 1 and n_results[18] >= 1 and n_results[25] == 0   # removal / touch re-plan, costs do not
+
+
+def test_cpp_island_archipelago_matches_the_python_mirror_on_the_oracle(harness):
+    """`BasicIslandArchipelago` (islands in a DenseSlotMap, re-link + lmb_navdata_update with the island / link remap
+    on change) against the Python `Archipelago` through a changing world: islands added, removed, touched, type costs
+    changed.  Identical traces mean identical descriptors, identical remaps (the same paths survive each change)
+    and identical packing."""
+    from oracle import oracle_py
+    from oracle.oracle_py import OracleBackend
+
+    py = _python_world_trace(OracleBackend())
+    lib = oracle_py.load()
+    lib.orc_create.restype = C.c_void_p
+    # the oracle wants navigation data at creation: any descriptor will do, the script uploads its own first
+    from landmass_b200 import synth
+
+    desc, keep = _abi.make_navdata_desc(synth.single_island_flat(synth.grid_mesh(2, 2)))
+    ctx = C.c_void_p(lib.orc_create(C.byref(desc), C.c_uint32(0)))
+    cpp = _cpp_world_trace(harness, ctx, (lib.orc_navdata_upload, lib.orc_navdata_update, lib.orc_step,
+                                         lib.orc_pathing_results))
+    _check_world(py, cpp)
+    del keep
 
 
 def _query_case(backend):
