@@ -252,7 +252,7 @@ class DenseSlotMap {
 // NavigationMesh::validate (nav_mesh.rs:19-35, 187-407) and a single-island NavigationData.
 // Island LINKING (boundary links, modified nodes, animation links: nav_data.rs:326-1180) is mirrored in
 // Python only; a world of one island — or one whose flattened descriptor the caller brings — is what this
-// header can feed on its own.  Height meshes are not mirrored here either.
+// header can feed on its own.
 // ---------------------------------------------------------------------------------------------
 struct ValidationError : std::runtime_error {  // nav_mesh.rs:131-162
   enum Kind {
@@ -261,7 +261,11 @@ struct ValidationError : std::runtime_error {  // nav_mesh.rs:131-162
     InvalidVertexIndexInPolygon,
     DegenerateEdgeInPolygon,
     DoublyConnectedEdge,
-    ConcavePolygon
+    ConcavePolygon,
+    IncorrectNumberOfPolygons,  // height mesh (nav_mesh.rs:410-479): expected, found
+    InvalidPolygonIndices,      // height polygon index
+    InvalidIndexInTriangle,     // triangle index, vertex index
+    ClockwiseTriangle           // height polygon index
   } kind;
   size_t a, b;  // the variant's payload (polygon index / the two vertex indices / the two lengths)
   ValidationError(Kind k, size_t a_, size_t b_ = 0)
@@ -282,19 +286,61 @@ struct ValidNavigationMesh {
   bool bounds_empty = true;
   std::array<float, 6> mesh_bounds{};       // min xyz, max xyz
   std::vector<std::pair<uint32_t, uint32_t>> boundary_edges;  // (polygon, edge), ascending
+  // optional height mesh (nav_mesh.rs:503-521): per polygon {base vertex, vertex count, base triangle, triangle count}
+  bool has_height = false;
+  std::vector<uint32_t> hpoly;   // [P*4]
+  std::vector<float> hverts;     // [HV*3]
+  std::vector<uint8_t> htris;    // [HT*3] indices relative to the polygon's base vertex
   size_t n_polys() const { return poly_type.size(); }
+};
+
+struct HeightPolygon {  // nav_mesh.rs:74-90
+  uint32_t base_vertex_index, vertex_count, base_triangle_index, triangle_count;
+};
+struct HeightNavigationMesh {  // nav_mesh.rs:52-68
+  std::vector<HeightPolygon> polygons;
+  std::vector<Vec3> vertices;
+  std::vector<std::array<uint32_t, 3>> triangles;
 };
 
 struct NavigationMesh {  // nav_mesh.rs:19-35 (vertices already in landmass coordinates; polygons counter-clockwise)
   std::vector<Vec3> vertices;
   std::vector<std::vector<uint32_t>> polygons;
   std::vector<uint32_t> polygon_type_indices;
+  std::optional<HeightNavigationMesh> height_mesh;
 
   ValidNavigationMesh validate() const {
     using VE = ValidationError;
     const size_t P = polygons.size(), V = vertices.size();
     if (P != polygon_type_indices.size()) throw VE(VE::TypeIndicesHaveWrongLength, P, polygon_type_indices.size());
     ValidNavigationMesh m;
+    if (height_mesh) {  // HeightNavigationMesh::validate (nav_mesh.rs:410-479), before the polygons are looked at
+      const HeightNavigationMesh& h = *height_mesh;
+      if (h.polygons.size() != P) throw VE(VE::IncorrectNumberOfPolygons, P, h.polygons.size());
+      for (size_t pi = 0; pi < P; pi++) {
+        const HeightPolygon& hp = h.polygons[pi];
+        const size_t last = (size_t)hp.base_triangle_index + hp.triangle_count;
+        if (last > h.triangles.size()) throw VE(VE::InvalidPolygonIndices, pi);
+        for (size_t ti = hp.base_triangle_index; ti < last; ti++) {
+          size_t real[3];
+          for (int k = 0; k < 3; k++) {
+            const size_t r = (size_t)hp.base_vertex_index + h.triangles[ti][k];
+            if (r >= h.vertices.size() || h.triangles[ti][k] >= hp.vertex_count) throw VE(VE::InvalidIndexInTriangle, ti, r);
+            real[k] = r;
+          }
+          const Vec3 &a = h.vertices[real[0]], &b = h.vertices[real[1]], &c = h.vertices[real[2]];
+          const float abx = b[0] - a[0], aby = b[1] - a[1], acx = c[0] - a[0], acy = c[1] - a[1];
+          const float lhs = abx * acy, rhs = aby * acx;
+          if (lhs - rhs < 0.0f) throw VE(VE::ClockwiseTriangle, pi);
+        }
+        const uint32_t q[4] = {hp.base_vertex_index, hp.vertex_count, hp.base_triangle_index, hp.triangle_count};
+        m.hpoly.insert(m.hpoly.end(), q, q + 4);
+      }
+      m.has_height = true;
+      for (const Vec3& v : h.vertices) m.hverts.insert(m.hverts.end(), v.begin(), v.end());
+      for (const auto& t : h.triangles)
+        for (int k = 0; k < 3; k++) m.htris.push_back((uint8_t)t[k]);
+    }
     for (const Vec3& v : vertices) m.vertices.insert(m.vertices.end(), v.begin(), v.end());
     m.poly_edge_begin.assign(P + 1, 0u);
     // the reference discovers errors polygon by polygon: size, vertex range, then per edge degenerate /
@@ -396,10 +442,23 @@ struct NavigationMesh {  // nav_mesh.rs:19-35 (vertices already in landmass coor
         m.poly_center[3 * p + k] = sum[k] / (float)polygons[p].size();
       }
     }
-    m.bounds_empty = V == 0;
-    if (V) {
+    // with a height mesh the bounds come from its vertices (nav_mesh.rs:334-345)
+    const std::vector<Vec3>& bsrc = height_mesh ? height_mesh->vertices : vertices;
+    if (height_mesh)
+      for (size_t p = 0; p < P; p++) {
+        const HeightPolygon& hp = height_mesh->polygons[p];
+        float lo[3] = {1.0f, 1.0f, 1.0f}, hi[3] = {0.0f, 0.0f, 0.0f};  // Empty
+        if (hp.vertex_count) {
+          for (int k = 0; k < 3; k++) lo[k] = INFINITY, hi[k] = -INFINITY;
+          for (uint32_t v = hp.base_vertex_index; v < hp.base_vertex_index + hp.vertex_count; v++)
+            for (int k = 0; k < 3; k++) lo[k] = std::fmin(lo[k], bsrc[v][k]), hi[k] = std::fmax(hi[k], bsrc[v][k]);
+        }
+        for (int k = 0; k < 3; k++) m.poly_bounds[6 * p + k] = lo[k], m.poly_bounds[6 * p + 3 + k] = hi[k];
+      }
+    m.bounds_empty = bsrc.empty();
+    if (!bsrc.empty()) {
       for (int k = 0; k < 3; k++) m.mesh_bounds[k] = INFINITY, m.mesh_bounds[3 + k] = -INFINITY;
-      for (const Vec3& v : vertices)
+      for (const Vec3& v : bsrc)
         for (int k = 0; k < 3; k++) {
           m.mesh_bounds[k] = std::fmin(m.mesh_bounds[k], v[k]);
           m.mesh_bounds[3 + k] = std::fmax(m.mesh_bounds[3 + k], v[k]);
@@ -455,6 +514,12 @@ class SingleIslandNavigationData {
     d.n_type_costs = (uint32_t)cost_index_.size();
     d.type_cost_index = cost_index_.data(), d.type_cost_value = cost_value_.data();
     d.node_link_begin = node_link_begin_.data();
+    if (mesh_.has_height) {
+      has_height_ = 1;
+      d.island_has_height = &has_height_, d.hpoly = mesh_.hpoly.data();
+      d.n_hverts = (uint32_t)(mesh_.hverts.size() / 3), d.hverts = mesh_.hverts.data();
+      d.n_htris = (uint32_t)(mesh_.htris.size() / 3), d.htris = mesh_.htris.data();
+    }
     d.modified_edge_begin = zero2_, d.modified_vert_begin = zero2_;
     d.node_region_number = node_region_number_.data();
   }
@@ -469,6 +534,7 @@ class SingleIslandNavigationData {
   float rotation_ = 0.0f;
   std::array<float, 6> bounds_{};
   uint32_t poly_begin_[2]{}, vert_begin_[2]{}, zero2_[2] = {0u, 0u};
+  uint8_t has_height_ = 0;
   std::vector<uint32_t> cost_index_, node_link_begin_, node_region_number_;
   std::vector<float> cost_value_;
   lmb_navdata_desc desc_{};

@@ -2,7 +2,7 @@
 // (nav_data.rs:326-514 boundary links, 827-1011 modified nodes, 1089-1156 region connectivity) and of the
 // flattening of a world of several islands into `lmb_navdata_desc`.  Companion of landmass_b200.hpp; the same
 // restatement as landmass_b200/linking.py + nav_data.flatten (Python), checked against it array by array in
-// tests/test_host_mirror_cpp.py.  Not mirrored here: animation links, height meshes.
+// tests/test_host_mirror_cpp.py.  Not mirrored here: animation links.
 //
 // Canonical orders replace the reference's HashMap / HashSet iteration orders exactly as in the Python mirror
 // (SURVEY.md Appendix E): islands in the order given (= DenseSlotMap order), boundary edges by (polygon, edge),
@@ -359,6 +359,20 @@ class NavigationData {
       poly_region_.insert(poly_region_.end(), m.poly_region.begin(), m.poly_region.end());
       poly_bounds_.insert(poly_bounds_.end(), m.poly_bounds.begin(), m.poly_bounds.end());
       poly_center_.insert(poly_center_.end(), m.poly_center.begin(), m.poly_center.end());
+      // height meshes: base vertex / triangle become global; islands without one get empty height polygons
+      if (m.has_height) {
+        any_height_ = true;
+        const uint32_t hvb = (uint32_t)(hverts_.size() / 3), htb = (uint32_t)(htris_.size() / 3);
+        for (size_t p = 0; p < m.n_polys(); p++) {
+          hpoly_.push_back(m.hpoly[4 * p] + hvb), hpoly_.push_back(m.hpoly[4 * p + 1]);
+          hpoly_.push_back(m.hpoly[4 * p + 2] + htb), hpoly_.push_back(m.hpoly[4 * p + 3]);
+        }
+        hverts_.insert(hverts_.end(), m.hverts.begin(), m.hverts.end());
+        htris_.insert(htris_.end(), m.htris.begin(), m.htris.end());
+      } else {
+        hpoly_.insert(hpoly_.end(), 4 * m.n_polys(), 0u);
+      }
+      has_height_.push_back(m.has_height ? 1 : 0);
       poly_begin_[i + 1] = pb + (uint32_t)m.n_polys();
       vert_begin_[i + 1] = vb + (uint32_t)(m.vertices.size() / 3);
     }
@@ -414,6 +428,11 @@ class NavigationData {
     d.poly_bounds = poly_bounds_.data(), d.poly_center = poly_center_.data();
     d.n_type_costs = (uint32_t)cost_index_.size();
     d.type_cost_index = cost_index_.data(), d.type_cost_value = cost_value_.data();
+    if (any_height_) {
+      d.island_has_height = has_height_.data(), d.hpoly = hpoly_.data();
+      d.n_hverts = (uint32_t)(hverts_.size() / 3), d.hverts = hverts_.data();
+      d.n_htris = (uint32_t)(htris_.size() / 3), d.htris = htris_.data();
+    }
     d.n_links = nl;
     d.link_dst_node = link_dst_.data(), d.link_dst_type = link_dst_type_.data(), d.link_portal = link_portal_.data();
     d.link_kind = link_kind_.data(), d.link_reverse = link_reverse_.data(), d.link_dst_portal = link_portal_.data();
@@ -439,6 +458,10 @@ class NavigationData {
       poly_region_, cost_index_, link_src_, link_dst_, link_dst_type_, link_kind_, link_reverse_, link_anim_kind_,
       link_anim_id_, node_link_begin_, node_links_, mod_node_, mod_edge_begin_, mod_edges_, mod_vert_begin_,
       node_region_number_;
+  std::vector<uint32_t> hpoly_;
+  std::vector<float> hverts_;
+  std::vector<uint8_t> htris_, has_height_;
+  bool any_height_ = false;
   lmb_navdata_desc desc_{};
 };
 

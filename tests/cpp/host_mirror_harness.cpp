@@ -176,11 +176,43 @@ int32_t hm_queries(void* ctx, void* fn_upload, void* fn_sample, void* fn_straigh
 // NavigationMesh::validate + SingleIslandNavigationData on caller-provided input; the flattened arrays are
 // copied out for comparison with the Python mirror.  Returns 0, or 1 + ValidationError::Kind with the
 // payload in out_err[0..1].
+static int32_t validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t n_polys, const uint32_t* poly_begin,
+                                const uint32_t* poly_verts, uint32_t n_types, const uint32_t* types,
+                                const float* translation, float rotation, uint64_t* out_err, uint32_t* out_u32,
+                                float* out_f32, float* out_island, const lb::HeightNavigationMesh* height,
+                                uint32_t* out_hu, float* out_hf);
+
 int32_t hm_validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t n_polys, const uint32_t* poly_begin,
                             const uint32_t* poly_verts, uint32_t n_types, const uint32_t* types,
                             const float* translation, float rotation, uint64_t* out_err, uint32_t* out_u32,
                             float* out_f32, float* out_island) {
+  return validate_flatten(n_vertices, vertices, n_polys, poly_begin, poly_verts, n_types, types, translation, rotation,
+                          out_err, out_u32, out_f32, out_island, nullptr, nullptr, nullptr);
+}
+
+// The same with a height mesh: hpolys [n_hpolys*4], hverts [n_hverts*3], htris [n_htris*3].  On success out_hu
+// receives n_hverts, n_htris, hpoly [P*4], htris [HT*3] (one word each) and out_hf the height vertices.
+int32_t hm_validate_flatten_height(uint32_t n_vertices, const float* vertices, uint32_t n_polys, const uint32_t* poly_begin,
+                                   const uint32_t* poly_verts, uint32_t n_types, const uint32_t* types,
+                                   const float* translation, float rotation, uint32_t n_hpolys, const uint32_t* hpolys,
+                                   uint32_t n_hverts, const float* hverts, uint32_t n_htris, const uint32_t* htris,
+                                   uint64_t* out_err, uint32_t* out_u32, float* out_f32, float* out_island,
+                                   uint32_t* out_hu, float* out_hf) {
+  lb::HeightNavigationMesh h;
+  for (uint32_t p = 0; p < n_hpolys; p++) h.polygons.push_back({hpolys[4 * p], hpolys[4 * p + 1], hpolys[4 * p + 2], hpolys[4 * p + 3]});
+  for (uint32_t v = 0; v < n_hverts; v++) h.vertices.push_back({hverts[3 * v], hverts[3 * v + 1], hverts[3 * v + 2]});
+  for (uint32_t t = 0; t < n_htris; t++) h.triangles.push_back({htris[3 * t], htris[3 * t + 1], htris[3 * t + 2]});
+  return validate_flatten(n_vertices, vertices, n_polys, poly_begin, poly_verts, n_types, types, translation, rotation,
+                          out_err, out_u32, out_f32, out_island, &h, out_hu, out_hf);
+}
+
+static int32_t validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t n_polys, const uint32_t* poly_begin,
+                                const uint32_t* poly_verts, uint32_t n_types, const uint32_t* types,
+                                const float* translation, float rotation, uint64_t* out_err, uint32_t* out_u32,
+                                float* out_f32, float* out_island, const lb::HeightNavigationMesh* height,
+                                uint32_t* out_hu, float* out_hf) {
   lb::NavigationMesh mesh;
+  if (height) mesh.height_mesh = *height;
   for (uint32_t v = 0; v < n_vertices; v++) mesh.vertices.push_back({vertices[3 * v], vertices[3 * v + 1], vertices[3 * v + 2]});
   for (uint32_t p = 0; p < n_polys; p++)
     mesh.polygons.emplace_back(poly_verts + poly_begin[p], poly_verts + poly_begin[p + 1]);
@@ -210,6 +242,14 @@ int32_t hm_validate_flatten(uint32_t n_vertices, const float* vertices, uint32_t
     out_island[3] = d.island_rotation[0];
     std::memcpy(out_island + 4, d.island_bounds, 6 * sizeof(float));
     out_err[0] = d.n_edges, out_err[1] = d.n_links + d.n_modified + d.n_region_numbers + d.n_possible_links;
+    if (height) {
+      if (!d.island_has_height || !d.island_has_height[0]) return -2;
+      uint32_t* hu = out_hu;
+      *hu++ = d.n_hverts, *hu++ = d.n_htris;
+      std::memcpy(hu, d.hpoly, (size_t)d.n_polys * 4 * sizeof(uint32_t)), hu += (size_t)d.n_polys * 4;
+      for (size_t k = 0; k < 3 * (size_t)d.n_htris; k++) *hu++ = d.htris[k];
+      std::memcpy(out_hf, d.hverts, 3 * (size_t)d.n_hverts * sizeof(float));
+    }
     return 0;
   } catch (const lb::ValidationError& e) {
     out_err[0] = e.a, out_err[1] = e.b;

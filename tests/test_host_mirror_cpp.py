@@ -29,6 +29,7 @@ def harness(tmp_path_factory):
     lib.hm_run_script.restype = C.c_int32
     lib.hm_queries.restype = C.c_int32
     lib.hm_validate_flatten.restype = C.c_int32
+    lib.hm_validate_flatten_height.restype = C.c_int32
     lib.hm_link_flatten.restype = C.c_int32
     lib.hm_run_world_script.restype = C.c_int32
     return lib
@@ -118,10 +119,11 @@ def check(py, cpp):
 
 
 KINDS = ["TypeIndicesHaveWrongLength", "NotEnoughVerticesInPolygon", "InvalidVertexIndexInPolygon",
-         "DegenerateEdgeInPolygon", "DoublyConnectedEdge", "ConcavePolygon"]
+         "DegenerateEdgeInPolygon", "DoublyConnectedEdge", "ConcavePolygon", "IncorrectNumberOfPolygons",
+         "InvalidPolygonIndices", "InvalidIndexInTriangle", "ClockwiseTriangle"]
 
 
-def cpp_validate_flatten(harness, vertices, polygons, types, translation=(0.0, 0.0, 0.0), rotation=0.0):
+def cpp_validate_flatten(harness, vertices, polygons, types, translation=(0.0, 0.0, 0.0), rotation=0.0, height=None):
     v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
     begin = np.zeros(len(polygons) + 1, dtype=np.uint32)
     begin[1:] = np.cumsum([len(p) for p in polygons])
@@ -134,8 +136,21 @@ def cpp_validate_flatten(harness, vertices, polygons, types, translation=(0.0, 0
     err = np.zeros(2, dtype=np.uint64)
     tr = np.asarray(translation, dtype=np.float32)
     p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
-    st = harness.hm_validate_flatten(C.c_uint32(V), p_(v), C.c_uint32(P), p_(begin), p_(pv), C.c_uint32(len(t)), p_(t),
-                                     p_(tr), C.c_float(rotation), p_(err), p_(out_u), p_(out_f), p_(out_i))
+    if height is None:
+        st = harness.hm_validate_flatten(C.c_uint32(V), p_(v), C.c_uint32(P), p_(begin), p_(pv), C.c_uint32(len(t)), p_(t),
+                                         p_(tr), C.c_float(rotation), p_(err), p_(out_u), p_(out_f), p_(out_i))
+    else:
+        hp = np.array([[q.base_vertex_index, q.vertex_count, q.base_triangle_index, q.triangle_count]
+                       for q in height.polygons], dtype=np.uint32).reshape(-1, 4)
+        hv = np.ascontiguousarray(height.vertices, dtype=np.float32).reshape(-1, 3)
+        ht = np.ascontiguousarray(height.triangles, dtype=np.uint32).reshape(-1, 3)
+        out_hu = np.zeros(2 + 4 * P + 3 * len(ht) + 4, dtype=np.uint32)
+        out_hf = np.zeros(3 * len(hv) + 3, dtype=np.float32)
+        st = harness.hm_validate_flatten_height(
+            C.c_uint32(V), p_(v), C.c_uint32(P), p_(begin), p_(pv), C.c_uint32(len(t)), p_(t), p_(tr), C.c_float(rotation),
+            C.c_uint32(len(hp)), p_(hp), C.c_uint32(len(hv)), p_(hv), C.c_uint32(len(ht)), p_(ht), p_(err), p_(out_u),
+            p_(out_f), p_(out_i), p_(out_hu), p_(out_hf))
+    assert st >= 0
     if st != 0:
         return KINDS[st - 1], int(err[0]), int(err[1])
     u = iter(np.split(out_u[:5 * P + 3 * E + 6], np.cumsum([P + 1, E, E, E, P, P, P + 1, P, 2, 2])[:-1]))
@@ -144,7 +159,11 @@ def cpp_validate_flatten(harness, vertices, polygons, types, translation=(0.0, 0
                 poly_type=next(u), poly_region=next(u), node_link_begin=next(u), node_region_number=next(u),
                 island_poly_begin=next(u), island_vert_begin=next(u), vertices=next(f).reshape(-1, 3),
                 poly_bounds=next(f).reshape(-1, 6), poly_center=next(f).reshape(-1, 3), island=out_i,
-                n_edges=int(err[0]), n_other=int(err[1]))
+                n_edges=int(err[0]), n_other=int(err[1]),
+                **({} if height is None else dict(
+                    n_hverts=int(out_hu[0]), n_htris=int(out_hu[1]), hpoly=out_hu[2:2 + 4 * P].reshape(-1, 4),
+                    htris=out_hu[2 + 4 * P:2 + 4 * P + 3 * int(out_hu[1])].reshape(-1, 3),
+                    hverts=out_hf[:3 * int(out_hu[0])].reshape(-1, 3))))
 
 
 @pytest.mark.parametrize("mesh_kind", ["grid", "maze", "irregular", "rosette12", "two_regions"])
@@ -206,7 +225,52 @@ def test_cpp_validation_errors_match_the_python_mirror(harness):
         want_args = tuple(int(a) for a in e.value.args_) + (0,) * (2 - len(e.value.args_))
         assert got == (e.value.kind,) + want_args, (polygons, got, e.value)
         seen.add(got[0])
-    assert seen == set(KINDS)
+    assert seen == set(KINDS[:6])
+
+
+def test_cpp_height_mesh_validation_and_flatten_match_the_python_mirror(harness):
+    """HeightNavigationMesh::validate (nav_mesh.rs:410-479): the flattened height arrays and the bounds taken from the
+    height vertices, and the four height-mesh errors, against the Python mirror."""
+    from landmass_b200 import HeightNavigationMesh, HeightPolygon, NavigationMesh, ValidationError
+    from landmass_b200.nav_data import NavigationData
+    from tests.helpers import create_height_mesh
+
+    verts = [(0.0, 0.0, 0.0), (2.0, 0.0, 0.0), (2.0, 2.0, 0.0), (0.0, 2.0, 0.0), (4.0, 0.0, 0.0), (4.0, 2.0, 0.0)]
+    polys = [[0, 1, 2, 3], [1, 4, 5, 2]]
+    hsrc = [(0.0, 0.0, 0.3), (2.0, 0.0, 0.1), (2.0, 2.0, 0.4), (0.0, 2.0, 0.2), (1.0, 1.0, 1.5), (4.0, 0.0, -0.2),
+            (4.0, 2.0, 0.6)]
+    good = create_height_mesh(hsrc, [[[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], [[1, 5, 6, 2]]])
+    mesh = NavigationMesh(vertices=verts, polygons=polys, polygon_type_indices=[0, 1], height_mesh=good).validate()
+    nd = NavigationData()
+    nd.add_island(Island(Transform((1.0, 2.0, 3.0), 0.0), mesh))
+    nd.update(0.01, 0.25)
+    flat = nd.flatten()
+    got = cpp_validate_flatten(harness, verts, polys, [0, 1], (1.0, 2.0, 3.0), 0.0, height=good)
+    assert isinstance(got, dict), got
+    assert got["n_hverts"] == flat["n_hverts"] and got["n_htris"] == flat["n_htris"]
+    assert np.array_equal(got["hpoly"], flat["hpoly"]) and np.array_equal(got["htris"], flat["htris"].astype(np.uint32))
+    for name in ["hverts", "poly_bounds", "poly_center", "vertices"]:
+        assert np.array_equal(got[name].view(np.uint32), np.asarray(flat[name], dtype=np.float32).view(np.uint32)), name
+    assert np.array_equal(got["island"][4:], flat["island_bounds"][0]) and got["island"][9] == np.float32(1.5)
+
+    one = HeightPolygon(0, 3, 0, 1)
+    tri_v = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)]
+    bad = [
+        HeightNavigationMesh(polygons=[one], vertices=tri_v, triangles=[[0, 1, 2]]),                     # IncorrectNumberOfPolygons
+        HeightNavigationMesh(polygons=[one, HeightPolygon(0, 3, 1, 1)], vertices=tri_v, triangles=[[0, 1, 2]]),  # InvalidPolygonIndices
+        HeightNavigationMesh(polygons=[one, HeightPolygon(0, 2, 0, 1)], vertices=tri_v, triangles=[[0, 1, 2]]),  # InvalidIndexInTriangle
+        HeightNavigationMesh(polygons=[one, HeightPolygon(0, 3, 1, 1)], vertices=tri_v,
+                             triangles=[[0, 1, 2], [0, 2, 1]]),                                            # ClockwiseTriangle
+    ]
+    seen = set()
+    for h in bad:
+        with pytest.raises(ValidationError) as e:
+            NavigationMesh(vertices=verts, polygons=polys, polygon_type_indices=[0, 1], height_mesh=h).validate()
+        got = cpp_validate_flatten(harness, verts, polys, [0, 1], height=h)
+        want_args = tuple(int(a) for a in e.value.args_) + (0,) * (2 - len(e.value.args_))
+        assert got == (e.value.kind,) + want_args, (got, e.value)
+        seen.add(got[0])
+    assert seen == set(KINDS[6:])
 
 
 def test_cpp_host_mirror_builds_its_own_navigation_data(harness):
