@@ -18,9 +18,10 @@
 // What `update` does here is what `Archipelago::update` keeps on the host: pack the
 // agents in DenseSlotMap order, one lmb_step, scatter desired velocity / state / reached link back,
 // translate `PathingResult.agent` from an index to the AgentId.  Navigation data enters as the
-// flattened `lmb_navdata_desc`: `NavigationMesh::validate` and a single-island `NavigationData` are
-// mirrored below (SingleIslandNavigationData); worlds of several linked islands, animation links and
-// height meshes bring the descriptor the Python mirror (or the caller's port of nav_data.rs) flattens.
+// flattened `lmb_navdata_desc`: `NavigationMesh::validate` (height meshes included) and a single-island
+// `NavigationData` are mirrored below (SingleIslandNavigationData), worlds of several linked islands in
+// landmass_b200_linking.hpp; only worlds with ANIMATION LINKS bring the descriptor the Python mirror (or
+// the caller's port of nav_data.rs:516-825) flattens.
 //
 // Coordinates are landmass-internal (XYZ, z up): `CoordinateSystem::to_landmass` stays with the caller.
 // The entry points are reached through a `Backend` policy class so that the same code runs on the
@@ -250,9 +251,8 @@ class DenseSlotMap {
 
 // ---------------------------------------------------------------------------------------------
 // NavigationMesh::validate (nav_mesh.rs:19-35, 187-407) and a single-island NavigationData.
-// Island LINKING (boundary links, modified nodes, animation links: nav_data.rs:326-1180) is mirrored in
-// Python only; a world of one island — or one whose flattened descriptor the caller brings — is what this
-// header can feed on its own.
+// Island linking (boundary links, modified nodes, regions) is in landmass_b200_linking.hpp; animation links
+// are mirrored in Python only.
 // ---------------------------------------------------------------------------------------------
 struct ValidationError : std::runtime_error {  // nav_mesh.rs:131-162
   enum Kind {
