@@ -141,6 +141,14 @@ class Agent {
     using_animation_link_ = false;
   }
   bool is_using_animation_link() const { return using_animation_link_; }
+  // feature `debug-avoidance` (agent.rs:105-108, debug.rs:415-503): the constraints of the last update that ran
+  // avoidance for this agent while keep_avoidance_data was set; lines are {point.xy, direction.xy}
+  // (ConstraintLine.normal = (-direction.y, direction.x))
+  struct AvoidanceData {
+    bool fell_back = false;  // DebugData::Fallback (else Satisfied: `fallback` is empty)
+    std::vector<std::array<float, 4>> original, fallback;
+  };
+  const AvoidanceData* avoidance_data() const { return has_avoidance_data_ ? &avoidance_data_ : nullptr; }
 
  private:
   template <class B>
@@ -150,6 +158,8 @@ class Agent {
   AgentState state_ = AgentState::Idle;
   std::optional<ReachedAnimationLink> current_animation_link_;
   bool using_animation_link_ = false;
+  AvoidanceData avoidance_data_;
+  bool has_avoidance_data_ = false;
 };
 
 // character.rs:14-31
@@ -589,6 +599,13 @@ struct CudaBackend {
                                uint32_t* out_nodes) {
     return lmb_sample_points(c, n, points, o, out_points, out_nodes);
   }
+  static int32_t agent_path(Ctx* c, uint32_t slot, uint32_t* nodes, uint32_t* portals, uint32_t cap, uint32_t* len) {
+    return lmb_agent_path(c, slot, nodes, portals, cap, len);
+  }
+  static int32_t agent_avoidance_constraints(Ctx* c, uint32_t agent_index, uint32_t cap, float* lines, uint32_t* n_orig,
+                                             uint32_t* n_fallback, uint32_t* ran) {
+    return lmb_agent_avoidance_constraints(c, agent_index, cap, lines, n_orig, n_fallback, ran);
+  }
   static int32_t find_straight_paths(Ctx* c, uint32_t n, const uint32_t* sn, const float* sp, const uint32_t* en,
                                      const float* ep, const uint32_t* ob, const uint32_t* ot, const float* oc,
                                      uint32_t* succ, uint32_t* begin, uint32_t* kind, float* pts, uint32_t* link,
@@ -700,6 +717,24 @@ class BasicArchipelago {
     }
   }
 
+  // `agent.current_path` read-back for debug drawing (debug.rs:300-350): the corridor as flat (node id, portal code)
+  // pairs — portal = edge index, 0x80000000 | link index, or LMB_NONE behind the last node; empty = no path.
+  std::pair<std::vector<uint32_t>, std::vector<uint32_t>> agent_path(AgentId id) {
+    std::vector<uint32_t> nodes(64), portals(64);
+    uint32_t len = 0;
+    for (;;) {
+      const int32_t st = Backend::agent_path(ctx_, id.idx, nodes.data(), portals.data(), (uint32_t)nodes.size(), &len);
+      if (st == LMB_ERR_CAPACITY) {
+        nodes.resize(len), portals.resize(len);
+        continue;
+      }
+      check(st, "lmb_agent_path");
+      break;
+    }
+    nodes.resize(len), portals.resize(len);
+    return {nodes, portals};
+  }
+
   // `Archipelago::update` (lib.rs:270-534): pack -> lmb_step -> scatter
   void update(float delta_time) {
     const std::vector<AgentId>& keys = agents_.keys();
@@ -724,7 +759,8 @@ class BasicArchipelago {
       }
       if (a.paused) f |= LMB_AGENT_PAUSED;
       if (a.using_animation_link_) f |= LMB_AGENT_USING_ANIMATION_LINK;
-      if (a.keep_avoidance_data) f |= LMB_AGENT_KEEP_AVOIDANCE_DATA;
+      // (an agent that stopped asking still has to learn whether avoidance ran, to drop its old data)
+      if (a.keep_avoidance_data || a.has_avoidance_data_) f |= LMB_AGENT_KEEP_AVOIDANCE_DATA;
       if (a.permitted_animation_links.all) {
         f |= LMB_AGENT_PERMIT_ALL_LINKS;
       } else {
@@ -807,6 +843,38 @@ class BasicArchipelago {
         a.current_animation_link_ = r;
       } else {
         a.current_animation_link_.reset();
+      }
+      if (a.keep_avoidance_data || a.has_avoidance_data_) {
+        // agent.avoidance_data = agent.keep_avoidance_data.then_some(debug_data), only for the agents avoidance
+        // visited (avoidance.rs:83-87, 161-172)
+        uint32_t n_orig = 0, n_fb = 0, ran = 0, cap = 64;
+        std::vector<float> lines;
+        for (;;) {
+          lines.resize(4 * (size_t)cap);
+          const int32_t st = Backend::agent_avoidance_constraints(ctx_, i, cap, lines.data(), &n_orig, &n_fb, &ran);
+          if (st == LMB_ERR_CAPACITY) {
+            cap = n_orig + n_fb;
+            continue;
+          }
+          check(st, "lmb_agent_avoidance_constraints");
+          break;
+        }
+        if (ran) {
+          if (!a.keep_avoidance_data) {
+            a.has_avoidance_data_ = false;
+            a.avoidance_data_ = Agent::AvoidanceData{};
+          } else {
+            Agent::AvoidanceData d;
+            d.fell_back = ran == 2;
+            for (uint32_t k = 0; k < n_orig + n_fb; k++) {
+              const std::array<float, 4> l{lines[4 * (size_t)k], lines[4 * (size_t)k + 1], lines[4 * (size_t)k + 2],
+                                           lines[4 * (size_t)k + 3]};
+              (k < n_orig ? d.original : d.fallback).push_back(l);
+            }
+            a.avoidance_data_ = std::move(d);
+            a.has_avoidance_data_ = true;
+          }
+        }
       }
     }
     // lib.rs:406-410: one result per agent that re-planned, in agent order

@@ -26,6 +26,20 @@ struct FnBackend {
   static int32_t pathing_results(Ctx* c, lmb_pathing_result* out, uint32_t cap, uint32_t* n) {
     return p_results(c, out, cap, n);
   }
+  static inline int32_t (*p_path)(void*, uint32_t, uint32_t*, uint32_t*, uint32_t, uint32_t*) = nullptr;
+  static inline int32_t (*p_constraints)(void*, uint32_t, uint32_t, float*, uint32_t*, uint32_t*, uint32_t*) = nullptr;
+  static int32_t agent_path(Ctx* c, uint32_t slot, uint32_t* nodes, uint32_t* portals, uint32_t cap, uint32_t* len) {
+    return p_path(c, slot, nodes, portals, cap, len);
+  }
+  static int32_t agent_avoidance_constraints(Ctx* c, uint32_t i, uint32_t cap, float* lines, uint32_t* no, uint32_t* nf,
+                                             uint32_t* ran) {
+    // bound only by the tests that exercise the debug export; everywhere else nobody asks
+    if (!p_constraints) {
+      *no = *nf = *ran = 0;
+      return LMB_OK;
+    }
+    return p_constraints(c, i, cap, lines, no, nf, ran);
+  }
   static inline int32_t (*p_sample)(void*, uint32_t, const float*, const lmb_options*, float*, uint32_t*) = nullptr;
   static inline int32_t (*p_straight)(void*, uint32_t, const uint32_t*, const float*, const uint32_t*, const float*,
                                       const uint32_t*, const uint32_t*, const float*, uint32_t*, uint32_t*, uint32_t*,
@@ -54,7 +68,13 @@ extern "C" {
 // of pathing results and the sum of their explored nodes, then for each result its agent key idx + version.
 int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_results, const lmb_navdata_desc* desc,
                       uint32_t max_agents, uint32_t frames, float dt, float* trace_f, uint32_t* trace_u,
-                      char* error, uint32_t error_cap) {
+                      char* error, uint32_t error_cap, void* fn_path, void* fn_constraints, uint32_t* extras_u,
+                      float* extras_f) {
+  // optional debug read-backs (fn_path / fn_constraints may be null): agent C keeps its avoidance data from the
+  // start; after the last frame extras_u = [corridor length of B, its first node, C's original / fallback constraint
+  // counts, C fell back] and extras_f = C's constraint lines (4 floats each)
+  FnBackend::p_path = reinterpret_cast<decltype(FnBackend::p_path)>(fn_path);
+  FnBackend::p_constraints = reinterpret_cast<decltype(FnBackend::p_constraints)>(fn_constraints);
   FnBackend::p_upload = reinterpret_cast<decltype(FnBackend::p_upload)>(fn_upload);
   FnBackend::p_step = reinterpret_cast<decltype(FnBackend::p_step)>(fn_step);
   FnBackend::p_results = reinterpret_cast<decltype(FnBackend::p_results)>(fn_results);
@@ -81,6 +101,7 @@ int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_result
       lb::Agent c = make({6.0f, 8.0f, 0.0f}, {6.0f, 2.0f, 0.0f}, 0.5f);
       c.target_reached_condition = lb::TargetReachedCondition::StraightPathDistance(0.25f);
       c.override_type_index_cost(0, 3.0f);
+      c.keep_avoidance_data = fn_constraints != nullptr;
       ids[2] = arch.add_agent(c);
     }
     lb::CharacterId ch = arch.add_character({{6.0f, 4.0f, 0.0f}, {0.2f, 0.0f, 0.0f}, 0.5f});
@@ -120,6 +141,24 @@ int32_t hm_run_script(void* ctx, void* fn_upload, void* fn_step, void* fn_result
       for (int k = 0; k < 4; k++) {
         tu[6 + 2 * k] = k < (int)pr.size() ? pr[(size_t)k].agent.idx : 0u;
         tu[7 + 2 * k] = k < (int)pr.size() ? pr[(size_t)k].agent.version : 0u;
+      }
+    }
+    if (fn_path && extras_u) {
+      const auto path = arch.agent_path(ids[1]);
+      extras_u[0] = (uint32_t)path.first.size();
+      extras_u[1] = path.first.empty() ? LMB_NONE : path.first[0];
+    }
+    if (fn_constraints && extras_u) {
+      const lb::Agent::AvoidanceData* data = arch.get_agent(ids[2])->avoidance_data();
+      extras_u[2] = data ? (uint32_t)data->original.size() : LMB_NONE;
+      extras_u[3] = data ? (uint32_t)data->fallback.size() : LMB_NONE;
+      extras_u[4] = data && data->fell_back ? 1u : 0u;
+      if (data) {
+        size_t w = 0;
+        for (const auto& l : data->original)
+          for (float x : l) extras_f[w++] = x;
+        for (const auto& l : data->fallback)
+          for (float x : l) extras_f[w++] = x;
       }
     }
   } catch (const std::exception& e) {

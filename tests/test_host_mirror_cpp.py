@@ -35,8 +35,9 @@ def harness(tmp_path_factory):
     return lib
 
 
-def python_trace(backend):
-    """The script of host_mirror_harness.cpp on the Python mirror."""
+def python_trace(backend, debug=False):
+    """The script of host_mirror_harness.cpp on the Python mirror.  debug: agent C keeps its avoidance data and the
+    debug read-backs of the last frame are returned as a fourth element."""
     arch = Archipelago(ArchipelagoOptions.from_agent_radius(0.5), backend=backend)
     arch.add_island(Island(Transform((0.0, 0.0, 0.0), 0.0), valid_mesh(dict(
         vertices=[(0.0, 0.0, 0.0), (15.0, 0.0, 0.0), (15.0, 15.0, 0.0), (0.0, 15.0, 0.0)],
@@ -53,6 +54,7 @@ def python_trace(backend):
     c = make((6.0, 8.0, 0.0), (6.0, 2.0, 0.0), 0.5)
     c.target_reached_condition = TargetReachedCondition.StraightPathDistance(0.25)
     assert c.override_type_index_cost(0, 3.0)
+    c.keep_avoidance_data = debug
     ids[2] = arch.add_agent(c)
     alive = [True, True, True, False]
     ch = arch.add_character(Character(np.array((6.0, 4.0, 0.0), dtype=np.float32),
@@ -93,18 +95,31 @@ def python_trace(backend):
             trace_u[f, 6 + 2 * k] = r.agent.idx
             trace_u[f, 7 + 2 * k] = r.agent.version
     arch._sync_navdata()
-    return trace_f, trace_u, arch._flat
+    if not debug:
+        return trace_f, trace_u, arch._flat
+    path = arch.agent_path(ids[1])
+    data = arch.get_agent(ids[2])._avoidance_data
+    extras_u = [0 if path is None else len(path[0]), _abi.NONE if path is None else int(path[0][0]),
+                len(data[1]), len(data[2]) if data[0] == "Fallback" else 0, int(data[0] == "Fallback")]
+    lines = np.concatenate([np.asarray(data[1], dtype=np.float32).reshape(-1, 4)]
+                           + ([np.asarray(data[2], dtype=np.float32).reshape(-1, 4)] if data[0] == "Fallback" else []))
+    return trace_f, trace_u, arch._flat, (extras_u, lines)
 
 
-def cpp_trace(harness, ctx, fns, desc):
+def cpp_trace(harness, ctx, fns, desc, debug_fns=None):
     trace_f = np.zeros((FRAMES, 4, 6), dtype=np.float32)
     trace_u = np.zeros((FRAMES, 14), dtype=np.uint32)
+    extras_u, extras_f = np.zeros(8, dtype=np.uint32), np.zeros(4 * 256, dtype=np.float32)
     err = C.create_string_buffer(512)
     st = harness.hm_run_script(ctx, *[C.cast(f, C.c_void_p) for f in fns],
                                C.byref(desc) if desc is not None else None, C.c_uint32(MAX_AGENTS),
                                C.c_uint32(FRAMES), C.c_float(DT), trace_f.ctypes.data_as(C.c_void_p),
-                               trace_u.ctypes.data_as(C.c_void_p), err, C.c_uint32(512))
+                               trace_u.ctypes.data_as(C.c_void_p), err, C.c_uint32(512),
+                               *([C.cast(f, C.c_void_p) for f in debug_fns] if debug_fns else [None, None]),
+                               extras_u.ctypes.data_as(C.c_void_p), extras_f.ctypes.data_as(C.c_void_p))
     assert st == 0, err.value.decode()
+    if debug_fns:
+        return trace_f, trace_u, None, (extras_u[:5].tolist(), extras_f[:4 * int(extras_u[2] + extras_u[3])].reshape(-1, 4))
     return trace_f, trace_u
 
 
@@ -570,6 +585,25 @@ def test_cpp_queries_match_the_python_mirror_on_cuda(harness):
     assert np.array_equal(got_n, want_n)
     assert np.array_equal(got_steps.view(np.uint32), want_steps.view(np.uint32))
     gpu.close()
+    del keep
+
+
+def test_cpp_debug_read_backs_match_the_python_mirror_on_the_oracle(harness):
+    """`agent_path` (lmb_agent_path) and `Agent::avoidance_data` (feature debug-avoidance: lmb_agent_avoidance_constraints,
+    kept per agent like agent.avoidance_data) of the C++ mirror after the scripted game loop."""
+    from oracle import oracle_py
+    from oracle.oracle_py import OracleBackend
+
+    py = python_trace(OracleBackend(), debug=True)
+    desc, keep = _abi.make_navdata_desc(py[2])
+    lib = oracle_py.load()
+    lib.orc_create.restype = C.c_void_p
+    ctx = C.c_void_p(lib.orc_create(C.byref(desc), C.c_uint32(0)))
+    cpp = cpp_trace(harness, ctx, (lib.orc_navdata_upload, lib.orc_step, lib.orc_pathing_results), desc,
+                    debug_fns=(lib.orc_agent_path, lib.orc_agent_avoidance_constraints))
+    check(py, cpp)
+    assert cpp[3][0] == py[3][0] and py[3][0][0] >= 1 and py[3][0][2] >= 4   # a corridor; >= the room's four walls
+    assert np.array_equal(cpp[3][1].view(np.uint32), py[3][1].view(np.uint32))
     del keep
 
 
