@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "landmass_b200.hpp"
+#include "landmass_b200_anim_links.hpp"
 #include "landmass_b200_linking.hpp"
 
 namespace lb = landmass_b200;
@@ -361,6 +362,54 @@ int32_t hm_run_world_script(void* ctx, void* fn_upload, void* fn_update, void* f
     return -1;
   }
   return 0;
+}
+
+// clip_edge_to_triangle on n (triangle, edge) pairs: tri [n*9], edge [n*6]; out [n*2], ok [n]
+void hm_clip_edges(uint32_t n, const float* tri, const float* edge, float max_vertical_distance, float* out,
+                   uint32_t* ok) {
+  for (uint32_t i = 0; i < n; i++) {
+    const float* t = tri + 9 * (size_t)i;
+    const float* e = edge + 6 * (size_t)i;
+    const lb::Vec3 tv[3] = {{t[0], t[1], t[2]}, {t[3], t[4], t[5]}, {t[6], t[7], t[8]}};
+    const lb::Vec3 ev[2] = {{e[0], e[1], e[2]}, {e[3], e[4], e[5]}};
+    const auto r = lb::clip_edge_to_triangle(tv, ev, max_vertical_distance);
+    ok[i] = r ? 1u : 0u;
+    out[2 * (size_t)i] = r ? r->first : 0.0f;
+    out[2 * (size_t)i + 1] = r ? r->second : 0.0f;
+  }
+}
+
+// validate (optionally with a height mesh) + sample_edge; returns the number of portions (<= cap) or -1
+int32_t hm_sample_edge(uint32_t n_vertices, const float* vertices, uint32_t n_polys, const uint32_t* poly_begin,
+                       const uint32_t* poly_verts, uint32_t n_hpolys, const uint32_t* hpolys, uint32_t n_hverts,
+                       const float* hverts, uint32_t n_htris, const uint32_t* htris, const float* edge,
+                       float max_vertical_distance, uint32_t cap, uint32_t* out_nodes, float* out_t) {
+  try {
+    lb::NavigationMesh mesh;
+    for (uint32_t v = 0; v < n_vertices; v++) mesh.vertices.push_back({vertices[3 * v], vertices[3 * v + 1], vertices[3 * v + 2]});
+    for (uint32_t p = 0; p < n_polys; p++) {
+      mesh.polygons.emplace_back(poly_verts + poly_begin[p], poly_verts + poly_begin[p + 1]);
+      mesh.polygon_type_indices.push_back(0);
+    }
+    if (n_hpolys) {
+      lb::HeightNavigationMesh h;
+      for (uint32_t p = 0; p < n_hpolys; p++) h.polygons.push_back({hpolys[4 * p], hpolys[4 * p + 1], hpolys[4 * p + 2], hpolys[4 * p + 3]});
+      for (uint32_t v = 0; v < n_hverts; v++) h.vertices.push_back({hverts[3 * v], hverts[3 * v + 1], hverts[3 * v + 2]});
+      for (uint32_t t = 0; t < n_htris; t++) h.triangles.push_back({htris[3 * t], htris[3 * t + 1], htris[3 * t + 2]});
+      mesh.height_mesh = h;
+    }
+    const lb::ValidNavigationMesh valid = mesh.validate();
+    const lb::Vec3 ev[2] = {{edge[0], edge[1], edge[2]}, {edge[3], edge[4], edge[5]}};
+    const auto portions = lb::sample_edge(valid, ev, max_vertical_distance);
+    if (portions.size() > cap) return -1;
+    for (size_t k = 0; k < portions.size(); k++) {
+      out_nodes[k] = portions[k].node;
+      out_t[2 * k] = portions[k].t0, out_t[2 * k + 1] = portions[k].t1;
+    }
+    return (int32_t)portions.size();
+  } catch (const std::exception&) {
+    return -1;
+  }
 }
 
 // Several islands -> validate each -> link (boundary links, modified nodes, regions) -> flatten, all in the C++

@@ -32,6 +32,7 @@ def harness(tmp_path_factory):
     lib.hm_validate_flatten_height.restype = C.c_int32
     lib.hm_link_flatten.restype = C.c_int32
     lib.hm_run_world_script.restype = C.c_int32
+    lib.hm_sample_edge.restype = C.c_int32
     return lib
 
 
@@ -497,6 +498,125 @@ def test_cpp_island_archipelago_matches_the_python_mirror_on_the_oracle(harness)
                                          lib.orc_pathing_results))
     _check_world(py, cpp)
     del keep
+
+
+def _cpp_clip(harness, tri, edge, mv):
+    tri = np.ascontiguousarray(tri, dtype=np.float32).reshape(-1, 9)
+    edge = np.ascontiguousarray(edge, dtype=np.float32).reshape(-1, 6)
+    out, ok = np.zeros((len(tri), 2), dtype=np.float32), np.zeros(len(tri), dtype=np.uint32)
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    harness.hm_clip_edges(C.c_uint32(len(tri)), p_(tri), p_(edge), C.c_float(mv), p_(out), p_(ok))
+    return out, ok
+
+
+def test_cpp_clip_edge_to_triangle_matches_goldens_and_python_mirror(harness):
+    """include/landmass_b200_anim_links.hpp `clip_edge_to_triangle` (geometry.rs:63-170): the reference's known
+    answers (geometry_test.rs:79-121, 369-412, 503-526) and 3 000 random cases — degenerate triangles and
+    axis-parallel edges among them — against landmass_b200.anim_links, bit for bit (None included)."""
+    import warnings
+
+    from landmass_b200.anim_links import clip_edge_to_triangle
+
+    flat = lambda z: [(1.0, 1.0, z), (11.0, 1.0, z), (6.0, 11.0, z)]  # noqa: E731
+    out, ok = _cpp_clip(harness, [flat(7.0), flat(5.0), flat(5.0), [(1, 1, 0), (11, 1, 10), (6, 11, 5)]],
+                        [[(0, 6, 7), (12, 6, 7)], [(1, 6, 1), (11, 6, 1)], [(1, 6, 1), (11, 6, 1)], [(1, 6, 5), (11, 6, 5)]], 1.0)
+    assert ok[0] == 1 and tuple(out[0]) == (np.float32(0.29166666), np.float32(0.70833333))
+    assert ok[1] == 0                                       # 4 below the triangle with max distance 1
+    out5, ok5 = _cpp_clip(harness, [flat(5.0)], [[(1, 6, 1), (11, 6, 1)]], 5.0)
+    assert ok5[0] == 1 and tuple(out5[0]) == (0.25, 0.75)
+    out2, ok2 = _cpp_clip(harness, [[(1, 1, 0), (11, 1, 10), (6, 11, 5)]], [[(1, 6, 5), (11, 6, 5)]], 2.0)
+    assert ok2[0] == 1 and tuple(out2[0]) == (np.float32(0.3), np.float32(0.7))
+
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 3000
+    tri = rng.uniform(-3, 12, (n, 3, 3)).astype(np.float32)
+    tri[:, :, 2] = rng.uniform(0, 4, (n, 3))
+    edge = rng.uniform(-3, 12, (n, 2, 3)).astype(np.float32)
+    edge[:, :, 2] = rng.uniform(0, 4, (n, 2))
+    edge[:300, 1, 0] = edge[:300, 0, 0]
+    edge[300:600, 1, 1] = edge[300:600, 0, 1]
+    tri[600:700, 2] = tri[600:700, 1]
+    edge[700:800, 1, 2] = edge[700:800, 0, 2]
+    tri[700:800, :, 2] = 1.0
+    out, ok = _cpp_clip(harness, tri, edge, 1.0)
+    hits = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i in range(n):
+            want = clip_edge_to_triangle([tri[i, 0], tri[i, 1], tri[i, 2]], [edge[i, 0], edge[i, 1]], 1.0)
+            assert (want is not None) == bool(ok[i]), i
+            if want is not None:
+                hits += 1
+                assert np.array_equal(np.array(want, dtype=np.float32).view(np.uint32), out[i].view(np.uint32)), i
+    assert hits > 300
+
+
+def _cpp_sample_edge(harness, vertices, polygons, height, edge, mv):
+    v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    begin = np.zeros(len(polygons) + 1, dtype=np.uint32)
+    begin[1:] = np.cumsum([len(p) for p in polygons])
+    pv = np.array([x for p in polygons for x in p], dtype=np.uint32)
+    if height is not None:
+        hp = np.array([[q.base_vertex_index, q.vertex_count, q.base_triangle_index, q.triangle_count]
+                       for q in height.polygons], dtype=np.uint32).reshape(-1, 4)
+        hv = np.ascontiguousarray(height.vertices, dtype=np.float32).reshape(-1, 3)
+        ht = np.ascontiguousarray(height.triangles, dtype=np.uint32).reshape(-1, 3)
+    else:
+        hp, hv, ht = np.zeros((0, 4), np.uint32), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)
+    e = np.ascontiguousarray(edge, dtype=np.float32).reshape(6)
+    on, ot = np.zeros(4096, dtype=np.uint32), np.zeros((4096, 2), dtype=np.float32)
+    p_ = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    k = harness.hm_sample_edge(C.c_uint32(len(v)), p_(v), C.c_uint32(len(polygons)), p_(begin), p_(pv), C.c_uint32(len(hp)),
+                               p_(hp), C.c_uint32(len(hv)), p_(hv), C.c_uint32(len(ht)), p_(ht), p_(e), C.c_float(mv),
+                               C.c_uint32(4096), p_(on), p_(ot))
+    assert k >= 0
+    return [(int(on[i]), ot[i].copy()) for i in range(k)]
+
+
+def test_cpp_sample_edge_matches_the_python_mirror(harness):
+    """`ValidNavigationMesh::sample_edge` (nav_mesh.rs:819-923) of the C++ mirror: random edges over grid, irregular,
+    maze and heptagon meshes and over a height mesh — the same nodes and merged intervals, bit for bit."""
+    import warnings
+
+    from landmass_b200 import NavigationMesh, synth
+    from landmass_b200.anim_links import sample_edge
+    from tests.helpers import create_height_mesh
+
+    rng = np.random.Generator(np.random.PCG64(11))
+    portions = 0
+
+    def compare(mesh, vertices, polygons, height, e, mv):
+        nonlocal portions
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = sample_edge(mesh, (e[0], e[1]), mv)
+        got = _cpp_sample_edge(harness, vertices, polygons, height, e, mv)
+        assert [w[0] for w in want] == [g[0] for g in got]
+        for w, g in zip(want, got):
+            assert np.array_equal(np.array(w[1], dtype=np.float32).view(np.uint32), g[1].view(np.uint32))
+        portions += len(want)
+
+    for m in (synth.grid_mesh(7, 5), synth.irregular_mesh(9, 7), synth.maze_mesh(5), synth.rosette_mesh(7, 3)):
+        polygons = [m.polygon_vertices(p).tolist() for p in range(m.n_polys)]
+        lo, hi = m.vertices.min(axis=0), m.vertices.max(axis=0)
+        for q in range(40):
+            e = rng.uniform(lo - 1, hi + 1, (2, 3)).astype(np.float32)
+            e[:, 2] = rng.uniform(-0.3, 0.3, 2)
+            if q % 5 == 0:
+                e[1, 0] = e[0, 0]
+            if q % 7 == 0:
+                e[1, 1] = e[0, 1]
+            compare(m, m.vertices, polygons, None, e, 0.25)
+    verts = [(0.0, 0.0, 0.0), (2.0, 0.0, 0.0), (2.0, 2.0, 0.0), (0.0, 2.0, 0.0), (4.0, 0.0, 0.0), (4.0, 2.0, 0.0)]
+    polys = [[0, 1, 2, 3], [1, 4, 5, 2]]
+    hsrc = [(0.0, 0.0, 0.3), (2.0, 0.0, 0.1), (2.0, 2.0, 0.4), (0.0, 2.0, 0.2), (1.0, 1.0, 1.5), (4.0, 0.0, -0.2),
+            (4.0, 2.0, 0.6)]
+    height = create_height_mesh(hsrc, [[[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], [[1, 5, 6, 2]]])
+    hm = NavigationMesh(vertices=verts, polygons=polys, polygon_type_indices=[0, 0], height_mesh=height).validate()
+    for q in range(40):
+        e = np.stack([rng.uniform(-0.5, 4.5, 2), rng.uniform(-0.5, 2.5, 2), rng.uniform(-0.2, 1.6, 2)], axis=1).astype(np.float32)
+        compare(hm, verts, polys, height, e, 0.3)
+    assert portions > 400
 
 
 def _query_case(backend):
