@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LMB_ABI_VERSION 3u
+#define LMB_ABI_VERSION 4u
 #define LMB_NONE 0xFFFFFFFFu
 
 typedef enum lmb_status {
@@ -229,13 +229,23 @@ typedef struct lmb_pathing_result {
 } lmb_pathing_result;
 
 #define LMB_CONFIG_NO_AVOIDANCE 1u /* skip phase D (testing phases A-C in isolation) */
+#define LMB_CONFIG_DEBUG_LOG 2u    /* one stderr line per A* arena (re)allocation: layout, slots, sizes */
+/* Test hooks of the A* kernels' data layouts and launch shapes (tests/test_astar_layouts.py).  None of
+ * them changes a result; production callers leave them clear and the library chooses. */
+#define LMB_CONFIG_ASTAR_COMPACT 4u        /* start with the per-polygon best_estimates layout even off a forest */
+#define LMB_CONFIG_ASTAR_DENSE 8u          /* dense best_estimates whatever the mesh */
+#define LMB_CONFIG_ASTAR_HASHED 16u        /* hashed best_estimates with a 2048-node arena */
+#define LMB_CONFIG_ASTAR_LARGE_SHAPES 32u  /* thread-per-query large-batch launch shapes for every batch */
+#define LMB_CONFIG_ASTAR_THREAD_ONLY 64u   /* never launch the warp-per-query (low latency) search kernel */
+#define LMB_CONFIG_ASTAR_WARP_ONLY 128u    /* launch only the warp-per-query search kernel */
+#define LMB_CONFIG_ASTAR_NO_FOREST 256u    /* do not use the best_estimates-free layout of forest meshes */
 
 typedef struct lmb_config {
   uint32_t struct_size;
   int32_t device;            /* CUDA device ordinal */
   uint32_t max_agents;       /* capacity of slot ids */
   uint32_t astar_slots;      /* A* arena slots = queries in flight; 0 = auto (up to 256 per SM) */
-  uint64_t scratch_bytes;    /* byte budget of the A* arena; 0 = auto (60 % of free HBM, <= 110 GB) */
+  uint64_t scratch_bytes;    /* byte budget of the A* arena; 0 = auto (40 % of free HBM, <= 64 GB) */
   uint32_t flags;            /* LMB_CONFIG_* */
   uint32_t reserved;
 } lmb_config;
@@ -254,6 +264,8 @@ typedef struct lmb_step_timings {
   uint32_t kernel_launches;   /* kernels launched by the step */
   uint64_t explored_nodes;    /* sum over this step's queries */
   uint64_t path_nodes;        /* sum of corridor lengths produced this step */
+  float allgather_ms;         /* lmb_step_sharded: device time of the ncclAllGather (0 otherwise) */
+  uint32_t astar_launch_kind; /* last A* launch: 0 none, 1 thread-per-query, 2 warp-per-query, 3 both */
 } lmb_step_timings;
 
 typedef struct lmb_ctx lmb_ctx;
@@ -301,6 +313,10 @@ int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* agents,
                           const lmb_characters_in* characters);
 int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* options, float delta_time);
 int32_t lmb_agents_download(lmb_ctx* ctx, const lmb_agents_out* out);
+/* For a device-resident loop: what the caller's own movement system does between two updates (README example
+ * README.md:55-131 — velocity = the desired velocity just computed, position += velocity * delta_time) applied
+ * to the resident inputs, and LMB_AGENT_RESET cleared.  Enqueued on the library stream; no synchronisation. */
+int32_t lmb_agents_integrate(lmb_ctx* ctx, float delta_time);
 
 /* Multi-GPU form of the step: agents are sharded over ranks by contiguous
  * ranges of the global agent order, navigation data is replicated, and the only exchange is
@@ -316,6 +332,21 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* options, float delta_tim
                        uint32_t n_total_agents, uint32_t first_agent);
 int32_t lmb_halo_buffer(lmb_ctx* ctx, void** device_ptr, uint64_t* record_bytes, uint64_t* n_records);
 int32_t lmb_step_end(lmb_ctx* ctx, const lmb_options* options, float delta_time);
+
+/* The same exchange done by the library, for callers without a collective of their
+ * own: the library opens libnccl.so.2 at run time and owns one communicator per context.
+ *   lmb_comm_unique_id : rank 0 makes the 128-byte ncclUniqueId; the caller ships it to every rank
+ *                        by whatever channel it has (the bench uses torch.distributed broadcast).
+ *   lmb_comm_init      : ncclCommInitRank on the context's device (collective over all ranks).
+ *   lmb_step_sharded   : phases A-C, ncclAllGather of the records on the library's stream, phase D,
+ *                        outputs — no host synchronisation between the phases.  Every rank passes
+ *                        the same `agents_per_rank` >= its own agent count; rank r's records live at
+ *                        [r * agents_per_rank, +n_r) of the halo buffer and the rest of its share is
+ *                        marked invalid, so ranks need not hold equal numbers of agents.
+ * lmb_get_step_timings().allgather_ms is the device time of the collective. */
+int32_t lmb_comm_unique_id(lmb_ctx* ctx, uint8_t out_id[128]);
+int32_t lmb_comm_init(lmb_ctx* ctx, const uint8_t id[128], uint32_t n_ranks, uint32_t rank);
+int32_t lmb_step_sharded(lmb_ctx* ctx, const lmb_options* options, float delta_time, uint32_t agents_per_rank);
 
 /* `Archipelago::get_pathing_results` (lib.rs:231-233): results of the last step in agent order. */
 int32_t lmb_pathing_results(lmb_ctx* ctx, lmb_pathing_result* out, uint32_t capacity,
@@ -388,6 +419,9 @@ int32_t lmb_agent_avoidance_constraints(lmb_ctx* ctx, uint32_t agent_index, uint
                                         uint32_t* out_n_original, uint32_t* out_n_fallback, uint32_t* out_ran);
 
 int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out);
+/* The same figures for the last lmb_find_paths / lmb_find_straight_paths batch (astar_ms, n_repath = queries,
+ * explored_nodes, path_nodes, kernel_launches); the batched queries leave the step's timings alone. */
+int32_t lmb_get_query_timings(lmb_ctx* ctx, lmb_step_timings* out);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NONE = 0xFFFFFFFF
 PORTAL_LINK = 0x80000000
 
@@ -39,6 +39,14 @@ LINK_BOUNDARY = 0
 LINK_ANIMATION = 1
 
 CONFIG_NO_AVOIDANCE = 1
+CONFIG_DEBUG_LOG = 2
+CONFIG_ASTAR_COMPACT = 4
+CONFIG_ASTAR_DENSE = 8
+CONFIG_ASTAR_HASHED = 16
+CONFIG_ASTAR_LARGE_SHAPES = 32
+CONFIG_ASTAR_THREAD_ONLY = 64
+CONFIG_ASTAR_WARP_ONLY = 128
+CONFIG_ASTAR_NO_FOREST = 256
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -216,6 +224,8 @@ class StepTimings(C.Structure):
         ("kernel_launches", C.c_uint32),
         ("explored_nodes", C.c_uint64),
         ("path_nodes", C.c_uint64),
+        ("allgather_ms", C.c_float),
+        ("astar_launch_kind", C.c_uint32),
     ]
 
 

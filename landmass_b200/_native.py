@@ -21,7 +21,8 @@ EXPORTED_SYMBOLS = [
     "lmb_step", "lmb_agents_upload", "lmb_step_resident", "lmb_agents_download",
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
     "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
-    "lmb_find_straight_paths", "lmb_agent_avoidance_constraints",
+    "lmb_find_straight_paths", "lmb_agent_avoidance_constraints", "lmb_get_query_timings",
+    "lmb_comm_unique_id", "lmb_comm_init", "lmb_step_sharded", "lmb_agents_integrate",
 ]
 
 
@@ -76,6 +77,11 @@ def declare_prototypes(lib, prefix: str):
     fn("step_begin", i32, [vp, C.POINTER(_abi.Options), f32, u32, u32])
     fn("halo_buffer", i32, [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
     fn("step_end", i32, [vp, C.POINTER(_abi.Options), f32])
+    fn("get_query_timings", i32, [vp, C.POINTER(_abi.StepTimings)])
+    fn("comm_unique_id", i32, [vp, C.POINTER(C.c_uint8)])
+    fn("comm_init", i32, [vp, C.POINTER(C.c_uint8), u32, u32])
+    fn("step_sharded", i32, [vp, C.POINTER(_abi.Options), f32, u32])
+    fn("agents_integrate", i32, [vp, f32])
     if prefix == "lmb_":
         lib.lmb_abi_version.restype = u32
         lib.lmb_abi_version.argtypes = []
@@ -344,6 +350,29 @@ class NativeBackend(CBackend):
 
     def step_end(self, options: _abi.Options, dt: float):
         self._check(self.lib.lmb_step_end(self.ctx, C.byref(options), C.c_float(dt)))
+
+    # library-owned halo exchange (lmb_comm.cu): NCCL opened by the library itself
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._check(self.lib.lmb_comm_unique_id(self.ctx, buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.lib.lmb_comm_init(self.ctx, buf, n_ranks, rank))
+
+    def step_sharded(self, options: _abi.Options, dt: float, agents_per_rank: int):
+        self._check(self.lib.lmb_step_sharded(self.ctx, C.byref(options), C.c_float(dt), agents_per_rank))
+
+    def agents_integrate(self, dt: float):
+        """position += desired_velocity * dt, velocity = desired_velocity, RESET cleared — on the device."""
+        self._check(self.lib.lmb_agents_integrate(self.ctx, C.c_float(dt)))
+
+    def query_timings(self) -> _abi.StepTimings:
+        """Timings of the last find_paths / find_straight_paths batch (astar_ms, explored_nodes ...)."""
+        t = _abi.StepTimings()
+        self._check(self.lib.lmb_get_query_timings(self.ctx, C.byref(t)))
+        return t
 
     def agents_download(self) -> dict:
         o, out = _abi.make_agents_out(self._n_agents)

@@ -33,20 +33,12 @@
 //   * the corridor is written into the path pool as raw (state, next state) pairs by the
 //     walk; `k_path_fixup` translates them to (node id, portal code) afterwards, fully
 //     parallel.
-#include <cstdlib>
-
 #include "k_astar_common.cuh"
 
 namespace lmb {
 
 using namespace astar_detail;
 
-__device__ __forceinline__ uint32_t ovf_used(const BestStore<0>&) { return 0u; }
-__device__ __forceinline__ uint32_t ovf_used(const BestStore<1>& b) { return b.ovf_count; }
-__device__ __forceinline__ uint32_t ovf_used(const BestStore<2>&) { return 0u; }
-__device__ __forceinline__ void ovf_clear(BestStore<0>&) {}
-__device__ __forceinline__ void ovf_clear(BestStore<1>& b) { b.ovf_count = 0; }
-__device__ __forceinline__ void ovf_clear(BestStore<2>& b) { b.count = 0; }
 
 // QPW: queries per warp (lanes >= QPW idle: fewer searches in lock-step per warp).
 // KS: compile-time kshift (2 = every polygon has <= 4 edges: one chunk, no chunk loop), or 0 =
@@ -84,9 +76,13 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
   heap.gm = reinterpret_cast<uint4*>(slot_base + arena.heap_offset);
   // the finished search's corridor is staged in the slot's (no longer needed) best_estimates
   // region as raw (state, next state) pairs, goal first, before it is copied to the path pool
+  // (layout 3 has no such region: the pairs are staged in place at the top of the node list, the k-th
+  // at nodes[n_nodes - 1 - k].  The walk visits strictly decreasing node indices i_0 > i_1 > ..., so
+  // i_k <= n_nodes - 1 - k: a staged pair never lands on a node the walk has yet to read.)
   uint2* const stage = reinterpret_cast<uint2*>(slot_base);
   const uint32_t stage_cap =
-      LAYOUT == 1 ? (arena.n_ids >> arena.kshift) : (LAYOUT == 2 ? arena.hash_cap : arena.n_states / 2);
+      LAYOUT == 3 ? 0xffffffffu
+                  : (LAYOUT == 1 ? (arena.n_ids >> arena.kshift) : (LAYOUT == 2 ? arena.hash_cap : arena.n_states / 2));
   heap.len = 0;
 
   const EdgeRec* __restrict__ recs = nav.edges;
@@ -446,6 +442,7 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           }
           // The lanes of the warp step through their k-th accepted successor together
           // (ascending j = ascending edge index).
+          bool pushed = false;
           while (acc) {
             const uint32_t j = __ffs(acc) - 1;
             acc &= acc - 1;
@@ -457,7 +454,13 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
             const uint32_t s2 = sel4(j, r[0].twin, r[1].twin, r[2].twin, r[3].twin);
             const float est = sel4(j, es[0], es[1], es[2], es[3]);
             const float ncost = sel4(j, nc[0], nc[1], nc[2], nc[3]);
-            if (!bs.store(s2, sel4(j, praw[0], praw[1], praw[2], praw[3]), est)) {
+            // The probes were issued together, before this expansion's inserts.  In the compact and hashed
+            // layouts two states can share a physical entry (the same polygon; the same home slot or probe
+            // chain), so after the first insert a later successor's probe may be out of date: take a fresh one.
+            BestRaw raw2 = sel4(j, praw[0], praw[1], praw[2], praw[3]);
+            if ((LAYOUT == 1 || LAYOUT == 2) && pushed) raw2 = bs.probe_edge(s2);
+            pushed = true;
+            if (!bs.store(s2, raw2, est)) {
               go_dense = true;
               break;
             }
@@ -529,7 +532,10 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
                                     : (wi == 1 ? make_uint2(w_lo.z, w_lo.w)
                                                : (wi == 2 ? make_uint2(w_hi.x, w_hi.y) : make_uint2(w_hi.z, w_hi.w)));
         if (w_rec.x != ST_END) {
-          if (w_pos < stage_cap) stage[w_pos] = make_uint2(w_rec.x, w_next);
+          if (LAYOUT == 3)
+            nodes[n_nodes - 1 - w_pos] = make_uint2(w_rec.x, w_next);
+          else if (w_pos < stage_cap)
+            stage[w_pos] = make_uint2(w_rec.x, w_next);
           w_pos++;
         }
         w_next = w_rec.x;
@@ -572,13 +578,19 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
       if (cL) {
         const uint32_t cOff = __shfl_sync(FULL, path_off, src);
         const uint2* st = reinterpret_cast<const uint2*>(base);
-        for (uint32_t k = lane; k < cL; k += 32) pool.entries[(size_t)cOff + (cL - 1 - k)] = st[k];
+        if (LAYOUT == 3) {
+          for (uint32_t k = lane; k < cL; k += 32) pool.entries[(size_t)cOff + k] = nd[nn - cL + k];
+        } else {
+          for (uint32_t k = lane; k < cL; k += 32) pool.entries[(size_t)cOff + (cL - 1 - k)] = st[k];
+        }
       } else {
         (void)__shfl_sync(FULL, path_off, src);
       }
       __syncwarp();
       const uint32_t n_staged = staged < stage_cap ? staged : stage_cap;
-      if (LAYOUT == 2) {
+      if (LAYOUT == 3) {
+        // nothing to restore
+      } else if (LAYOUT == 2) {
         // hashed: entries cannot be removed one by one (probe chains): clear the whole table
         uint4* t4 = reinterpret_cast<uint4*>(base);
         const uint4 e4 = make_uint4(BP_EMPTY, 0u, BP_EMPTY, 0u);
@@ -792,6 +804,7 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
     launch_astar_t<QPW, 48, 4, KS, LAYOUT, SIMPLE>(nav, arena, q, pool, counters, type_raw, stream);
     return;
   } else {
+  static_assert(HS >= AT_HEAP_SM_MIN, "a slot's open-list spill is sized for HS >= AT_HEAP_SM_MIN (arena_layout)");
   constexpr uint32_t QPB = QPW * (AT_THREADS / 32);
   const size_t smem = (size_t)HS * QPB * sizeof(uint4);
   static bool configured = false;
@@ -844,9 +857,14 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 // latency per query but issue-bound, no faster when loaded.)
 uint32_t astar_resident_queries_per_sm(bool big_heap) { return (big_heap ? 2 : 5) * 16 * (AT_THREADS / 32); }
 
-void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream) {
-  if (q.n == 0) return;
+void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                       AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
+                       cudaStream_t stream);  // k_astar_warp.cu
+
+uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                      AStarCounters* counters, const uint32_t* type_raw, bool big_heap, uint32_t flags,
+                      cudaStream_t stream) {
+  if (q.n == 0) return 0;
   const bool k4 = arena.kshift == 2;
   const bool simple = nav.n_types == 1 && !q.override_begin;  // the kernel's SIMPLE flag
 #define LMB_ASTAR_LAUNCH_S(QPW, HS, BPS, K, L)                                                             \
@@ -863,15 +881,23 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   do {                                                                  \
     if (arena.layout == 1) LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 1);         \
     else if (arena.layout == 2) LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 2);    \
+    else if (arena.layout == 3) LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 3);    \
     else LMB_ASTAR_LAUNCH_L(QPW, HS, BPS, 0);                           \
   } while (0)
   int dev = 0, sm_count = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  // LMB_ASTAR_SHAPE=large: tests run the large-batch shapes (the benchmarked ones) at sizes the oracle can check
-  const char* shape_env = getenv("LMB_ASTAR_SHAPE");  // (read per launch: a test sets it for its own launches only)
-  const bool force_large = shape_env && shape_env[0] == 'l';
-  if (force_large) {
+  uint32_t kind = 1;
+  // LMB_CONFIG_ASTAR_LARGE_SHAPES: tests run the large-batch shapes (the benchmarked ones) at sizes the oracle can check
+  const bool force_large = flags & LMB_CONFIG_ASTAR_LARGE_SHAPES;
+  // Small batches finish with their longest search: up to 16 queries per SM go to the warp-per-query kernel
+  // (k_astar_warp.cu), whose single-search latency is several times lower.
+  const bool warp = (flags & LMB_CONFIG_ASTAR_WARP_ONLY) ||
+                    (!force_large && !(flags & LMB_CONFIG_ASTAR_THREAD_ONLY) && q.n <= 16u * (uint32_t)sm_count);
+  if (warp) {
+    kind = 2;
+    launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, (uint32_t)sm_count, stream);
+  } else if (force_large) {
     if (big_heap) LMB_ASTAR_LAUNCH(8, 96, 4);
     else LMB_ASTAR_LAUNCH(16, 40, 5);
   } else if (q.n <= 8u * (uint32_t)sm_count)
@@ -892,6 +918,7 @@ void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries
   uint32_t fix_blocks = (q.n + 7) / 8;
   if (fix_blocks > 148 * 16) fix_blocks = 148 * 16;
   k_path_fixup<<<fix_blocks, 256, 0, stream>>>(nav, a, q, pool);
+  return kind;
 }
 
 }  // namespace lmb

@@ -140,7 +140,7 @@ __device__ __forceinline__ EdgeRec ld_rec(const EdgeRec* p) {
 constexpr uint32_t BP_EMPTY = 0xFFFFFFFFu;
 constexpr uint32_t BP_SPECIAL = 0xFFFFFFFEu;
 
-template <int LAYOUT>  // 0 dense, 1 compact, 2 hashed
+template <int LAYOUT>  // 0 dense, 1 compact, 2 hashed, 3 none (forest meshes)
 struct BestStore;
 
 template <>
@@ -304,6 +304,93 @@ struct BestStore<2> {
     return true;
   }
 };
+
+// * none (layout 3) — forest meshes (the polygon graph incl. off-mesh links has no cycle; exact
+//   union-find test at upload).  A state's successors exclude the edge it was entered through
+//   (pathfinding.rs:165-166), so on a forest a search enters every polygon once and generates every
+//   state once: `try_add_node` (astar.rs:139-160) always finds the entry absent (+inf) and the stale
+//   test (astar.rs:172-176) never fires.  Nothing is stored, probed or restored; the finished
+//   corridor is staged in place at the top of the node list (see stage_index()).
+template <>
+struct BestStore<3> {
+  typedef uint32_t Raw;
+  typedef uint32_t RootRaw;
+  __device__ __forceinline__ void init(uint8_t*, const AStarArena&) {}
+  __device__ __forceinline__ Raw probe(uint32_t) const { return 0u; }
+  __device__ __forceinline__ Raw probe_edge(uint32_t) const { return 0u; }
+  __device__ __forceinline__ RootRaw probe_root(uint32_t) const { return 0u; }
+  __device__ __forceinline__ float root_value(uint32_t, RootRaw) const { return __builtin_huge_valf(); }
+  __device__ __forceinline__ float value(uint32_t, Raw) const { return __builtin_huge_valf(); }
+  __device__ __forceinline__ float value_edge(uint32_t, Raw) const { return __builtin_huge_valf(); }
+  __device__ __forceinline__ float value_fast(uint32_t, Raw, bool& need_table) const {
+    need_table = false;
+    return __builtin_huge_valf();
+  }
+  __device__ __forceinline__ bool store(uint32_t, Raw, float) { return true; }
+};
+
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<0>&) { return 0u; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<1>& b) { return b.ovf_count; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<2>&) { return 0u; }
+__device__ __forceinline__ uint32_t ovf_used(const BestStore<3>&) { return 0u; }
+__device__ __forceinline__ void ovf_clear(BestStore<0>&) {}
+__device__ __forceinline__ void ovf_clear(BestStore<1>& b) { b.ovf_count = 0; }
+__device__ __forceinline__ void ovf_clear(BestStore<2>& b) { b.count = 0; }
+__device__ __forceinline__ void ovf_clear(BestStore<3>&) {}
+
+// Restores a finished query's best_estimates region to "absent" (all 32 lanes of a warp cooperate).
+// nn nodes were created (nd = the slot's node list); n_staged entries at the start of the region
+// were overwritten by the staged corridor.
+template <int LAYOUT>
+__device__ __forceinline__ void restore_best(const AStarArena& arena, uint8_t* base, const uint2* nd, uint32_t nn,
+                                             uint32_t n_staged, bool ovf_used, uint32_t lane) {
+  if (LAYOUT == 3) return;
+  if (LAYOUT == 2) {
+    // hashed: entries cannot be removed one by one (probe chains): clear the whole table
+    uint4* t4 = reinterpret_cast<uint4*>(base);
+    const uint4 e4 = make_uint4(BP_EMPTY, 0u, BP_EMPTY, 0u);
+    for (uint32_t k = lane; k < arena.hash_cap / 2; k += 32) t4[k] = e4;
+  } else if (LAYOUT == 0) {
+    float* b = reinterpret_cast<float*>(base);
+    if ((size_t)nn * 16 >= arena.n_states) {
+      float4* b4 = reinterpret_cast<float4*>(b);
+      const uint32_t n4 = (arena.n_states + 3) >> 2;
+      const float4 inf4 = make_float4(F_INF, F_INF, F_INF, F_INF);
+      for (uint32_t k = lane; k < n4; k += 32) b4[k] = inf4;
+    } else {
+      for (uint32_t k = lane; k < nn; k += 32) b[__ldcg(nd + k).x] = F_INF;
+      uint2* st = reinterpret_cast<uint2*>(base);
+      const uint2 e2 = make_uint2(__float_as_uint(F_INF), __float_as_uint(F_INF));
+      for (uint32_t k = lane; k < n_staged; k += 32) st[k] = e2;
+    }
+  } else {
+    uint2* bp = reinterpret_cast<uint2*>(base);
+    float* sp = reinterpret_cast<float*>(base + arena.special_offset);
+    const uint32_t n_polys = arena.n_ids >> arena.kshift;
+    if ((size_t)nn * 8 >= n_polys) {
+      uint4* b4 = reinterpret_cast<uint4*>(base);
+      const uint32_t n4 = (n_polys + 1) >> 1;
+      const uint4 e4 = make_uint4(__float_as_uint(F_INF), BP_EMPTY, __float_as_uint(F_INF), BP_EMPTY);
+      for (uint32_t k = lane; k < n4; k += 32) b4[k] = e4;
+      for (uint32_t k = lane; k < arena.n_states - arena.n_ids; k += 32) sp[k] = F_INF;
+    } else {
+      for (uint32_t k = lane; k < nn; k += 32) {
+        const uint32_t st = __ldcg(nd + k).x;
+        if (st < arena.n_ids)
+          bp[st >> arena.kshift] = make_uint2(__float_as_uint(F_INF), BP_EMPTY);
+        else
+          sp[st - arena.n_ids] = F_INF;
+      }
+      const uint2 e2 = make_uint2(__float_as_uint(F_INF), BP_EMPTY);
+      for (uint32_t k = lane; k < n_staged; k += 32) bp[k] = e2;
+    }
+    if (ovf_used) {
+      uint4* o4 = reinterpret_cast<uint4*>(base + arena.ovf_offset);
+      const uint4 e4 = make_uint4(BP_EMPTY, 0u, BP_EMPTY, 0u);
+      for (uint32_t k = lane; k < arena.ovf_cap / 2; k += 32) o4[k] = e4;
+    }
+  }
+}
 
 enum : uint32_t { PH_IDLE = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINISH = 3, PH_EXIT = 4 };
 

@@ -1,0 +1,662 @@
+// Kernel 2, low-latency form — batched A*, one query per WARP.
+//
+// Same search, same results as k_astar.cu (pathfinding.rs:19-382, astar.rs:126-206; corridors, portal
+// codes and `explored_nodes` bit-exact), same arena slots, same outputs; what differs is who does the
+// work.  k_astar.cu gives a query to one thread and hides latency with thousands of queries in flight:
+// the best shape when a batch is large, but a single search then runs ~700 dependent warp instructions
+// per expansion (2-2.5 us per explored node) and a small batch — the few hundred re-plans of a steady
+// frame — takes as long as its longest search.  Here the 32 lanes of a warp share ONE search, and the
+// serial chain of an expansion is cut to what really is serial:
+//
+//   * expansion: lane j owns edge j of the popped polygon — its record (32 B), its row of the distance
+//     table, its `best_estimates` probe, its cost / heuristic (two square roots) and its accept test
+//     all run side by side; a ballot gives the accepted set in ascending edge order (the reference's
+//     successor order), node-list appends and `best` stores are one parallel step;
+//   * open list: the exact `BinaryHeap<Reverse<NodeRef>>` emulation of k_astar_common.cuh, but
+//       - `sift_down_to_bottom` picks the greater child independently of the hole, so its path is a
+//         function of the heap alone: 31 lanes evaluate the winner bits of a five-level subtree at
+//         once (two 16-byte shared-memory reads each), a ballot publishes them, and the path is
+//         walked five levels per round with ALU operations only;
+//       - the moves along the path are one parallel step (lane k moves the entry of level k), and the
+//         `sift_up` that follows is ONE ballot over the path entries (stop at the first ancestor the
+//         hole element is <= to, scanning upward: the highest set bit);
+//       - `push` = one parallel read of the ancestors, one ballot (lowest set bit), one parallel write;
+//     all with the reference comparator (`rev_le`, including the cost-vs-estimate quirk of astar.rs:71);
+//   * the loads of an expansion (records, distance row, best[root]) are issued before the pop and
+//     consumed after it, like in k_astar.cu;
+//   * walk: the back-pointer chain is followed through a 128-node window held in registers (four
+//     nodes per lane, moved by shuffles); a dependent memory round trip is paid only when the chain
+//     leaves the window.
+//
+// One warp runs one query at a time and pulls the next from the batch's queue; 8 or 16 warps per SM
+// (1536 / 768 open-list entries per query in shared memory, in-place spill beyond that).
+#include "k_astar_common.cuh"
+
+namespace lmb {
+
+using namespace astar_detail;
+
+namespace {
+
+// rev_le on packed entries {cost, estimate, index, state}
+__device__ __forceinline__ bool rev_le4(const uint4& x, const uint4& y) {
+  const float xc = __uint_as_float(x.x), xe = __uint_as_float(x.y), ye = __uint_as_float(y.y),
+              yc = __uint_as_float(y.x);
+  (void)xc;
+  // Reverse::le(x, y) = NodeRef::le(y, x): y.estimate < x.estimate, or equal estimates and x.estimate <= y.cost
+  return (ye < xe) | ((ye == xe) & (xe <= yc));
+}
+
+template <uint32_t HS>
+struct WarpHeap {
+  uint4* sm;      // this warp's entries [0, HS)
+  uint4* gm;      // spill: entry i (>= HS) at gm[i - HS + 1]
+  uint32_t len;
+  uint32_t lane;
+  uint32_t lv_m, lv_o;  // level / offset of this lane's node inside a 31-node (five-level) subtree
+
+  __device__ __forceinline__ void init(uint4* sm_, uint4* gm_, uint32_t lane_) {
+    sm = sm_;
+    gm = gm_;
+    len = 0;
+    lane = lane_;
+    lv_m = 31u - __clz(lane_ + 1u);
+    lv_o = lane_ + 1u - (1u << lv_m);
+  }
+  __device__ __forceinline__ uint4 ld(uint32_t i) const {
+    if (i < HS) return sm[i];
+    return __ldcg(gm + (i - HS + 1));
+  }
+  __device__ __forceinline__ void st(uint32_t i, const uint4& v) const {
+    if (i < HS)
+      sm[i] = v;
+    else
+      __stcg(gm + (i - HS + 1), v);
+  }
+
+  // BinaryHeap::push = sift_up(0, old_len)
+  __device__ __forceinline__ void push(const uint4& e) {
+    const uint32_t p1 = len + 1u;  // 1-based index of the new position; its k-th ancestor is p1 >> k
+    len = p1;
+    const uint32_t depth = 31u - __clz(p1);
+    uint4 anc = make_uint4(0u, 0u, 0u, 0u);
+    bool stop = false;
+    if (lane < depth) {
+      anc = ld((p1 >> (lane + 1u)) - 1u);
+      stop = rev_le4(e, anc);
+    }
+    const uint32_t mask = __ballot_sync(FULL, stop);
+    const uint32_t rise = mask ? (uint32_t)__ffs(mask) - 1u : depth;  // levels the new entry moves up
+    if (lane < rise) st((p1 >> lane) - 1u, anc);
+    if (lane == 0) st((p1 >> rise) - 1u, e);
+    __syncwarp();
+  }
+
+  // BinaryHeap::pop = swap_remove(0) + sift_down_to_bottom(0) + sift_up
+  __device__ __forceinline__ uint4 pop() {
+    len--;
+    const uint4 last = ld(len);
+    if (len == 0) return last;
+    const uint4 top = sm[0];
+    const uint32_t end = len;
+    uint32_t pos = 0, d = 0, my_pos = 0;
+    while (2u * pos + 2u < end) {  // `pos` has two children
+      // winner bits of the five levels below `pos`: lane l < 31 owns the node with local heap index l
+      const uint32_t g = ((pos + 1u) << lv_m) + lv_o - 1u;
+      bool bit = false;
+      if (lane < 31u && 2u * g + 2u < end) {
+        const uint4 a = ld(2u * g + 1u), b = ld(2u * g + 2u);
+        bit = rev_le4(a, b);  // child += (a <= b): the right child wins
+      }
+      const uint32_t bits = __ballot_sync(FULL, bit);
+      uint32_t t = 0;
+#pragma unroll
+      for (int lv = 0; lv < 5; lv++) {
+        if (2u * pos + 2u < end) {
+          const uint32_t r = (bits >> t) & 1u;
+          t = 2u * t + 1u + r;
+          pos = 2u * pos + 1u + r;
+          d++;
+          if (lane == d) my_pos = pos;
+        }
+      }
+    }
+    if (2u * pos + 2u == end) {  // a single child at the bottom
+      pos = 2u * pos + 1u;
+      d++;
+      if (lane == d) my_pos = pos;
+    }
+    // Entry of level k moves to level k-1 (lane k); the hole element (the old last entry) goes to the
+    // bottom and sifts up: it stops below the first entry, scanning upward, that it is <= to.
+    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
+    bool stop = false;
+    if (lane >= 1u && lane <= d) {
+      mine = ld(my_pos);
+      stop = rev_le4(last, mine);
+    }
+    const uint32_t mask = __ballot_sync(FULL, stop);
+    const uint32_t j = mask ? 31u - __clz(mask) : 0u;
+    const uint32_t pos_j = __shfl_sync(FULL, my_pos, j);
+    if (lane >= 1u && lane <= j) st((my_pos - 1u) >> 1, mine);
+    if (lane == 0) st(pos_j, last);
+    __syncwarp();
+    return top;
+  }
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// key under which two states collide physically in a layout's table (never for the dense array)
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t collision_key(const BestStore<LAYOUT>&, uint32_t st, uint32_t lane) {
+  return 0x80000000u | lane;
+}
+template <>
+__device__ __forceinline__ uint32_t collision_key<1>(const BestStore<1>& bs, uint32_t st, uint32_t) {
+  return st >> bs.kshift;  // one entry per polygon
+}
+template <>
+__device__ __forceinline__ uint32_t collision_key<2>(const BestStore<2>& bs, uint32_t st, uint32_t) {
+  return bs.home(st) & bs.mask;  // a stale probe of the home slot would overwrite a neighbour's insert
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ bool needs_chain(const BestStore<LAYOUT>&, uint32_t, const typename BestStore<LAYOUT>::Raw&) {
+  return false;
+}
+template <>
+__device__ __forceinline__ bool needs_chain<1>(const BestStore<1>& bs, uint32_t st, const uint2& raw) {
+  return raw.y != BP_EMPTY && raw.y != (st & bs.kmask);
+}
+template <>
+__device__ __forceinline__ bool needs_chain<2>(const BestStore<2>&, uint32_t st, const uint2& raw) {
+  return raw.x != BP_EMPTY && raw.x != st;
+}
+
+}  // namespace
+
+template <uint32_t HS, uint32_t BPS, int LAYOUT>
+__global__ void __launch_bounds__(AT_THREADS, BPS)
+k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
+             const uint32_t* __restrict__ type_raw, uint32_t simple_u) {
+  constexpr uint32_t WPB = AT_THREADS / 32;
+  extern __shared__ uint4 s_heap[];  // [WPB][HS]
+  __shared__ float s_cost[LMB_MAX_TYPES];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  for (uint32_t t = threadIdx.x; t < nav.n_types; t += AT_THREADS) s_cost[t] = nav.type_cost[t];
+  __syncthreads();
+  const uint32_t slot = blockIdx.x * WPB + warp;
+  if (slot >= arena.n_slots) return;
+
+  typedef typename BestStore<LAYOUT>::Raw BestRaw;
+  typedef typename BestStore<LAYOUT>::RootRaw BestRootRaw;
+  uint8_t* const slot_base = arena.base + (size_t)slot * arena.slot_stride;
+  BestStore<LAYOUT> bs;
+  bs.init(slot_base, arena);
+  uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
+  uint2* const stage = reinterpret_cast<uint2*>(slot_base);
+  const uint32_t stage_cap =
+      LAYOUT == 3 ? 0xffffffffu
+                  : (LAYOUT == 1 ? (arena.n_ids >> arena.kshift) : (LAYOUT == 2 ? arena.hash_cap : arena.n_states / 2));
+  WarpHeap<HS> heap;
+  heap.init(s_heap + (size_t)warp * HS, reinterpret_cast<uint4*>(slot_base + arena.heap_offset), lane);
+
+  const EdgeRec* __restrict__ recs = nav.edges;
+  const uint32_t heap_cap = arena.heap_cap, node_cap = arena.node_cap;
+  const uint32_t node_cap_window = (node_cap + 31u) & ~31u;  // the node list is allocated in 256-byte units
+  const uint32_t kshift = arena.kshift, kmask = (1u << kshift) - 1u;
+  const bool simple = simple_u != 0;
+  const float cost0 = s_cost[0];
+  const uint32_t ST_LINK0 = arena.n_ids;
+  const uint32_t ST_START = arena.n_ids + nav.n_links;
+  const uint32_t ST_END = ST_START + 1;
+  const uint32_t lt = lanemask_lt();
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(&counters->queue_head, 1u);
+    qi = __shfl_sync(FULL, qi, 0);
+    if (qi >= q.n) break;
+    const uint32_t qid = q.list ? q.list[qi] : qi;
+    const uint32_t start_node = q.start_node[qid], end_node = q.end_node[qid];
+    const V3 start_point{q.start_point[3 * (size_t)qid], q.start_point[3 * (size_t)qid + 1],
+                         q.start_point[3 * (size_t)qid + 2]};
+    const V3 end_point{q.end_point[3 * (size_t)qid], q.end_point[3 * (size_t)qid + 1], q.end_point[3 * (size_t)qid + 2]};
+    const uint32_t owner = q.owner ? q.owner[qid] : qid;
+    uint32_t ov_begin = 0, ov_end = 0;
+    if (!simple && q.override_begin) {
+      ov_begin = q.override_begin[owner];
+      ov_end = q.override_begin[owner + 1];
+    }
+    // type cost: override -> archipelago -> 1.0 (pathfinding.rs:73-77)
+    auto cost_of = [&](uint32_t t) -> float {
+      if (simple) return cost0;
+      float c = s_cost[t];
+      if (ov_begin != ov_end) {
+        const uint32_t raw = type_raw[t];
+        for (uint32_t k = ov_begin; k < ov_end; k++)
+          if (q.override_type[k] == raw) c = q.override_cost[k];
+      }
+      return c;
+    };
+    // PermittedAnimationLinks::is_permitted (agent.rs:178-186)
+    auto is_kind_permitted = [&](uint32_t kind) -> bool {
+      if (!q.owner_flags || (q.owner_flags[owner] & LMB_AGENT_PERMIT_ALL_LINKS)) return true;
+      if (q.permitted_begin)
+        for (uint32_t m = q.permitted_begin[owner]; m < q.permitted_begin[owner + 1]; m++)
+          if (q.permitted_kind[m] == kind) return true;
+      return false;
+    };
+    // cheapest_type_index_cost (pathfinding.rs:300-314)
+    float cheapest = 1.0f;
+    for (uint32_t t = 0; t < nav.n_types; t++) {
+      const float c = cost_of(t);
+      if (nav.type_registered[t] && is_finite(c) && c < cheapest) cheapest = c;
+    }
+    // are_nodes_connected (nav_data.rs:1022-1087); every lane runs the same (rare) BFS on the same data
+    bool connected;
+    {
+      const uint32_t i1 = nav.poly_island[start_node], i2 = nav.poly_island[end_node];
+      if (i1 == i2 && nav.poly_region[start_node] == nav.poly_region[end_node]) {
+        connected = true;
+      } else {
+        const uint32_t r1 = nav.node_region_number[start_node], r2 = nav.node_region_number[end_node];
+        connected = r1 != LMB_NONE && r2 != LMB_NONE && nav.region_root[r1] == nav.region_root[r2];
+        if (!connected && r1 != LMB_NONE && r2 != LMB_NONE && nav.n_possible_links) {
+          uint32_t found = 0;
+          if (lane == 0) {
+            uint32_t* seen = reinterpret_cast<uint32_t*>(nodes);
+            uint32_t* queue = seen + nav.n_region_numbers;
+            for (uint32_t r = 0; r < nav.n_region_numbers; r++) seen[r] = 0u;
+            uint32_t head = 0, tail = 0;
+            seen[r1] = 1u;
+            queue[tail++] = r1;
+            while (head < tail) {
+              const uint32_t r = queue[head++];
+              if (r == r2) {
+                found = 1;
+                break;
+              }
+              for (uint32_t k = 0; k < nav.n_possible_links; k++) {
+                if (nav.possible_link_src[k] != r) continue;
+                if (!is_kind_permitted(nav.possible_link_kind[k])) continue;
+                const uint32_t dst = nav.possible_link_dst[k];
+                if (seen[dst]) continue;
+                seen[dst] = 1u;
+                queue[tail++] = dst;
+              }
+            }
+          }
+          connected = __shfl_sync(FULL, found, 0) != 0;
+        }
+      }
+    }
+
+    uint32_t n_nodes = 0, explored = 0, hmax = 0, ovf_total = 0;
+    uint32_t status = 1, success = 0, path_off = 0, path_len = 0;
+    uint32_t goal_index = LMB_NONE;
+    heap.len = 0;
+    ovf_clear(bs);
+
+    // try_add_node of a special state (Start, End, off-mesh link): the same work on every lane
+    auto push_special = [&](uint32_t s2, float ncost, float est, uint32_t prev) {
+      const BestRaw raw = bs.probe(s2);
+      if (bs.value(s2, raw) <= est) return;
+      if (n_nodes >= node_cap || heap.len >= heap_cap) {
+        status = heap.len >= heap_cap ? 7u : 2u;
+        return;
+      }
+      uint32_t ok = 1;
+      if (lane == 0) {
+        ok = bs.store(s2, raw, est) ? 1u : 0u;
+        nodes[n_nodes] = make_uint2(s2, prev);
+      }
+      __syncwarp();
+      if (LAYOUT == 1 || LAYOUT == 2) {
+        ok = __shfl_sync(FULL, ok, 0);
+        if (!ok) {
+          status = LAYOUT == 1 ? 5u : 2u;
+          return;
+        }
+      }
+      heap.push(make_uint4(__float_as_uint(ncost), __float_as_uint(est), n_nodes, s2));
+      n_nodes++;
+      hmax = max(hmax, heap.len);
+    };
+
+    if (connected) {
+      const float est = fadd(0.0f, fmul(distance(start_point, end_point), cheapest));
+      if (!(F_INF <= est)) push_special(ST_START, 0.0f, est, LMB_NONE);
+    }
+
+    // =========================================== search ===========================================
+    while (status == 1 && heap.len != 0) {
+      // ---- peek the root, issue this expansion's loads, then pop ----
+      const uint32_t s = heap.sm[0].w;
+      const BestRootRaw raw_s = bs.probe_root(s);
+      const bool is_edge = s < ST_LINK0;
+      const bool preloaded = is_edge && kshift != 0;
+      EdgeRec r;
+      r.twin = LMB_NONE, r.info = 0, r.poly = 0, r.first_edge = 0, r.aux = 0;
+      r.mx = r.my = r.mz = 0.0f;
+      EdgeRec self = r;
+      float dtab = 0.0f;
+      uint32_t first = 0, cnt = 0;
+      if (is_edge) {
+        if (kshift) {
+          first = s & ~kmask;
+          cnt = kmask + 1u;
+          if (lane < cnt) {
+            r = ld_rec(recs + first + lane);
+            dtab = __ldg(nav.edge_dist + ((size_t)s << kshift) + lane);
+          }
+        } else {
+          self = ld_rec(recs + s);
+        }
+      }
+      const uint4 cur = heap.pop();
+      const float cur_cost = __uint_as_float(cur.x), cur_est = __uint_as_float(cur.y);
+
+      // ---- resolve (node, point, ignored step) — pathfinding.rs:93-143 ----
+      uint32_t poly = 0, cur_type = 0, has_links = 0;
+      uint32_t ignore_edge = LMB_NONE, ignore_link = LMB_NONE;
+      V3 point{0.0f, 0.0f, 0.0f};
+      if (is_edge) {
+        if (kshift) {
+          const uint32_t own = s & kmask;
+          poly = s >> kshift;
+          const uint32_t info0 = __shfl_sync(FULL, r.info, 0);
+          cur_type = (info0 >> 8) & 0xffu;
+          has_links = (info0 >> 24) & 1u;
+          point = {__shfl_sync(FULL, r.mx, own), __shfl_sync(FULL, r.my, own), __shfl_sync(FULL, r.mz, own)};
+        } else {
+          first = self.first_edge;
+          cnt = self.info & 0xffu;
+          poly = self.poly;
+          cur_type = (self.info >> 8) & 0xffu;
+          has_links = (self.info >> 24) & 1u;
+          point = {self.mx, self.my, self.mz};
+        }
+        ignore_edge = s;
+      } else if (s != ST_END) {
+        if (s == ST_START) {
+          poly = start_node;
+          point = start_point;
+        } else {
+          const uint32_t l = s - ST_LINK0;
+          poly = nav.link_dst_node[l];
+          const float* pp;
+          if (nav.link_kind[l] == LMB_LINK_BOUNDARY) {
+            pp = nav.link_portal + 6 * (size_t)l;
+            ignore_link = nav.link_reverse[l];
+          } else {
+            pp = nav.link_dst_portal + 6 * (size_t)l;
+          }
+          point = midpoint(V3{pp[0], pp[1], pp[2]}, V3{pp[3], pp[4], pp[5]});
+        }
+        if (kshift) {
+          first = poly << kshift;
+          cnt = kmask + 1u;
+        } else {
+          first = nav.poly_edge_begin[poly];
+          cnt = nav.poly_edge_begin[poly + 1] - first;
+        }
+        cur_type = nav.poly_type_dense[poly];
+        has_links = nav.node_link_begin[poly + 1] > nav.node_link_begin[poly];
+      }
+      // stale (astar.rs:172-176)
+      if (bs.root_value(s, raw_s) < cur_est) continue;
+      explored++;
+      if (s == ST_END) {  // goal (astar.rs:179-184)
+        goal_index = cur.z;
+        break;
+      }
+      const float cur_type_cost = cost_of(cur_type);
+      if (poly == end_node) {
+        // the single successor GoToEnd (pathfinding.rs:152-155); h(End) = 0
+        const float c = fmul(distance(point, end_point), cur_type_cost);
+        const float ncost = fadd(cur_cost, c);
+        push_special(ST_END, ncost, fadd(ncost, 0.0f), cur.z);
+        continue;
+      }
+
+      // ---- node connections in ascending edge index, 32 at a time: lane j takes edge e0 + j ----
+      for (uint32_t e0 = 0; e0 < cnt && status == 1; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        if (e0 > 0 || !preloaded) {
+          if (e < cnt)
+            r = ld_rec(recs + first + e);
+          else
+            r.twin = LMB_NONE, r.info = 0;
+        }
+        const bool ok = e < cnt && r.twin != LMB_NONE && first + e != ignore_edge &&
+                        is_finite(cost_of((r.info >> 16) & 0xffu));
+        BestRaw praw{};
+        if (ok) praw = bs.probe_edge(r.twin);
+        const V3 mid{r.mx, r.my, r.mz};
+        const float dj = preloaded ? dtab : distance(point, mid);
+        const float nc = fadd(cur_cost, fmul(dj, cur_type_cost));
+        const float es = fadd(nc, fmul(distance(mid, end_point), cheapest));
+        const bool acc = ok && !(bs.value_edge(r.twin, praw) <= es);
+        const uint32_t amask = __ballot_sync(FULL, acc);
+        if (amask == 0) continue;
+        const uint32_t n_acc = __popc(amask);
+        if (n_nodes + n_acc > node_cap || heap.len + n_acc > heap_cap) {
+          status = heap.len + n_acc > heap_cap ? 7u : 2u;
+          break;
+        }
+        const uint32_t rank = __popc(amask & lt);
+        if (acc) nodes[n_nodes + rank] = make_uint2(r.twin, cur.z);
+        // best_estimates inserts: side by side, except where two accepted states share a physical entry
+        // (compact: the same polygon; hashed: the same home slot) — the later one then needs a fresh probe
+        if (LAYOUT == 1 || LAYOUT == 2) {
+          const uint32_t peers = __match_any_sync(FULL, acc ? collision_key<LAYOUT>(bs, r.twin, lane) : (0x80000000u | lane));
+          const bool later = acc && (peers & lt) != 0;
+          // an insert that has to walk a probe chain (hashed) or goes to the overflow table (compact) can end
+          // anywhere: then every insert of this expansion is made in turn, each with a fresh probe
+          const bool chained = acc && needs_chain<LAYOUT>(bs, r.twin, praw);
+          uint32_t lmask = __any_sync(FULL, chained) ? amask : __ballot_sync(FULL, later);
+          bool fail = false;
+          if (acc && !((lmask >> lane) & 1u)) fail = !bs.store(r.twin, praw, es);
+          while (lmask) {
+            const uint32_t j = (uint32_t)__ffs(lmask) - 1u;
+            lmask &= lmask - 1u;
+            __syncwarp();
+            if (lane == j) fail = !bs.store(r.twin, bs.probe(r.twin), es);
+          }
+          __syncwarp();
+          if (LAYOUT == 1) ovf_total = __reduce_add_sync(FULL, ovf_used(bs));
+          if (__any_sync(FULL, fail) || (LAYOUT == 1 && ovf_total > arena.ovf_cap / 2u)) {
+            status = LAYOUT == 1 ? 5u : 2u;
+            break;
+          }
+        } else if (LAYOUT == 0) {
+          if (acc) bs.store(r.twin, praw, es);
+        }
+        // pushes in ascending edge order
+        uint32_t m = amask, k = 0;
+        while (m) {
+          const uint32_t j = (uint32_t)__ffs(m) - 1u;
+          m &= m - 1u;
+          const uint32_t s2 = __shfl_sync(FULL, r.twin, j);
+          const float e2 = __shfl_sync(FULL, es, j), c2 = __shfl_sync(FULL, nc, j);
+          heap.push(make_uint4(__float_as_uint(c2), __float_as_uint(e2), n_nodes + k, s2));
+          k++;
+        }
+        n_nodes += n_acc;
+        hmax = max(hmax, heap.len);
+      }
+      // ---- off-mesh links in ascending link index (canonical; pathfinding.rs:196-229) ----
+      if (has_links && status == 1) {
+        for (uint32_t k = nav.node_link_begin[poly]; k < nav.node_link_begin[poly + 1] && status == 1; k++) {
+          const uint32_t l = nav.node_links[k];
+          if (l == ignore_link) continue;
+          if (!is_finite(cost_of(nav.link_dst_type_dense[l]))) continue;
+          float link_cost = 0.0f;
+          if (nav.link_kind[l] == LMB_LINK_ANIMATION) {
+            if (!is_kind_permitted(nav.link_anim_kind[l])) continue;
+            link_cost = nav.link_cost[l];
+          }
+          const float* pp = nav.link_portal + 6 * (size_t)l;
+          const V3 pm = midpoint(V3{pp[0], pp[1], pp[2]}, V3{pp[3], pp[4], pp[5]});
+          const float c = fadd(fmul(distance(point, pm), cur_type_cost), link_cost);
+          const float ncost = fadd(cur_cost, c);
+          V3 hp = pm;  // heuristic of an OffMeshLink state: portal (boundary) / destination portal (animation)
+          if (nav.link_kind[l] != LMB_LINK_BOUNDARY) {
+            const float* dp = nav.link_dst_portal + 6 * (size_t)l;
+            hp = midpoint(V3{dp[0], dp[1], dp[2]}, V3{dp[3], dp[4], dp[5]});
+          }
+          push_special(ST_LINK0 + l, ncost, fadd(ncost, fmul(distance(hp, end_point), cheapest)), cur.z);
+        }
+      }
+    }
+
+    // ============================ walk the back-pointers (astar.rs:86-105) ============================
+    // staged goal-first as (state, next state) pairs; k_path_fixup turns them into (node, portal)
+    uint32_t w_pos = 0;
+    if (status == 1 && goal_index != LMB_NONE) {
+      __syncwarp();
+      uint32_t w_node = goal_index, w_next = ST_END;
+      bool done = false;
+      while (!done) {
+        const uint32_t base = w_node & ~127u;
+        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+        const uint32_t i0 = base + 4u * lane;
+        if (i0 < node_cap_window) {
+          const uint4* sec = reinterpret_cast<const uint4*>(nodes + i0);
+          lo = __ldcg(sec);
+          hi = __ldcg(sec + 1);
+        }
+        for (;;) {
+          const uint32_t idx = w_node - base, wi = idx & 3u;
+          const uint32_t mx = wi == 0 ? lo.x : (wi == 1 ? lo.z : (wi == 2 ? hi.x : hi.z));
+          const uint32_t my = wi == 0 ? lo.y : (wi == 1 ? lo.w : (wi == 2 ? hi.y : hi.w));
+          const uint32_t rx = __shfl_sync(FULL, mx, idx >> 2), ry = __shfl_sync(FULL, my, idx >> 2);
+          if (rx != ST_END) {
+            if (lane == 0) {
+              if (LAYOUT == 3)
+                nodes[n_nodes - 1u - w_pos] = make_uint2(rx, w_next);
+              else if (w_pos < stage_cap)
+                stage[w_pos] = make_uint2(rx, w_next);
+            }
+            w_pos++;
+          }
+          w_next = rx;
+          if (ry == LMB_NONE) {
+            done = true;
+            break;
+          }
+          w_node = ry;
+          if ((ry & ~127u) != base) break;
+        }
+      }
+      if (w_pos > stage_cap) {
+        status = 6;  // cannot happen for a simple path
+      } else {
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd(pool.cursor, (unsigned long long)w_pos);
+        off = __shfl_sync(FULL, off, 0);
+        if (off + w_pos > pool.capacity) {
+          status = 3;
+        } else {
+          success = 1;
+          path_off = (uint32_t)off;
+          path_len = w_pos;
+        }
+      }
+    }
+
+    // ================= finish: corridor -> pool, best_estimates back to "absent", results =================
+    __syncwarp();
+    if (success) {
+      if (LAYOUT == 3) {
+        for (uint32_t k = lane; k < path_len; k += 32)
+          pool.entries[(size_t)path_off + k] = __ldcg(nodes + (n_nodes - path_len + k));
+      } else {
+        for (uint32_t k = lane; k < path_len; k += 32)
+          pool.entries[(size_t)path_off + (path_len - 1u - k)] = __ldcg(stage + k);
+      }
+    }
+    __syncwarp();
+    if (n_nodes) {
+      const uint32_t staged = (status != 2 && status != 5) ? (w_pos < stage_cap ? w_pos : stage_cap) : 0u;
+      restore_best<LAYOUT>(arena, slot_base, nodes, n_nodes, staged, ovf_total != 0, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      q.out_status[qid] = status;
+      if (status == 1) {
+        q.out_success[qid] = success;
+        q.out_explored[qid] = explored;
+        q.out_path_off[qid] = path_off;
+        q.out_path_len[qid] = path_len;
+        if (q.slot) {
+          const uint32_t sl = q.slot[qid];
+          pool.slot_path_off[sl] = path_off;
+          pool.slot_path_len[sl] = path_len;
+          pool.slot_cost_hint[sl] = explored;
+        }
+        atomicAdd(&counters->n_done, 1u);
+        atomicAdd(&counters->explored_total, (unsigned long long)explored);
+        atomicAdd(&counters->path_nodes_total, (unsigned long long)path_len);
+        atomicAdd(&counters->heap_max_total, (unsigned long long)hmax);
+      } else if (status == 2) {
+        atomicAdd(&counters->n_retry_arena, 1u);
+      } else if (status == 7) {
+        atomicAdd(&counters->n_retry_heap, 1u);
+      } else if (status == 5) {
+        atomicAdd(&counters->n_retry_dense, 1u);
+      } else if (status == 6) {
+        atomicAdd(&counters->n_failed, 1u);
+      } else {
+        atomicAdd(&counters->n_retry_pool, 1u);
+      }
+    }
+  }
+}
+
+template <uint32_t HS, uint32_t BPS, int LAYOUT>
+static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                          AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
+                          cudaStream_t stream) {
+  static_assert(HS >= AT_HEAP_SM_MIN, "a slot's open-list spill is sized for HS >= AT_HEAP_SM_MIN (arena_layout)");
+  constexpr uint32_t WPB = AT_THREADS / 32;
+  const size_t smem = (size_t)HS * WPB * sizeof(uint4);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  uint32_t slots = arena.n_slots < q.n ? arena.n_slots : q.n;
+  const uint32_t resident = sm_count * BPS * WPB;
+  if (slots > resident) slots = resident;
+  AStarArena a = arena;
+  a.n_slots = slots;
+  k_astar_warp<HS, BPS, LAYOUT><<<(slots + WPB - 1) / WPB, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw,
+                                                                                  simple ? 1u : 0u);
+}
+
+void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                       AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
+                       cudaStream_t stream) {
+  // up to 8 queries per SM: 1536 open-list entries each in shared memory; more: 16 warps per SM with 768
+  const bool wide = q.n > 8u * sm_count && arena.n_slots > 8u * sm_count;
+#define LMB_WARP_LAUNCH(L)                                                                                  \
+  do {                                                                                                      \
+    if (wide) launch_warp_t<768, 4, L>(nav, arena, q, pool, counters, type_raw, simple, sm_count, stream);   \
+    else launch_warp_t<1536, 2, L>(nav, arena, q, pool, counters, type_raw, simple, sm_count, stream);       \
+  } while (0)
+  if (arena.layout == 1) LMB_WARP_LAUNCH(1);
+  else if (arena.layout == 2) LMB_WARP_LAUNCH(2);
+  else if (arena.layout == 3) LMB_WARP_LAUNCH(3);
+  else LMB_WARP_LAUNCH(0);
+#undef LMB_WARP_LAUNCH
+}
+
+}  // namespace lmb

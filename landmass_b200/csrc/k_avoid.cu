@@ -1057,7 +1057,7 @@ void launch_avoid_grid(uint32_t n_records, const AvoidRecord* records, AvoidGrid
     k_max_radius<<<blocks_for(n_records, 256), 256, 0, stream>>>(n_records, records, max_radius_bits);
     k_grid_count<<<blocks_for(n_records, 256), 256, 0, stream>>>(grid, n_records, records);
   }
-  launch_exclusive_scan(grid.cell_count, grid.cell_start, cells + 1, stream);
+  launch_exclusive_scan(grid.cell_count, grid.cell_start, cells + 1, grid.scan_tmp, stream);
   cudaMemsetAsync(grid.cell_count, 0, ((size_t)cells + 1) * sizeof(uint32_t), stream);
   if (n_records) k_grid_fill<<<blocks_for(n_records, 256), 256, 0, stream>>>(grid, n_records, records);
 }

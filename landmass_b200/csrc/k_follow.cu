@@ -608,9 +608,95 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* in, uin
   }
 }
 
-void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t stream) {
+// Multi-block form (reduce, scan the tile sums, scan the tiles): the avoidance grid has up to 8 M cells and
+// one block walking them 1024 at a time was a visible part of a steady frame.
+constexpr uint32_t SCAN_TILE = 4096;  // 1024 threads x 4 consecutive elements
+
+__global__ void __launch_bounds__(1024) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* sums) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t i0 = (size_t)blockIdx.x * SCAN_TILE + 4u * threadIdx.x;
+  uint32_t v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (i0 + k < n) v += in[i0 + k];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) warp_sums[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane];
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) sums[blockIdx.x] = w;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(const uint32_t* in, uint32_t* out, uint32_t n,
+                                                     const uint32_t* __restrict__ tile_offset) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t i0 = (size_t)blockIdx.x * SCAN_TILE + 4u * threadIdx.x;
+  uint32_t v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    v[k] = i0 + k < n ? in[i0 + k] : 0u;
+    t += v[k];
+  }
+  uint32_t x = t;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sums[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= (uint32_t)o) w += y;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  uint32_t prefix = tile_offset[blockIdx.x] + (warp ? warp_sums[warp - 1] : 0u) + x - t;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (i0 + k < n) out[i0 + k] = prefix;
+    prefix += v[k];
+  }
+}
+
+uint32_t exclusive_scan_tmp_words(uint32_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t stream) {
   if (n == 0) return;
-  k_exclusive_scan<<<1, 1024, 0, stream>>>(in, out, n);
+  if (n <= SCAN_TILE || !tmp) {
+    k_exclusive_scan<<<1, 1024, 0, stream>>>(in, out, n);
+    return;
+  }
+  const uint32_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_tile_sums<<<tiles, 1024, 0, stream>>>(in, n, tmp);
+  k_exclusive_scan<<<1, 1024, 0, stream>>>(tmp, tmp, tiles);
+  k_scan_tiles<<<tiles, 1024, 0, stream>>>(in, out, n, tmp);
+}
+
+// What a caller's movement system does between two updates (README example; SURVEY.md §8d common inputs:
+// velocity = previous desired velocity, p += v dt), on the device, so that a resident loop needs no host round
+// trip: position += desired_velocity * dt, velocity = desired_velocity, LMB_AGENT_RESET cleared.
+__global__ void k_integrate(uint32_t n, float dt, const float* __restrict__ out_velocity, float* position,
+                            float* velocity, uint32_t* flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < 3; k++) {
+    const float v = out_velocity[3 * (size_t)i + k];
+    position[3 * (size_t)i + k] = fadd(position[3 * (size_t)i + k], fmul(v, dt));
+    velocity[3 * (size_t)i + k] = v;
+  }
+  flags[i] &= ~LMB_AGENT_RESET;
+}
+
+void launch_integrate(uint32_t n, float dt, const float* out_velocity, float* position, float* velocity,
+                      uint32_t* flags, cudaStream_t stream) {
+  if (n) k_integrate<<<(n + 255) / 256, 256, 0, stream>>>(n, dt, out_velocity, position, velocity, flags);
 }
 
 // ---- path pool compaction -----------------------------------------------------------
@@ -631,8 +717,9 @@ __global__ void k_pool_set_cursor(PathPool pool, const uint32_t* new_off, uint32
 }
 
 // step 1: new offsets (exclusive scan of the lengths) and the live total into *cursor
-void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, cudaStream_t stream) {
-  launch_exclusive_scan(src.slot_path_len, scan_tmp, max_agents, stream);
+void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, uint32_t* tile_tmp,
+                      cudaStream_t stream) {
+  launch_exclusive_scan(src.slot_path_len, scan_tmp, max_agents, tile_tmp, stream);
   k_pool_set_cursor<<<1, 32, 0, stream>>>(src, scan_tmp, max_agents);
 }
 // step 2: copy every live path to its new offset in dst and update slot_path_off

@@ -19,9 +19,21 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "lmb_context.h"
 
 static thread_local std::string g_create_error;
+
+void lmb_comm_release(lmb_ctx* ctx);  // lmb_comm.cu
+int32_t lmb_step_begin_impl(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first,
+                            bool sync_at_end);
+
+// NVTX range per phase: makes every nsys / ncu capture attributable to a phase of the step.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 
 // ---------------------------------------------------------------------------
@@ -82,6 +94,8 @@ int32_t lmb_create(const lmb_config* config, lmb_ctx** out_ctx) {
   e = cudaSetDevice(ctx->device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   for (int i = 0; i < 11 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev[i]);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_q[i]);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_ag[i]);
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_counters, sizeof(AStarCounters));
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_small, 64 * sizeof(uint32_t));
   cudaDeviceProp prop;
@@ -126,6 +140,11 @@ void lmb_destroy(lmb_ctx* ctx) {
   }
   for (int i = 0; i < 11; i++)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->ev_q[i]) cudaEventDestroy(ctx->ev_q[i]);
+    if (ctx->ev_ag[i]) cudaEventDestroy(ctx->ev_ag[i]);
+  }
+  lmb_comm_release(ctx);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->h_small) cudaFreeHost(ctx->h_small);
   delete ctx;
@@ -159,7 +178,10 @@ static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_ca
   a.ovf_cap = layout == 1 ? OVF_CAP : 0u;
   a.hash_cap = 0;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t spill = (heap_cap > AT_HEAP_SM ? heap_cap - AT_HEAP_SM : 0) + 2;
+  // the kernels address the spill as gm[i - HS + 1] with the HS of the launch shape, i < heap_cap: size it for
+  // the smallest HS any shape uses (sizing it from AT_HEAP_SM = 48 let the <16,40,5> shape write 7
+  // entries past the region)
+  const size_t spill = (heap_cap > AT_HEAP_SM_MIN ? heap_cap - AT_HEAP_SM_MIN : 0) + 2;
   a.special_offset = 0;
   if (layout == 1) {
     const size_t n_polys = ctx->n_ids >> ctx->kshift;
@@ -170,6 +192,8 @@ static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_ca
     while (cap < 2u * node_cap + 16u) cap <<= 1;  // every node adds at most one key: never more than half full
     a.hash_cap = cap;
     a.best_bytes = (size_t)cap * 8;
+  } else if (layout == 3) {
+    a.best_bytes = 0;  // forest: no best_estimates at all
   } else {
     a.best_bytes = up((size_t)a.n_states * 4);
   }
@@ -191,10 +215,10 @@ static int32_t setup_arena_into(lmb_ctx* ctx, AStarArena& a, DevBuf<uint8_t>& bu
     CUDA_TRY(ctx, buf.reserve_exact(bytes));
   }
   a.base = buf.p;
-  if (getenv("LMB_DEBUG"))
+  if (ctx->cfg.flags & LMB_CONFIG_DEBUG_LOG)
     fprintf(stderr, "[lmb] A* %s: %u slots x %.2f MB (n_states %u, node_cap %u, heap_cap %u, kshift %u, %s best)\n",
             what, slots, a.slot_stride / 1048576.0, a.n_states, node_cap, heap_cap, a.kshift,
-            a.layout == 1 ? "compact" : (a.layout == 2 ? "hashed" : "dense"));
+            a.layout == 1 ? "compact" : (a.layout == 2 ? "hashed" : (a.layout == 3 ? "no" : "dense")));
   launch_arena_init(a, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
   return LMB_OK;
@@ -218,7 +242,7 @@ static size_t arena_budget(const lmb_ctx* ctx) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)16 << 30;
   free_b += ctx->d_arena.cap;
-  return std::min<size_t>((size_t)(free_b * 0.6), (size_t)110 << 30);
+  return std::min<size_t>((size_t)(free_b * 0.4), (size_t)64 << 30);
 }
 
 // Makes sure the arena can run `n_queries` concurrently (up to the slot limit / byte budget).
@@ -552,8 +576,8 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
     // off-mesh links — is a forest: a search then enters every polygon through one edge only.
     // With a single cycle a search comes round both ways and enters whole regions twice, so
     // anything else starts dense.  (A compact query that fills its overflow table is re-run
-    // dense and switches the context for good, see run_astar; LMB_ASTAR_COMPACT=1 forces compact
-    // as the starting layout for tests of that path, LMB_ASTAR_DENSE=1 forces dense.)
+    // dense and switches the context for good, see run_astar; lmb_config.flags carries the test
+    // hooks that force a starting layout.)
     {
       std::vector<uint32_t> parent(d->n_polys);
       for (uint32_t p = 0; p < d->n_polys; p++) parent[p] = p;
@@ -578,13 +602,28 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
         if (link_src[l] != LMB_NONE) join(link_src[l], d->link_dst_node[l]);
       const bool forest = connections + components == d->n_polys;
       const uint32_t n_states = ctx->n_ids + nav.n_links + 2;
+      const uint32_t fl = ctx->cfg.flags;
+      const bool f_compact = fl & LMB_CONFIG_ASTAR_COMPACT, f_dense = fl & LMB_CONFIG_ASTAR_DENSE;
+      const bool f_hashed = fl & LMB_CONFIG_ASTAR_HASHED;
+      ctx->nav_is_forest = forest;
       ctx->best_layout = 0;
-      if (ctx->kshift != 0 && (forest || getenv("LMB_ASTAR_COMPACT")) && !getenv("LMB_ASTAR_DENSE"))
+      if (f_dense || f_hashed || f_compact) {
+        // test hooks: force a layout (compact needs padded ids)
+        ctx->best_layout = f_dense ? 0 : (f_compact && ctx->kshift != 0 ? 1 : (f_hashed ? 2 : 0));
+      } else if (forest && !(fl & LMB_CONFIG_ASTAR_NO_FOREST)) {
+        // Forest: the entered edge is excluded from a state's successors (pathfinding.rs:165-166), so a
+        // search enters every polygon once and generates every state once — `best_estimates` can never
+        // reject or make stale anything.  No table at all: layout 3.
+        ctx->best_layout = 3;
+      } else if (forest && ctx->kshift != 0) {
         ctx->best_layout = 1;
-      else if ((n_states > (1u << 21) || getenv("LMB_ASTAR_HASHED")) && !getenv("LMB_ASTAR_DENSE"))
+      } else if (n_states > (1u << 21)) {
         ctx->best_layout = 2;  // a search touches a small part of a mesh this large: keep only what it touches
+      }
       if (ctx->best_layout == 2) ctx->arena_node_cap = std::min<uint32_t>(ctx->arena_node_cap, 131072u);
-      if (getenv("LMB_ASTAR_HASHED")) ctx->arena_node_cap = std::min<uint32_t>(ctx->arena_node_cap, 2048u);
+      if (f_hashed) ctx->arena_node_cap = std::min<uint32_t>(ctx->arena_node_cap, 2048u);
+      // the are_nodes_connected BFS borrows the node list as seen[] / queue[] (2 x n_region_numbers words)
+      ctx->arena_node_cap = std::max<uint32_t>(ctx->arena_node_cap, d->n_region_numbers + 64);
       ctx->big_heap = !forest;  // first guess: a wavefront; corrected from the first batch's open lists
     }
     ctx->arena = AStarArena{};
@@ -635,7 +674,8 @@ static int32_t compact_pool(lmb_ctx* ctx, unsigned long long needed_free) {
   int other = 1 - ctx->pool_cur;
   PathPool src = make_pool(ctx);
   // live size = sum of path lengths (the scan also yields every path's new offset)
-  launch_pool_scan(src, m, ctx->d_scan_tmp.p, s);
+  CUDA_TRY(ctx, ctx->d_scan_tiles.reserve(exclusive_scan_tmp_words(m)));
+  launch_pool_scan(src, m, ctx->d_scan_tmp.p, ctx->d_scan_tiles.p, s);
   unsigned long long live = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&live, ctx->d_pool_cursor.p, sizeof(live), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
@@ -737,7 +777,8 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     AStarQueries qq = q;
     qq.n = n_run;
     qq.list = list;
-    launch_astar(ctx->nav, *cur, qq, make_pool(ctx), ctx->d_counters.p, ctx->d_type_raw.p, ctx->big_heap, s);
+    ctx->timings.astar_launch_kind |= launch_astar(ctx->nav, *cur, qq, make_pool(ctx), ctx->d_counters.p,
+                                                   ctx->d_type_raw.p, ctx->big_heap, ctx->cfg.flags, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
@@ -798,6 +839,22 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
   return ctx->fail(LMB_ERR_CAPACITY, "A* scratch kept overflowing");
 }
 
+// A* of the batched query API: the last step's timings / PathingResult bookkeeping (ctx->timings) must not be
+// disturbed by a query made between two steps; the batch's own figures go to ctx->query_timings.
+static int32_t run_astar_query(lmb_ctx* ctx, const AStarQueries& q) {
+  const lmb_step_timings saved = ctx->timings;
+  ctx->timings = lmb_step_timings{};
+  cudaEventRecord(ctx->ev_q[0], ctx->stream);
+  const int32_t st = run_astar(ctx, q);
+  cudaEventRecord(ctx->ev_q[1], ctx->stream);
+  if (st == LMB_OK && cudaEventSynchronize(ctx->ev_q[1]) == cudaSuccess)
+    cudaEventElapsedTime(&ctx->timings.astar_ms, ctx->ev_q[0], ctx->ev_q[1]);
+  ctx->timings.n_repath = q.n;
+  ctx->query_timings = ctx->timings;
+  ctx->timings = saved;
+  return st;
+}
+
 // ---------------------------------------------------------------------------
 // batched queries
 // ---------------------------------------------------------------------------
@@ -810,15 +867,17 @@ int32_t lmb_sample_points(lmb_ctx* ctx, uint32_t n, const float* points, const l
   if (n == 0) return LMB_OK;
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
-  CUDA_TRY(ctx, ctx->d_position.upload(points, 3 * (size_t)n, s));
-  CUDA_TRY(ctx, ctx->d_agent_point.reserve(3 * (size_t)n));
-  CUDA_TRY(ctx, ctx->d_agent_node.reserve(n));
-  launch_sample_points(ctx->nav, *options, n, ctx->d_position.p, nullptr, 0, 0, ctx->d_agent_point.p,
-                       ctx->d_agent_node.p, s);
+  // scratch of its own: the resident agent inputs (d_position, d_agent_point ...) must survive a query made
+  // between two lmb_step_resident calls
+  CUDA_TRY(ctx, ctx->d_query_point.upload(points, 3 * (size_t)n, s));
+  CUDA_TRY(ctx, ctx->d_query_out_point.reserve(3 * (size_t)n));
+  CUDA_TRY(ctx, ctx->d_query_out_node.reserve(n));
+  launch_sample_points(ctx->nav, *options, n, ctx->d_query_point.p, nullptr, 0, 0, ctx->d_query_out_point.p,
+                       ctx->d_query_out_node.p, s);
   CUDA_TRY(ctx, cudaGetLastError());
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_points, ctx->d_agent_point.p, 3 * (size_t)n * sizeof(float),
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_points, ctx->d_query_out_point.p, 3 * (size_t)n * sizeof(float),
                                 cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_nodes, ctx->d_agent_node.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_nodes, ctx->d_query_out_node.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return LMB_OK;
 }
@@ -925,8 +984,7 @@ int32_t lmb_find_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_node, con
   unsigned long long cursor0 = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&cursor0, ctx->d_pool_cursor.p, sizeof(cursor0), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  ctx->timings = lmb_step_timings{};
-  st = run_astar(ctx, q);
+  st = run_astar_query(ctx, q);
   if (st != LMB_OK) return st;
   std::vector<uint32_t> off(n), len(n);
   CUDA_TRY(ctx, cudaMemcpyAsync(out_success, q.out_success, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -1004,8 +1062,7 @@ int32_t lmb_find_straight_paths(lmb_ctx* ctx, uint32_t n, const uint32_t* start_
   unsigned long long cursor0 = 0;
   CUDA_TRY(ctx, cudaMemcpyAsync(&cursor0, ctx->d_pool_cursor.p, sizeof(cursor0), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  ctx->timings = lmb_step_timings{};
-  st = run_astar(ctx, q);
+  st = run_astar_query(ctx, q);
   if (st != LMB_OK) return st;
   std::vector<uint32_t> len(n), begin(n + 1), count(n);
   CUDA_TRY(ctx, cudaMemcpyAsync(out_success, q.out_success, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -1072,6 +1129,12 @@ int32_t lmb_agents_upload(lmb_ctx* ctx, const lmb_agents_in* a, const lmb_charac
     if (a->slot[i] >= ctx->cfg.max_agents)
       return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "agent %u: slot %u >= max_agents %u", i, a->slot[i],
                        ctx->cfg.max_agents);
+  if (n && a->override_begin && a->override_begin[n] && (!a->override_type || !a->override_cost))
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_upload: override arrays are null but the CSR is not empty");
+  if (n && a->permitted_begin && a->permitted_begin[n] && !a->permitted_kind)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_upload: permitted_kind is null but the CSR is not empty");
+  if (c && c->n && (!c->position || !c->velocity || !c->radius))
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_upload: null character array");
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   cudaEventRecord(ctx->ev[0], s);
@@ -1166,9 +1229,21 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
 extern "C" {
 
 int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first) {
+  return lmb_step_begin_impl(ctx, o, dt, n_total, first, /*sync_at_end=*/true);
+}
+
+}  // extern "C"
+
+// sync_at_end = false (lmb_step_sharded): the exchange and phase D are enqueued behind this on the same
+// stream, so nothing has to wait for the host here.
+int32_t lmb_step_begin_impl(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first,
+                            bool sync_at_end) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
   if (!ctx->has_nav) return ctx->fail(LMB_ERR_NO_NAVDATA, "no navigation data uploaded");
   if (!o) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step: null options");
+  if (first > n_total || ctx->n_agents > n_total - first)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step_begin: agent range [%u,+%u) outside %u", first,
+                     ctx->n_agents, n_total);
   cudaSetDevice(ctx->device);
   cudaStream_t s = ctx->stream;
   const uint32_t n = ctx->n_agents;
@@ -1207,7 +1282,9 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
   AgentArrays ag = lmb_make_agent_arrays(ctx);
   AgentPersist persist = lmb_make_persist(ctx);
 
+  NvtxRange nvtx_step("lmb:step_begin");
   cudaEventRecord(ctx->ev[2], s);
+  nvtxRangePushA("lmb:phaseA sample_points");
   launch_reset_slots(ag, persist, make_pool(ctx), s);
   // phase A: sample agents (skipped when paused / using a link), targets, characters
   launch_sample_points(ctx->nav, *o, n, ag.position, ag.flags, LMB_AGENT_PAUSED | LMB_AGENT_USING_ANIMATION_LINK,
@@ -1217,6 +1294,7 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
   launch_sample_points(ctx->nav, *o, ctx->n_chars, ctx->d_char_position.p, nullptr, 0, 0, ctx->d_char_point.p,
                        ctx->d_char_node.p, s);
   T.kernel_launches += (n ? 3 : 0) + (ctx->n_chars ? 1 : 0);
+  nvtxRangePop();
   cudaEventRecord(ctx->ev[3], s);
 
   // phase B: decision
@@ -1237,7 +1315,9 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
   scratch.waypoint_link = ctx->d_waypoint_link.p;
   scratch.waypoint_points = ctx->d_waypoint_points.p;
   CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_queue_count.p, 0, sizeof(uint32_t), s));
+  nvtxRangePushA("lmb:phaseB repath_decide");
   launch_repath_decide(ctx->nav, ag, persist, make_pool(ctx), queue, scratch, s);
+  nvtxRangePop();
   T.kernel_launches += n ? 1 : 0;
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small, ctx->d_queue_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -1261,32 +1341,36 @@ int32_t lmb_step_begin(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_
     q.permitted_kind = ctx->d_permitted_kind.p;
   }
   if (n_repath) {
+    NvtxRange r("lmb:phaseB astar");
     st = run_astar(ctx, q);
     if (st != LMB_OK) return st;
   }
   cudaEventRecord(ctx->ev[5], s);
 
   // phase C
+  nvtxRangePushA("lmb:phaseC follow");
   launch_follow(ctx->nav, ag, persist, make_pool(ctx), q, scratch, s);
+  nvtxRangePop();
   T.kernel_launches += n ? 1 : 0;
   CUDA_TRY(ctx, cudaGetLastError());
   cudaEventRecord(ctx->ev[6], s);
 
   // phase D, first half: this rank's avoidance records into the halo buffer
-  if (first > n_total || n > n_total - first)
-    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_step_begin: agent range [%u,+%u) outside %u", first, n, n_total);
   ctx->halo_total = n_total;
   ctx->halo_first = first;
   (void)dt;
   if (!(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE)) {
+    NvtxRange r("lmb:phaseD records");
     st = lmb_avoidance_build_records(ctx, o, n_total, first);
     if (st != LMB_OK) return st;
   }
   cudaEventRecord(ctx->ev[10], s);
-  CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the caller may now all-gather the halo buffer
+  if (sync_at_end) CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the caller may now all-gather the halo buffer
   ctx->step_open = true;
   return LMB_OK;
 }
+
+extern "C" {
 
 int32_t lmb_halo_buffer(lmb_ctx* ctx, void** device_ptr, uint64_t* record_bytes, uint64_t* n_records) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
@@ -1312,6 +1396,7 @@ int32_t lmb_step_end(lmb_ctx* ctx, const lmb_options* o, float dt) {
   cudaEventRecord(ctx->ev[9], s);
   // phase D, second half: grid over ALL records, ORCA for this rank's agents
   if (!(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE)) {
+    NvtxRange r("lmb:phaseD avoidance");
     st = lmb_avoidance_solve(ctx, o, dt, ctx->halo_total, ctx->halo_first);
     if (st != LMB_OK) return st;
   }
@@ -1345,6 +1430,17 @@ int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
   int32_t st = lmb_step_begin(ctx, o, dt, ctx->n_agents, 0);
   if (st != LMB_OK) return st;
   return lmb_step_end(ctx, o, dt);
+}
+
+int32_t lmb_agents_integrate(lmb_ctx* ctx, float delta_time) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (ctx->last_n_results != ctx->n_agents)
+    return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_integrate: no step has run for the uploaded agents");
+  cudaSetDevice(ctx->device);
+  launch_integrate(ctx->n_agents, delta_time, ctx->d_out_velocity.p, ctx->d_position.p, ctx->d_velocity.p,
+                   ctx->d_flags.p, ctx->stream);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return LMB_OK;
 }
 
 int32_t lmb_agents_download(lmb_ctx* ctx, const lmb_agents_out* out) {
@@ -1488,6 +1584,12 @@ int32_t lmb_agent_avoidance_constraints(lmb_ctx* ctx, uint32_t agent_index, uint
 int32_t lmb_get_step_timings(lmb_ctx* ctx, lmb_step_timings* out) {
   if (!ctx || !out) return LMB_ERR_INVALID_ARGUMENT;
   *out = ctx->timings;
+  return LMB_OK;
+}
+
+int32_t lmb_get_query_timings(lmb_ctx* ctx, lmb_step_timings* out) {
+  if (!ctx || !out) return LMB_ERR_INVALID_ARGUMENT;
+  *out = ctx->query_timings;
   return LMB_OK;
 }
 

@@ -67,6 +67,8 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
   grid.cell_count = ctx->d_cell_count.p;
   grid.cell_start = ctx->d_cell_start2.p;
   grid.sorted = ctx->d_sorted.p;
+  CUDA_TRY(ctx, ctx->d_scan_tiles.reserve(exclusive_scan_tmp_words((uint32_t)cells + 1)));
+  grid.scan_tmp = ctx->d_scan_tiles.p;
   uint32_t* max_radius_bits = ctx->d_avoid_overflow.p + 1;
   launch_avoid_grid(n_total, ctx->d_records.p, grid, max_radius_bits, s);
   ctx->timings.kernel_launches += 4;

@@ -86,7 +86,8 @@ struct lmb_ctx {
   uint32_t kshift = 0, n_ids = 0;              // edge-record id space (see EdgeRec)
   uint32_t arena_node_cap = 0, arena_heap_cap = 0;
   bool big_heap = false;                       // launch shape for large open lists (k_astar.cu)
-  int best_layout = 0;                         // best_estimates layout (k_astar_common.cuh): 0 dense, 1 compact, 2 hashed
+  int best_layout = 0;                         // best_estimates layout (k_astar_common.cuh): 0 dense, 1 compact, 2 hashed, 3 none (forest)
+  bool nav_is_forest = false;
   DevBuf<AStarCounters> d_counters;
   AStarCounters* h_counters = nullptr;  // pinned
 
@@ -112,6 +113,9 @@ struct lmb_ctx {
        has_overrides = false, has_permitted = false;
   DevBuf<float> d_char_position, d_char_velocity, d_char_radius, d_char_point;
   DevBuf<uint32_t> d_char_node;
+  // scratch of lmb_sample_points (never the agents' buffers: queries are side-effect free for steps)
+  DevBuf<float> d_query_point, d_query_out_point;
+  DevBuf<uint32_t> d_query_out_node;
   // sampled
   DevBuf<float> d_agent_point, d_target_point;
   DevBuf<uint32_t> d_agent_node, d_target_node;
@@ -127,7 +131,7 @@ struct lmb_ctx {
   DevBuf<uint32_t> d_out_state, d_out_link_id;
   // avoidance
   DevBuf<AvoidRecord> d_records, d_char_records;
-  DevBuf<uint32_t> d_cell_count, d_cell_start2, d_sorted, d_avoid_overflow;
+  DevBuf<uint32_t> d_cell_count, d_cell_start2, d_sorted, d_avoid_overflow, d_scan_tiles;
   DevBuf<uint8_t> d_avoid_scratch;
   // debug-avoidance export: agents that set LMB_AGENT_KEEP_AVOIDANCE_DATA (in upload order)
   std::vector<uint32_t> h_dbg_row_of;  // [n_agents] row or LMB_NONE; empty = nobody asked
@@ -139,8 +143,13 @@ struct lmb_ctx {
   uint32_t avoid_caps[5] = {64, 64, 128, 256, 256};  // neighbours, explore, border edges, cones, lines
 
   lmb_step_timings timings{};
+  lmb_step_timings query_timings{};  // of the last lmb_find_paths / lmb_find_straight_paths batch
   cudaEvent_t ev[11]{};
+  cudaEvent_t ev_q[2]{};
+  cudaEvent_t ev_ag[2]{};            // around the library-owned all-gather (lmb_step_sharded)
   uint32_t halo_total = 0, halo_first = 0;
+  void* comm = nullptr;  // ncclComm_t of lmb_comm_init (lmb_comm.cu)
+  uint32_t comm_ranks = 0, comm_rank = 0;
   bool step_open = false;
   double path_len_estimate = 0.0;
   double explored_estimate = 0.0;  // running mean explored_nodes: the hint of an agent without history  // running mean corridor length, sizes the pool before A*

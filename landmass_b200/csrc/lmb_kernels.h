@@ -14,8 +14,9 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
 
 // ---- kernel 2: batched A* (k_astar.cu) ----
 constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
-constexpr uint32_t AT_HEAP_SM = 48;   // open-list entries per query held in shared memory (16 B each); the
-                                      // spill region of a slot holds heap_cap - AT_HEAP_SM + 1
+constexpr uint32_t AT_HEAP_SM = 48;   // unit of the open-list capacity bookkeeping (heap_cap = AT_HEAP_SM + spill growth)
+constexpr uint32_t AT_HEAP_SM_MIN = 40;  // smallest number of open-list entries any launch shape keeps in shared
+                                         // memory: a slot's spill region holds heap_cap - AT_HEAP_SM_MIN + 2 entries
 
 struct AStarArena {
   uint8_t* base;          // device memory for all slots
@@ -30,7 +31,7 @@ struct AStarArena {
   size_t heap_offset;     // byte offset of the open-list spill inside a slot
   // best_estimates layout (k_astar_common.cuh): dense f32[n_states] at offset 0, or compact
   uint32_t layout;        // 0 = dense, 1 = compact (per-polygon entries + specials + overflow table),
-                          // 2 = hashed (open-addressing table)
+                          // 2 = hashed (open-addressing table), 3 = none (forest meshes: no region at all)
   uint32_t hash_cap;      // hashed: table entries (power of two, >= 2 x node_cap)
   uint32_t ovf_cap;       // overflow-table entries (power of two)
   size_t special_offset;  // compact: f32[n_links + 2]
@@ -85,8 +86,11 @@ struct AStarCounters {  // device-resident
   unsigned long long heap_max_total;  // sum over finished queries of their largest open list
 };
 
-void launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                  AStarCounters* counters, const uint32_t* type_raw, bool big_heap, cudaStream_t stream);
+// flags: lmb_config.flags (LMB_CONFIG_ASTAR_* launch-shape test hooks).  Returns the kernel family launched:
+// 1 = thread-per-query (k_astar.cu), 2 = warp-per-query (k_astar_warp.cu), 0 = nothing.
+uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                      AStarCounters* counters, const uint32_t* type_raw, bool big_heap, uint32_t flags,
+                      cudaStream_t stream);
 // order[] = query indices 0..n-1 sorted by descending cost hint of their agent slot (bucketed)
 void launch_order_queries(uint32_t n, const uint32_t* q_slot, const uint32_t* slot_cost_hint, uint32_t unknown_hint,
                           uint32_t* order, cudaStream_t stream);
@@ -167,7 +171,8 @@ void launch_remap_paths(const PathPool& pool, uint32_t max_agents, const uint32_
                         cudaStream_t stream);
 
 // path pool compaction
-void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, cudaStream_t stream);
+void launch_pool_scan(const PathPool& src, uint32_t max_agents, uint32_t* scan_tmp, uint32_t* tile_tmp,
+                      cudaStream_t stream);
 void launch_pool_copy(const PathPool& src, uint2* dst_entries, uint32_t max_agents, const uint32_t* scan_tmp,
                       cudaStream_t stream);
 
@@ -186,6 +191,7 @@ struct AvoidGrid {
   uint32_t* cell_count;   // [nx*ny + 1]
   uint32_t* cell_start;   // [nx*ny + 1]
   uint32_t* sorted;       // [n_records] record indices grouped by cell
+  uint32_t* scan_tmp;     // [exclusive_scan_tmp_words(nx*ny + 1)]
   uint32_t capacity_cells;
 };
 
@@ -220,7 +226,10 @@ void launch_avoidance(const DevNav& nav, const AgentArrays& ag, const AgentPersi
                       const AvoidRecord* char_records, AvoidGrid& grid, const AvoidScratch& scratch,
                       float* bounds_tmp, cudaStream_t stream);
 
-// generic single-block exclusive scan (u32), in place allowed
-void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t stream);
+// exclusive scan (u32), in place allowed; tmp = exclusive_scan_tmp_words(n) words (NULL: single block)
+void launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, cudaStream_t stream);
+uint32_t exclusive_scan_tmp_words(uint32_t n);
+void launch_integrate(uint32_t n, float dt, const float* out_velocity, float* position, float* velocity,
+                      uint32_t* flags, cudaStream_t stream);
 
 }  // namespace lmb

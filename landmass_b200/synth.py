@@ -221,3 +221,50 @@ def default_options(radius: float = 0.5):
     from .archipelago import ArchipelagoOptions
 
     return ArchipelagoOptions.from_agent_radius(radius).to_abi()
+
+
+def tiled_archipelago_flat(k: int, g: int, type_block: int = 16, costs=((0, 1.0), (1, 2.0), (2, 5.0))) -> dict:
+    """BASELINE config 4's world: k x k islands, each a g x g unit-quad grid, tiled by pure translations so that
+    borders coincide (boundary links at edge_link_distance 0.01), polygon types (x/type_block + y/type_block) mod 3
+    with costs {0: 1, 1: 2, 2: 5}.  Returns the flattened navigation data (island linking done on the host,
+    nav_data.rs:326-514)."""
+    from .nav_data import Island, NavigationData, Transform
+
+    types = ((np.arange(g)[None, :] // type_block + np.arange(g)[:, None] // type_block) % 3)
+    mesh = grid_mesh(g, g, types=types)
+    nd = NavigationData()
+    for iy in range(k):
+        for ix in range(k):
+            nd.add_island(Island(Transform(translation=(ix * g, iy * g, 0.0), rotation=0.0), mesh))
+    for t, c in costs:
+        nd.set_type_index_cost(t, c)
+    nd.update(0.01, 0.25)
+    return nd.flatten()
+
+
+def uniform_agents(n: int, span_x: float, span_y: float, seed: int = SEED, target_reach: float | None = None,
+                   radius: float = 0.5) -> dict:
+    """n agents uniform over [0.1, span - 0.1]^2 with uniform targets (or targets within `target_reach` of the
+    agent); same per-agent parameters as make_agents."""
+    from . import _abi
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pos = np.zeros((n, 3), dtype=np.float32)
+    tgt = np.zeros((n, 3), dtype=np.float32)
+    hi = np.array([span_x - 0.1, span_y - 0.1])
+    pos[:, :2] = rng.uniform([0.1, 0.1], hi, size=(n, 2))
+    if target_reach is None:
+        tgt[:, :2] = rng.uniform([0.1, 0.1], hi, size=(n, 2))
+    else:
+        tgt[:, :2] = np.clip(pos[:, :2] + rng.uniform(-target_reach, target_reach, size=(n, 2)), 0.1, hi)
+    return {
+        "n": n,
+        "slot": np.arange(n, dtype=np.uint32),
+        "flags": np.full(n, _abi.AGENT_HAS_TARGET | _abi.AGENT_RESET | _abi.AGENT_PERMIT_ALL_LINKS, dtype=np.uint32),
+        "position": pos,
+        "velocity": np.zeros((n, 3), dtype=np.float32),
+        "target": tgt,
+        "radius": np.full(n, radius, dtype=np.float32),
+        "desired_speed": np.full(n, 1.0, dtype=np.float32),
+        "max_speed": np.full(n, 2.0, dtype=np.float32),
+    }

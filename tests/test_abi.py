@@ -61,7 +61,15 @@ def test_constants_match_header():
                         ("LMB_AGENT_PAUSED", _abi.AGENT_PAUSED), ("LMB_AGENT_RESET", _abi.AGENT_RESET),
                         ("LMB_AGENT_PERMIT_ALL_LINKS", _abi.AGENT_PERMIT_ALL_LINKS),
                         ("LMB_AGENT_KEEP_AVOIDANCE_DATA", _abi.AGENT_KEEP_AVOIDANCE_DATA),
-                        ("LMB_CONFIG_NO_AVOIDANCE", _abi.CONFIG_NO_AVOIDANCE)]:
+                        ("LMB_CONFIG_NO_AVOIDANCE", _abi.CONFIG_NO_AVOIDANCE),
+                        ("LMB_CONFIG_DEBUG_LOG", _abi.CONFIG_DEBUG_LOG),
+                        ("LMB_CONFIG_ASTAR_COMPACT", _abi.CONFIG_ASTAR_COMPACT),
+                        ("LMB_CONFIG_ASTAR_DENSE", _abi.CONFIG_ASTAR_DENSE),
+                        ("LMB_CONFIG_ASTAR_HASHED", _abi.CONFIG_ASTAR_HASHED),
+                        ("LMB_CONFIG_ASTAR_LARGE_SHAPES", _abi.CONFIG_ASTAR_LARGE_SHAPES),
+                        ("LMB_CONFIG_ASTAR_THREAD_ONLY", _abi.CONFIG_ASTAR_THREAD_ONLY),
+                        ("LMB_CONFIG_ASTAR_WARP_ONLY", _abi.CONFIG_ASTAR_WARP_ONLY),
+                        ("LMB_CONFIG_ASTAR_NO_FOREST", _abi.CONFIG_ASTAR_NO_FOREST)]:
         m = re.search(rf"#define {name} (\d+)u", text)
         assert m and int(m.group(1)) == value, name
 

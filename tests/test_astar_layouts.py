@@ -13,12 +13,23 @@ pytestmark = pytest.mark.gpu
 NAMES = ["success", "explored", "begin", "nodes", "portals"]
 
 
+KERNELS = [pytest.param(0, id="warp-per-query"),
+           pytest.param(_abi.CONFIG_ASTAR_THREAD_ONLY, id="thread-per-query")]
+
+
+@pytest.fixture(params=KERNELS)
+def kernel(request):
+    """Small batches go to the warp-per-query kernel (k_astar_warp.cu) by default; THREAD_ONLY keeps them on
+    the thread-per-query kernel (k_astar.cu).  Every layout test runs on both."""
+    return request.param
+
+
 def backends(flat, max_agents=4096, flags=0, **kw):
     from landmass_b200._native import NativeBackend
     from oracle.oracle_py import OracleBackend
 
     gpu = NativeBackend(max_agents=max_agents, flags=flags, **kw)
-    cpu = OracleBackend(flags=flags)
+    cpu = OracleBackend(flags=flags & _abi.CONFIG_NO_AVOIDANCE)
     gpu.navdata_upload(flat)
     cpu.navdata_upload(flat)
     return gpu, cpu
@@ -38,38 +49,36 @@ def centre_queries(mesh, pairs):
     return sn, mesh.poly_center[sn].astype(np.float32), en, mesh.poly_center[en].astype(np.float32)
 
 
-def test_csr_state_ids_polygon_with_12_edges():
+def test_csr_state_ids_polygon_with_12_edges(kernel):
     """A 12-gon makes max edges > 8: the kernel falls back to CSR edge ids (the state's own record
     is read before the polygon's records can be addressed)."""
     mesh = synth.rosette_mesh(12, 3)
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat)
+    gpu, cpu = backends(flat, flags=kernel)
     pairs = [(a, b) for a in range(mesh.n_polys) for b in range(mesh.n_polys)]
     g = assert_same_paths(gpu, cpu, *centre_queries(mesh, pairs))
     assert g[0].all()
 
 
-def test_padded_ids_with_8_record_polygons():
+def test_padded_ids_with_8_record_polygons(kernel):
     """Hexagon + ring: max edges in (4, 8] -> 8 records per polygon, two chunks per expansion."""
     mesh = synth.rosette_mesh(7, 4)
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat)
+    gpu, cpu = backends(flat, flags=kernel)
     pairs = [(a, b) for a in range(mesh.n_polys) for b in range(mesh.n_polys)]
     g = assert_same_paths(gpu, cpu, *centre_queries(mesh, pairs))
     assert g[0].all()
 
 
 @pytest.mark.parametrize("extra", [0, 6, 40])
-def test_compact_best_with_overflow_and_slot_reuse(extra, capfd, monkeypatch):
+def test_compact_best_with_overflow_and_slot_reuse(extra, capfd, kernel):
     """Perfect mazes (forests) use the compact best_estimates layout.  With extra openings the
     layout is only used when forced; short searches then complete through the overflow table while
     long ones fill it and are re-run dense.  128 slots for 1500 queries re-use every slot ~12
     times (scatter and dense restore)."""
-    monkeypatch.setenv("LMB_DEBUG", "1")
-    monkeypatch.setenv("LMB_ASTAR_COMPACT", "1")
     mesh = synth.loopy_maze_mesh(28, extra)
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat, astar_slots=128)
+    gpu, cpu = backends(flat, astar_slots=128, flags=kernel | _abi.CONFIG_DEBUG_LOG | _abi.CONFIG_ASTAR_COMPACT)
     rng = np.random.Generator(np.random.PCG64(17 + extra))
     nq = 1500
     sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
@@ -83,27 +92,28 @@ def test_compact_best_with_overflow_and_slot_reuse(extra, capfd, monkeypatch):
     assert "compact best" in err and (extra > 0 or "dense best" not in err)
 
 
-def test_forest_detection_picks_layout(capfd, monkeypatch):
-    monkeypatch.setenv("LMB_DEBUG", "1")
-    for mesh, want in [(synth.maze_mesh(12), "compact best"), (synth.loopy_maze_mesh(12, 1), "dense best"),
-                       (synth.grid_mesh(8, 8), "dense best")]:
-        gpu, cpu = backends(synth.single_island_flat(mesh))
+def test_forest_detection_picks_layout(capfd, kernel):
+    """A forest needs no best_estimates at all ("no best"); LMB_CONFIG_ASTAR_NO_FOREST falls back to the
+    per-polygon layout; one extra opening (a cycle) or an open grid is dense."""
+    for mesh, want, fl in [(synth.maze_mesh(12), "no best", 0),
+                           (synth.maze_mesh(12), "compact best", _abi.CONFIG_ASTAR_NO_FOREST),
+                           (synth.loopy_maze_mesh(12, 1), "dense best", 0),
+                           (synth.grid_mesh(8, 8), "dense best", 0)]:
+        gpu, cpu = backends(synth.single_island_flat(mesh), flags=kernel | fl | _abi.CONFIG_DEBUG_LOG)
         assert_same_paths(gpu, cpu, *centre_queries(mesh, [(0, mesh.n_polys - 1), (3, 5)]))
         assert want in capfd.readouterr().err
         gpu.close()
 
 
-def test_compact_best_falls_back_to_dense(capfd, monkeypatch):
+def test_compact_best_falls_back_to_dense(capfd, kernel):
     """Compact layout forced on a maze with cycles: long searches enter more than 512 polygons a
     second time, the overflow table fills, the queries are re-run and the context switches to the
     dense layout — results unchanged."""
-    monkeypatch.setenv("LMB_DEBUG", "1")
-    monkeypatch.setenv("LMB_ASTAR_COMPACT", "1")
     rooms = 64
     base = synth.maze_mesh(rooms)
     mesh = synth.loopy_maze_mesh(rooms, base.n_polys // 17)
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat)
+    gpu, cpu = backends(flat, flags=kernel | _abi.CONFIG_DEBUG_LOG | _abi.CONFIG_ASTAR_COMPACT)
     rng = np.random.Generator(np.random.PCG64(23))
     nq = 200
     sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
@@ -117,14 +127,10 @@ def test_compact_best_falls_back_to_dense(capfd, monkeypatch):
 
 
 @pytest.mark.parametrize("mesh_kind", ["grid", "maze", "rosette"])
-def test_hashed_best_with_table_growth(mesh_kind, capfd, monkeypatch):
+def test_hashed_best_with_table_growth(mesh_kind, capfd, kernel):
     """Hashed best_estimates (chosen for meshes above 2M states; forced here, with a 2048-node
     arena): probe chains, the half-full limit -> arena retry with a doubled table, slot re-use
     (whole-table clear), CSR ids (rosette)."""
-    monkeypatch.setenv("LMB_DEBUG", "1")
-    monkeypatch.setenv("LMB_ASTAR_HASHED", "1")
-    monkeypatch.setenv("LMB_ASTAR_DENSE", "")  # unset below
-    monkeypatch.delenv("LMB_ASTAR_DENSE")
     if mesh_kind == "rosette":
         mesh = synth.rosette_mesh(12, 6)
         pairs = [(a, b) for a in range(mesh.n_polys) for b in range(0, mesh.n_polys, 3)]
@@ -138,7 +144,7 @@ def test_hashed_best_with_table_growth(mesh_kind, capfd, monkeypatch):
         en[:100] = sn[:100]
         ep[:100] = sp[:100] + np.float32(0.05)
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat, astar_slots=96)
+    gpu, cpu = backends(flat, astar_slots=96, flags=kernel | _abi.CONFIG_DEBUG_LOG | _abi.CONFIG_ASTAR_HASHED)
     g = assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
     assert g[0].all()
     err = capfd.readouterr().err
@@ -147,13 +153,12 @@ def test_hashed_best_with_table_growth(mesh_kind, capfd, monkeypatch):
         assert err.count("arena:") >= 2  # the 2048-node table overflowed at least once
 
 
-def test_dense_best_slot_reuse_and_arena_retry(capfd, monkeypatch):
+def test_dense_best_slot_reuse_and_arena_retry(capfd, kernel):
     """Open grid (dense layout): corner-to-corner searches outgrow the initial node list
     (n_states / 4) -> retry with a doubled arena; 64 slots re-used by 400 queries."""
-    monkeypatch.setenv("LMB_DEBUG", "1")
     mesh = synth.grid_mesh(120, 120)
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat, astar_slots=64)
+    gpu, cpu = backends(flat, astar_slots=64, flags=kernel | _abi.CONFIG_DEBUG_LOG)
     rng = np.random.Generator(np.random.PCG64(29))
     nq = 400
     sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
@@ -169,14 +174,14 @@ def test_dense_best_slot_reuse_and_arena_retry(capfd, monkeypatch):
     assert err.count("arena:") >= 2 and "compact best" not in err
 
 
-def test_step_more_agents_than_slots_longest_first_order():
+def test_step_more_agents_than_slots_longest_first_order(kernel):
     """The step orders a batch longest-first from the previous frame's explored_nodes when it has
     more queries than slots.  The order must not change any result: every agent re-plans on
     three consecutive frames (hints absent, then present) and matches the oracle each time."""
     mesh = synth.maze_mesh(24)
     flat = synth.single_island_flat(mesh)
     n = 1200
-    gpu, cpu = backends(flat, flags=_abi.CONFIG_NO_AVOIDANCE, astar_slots=128)
+    gpu, cpu = backends(flat, flags=_abi.CONFIG_NO_AVOIDANCE | kernel, astar_slots=128)
     ag = synth.make_agents(mesh, n)
     opts = synth.default_options()
     for frame in range(3):
@@ -191,13 +196,15 @@ def test_step_more_agents_than_slots_longest_first_order():
             assert np.array_equal(gp[0], cp[0]) and np.array_equal(gp[1], cp[1])
 
 
-@pytest.mark.parametrize("case", ["maze_simple", "maze_overrides", "grid_simple", "grid_types", "loopy_maze_types"])
-def test_large_batch_shapes_against_the_oracle(case, monkeypatch):
+@pytest.mark.parametrize("case", ["maze_simple", "maze_compact", "maze_overrides", "grid_simple", "grid_types",
+                                  "loopy_maze_types"])
+def test_large_batch_shapes_against_the_oracle(case):
     """The launch shapes of large batches — `<16, 40, 5, SIMPLE>` (the benchmarked kernel: one polygon
     type, no overrides), `<16, 48, 4>` (cost tables / per-query overrides in play) and `<8, 96, 4>` (large
     open lists) — only run above ~19 000 queries, which the oracle cannot check in seconds.
-    LMB_ASTAR_SHAPE=large forces them here: 2 500 queries on 192 slots, bit-exact."""
-    monkeypatch.setenv("LMB_ASTAR_SHAPE", "large")
+    LMB_CONFIG_ASTAR_LARGE_SHAPES forces them here: 2 500 queries on 192 slots, bit-exact.  `maze_simple` runs
+    the best_estimates-free forest layout (the benchmarked one), `maze_compact` the per-polygon layout."""
+    flags = _abi.CONFIG_ASTAR_LARGE_SHAPES | (_abi.CONFIG_ASTAR_NO_FOREST if case == "maze_compact" else 0)
     rng = np.random.Generator(np.random.PCG64(4242))
     nq = 2500
     overrides = None
@@ -217,7 +224,7 @@ def test_large_batch_shapes_against_the_oracle(case, monkeypatch):
         flat["n_type_costs"] = 3
         flat["type_cost_index"] = np.array([0, 1, 2], dtype=np.uint32)
         flat["type_cost_value"] = np.array([1.0, 2.5, 0.5], dtype=np.float32)
-    gpu, cpu = backends(flat, astar_slots=192)
+    gpu, cpu = backends(flat, astar_slots=192, flags=flags)
     sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
     ep, en = synth.random_points_on_mesh(mesh, nq, rng)
     if case == "maze_overrides":
