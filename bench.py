@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native landmass agent step.
+"""bench.py — benchmark of the B200-native landmass agent step (`Archipelago::update`).
 
-Metric (BASELINE.json): agent-updates/s of one `Archipelago::update`, repaths included.
-Workload at N=1 (configs[1]): 256x256-room grid maze (131 071 polygons), 100 000 agents with
-uniform random positions/targets; every timed step is a full update in which EVERY agent
-re-plans (the device-side path is dropped before each step), i.e. 100k point samples x2,
-100k A* queries, funnel + reached test, and ORCA avoidance.  N>1: the same per GPU (weak
-scaling), agents sharded by contiguous ranges, navmesh replicated, one NCCL all-gather of
-the 32-byte avoidance records per step.
+Metric (BASELINE.json): agent-updates/s of one update, repaths included.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
 
-`value`  : device-timed throughput with inputs resident in HBM (CUDA events on the step stream).
-`e2e`    : the same step through lmb_step with HOST buffers (H2D + D2H inside the timed region).
+--config 2 (default, the headline; BASELINE configs[1]): 256x256-room grid maze (131 071 polygons), 100 000
+    agents per GPU with uniform positions / targets; every timed step is a full update in which EVERY agent
+    re-plans (sample x2, 100k A* searches, funnel + reached test, ORCA avoidance).  N > 1: weak scaling at
+    constant density — the world holds one maze island per GPU, rank r's agents live on island r, the
+    navigation data (all N islands) is replicated, and the step is lmb_step_sharded: phases A-C, ONE
+    ncclAllGather of the 32-byte avoidance records issued by the library on its own stream, phase D over
+    all records.
+--config 3: open field 2048 x 2048 m (256x256 quads of 8 m), 1 M agents per GPU walking to the antipodal
+    point; frame 0 (everyone plans) and the median of the steady frames (agents move, natural re-plans).
+--config 4: 8x8 islands of 128x128 quads (1 M polygons, boundary links, type costs {1, 2, 5}), agents
+    sharded over the GPUs, walking to targets ~1.5 islands away; frame 0 + median steady frame.
+--config 5: repath storm on the 512x512-room maze: every agent re-plans every frame; A* queries/s for
+    1 k / 10 k / 100 k agents and by corridor length.
+
+`value`   : device-timed throughput with inputs resident in HBM (CUDA events on the step stream; N > 1:
+            wall clock between barriers, max over ranks).
+`e2e`     : the same step through the C ABI with HOST buffers (H2D + D2H inside the timed region).
 `roofline`: the dominant kernel (k_astar) against the measured HBM copy bandwidth.
-`cpu_baseline`: the CPU oracle (single-threaded C++ port of the reference; the Rust crate
-            cannot be built here) on a bounded sample of the same workload.
+`cpu_baseline`: the CPU oracle (single-threaded C++ port of the reference; the Rust crate cannot be built
+            here) on a bounded sample of the same workload.
+`parity_check`: a sample of this run's own outputs (PathingResults, corridors) checked against the oracle
+            outside the timed region.
 """
 from __future__ import annotations
 
@@ -35,11 +46,12 @@ sys.path.insert(0, ROOT)
 ROOMS = 256
 AGENTS_PER_GPU = 100_000
 DT = 1.0 / 60.0
+ISLAND_PITCH = 640.0  # spacing of the per-GPU maze islands (a 256-room maze is 513 m wide)
 B_STEP = 240.0  # algorithmic bytes per steady agent-update
-# DRAM bytes per explored node of k_astar, from the one `ncu --set full` capture of a fully loaded
-# launch (profiles/r01_ncu_astar_loaded.md: dram read + write / explored nodes).  The bench-size
-# launch itself cannot be captured: kernel replay would have to save and restore its ~100 GB arena.
-NCU_DRAM_BYTES_PER_EXPLORED = 114.4
+# DRAM bytes per explored node of k_astar from `ncu --set full` of a fully loaded launch on a capturable
+# (scratch_bytes-limited) arena — profiles/r02_ncu_astar_loaded.md
+NCU_DRAM_BYTES_PER_EXPLORED = None
+NCU_SOURCE = "profiles/r02_ncu_astar_loaded.md"
 
 
 def measured_peak_gbs():
@@ -105,19 +117,108 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_workload(rooms: int, n_agents: int, rank: int):
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def maze_world(rooms: int, n_islands: int):
+    """One maze island per GPU, `ISLAND_PITCH` apart along x (no links between them: a maze's border is
+    closed).  Returns (mesh, flattened navdata)."""
     from landmass_b200 import synth
+    from landmass_b200.nav_data import Island, NavigationData, Transform
 
     mesh = synth.maze_mesh(rooms)
-    flat = synth.single_island_flat(mesh)
-    ag = synth.make_agents(mesh, n_agents, seed=synth.SEED + 7919 * rank)
-    return mesh, flat, ag
+    if n_islands == 1:
+        return mesh, synth.single_island_flat(mesh)
+    nd = NavigationData()
+    for r in range(n_islands):
+        nd.add_island(Island(Transform(translation=(r * ISLAND_PITCH, 0.0, 0.0), rotation=0.0), mesh))
+    nd.update(0.01, 0.25)
+    return mesh, nd.flatten()
 
 
+def build_workload(args, world: int, rank: int):
+    """-> dict(flat, ag (this rank's agents), n, moving, desc)"""
+    from landmass_b200 import synth
+
+    cfg = args.config
+    if cfg in (2, 5):
+        rooms = args.rooms if cfg == 2 else 512
+        mesh, flat = maze_world(rooms, world)
+        ag = synth.make_agents(mesh, args.agents, seed=synth.SEED + 7919 * rank)
+        if world > 1:
+            ag["position"] = ag["position"] + np.array([rank * ISLAND_PITCH, 0, 0], dtype=np.float32)
+            ag["target"] = ag["target"] + np.array([rank * ISLAND_PITCH, 0, 0], dtype=np.float32)
+        return {"flat": flat, "ag": ag, "n": args.agents, "moving": False, "mesh": mesh,
+                "polygons": int(flat["n_polys"])}
+    if cfg == 3:
+        # one open field per GPU (constant density): fields ISLAND_PITCH * 4 apart
+        from landmass_b200.nav_data import Island, NavigationData, Transform
+
+        mesh = synth.grid_mesh(256, 256, cell=8.0)
+        pitch = 2048.0 + 64.0
+        if world == 1:
+            flat = synth.single_island_flat(mesh)
+        else:
+            nd = NavigationData()
+            for r in range(world):
+                nd.add_island(Island(Transform(translation=(r * pitch, 0.0, 0.0), rotation=0.0), mesh))
+            nd.update(0.01, 0.25)
+            flat = nd.flatten()
+        n = args.agents
+        rng = np.random.Generator(np.random.PCG64(synth.SEED + rank))
+        pos, _ = synth.random_points_on_mesh(mesh, n, rng)
+        ag = synth.make_agents(mesh, n)
+        off = np.array([rank * pitch, 0, 0], dtype=np.float32)
+        ag["position"] = pos + off
+        ag["target"] = np.stack([2048.0 - pos[:, 0], 2048.0 - pos[:, 1], pos[:, 2]], axis=1).astype(np.float32) + off
+        return {"flat": flat, "ag": ag, "n": n, "moving": True, "mesh": mesh, "polygons": int(flat["n_polys"])}
+    if cfg == 4:
+        k, g, cell = 8, 128, args.cell
+        flat = synth.tiled_archipelago_flat(k, g, cell=cell)
+        n = args.agents
+        span = k * g * cell
+        # agents of rank r: a contiguous slice of the global (seeded) agent list — slot ranges per rank
+        allag = synth.uniform_agents(n * world, span, span, seed=synth.SEED, target_reach=1.5 * g * cell)
+        from landmass_b200 import sharded
+
+        ag = sharded.slice_agents(allag, rank * n, (rank + 1) * n, slot_base=rank * n)
+        return {"flat": flat, "ag": ag, "n": n, "moving": True, "mesh": None, "polygons": int(flat["n_polys"])}
+    raise SystemExit(f"unknown --config {cfg}")
+
+
+def workload_config(args, n_gpus, sample_note=None):
+    c = args.config
+    text = {
+        2: f"configs[1]: {args.rooms}x{args.rooms} grid-maze navmesh ({2 * args.rooms * args.rooms - 1} polygons)"
+           f"{' per GPU (one maze island per GPU, constant density)' if n_gpus > 1 else ''}, {args.agents} agents "
+           "per GPU, full Archipelago::update with every agent re-planning each step (sample x2, A*, funnel, "
+           "ORCA avoidance)",
+        3: f"configs[2]: open field 2048x2048 m (256x256 quads of 8 m){' per GPU' if n_gpus > 1 else ''}, "
+           f"{args.agents} agents per GPU walking to the antipodal point; value = median steady frame",
+        4: f"configs[3]: 8x8 islands of 128x128 quads of {args.cell} m (1 048 576 polygons, boundary links, type "
+           f"costs 1/2/5), {args.agents} agents per GPU sharded by slot range; value = median steady frame",
+        5: f"configs[4]: repath storm on the 512x512-room maze (524 287 polygons), {args.agents} agents per GPU, "
+           "every agent re-plans every frame",
+    }[c]
+    cfg = {
+        "workload": text, "agents_per_gpu": args.agents,
+        "parallelism": f"agents sharded x{n_gpus}, navmesh replicated, one ncclAllGather of 32 B/agent per step "
+                       "issued by the library (lmb_step_sharded)" if n_gpus > 1 else "1 GPU",
+        "cache": "inputs and A* working set (one arena slot per query in flight, tens of GB) far exceed the "
+                 "126 MB L2; no flush needed",
+    }
+    if sample_note:
+        cfg["sample"] = sample_note
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / CPU baseline (the only places that execute oracle/)
+# ---------------------------------------------------------------------------------------------
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU path.  The Rust crate cannot be compiled in
-    this image (no cargo/rustc), so this times the oracle port (single-threaded, like the
-    reference) on a bounded sample of the same workload."""
+    """`--impl reference`: the reference's own CPU path.  The Rust crate cannot be compiled in this image (no
+    cargo/rustc), so this times the oracle port (single-threaded, like the reference) on a bounded sample of
+    the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -125,54 +226,58 @@ def run_reference(args):
     from oracle.oracle_py import OracleBackend
 
     sample = args.ref_sample
-    mesh, flat, ag = build_workload(args.rooms, sample, 0)
+    a2 = argparse.Namespace(**vars(args))
+    a2.agents = sample
+    w = build_workload(a2, 1, 0)
     cpu = OracleBackend()
-    cpu.navdata_upload(flat)
+    cpu.navdata_upload(w["flat"])
     opts = synth.default_options()
     times = []
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        cpu.step(ag, None, opts, DT)  # RESET flag set: every agent re-plans
+        cpu.step(w["ag"], None, opts, DT)  # RESET flag set: every agent re-plans
         t1 = time.perf_counter()
         if step >= args.warmup:
             times.append(t1 - t0)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms * 1e-3)
-    all_cores = reference_all_cores(args, sample)
     line = {
         "impl": "reference", "metric": "agent-updates/s", "value": value, "unit": "agent-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus, sample_note=f"{sample} agents of the workload per step"),
         "cpu_baseline": {"value": value, "unit": "agent-updates/s", "cores": 1, "kind": "port",
-                         "sample": f"{sample} agents (every agent re-plans) per step on the full "
-                                   f"{args.rooms}x{args.rooms} maze; single thread like the reference"},
+                         "sample": f"{sample} agents (every agent re-plans) per step on the full mesh; single "
+                                   "thread like the reference"},
         "e2e": {"value": value, "unit": "agent-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        # not reference behaviour (`Archipelago::update` is serial): what the host could do by running
-        # one independent archipelago per core, for readers who want the harsher ratio
-        "all_cores": all_cores,
+        # not reference behaviour (`Archipelago::update` is serial): what the host could do by running one
+        # independent archipelago per core, for readers who want the harsher ratio
+        "all_cores": reference_all_cores(args, sample),
     }
     print(json.dumps(line))
 
 
-def _reference_worker(rank, rooms, sample, steps, barrier, out):
+def _reference_worker(rank, args, sample, steps, barrier, out):
     from landmass_b200 import synth
     from oracle.oracle_py import OracleBackend
 
-    mesh, flat, ag = build_workload(rooms, sample, rank)
+    a2 = argparse.Namespace(**vars(args))
+    a2.agents = sample
+    w = build_workload(a2, 1, 0)
+    w["ag"] = synth.make_agents(w["mesh"], sample, seed=synth.SEED + 7919 * rank) if w["mesh"] is not None else w["ag"]
     cpu = OracleBackend()
-    cpu.navdata_upload(flat)
+    cpu.navdata_upload(w["flat"])
     opts = synth.default_options()
     barrier.wait()
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu.step(ag, None, opts, DT)
+        cpu.step(w["ag"], None, opts, DT)
     out.put((rank, time.perf_counter() - t0))
 
 
 def reference_all_cores(args, sample):
-    """One oracle process per host core, each with its own `sample` agents on its own copy of the maze,
-    started together; aggregate agent-updates/s = processes x sample x steps / slowest process."""
+    """One oracle process per host core, each with its own `sample` agents on its own copy of the mesh, started
+    together; aggregate agent-updates/s = processes x sample x steps / slowest process."""
     import multiprocessing as mp
 
     procs = max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
@@ -180,7 +285,7 @@ def reference_all_cores(args, sample):
     steps = min(args.steps, 2)
     ctx = mp.get_context("fork")
     barrier, out = ctx.Barrier(procs), ctx.Queue()
-    workers = [ctx.Process(target=_reference_worker, args=(r, args.rooms, sample, steps, barrier, out))
+    workers = [ctx.Process(target=_reference_worker, args=(r, args, sample, steps, barrier, out))
                for r in range(procs)]
     for w in workers:
         w.start()
@@ -191,36 +296,92 @@ def reference_all_cores(args, sample):
             "sample": f"{sample} agents per process, every agent re-plans, {steps} step(s)"}
 
 
-def workload_config(args, n_gpus, sample_note=None):
-    cfg = {
-        "workload": f"configs[1]: {args.rooms}x{args.rooms} grid-maze navmesh, {args.agents} agents per GPU, "
-                    "full Archipelago::update with every agent re-planning each step (sample x2, A*, "
-                    "funnel, ORCA avoidance)",
-        "agents_per_gpu": args.agents, "polygons": 2 * args.rooms * args.rooms - 1,
-        "parallelism": f"agents sharded x{n_gpus}, navmesh replicated, NCCL all-gather of 32 B/agent",
-        "cache": "inputs and A* working set (one arena slot per query in flight, ~100 GB) far exceed the "
-                 "126 MB L2; no flush needed",
-    }
-    if sample_note:
-        cfg["sample"] = sample_note
-    return cfg
+def cpu_baseline(args) -> dict:
+    from landmass_b200 import synth
+    from oracle.oracle_py import OracleBackend
+
+    sample = args.cpu_sample
+    a2 = argparse.Namespace(**vars(args))
+    a2.agents = sample
+    w = build_workload(a2, 1, 0)
+    cpu = OracleBackend()
+    cpu.navdata_upload(w["flat"])
+    opts = synth.default_options()
+    t0 = time.perf_counter()
+    cpu.step(w["ag"], None, opts, DT)
+    dt = time.perf_counter() - t0
+    cpu.close()
+    return {"value": sample / dt, "unit": "agent-updates/s", "cores": 1, "kind": "port", "seconds": dt,
+            "sample": f"one full update of {sample} agents (every agent re-plans) on the same mesh; oracle = "
+                      "single-threaded C++ port of the reference (the Rust crate cannot be built here)"}
 
 
+def parity_check(gpu, w, n_check=200) -> dict:
+    """A sample of the last step's own results against the oracle, outside any timed region: PathingResult
+    (success, explored_nodes) and the stored corridor (node ids + portal codes) of n_check agents, bit-exact."""
+    from landmass_b200 import synth
+    from oracle.oracle_py import OracleBackend
+
+    ag, n = w["ag"], w["n"]
+    rng = np.random.Generator(np.random.PCG64(12345))
+    pr = gpu.pathing_results_array()
+    if len(pr) == 0:
+        return {"n": 0, "ok": False, "mismatches": 0, "what": "no agent re-planned in the checked step"}
+    idx = np.sort(rng.choice(pr[:, 0].astype(np.int64), size=min(n_check, len(pr)), replace=False))
+    by_agent = {int(a): (int(s), int(e)) for a, s, e in pr}
+    cpu = OracleBackend()
+    cpu.navdata_upload(w["flat"])
+    opts = synth.default_options()
+    pos = gpu.resident_positions()[idx] if w["moving"] else ag["position"][idx]
+    sp, sn = cpu.sample_points(pos, opts)
+    tp, tn = cpu.sample_points(ag["target"][idx], opts)
+    checked = bad = 0
+    todo = [k for k, i in enumerate(idx) if int(i) in by_agent and sn[k] != 0xFFFFFFFF and tn[k] != 0xFFFFFFFF]
+    if todo:
+        t = np.array(todo)
+        succ, expl, begin, nodes, portals = cpu.find_paths(sn[t], sp[t], tn[t], tp[t], path_capacity=1 << 24)
+        for j, k in enumerate(todo):
+            i = int(idx[k])
+            checked += 1
+            if by_agent[i] != (int(succ[j]), int(expl[j])):
+                bad += 1
+                continue
+            gn, gp = gpu.agent_path(int(ag["slot"][i]))
+            if not (np.array_equal(gn, nodes[begin[j]:begin[j + 1]]) and np.array_equal(gp, portals[begin[j]:begin[j + 1]])):
+                bad += 1
+    cpu.close()
+    return {"n": checked, "ok": bad == 0 and checked > 0, "mismatches": bad,
+            "what": "PathingResult (success, explored_nodes) and corridor (nodes, portal codes) of a random sample "
+                    "of this run's re-planning agents vs the CPU oracle, bit-exact"}
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--rooms", type=int, default=ROOMS)
-    ap.add_argument("--agents", type=int, default=AGENTS_PER_GPU)
-    ap.add_argument("--cpu-sample", type=int, default=1000,
-                    help="agents in the CPU-baseline sample (one step; ~15-25 s)")
-    ap.add_argument("--ref-sample", type=int, default=150,
-                    help="agents per step of the --impl reference arm")
+    ap.add_argument("--agents", type=int, default=None, help="agents per GPU")
+    ap.add_argument("--cell", type=float, default=4.0, help="config 4: quad size in metres")
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="agents in the CPU-baseline sample (one step)")
+    ap.add_argument("--ref-sample", type=int, default=150, help="agents per step of the --impl reference arm")
+    ap.add_argument("--flags", type=int, default=0, help="lmb_config.flags (kernel-shape test hooks)")
+    ap.add_argument("--scratch-gb", type=float, default=0.0, help="A* arena byte budget (0 = auto)")
+    ap.add_argument("--shape", type=int, default=0, help="lmb_config.astar_shape (launch-shape tuning hook)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true")
     args = ap.parse_args()
+    moving = args.config in (3, 4)
+    if args.steps is None:
+        args.steps = 50 if moving else 5
+    if args.warmup is None:
+        args.warmup = 5 if moving else 3
+    if args.agents is None:
+        args.agents = {2: AGENTS_PER_GPU, 3: 1_000_000, 4: 500_000, 5: 10_000}[args.config]
     if args.impl == "reference":
         run_reference(args)
         return
@@ -231,12 +392,12 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
 
-    # keep stdout to the ONE JSON line: everything else any library writes to fd 1 (NCCL prints its
-    # version banner there) goes to stderr; the JSON line is written to the saved descriptor
+    # keep stdout to the ONE JSON line: everything else any library writes to fd 1 (NCCL prints its version
+    # banner there) goes to stderr; the JSON line is written to the saved descriptor
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
-    import torch  # plumbing only: device selection, NCCL all-gather, barriers
+    import torch  # plumbing only: device selection, barriers, broadcast of the NCCL unique id
 
     from landmass_b200 import _abi, synth
     from landmass_b200._native import NativeBackend
@@ -250,34 +411,25 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    n = args.agents
-    mesh, flat, ag = build_workload(args.rooms, n, rank)
+    w = build_workload(args, world, rank)
+    n, ag, flat = w["n"], w["ag"], w["flat"]
     opts = synth.default_options()
-    gpu = NativeBackend(max_agents=n, device=local_rank)
+    gpu = NativeBackend(max_agents=n, device=local_rank, flags=args.flags, astar_shape=args.shape,
+                        scratch_bytes=int(args.scratch_gb * (1 << 30)))
     gpu.navdata_upload(flat)
+    if world > 1:
+        # the library owns the collective: rank 0 makes the NCCL unique id, torch only ships the 128 bytes
+        uid = [gpu.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        gpu.comm_init(uid[0], world, rank)
 
-    n_total, first = n * world, n * rank
-
-    halo = None
-
-    def one_step_resident():
-        nonlocal halo
+    def one_step():
         if world == 1:
             gpu.step_resident(opts, DT)
-            return
-        gpu.step_begin(opts, DT, n_total, first)
-        ptr, rec_bytes, n_rec = gpu.halo_buffer()
-        if halo is None or halo[0] != ptr:
-            # wrap the library's device buffer (no copy); torch is only the NCCL plumbing here
-            class _Buf:
-                __cuda_array_interface__ = {"shape": (int(n_rec * rec_bytes),), "typestr": "|u1",
-                                            "data": (int(ptr), False), "version": 2}
-            halo = (ptr, torch.as_tensor(_Buf(), device=torch.device("cuda", local_rank)))
-        buf = halo[1]
-        mine = buf[first * rec_bytes:(first + n) * rec_bytes]
-        dist.all_gather_into_tensor(buf, mine)
-        torch.cuda.synchronize()
-        gpu.step_end(opts, DT)
+        else:
+            gpu.step_sharded(opts, DT, n)
+        if moving:
+            gpu.agents_integrate(DT)
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,42 +437,73 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timings_row():
+        T = gpu.step_timings()
+        return {"total_ms": T.total_ms, "sample": T.sample_ms, "repath_decide": T.repath_decide_ms,
+                "astar": T.astar_ms, "follow": T.follow_ms, "avoidance": T.avoidance_ms, "allgather": T.allgather_ms,
+                "n_repath": T.n_repath, "explored": T.explored_nodes, "path_nodes": T.path_nodes,
+                "launches": T.kernel_launches}
+
     # ---- device-resident timing (`value`) ----
     gpu.agents_upload(ag, None)
+    frame0 = None
+    if moving:
+        barrier()
+        t0 = time.perf_counter()
+        one_step()
+        barrier()
+        frame0 = {"wall_ms": 1e3 * (time.perf_counter() - t0), **timings_row()}
     for _ in range(args.warmup):
-        one_step_resident()
+        one_step()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    dev_ms, astar_ms, phases = [], [], []
-    explored = path_nodes = n_repath = launches = 0
-    t0 = time.perf_counter()
+    rows, walls = [], []
+    t_all = time.perf_counter()
     for _ in range(args.steps):
-        one_step_resident()
-        T = gpu.step_timings()
-        dev_ms.append(T.total_ms)
-        astar_ms.append(T.astar_ms)
-        phases.append((T.sample_ms, T.repath_decide_ms, T.astar_ms, T.follow_ms, T.avoidance_ms))
-        explored += T.explored_nodes
-        path_nodes += T.path_nodes
-        n_repath += T.n_repath
-        launches += T.kernel_launches
+        t0 = time.perf_counter()
+        one_step()
+        if moving and world > 1:
+            barrier()
+        walls.append(1e3 * (time.perf_counter() - t0))
+        rows.append(timings_row())
     barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    wall_ms = 1e3 * (time.perf_counter() - t_all) / args.steps
     clocks = sampler.stop()
-    print(f"[bench rank {rank}] per-step device ms: {[round(x, 1) for x in dev_ms]}", file=sys.stderr)
-    out = gpu.agents_download()
-    step_ms = float(np.mean(dev_ms)) if world == 1 else wall_ms  # multi-GPU: wall between barriers incl. all-gather
-    red = torch.tensor([step_ms, float(np.mean(astar_ms))], device="cuda", dtype=torch.float64)
+    dev_ms = [r["total_ms"] for r in rows]
+    print(f"[bench rank {rank}] per-step device ms: {[round(x, 2) for x in dev_ms[:12]]}", file=sys.stderr)
+    if moving:
+        step_ms = float(np.median(dev_ms)) if world == 1 else float(np.median(walls))
+    else:
+        step_ms = float(np.mean(dev_ms)) if world == 1 else wall_ms  # multi-GPU: wall between barriers
+    astar_ms = float(np.mean([r["astar"] for r in rows]))
+    red = torch.tensor([step_ms, astar_ms, float(np.mean([r["allgather"] for r in rows]))], device="cuda",
+                       dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    step_ms_max, astar_ms_max = float(red[0]), float(red[1])
+    step_ms_max, astar_ms_max, allgather_ms_max = float(red[0]), float(red[1]), float(red[2])
+    explored = sum(r["explored"] for r in rows)
+    path_nodes = sum(r["path_nodes"] for r in rows)
+    n_repath = sum(r["n_repath"] for r in rows)
+    launches = sum(r["launches"] for r in rows)
+    out = gpu.agents_download()
 
-    # ---- context figure: steady frames of the same agents (no re-plan forced) ----
-    # Not the headline: the agents keep the corridors of the last timed step and only sample,
-    # check their corridor, follow it (funnel) and avoid each other.
+    parity = None
+    if not args.skip_parity:
+        if moving:
+            # one more step WITHOUT the integration, so that the resident positions are the ones it planned from
+            if world == 1:
+                gpu.step_resident(opts, DT)
+            else:
+                gpu.step_sharded(opts, DT, n)
+        if rank == 0:
+            parity = parity_check(gpu, w)
+        if moving:
+            gpu.agents_integrate(DT)
+
+    # ---- context figure (config 2): steady frames of the same agents (no re-plan forced) ----
     steady = None
-    if world == 1:
+    if world == 1 and args.config == 2:
         ag_steady = dict(ag)
         ag_steady["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
         gpu.agents_upload(ag_steady, None)
@@ -336,102 +519,92 @@ def main():
                   "note": "same agents keeping their corridors: sample x2, corridor check, funnel, ORCA"}
         gpu.agents_upload(ag, None)
 
-    # ---- end-to-end timing through lmb_step with host buffers (`e2e`) ----
+    # ---- end-to-end timing through the C ABI with host buffers (`e2e`) ----
     e2e = None
-    if not args.skip_e2e and world == 1:
-        gpu.step(ag, None, opts, DT)
+    if not args.skip_e2e:
+        reps = max(2, min(args.steps, 10) // 2)
+        host_ag = dict(ag)
+        if moving:
+            host_ag["position"] = gpu.resident_positions()
+            host_ag["velocity"] = out["desired_velocity"].copy()
+            host_ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
+
+        def e2e_step():
+            if world == 1:
+                o = gpu.step(host_ag, None, opts, DT)
+            else:
+                gpu.agents_upload(host_ag, None)
+                gpu.step_sharded(opts, DT, n)
+                o = gpu.agents_download()
+            _ = float(o["desired_velocity"][0, 0])
+            if moving:
+                host_ag["velocity"] = o["desired_velocity"]
+                host_ag["position"] = host_ag["position"] + o["desired_velocity"] * np.float32(DT)
+            return o
+
+        o = e2e_step()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(max(2, args.steps // 2)):
-            out = gpu.step(ag, None, opts, DT)
-            _ = float(out["desired_velocity"][0, 0])
-        barrier()
-        e2e_ms = 1e3 * (time.perf_counter() - t0) / max(2, args.steps // 2)
-        h2d = sum(int(np.asarray(v).nbytes) for k, v in ag.items() if k != "n")
-        d2h = sum(int(v.nbytes) for v in out.values())
-        e2e = {"value": n * world / (e2e_ms * 1e-3), "unit": "agent-updates/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
-    elif world > 1:
-        # multi-GPU e2e: upload + sharded step + download per step, wall clock, max over ranks
-        barrier()
-        t0 = time.perf_counter()
-        reps = max(2, args.steps // 2)
         for _ in range(reps):
-            gpu.agents_upload(ag, None)
-            one_step_resident()
-            out = gpu.agents_download()
-            _ = float(out["desired_velocity"][0, 0])
+            o = e2e_step()
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0) / reps
         r2 = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(r2, op=dist.ReduceOp.MAX)
-        h2d = sum(int(np.asarray(v).nbytes) for k, v in ag.items() if k != "n")
-        d2h = sum(int(v.nbytes) for v in out.values())
-        e2e = {"value": n * world / (float(r2[0]) * 1e-3), "unit": "agent-updates/s",
-               "ms_per_step": float(r2[0]), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        if dist is not None:
+            dist.all_reduce(r2, op=dist.ReduceOp.MAX)
+        h2d = sum(int(np.asarray(v).nbytes) for k, v in host_ag.items() if k != "n")
+        d2h = sum(int(v.nbytes) for v in o.values())
+        e2e = {"value": n * world / (float(r2[0]) * 1e-3), "unit": "agent-updates/s", "ms_per_step": float(r2[0]),
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        # algorithmic bytes of the A* launch: 32 per query + 8 per corridor node + 96 per explored node
+        # algorithmic bytes of the A* launches: 32 per query + 8 per corridor node + 96 per explored node
         astar_bytes = (32.0 * n_repath + 8.0 * path_nodes + 96.0 * explored) / args.steps
         achieved = astar_bytes / (astar_ms_max * 1e-3) / 1e9 if astar_ms_max > 0 else 0.0
-        mean_phase = np.mean(np.array(phases), axis=0)
+        mean = lambda k: float(np.mean([r[k] for r in rows]))
         line = {
             "metric": "agent-updates/s", "value": n * world / (step_ms_max * 1e-3), "unit": "agent-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks, "gpu_launches": int(launches),
-            "astar_queries_per_s": n_repath / args.steps * world / (astar_ms_max * 1e-3),
-            "explored_nodes_per_s": explored / args.steps * world / (astar_ms_max * 1e-3),
-            "phase_ms": {"sample": float(mean_phase[0]), "repath_decide": float(mean_phase[1]),
-                         "astar": float(mean_phase[2]), "follow": float(mean_phase[3]),
-                         "avoidance": float(mean_phase[4]), "wall_per_step": wall_ms},
+            "repaths_per_step": n_repath / args.steps,
+            "astar_queries_per_s": (n_repath / args.steps * world / (astar_ms_max * 1e-3)) if astar_ms_max > 0 else 0.0,
+            "explored_nodes_per_s": (explored / args.steps * world / (astar_ms_max * 1e-3)) if astar_ms_max > 0 else 0.0,
+            "allgather_ms": allgather_ms_max,
+            "phase_ms": {"sample": mean("sample"), "repath_decide": mean("repath_decide"), "astar": mean("astar"),
+                         "follow": mean("follow"), "avoidance": mean("avoidance"), "allgather": mean("allgather"),
+                         "wall_per_step": wall_ms},
             "roofline": {"bound": "hbm", "kernel": "k_astar", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps,
-                         "traffic_source": "ncu dram bytes per explored node of a fully loaded smaller "
-                                           "launch (profiles/r01_ncu_astar_loaded.md) x explored nodes of this "
-                                           "launch; the bench-size launch is not capturable (~100 GB arena)",
+                         "traffic": (NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps
+                                     if NCU_DRAM_BYTES_PER_EXPLORED else None),
+                         "traffic_source": f"ncu dram bytes per explored node ({NCU_SOURCE}) x explored nodes of "
+                                           "this launch",
                          "algorithmic_bytes": astar_bytes, "peak_source": peak_src,
-                         "note": "latency-bound graph search: one dependent chain per query (pop -> "
-                                 "records -> best[] probes -> push), random 32-byte sectors of a per-query "
-                                 "arena; algorithmic bytes = 32/query + 8/corridor node + 96/explored node"},
+                         "note": "latency/issue-bound graph search: one dependent chain per query (pop -> records "
+                                 "-> push), algorithmic bytes = 32/query + 8/corridor node + 96/explored node"},
         }
+        if moving:
+            line["frame0"] = frame0
+            line["steady_ms_median"] = step_ms_max
+            line["steady_ms_p90"] = float(np.percentile(dev_ms if world == 1 else walls, 90))
         if e2e:
             line["e2e"] = e2e
         if steady:
             line["steady_state"] = steady
+        if parity:
+            line["parity_check"] = parity
         if not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        states = np.bincount(out["state"], minlength=9).tolist()
-        line["state_histogram"] = states
+        line["state_histogram"] = np.bincount(out["state"], minlength=9).tolist()
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     gpu.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
-
-
-def cpu_baseline(args) -> dict:
-    from landmass_b200 import synth
-    from oracle.oracle_py import OracleBackend
-
-    sample = args.cpu_sample
-    _, flat, ag = build_workload(args.rooms, sample, 0)
-    cpu = OracleBackend()
-    cpu.navdata_upload(flat)
-    opts = synth.default_options()
-    t0 = time.perf_counter()
-    cpu.step(ag, None, opts, DT)
-    dt = time.perf_counter() - t0
-    cpu.close()
-    return {"value": sample / dt, "unit": "agent-updates/s", "cores": 1, "kind": "port",
-            "seconds": dt,
-            "sample": f"one full update of {sample} agents (every agent re-plans) on the same "
-                      f"{args.rooms}x{args.rooms} maze; oracle = single-threaded C++ port of the reference "
-                      "(the Rust crate cannot be built here)"}
 
 
 if __name__ == "__main__":

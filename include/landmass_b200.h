@@ -247,7 +247,8 @@ typedef struct lmb_config {
   uint32_t astar_slots;      /* A* arena slots = queries in flight; 0 = auto (up to 256 per SM) */
   uint64_t scratch_bytes;    /* byte budget of the A* arena; 0 = auto (40 % of free HBM, <= 64 GB) */
   uint32_t flags;            /* LMB_CONFIG_* */
-  uint32_t reserved;
+  uint32_t astar_shape;      /* tuning hook: launch shape of large A* batches on forest meshes
+                                (0 = library default; k_astar.cu launch_astar lists the others) */
 } lmb_config;
 
 /* Device timings (milliseconds, CUDA events on the step stream) of the last step. */
@@ -317,6 +318,8 @@ int32_t lmb_agents_download(lmb_ctx* ctx, const lmb_agents_out* out);
  * README.md:55-131 — velocity = the desired velocity just computed, position += velocity * delta_time) applied
  * to the resident inputs, and LMB_AGENT_RESET cleared.  Enqueued on the library stream; no synchronisation. */
 int32_t lmb_agents_integrate(lmb_ctx* ctx, float delta_time);
+/* The resident positions (as uploaded, or as advanced by lmb_agents_integrate): [n*3] floats. */
+int32_t lmb_agents_positions(lmb_ctx* ctx, float* out_position, uint32_t capacity);
 
 /* Multi-GPU form of the step: agents are sharded over ranks by contiguous
  * ranges of the global agent order, navigation data is replicated, and the only exchange is

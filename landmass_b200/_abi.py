@@ -206,7 +206,7 @@ class Config(C.Structure):
         ("astar_slots", C.c_uint32),
         ("scratch_bytes", C.c_uint64),
         ("flags", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("astar_shape", C.c_uint32),
     ]
 
 

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "lmb_pathing_results", "lmb_agent_path", "lmb_sample_points", "lmb_find_paths",
     "lmb_get_step_timings", "lmb_step_begin", "lmb_halo_buffer", "lmb_step_end",
     "lmb_find_straight_paths", "lmb_agent_avoidance_constraints", "lmb_get_query_timings",
-    "lmb_comm_unique_id", "lmb_comm_init", "lmb_step_sharded", "lmb_agents_integrate",
+    "lmb_comm_unique_id", "lmb_comm_init", "lmb_step_sharded", "lmb_agents_integrate", "lmb_agents_positions",
 ]
 
 
@@ -82,6 +82,7 @@ def declare_prototypes(lib, prefix: str):
     fn("comm_init", i32, [vp, C.POINTER(C.c_uint8), u32, u32])
     fn("step_sharded", i32, [vp, C.POINTER(_abi.Options), f32, u32])
     fn("agents_integrate", i32, [vp, f32])
+    fn("agents_positions", i32, [vp, _abi.f32p, u32])
     if prefix == "lmb_":
         lib.lmb_abi_version.restype = u32
         lib.lmb_abi_version.argtypes = []
@@ -310,7 +311,7 @@ class NativeBackend(CBackend):
     prefix = "lmb_"
 
     def __init__(self, max_agents: int = 1024, device: int = 0, astar_slots: int = 0,
-                 scratch_bytes: int = 0, flags: int = 0, lib_path: str | None = None):
+                 scratch_bytes: int = 0, flags: int = 0, lib_path: str | None = None, astar_shape: int = 0):
         super().__init__()
         self.lib = load_library(lib_path)
         if self.lib.lmb_abi_version() != _abi.ABI_VERSION:
@@ -322,6 +323,7 @@ class NativeBackend(CBackend):
         cfg.astar_slots = astar_slots
         cfg.scratch_bytes = scratch_bytes
         cfg.flags = flags
+        cfg.astar_shape = astar_shape
         ctx = C.c_void_p()
         st = self.lib.lmb_create(C.byref(cfg), C.byref(ctx))
         if st != 0:
@@ -367,6 +369,11 @@ class NativeBackend(CBackend):
     def agents_integrate(self, dt: float):
         """position += desired_velocity * dt, velocity = desired_velocity, RESET cleared — on the device."""
         self._check(self.lib.lmb_agents_integrate(self.ctx, C.c_float(dt)))
+
+    def resident_positions(self) -> np.ndarray:
+        out = np.zeros((max(self._n_agents, 1), 3), dtype=np.float32)
+        self._check(self.lib.lmb_agents_positions(self.ctx, _abi.ptr(out, _abi.f32p), self._n_agents))
+        return out[:self._n_agents]
 
     def query_timings(self) -> _abi.StepTimings:
         """Timings of the last find_paths / find_straight_paths batch (astar_ms, explored_nodes ...)."""

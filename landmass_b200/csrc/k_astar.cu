@@ -855,7 +855,12 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 // (Measured and rejected: 32 queries per warp; 384 queries per SM with 28 shared-memory entries;
 // 64 / 192 / 384 entries at 192 / 64 / 32 queries per SM; a 4-lanes-per-query variant — lower
 // latency per query but issue-bound, no faster when loaded.)
-uint32_t astar_resident_queries_per_sm(bool big_heap) { return (big_heap ? 2 : 5) * 16 * (AT_THREADS / 32); }
+uint32_t astar_resident_queries_per_sm(bool big_heap, uint32_t shape) {
+  if (!big_heap && shape == 1) return 6 * 16 * (AT_THREADS / 32);
+  if (!big_heap && shape == 2) return 3 * 32 * (AT_THREADS / 32);
+  if (!big_heap && shape == 3) return 4 * 32 * (AT_THREADS / 32);
+  return (big_heap ? 2 : 5) * 16 * (AT_THREADS / 32);
+}
 
 void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                        AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
@@ -863,7 +868,7 @@ void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQu
 
 uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                       AStarCounters* counters, const uint32_t* type_raw, bool big_heap, uint32_t flags,
-                      cudaStream_t stream) {
+                      uint32_t shape, cudaStream_t stream) {
   if (q.n == 0) return 0;
   const bool k4 = arena.kshift == 2;
   const bool simple = nav.n_types == 1 && !q.override_begin;  // the kernel's SIMPLE flag
@@ -897,17 +902,20 @@ uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQue
   if (warp) {
     kind = 2;
     launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, (uint32_t)sm_count, stream);
-  } else if (force_large) {
-    if (big_heap) LMB_ASTAR_LAUNCH(8, 96, 4);
-    else LMB_ASTAR_LAUNCH(16, 40, 5);
-  } else if (q.n <= 8u * (uint32_t)sm_count)
+  } else if (!force_large && q.n <= 8u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(1, 1536, 2);  // few queries: one per warp, the whole open list on chip
-  else if (q.n <= 32u * (uint32_t)sm_count)
+  else if (!force_large && q.n <= 32u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(4, 384, 2);
-  else if (q.n <= 128u * (uint32_t)sm_count)
+  else if (!force_large && q.n <= 128u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(8, 96, 4);
   else if (big_heap)
     LMB_ASTAR_LAUNCH(8, 96, 4);
+  else if (arena.layout == 3 && k4 && shape == 1)
+    LMB_ASTAR_LAUNCH_S(16, 36, 6, 2, 3);  // tuning hooks (lmb_config.astar_shape), forest quad meshes only
+  else if (arena.layout == 3 && k4 && shape == 2)
+    LMB_ASTAR_LAUNCH_S(32, 32, 3, 2, 3);
+  else if (arena.layout == 3 && k4 && shape == 3)
+    LMB_ASTAR_LAUNCH_S(32, 26, 4, 2, 3);
   else
     LMB_ASTAR_LAUNCH(16, 40, 5);
 #undef LMB_ASTAR_LAUNCH

@@ -247,7 +247,7 @@ static size_t arena_budget(const lmb_ctx* ctx) {
 
 // Makes sure the arena can run `n_queries` concurrently (up to the slot limit / byte budget).
 static int32_t ensure_arena(lmb_ctx* ctx, uint32_t n_queries) {
-  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * astar_resident_queries_per_sm(ctx->big_heap);
+  const uint32_t max_slots = ctx->cfg.astar_slots ? ctx->cfg.astar_slots : ctx->sm_count * astar_resident_queries_per_sm(ctx->big_heap, ctx->best_layout == 3 ? ctx->cfg.astar_shape : 0u);
   uint32_t want = std::min<uint32_t>(max_slots, (n_queries + AT_THREADS - 1) / AT_THREADS * AT_THREADS);
   want = std::max<uint32_t>(want, AT_THREADS);
   if (ctx->arena.base && ctx->arena.n_slots >= want) return LMB_OK;
@@ -778,7 +778,8 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     qq.n = n_run;
     qq.list = list;
     ctx->timings.astar_launch_kind |= launch_astar(ctx->nav, *cur, qq, make_pool(ctx), ctx->d_counters.p,
-                                                   ctx->d_type_raw.p, ctx->big_heap, ctx->cfg.flags, s);
+                                                   ctx->d_type_raw.p, ctx->big_heap, ctx->cfg.flags,
+                                                   ctx->best_layout == 3 ? ctx->cfg.astar_shape : 0u, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
@@ -1440,6 +1441,18 @@ int32_t lmb_agents_integrate(lmb_ctx* ctx, float delta_time) {
   launch_integrate(ctx->n_agents, delta_time, ctx->d_out_velocity.p, ctx->d_position.p, ctx->d_velocity.p,
                    ctx->d_flags.p, ctx->stream);
   CUDA_TRY(ctx, cudaGetLastError());
+  return LMB_OK;
+}
+
+int32_t lmb_agents_positions(lmb_ctx* ctx, float* out_position, uint32_t capacity) {
+  if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
+  if (ctx->n_agents > capacity) return ctx->fail(LMB_ERR_CAPACITY, "lmb_agents_positions: %u agents", ctx->n_agents);
+  if (ctx->n_agents == 0) return LMB_OK;
+  if (!out_position) return ctx->fail(LMB_ERR_INVALID_ARGUMENT, "lmb_agents_positions: null output");
+  cudaSetDevice(ctx->device);
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_position, ctx->d_position.p, 3 * (size_t)ctx->n_agents * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return LMB_OK;
 }
 

@@ -15,7 +15,7 @@ void launch_sample_points(const DevNav& nav, const lmb_options& o, uint32_t n, c
 // ---- kernel 2: batched A* (k_astar.cu) ----
 constexpr uint32_t AT_THREADS = 128;  // threads (= concurrent queries) per block, 2 blocks per SM
 constexpr uint32_t AT_HEAP_SM = 48;   // unit of the open-list capacity bookkeeping (heap_cap = AT_HEAP_SM + spill growth)
-constexpr uint32_t AT_HEAP_SM_MIN = 40;  // smallest number of open-list entries any launch shape keeps in shared
+constexpr uint32_t AT_HEAP_SM_MIN = 24;  // smallest number of open-list entries any launch shape keeps in shared
                                          // memory: a slot's spill region holds heap_cap - AT_HEAP_SM_MIN + 2 entries
 
 struct AStarArena {
@@ -90,12 +90,12 @@ struct AStarCounters {  // device-resident
 // 1 = thread-per-query (k_astar.cu), 2 = warp-per-query (k_astar_warp.cu), 0 = nothing.
 uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                       AStarCounters* counters, const uint32_t* type_raw, bool big_heap, uint32_t flags,
-                      cudaStream_t stream);
+                      uint32_t shape, cudaStream_t stream);
 // order[] = query indices 0..n-1 sorted by descending cost hint of their agent slot (bucketed)
 void launch_order_queries(uint32_t n, const uint32_t* q_slot, const uint32_t* slot_cost_hint, uint32_t unknown_hint,
                           uint32_t* order, cudaStream_t stream);
 void launch_build_edge_dist(const EdgeRec* recs, uint32_t n_ids, uint32_t kshift, float* out, cudaStream_t stream);
-uint32_t astar_resident_queries_per_sm(bool big_heap);
+uint32_t astar_resident_queries_per_sm(bool big_heap, uint32_t shape);
 void launch_arena_init(const AStarArena& arena, cudaStream_t stream);
 
 // ---- kernel 3: repath decision + funnel / follow (k_follow.cu) ----

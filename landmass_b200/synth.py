@@ -223,7 +223,8 @@ def default_options(radius: float = 0.5):
     return ArchipelagoOptions.from_agent_radius(radius).to_abi()
 
 
-def tiled_archipelago_flat(k: int, g: int, type_block: int = 16, costs=((0, 1.0), (1, 2.0), (2, 5.0))) -> dict:
+def tiled_archipelago_flat(k: int, g: int, type_block: int = 16, costs=((0, 1.0), (1, 2.0), (2, 5.0)),
+                           cell: float = 1.0) -> dict:
     """BASELINE config 4's world: k x k islands, each a g x g unit-quad grid, tiled by pure translations so that
     borders coincide (boundary links at edge_link_distance 0.01), polygon types (x/type_block + y/type_block) mod 3
     with costs {0: 1, 1: 2, 2: 5}.  Returns the flattened navigation data (island linking done on the host,
@@ -231,11 +232,11 @@ def tiled_archipelago_flat(k: int, g: int, type_block: int = 16, costs=((0, 1.0)
     from .nav_data import Island, NavigationData, Transform
 
     types = ((np.arange(g)[None, :] // type_block + np.arange(g)[:, None] // type_block) % 3)
-    mesh = grid_mesh(g, g, types=types)
+    mesh = grid_mesh(g, g, cell=cell, types=types)
     nd = NavigationData()
     for iy in range(k):
         for ix in range(k):
-            nd.add_island(Island(Transform(translation=(ix * g, iy * g, 0.0), rotation=0.0), mesh))
+            nd.add_island(Island(Transform(translation=(ix * g * cell, iy * g * cell, 0.0), rotation=0.0), mesh))
     for t, c in costs:
         nd.set_type_index_cost(t, c)
     nd.update(0.01, 0.25)
