@@ -29,7 +29,7 @@
 //     leaves the window.
 //
 // One warp runs one query at a time and pulls the next from the batch's queue; 8 or 16 warps per SM
-// (1536 / 768 open-list entries per query in shared memory, in-place spill beyond that).
+// (1472 / 736 open-list entries per query in shared memory, in-place spill beyond that).
 #include "k_astar_common.cuh"
 
 namespace lmb {
@@ -63,39 +63,48 @@ struct WarpHeap {
     lv_m = 31u - __clz(lane_ + 1u);
     lv_o = lane_ + 1u - (1u << lv_m);
   }
+  // SP = false: every index the operation can reach is < HS (the caller checks the length once, uniformly), so
+  // an access is one shared-memory instruction without a branch; SP = true adds the in-place spill.
+  template <bool SP>
   __device__ __forceinline__ uint4 ld(uint32_t i) const {
-    if (i < HS) return sm[i];
+    if (!SP || i < HS) return sm[i];
     return __ldcg(gm + (i - HS + 1));
   }
+  template <bool SP>
   __device__ __forceinline__ void st(uint32_t i, const uint4& v) const {
-    if (i < HS)
+    if (!SP || i < HS)
       sm[i] = v;
     else
       __stcg(gm + (i - HS + 1), v);
   }
 
-  // BinaryHeap::push = sift_up(0, old_len)
-  __device__ __forceinline__ void push(const uint4& e) {
+  // BinaryHeap::push = sift_up(0, old_len).  Lanes that have nothing to do read entry 0 (a valid address)
+  // and are masked out of the ballot: no divergent branch around the loads.
+  template <bool SP>
+  __device__ __forceinline__ void push_t(const uint4& e) {
     const uint32_t p1 = len + 1u;  // 1-based index of the new position; its k-th ancestor is p1 >> k
     len = p1;
     const uint32_t depth = 31u - __clz(p1);
-    uint4 anc = make_uint4(0u, 0u, 0u, 0u);
-    bool stop = false;
-    if (lane < depth) {
-      anc = ld((p1 >> (lane + 1u)) - 1u);
-      stop = rev_le4(e, anc);
-    }
-    const uint32_t mask = __ballot_sync(FULL, stop);
+    const bool has = lane < depth;
+    const uint4 anc = ld<SP>(has ? (p1 >> (lane + 1u)) - 1u : 0u);
+    const uint32_t mask = __ballot_sync(FULL, has & rev_le4(e, anc));
     const uint32_t rise = mask ? (uint32_t)__ffs(mask) - 1u : depth;  // levels the new entry moves up
-    if (lane < rise) st((p1 >> lane) - 1u, anc);
-    if (lane == 0) st((p1 >> rise) - 1u, e);
+    if (lane < rise) st<SP>((p1 >> lane) - 1u, anc);
+    if (lane == 0) st<SP>((p1 >> rise) - 1u, e);
     __syncwarp();
+  }
+  __device__ __forceinline__ void push(const uint4& e) {
+    if (len < HS)
+      push_t<false>(e);
+    else
+      push_t<true>(e);
   }
 
   // BinaryHeap::pop = swap_remove(0) + sift_down_to_bottom(0) + sift_up
-  __device__ __forceinline__ uint4 pop() {
+  template <bool SP>
+  __device__ __forceinline__ uint4 pop_t() {
     len--;
-    const uint4 last = ld(len);
+    const uint4 last = ld<SP>(len);
     if (len == 0) return last;
     const uint4 top = sm[0];
     const uint32_t end = len;
@@ -103,12 +112,10 @@ struct WarpHeap {
     while (2u * pos + 2u < end) {  // `pos` has two children
       // winner bits of the five levels below `pos`: lane l < 31 owns the node with local heap index l
       const uint32_t g = ((pos + 1u) << lv_m) + lv_o - 1u;
-      bool bit = false;
-      if (lane < 31u && 2u * g + 2u < end) {
-        const uint4 a = ld(2u * g + 1u), b = ld(2u * g + 2u);
-        bit = rev_le4(a, b);  // child += (a <= b): the right child wins
-      }
-      const uint32_t bits = __ballot_sync(FULL, bit);
+      const bool two = (lane < 31u) & (2u * g + 2u < end);
+      const uint32_t ia = two ? 2u * g + 1u : 0u;
+      const uint4 a = ld<SP>(ia), b = ld<SP>(ia + 1u);
+      const uint32_t bits = __ballot_sync(FULL, two & rev_le4(a, b));  // child += (a <= b): the right child wins
       uint32_t t = 0;
 #pragma unroll
       for (int lv = 0; lv < 5; lv++) {
@@ -128,21 +135,89 @@ struct WarpHeap {
     }
     // Entry of level k moves to level k-1 (lane k); the hole element (the old last entry) goes to the
     // bottom and sifts up: it stops below the first entry, scanning upward, that it is <= to.
-    uint4 mine = make_uint4(0u, 0u, 0u, 0u);
-    bool stop = false;
-    if (lane >= 1u && lane <= d) {
-      mine = ld(my_pos);
-      stop = rev_le4(last, mine);
-    }
-    const uint32_t mask = __ballot_sync(FULL, stop);
+    const bool on_path = (lane >= 1u) & (lane <= d);
+    const uint4 mine = ld<SP>(on_path ? my_pos : 0u);
+    const uint32_t mask = __ballot_sync(FULL, on_path & rev_le4(last, mine));
     const uint32_t j = mask ? 31u - __clz(mask) : 0u;
     const uint32_t pos_j = __shfl_sync(FULL, my_pos, j);
-    if (lane >= 1u && lane <= j) st((my_pos - 1u) >> 1, mine);
-    if (lane == 0) st(pos_j, last);
+    if (lane >= 1u && lane <= j) st<SP>((my_pos - 1u) >> 1, mine);
+    if (lane == 0) st<SP>(pos_j, last);
     __syncwarp();
     return top;
   }
+  __device__ __forceinline__ uint4 pop() {
+    if (len <= HS) return pop_t<false>();
+    return pop_t<true>();
+  }
 };
+
+// ---- asynchronous staging of an expansion's first loads ------------------------------------------------
+// The records of the popped polygon, its row of the distance table and best[root] are wanted AFTER the pop,
+// and the pop's ~300 cycles of shared-memory work are there to hide their L2 round trip.  Loaded into
+// registers they do not overlap it: ptxas gives the pop's first LDS the scoreboard of the outstanding LDGs,
+// and the first instruction of the pop then waits the whole round trip (ncu: 25 % of all stall samples on
+// that one instruction).  cp.async has no destination register and no scoreboard: global -> shared memory,
+// completion by cp.async.wait_group behind the pop.
+struct __align__(16) LaneStage {  // per lane
+  uint4 a;        // EdgeRec {mx, my, mz, twin}
+  uint32_t info;  // EdgeRec::info
+  float dist;     // edge_dist[s][lane]
+  uint32_t pad[2];
+};
+struct __align__(16) WarpStage {  // per warp
+  LaneStage lane[32];
+  uint4 root;  // best[root] probe: layout-specific words
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// best[root] probe through the staging slot: issue (one lane) and read back (all lanes, after the wait)
+template <int LAYOUT>
+__device__ __forceinline__ void stage_root_probe(const BestStore<LAYOUT>&, uint32_t, uint4*) {}
+template <>
+__device__ __forceinline__ void stage_root_probe<0>(const BestStore<0>& bs, uint32_t st, uint4* slot) {
+  cp_async_4(slot, bs.b + st);
+}
+template <>
+__device__ __forceinline__ void stage_root_probe<1>(const BestStore<1>& bs, uint32_t st, uint4* slot) {
+  if (st < bs.n_ids)
+    cp_async_8(slot, bs.bp + (st >> bs.kshift));
+  else
+    cp_async_4(reinterpret_cast<uint32_t*>(slot) + 2, bs.sp + (st - bs.n_ids));
+}
+template <>
+__device__ __forceinline__ void stage_root_probe<2>(const BestStore<2>& bs, uint32_t st, uint4* slot) {
+  cp_async_8(slot, bs.tab + (bs.home(st) & bs.mask));
+}
+template <int LAYOUT>
+__device__ __forceinline__ float staged_root_value(const BestStore<LAYOUT>&, uint32_t, const uint4&) {
+  return __builtin_huge_valf();
+}
+template <>
+__device__ __forceinline__ float staged_root_value<0>(const BestStore<0>&, uint32_t, const uint4& v) {
+  return __uint_as_float(v.x);
+}
+template <>
+__device__ __forceinline__ float staged_root_value<1>(const BestStore<1>& bs, uint32_t st, const uint4& v) {
+  if (st >= bs.n_ids) return __uint_as_float(v.z);
+  return bs.value_edge(st, make_uint2(v.x, v.y));
+}
+template <>
+__device__ __forceinline__ float staged_root_value<2>(const BestStore<2>& bs, uint32_t st, const uint4& v) {
+  return bs.value(st, make_uint2(v.x, v.y));
+}
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
@@ -179,12 +254,12 @@ __device__ __forceinline__ bool needs_chain<2>(const BestStore<2>&, uint32_t st,
 
 }  // namespace
 
-template <uint32_t HS, uint32_t BPS, int LAYOUT>
+template <uint32_t HS, uint32_t BPS, int LAYOUT, bool SIMPLE>
 __global__ void __launch_bounds__(AT_THREADS, BPS)
 k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
-             const uint32_t* __restrict__ type_raw, uint32_t simple_u) {
+             const uint32_t* __restrict__ type_raw) {
   constexpr uint32_t WPB = AT_THREADS / 32;
-  extern __shared__ uint4 s_heap[];  // [WPB][HS]
+  extern __shared__ uint4 s_heap[];  // [WPB][HS] open lists, then [WPB] WarpStage
   __shared__ float s_cost[LMB_MAX_TYPES];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   for (uint32_t t = threadIdx.x; t < nav.n_types; t += AT_THREADS) s_cost[t] = nav.type_cost[t];
@@ -193,7 +268,6 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
   if (slot >= arena.n_slots) return;
 
   typedef typename BestStore<LAYOUT>::Raw BestRaw;
-  typedef typename BestStore<LAYOUT>::RootRaw BestRootRaw;
   uint8_t* const slot_base = arena.base + (size_t)slot * arena.slot_stride;
   BestStore<LAYOUT> bs;
   bs.init(slot_base, arena);
@@ -204,12 +278,14 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
                   : (LAYOUT == 1 ? (arena.n_ids >> arena.kshift) : (LAYOUT == 2 ? arena.hash_cap : arena.n_states / 2));
   WarpHeap<HS> heap;
   heap.init(s_heap + (size_t)warp * HS, reinterpret_cast<uint4*>(slot_base + arena.heap_offset), lane);
+  WarpStage* const stage_w = reinterpret_cast<WarpStage*>(s_heap + (size_t)WPB * HS) + warp;
+  LaneStage* const stage_l = stage_w->lane + lane;
 
   const EdgeRec* __restrict__ recs = nav.edges;
   const uint32_t heap_cap = arena.heap_cap, node_cap = arena.node_cap;
   const uint32_t node_cap_window = (node_cap + 31u) & ~31u;  // the node list is allocated in 256-byte units
   const uint32_t kshift = arena.kshift, kmask = (1u << kshift) - 1u;
-  const bool simple = simple_u != 0;
+  constexpr bool simple = SIMPLE;  // one polygon type, no per-query overrides: every type cost is cost0
   const float cost0 = s_cost[0];
   const uint32_t ST_LINK0 = arena.n_ids;
   const uint32_t ST_START = arena.n_ids + nav.n_links;
@@ -228,7 +304,7 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
     const V3 end_point{q.end_point[3 * (size_t)qid], q.end_point[3 * (size_t)qid + 1], q.end_point[3 * (size_t)qid + 2]};
     const uint32_t owner = q.owner ? q.owner[qid] : qid;
     uint32_t ov_begin = 0, ov_end = 0;
-    if (!simple && q.override_begin) {
+    if (!SIMPLE && q.override_begin) {
       ov_begin = q.override_begin[owner];
       ov_end = q.override_begin[owner + 1];
     }
@@ -337,7 +413,6 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
     while (status == 1 && heap.len != 0) {
       // ---- peek the root, issue this expansion's loads, then pop ----
       const uint32_t s = heap.sm[0].w;
-      const BestRootRaw raw_s = bs.probe_root(s);
       const bool is_edge = s < ST_LINK0;
       const bool preloaded = is_edge && kshift != 0;
       EdgeRec r;
@@ -346,20 +421,33 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
       EdgeRec self = r;
       float dtab = 0.0f;
       uint32_t first = 0, cnt = 0;
+      __syncwarp();  // nobody still reads the previous expansion's staging slots
+      if (LAYOUT != 3 && lane == 0) stage_root_probe<LAYOUT>(bs, s, &stage_w->root);
       if (is_edge) {
         if (kshift) {
           first = s & ~kmask;
           cnt = kmask + 1u;
-          if (lane < cnt) {
-            r = ld_rec(recs + first + lane);
-            dtab = __ldg(nav.edge_dist + ((size_t)s << kshift) + lane);
-          }
+          // lanes beyond the polygon's records copy its last one again (same line: no traffic) and drop out at
+          // the `e < cnt` test: no divergent branch around the copies
+          const uint32_t le = lane < cnt ? lane : cnt - 1u;
+          const EdgeRec* rp = recs + first + le;
+          cp_async_16(&stage_l->a, rp);
+          cp_async_4(&stage_l->info, &rp->info);
+          cp_async_4(&stage_l->dist, nav.edge_dist + ((size_t)s << kshift) + le);
         } else {
           self = ld_rec(recs + s);
         }
       }
       const uint4 cur = heap.pop();
       const float cur_cost = __uint_as_float(cur.x), cur_est = __uint_as_float(cur.y);
+      cp_async_wait_all();
+      __syncwarp();  // lanes read each other's slots below (lane 0's info, the state's own midpoint, the root probe)
+      if (preloaded) {
+        const uint4 a = stage_l->a;
+        r.mx = __uint_as_float(a.x), r.my = __uint_as_float(a.y), r.mz = __uint_as_float(a.z), r.twin = a.w;
+        r.info = stage_l->info;
+        dtab = stage_l->dist;
+      }
 
       // ---- resolve (node, point, ignored step) — pathfinding.rs:93-143 ----
       uint32_t poly = 0, cur_type = 0, has_links = 0;
@@ -369,10 +457,12 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
         if (kshift) {
           const uint32_t own = s & kmask;
           poly = s >> kshift;
-          const uint32_t info0 = __shfl_sync(FULL, r.info, 0);
+          const uint32_t info0 = stage_w->lane[0].info;
           cur_type = (info0 >> 8) & 0xffu;
           has_links = (info0 >> 24) & 1u;
-          point = {__shfl_sync(FULL, r.mx, own), __shfl_sync(FULL, r.my, own), __shfl_sync(FULL, r.mz, own)};
+          // the state's own midpoint: only the rare branches below (GoToEnd, off-mesh links) use it
+          const uint4 oa = stage_w->lane[own].a;
+          point = {__uint_as_float(oa.x), __uint_as_float(oa.y), __uint_as_float(oa.z)};
         } else {
           first = self.first_edge;
           cnt = self.info & 0xffu;
@@ -409,7 +499,7 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
         has_links = nav.node_link_begin[poly + 1] > nav.node_link_begin[poly];
       }
       // stale (astar.rs:172-176)
-      if (bs.root_value(s, raw_s) < cur_est) continue;
+      if (LAYOUT != 3 && staged_root_value<LAYOUT>(bs, s, stage_w->root) < cur_est) continue;
       explored++;
       if (s == ST_END) {  // goal (astar.rs:179-184)
         goal_index = cur.z;
@@ -619,17 +709,17 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
   }
 }
 
-template <uint32_t HS, uint32_t BPS, int LAYOUT>
+template <uint32_t HS, uint32_t BPS, int LAYOUT, bool SIMPLE>
 static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                          AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
+                          AStarCounters* counters, const uint32_t* type_raw, uint32_t sm_count,
                           cudaStream_t stream) {
   static_assert(HS >= AT_HEAP_SM_MIN, "a slot's open-list spill is sized for HS >= AT_HEAP_SM_MIN (arena_layout)");
   constexpr uint32_t WPB = AT_THREADS / 32;
-  const size_t smem = (size_t)HS * WPB * sizeof(uint4);
+  const size_t smem = (size_t)HS * WPB * sizeof(uint4) + WPB * sizeof(WarpStage);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT, SIMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
@@ -638,25 +728,31 @@ static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const ASta
   if (slots > resident) slots = resident;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar_warp<HS, BPS, LAYOUT><<<(slots + WPB - 1) / WPB, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters, type_raw,
-                                                                                  simple ? 1u : 0u);
+  k_astar_warp<HS, BPS, LAYOUT, SIMPLE><<<(slots + WPB - 1) / WPB, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters,
+                                                                                          type_raw);
 }
 
 void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                        AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
                        cudaStream_t stream) {
-  // up to 8 queries per SM: 1536 open-list entries each in shared memory; more: 16 warps per SM with 768
+  // up to 8 queries per SM: 1472 open-list entries each in shared memory; more: 16 warps per SM with 736
   const bool wide = q.n > 8u * sm_count && arena.n_slots > 8u * sm_count;
-#define LMB_WARP_LAUNCH(L)                                                                                  \
-  do {                                                                                                      \
-    if (wide) launch_warp_t<768, 4, L>(nav, arena, q, pool, counters, type_raw, simple, sm_count, stream);   \
-    else launch_warp_t<1536, 2, L>(nav, arena, q, pool, counters, type_raw, simple, sm_count, stream);       \
+#define LMB_WARP_LAUNCH_S(HS, BPS, L)                                                                   \
+  do {                                                                                                  \
+    if (simple) launch_warp_t<HS, BPS, L, true>(nav, arena, q, pool, counters, type_raw, sm_count, stream);  \
+    else launch_warp_t<HS, BPS, L, false>(nav, arena, q, pool, counters, type_raw, sm_count, stream);        \
+  } while (0)
+#define LMB_WARP_LAUNCH(L)                 \
+  do {                                     \
+    if (wide) LMB_WARP_LAUNCH_S(736, 4, L); \
+    else LMB_WARP_LAUNCH_S(1472, 2, L);     \
   } while (0)
   if (arena.layout == 1) LMB_WARP_LAUNCH(1);
   else if (arena.layout == 2) LMB_WARP_LAUNCH(2);
   else if (arena.layout == 3) LMB_WARP_LAUNCH(3);
   else LMB_WARP_LAUNCH(0);
 #undef LMB_WARP_LAUNCH
+#undef LMB_WARP_LAUNCH_S
 }
 
 }  // namespace lmb

@@ -19,6 +19,8 @@
 // oracle/avoidance_oracle.cpp op for op (RVO2 restatement); see that file's header.
 //
 // One thread per agent; per-agent variable-length state lives in a global scratch block.
+#include <type_traits>
+
 #include "lmb_device.cuh"
 #include "lmb_kernels.h"
 
@@ -40,44 +42,64 @@ struct Line {
   V2 point, direction;
 };
 
+// Per-agent variable-length arrays, INTERLEAVED by agent: element i of the agent with chunk-local index t lives
+// at base[i * stride + t] (stride = agents per chunk, a multiple of 32).  The threads of a warp walk their
+// arrays in near lock-step, so element i of 32 neighbouring agents is one contiguous run instead of 32 sectors
+// several KB apart (one private block per agent, as before, made every access its own 32-byte sector).
+template <class T>
+struct Strided {
+  T* p;
+  uint32_t stride;
+  __device__ __forceinline__ T& operator[](uint32_t i) const { return p[(size_t)i * stride]; }
+  __device__ __forceinline__ explicit operator bool() const { return p != nullptr; }
+};
+
 struct Scratch {
-  float2* nb;         // (d2, index bits)
-  uint2* heap;        // (node, score bits)
-  uint32_t* explored;
-  float4* vis;        // line a.xy, b.xy (relative to the agent, oriented CCW)
-  uint2* border;      // (left vertex id, right vertex id) per line
-  Cone* cones[2];
-  float2* new_verts;
-  LoopNode* lnodes;
-  uint2* loops;       // (head, tail); LMB_NONE head = removed
-  uint2* finished;
-  Line* lines;
-  Line* proj;
+  Strided<float2> nb;         // (d2, index bits)
+  Strided<uint2> heap;        // (node, score bits)
+  Strided<uint32_t> explored;
+  Strided<float4> vis;        // line a.xy, b.xy (relative to the agent, oriented CCW)
+  Strided<uint2> border;      // (left vertex id, right vertex id) per line
+  Strided<Cone> cones[2];
+  Strided<float2> new_verts;
+  Strided<LoopNode> lnodes;
+  Strided<uint2> loops;       // (head, tail); LMB_NONE head = removed
+  Strided<uint2> finished;
+  Strided<Line> lines;
+  Strided<Line> proj;
   uint32_t max_nb, max_explore, max_border, max_cones, max_lines, max_loops;
 };
 
 __device__ __forceinline__ Scratch carve(const AvoidScratch& s, uint32_t t) {
   Scratch r;
-  uint8_t* p = s.base + (size_t)t * s.per_agent_bytes;
+  uint8_t* p = s.base;
+  const uint32_t stride = s.agent_stride;
   r.max_nb = s.max_neighbours;
   r.max_explore = s.max_explore;
   r.max_border = s.max_border_edges;
   r.max_cones = s.max_cones;
   r.max_lines = s.max_lines;
   r.max_loops = s.max_border_edges;
-  r.nb = (float2*)p;                 p += (size_t)r.max_nb * 8;
-  r.heap = (uint2*)p;                p += (size_t)r.max_explore * 8;
-  r.explored = (uint32_t*)p;         p += (size_t)r.max_explore * 4 * 2;
-  r.vis = (float4*)p;                p += (size_t)r.max_border * 16;
-  r.border = (uint2*)p;              p += (size_t)r.max_border * 8;
-  r.cones[0] = (Cone*)p;             p += (size_t)r.max_cones * 12;
-  r.cones[1] = (Cone*)p;             p += (size_t)r.max_cones * 12;
-  r.new_verts = (float2*)p;          p += (size_t)r.max_border * 8;
-  r.lnodes = (LoopNode*)p;           p += (size_t)r.max_border * 2 * 12;
-  r.loops = (uint2*)p;               p += (size_t)r.max_loops * 8;
-  r.finished = (uint2*)p;            p += (size_t)r.max_loops * 8;
-  r.lines = (Line*)p;                p += (size_t)r.max_lines * 16;
-  r.proj = (Line*)p;
+  auto take = [&](auto& arr, size_t count) {
+    typedef typename std::remove_reference<decltype(arr[0])>::type T;
+    arr.p = reinterpret_cast<T*>(p) + t;
+    arr.stride = stride;
+    p += count * stride * sizeof(T);  // every element size divides 16 or is 12: regions stay 4-byte aligned,
+                                      // and 16-byte ones 16-byte aligned because stride is a multiple of 32
+  };
+  take(r.vis, r.max_border);          // 16-byte element types first (alignment)
+  take(r.lines, r.max_lines);
+  take(r.proj, r.max_lines);
+  take(r.nb, r.max_nb);
+  take(r.heap, r.max_explore);
+  take(r.border, r.max_border);
+  take(r.new_verts, r.max_border);
+  take(r.loops, r.max_loops);
+  take(r.finished, r.max_loops);
+  take(r.explored, (size_t)r.max_explore * 2);
+  take(r.cones[0], r.max_cones);
+  take(r.cones[1], r.max_cones);
+  take(r.lnodes, (size_t)r.max_border * 2);
   return r;
 }
 
@@ -112,8 +134,8 @@ struct VisSet {
 // Tests (add_id < 0) or inserts the span [lo,hi] of line (a,b).  When inserting, the new
 // cone list is streamed into the other buffer and *n_out is its length.
 __device__ bool vis_process_piece(VisSet& vs, V2 a, V2 b, float lo, float hi, int add_id, uint32_t* n_out) {
-  const Cone* cones = vs.s->cones[vs.cur];
-  Cone* out = add_id >= 0 ? vs.s->cones[1 - vs.cur] : nullptr;
+  const Strided<Cone> cones = vs.s->cones[vs.cur];
+  const Strided<Cone> out = add_id >= 0 ? vs.s->cones[1 - vs.cur] : Strided<Cone>{nullptr, 0u};
   uint32_t no = 0;
   bool visible = false;
   float cur = lo;
@@ -229,7 +251,7 @@ __device__ bool vis_process(VisSet& vs, V2 a, V2 b, bool add, uint32_t* out_id) 
 // std BinaryHeap<ExploreNode> (avoidance.rs:200-226): a <= b  <=>  b.score <= a.score
 // ---------------------------------------------------------------------------
 struct ExploreHeap {
-  uint2* data;
+  Strided<uint2> data;
   uint32_t len;
   __device__ __forceinline__ static bool le(uint2 a, uint2 b) {
     return __uint_as_float(b.y) <= __uint_as_float(a.y);
@@ -380,7 +402,7 @@ __device__ ObVertex make_ob_vertex(const ObstacleView& ob, uint32_t node, bool i
 }
 
 __device__ void lines_for_obstacle(const DodgyAgent& self, const ObstacleView& ob, float margin,
-                                   float time_horizon, Line* lines, uint32_t& n_lines, uint32_t max_lines,
+                                   float time_horizon, Strided<Line> lines, uint32_t& n_lines, uint32_t max_lines,
                                    bool& overflow) {
   if (ob.n < 2) return;
   const Scratch& s = *ob.s;
@@ -524,7 +546,7 @@ __device__ void lines_for_obstacle(const DodgyAgent& self, const ObstacleView& o
   }
 }
 
-__device__ bool linear_program_1(const Line* lines, uint32_t line_no, float radius, V2 opt_velocity,
+__device__ bool linear_program_1(Strided<Line> lines, uint32_t line_no, float radius, V2 opt_velocity,
                                  bool direction_opt, V2& result) {
   const Line ln = lines[line_no];
   float dot_product = dot(ln.point, ln.direction);
@@ -565,7 +587,7 @@ __device__ bool linear_program_1(const Line* lines, uint32_t line_no, float radi
   return true;
 }
 
-__device__ uint32_t linear_program_2(const Line* lines, uint32_t n, float radius, V2 opt_velocity,
+__device__ uint32_t linear_program_2(Strided<Line> lines, uint32_t n, float radius, V2 opt_velocity,
                                      bool direction_opt, V2& result) {
   if (direction_opt) {
     result = opt_velocity * radius;
@@ -589,8 +611,8 @@ __device__ uint32_t linear_program_2(const Line* lines, uint32_t n, float radius
 
 // Returns the size of the last projected constraint set left in `proj` (the fallback constraints
 // the debug-avoidance export reports, debug.rs:470-481).
-__device__ uint32_t linear_program_3(const Line* lines, uint32_t n, uint32_t num_obst_lines, uint32_t begin_line,
-                                     float radius, V2& result, Line* proj) {
+__device__ uint32_t linear_program_3(Strided<Line> lines, uint32_t n, uint32_t num_obst_lines, uint32_t begin_line,
+                                     float radius, V2& result, Strided<Line> proj) {
   float distance_ = 0.0f;
   uint32_t last_np = 0;
   for (uint32_t i = begin_line; i < n; i++) {
@@ -873,7 +895,7 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
   // ---- stitch visible lines into loops (avoidance.rs:389-439), ascending line id ----
   uint32_t n_loops = 0, n_finished = 0, n_lnodes = 0;
   if (!overflow) {
-    const Cone* cones = s.cones[vs.cur];
+    const Strided<Cone> cones = s.cones[vs.cur];
     for (uint32_t line_id = 0; line_id < vs.n_lines; line_id++) {
       bool vis = false;
       for (uint32_t c = 0; c < vs.n_cones; c++)
@@ -940,7 +962,7 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
   uint32_t n_lines = 0;
   if (!overflow) {
     for (uint32_t pass = 0; pass < 2; pass++) {
-      const uint2* list = pass == 0 ? s.finished : s.loops;
+      const Strided<uint2> list = pass == 0 ? s.finished : s.loops;
       const uint32_t cnt = pass == 0 ? n_finished : n_loops;
       for (uint32_t k = 0; k < cnt; k++) {
         ObstacleView ob;
@@ -1012,9 +1034,11 @@ __global__ void k_stage_moves(AgentArrays ag, AgentPersist persist, float* stage
   uint32_t s = ag.slot[i];
   for (int k = 0; k < 3; k++) staged[3 * (size_t)i + k] = persist.desired_move[3 * (size_t)s + k];
 }
-__global__ void k_commit_moves(AgentArrays ag, AgentPersist persist, const float* staged) {
+// (skipped when some agent's scratch overflowed: the host then re-runs the phase with larger capacities and
+// nothing of the aborted attempt may have been published)
+__global__ void k_commit_moves(AgentArrays ag, AgentPersist persist, const float* staged, const uint32_t* overflow) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ag.n) return;
+  if (i >= ag.n || *overflow) return;
   uint32_t s = ag.slot[i];
   for (int k = 0; k < 3; k++) persist.desired_move[3 * (size_t)s + k] = staged[3 * (size_t)i + k];
 }
@@ -1066,8 +1090,8 @@ void launch_stage_moves(const AgentArrays& ag, const AgentPersist& persist, floa
   if (ag.n) k_stage_moves<<<blocks_for(ag.n, 256), 256, 0, stream>>>(ag, persist, staged);
 }
 void launch_commit_moves(const AgentArrays& ag, const AgentPersist& persist, const float* staged,
-                         cudaStream_t stream) {
-  if (ag.n) k_commit_moves<<<blocks_for(ag.n, 256), 256, 0, stream>>>(ag, persist, staged);
+                         const uint32_t* overflow, cudaStream_t stream) {
+  if (ag.n) k_commit_moves<<<blocks_for(ag.n, 256), 256, 0, stream>>>(ag, persist, staged, overflow);
 }
 
 void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_options& o, float delta_time,

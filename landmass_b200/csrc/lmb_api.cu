@@ -1396,19 +1396,26 @@ int32_t lmb_step_end(lmb_ctx* ctx, const lmb_options* o, float dt) {
   int32_t st;
   cudaEventRecord(ctx->ev[9], s);
   // phase D, second half: grid over ALL records, ORCA for this rank's agents
-  if (!(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE)) {
-    NvtxRange r("lmb:phaseD avoidance");
-    st = lmb_avoidance_solve(ctx, o, dt, ctx->halo_total, ctx->halo_first);
-    if (st != LMB_OK) return st;
+  const bool avoid = !(ctx->cfg.flags & LMB_CONFIG_NO_AVOIDANCE) && n > 0;
+  ctx->h_small[8] = 0;
+  for (int attempt = 0;; attempt++) {
+    if (avoid) {
+      NvtxRange r("lmb:phaseD avoidance");
+      st = lmb_avoidance_solve(ctx, o, dt, ctx->halo_total, ctx->halo_first);
+      if (st != LMB_OK) return st;
+    }
+    cudaEventRecord(ctx->ev[7], s);
+    launch_gather_outputs(ag, persist, ctx->d_out_velocity.p, ctx->d_out_state.p, ctx->d_out_link_id.p,
+                          ctx->d_out_link_start.p, ctx->d_out_link_end.p, s);
+    T.kernel_launches += n ? 1 : 0;
+    CUDA_TRY(ctx, cudaGetLastError());
+    cudaEventRecord(ctx->ev[8], s);
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the step's one synchronisation behind the A* phase
+    if (!avoid || ctx->h_small[8] == 0) break;
+    // some agent's avoidance scratch was too small: nothing was committed; grow for good and redo phase D
+    if (attempt >= 7) return ctx->fail(LMB_ERR_CAPACITY, "avoidance scratch kept overflowing");
+    for (int k = 0; k < 5; k++) ctx->avoid_caps[k] *= 2;
   }
-  cudaEventRecord(ctx->ev[7], s);
-
-  launch_gather_outputs(ag, persist, ctx->d_out_velocity.p, ctx->d_out_state.p, ctx->d_out_link_id.p,
-                        ctx->d_out_link_start.p, ctx->d_out_link_end.p, s);
-  T.kernel_launches += n ? 1 : 0;
-  CUDA_TRY(ctx, cudaGetLastError());
-  cudaEventRecord(ctx->ev[8], s);
-  CUDA_TRY(ctx, cudaStreamSynchronize(s));
   cudaEventElapsedTime(&T.sample_ms, ctx->ev[2], ctx->ev[3]);
   cudaEventElapsedTime(&T.repath_decide_ms, ctx->ev[3], ctx->ev[4]);
   cudaEventElapsedTime(&T.astar_ms, ctx->ev[4], ctx->ev[5]);

@@ -12,7 +12,7 @@ void launch_avoid_grid(uint32_t n_records, const AvoidRecord* records, AvoidGrid
                        cudaStream_t stream);
 void launch_stage_moves(const AgentArrays& ag, const AgentPersist& persist, float* staged, cudaStream_t stream);
 void launch_commit_moves(const AgentArrays& ag, const AgentPersist& persist, const float* staged,
-                         cudaStream_t stream);
+                         const uint32_t* overflow, cudaStream_t stream);
 void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_options& o, float delta_time,
                             uint32_t first_agent_global, uint32_t chunk_begin, uint32_t chunk_n,
                             uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
@@ -40,7 +40,10 @@ int32_t lmb_avoidance_build_records(lmb_ctx* ctx, const lmb_options* o, uint32_t
   return LMB_OK;
 }
 
-// Runs avoidance for this rank's agents against all n_total records.
+// Enqueues avoidance for this rank's agents against all n_total records: grid, per-agent solve into a staging
+// buffer, commit.  No host synchronisation: if some agent's scratch overflows, the device-side flag keeps the
+// commit kernel from publishing anything and the caller (lmb_step_end) sees the flag at its own final sync,
+// grows the capacities and calls this again — the capacities stick, so a steady state never retries.
 int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32_t n_total, uint32_t first) {
   cudaStream_t s = ctx->stream;
   const uint32_t n = ctx->n_agents;
@@ -77,7 +80,7 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
   CUDA_TRY(ctx, ctx->d_out_velocity.reserve(3 * (size_t)n));
   float* staged = ctx->d_out_velocity.p;  // reused as the staging buffer; gather overwrites it later
 
-  for (int attempt = 0; attempt < 8; attempt++) {
+  {
     AvoidScratch sc{};
     sc.max_neighbours = ctx->avoid_caps[0];
     sc.max_explore = ctx->avoid_caps[1];
@@ -86,7 +89,8 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
     sc.max_lines = ctx->avoid_caps[4];
     sc.per_agent_bytes = avoid_scratch_bytes_per_agent(sc);
     const uint32_t chunk = std::min<uint32_t>(n, 131072u);
-    CUDA_TRY(ctx, ctx->d_avoid_scratch.reserve(sc.per_agent_bytes * (size_t)chunk));
+    sc.agent_stride = (chunk + 31u) & ~31u;
+    CUDA_TRY(ctx, ctx->d_avoid_scratch.reserve(sc.per_agent_bytes * (size_t)sc.agent_stride));
     sc.base = ctx->d_avoid_scratch.p;
     sc.overflow = ctx->d_avoid_overflow.p;
     CUDA_TRY(ctx, cudaMemsetAsync(sc.overflow, 0, sizeof(uint32_t), s));
@@ -109,17 +113,11 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
                              ctx->n_chars, ctx->d_char_records.p, grid, sc, max_radius_bits, staged, dbg, s);
       ctx->timings.kernel_launches += 1;
     }
+    launch_commit_moves(ag, persist, staged, sc.overflow, s);
+    ctx->timings.kernel_launches += 2;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_small + 8, sc.overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    if (ctx->h_small[8] == 0) {
-      launch_commit_moves(ag, persist, staged, s);
-      ctx->timings.kernel_launches += 2;
-      CUDA_TRY(ctx, cudaGetLastError());
-      return LMB_OK;
-    }
-    for (int k = 0; k < 5; k++) ctx->avoid_caps[k] *= 2;  // scratch too small for some agent: grow, redo
   }
-  return ctx->fail(LMB_ERR_CAPACITY, "avoidance scratch kept overflowing");
+  return LMB_OK;
 }
 

@@ -199,6 +199,7 @@ struct AvoidScratch {
   // per-agent variable-length scratch, sized by `per_agent_*`
   uint8_t* base;
   size_t per_agent_bytes;
+  uint32_t agent_stride;  // agents per chunk rounded up to 32: the arrays are interleaved by agent (k_avoid.cu)
   uint32_t max_neighbours;
   uint32_t max_lines;
   uint32_t max_cones;
