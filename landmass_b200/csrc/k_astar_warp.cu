@@ -28,8 +28,10 @@
 //     nodes per lane, moved by shuffles); a dependent memory round trip is paid only when the chain
 //     leaves the window.
 //
-// One warp runs one query at a time and pulls the next from the batch's queue; 8 or 16 warps per SM
-// (1472 / 736 open-list entries per query in shared memory, in-place spill beyond that).
+// One warp runs one query at a time and pulls the next from the batch's queue; 1, 4, 8 or 16 warps per SM
+// with 13 824 / 3 456 / 1 472 / 736 open-list entries per query in shared memory (in-place spill beyond that).
+#include <algorithm>
+
 #include "k_astar_common.cuh"
 
 namespace lmb {
@@ -254,15 +256,14 @@ __device__ __forceinline__ bool needs_chain<2>(const BestStore<2>&, uint32_t st,
 
 }  // namespace
 
-template <uint32_t HS, uint32_t BPS, int LAYOUT, bool SIMPLE>
-__global__ void __launch_bounds__(AT_THREADS, BPS)
+template <uint32_t HS, uint32_t WPB, uint32_t BPS, int LAYOUT, bool SIMPLE>
+__global__ void __launch_bounds__(WPB * 32, BPS)
 k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
              const uint32_t* __restrict__ type_raw) {
-  constexpr uint32_t WPB = AT_THREADS / 32;
   extern __shared__ uint4 s_heap[];  // [WPB][HS] open lists, then [WPB] WarpStage
   __shared__ float s_cost[LMB_MAX_TYPES];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t t = threadIdx.x; t < nav.n_types; t += AT_THREADS) s_cost[t] = nav.type_cost[t];
+  for (uint32_t t = threadIdx.x; t < nav.n_types; t += WPB * 32) s_cost[t] = nav.type_cost[t];
   __syncthreads();
   const uint32_t slot = blockIdx.x * WPB + warp;
   if (slot >= arena.n_slots) return;
@@ -709,17 +710,16 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
   }
 }
 
-template <uint32_t HS, uint32_t BPS, int LAYOUT, bool SIMPLE>
+template <uint32_t HS, uint32_t WPB, uint32_t BPS, int LAYOUT, bool SIMPLE>
 static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                           AStarCounters* counters, const uint32_t* type_raw, uint32_t sm_count,
                           cudaStream_t stream) {
   static_assert(HS >= AT_HEAP_SM_MIN, "a slot's open-list spill is sized for HS >= AT_HEAP_SM_MIN (arena_layout)");
-  constexpr uint32_t WPB = AT_THREADS / 32;
   const size_t smem = (size_t)HS * WPB * sizeof(uint4) + WPB * sizeof(WarpStage);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar_warp<HS, BPS, LAYOUT, SIMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
@@ -728,24 +728,27 @@ static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const ASta
   if (slots > resident) slots = resident;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar_warp<HS, BPS, LAYOUT, SIMPLE><<<(slots + WPB - 1) / WPB, AT_THREADS, smem, stream>>>(nav, a, q, pool, counters,
+  k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE><<<(slots + WPB - 1) / WPB, WPB * 32, smem, stream>>>(nav, a, q, pool, counters,
                                                                                           type_raw);
 }
 
 void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                        AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
                        cudaStream_t stream) {
-  // up to 8 queries per SM: 1472 open-list entries each in shared memory; more: 16 warps per SM with 736
-  const bool wide = q.n > 8u * sm_count && arena.n_slots > 8u * sm_count;
-#define LMB_WARP_LAUNCH_S(HS, BPS, L)                                                                   \
-  do {                                                                                                  \
-    if (simple) launch_warp_t<HS, BPS, L, true>(nav, arena, q, pool, counters, type_raw, sm_count, stream);  \
-    else launch_warp_t<HS, BPS, L, false>(nav, arena, q, pool, counters, type_raw, sm_count, stream);        \
+  // The fewer queries, the more of the 227 KB of shared memory each open list gets (a spilled level costs an L2
+  // round trip per pop): one query per SM -> 13 824 entries on chip; 4 per SM -> 3 456; 8 -> 1 472; 16 -> 736.
+  const uint32_t per_sm = (std::min(q.n, arena.n_slots) + sm_count - 1) / sm_count;
+#define LMB_WARP_LAUNCH_S(HS, WPB, BPS, L)                                                                       \
+  do {                                                                                                           \
+    if (simple) launch_warp_t<HS, WPB, BPS, L, true>(nav, arena, q, pool, counters, type_raw, sm_count, stream);   \
+    else launch_warp_t<HS, WPB, BPS, L, false>(nav, arena, q, pool, counters, type_raw, sm_count, stream);         \
   } while (0)
-#define LMB_WARP_LAUNCH(L)                 \
-  do {                                     \
-    if (wide) LMB_WARP_LAUNCH_S(736, 4, L); \
-    else LMB_WARP_LAUNCH_S(1472, 2, L);     \
+#define LMB_WARP_LAUNCH(L)                                  \
+  do {                                                      \
+    if (per_sm <= 1) LMB_WARP_LAUNCH_S(13824, 1, 1, L);      \
+    else if (per_sm <= 4) LMB_WARP_LAUNCH_S(3456, 4, 1, L);  \
+    else if (per_sm <= 8) LMB_WARP_LAUNCH_S(1472, 4, 2, L);  \
+    else LMB_WARP_LAUNCH_S(736, 4, 4, L);                    \
   } while (0)
   if (arena.layout == 1) LMB_WARP_LAUNCH(1);
   else if (arena.layout == 2) LMB_WARP_LAUNCH(2);
