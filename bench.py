@@ -48,10 +48,13 @@ AGENTS_PER_GPU = 100_000
 DT = 1.0 / 60.0
 ISLAND_PITCH = 640.0  # spacing of the per-GPU maze islands (a 256-room maze is 513 m wide)
 B_STEP = 240.0  # algorithmic bytes per steady agent-update
-# DRAM bytes per explored node of k_astar from `ncu --set full` of a fully loaded launch on a capturable
-# (scratch_bytes-limited) arena — profiles/r02_ncu_astar_loaded.md
-NCU_DRAM_BYTES_PER_EXPLORED = None
-NCU_SOURCE = "profiles/r02_ncu_astar_loaded.md"
+# DRAM bytes per explored node of k_astar MEASURED ON THIS WORKLOAD AT THIS SIZE: ncu application replay of the
+# bench's own 100 000-query launch (dram__bytes_read.sum + dram__bytes_write.sum = 112.4 GB for 6.479 G explored
+# nodes) — profiles/r02_ncu_dram_bench.csv.  Only used for the other --config runs' `traffic`; config 2 reports
+# the measured launch total itself.
+NCU_DRAM_BYTES_PER_EXPLORED = 17.35
+NCU_DRAM_BYTES_BENCH_LAUNCH = 112_420_450_304
+NCU_SOURCE = "profiles/r02_ncu_dram_bench.csv"
 
 
 def measured_peak_gbs():
@@ -578,13 +581,15 @@ def main():
                          "wall_per_step": wall_ms},
             "roofline": {"bound": "hbm", "kernel": "k_astar", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps
-                                     if NCU_DRAM_BYTES_PER_EXPLORED else None),
-                         "traffic_source": f"ncu dram bytes per explored node ({NCU_SOURCE}) x explored nodes of "
-                                           "this launch",
+                         "traffic": NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps,
+                         "traffic_source": f"ncu dram__bytes_read+write of this workload's own k_astar launch at full "
+                                           f"size ({NCU_SOURCE}: {NCU_DRAM_BYTES_BENCH_LAUNCH} B for 6.479e9 explored "
+                                           "nodes = 17.35 B per explored node) x explored nodes of this run",
                          "algorithmic_bytes": astar_bytes, "peak_source": peak_src,
                          "note": "latency/issue-bound graph search: one dependent chain per query (pop -> records "
-                                 "-> push), algorithmic bytes = 32/query + 8/corridor node + 96/explored node"},
+                                 "-> push), algorithmic bytes = 32/query + 8/corridor node + 96/explored node "
+                                 "(SURVEY 8d); measured DRAM traffic is BELOW that figure because the forest layout "
+                                 "has no closed set and the open lists stay in shared memory"},
         }
         if moving:
             line["frame0"] = frame0

@@ -363,26 +363,20 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           }
           // distance(point, edge midpoint): a constant of the mesh for edge states (table built at
           // upload with the same rounding sequence), computed here for Start / link states
-          // (LAZY, the best_estimates-free forest layout: there is no probe latency to overlap and every candidate
-          // is accepted, so cost and estimate are evaluated per pushed successor in the push loop instead — the
-          // lanes of a warp then pay for their max candidate COUNT (~2.5 in a maze), not for four edges.)
-          constexpr bool LAZY = LAYOUT == 3;
-          float dj[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          float nc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, es[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-          if (!LAZY) {
-            if (preloaded) {
-              dj[0] = dtab.x, dj[1] = dtab.y, dj[2] = dtab.z, dj[3] = dtab.w;
-            } else {
+          float dj[4];
+          if (preloaded) {
+            dj[0] = dtab.x, dj[1] = dtab.y, dj[2] = dtab.z, dj[3] = dtab.w;
+          } else {
 #pragma unroll
-              for (int j = 0; j < 4; j++) dj[j] = distance(point, V3{r[j].mx, r[j].my, r[j].mz});
-            }
+            for (int j = 0; j < 4; j++) dj[j] = distance(point, V3{r[j].mx, r[j].my, r[j].mz});
+          }
+          float nc[4], es[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const V3 mid{r[j].mx, r[j].my, r[j].mz};
-              const float c = fmul(dj[j], cur_type_cost);
-              nc[j] = fadd(cur_cost, c);
-              es[j] = fadd(nc[j], fmul(distance(mid, end_point), cheapest));
-            }
+          for (int j = 0; j < 4; j++) {
+            const V3 mid{r[j].mx, r[j].my, r[j].mz};
+            const float c = fmul(dj[j], cur_type_cost);
+            nc[j] = fadd(cur_cost, c);
+            es[j] = fadd(nc[j], fmul(distance(mid, end_point), cheapest));
           }
           if (e0 == 0) {
             // (cur.state == s: naming the popped entry keeps this use behind the pop)
@@ -432,19 +426,15 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           // accept = candidate and not (best <= estimate); the common cases of the probe (tracked /
           // absent) are resolved without branches, the overflow table (compact layout) behind one
           uint32_t acc = 0, slow = 0;
-          if (LAZY) {
-            acc = cand;
-          } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              bool need_table = false;
-              const float bv = bs.value_fast(r[j].twin, praw[j], need_table);
-              acc |= !(bv <= es[j]) ? (1u << j) : 0u;
-              slow |= need_table ? (1u << j) : 0u;
-            }
-            acc &= cand;
-            slow &= cand;
+          for (int j = 0; j < 4; j++) {
+            bool need_table = false;
+            const float bv = bs.value_fast(r[j].twin, praw[j], need_table);
+            acc |= !(bv <= es[j]) ? (1u << j) : 0u;
+            slow |= need_table ? (1u << j) : 0u;
           }
+          acc &= cand;
+          slow &= cand;
           if (slow) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
@@ -456,24 +446,14 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
           while (acc) {
             const uint32_t j = __ffs(acc) - 1;
             acc &= acc - 1;
-            float est, ncost;
-            if (LAZY) {
-              const V3 mid{sel4(j, r[0].mx, r[1].mx, r[2].mx, r[3].mx), sel4(j, r[0].my, r[1].my, r[2].my, r[3].my),
-                           sel4(j, r[0].mz, r[1].mz, r[2].mz, r[3].mz)};
-              const float d = preloaded ? sel4(j, dtab.x, dtab.y, dtab.z, dtab.w) : distance(point, mid);
-              ncost = fadd(cur_cost, fmul(d, cur_type_cost));
-              est = fadd(ncost, fmul(distance(mid, end_point), cheapest));
-              if (F_INF <= est) continue;  // try_add_node with an absent entry (+inf): only est = +inf is refused
-            } else {
-              est = sel4(j, es[0], es[1], es[2], es[3]);
-              ncost = sel4(j, nc[0], nc[1], nc[2], nc[3]);
-            }
             if (n_nodes >= node_cap || heap.len >= heap_cap) {
               heap_full = heap.len >= heap_cap;
               overflow = true;
               break;
             }
             const uint32_t s2 = sel4(j, r[0].twin, r[1].twin, r[2].twin, r[3].twin);
+            const float est = sel4(j, es[0], es[1], es[2], es[3]);
+            const float ncost = sel4(j, nc[0], nc[1], nc[2], nc[3]);
             // The probes were issued together, before this expansion's inserts.  In the compact and hashed
             // layouts two states can share a physical entry (the same polygon; the same home slot or probe
             // chain), so after the first insert a later successor's probe may be out of date: take a fresh one.
@@ -872,6 +852,9 @@ static void launch_astar_t(const DevNav& nav, const AStarArena& arena, const ASt
 //    8 per SM -> one query per warp with 1536 entries (a lone lane is not held back by
 //    lock-step neighbours, and an open-field open list fits on chip); up to 128 per SM -> 8 queries
 //    per warp with 96 entries.
+// (Measured and rejected in round 2, forest layout: evaluating cost / estimate per pushed successor inside the
+// push loop instead of for all four edges up front — 5 % less latency for a lone query, but in a loaded warp the
+// loop body then runs with ~6 of 16 lanes active and the bench step went 338 -> 349 ms.)
 // (Measured and rejected: 32 queries per warp; 384 queries per SM with 28 shared-memory entries;
 // 64 / 192 / 384 entries at 192 / 64 / 32 queries per SM; a 4-lanes-per-query variant — lower
 // latency per query but issue-bound, no faster when loaded.)
@@ -917,8 +900,12 @@ uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQue
   const bool force_large = flags & LMB_CONFIG_ASTAR_LARGE_SHAPES;
   // Small batches finish with their longest search: up to 16 queries per SM go to the warp-per-query kernel
   // (k_astar_warp.cu), whose single-search latency is several times lower.
+  // (measured, scripts/astar_latency.py: on a forest the warp kernel wins up to 16 queries per SM; with large
+  // open lists it wins while a query's open list fits in its share of shared memory — up to 4 per SM — and the
+  // thread-per-query shapes are ahead again beyond that)
+  const uint32_t warp_max = (arena.layout == 3 ? 16u : 4u) * (uint32_t)sm_count;
   const bool warp = (flags & LMB_CONFIG_ASTAR_WARP_ONLY) ||
-                    (!force_large && !(flags & LMB_CONFIG_ASTAR_THREAD_ONLY) && q.n <= 16u * (uint32_t)sm_count);
+                    (!force_large && !(flags & LMB_CONFIG_ASTAR_THREAD_ONLY) && q.n <= warp_max);
   if (warp) {
     kind = 2;
     launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, (uint32_t)sm_count, stream);

@@ -57,7 +57,12 @@ struct Strided {
 struct Scratch {
   Strided<float2> nb;         // (d2, index bits)
   Strided<uint2> heap;        // (node, score bits)
-  Strided<uint32_t> explored;
+  Strided<uint32_t> explored;      // explored set of the flood: open-addressing table of node ids, 4 x max_explore
+                                   // slots, EMPTY (LMB_NONE) between agents (the host fills the scratch with 0xFF
+                                   // whenever its layout changes; every flood un-inserts what it inserted)
+  Strided<uint32_t> explored_slot; // the slots this flood filled, in insertion order (2 x max_explore)
+  Strided<uint32_t> explored_list; // the explored node ids in insertion order (2 x max_explore): the whole set while
+                                   // it is small (coalesced across the agents of a warp, unlike hashed slots)
   Strided<float4> vis;        // line a.xy, b.xy (relative to the agent, oriented CCW)
   Strided<uint2> border;      // (left vertex id, right vertex id) per line
   Strided<Cone> cones[2];
@@ -96,7 +101,9 @@ __device__ __forceinline__ Scratch carve(const AvoidScratch& s, uint32_t t) {
   take(r.new_verts, r.max_border);
   take(r.loops, r.max_loops);
   take(r.finished, r.max_loops);
-  take(r.explored, (size_t)r.max_explore * 2);
+  take(r.explored, (size_t)r.max_explore * 4);
+  take(r.explored_slot, (size_t)r.max_explore * 2);
+  take(r.explored_list, (size_t)r.max_explore * 2);
   take(r.cones[0], r.max_cones);
   take(r.cones[1], r.max_cones);
   take(r.lnodes, (size_t)r.max_border * 2);
@@ -715,7 +722,7 @@ __global__ void k_grid_fill(AvoidGrid g, uint32_t n, const AvoidRecord* records)
 // ---------------------------------------------------------------------------
 // the per-agent avoidance kernel
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, 14)
 k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_t first_agent_global,
             uint32_t chunk_begin, uint32_t chunk_n, uint32_t n_records, const AvoidRecord* records,
             uint32_t n_characters, const AvoidRecord* char_records, AvoidGrid grid, AvoidScratch scratch,
@@ -727,6 +734,7 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
   const AvoidRecord me = records[gi];
   if (!me.valid) return;
   Scratch s = carve(scratch, t);
+
   bool overflow = false;
   if (delta_time == 0.0f) delta_time = 1.0f;
 
@@ -811,21 +819,57 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
     heap.data = s.heap;
     heap.len = 0;
     uint32_t n_explored = 0;
+    const uint32_t ex_mask = 4u * s.max_explore - 1u;  // max_explore is a power of two (64 << k)
+    constexpr uint32_t EX_LINEAR = 8;
+    // slot of `node` in the hash table (true) or the empty slot where it belongs (false)
+    auto ex_probe = [&](uint32_t node, uint32_t& slot) -> bool {
+      for (uint32_t hh = (node * 2654435761u) >> 7;; hh++) {
+        const uint32_t v = s.explored[hh & ex_mask];
+        if (v == node || v == LMB_NONE) {
+          slot = hh & ex_mask;
+          return v == node;
+        }
+      }
+    };
     heap.push(make_uint2(ag.agent_node[i], __float_as_uint(0.0f)));
     while (heap.len > 0) {
       const uint32_t node = heap.pop().x;
+      // `explored.insert(node)` (avoidance.rs:228-232).  Up to EX_LINEAR nodes the set is a list scanned linearly
+      // (a coarse mesh: a handful of polygons per flood, and entry k of 32 neighbouring agents is one line).  On a
+      // fine mesh a flood visits hundreds of polygons and pops each several times — the linear scan was half of
+      // the kernel's instructions there (ncu, config 1) — so beyond that the set is a hash table with linear
+      // probing, at most half full.
       bool seen = false;
-      for (uint32_t k = 0; k < n_explored; k++)
-        if (s.explored[k] == node) {
-          seen = true;
-          break;
-        }
+      uint32_t h = 0;
+      if (n_explored <= EX_LINEAR) {
+        for (uint32_t k = 0; k < n_explored; k++)
+          if (s.explored_list[k] == node) {
+            seen = true;
+            break;
+          }
+      } else {
+        seen = ex_probe(node, h);
+      }
       if (seen) continue;
       if (n_explored >= s.max_explore * 2) {
         overflow = true;
         break;
       }
-      s.explored[n_explored++] = node;
+      s.explored_list[n_explored] = node;
+      if (n_explored == EX_LINEAR) {  // the list outgrows the linear scan: hash what it holds
+        for (uint32_t k = 0; k < EX_LINEAR; k++) {
+          uint32_t hk;
+          ex_probe(s.explored_list[k], hk);
+          s.explored[hk] = s.explored_list[k];
+          s.explored_slot[k] = hk;
+        }
+        ex_probe(node, h);
+      }
+      if (n_explored >= EX_LINEAR) {
+        s.explored[h] = node;
+        s.explored_slot[n_explored] = h;
+      }
+      n_explored++;
       const uint32_t eb = nav.poly_edge_begin[node], n = nav.poly_edge_begin[node + 1] - eb;
       auto consider = [&](V2 v1, V2 v2, uint32_t dst) {
         if (!vis_process(vs, v1, v2, false, nullptr)) return;
@@ -889,6 +933,9 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
         }
       }
     }
+    // leave the explored table empty for the next agent that gets this scratch
+    if (n_explored > EX_LINEAR)
+      for (uint32_t k = 0; k < n_explored; k++) s.explored[s.explored_slot[k]] = LMB_NONE;
   }
   overflow = overflow || vs.overflow;
 
@@ -1061,7 +1108,7 @@ size_t avoid_scratch_bytes_per_agent(const AvoidScratch& s) {
   size_t b = 0;
   b += (size_t)s.max_neighbours * 8;
   b += (size_t)s.max_explore * 8;
-  b += (size_t)s.max_explore * 8;
+  b += (size_t)s.max_explore * 32;  // explored table (4 x) + the slots a flood filled (2 x) + the node list (2 x)
   b += (size_t)s.max_border_edges * 16;
   b += (size_t)s.max_border_edges * 8;
   b += (size_t)s.max_cones * 12 * 2;
@@ -1101,7 +1148,19 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
                             cudaStream_t stream) {
   if (!chunk_n) return;
-  k_avoidance<<<blocks_for(chunk_n, 64), 64, 0, stream>>>(nav, ag, o, delta_time, first_agent_global, chunk_begin,
+  // Few agents: spread them over the SMs in small blocks.  One thread walks its agent's scratch serially (flood
+  // heap, cone list, loop nodes: tens of thousands of dependent accesses on a fine mesh), so what it needs is its
+  // ~25 KB of scratch in ITS SM's L1 — 64 agents per block put 1.5 MB behind one L1 and left 146 SMs idle
+  // (config 1, 100 agents: 3.3 ms of a 3.6 ms frame).
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  uint32_t threads = 64;
+  while (threads > 8 && (uint64_t)chunk_n * 8 <= (uint64_t)sm_count * threads * 4) threads >>= 1;
+  k_avoidance<<<blocks_for(chunk_n, threads), threads, 0, stream>>>(nav, ag, o, delta_time, first_agent_global, chunk_begin,
                                                           chunk_n, n_records, records, n_characters, char_records,
                                                           grid, scratch, max_radius_bits, staged_moves, dbg);
 }

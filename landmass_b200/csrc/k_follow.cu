@@ -54,13 +54,12 @@ __device__ Portal get_portal_endpoints(const DevNav& nav, const PathView& path, 
   } else {
     // get_edge_indices (nav_mesh.rs:945-950): left = vertex[edge+1], right = vertex[edge];
     // world vertices are transform.apply(local) precomputed at upload (same function, same bits).
-    uint32_t eb = nav.poly_edge_begin[ent.x], n = nav.poly_edge_begin[ent.x + 1] - eb;
-    uint32_t edge = ent.y;
-    uint32_t li = nav.edge_vertex[eb + (edge == n - 1 ? 0 : edge + 1)];
-    uint32_t ri = nav.edge_vertex[eb + edge];
+    // (one 32-byte record of the per-edge portal table: the world vertices themselves, copied at upload)
+    const uint32_t rec = nav.rec_kshift ? ((ent.x << nav.rec_kshift) | ent.y) : nav.poly_edge_begin[ent.x] + ent.y;
+    const float4 l = __ldg(nav.portal_lr + 2 * (size_t)rec), r = __ldg(nav.portal_lr + 2 * (size_t)rec + 1);
     p.walkable = true;
-    p.a = ld3(nav.verts_world, li);
-    p.b = ld3(nav.verts_world, ri);
+    p.a = {l.x, l.y, l.z};
+    p.b = {r.x, r.y, r.z};
   }
   return p;
 }

@@ -463,6 +463,18 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
     }
   }
 
+  // portal endpoints per edge record (world coordinates: the same verts_world values the funnel used to gather
+  // through poly_edge_begin -> edge_vertex -> verts_world)
+  std::vector<float4> portal_lr((size_t)std::max<uint32_t>(n_ids, 4u) * 2, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+  for (uint32_t p = 0; p < d->n_polys; p++) {
+    const uint32_t eb = d->poly_edge_begin[p], ne = d->poly_edge_begin[p + 1] - eb;
+    for (uint32_t e = 0; e < ne; e++) {
+      const uint32_t li = d->edge_vertex[eb + (e == ne - 1 ? 0 : e + 1)], ri = d->edge_vertex[eb + e];
+      const size_t k = (size_t)rec_id(p, e) * 2;
+      portal_lr[k] = make_float4(verts_world[3 * (size_t)li], verts_world[3 * (size_t)li + 1], verts_world[3 * (size_t)li + 2], 0.0f);
+      portal_lr[k + 1] = make_float4(verts_world[3 * (size_t)ri], verts_world[3 * (size_t)ri + 1], verts_world[3 * (size_t)ri + 2], 0.0f);
+    }
+  }
   std::vector<uint32_t> link_dst_type_dense(d->n_links);
   for (uint32_t l = 0; l < d->n_links; l++) link_dst_type_dense[l] = type_dense[d->link_dst_type[l]];
   std::vector<uint32_t> node_modified(d->n_polys, LMB_NONE);
@@ -491,6 +503,7 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
   UPV(d_cell_start, cell_start);
   UPV(d_cell_polys, cell_polys);
   UPV(d_edges, edges);
+  UPV(d_portal_lr, portal_lr);
   UPV(d_type_cost, type_cost);
   UPV(d_type_registered, type_registered);
   UPV(d_type_raw, type_raw);
@@ -534,6 +547,8 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
   nav.cell_start = ctx->d_cell_start.p;
   nav.cell_polys = ctx->d_cell_polys.p;
   nav.edges = ctx->d_edges.p;
+  nav.portal_lr = ctx->d_portal_lr.p;
+  nav.rec_kshift = ctx->kshift;
   nav.edge_dist = nullptr;
   if (ctx->kshift) {
     CUDA_TRY(ctx, ctx->d_edge_dist.reserve((size_t)ctx->n_ids << ctx->kshift));
@@ -601,6 +616,13 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
       for (uint32_t l = 0; l < d->n_links; l++)
         if (link_src[l] != LMB_NONE) join(link_src[l], d->link_dst_node[l]);
       const bool forest = connections + components == d->n_polys;
+      // polygons of the largest connected component: on a forest a search never creates more nodes than its
+      // own component has polygons (+ Start / End), whatever else the world holds (e.g. one maze island per GPU)
+      uint32_t max_component = 0;
+      {
+        std::vector<uint32_t> size(d->n_polys, 0);
+        for (uint32_t p = 0; p < d->n_polys; p++) max_component = std::max(max_component, ++size[find(p)]);
+      }
       const uint32_t n_states = ctx->n_ids + nav.n_links + 2;
       const uint32_t fl = ctx->cfg.flags;
       const bool f_compact = fl & LMB_CONFIG_ASTAR_COMPACT, f_dense = fl & LMB_CONFIG_ASTAR_DENSE;
@@ -624,6 +646,10 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
       if (f_hashed) ctx->arena_node_cap = std::min<uint32_t>(ctx->arena_node_cap, 2048u);
       // the are_nodes_connected BFS borrows the node list as seen[] / queue[] (2 x n_region_numbers words)
       ctx->arena_node_cap = std::max<uint32_t>(ctx->arena_node_cap, d->n_region_numbers + 64);
+      if (ctx->best_layout == 3) {
+        ctx->arena_node_cap = std::max<uint32_t>(max_component + 64, d->n_region_numbers + 64);
+        ctx->arena_heap_cap = AT_HEAP_SM + 1024;  // a tree's open list is its unexpanded branches: small (doubles on overflow)
+      }
       ctx->big_heap = !forest;  // first guess: a wavefront; corrected from the first batch's open lists
     }
     ctx->arena = AStarArena{};
@@ -1435,7 +1461,8 @@ int32_t lmb_step_end(lmb_ctx* ctx, const lmb_options* o, float dt) {
 
 int32_t lmb_step_resident(lmb_ctx* ctx, const lmb_options* o, float dt) {
   if (!ctx) return LMB_ERR_INVALID_ARGUMENT;
-  int32_t st = lmb_step_begin(ctx, o, dt, ctx->n_agents, 0);
+  // (no caller stands between the halves here: phase D is enqueued behind phase C without a host sync)
+  int32_t st = lmb_step_begin_impl(ctx, o, dt, ctx->n_agents, 0, /*sync_at_end=*/false);
   if (st != LMB_OK) return st;
   return lmb_step_end(ctx, o, dt);
 }

@@ -92,6 +92,17 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
     sc.agent_stride = (chunk + 31u) & ~31u;
     CUDA_TRY(ctx, ctx->d_avoid_scratch.reserve(sc.per_agent_bytes * (size_t)sc.agent_stride));
     sc.base = ctx->d_avoid_scratch.p;
+    {
+      // The flood's explored table must be EMPTY (0xFFFFFFFF) when an agent starts; floods clean up behind
+      // themselves, so the whole scratch is filled once per layout (capacities, stride or buffer changed).
+      const uint64_t sig = ((uint64_t)sc.agent_stride << 32) ^ ((uint64_t)sc.max_explore << 20) ^ ((uint64_t)sc.max_lines << 12) ^
+                           ((uint64_t)sc.max_cones << 6) ^ sc.max_border_edges ^ ((uint64_t)sc.max_neighbours << 40) ^
+                           (uint64_t)(uintptr_t)sc.base;
+      if (sig != ctx->avoid_scratch_sig) {
+        CUDA_TRY(ctx, cudaMemsetAsync(sc.base, 0xFF, sc.per_agent_bytes * (size_t)sc.agent_stride, s));
+        ctx->avoid_scratch_sig = sig;
+      }
+    }
     sc.overflow = ctx->d_avoid_overflow.p;
     CUDA_TRY(ctx, cudaMemsetAsync(sc.overflow, 0, sizeof(uint32_t), s));
     // debug-avoidance export: one row of 2 x max_lines per asking agent, "did not run" until written

@@ -78,6 +78,7 @@ struct lmb_ctx {
   DevBuf<uint8_t> d_htris, d_type_registered;
   DevBuf<EdgeRec> d_edges;
   DevBuf<float> d_edge_dist;
+  DevBuf<float4> d_portal_lr;
   float world_min[2] = {0, 0}, world_max[2] = {0, 0};
 
   // --- A* ---
@@ -141,6 +142,7 @@ struct lmb_ctx {
   DevBuf<float> d_bounds_tmp;
   uint32_t last_n_results = 0;
   uint32_t avoid_caps[5] = {64, 64, 128, 256, 256};  // neighbours, explore, border edges, cones, lines
+  uint64_t avoid_scratch_sig = 0;                    // layout the scratch was last filled for (lmb_avoid_host.cu)
 
   lmb_step_timings timings{};
   lmb_step_timings query_timings{};  // of the last lmb_find_paths / lmb_find_straight_paths batch

@@ -146,6 +146,10 @@ struct DevNav {
   const uint32_t* cell_polys;
   const EdgeRec* edges;
   const float* edge_dist;      // padded ids only: [n_ids * K] midpoint-to-midpoint distances inside a polygon
+  const float4* portal_lr;     // [n_ids * 2] per edge record: world {left.xyz, -}, {right.xyz, -} of the edge as a
+                               // portal (left = vertex[e+1], right = vertex[e], nav_mesh.rs:945-950): the funnel walks
+                               // a corridor with ONE dependent load per portal instead of four
+  uint32_t rec_kshift;         // record id of (node, edge): node << rec_kshift | edge, or (0) poly_edge_begin[node] + edge
   const float* type_cost;      // [n_types] archipelago cost of each dense type (1.0 if unregistered)
   const uint8_t* type_registered;  // [n_types] 1 if present in nav_data.type_index_to_cost
   // links

@@ -1,0 +1,150 @@
+"""Builds the round-2 files under profiles/ from the ncu reports and bench lines a GPU run left in gpurun_out/.
+
+  python scripts/make_r02_profiles.py <final bundle dir> <single-search dir v2> <single-search dir v1> <cfg3 dir> <objs dir>
+
+Every number in profiles/r02_*.md comes out of an .ncu-rep through `ncu -i ... --page raw/source --csv`
+(scripts/ncu_lines.py joins the source page with `nvdisasm -g` line info of the object that was profiled)."""
+import csv
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+final, single2, single1, cfg3, objs = sys.argv[1:6]
+P = os.path.join(ROOT, "profiles")
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+KEYS = [("gpu__time_duration.sum", "time"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+        ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp instructions"),
+        ("smsp__thread_inst_executed_per_inst_executed.ratio", "active lanes / instruction"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+        ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard / issue"),
+        ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard / issue"),
+        ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait / issue"),
+        ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving / issue"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction / issue"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected / issue")]
+
+
+def table(reps):
+    """reps: [(label, path)] -> markdown table metric x report"""
+    cols = []
+    for label, path in reps:
+        hdr, units, rows = raw(path)
+        r = rows[0]
+        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0]}
+        for k, name in KEYS:
+            if k in hdr:
+                v, u = r[hdr.index(k)], units[hdr.index(k)]
+                try:
+                    v = f"{float(v):.4g}"
+                except ValueError:
+                    pass
+                d[name] = f"{v} {u}".strip()
+        cols.append((label, d))
+    names = ["kernel"] + [n for _, n in KEYS]
+    out = "| metric | " + " | ".join(l for l, _ in cols) + " |\n|---|" + "---|" * len(cols) + "\n"
+    for n in names:
+        out += f"| {n} | " + " | ".join(d.get(n, "-") for _, d in cols) + " |\n"
+    return out
+
+
+def lines(rep, obj, kern, mangled, top=16):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), rep, obj, kern, str(top), mangled],
+                         capture_output=True, text=True).stdout
+    return "```\n" + out.rstrip() + "\n```\n"
+
+
+def src_line(path, n):
+    try:
+        return open(path).read().split("\n")[n - 1].strip()
+    except Exception:
+        return ""
+
+
+# ---- single search ----
+with open(os.path.join(P, "r02_ncu_astar_single.md"), "w") as f:
+    f.write("# ncu --set full of ONE A* search (256-room maze, 86 725 explored nodes; open field, 53 411)\n\n"
+            "`ncu --set full --import-source on --clock-control none -k regex:k_astar --launch-skip 1 --launch-count 1 "
+            "python scripts/profile_single.py <maze|field> <warp|thread> 1`.  Under ncu the L2 is flushed before every "
+            "replay pass, so every edge record of the search misses L2 once (16.8 MB of DRAM reads = the record table); "
+            "the un-profiled run of the same search is ~15 % faster (scripts/astar_latency.py).\n\n")
+    f.write(table([("warp kernel, first version (loads into registers)", os.path.join(single1, "ncu_warp_maze1.ncu-rep")),
+                   ("warp kernel, cp.async staging (maze)", os.path.join(single2, "ncu_warp_maze1.ncu-rep")),
+                   ("thread kernel `<1,1536,2>` (maze)", os.path.join(single1, "ncu_thread_maze1.ncu-rep")),
+                   ("warp kernel, cp.async staging (field, 1472 entries on chip)", os.path.join(single2, "ncu_warp_field1.ncu-rep"))]))
+    f.write("\nPer explored node: 397 -> 340 warp instructions (warp kernel), 411 (thread kernel).\n\n"
+            "## The false scoreboard wait in front of the pop (first version)\n\n"
+            "25.5 % of all stall samples of the first version sat on ONE instruction, `IMAD.MOV.U32 R31, RZ, RZ, R36` — the "
+            "first use of the `LDS.128` that reads the heap's last entry at the start of `pop()` — with reason "
+            "`long_scoreboard`: ptxas gave that LDS the scoreboard of the three outstanding `LDG`s of the records / distance "
+            "row, so the pop waited the whole L2 round trip it was meant to overlap.  With `cp.async` (no destination "
+            "register, no scoreboard) the wait moves to `cp.async.wait_group` BEHIND the pop and shrinks to the part of "
+            "the round trip the (short, maze) pop does not cover:\n\n")
+    f.write("Warp kernel with cp.async staging, maze, top source lines by stall samples "
+            "(`k_astar_warp.cu:183` at that commit = `cp.async.wait_group 0`):\n\n")
+    f.write(lines(os.path.join(single2, "ncu_warp_maze1.ncu-rep"), os.path.join(objs, "r2c", "k_astar_warp.o"), "k_astar_warp",
+                  "k_astar_warpILj1472ELj2ELi3ELb1E"))
+    f.write("\nSame kernel on the open field with 1 472 on-chip entries (`:109` / `:47` = the spilled levels of the pop: "
+            "loads of heap entries from global memory and the comparison that waits for them; the 13 824-entry shape "
+            "added afterwards keeps a lone search's whole open list on chip: 2.06 -> 1.61 us per node):\n\n")
+    f.write(lines(os.path.join(single2, "ncu_warp_field1.ncu-rep"), os.path.join(objs, "r2c", "k_astar_warp.o"), "k_astar_warp",
+                  "k_astar_warpILj1472ELj2ELi0ELb1E"))
+    f.write("\nThread kernel, maze (`k_astar.cu:295` = the pin behind the pop: the same L2 round trip of the records):\n\n")
+    f.write(lines(os.path.join(single1, "ncu_thread_maze1.ncu-rep"), os.path.join(objs, "r2d", "k_astar.o"), "k_astar<",
+                  "k_astarILj1ELj1536ELj2ELj2ELi3ELb1E"))
+
+# ---- loaded ----
+rep = os.path.join(final, "ncu_astar_loaded.ncu-rep")
+if os.path.exists(rep):
+    hdr, units, rows = raw(rep)
+    with open(os.path.join(P, "r02_ncu_astar_loaded_raw.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow(hdr)
+        w.writerow(units)
+        for r in rows:
+            w.writerow(r)
+    log = open(os.path.join(final, "ncu_loaded.log")).read() if os.path.exists(os.path.join(final, "ncu_loaded.log")) else ""
+    with open(os.path.join(P, "r02_ncu_astar_loaded.md"), "w") as f:
+        f.write("# ncu --set full of a fully loaded `k_astar<16,40,5,quad,forest,SIMPLE>` launch\n\n"
+                "`ncu --set full --import-source on --clock-control none -k regex:k_astar --launch-skip 1 --launch-count 1 "
+                "python scripts/profile_loaded.py 128 250000 47360`: 128x128-room maze (32 767 polygons), 250 000 queries on "
+                "47 360 arena slots (the bench's slot count; 0.29 MB per slot, so kernel replay can save / restore the "
+                "arena).  3.978 G explored nodes per launch.\n\n```\n" + log.strip()[-600:] + "\n```\n\n")
+        f.write(table([("loaded launch", rep)]))
+        r = rows[0]
+        inst = float(r[hdr.index("smsp__inst_executed.sum")])
+        f.write(f"\nPer explored node: {inst / 3977993509:.1f} warp instructions; DRAM "
+                f"{(float(r[hdr.index('dram__bytes_read.sum')]) + float(r[hdr.index('dram__bytes_write.sum')])) * 1e9 / 3977993509:.1f} B "
+                "(the units of the two DRAM rows above are Gbyte).\n\nTop source lines by stall samples:\n\n")
+        f.write(lines(rep, os.path.join(objs, "final", "k_astar.o"), "k_astar<", "k_astarILj16ELj40ELj5ELj2ELi3ELb1E", 24))
+
+# ---- config 3: avoidance / follow ----
+a, fo = os.path.join(cfg3, "ncu_avoid_cfg3.ncu-rep"), os.path.join(cfg3, "ncu_follow_cfg3.ncu-rep")
+if os.path.exists(a):
+    with open(os.path.join(P, "r02_ncu_avoid_follow_cfg3.md"), "w") as f:
+        f.write("# ncu --set full of `k_avoidance` (one 131 072-agent chunk) and `k_follow` (1 M agents) at config 3\n\n"
+                "`ncu --set full -k regex:k_avoidance|k_follow --launch-skip 4 --launch-count 1 python bench.py --config 3 "
+                "--steps 3 --warmup 2` (open field, 1 M agents, steady frame; scratch interleaved by agent, portal table).\n\n")
+        f.write(table([("k_avoidance", a), ("k_follow", fo)]))
+        f.write("\nk_avoidance, top source lines by stall samples (`k_avoid.cu:769` = the insertion into the sorted "
+                "neighbour list, `lmb_device.cuh:30` = the first use of a gathered neighbour record):\n\n")
+        f.write(lines(a, os.path.join(objs, "r2f", "k_avoid.o"), "k_avoidance", "k_avoidance", 12))
+
+# ---- plain copies ----
+for src, dst in (("ncu_launches_bench.csv", "r02_ncu_launches_bench.csv"), ("ncu_dram_bench.csv", "r02_ncu_dram_bench.csv"),
+                 ("bench_cfg2.json", "r02_bench_1gpu.json"), ("bench_ref.json", "r02_bench_reference_arm.json")):
+    if os.path.exists(os.path.join(final, src)):
+        shutil.copy(os.path.join(final, src), os.path.join(P, dst))
+print("profiles written")

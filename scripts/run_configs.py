@@ -161,7 +161,8 @@ def config4(n=100_000, frames=4, k=8, g=128):
 
 
 def config1():
-    """64 x 64 quad grid, 100 agents (the reference's CPU-runnable case) — GPU vs oracle exact."""
+    """64 x 64 quad grid, 100 agents (the reference's CPU-runnable case) — GPU vs oracle exact.  Frame 0 (every
+    agent plans; on the GPU it also allocates the A* arena) and the steady frames are reported separately."""
     from oracle.oracle_py import OracleBackend
 
     mesh = synth.grid_mesh(64, 64)
@@ -171,18 +172,29 @@ def config1():
     gpu, cpu = NativeBackend(max_agents=100), OracleBackend()
     gpu.navdata_upload(flat)
     cpu.navdata_upload(flat)
-    t_cpu = t_gpu = 0.0
-    for f in range(20):
-        t0 = time.perf_counter(); og = gpu.step(ag, None, opts, 1 / 60); t1 = time.perf_counter()
-        oc = cpu.step(ag, None, opts, 1 / 60); t2 = time.perf_counter()
-        t_gpu += t1 - t0; t_cpu += t2 - t1
-        assert np.array_equal(og["state"], oc["state"]) and gpu.pathing_results() == cpu.pathing_results()
-        np.testing.assert_allclose(og["desired_velocity"], oc["desired_velocity"], rtol=1e-4, atol=1e-6)
-        ag["flags"] = ag["flags"] & ~np.uint32(_abi.AGENT_RESET)
-        ag["velocity"] = oc["desired_velocity"].copy()
-        ag["position"] = ag["position"] + oc["desired_velocity"] * np.float32(1 / 60)
-    print(json.dumps({"config": 1, "agents": 100, "frames": 20, "gpu_ms_per_frame_e2e": t_gpu / 20 * 1e3,
-                      "cpu_oracle_ms_per_frame": t_cpu / 20 * 1e3}))
+    # second, identical pair of runs so that one-time costs (arena allocation, first kernel loads) are visible
+    rows = []
+    for rep in range(2):
+        a = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in ag.items()}
+        tg, tc, repaths = [], [], []
+        for f in range(60):
+            t0 = time.perf_counter(); og = gpu.step(a, None, opts, 1 / 60); t1 = time.perf_counter()
+            oc = cpu.step(a, None, opts, 1 / 60); t2 = time.perf_counter()
+            tg.append(t1 - t0); tc.append(t2 - t1)
+            assert np.array_equal(og["state"], oc["state"]) and gpu.pathing_results() == cpu.pathing_results()
+            np.testing.assert_allclose(og["desired_velocity"], oc["desired_velocity"], rtol=1e-4, atol=1e-6)
+            repaths.append(len(gpu.pathing_results()))
+            a["flags"] = a["flags"] & ~np.uint32(_abi.AGENT_RESET)
+            a["velocity"] = oc["desired_velocity"].copy()
+            a["position"] = a["position"] + oc["desired_velocity"] * np.float32(1 / 60)
+        rows.append({"run": rep, "frame0_gpu_ms": tg[0] * 1e3, "frame0_cpu_ms": tc[0] * 1e3,
+                     "steady_gpu_ms_median": float(np.median(tg[1:])) * 1e3,
+                     "steady_cpu_ms_median": float(np.median(tc[1:])) * 1e3,
+                     "mean_gpu_ms": float(np.mean(tg)) * 1e3, "mean_cpu_ms": float(np.mean(tc)) * 1e3,
+                     "repaths_frame0": repaths[0], "repaths_later": int(sum(repaths[1:]))})
+        a2 = None
+        # re-arm for the second run: every agent re-plans again
+    print(json.dumps({"config": 1, "agents": 100, "frames": 60, "runs": rows}))
 
 
 if __name__ == "__main__":
