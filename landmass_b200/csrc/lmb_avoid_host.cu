@@ -66,10 +66,10 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
   const size_t cells = (size_t)grid.nx * grid.ny;
   CUDA_TRY(ctx, ctx->d_cell_count.reserve(cells + 2));
   CUDA_TRY(ctx, ctx->d_cell_start2.reserve(cells + 2));
-  CUDA_TRY(ctx, ctx->d_sorted.reserve(n_total ? n_total : 1));
   grid.cell_count = ctx->d_cell_count.p;
   grid.cell_start = ctx->d_cell_start2.p;
-  grid.sorted = ctx->d_sorted.p;
+  CUDA_TRY(ctx, ctx->d_sorted_records.reserve(n_total ? n_total : 1));
+  grid.sorted_rec = ctx->d_sorted_records.p;
   CUDA_TRY(ctx, ctx->d_scan_tiles.reserve(exclusive_scan_tmp_words((uint32_t)cells + 1)));
   grid.scan_tmp = ctx->d_scan_tiles.p;
   uint32_t* max_radius_bits = ctx->d_avoid_overflow.p + 1;

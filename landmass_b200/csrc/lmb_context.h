@@ -131,8 +131,8 @@ struct lmb_ctx {
   DevBuf<float> d_out_velocity, d_out_link_start, d_out_link_end;
   DevBuf<uint32_t> d_out_state, d_out_link_id;
   // avoidance
-  DevBuf<AvoidRecord> d_records, d_char_records;
-  DevBuf<uint32_t> d_cell_count, d_cell_start2, d_sorted, d_avoid_overflow, d_scan_tiles;
+  DevBuf<AvoidRecord> d_records, d_char_records, d_sorted_records;
+  DevBuf<uint32_t> d_cell_count, d_cell_start2, d_avoid_overflow, d_scan_tiles;
   DevBuf<uint8_t> d_avoid_scratch;
   // debug-avoidance export: agents that set LMB_AGENT_KEEP_AVOIDANCE_DATA (in upload order)
   std::vector<uint32_t> h_dbg_row_of;  // [n_agents] row or LMB_NONE; empty = nobody asked

@@ -190,7 +190,9 @@ struct AvoidGrid {
   uint32_t nx, ny;
   uint32_t* cell_count;   // [nx*ny + 1]
   uint32_t* cell_start;   // [nx*ny + 1]
-  uint32_t* sorted;       // [n_records] record indices grouped by cell
+  AvoidRecord* sorted_rec;  // [n_records] the records themselves in cell order, `valid` replaced by the
+                            // record's index (the cells of a grid row are contiguous: an agent's candidates of one
+                            // row are then one contiguous run of 32-byte records)
   uint32_t* scan_tmp;     // [exclusive_scan_tmp_words(nx*ny + 1)]
   uint32_t capacity_cells;
 };
