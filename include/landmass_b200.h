@@ -239,6 +239,7 @@ typedef struct lmb_pathing_result {
 #define LMB_CONFIG_ASTAR_THREAD_ONLY 64u   /* never launch the warp-per-query (low latency) search kernel */
 #define LMB_CONFIG_ASTAR_WARP_ONLY 128u    /* launch only the warp-per-query search kernel */
 #define LMB_CONFIG_ASTAR_NO_FOREST 256u    /* do not use the best_estimates-free layout of forest meshes */
+#define LMB_CONFIG_NO_L2_WINDOW 512u       /* do not pin the A* tables in L2 (access-policy window; A/B hook) */
 
 typedef struct lmb_config {
   uint32_t struct_size;

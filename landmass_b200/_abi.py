@@ -47,6 +47,7 @@ CONFIG_ASTAR_LARGE_SHAPES = 32
 CONFIG_ASTAR_THREAD_ONLY = 64
 CONFIG_ASTAR_WARP_ONLY = 128
 CONFIG_ASTAR_NO_FOREST = 256
+CONFIG_NO_L2_WINDOW = 512
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)

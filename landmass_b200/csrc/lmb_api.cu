@@ -502,7 +502,10 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
   }
   UPV(d_cell_start, cell_start);
   UPV(d_cell_polys, cell_polys);
-  UPV(d_edges, edges);
+  const size_t edges_bytes = (edges.size() * sizeof(EdgeRec) + 255) & ~(size_t)255;
+  const size_t dist_bytes = ctx->kshift ? ((size_t)ctx->n_ids << ctx->kshift) * sizeof(float) : 0;
+  CUDA_TRY(ctx, ctx->d_astar_tables.reserve(edges_bytes + dist_bytes + 256));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_astar_tables.p, edges.data(), edges.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice, s));
   UPV(d_portal_lr, portal_lr);
   UPV(d_type_cost, type_cost);
   UPV(d_type_registered, type_registered);
@@ -546,15 +549,35 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
   nav.htris = ctx->d_htris.p;
   nav.cell_start = ctx->d_cell_start.p;
   nav.cell_polys = ctx->d_cell_polys.p;
-  nav.edges = ctx->d_edges.p;
+  nav.edges = reinterpret_cast<const EdgeRec*>(ctx->d_astar_tables.p);
   nav.portal_lr = ctx->d_portal_lr.p;
   nav.rec_kshift = ctx->kshift;
   nav.edge_dist = nullptr;
   if (ctx->kshift) {
-    CUDA_TRY(ctx, ctx->d_edge_dist.reserve((size_t)ctx->n_ids << ctx->kshift));
-    launch_build_edge_dist(ctx->d_edges.p, ctx->n_ids, ctx->kshift, ctx->d_edge_dist.p, s);
+    float* dist = reinterpret_cast<float*>(ctx->d_astar_tables.p + edges_bytes);
+    launch_build_edge_dist(nav.edges, ctx->n_ids, ctx->kshift, dist, s);
     CUDA_TRY(ctx, cudaGetLastError());
-    nav.edge_dist = ctx->d_edge_dist.p;
+    nav.edge_dist = dist;
+  }
+  {
+    // L2 persistence for the tables (B200: 126 MB of L2; the tables are 12-200 MB).  Best effort: a device
+    // without the feature, or a window larger than the limit, just keeps the default policy.
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    const size_t want = edges_bytes + dist_bytes;
+    if (max_persist > 0 && max_window > 0 && !(ctx->cfg.flags & LMB_CONFIG_NO_L2_WINDOW)) {
+      const size_t carve = std::min<size_t>(want, (size_t)max_persist);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr = ctx->d_astar_tables.p;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(want, (size_t)max_window);
+      attr.accessPolicyWindow.hitRatio = want ? (float)std::min(1.0, (double)carve / (double)want) : 1.0f;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
   }
   nav.type_cost = ctx->d_type_cost.p;
   nav.type_registered = ctx->d_type_registered.p;

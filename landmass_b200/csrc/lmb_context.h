@@ -76,8 +76,10 @@ struct lmb_ctx {
       d_modified_vert_begin, d_node_region_number, d_region_root, d_possible_src, d_possible_dst,
       d_possible_kind;
   DevBuf<uint8_t> d_htris, d_type_registered;
-  DevBuf<EdgeRec> d_edges;
-  DevBuf<float> d_edge_dist;
+  // EdgeRec table followed by the distance table, in ONE allocation: the A* kernels' read-only working set,
+  // covered by one L2 access-policy window on the step stream (persisting), so that the per-query arenas
+  // streaming through L2 do not evict it
+  DevBuf<uint8_t> d_astar_tables;
   DevBuf<float4> d_portal_lr;
   float world_min[2] = {0, 0}, world_max[2] = {0, 0};
 

@@ -147,4 +147,19 @@ for src, dst in (("ncu_launches_bench.csv", "r02_ncu_launches_bench.csv"), ("ncu
                  ("bench_cfg2.json", "r02_bench_1gpu.json"), ("bench_ref.json", "r02_bench_reference_arm.json")):
     if os.path.exists(os.path.join(final, src)):
         shutil.copy(os.path.join(final, src), os.path.join(P, dst))
+# every bench line of the other configs, one per line
+names = ["bench_cfg3.json", "bench_cfg4_cell1_100k.json", "bench_cfg4_100k.json", "bench_cfg4_500k.json",
+         "bench_cfg5_1000.json", "bench_cfg5_10000.json", "bench_cfg5_50000.json", "config1.json"]
+with open(os.path.join(P, "r02_configs.jsonl"), "w") as f:
+    for n in names:
+        path = os.path.join(final, n)
+        if os.path.exists(path) and os.path.getsize(path) > 2:
+            try:
+                d = json.loads(open(path).read().strip().split("\n")[-1])
+            except Exception:
+                continue
+            d["_file"] = n
+            f.write(json.dumps(d) + "\n")
+if os.path.exists(os.path.join(final, "latency.jsonl")):
+    shutil.copy(os.path.join(final, "latency.jsonl"), os.path.join(P, "r02_astar_latency.jsonl"))
 print("profiles written")
