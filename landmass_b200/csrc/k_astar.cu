@@ -35,6 +35,7 @@
 //     parallel.
 #include "k_astar_common.cuh"
 
+
 namespace lmb {
 
 using namespace astar_detail;
@@ -227,15 +228,8 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
     if (__all_sync(FULL, phase == PH_EXIT)) break;
 
     // ============ WALK (part 1): issue this iteration's back-pointer load early ============
-    // The whole 32-byte sector (four nodes) around the current node: a search that follows a
-    // corridor creates the path's nodes one after the other, so the next back-pointers are often
-    // in the same sector and several steps can be taken from one load.
-    uint4 w_lo = make_uint4(0u, 0u, 0u, 0u), w_hi = w_lo;
-    if (phase == PH_WALK) {
-      const uint4* sec = reinterpret_cast<const uint4*>(nodes + (w_node & ~3u));
-      w_lo = sec[0];
-      w_hi = sec[1];
-    }
+    uint2 w_one = make_uint2(0u, 0u);
+    if (phase == PH_WALK) w_one = nodes[w_node];
 
     // =============================== SEARCH: one pop ===============================
     if (phase == PH_SEARCH) {
@@ -522,43 +516,37 @@ k_astar(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounte
         }
       }
     } else if (phase == PH_WALK) {
-      // ============ WALK (part 2): consume the back-pointers loaded above ============
-      // (astar.rs:86-105) staged goal-first as (state, next state); up to four nodes per iteration
-      // while the chain stays inside the loaded sector
-#pragma unroll 1
-      for (int k = 0; k < 4; k++) {
-        const uint32_t wi = w_node & 3u;
-        const uint2 w_rec = wi == 0 ? make_uint2(w_lo.x, w_lo.y)
-                                    : (wi == 1 ? make_uint2(w_lo.z, w_lo.w)
-                                               : (wi == 2 ? make_uint2(w_hi.x, w_hi.y) : make_uint2(w_hi.z, w_hi.w)));
-        if (w_rec.x != ST_END) {
-          if (LAYOUT == 3)
-            nodes[n_nodes - 1 - w_pos] = make_uint2(w_rec.x, w_next);
-          else if (w_pos < stage_cap)
-            stage[w_pos] = make_uint2(w_rec.x, w_next);
-          w_pos++;
-        }
-        w_next = w_rec.x;
-        if (w_rec.y == LMB_NONE) {
-          // reached the Start node: the corridor has w_pos nodes; allocate it in the pool
-          phase = PH_FINISH;
-          if (w_pos > stage_cap) {
-            status = 6;  // cannot happen for a simple path (corridor longer than the staging area)
+      // ============ WALK (part 2): consume the back-pointer loaded above ============
+      // (astar.rs:86-105) staged goal-first as (state, next state), one node per warp iteration.
+      // (Measured in round 2 on the bench / on config 5 with 10 000 agents: this form 338.5 / 905 ms; round 1's
+      // form — the node's whole 32-byte sector, up to four steps per iteration — 337.4 / 950 ms; all 32 lanes
+      // walking one finished search at a time through a register window (warp_walk) 386.9 / 888 ms: 17 % fewer
+      // instructions, but the warp's other searches stand still during a walk whose every second step is a
+      // dependent HBM round trip.)
+      if (w_one.x != ST_END) {
+        if (LAYOUT == 3)
+          nodes[n_nodes - 1 - w_pos] = make_uint2(w_one.x, w_next);
+        else if (w_pos < stage_cap)
+          stage[w_pos] = make_uint2(w_one.x, w_next);
+        w_pos++;
+      }
+      w_next = w_one.x;
+      w_node = w_one.y;
+      if (w_one.y == LMB_NONE) {
+        // reached the Start node: the corridor has w_pos nodes; allocate it in the pool
+        phase = PH_FINISH;
+        if (w_pos > stage_cap) {
+          status = 6;  // cannot happen for a simple path (corridor longer than the staging area)
+        } else {
+          const unsigned long long off = atomicAdd(pool.cursor, (unsigned long long)w_pos);
+          if (off + w_pos > pool.capacity) {
+            status = 3;
           } else {
-            const unsigned long long off = atomicAdd(pool.cursor, (unsigned long long)w_pos);
-            if (off + w_pos > pool.capacity) {
-              status = 3;
-            } else {
-              success = 1;
-              path_off = (uint32_t)off;
-              path_len = w_pos;
-            }
+            success = 1;
+            path_off = (uint32_t)off;
+            path_len = w_pos;
           }
-          break;
         }
-        const bool same_sector = (w_rec.y >> 2) == (w_node >> 2);
-        w_node = w_rec.y;
-        if (!same_sector) break;
       }
     }
 

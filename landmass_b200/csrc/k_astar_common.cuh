@@ -392,6 +392,47 @@ __device__ __forceinline__ void restore_best(const AStarArena& arena, uint8_t* b
   }
 }
 
+// Follows the back-pointers of ONE finished search from its End node to the Start node (astar.rs:86-105) with
+// all 32 lanes of the warp: the chain is read through a 128-node window held in registers (four nodes per lane,
+// moved by shuffles); a dependent memory round trip is paid only when the chain leaves the window.  Calls
+// `stage(k, {state, next state})` on lane 0 for the k-th corridor node, goal side first (the End node itself is
+// not part of the corridor), and returns the number of corridor nodes.  `nodes` = the slot's node list
+// {state, prev}, allocated in 256-byte units (node_cap_window = node_cap rounded up to 32).
+template <class StageFn>
+__device__ __forceinline__ uint32_t warp_walk(const uint2* nodes, uint32_t node_cap_window, uint32_t goal_index,
+                                              uint32_t st_end, uint32_t lane, StageFn stage) {
+  uint32_t w_pos = 0, w_node = goal_index, w_next = st_end;
+  bool done = false;
+  while (!done) {
+    const uint32_t base = w_node & ~127u;
+    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+    const uint32_t i0 = base + 4u * lane;
+    if (i0 < node_cap_window) {
+      const uint4* sec = reinterpret_cast<const uint4*>(nodes + i0);
+      lo = __ldcg(sec);
+      hi = __ldcg(sec + 1);
+    }
+    for (;;) {
+      const uint32_t idx = w_node - base, wi = idx & 3u;
+      const uint32_t mx = wi == 0 ? lo.x : (wi == 1 ? lo.z : (wi == 2 ? hi.x : hi.z));
+      const uint32_t my = wi == 0 ? lo.y : (wi == 1 ? lo.w : (wi == 2 ? hi.y : hi.w));
+      const uint32_t rx = __shfl_sync(FULL, mx, idx >> 2), ry = __shfl_sync(FULL, my, idx >> 2);
+      if (rx != st_end) {
+        if (lane == 0) stage(w_pos, make_uint2(rx, w_next));
+        w_pos++;
+      }
+      w_next = rx;
+      if (ry == LMB_NONE) {
+        done = true;
+        break;
+      }
+      w_node = ry;
+      if ((ry & ~127u) != base) break;
+    }
+  }
+  return w_pos;
+}
+
 enum : uint32_t { PH_IDLE = 0, PH_SEARCH = 1, PH_WALK = 2, PH_FINISH = 3, PH_EXIT = 4 };
 
 

@@ -611,40 +611,12 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
     uint32_t w_pos = 0;
     if (status == 1 && goal_index != LMB_NONE) {
       __syncwarp();
-      uint32_t w_node = goal_index, w_next = ST_END;
-      bool done = false;
-      while (!done) {
-        const uint32_t base = w_node & ~127u;
-        uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
-        const uint32_t i0 = base + 4u * lane;
-        if (i0 < node_cap_window) {
-          const uint4* sec = reinterpret_cast<const uint4*>(nodes + i0);
-          lo = __ldcg(sec);
-          hi = __ldcg(sec + 1);
-        }
-        for (;;) {
-          const uint32_t idx = w_node - base, wi = idx & 3u;
-          const uint32_t mx = wi == 0 ? lo.x : (wi == 1 ? lo.z : (wi == 2 ? hi.x : hi.z));
-          const uint32_t my = wi == 0 ? lo.y : (wi == 1 ? lo.w : (wi == 2 ? hi.y : hi.w));
-          const uint32_t rx = __shfl_sync(FULL, mx, idx >> 2), ry = __shfl_sync(FULL, my, idx >> 2);
-          if (rx != ST_END) {
-            if (lane == 0) {
-              if (LAYOUT == 3)
-                nodes[n_nodes - 1u - w_pos] = make_uint2(rx, w_next);
-              else if (w_pos < stage_cap)
-                stage[w_pos] = make_uint2(rx, w_next);
-            }
-            w_pos++;
-          }
-          w_next = rx;
-          if (ry == LMB_NONE) {
-            done = true;
-            break;
-          }
-          w_node = ry;
-          if ((ry & ~127u) != base) break;
-        }
-      }
+      w_pos = warp_walk(nodes, node_cap_window, goal_index, ST_END, lane, [&](uint32_t k, uint2 pair) {
+        if (LAYOUT == 3)
+          nodes[n_nodes - 1u - k] = pair;
+        else if (k < stage_cap)
+          stage[k] = pair;
+      });
       if (w_pos > stage_cap) {
         status = 6;  // cannot happen for a simple path
       } else {
