@@ -374,6 +374,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="lmb_config.flags (kernel-shape test hooks)")
     ap.add_argument("--scratch-gb", type=float, default=0.0, help="A* arena byte budget (0 = auto)")
     ap.add_argument("--shape", type=int, default=0, help="lmb_config.astar_shape (launch-shape tuning hook)")
+    ap.add_argument("--slots", type=int, default=0, help="lmb_config.astar_slots: A* queries in flight (0 = auto)")
     ap.add_argument("--lib", default=None, help="path of an alternative liblandmass_b200.so (A/B of kernel variants)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -419,7 +420,7 @@ def main():
     n, ag, flat = w["n"], w["ag"], w["flat"]
     opts = synth.default_options()
     gpu = NativeBackend(max_agents=n, device=local_rank, flags=args.flags, astar_shape=args.shape,
-                        scratch_bytes=int(args.scratch_gb * (1 << 30)), lib_path=args.lib)
+                        scratch_bytes=int(args.scratch_gb * (1 << 30)), lib_path=args.lib, astar_slots=args.slots)
     gpu.navdata_upload(flat)
     if world > 1:
         # the library owns the collective: rank 0 makes the NCCL unique id, torch only ships the 128 bytes

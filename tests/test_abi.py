@@ -132,3 +132,45 @@ def test_error_paths_of_the_newer_entry_points():
     ran, original, fallback, fell_back = gpu.agent_avoidance_constraints(1)
     assert ran and original.shape[1] == 4 and len(original) >= 3
     gpu.close()
+
+
+@pytest.mark.gpu
+def test_error_paths_of_the_round_2_entry_points():
+    """lmb_step_sharded without a communicator, with too small a share, lmb_comm_init with a bad rank,
+    lmb_agents_integrate before a step, a step range outside the halo, null CSR arrays."""
+    import numpy as np
+
+    from landmass_b200 import synth
+
+    mesh = synth.grid_mesh(4, 4)
+    flat = synth.single_island_flat(mesh)
+    opts = synth.default_options()
+    gpu = _native.NativeBackend(max_agents=8)
+    gpu.navdata_upload(flat)
+    ag = synth.make_agents(mesh, 4)
+    gpu.agents_upload(ag, None)
+    with pytest.raises(_native.NativeError) as e:
+        gpu.agents_integrate(0.1)  # no step has produced velocities for these agents
+    assert e.value.status == _abi.ERR_INVALID_ARGUMENT
+    with pytest.raises(_native.NativeError) as e:
+        gpu.step_sharded(opts, 0.1, 4)
+    assert e.value.status == _abi.ERR_INVALID_ARGUMENT and "lmb_comm_init" in str(e.value)
+    with pytest.raises(_native.NativeError) as e:
+        gpu.comm_init(b"\0" * 128, 2, 2)  # rank out of range: refused before NCCL is touched
+    assert e.value.status == _abi.ERR_INVALID_ARGUMENT
+    gpu.comm_init(gpu.comm_unique_id(), 1, 0)
+    with pytest.raises(_native.NativeError) as e:
+        gpu.step_sharded(opts, 0.1, 3)  # this rank holds 4 agents
+    assert e.value.status == _abi.ERR_INVALID_ARGUMENT and "agents_per_rank" in str(e.value)
+    with pytest.raises(_native.NativeError) as e:
+        gpu.step_begin(opts, 0.1, 6, 3)  # [3, 7) does not fit 6 records: refused before anything is stepped
+    assert e.value.status == _abi.ERR_INVALID_ARGUMENT
+    out = None
+    gpu.step_sharded(opts, 0.1, 4)
+    gpu.agents_integrate(0.1)
+    moved = gpu.resident_positions()
+    out = gpu.agents_download()
+    np.testing.assert_array_equal(moved, (ag["position"] + out["desired_velocity"] * np.float32(0.1)).astype(np.float32))
+    t = gpu.step_timings()
+    assert t.astar_launch_kind in (1, 2, 3) and t.allgather_ms >= 0.0
+    gpu.close()
