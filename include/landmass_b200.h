@@ -240,6 +240,8 @@ typedef struct lmb_pathing_result {
 #define LMB_CONFIG_ASTAR_WARP_ONLY 128u    /* launch only the warp-per-query search kernel */
 #define LMB_CONFIG_ASTAR_NO_FOREST 256u    /* do not use the best_estimates-free layout of forest meshes */
 #define LMB_CONFIG_NO_L2_WINDOW 512u       /* do not pin the A* tables in L2 (access-policy window; A/B hook) */
+#define LMB_CONFIG_ASTAR_SMALL_HEAP 1024u  /* start with a 64-entry open list per query: forces the in-place spill,
+                                              its overflow (status 7) and the doubling retry at test sizes */
 
 typedef struct lmb_config {
   uint32_t struct_size;

@@ -850,6 +850,7 @@ uint32_t astar_resident_queries_per_sm(bool big_heap, uint32_t shape) {
   if (!big_heap && shape == 1) return 6 * 16 * (AT_THREADS / 32);
   if (!big_heap && shape == 2) return 3 * 32 * (AT_THREADS / 32);
   if (!big_heap && shape == 3) return 4 * 32 * (AT_THREADS / 32);
+  if (!big_heap && shape == 4) return 7 * 8 * (AT_THREADS / 32);
   return (big_heap ? 2 : 5) * 16 * (AT_THREADS / 32);
 }
 
@@ -911,6 +912,8 @@ uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQue
     LMB_ASTAR_LAUNCH_S(32, 32, 3, 2, 3);
   else if (arena.layout == 3 && k4 && shape == 3)
     LMB_ASTAR_LAUNCH_S(32, 26, 4, 2, 3);
+  else if (arena.layout == 3 && k4 && shape == 4)
+    LMB_ASTAR_LAUNCH_S(8, 56, 7, 2, 3);
   else
     LMB_ASTAR_LAUNCH(16, 40, 5);
 #undef LMB_ASTAR_LAUNCH

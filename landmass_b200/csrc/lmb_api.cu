@@ -681,6 +681,7 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
         ctx->arena_node_cap = std::max<uint32_t>(max_component + 64, d->n_region_numbers + 64);
         ctx->arena_heap_cap = AT_HEAP_SM + 1024;  // a tree's open list is its unexpanded branches: small (doubles on overflow)
       }
+      if (fl & LMB_CONFIG_ASTAR_SMALL_HEAP) ctx->arena_heap_cap = AT_HEAP_SM + 16;  // test hook: 64 entries
       ctx->big_heap = !forest;  // first guess: a wavefront; corrected from the first batch's open lists
     }
     ctx->arena = AStarArena{};

@@ -70,7 +70,8 @@ def test_constants_match_header():
                         ("LMB_CONFIG_ASTAR_THREAD_ONLY", _abi.CONFIG_ASTAR_THREAD_ONLY),
                         ("LMB_CONFIG_ASTAR_WARP_ONLY", _abi.CONFIG_ASTAR_WARP_ONLY),
                         ("LMB_CONFIG_ASTAR_NO_FOREST", _abi.CONFIG_ASTAR_NO_FOREST),
-                        ("LMB_CONFIG_NO_L2_WINDOW", _abi.CONFIG_NO_L2_WINDOW)]:
+                        ("LMB_CONFIG_NO_L2_WINDOW", _abi.CONFIG_NO_L2_WINDOW),
+                        ("LMB_CONFIG_ASTAR_SMALL_HEAP", _abi.CONFIG_ASTAR_SMALL_HEAP)]:
         m = re.search(rf"#define {name} (\d+)u", text)
         assert m and int(m.group(1)) == value, name
 

@@ -174,6 +174,31 @@ def test_dense_best_slot_reuse_and_arena_retry(capfd, kernel):
     assert err.count("arena:") >= 2 and "compact best" not in err
 
 
+@pytest.mark.parametrize("shape", [0, _abi.CONFIG_ASTAR_THREAD_ONLY, _abi.CONFIG_ASTAR_LARGE_SHAPES])
+@pytest.mark.parametrize("mesh_kind", ["grid", "maze", "forest"])
+def test_open_list_spill_overflow_and_retry(mesh_kind, shape, capfd):
+    """the spill region of a slot must hold heap_cap entries for the SMALLEST number of shared-memory
+    entries any launch shape keeps (the <16,40,5> shape wrote past a region sized for 48).  LMB_CONFIG_ASTAR_SMALL_HEAP
+    starts every query with a 64-entry open list, so that at test sizes the open lists spill in place, overflow
+    (status 7) and are re-run with doubled capacities — on an open grid several times over — through the warp
+    kernel, the small thread-per-query shapes and the large-batch shapes; results stay bit-exact."""
+    mesh = {"grid": lambda: synth.grid_mesh(64, 64), "maze": lambda: synth.loopy_maze_mesh(24, 40),
+            "forest": lambda: synth.maze_mesh(32)}[mesh_kind]()
+    flat = synth.single_island_flat(mesh)
+    gpu, cpu = backends(flat, astar_slots=96, flags=shape | _abi.CONFIG_DEBUG_LOG | _abi.CONFIG_ASTAR_SMALL_HEAP)
+    rng = np.random.Generator(np.random.PCG64(77))
+    nq = 600
+    sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+    ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+    g = assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 21)
+    assert g[0].all()
+    err = capfd.readouterr().err
+    if mesh_kind == "grid":
+        assert err.count("arena:") >= 3, err  # 64 -> 80 -> 112 -> ... entries
+    # and again on the grown arena (slot re-use after a spilled search)
+    assert_same_paths(gpu, cpu, sn[::-1].copy(), sp[::-1].copy(), en[::-1].copy(), ep[::-1].copy(), cap=1 << 21)
+
+
 def test_step_more_agents_than_slots_longest_first_order(kernel):
     """The step orders a batch longest-first from the previous frame's explored_nodes when it has
     more queries than slots.  The order must not change any result: every agent re-plans on
