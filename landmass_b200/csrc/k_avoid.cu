@@ -766,28 +766,32 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
         // row) instead of a cell_start pair per cell and a random sector per record (5.7 -> 4.8 ms per M agents).
         const uint32_t c0 = (uint32_t)cy * grid.nx + (uint32_t)cx0, c1 = (uint32_t)cy * grid.nx + (uint32_t)cx1;
         const uint32_t kb = grid.cell_start[c0], ke = grid.cell_start[c1 + 1];
-        for (uint32_t k = kb; k < ke; k++) {
-          const AvoidRecord r = grid.sorted_rec[k];
-          const uint32_t j = r.valid;  // the record's index (k_grid_fill)
-          if (j == gi) continue;
-          float dx = fsub(r.px, me.px), dy = fsub(r.py, me.py), dz = fsub(r.pz, me.pz);
-          float d2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
-          if (!(d2 <= neighbourhood_squared)) continue;
-          float nh = fadd(o.neighbourhood, r.radius);
-          if (!(d2 < fmul(nh, nh))) continue;
-          // insertion sort by (d2, j)
-          if (n_nb >= s.max_nb) {
-            overflow = true;
-            continue;
+        // Four candidates at a time: the first half of each record (position) is loaded for all four before any is
+        // used (independent loads in flight together); the second half (radius, index) only for the ~1 in 3 that
+        // passes the first distance test.
+        const float4* rec4 = reinterpret_cast<const float4*>(grid.sorted_rec);
+        for (uint32_t k0 = kb; k0 < ke; k0 += 4) {
+          float4 pa[4];
+#pragma unroll
+          for (uint32_t u = 0; u < 4; u++) pa[u] = __ldg(rec4 + 2 * (size_t)min(k0 + u, ke - 1u));
+#pragma unroll
+          for (uint32_t u = 0; u < 4; u++) {
+            if (k0 + u >= ke) continue;
+            float dx = fsub(pa[u].x, me.px), dy = fsub(pa[u].y, me.py), dz = fsub(pa[u].z, me.pz);
+            float d2 = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+            if (!(d2 <= neighbourhood_squared)) continue;
+            const float4 pb = __ldg(rec4 + 2 * (size_t)(k0 + u) + 1);  // {vy, radius, responsibility, index}
+            const uint32_t j = __float_as_uint(pb.w);                  // the record's index (k_grid_fill)
+            if (j == gi) continue;
+            float nh = fadd(o.neighbourhood, pb.y);
+            if (!(d2 < fmul(nh, nh))) continue;
+            // appended unsorted: the (d2, index) order is produced where it is consumed (the ORCA lines below)
+            if (n_nb >= s.max_nb) {
+              overflow = true;
+              continue;
+            }
+            nb_set(n_nb++, make_float2(d2, __uint_as_float(j)));
           }
-          uint32_t pos = n_nb++;
-          while (pos > 0) {
-            float2 q = nb_get(pos - 1);
-            if (q.x < d2 || (q.x == d2 && __float_as_uint(q.y) < j)) break;
-            nb_set(pos, q);
-            pos--;
-          }
-          nb_set(pos, make_float2(d2, __uint_as_float(j)));
         }
       }
     }
@@ -803,14 +807,7 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
       overflow = true;
       continue;
     }
-    uint32_t pos = n_nb++;
-    while (pos > n_agent_nb) {
-      float2 q = nb_get(pos - 1);
-      if (q.x < d2 || (q.x == d2 && (__float_as_uint(q.y) & 0x7fffffffu) < j)) break;
-      nb_set(pos, q);
-      pos--;
-    }
-    nb_set(pos, make_float2(d2, __uint_as_float(j | 0x80000000u)));
+    nb_set(n_nb++, make_float2(d2, __uint_as_float(j | 0x80000000u)));
   }
 
   // ---- obstacles: nav_mesh_borders_to_dodgy_obstacles (avoidance.rs:189-471) ----
@@ -1037,8 +1034,26 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
   }
   const uint32_t obstacle_line_count = n_lines;
   if (!overflow) {
+    // Neighbours in kdtree `within` order — agents by ascending (squared distance, index), then characters the
+    // same way (avoidance.rs:90-130) — by SELECTION: for every output position one pass over the unsorted list
+    // for the smallest key above the previous one.  n^2 independent loads instead of the n^2 / 4 DEPENDENT
+    // load-compare-store steps of an insertion sort in the HBM scratch (ncu, config 3: 31 % of the kernel's stall
+    // samples sat on that one load).  Keys are unique (distinct indices).
+    float last_d2 = -1.0f;
+    uint32_t last_j = 0;
     for (uint32_t k = 0; k < n_nb; k++) {
-      uint32_t j = __float_as_uint(nb_get(k).y);
+      const uint32_t pb = k < n_agent_nb ? 0u : n_agent_nb, pe = k < n_agent_nb ? n_agent_nb : n_nb;
+      if (k == n_agent_nb) last_d2 = -1.0f, last_j = 0;
+      float bd2 = F_INF;
+      uint32_t j = 0xffffffffu;
+      for (uint32_t m = pb; m < pe; m++) {
+        const float2 q = nb_get(m);
+        const uint32_t qj = __float_as_uint(q.y);
+        const bool after = q.x > last_d2 || (q.x == last_d2 && qj > last_j);
+        const bool better = q.x < bd2 || (q.x == bd2 && qj < j);
+        if (after && better) bd2 = q.x, j = qj;
+      }
+      last_d2 = bd2, last_j = j;
       const AvoidRecord r = (j & 0x80000000u) ? char_records[j & 0x7fffffffu] : records[j];
       DodgyAgent other{V2{r.px, r.py}, V2{r.vx, r.vy}, r.radius, r.responsibility};
       if (n_lines >= s.max_lines) {
