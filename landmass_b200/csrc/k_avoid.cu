@@ -1039,9 +1039,9 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
     // for the smallest key above the previous one.  n^2 independent loads instead of the n^2 / 4 DEPENDENT
     // load-compare-store steps of an insertion sort in the HBM scratch (ncu, config 3: 31 % of the kernel's stall
     // samples sat on that one load).  Keys are unique (distinct indices).
-    float last_d2 = -1.0f;
-    uint32_t last_j = 0;
-    for (uint32_t k = 0; k < n_nb; k++) {
+    // The record of neighbour k (a random 32-byte sector) is requested BEFORE the selection pass for neighbour
+    // k + 1 runs and used after it, so the pass hides the round trip.
+    auto select_next = [&](uint32_t k, float last_d2, uint32_t last_j, float& out_d2) -> uint32_t {
       const uint32_t pb = k < n_agent_nb ? 0u : n_agent_nb, pe = k < n_agent_nb ? n_agent_nb : n_nb;
       if (k == n_agent_nb) last_d2 = -1.0f, last_j = 0;
       float bd2 = F_INF;
@@ -1053,8 +1053,19 @@ k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_
         const bool better = q.x < bd2 || (q.x == bd2 && qj < j);
         if (after && better) bd2 = q.x, j = qj;
       }
-      last_d2 = bd2, last_j = j;
+      out_d2 = bd2;
+      return j;
+    };
+    float cur_d2 = -1.0f;
+    uint32_t cur_j = n_nb ? select_next(0, -1.0f, 0u, cur_d2) : 0u;
+    for (uint32_t k = 0; k < n_nb; k++) {
+      const uint32_t j = cur_j;
       const AvoidRecord r = (j & 0x80000000u) ? char_records[j & 0x7fffffffu] : records[j];
+      if (k + 1 < n_nb) {
+        float nd2;
+        cur_j = select_next(k + 1, cur_d2, j, nd2);
+        cur_d2 = nd2;
+      }
       DodgyAgent other{V2{r.px, r.py}, V2{r.vx, r.vy}, r.radius, r.responsibility};
       if (n_lines >= s.max_lines) {
         overflow = true;
