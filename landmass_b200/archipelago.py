@@ -291,15 +291,19 @@ class Archipelago:
         self._flat = None
         self._last_step_keys = []
         self._device_versions: dict[int, int] = {}
+        self._max_agents = max_agents
         if backend is None:
             from ._native import NativeBackend  # raises loudly if the CUDA library is missing
 
-            backend = NativeBackend(max_agents=max_agents,
+            # device slot = DenseSlotMap key index, and index 0 is the slot map's sentinel: one slot more than agents
+            backend = NativeBackend(max_agents=max_agents + 1,
                                     flags=_abi.CONFIG_NO_AVOIDANCE if no_avoidance else 0)
         self.backend = backend
 
     # --- agents / characters / islands (lib.rs:106-205) ---
     def add_agent(self, agent: Agent) -> Key:
+        if len(self.agents) >= self._max_agents:
+            raise ValueError(f"Archipelago was created for at most {self._max_agents} agents")
         return self.agents.insert(agent)
 
     def remove_agent(self, agent_id: Key):
@@ -540,12 +544,15 @@ class Archipelago:
         }
         out = self.backend.step(ag, ch, self.archipelago_options.to_abi(), float(delta_time))
 
+        link_keys = None
         for i, (key, a) in enumerate(items):
             a._current_desired_move = cs.from_landmass(out["desired_velocity"][i])
             a._state = AgentState(int(out["state"][i]))
             if out["reached_link_id"][i] != _abi.NONE:
+                if link_keys is None:  # AnimationLinkId of the reached link, like find_path's steps
+                    link_keys = {k.idx: k for k in self.nav_data.get_animation_link_ids()}
                 a._current_animation_link = ReachedAnimationLink(
-                    int(out["reached_link_id"][i]),
+                    link_keys.get(int(out["reached_link_id"][i]), int(out["reached_link_id"][i])),
                     cs.from_landmass(out["reached_link_start"][i]),
                     cs.from_landmass(out["reached_link_end"][i]))
             else:

@@ -12,6 +12,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <mutex>
 
 #include "lmb_context.h"
 
@@ -27,16 +28,26 @@ struct NcclApi {
   std::string error;
 };
 
+void load_nccl(NcclApi& api);
+
 NcclApi& nccl_api() {
   static NcclApi api;
-  if (api.handle || !api.error.empty()) return api;
+  static std::once_flag once;
+  std::call_once(once, [] { load_nccl(api); });
+  return api;
+}
+
+}  // namespace
+
+namespace {
+void load_nccl(NcclApi& api) {
   for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
     api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
     if (api.handle) break;
   }
   if (!api.handle) {
     api.error = std::string("cannot open libnccl.so.2: ") + dlerror();
-    return api;
+    return;
   }
   auto sym = [&](const char* n) -> void* {
     void* p = dlsym(api.handle, n);
@@ -49,7 +60,6 @@ NcclApi& nccl_api() {
   api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
   if (!api.error.empty()) api.handle = nullptr;
-  return api;
 }
 
 }  // namespace

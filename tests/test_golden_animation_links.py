@@ -112,7 +112,7 @@ def test_agent_can_use_animation_link(make_backend):  # lib_test.rs:1013-1123
     assert np.array_equal(agent.get_desired_velocity(), np.float32([0.0, 1.0]))
     assert not agent.is_using_animation_link()
     r = agent.reached_animation_link()
-    assert r is not None and r.link_id == link.idx
+    assert r is not None and r.link_id == link
     assert np.array_equal(r.start_point, np.float32([1.25, 1.9]))
     assert np.array_equal(r.end_point, np.float32([1.25, 3.1]))
     agent.start_animation_link()
