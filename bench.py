@@ -49,11 +49,11 @@ DT = 1.0 / 60.0
 ISLAND_PITCH = 640.0  # spacing of the per-GPU maze islands (a 256-room maze is 513 m wide)
 B_STEP = 240.0  # algorithmic bytes per steady agent-update
 # DRAM bytes per explored node of k_astar MEASURED ON THIS WORKLOAD AT THIS SIZE: ncu application replay of the
-# bench's own 100 000-query launch (dram__bytes_read.sum + dram__bytes_write.sum = 112.4 GB for 6.479 G explored
+# bench's own 100 000-query launch (dram__bytes_read.sum + dram__bytes_write.sum = 109.3 GB for 6.479 G explored
 # nodes) — profiles/r02_ncu_dram_bench.csv.  Only used for the other --config runs' `traffic`; config 2 reports
 # the measured launch total itself.
-NCU_DRAM_BYTES_PER_EXPLORED = 17.35
-NCU_DRAM_BYTES_BENCH_LAUNCH = 112_420_450_304
+NCU_DRAM_BYTES_PER_EXPLORED = 16.87
+NCU_DRAM_BYTES_BENCH_LAUNCH = 109_321_088_512
 NCU_SOURCE = "profiles/r02_ncu_dram_bench.csv"
 
 
@@ -586,7 +586,7 @@ def main():
                          "traffic": NCU_DRAM_BYTES_PER_EXPLORED * explored / args.steps,
                          "traffic_source": f"ncu dram__bytes_read+write of this workload's own k_astar launch at full "
                                            f"size ({NCU_SOURCE}: {NCU_DRAM_BYTES_BENCH_LAUNCH} B for 6.479e9 explored "
-                                           "nodes = 17.35 B per explored node) x explored nodes of this run",
+                                           "nodes = 16.87 B per explored node) x explored nodes of this run",
                          "algorithmic_bytes": astar_bytes, "peak_source": peak_src,
                          "note": "latency/issue-bound graph search: one dependent chain per query (pop -> records "
                                  "-> push), algorithmic bytes = 32/query + 8/corridor node + 96/explored node "

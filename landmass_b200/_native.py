@@ -307,6 +307,30 @@ class CBackend:
             return succ[:n], begin, kind[:k], pts[:k], link[:k]
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """The library dlopens "libnccl.so.2" and gets whichever copy the process already holds under that soname,
+    else the loader's search path.  In a Python process that later imports torch that must be the copy torch was
+    built against (the `nvidia-nccl` wheel: a system libnccl of another version under the same soname makes
+    `import torch` fail with an undefined symbol), so the wheel's copy — if there is one — is loaded first."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+        path = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(path):
+            C.CDLL(path, mode=C.RTLD_GLOBAL)
+            return
+
+
 class NativeBackend(CBackend):
     prefix = "lmb_"
 
@@ -355,11 +379,13 @@ class NativeBackend(CBackend):
 
     # library-owned halo exchange (lmb_comm.cu): NCCL opened by the library itself
     def comm_unique_id(self) -> bytes:
+        _preload_nccl()
         buf = (C.c_uint8 * 128)()
         self._check(self.lib.lmb_comm_unique_id(self.ctx, buf))
         return bytes(buf)
 
     def comm_init(self, unique_id: bytes, n_ranks: int, rank: int):
+        _preload_nccl()
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.lmb_comm_init(self.ctx, buf, n_ranks, rank))
 

@@ -138,9 +138,11 @@ if os.path.exists(a):
                 "`ncu --set full -k regex:k_avoidance|k_follow --launch-skip 4 --launch-count 1 python bench.py --config 3 "
                 "--steps 3 --warmup 2` (open field, 1 M agents, steady frame; scratch interleaved by agent, portal table).\n\n")
         f.write(table([("k_avoidance", a), ("k_follow", fo)]))
-        f.write("\nk_avoidance, top source lines by stall samples (`k_avoid.cu:769` = the insertion into the sorted "
-                "neighbour list, `lmb_device.cuh:30` = the first use of a gathered neighbour record):\n\n")
-        f.write(lines(a, os.path.join(objs, "r2f", "k_avoid.o"), "k_avoidance", "k_avoidance", 12))
+        f.write("\nk_avoidance, top source lines by stall samples (`lmb_device.cuh:29-32` = the first use of a gathered "
+                "neighbour record, `k_avoid.cu:1049-1054` = `select_next`, the scan of the candidate list in the agent's "
+                "interleaved scratch that yields the neighbours in (distance^2, index) order, `k_avoid.cu:53` = a `Strided` "
+                "scratch access):\n\n")
+        f.write(lines(a, os.path.join(objs, "final", "k_avoid.o"), "k_avoidance", "k_avoidance", 12))
 
 # ---- plain copies ----
 for src, dst in (("ncu_launches_bench.csv", "r02_ncu_launches_bench.csv"), ("ncu_dram_bench.csv", "r02_ncu_dram_bench.csv"),
@@ -163,3 +165,91 @@ with open(os.path.join(P, "r02_configs.jsonl"), "w") as f:
 if os.path.exists(os.path.join(final, "latency.jsonl")):
     shutil.copy(os.path.join(final, "latency.jsonl"), os.path.join(P, "r02_astar_latency.jsonl"))
 print("profiles written")
+
+
+# ---- index: profiles/r02_README.md ----
+def jload(name):
+    try:
+        return json.loads(open(os.path.join(P, name)).read().strip().split("\n")[-1])
+    except Exception:
+        return None
+
+
+def launch_shares():
+    """kernel -> (launches, total ms) from the ncu launch list (one row per launch and metric)"""
+    path = os.path.join(P, "r02_ncu_launches_bench.csv")
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    ki, vi, ui, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("Metric Name")
+    agg = {}
+    for r in rows[1:]:
+        if r[mi] != "gpu__time_duration.sum":
+            continue
+        name = r[ki].replace("void ", "").replace("lmb::", "")
+        name = name.split("(")[0] if not name.startswith("k_astar<") else name.split(">")[0] + ">"
+        v = float(r[vi].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ui], 1e-6)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    return agg
+
+
+b1, ref = jload("r02_bench_1gpu.json"), jload("r02_bench_reference_arm.json")
+multi = {n: jload(f"r02_bench_{n}gpu.json") for n in (2, 4, 8)}
+with open(os.path.join(P, "r02_README.md"), "w") as f:
+    f.write("# Round-2 profiles — index\n\nEverything here was produced on the pool's B200s by `scripts/r02_measure.sh` (one GPU) or by "
+            "the commands quoted\nin the file, and condensed by `scripts/make_r02_profiles.py` (this index included); numbers in "
+            "DESIGN.md cite these files.\n\n| file | what |\n|---|---|\n")
+    if b1:
+        pc = b1.get("parity_check", {})
+        f.write(f"| `r02_bench_1gpu.json` | `python bench.py` (config 2, the headline): {b1['ms_per_step']:.1f} ms per step = "
+                f"{b1['value']:.0f} agent-updates/s, e2e {b1['e2e']['value']:.0f}/s, roofline frac {b1['roofline']['frac']:.3f}, "
+                f"`parity_check` {pc.get('n')} agents ok = {pc.get('ok')}, clocks {b1['clocks']['sm_mhz']:.0f} MHz, throttle reasons "
+                f"{b1['clocks']['reasons']} |\n")
+    if ref:
+        ac = ref.get("all_cores") or {}
+        f.write(f"| `r02_bench_reference_arm.json` | `python bench.py --impl reference`: {ref['value']:.1f} agent-updates/s on one core "
+                f"(the reference is single-threaded), {ac.get('value', 0):.0f}/s with one oracle process per host core |\n")
+    for n in (2, 4, 8):
+        d = multi[n]
+        if d and b1:
+            f.write(f"| `r02_bench_{n}gpu.json` | `torchrun --nproc-per-node {n} bench.py --gpus {n}`: {d['ms_per_step']:.1f} ms per step = "
+                    f"{d['value']:.0f} agent-updates/s ({d['value'] / b1['value']:.2f}x the 1-GPU line), library-owned "
+                    f"`ncclAllGather`, `allgather_ms` {d.get('phase_ms', {}).get('allgather', 0):.2f} |\n")
+    f.write("| `r02_bench_2gpu_config4.json` | `bench.py --gpus 2 --config 4 --agents 250000`: the shared 64-island world, moving agents |\n"
+            "| `r02_configs.jsonl` | `bench.py --config 3 / 4 / 5` lines and config 1 (`scripts/run_configs.py 1`), one JSON per line "
+            "(`_file` names the run) |\n"
+            "| `r02_astar_latency.jsonl` | `scripts/astar_latency.py maze field tiled`: microseconds per explored node of the longest "
+            "search per kernel family, 1 ... 2368 queries |\n"
+            "| `r02_ncu_launches_bench.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none -c 400` of `bench.py --steps 2 "
+            "--warmup 1`: every kernel launch of the bench (cold-cache, serialised: compare shares) |\n")
+    try:
+        vals = {}
+        for r in csv.reader(l for l in open(os.path.join(P, "r02_ncu_dram_bench.csv")) if l.startswith('"')):
+            if r[0] != "ID":
+                vals[r[-3]] = float(r[-1].replace(",", ""))
+        rd, wr = vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"]
+        f.write(f"| `r02_ncu_dram_bench.csv` | DRAM bytes of the bench's own 100 000-query `k_astar` launch (ncu application replay): "
+                f"{rd / 1e9:.1f} GB read + {wr / 1e9:.1f} GB written = {(rd + wr) / 6.479e9:.1f} B per explored node |\n")
+    except Exception as e:  # noqa: BLE001
+        f.write(f"| `r02_ncu_dram_bench.csv` | DRAM bytes of the bench-size `k_astar` launch ({e}) |\n")
+    f.write("| `r02_ncu_astar_loaded.md`, `_raw.csv` | `ncu --set full` of a fully loaded `k_astar<16,40,5,quad,forest,SIMPLE>` launch "
+            "on a capturable arena, with the per-line stall table |\n"
+            "| `r02_ncu_astar_single.md` | `ncu --set full` of ONE search: warp kernel before / after `cp.async` staging, thread kernel, "
+            "open field; the false scoreboard wait |\n"
+            "| `r02_ncu_avoid_follow_cfg3.md` | `ncu --set full` of `k_avoidance` and `k_follow` at config 3 (1 M agents) |\n")
+    try:
+        agg = launch_shares()
+        total = sum(v[1] for v in agg.values())
+        top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        f.write("\nShare of the bench step by kernel (from `r02_ncu_launches_bench.csv`; the un-profiled run reports `phase_ms.astar` = "
+                f"{b1['phase_ms']['astar']:.1f} of {b1['ms_per_step']:.1f} ms = {100 * b1['phase_ms']['astar'] / b1['ms_per_step']:.1f} %):\n\n"
+                "| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+        for name, (cnt, ms) in top[:8]:
+            f.write(f"| `{name}` | {cnt} | {ms:.1f} | {100 * ms / total:.2f} % |\n")
+        rest = top[8:]
+        f.write(f"| everything else ({sum(v[0] for _, v in rest)} launches of {len(rest)} kernels) | | {sum(v[1] for _, v in rest):.1f} | "
+                f"{100 * sum(v[1] for _, v in rest) / total:.2f} % |\n")
+    except Exception as e:  # noqa: BLE001
+        f.write(f"\n(launch shares unavailable: {e})\n")
+print("index written")
