@@ -242,6 +242,7 @@ typedef struct lmb_pathing_result {
 #define LMB_CONFIG_NO_L2_WINDOW 512u       /* do not pin the A* tables in L2 (access-policy window; A/B hook) */
 #define LMB_CONFIG_ASTAR_SMALL_HEAP 1024u  /* start with a 64-entry open list per query: forces the in-place spill,
                                               its overflow (status 7) and the doubling retry at test sizes */
+#define LMB_CONFIG_ASTAR_NO_PAIR 2048u     /* warp-per-query launches never use a second (heap) warp per query */
 
 typedef struct lmb_config {
   uint32_t struct_size;
@@ -269,7 +270,8 @@ typedef struct lmb_step_timings {
   uint64_t explored_nodes;    /* sum over this step's queries */
   uint64_t path_nodes;        /* sum of corridor lengths produced this step */
   float allgather_ms;         /* lmb_step_sharded: device time of the ncclAllGather (0 otherwise) */
-  uint32_t astar_launch_kind; /* last A* launch: 0 none, 1 thread-per-query, 2 warp-per-query, 3 both */
+  uint32_t astar_launch_kind; /* A* launches of the step, or-ed: 1 thread-per-query, 2 warp-per-query,
+                                 4 warp pair per query (search warp + heap warp) */
 } lmb_step_timings;
 
 typedef struct lmb_ctx lmb_ctx;

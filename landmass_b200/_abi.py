@@ -49,6 +49,7 @@ CONFIG_ASTAR_WARP_ONLY = 128
 CONFIG_ASTAR_NO_FOREST = 256
 CONFIG_NO_L2_WINDOW = 512
 CONFIG_ASTAR_SMALL_HEAP = 1024
+CONFIG_ASTAR_NO_PAIR = 2048
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)

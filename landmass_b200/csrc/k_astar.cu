@@ -854,9 +854,9 @@ uint32_t astar_resident_queries_per_sm(bool big_heap, uint32_t shape) {
   return (big_heap ? 2 : 5) * 16 * (AT_THREADS / 32);
 }
 
-void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                       AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
-                       cudaStream_t stream);  // k_astar_warp.cu
+uint32_t launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                           AStarCounters* counters, const uint32_t* type_raw, bool simple, bool pair, uint32_t sm_count,
+                           cudaStream_t stream);  // k_astar_warp.cu
 
 uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                       AStarCounters* counters, const uint32_t* type_raw, bool big_heap, uint32_t flags,
@@ -896,8 +896,8 @@ uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQue
   const bool warp = (flags & LMB_CONFIG_ASTAR_WARP_ONLY) ||
                     (!force_large && !(flags & LMB_CONFIG_ASTAR_THREAD_ONLY) && q.n <= warp_max);
   if (warp) {
-    kind = 2;
-    launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, (uint32_t)sm_count, stream);
+    kind = launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, !(flags & LMB_CONFIG_ASTAR_NO_PAIR),
+                             (uint32_t)sm_count, stream) == 3u ? 4u : 2u;
   } else if (!force_large && q.n <= 8u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(1, 1536, 2);  // few queries: one per warp, the whole open list on chip
   else if (!force_large && q.n <= 32u * (uint32_t)sm_count)

@@ -56,6 +56,7 @@ struct WarpHeap {
   uint32_t len;
   uint32_t lane;
   uint32_t lv_m, lv_o;  // level / offset of this lane's node inside a 31-node (five-level) subtree
+  uint32_t anc_one, anc_zero;
 
   __device__ __forceinline__ void init(uint4* sm_, uint4* gm_, uint32_t lane_) {
     sm = sm_;
@@ -64,6 +65,15 @@ struct WarpHeap {
     lane = lane_;
     lv_m = 31u - __clz(lane_ + 1u);
     lv_o = lane_ + 1u - (1u << lv_m);
+    // ancestors of this lane's node inside the subtree, split by the winner bit that leads towards the node
+    anc_one = anc_zero = 0;
+    for (uint32_t j = 0; j < lv_m && lane_ < 31u; j++) {
+      const uint32_t a = (1u << j) - 1u + (lv_o >> (lv_m - j));
+      if ((lv_o >> (lv_m - j - 1u)) & 1u)
+        anc_one |= 1u << a;
+      else
+        anc_zero |= 1u << a;
+    }
   }
   // SP = false: every index the operation can reach is < HS (the caller checks the length once, uniformly), so
   // an access is one shared-memory instruction without a branch; SP = true adds the in-place spill.
@@ -117,18 +127,23 @@ struct WarpHeap {
       const bool two = (lane < 31u) & (2u * g + 2u < end);
       const uint32_t ia = two ? 2u * g + 1u : 0u;
       const uint4 a = ld<SP>(ia), b = ld<SP>(ia + 1u);
-      const uint32_t bits = __ballot_sync(FULL, two & rev_le4(a, b));  // child += (a <= b): the right child wins
-      uint32_t t = 0;
-#pragma unroll
-      for (int lv = 0; lv < 5; lv++) {
-        if (2u * pos + 2u < end) {
-          const uint32_t r = (bits >> t) & 1u;
-          t = 2u * t + 1u + r;
-          pos = 2u * pos + 1u + r;
-          d++;
-          if (lane == d) my_pos = pos;
-        }
-      }
+      const bool right = two & rev_le4(a, b);  // child += (a <= b): the right child wins
+      const uint32_t bits = __ballot_sync(FULL, right);
+      // A node lies on the path when every ancestor's bit points its way (a node with two children has ancestors
+      // with two children: the heap is a complete tree), so each lane decides for itself and the path is read off
+      // a second ballot: one lane per level, levels 0 .. nl-1.
+      const bool onp = two & ((bits & anc_one) == anc_one) & ((bits & anc_zero) == 0u);
+      const uint32_t pm = __ballot_sync(FULL, onp);
+      const uint32_t nl = __popc(pm);
+      const uint32_t c = 2u * g + 1u + (right ? 1u : 0u);  // the child this node sends the hole to
+      // depth d + m + 1 of the path = the choice of the on-path node of level m; lane (d + m + 1) keeps it
+      const uint32_t m = lane - d - 1u, mc = m < 4u ? m : 4u;
+      const uint32_t level = ((1u << (1u << mc)) - 1u) << ((1u << mc) - 1u);
+      const uint32_t src = (uint32_t)__ffs(pm & level) - 1u;
+      const uint32_t v = __shfl_sync(FULL, c, src & 31u);
+      if (m < nl) my_pos = v;
+      pos = __shfl_sync(FULL, c, 31u - __clz(pm));
+      d += nl;
     }
     if (2u * pos + 2u == end) {  // a single child at the bottom
       pos = 2u * pos + 1u;
@@ -181,6 +196,11 @@ __device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -227,6 +247,202 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
   return m;
 }
 
+// ---- the open list as the search sees it ----------------------------------------------------------------
+// PAIR = false: the warp that runs the search also owns the heap (WarpHeap).
+// PAIR = true: a second warp — the heap warp — owns it, and the two take turns through a mailbox in shared
+// memory and one named barrier.  An expansion's chain pop -> records -> costs -> pushes is serial for one
+// warp (~340 dependent-ish instructions per explored node, issue slots 15 % busy); but the pop needs nothing
+// from the expansion and the expansion needs only the root's identity, so with two warps they run side by
+// side: the heap warp publishes the root and pops it while the search warp expands it; the search warp hands
+// the accepted successors over as one batch and the heap warp pushes them in order.  Same heap operations in
+// the same order as the single-warp kernel, hence the same corridors.
+constexpr uint32_t PAIR_BATCH = 48;
+enum : uint32_t { BOX_MORE = 1u, BOX_STOP = 2u, BOX_EXIT = 4u };
+struct __align__(16) PairBox {
+  uint4 e[PAIR_BATCH];  // entries to push, in order
+  uint4 root;           // the root after the pushes (the entry the heap warp then pops)
+  uint32_t n, flags;    // batch size; MORE: the expansion goes on, no pop yet; STOP: the query is over; EXIT
+  uint32_t len, pad;    // open-list length after the pushes
+  uint32_t rslot;       // record-cache slot that holds the root's records, or LMB_NONE
+  uint32_t next_len;    // open-list length before the pushes (after the pop) ...
+  uint32_t pad2[2];
+  uint4 next;           // ... and its root then: what a pushed entry has to beat to be the next root
+};
+// The search warp of a pair has no pop to hide the L2 round trip of the root's records behind, so the records are
+// fetched a step ahead (cp.async into staging slots, like the staging of the single-warp kernel), by whichever
+// warp is idle at the time:
+//   * the heap warp knows the root-to-be as soon as its pop ends — a whole expansion ahead — and fetches that
+//     state's records into slot 0 / 1 (alternating: the search warp may be reading the other);
+//   * the search warp, idle while its batch is being pushed, checks whether one of the entries is about to take
+//     the root (sift_up passes every ancestor the entry is not <= to) and fetches that one into slot 2.
+// The heap warp publishes the slot with the root.  Records are immutable; anything else (special states, CSR ids,
+// a wrong guess) is a miss and the search warp fetches and waits as before.
+constexpr uint32_t REC_CACHE = 3;
+struct __align__(16) RecSlot {
+  LaneStage lane[32];
+};
+__device__ __forceinline__ void pair_sync(uint32_t id) {
+  __syncwarp();
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+template <uint32_t HS, bool PAIR>
+struct OpenList;
+
+template <uint32_t HS>
+struct OpenList<HS, false> {
+  WarpHeap<HS> heap;
+  __device__ __forceinline__ void init(uint4* sm, uint4* gm, uint32_t lane, PairBox*, uint32_t) { heap.init(sm, gm, lane); }
+  __device__ __forceinline__ void reset() { heap.len = 0; }
+  __device__ __forceinline__ uint32_t len() const { return heap.len; }
+  template <class F>
+  __device__ __forceinline__ bool peek(uint32_t& s, F&&) {
+    if (heap.len == 0) return false;
+    s = heap.sm[0].w;
+    return true;
+  }
+  __device__ __forceinline__ uint4 take() { return heap.pop(); }
+  __device__ __forceinline__ void push(const uint4& e) { heap.push(e); }
+  // the accepted lanes' entries in ascending lane order; entry k gets node index base + k
+  __device__ __forceinline__ void push_lanes(bool, uint32_t amask, uint32_t, float nc, float es, uint32_t state,
+                                             uint32_t base) {
+    uint32_t m = amask, k = 0;
+    while (m) {
+      const uint32_t j = (uint32_t)__ffs(m) - 1u;
+      m &= m - 1u;
+      const uint32_t s2 = __shfl_sync(FULL, state, j);
+      const float e2 = __shfl_sync(FULL, es, j), c2 = __shfl_sync(FULL, nc, j);
+      heap.push(make_uint4(__float_as_uint(c2), __float_as_uint(e2), base + k, s2));
+      k++;
+    }
+  }
+  __device__ __forceinline__ void stop() {}
+  __device__ __forceinline__ void exit() {}
+};
+
+template <uint32_t HS>
+struct OpenList<HS, true> {  // the search warp's end of the mailbox
+  PairBox* box;
+  uint32_t id, lane, n, len_x;
+  uint4 root;
+  uint32_t rslot;
+  __device__ __forceinline__ void init(uint4*, uint4*, uint32_t lane_, PairBox* box_, uint32_t id_) {
+    box = box_, id = id_, lane = lane_, n = 0, len_x = 0;
+  }
+  __device__ __forceinline__ void reset() { n = 0, len_x = 0; }
+  __device__ __forceinline__ uint32_t len() const { return len_x + n; }
+  __device__ __forceinline__ void flush(uint32_t flags) {
+    __syncwarp();
+    if (lane == 0) box->n = n, box->flags = flags;
+    pair_sync(id);  // the heap warp takes the batch ...
+    pair_sync(id);  // ... has pushed it, and (unless MORE) has published the root it is popping now
+    len_x += n;
+    n = 0;
+  }
+  // `idle(box, n)` runs while the heap warp pushes the n entries just handed over
+  template <class F>
+  __device__ __forceinline__ bool peek(uint32_t& s, F&& idle) {
+    __syncwarp();
+    if (lane == 0) box->n = n, box->flags = 0;
+    pair_sync(id);
+    idle(box, n);
+    pair_sync(id);
+    n = 0;
+    root = box->root;
+    rslot = box->rslot;
+    const uint32_t l = box->len;
+    len_x = l ? l - 1u : 0u;
+    s = root.w;
+    return l != 0;
+  }
+  __device__ __forceinline__ uint4 take() { return root; }
+  __device__ __forceinline__ void push(const uint4& e) {
+    if (n == PAIR_BATCH) flush(BOX_MORE);
+    if (lane == 0) box->e[n] = e;
+    n++;
+  }
+  __device__ __forceinline__ void push_lanes(bool acc, uint32_t amask, uint32_t rank, float nc, float es, uint32_t state,
+                                             uint32_t base) {
+    const uint32_t cnt = __popc(amask);
+    if (n + cnt > PAIR_BATCH) flush(BOX_MORE);
+    if (acc) box->e[n + rank] = make_uint4(__float_as_uint(nc), __float_as_uint(es), base + rank, state);
+    n += cnt;
+  }
+  __device__ __forceinline__ void signal(uint32_t flags) {
+    __syncwarp();
+    if (lane == 0) box->n = 0, box->flags = flags;
+    pair_sync(id);
+    n = 0, len_x = 0;
+  }
+  __device__ __forceinline__ void stop() { signal(BOX_STOP); }
+  __device__ __forceinline__ void exit() { signal(BOX_EXIT); }
+};
+
+// the records of padded-id state `st` (its polygon's records and its row of the distance table) -> a staging
+// slot; lanes beyond the polygon's records copy its last one again (same line: no traffic) and drop out at the
+// `e < cnt` test of the expansion: no divergent branch around the copies
+struct RecSource {
+  const EdgeRec* recs;
+  const float* edge_dist;
+  uint32_t kshift, n_ids;
+};
+__device__ __forceinline__ void issue_records(LaneStage* dst, const RecSource& src, uint32_t st, uint32_t lane) {
+  const uint32_t kmask = (1u << src.kshift) - 1u;
+  const uint32_t le = lane < kmask + 1u ? lane : kmask;
+  const EdgeRec* rp = src.recs + (st & ~kmask) + le;
+  cp_async_16(&dst[lane].a, rp);
+  cp_async_4(&dst[lane].info, &rp->info);
+  cp_async_4(&dst[lane].dist, src.edge_dist + ((size_t)st << src.kshift) + le);
+}
+
+// The heap warp of a pair: pushes the batches it is handed, publishes the root, pops it — and keeps the record
+// cache (REC_CACHE) a node ahead of the search warp.
+template <uint32_t HS>
+__device__ __forceinline__ void heap_warp_loop(uint4* sm, uint4* gm, PairBox* box, uint32_t id, uint32_t lane,
+                                               const RecSource src, RecSlot* cache) {
+  WarpHeap<HS> heap;
+  heap.init(sm, gm, lane);
+  const bool pf = src.kshift != 0;  // padded ids: a state's records are one aligned run
+  uint32_t a_state = LMB_NONE, a_slot = LMB_NONE;  // the root-to-be whose records were fetched, and where to
+  uint32_t root_slot = LMB_NONE;                   // the slot named for the current root (being read)
+  if (lane == 0) box->next_len = 0;
+  for (;;) {
+    pair_sync(id);
+    const uint32_t n = box->n, flags = box->flags;
+    if (flags & BOX_EXIT) break;
+    if (flags & BOX_STOP) {
+      heap.len = 0;
+      if (lane == 0) box->next_len = 0;
+      continue;
+    }
+    for (uint32_t k = 0; k < n; k++) heap.push(box->e[k]);
+    const bool more = flags & BOX_MORE;
+    if (!more) {
+      const uint4 root = heap.sm[0];
+      root_slot = (heap.len != 0 && root.w == a_state) ? a_slot : LMB_NONE;
+      if (root_slot != LMB_NONE) cp_async_wait_all();  // the fetch is complete before the slot is named
+      if (lane == 0) box->root = root, box->len = heap.len, box->rslot = root_slot;
+    }
+    pair_sync(id);
+    if (!more && heap.len != 0) {
+      heap.pop();
+      if (pf && heap.len != 0) {
+        const uint32_t a = heap.sm[0].w;  // the next root unless a successor of this expansion beats it
+        if (a >= src.n_ids) {
+          a_state = a_slot = LMB_NONE;
+        } else if (a != a_state || a_slot == LMB_NONE) {
+          a_state = a;
+          a_slot = root_slot == LMB_NONE ? 0u : root_slot ^ 1u;
+          cp_async_wait_all();  // an earlier fetch into that slot that was never named (a node old: no wait in practice)
+          issue_records(cache[a_slot].lane, src, a, lane);
+        }
+      }
+    }
+    if (lane == 0) box->next = heap.sm[0], box->next_len = heap.len;
+  }
+  cp_async_wait_all();
+}
+
 // key under which two states collide physically in a layout's table (never for the dense array)
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t collision_key(const BestStore<LAYOUT>&, uint32_t st, uint32_t lane) {
@@ -256,20 +472,31 @@ __device__ __forceinline__ bool needs_chain<2>(const BestStore<2>&, uint32_t st,
 
 }  // namespace
 
-template <uint32_t HS, uint32_t WPB, uint32_t BPS, int LAYOUT, bool SIMPLE>
-__global__ void __launch_bounds__(WPB * 32, BPS)
+template <uint32_t HS, uint32_t WPB, uint32_t BPS, int LAYOUT, bool SIMPLE, bool PAIR>
+__global__ void __launch_bounds__(WPB * (PAIR ? 64 : 32), BPS)
 k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarCounters* counters,
              const uint32_t* __restrict__ type_raw) {
-  extern __shared__ uint4 s_heap[];  // [WPB][HS] open lists, then [WPB] WarpStage
+  extern __shared__ uint4 s_heap[];  // [WPB][HS] open lists, [WPB] WarpStage, then (PAIR) [WPB] PairBox, [WPB][REC_CACHE] RecSlot
   __shared__ float s_cost[LMB_MAX_TYPES];
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  for (uint32_t t = threadIdx.x; t < nav.n_types; t += WPB * 32) s_cost[t] = nav.type_cost[t];
+  constexpr uint32_t THREADS = WPB * (PAIR ? 64 : 32);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = PAIR ? threadIdx.x >> 6 : threadIdx.x >> 5;  // the query unit inside the block
+  for (uint32_t t = threadIdx.x; t < nav.n_types; t += THREADS) s_cost[t] = nav.type_cost[t];
   __syncthreads();
   const uint32_t slot = blockIdx.x * WPB + warp;
   if (slot >= arena.n_slots) return;
 
   typedef typename BestStore<LAYOUT>::Raw BestRaw;
   uint8_t* const slot_base = arena.base + (size_t)slot * arena.slot_stride;
+  WarpStage* const stage_w = reinterpret_cast<WarpStage*>(s_heap + (size_t)WPB * HS) + warp;
+  PairBox* const box = reinterpret_cast<PairBox*>(reinterpret_cast<WarpStage*>(s_heap + (size_t)WPB * HS) + WPB) + warp;
+  RecSlot* const cache = reinterpret_cast<RecSlot*>(reinterpret_cast<PairBox*>(reinterpret_cast<WarpStage*>(s_heap + (size_t)WPB * HS) + WPB) + WPB) +
+                         (size_t)warp * REC_CACHE;
+  if (PAIR && ((threadIdx.x >> 5) & 1u)) {
+    heap_warp_loop<HS>(s_heap + (size_t)warp * HS, reinterpret_cast<uint4*>(slot_base + arena.heap_offset), box, 1u + warp,
+                       lane, RecSource{nav.edges, nav.edge_dist, arena.kshift, arena.n_ids}, cache);
+    return;
+  }
   BestStore<LAYOUT> bs;
   bs.init(slot_base, arena);
   uint2* const nodes = reinterpret_cast<uint2*>(slot_base + arena.nodes_offset);  // {state, prev}
@@ -277,9 +504,8 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
   const uint32_t stage_cap =
       LAYOUT == 3 ? 0xffffffffu
                   : (LAYOUT == 1 ? (arena.n_ids >> arena.kshift) : (LAYOUT == 2 ? arena.hash_cap : arena.n_states / 2));
-  WarpHeap<HS> heap;
-  heap.init(s_heap + (size_t)warp * HS, reinterpret_cast<uint4*>(slot_base + arena.heap_offset), lane);
-  WarpStage* const stage_w = reinterpret_cast<WarpStage*>(s_heap + (size_t)WPB * HS) + warp;
+  OpenList<HS, PAIR> heap;
+  heap.init(s_heap + (size_t)warp * HS, reinterpret_cast<uint4*>(slot_base + arena.heap_offset), lane, box, 1u + warp);
   LaneStage* const stage_l = stage_w->lane + lane;
 
   const EdgeRec* __restrict__ recs = nav.edges;
@@ -292,6 +518,7 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
   const uint32_t ST_START = arena.n_ids + nav.n_links;
   const uint32_t ST_END = ST_START + 1;
   const uint32_t lt = lanemask_lt();
+  const RecSource rec_src{recs, nav.edge_dist, kshift, arena.n_ids};
 
   for (;;) {
     uint32_t qi = 0;
@@ -376,15 +603,15 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
     uint32_t n_nodes = 0, explored = 0, hmax = 0, ovf_total = 0;
     uint32_t status = 1, success = 0, path_off = 0, path_len = 0;
     uint32_t goal_index = LMB_NONE;
-    heap.len = 0;
+    heap.reset();
     ovf_clear(bs);
 
     // try_add_node of a special state (Start, End, off-mesh link): the same work on every lane
     auto push_special = [&](uint32_t s2, float ncost, float est, uint32_t prev) {
       const BestRaw raw = bs.probe(s2);
       if (bs.value(s2, raw) <= est) return;
-      if (n_nodes >= node_cap || heap.len >= heap_cap) {
-        status = heap.len >= heap_cap ? 7u : 2u;
+      if (n_nodes >= node_cap || heap.len() >= heap_cap) {
+        status = heap.len() >= heap_cap ? 7u : 2u;
         return;
       }
       uint32_t ok = 1;
@@ -402,7 +629,7 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
       }
       heap.push(make_uint4(__float_as_uint(ncost), __float_as_uint(est), n_nodes, s2));
       n_nodes++;
-      hmax = max(hmax, heap.len);
+      hmax = max(hmax, heap.len());
     };
 
     if (connected) {
@@ -411,9 +638,27 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
     }
 
     // =========================================== search ===========================================
-    while (status == 1 && heap.len != 0) {
+    while (status == 1) {
       // ---- peek the root, issue this expansion's loads, then pop ----
-      const uint32_t s = heap.sm[0].w;
+      uint32_t s = 0;
+      uint32_t x_cand = LMB_NONE;  // (pair) the entry handed over that is about to take the root: records -> slot 2
+      auto idle = [&](const PairBox* bx, uint32_t n_batch) {
+        if (!kshift || n_batch == 0) return;
+        uint4 ref = bx->next;
+        bool have = bx->next_len != 0;
+        for (uint32_t k = 0; k < n_batch; k++) {
+          const uint4 e = bx->e[k];
+          if (!have || !rev_le4(e, ref)) ref = e, have = true, x_cand = e.w;
+        }
+        if (x_cand >= ST_LINK0) {
+          x_cand = LMB_NONE;
+          return;
+        }
+        cp_async_wait_all();  // the previous fetch into this slot
+        issue_records(cache[2].lane, rec_src, x_cand, lane);
+        cp_async_commit();
+      };
+      if (!heap.peek(s, idle)) break;
       const bool is_edge = s < ST_LINK0;
       const bool preloaded = is_edge && kshift != 0;
       EdgeRec r;
@@ -423,31 +668,55 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
       float dtab = 0.0f;
       uint32_t first = 0, cnt = 0;
       __syncwarp();  // nobody still reads the previous expansion's staging slots
-      if (LAYOUT != 3 && lane == 0) stage_root_probe<LAYOUT>(bs, s, &stage_w->root);
-      if (is_edge) {
-        if (kshift) {
+      const LaneStage* rs = stage_w->lane;  // where the root's records are staged
+      if constexpr (PAIR) {
+        // records: in the slot the heap warp names (fetched a node ahead, complete), else fetched now
+        bool fetched = false;
+        if (LAYOUT != 3) {
+          if (lane == 0) stage_root_probe<LAYOUT>(bs, s, &stage_w->root);
+          fetched = true;
+        }
+        if (preloaded) {
           first = s & ~kmask;
           cnt = kmask + 1u;
-          // lanes beyond the polygon's records copy its last one again (same line: no traffic) and drop out at
-          // the `e < cnt` test: no divergent branch around the copies
-          const uint32_t le = lane < cnt ? lane : cnt - 1u;
-          const EdgeRec* rp = recs + first + le;
-          cp_async_16(&stage_l->a, rp);
-          cp_async_4(&stage_l->info, &rp->info);
-          cp_async_4(&stage_l->dist, nav.edge_dist + ((size_t)s << kshift) + le);
-        } else {
+          if (s == x_cand) {
+            rs = cache[2].lane;
+            fetched = true;
+          } else if (heap.rslot != LMB_NONE) {
+            rs = cache[heap.rslot].lane;
+          } else {
+            issue_records(stage_w->lane, rec_src, s, lane);
+            fetched = true;
+          }
+        } else if (is_edge) {
           self = ld_rec(recs + s);
         }
+        if (fetched) cp_async_wait_all();
+      } else {
+        if (LAYOUT != 3 && lane == 0) stage_root_probe<LAYOUT>(bs, s, &stage_w->root);
+        if (is_edge) {
+          if (kshift) {
+            first = s & ~kmask;
+            cnt = kmask + 1u;
+            issue_records(stage_w->lane, rec_src, s, lane);
+          } else {
+            self = ld_rec(recs + s);
+          }
+        }
       }
-      const uint4 cur = heap.pop();
+      const uint4 cur = heap.take();
       const float cur_cost = __uint_as_float(cur.x), cur_est = __uint_as_float(cur.y);
-      cp_async_wait_all();
+      if (!PAIR) cp_async_wait_all();
       __syncwarp();  // lanes read each other's slots below (lane 0's info, the state's own midpoint, the root probe)
+      uint32_t info0 = 0;
+      uint4 oa = make_uint4(0, 0, 0, 0);
       if (preloaded) {
-        const uint4 a = stage_l->a;
+        const uint4 a = rs[lane].a;
         r.mx = __uint_as_float(a.x), r.my = __uint_as_float(a.y), r.mz = __uint_as_float(a.z), r.twin = a.w;
-        r.info = stage_l->info;
-        dtab = stage_l->dist;
+        r.info = rs[lane].info;
+        dtab = rs[lane].dist;
+        info0 = rs[0].info;
+        oa = rs[s & kmask].a;  // the state's own midpoint: only the rare branches below (GoToEnd, off-mesh links) use it
       }
 
       // ---- resolve (node, point, ignored step) — pathfinding.rs:93-143 ----
@@ -456,13 +725,9 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
       V3 point{0.0f, 0.0f, 0.0f};
       if (is_edge) {
         if (kshift) {
-          const uint32_t own = s & kmask;
           poly = s >> kshift;
-          const uint32_t info0 = stage_w->lane[0].info;
           cur_type = (info0 >> 8) & 0xffu;
           has_links = (info0 >> 24) & 1u;
-          // the state's own midpoint: only the rare branches below (GoToEnd, off-mesh links) use it
-          const uint4 oa = stage_w->lane[own].a;
           point = {__uint_as_float(oa.x), __uint_as_float(oa.y), __uint_as_float(oa.z)};
         } else {
           first = self.first_edge;
@@ -536,8 +801,8 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
         const uint32_t amask = __ballot_sync(FULL, acc);
         if (amask == 0) continue;
         const uint32_t n_acc = __popc(amask);
-        if (n_nodes + n_acc > node_cap || heap.len + n_acc > heap_cap) {
-          status = heap.len + n_acc > heap_cap ? 7u : 2u;
+        if (n_nodes + n_acc > node_cap || heap.len() + n_acc > heap_cap) {
+          status = heap.len() + n_acc > heap_cap ? 7u : 2u;
           break;
         }
         const uint32_t rank = __popc(amask & lt);
@@ -569,17 +834,9 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
           if (acc) bs.store(r.twin, praw, es);
         }
         // pushes in ascending edge order
-        uint32_t m = amask, k = 0;
-        while (m) {
-          const uint32_t j = (uint32_t)__ffs(m) - 1u;
-          m &= m - 1u;
-          const uint32_t s2 = __shfl_sync(FULL, r.twin, j);
-          const float e2 = __shfl_sync(FULL, es, j), c2 = __shfl_sync(FULL, nc, j);
-          heap.push(make_uint4(__float_as_uint(c2), __float_as_uint(e2), n_nodes + k, s2));
-          k++;
-        }
+        heap.push_lanes(acc, amask, rank, nc, es, r.twin, n_nodes);
         n_nodes += n_acc;
-        hmax = max(hmax, heap.len);
+        hmax = max(hmax, heap.len());
       }
       // ---- off-mesh links in ascending link index (canonical; pathfinding.rs:196-229) ----
       if (has_links && status == 1) {
@@ -605,6 +862,8 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
         }
       }
     }
+
+    heap.stop();  // (pair) the heap warp drops what is left of the open list and waits for the next query
 
     // ============================ walk the back-pointers (astar.rs:86-105) ============================
     // staged goal-first as (state, next state) pairs; k_path_fixup turns them into (node, portal)
@@ -680,18 +939,23 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
       }
     }
   }
+  heap.exit();
+  if (PAIR) cp_async_wait_all();
 }
 
-template <uint32_t HS, uint32_t WPB, uint32_t BPS, int LAYOUT, bool SIMPLE>
+template <uint32_t HS, uint32_t WPB, uint32_t BPS, int LAYOUT, bool SIMPLE, bool PAIR>
 static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
                           AStarCounters* counters, const uint32_t* type_raw, uint32_t sm_count,
                           cudaStream_t stream) {
   static_assert(HS >= AT_HEAP_SM_MIN, "a slot's open-list spill is sized for HS >= AT_HEAP_SM_MIN (arena_layout)");
-  const size_t smem = (size_t)HS * WPB * sizeof(uint4) + WPB * sizeof(WarpStage);
+  static_assert(!PAIR || WPB <= 15, "one named barrier per pair");
+  const size_t smem = (size_t)HS * WPB * sizeof(uint4) + WPB * sizeof(WarpStage) +
+                      (PAIR ? WPB * (sizeof(PairBox) + REC_CACHE * sizeof(RecSlot)) : 0);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    cudaFuncSetAttribute(k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    cudaFuncSetAttribute(k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE, PAIR>, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
@@ -700,34 +964,41 @@ static void launch_warp_t(const DevNav& nav, const AStarArena& arena, const ASta
   if (slots > resident) slots = resident;
   AStarArena a = arena;
   a.n_slots = slots;
-  k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE><<<(slots + WPB - 1) / WPB, WPB * 32, smem, stream>>>(nav, a, q, pool, counters,
-                                                                                          type_raw);
+  k_astar_warp<HS, WPB, BPS, LAYOUT, SIMPLE, PAIR>
+      <<<(slots + WPB - 1) / WPB, WPB * (PAIR ? 64 : 32), smem, stream>>>(nav, a, q, pool, counters, type_raw);
 }
 
-void launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
-                       AStarCounters* counters, const uint32_t* type_raw, bool simple, uint32_t sm_count,
-                       cudaStream_t stream) {
+// Returns the launch kind: 2 = one warp per query, 3 = a pair of warps per query.
+uint32_t launch_astar_warp(const DevNav& nav, const AStarArena& arena, const AStarQueries& q, const PathPool& pool,
+                           AStarCounters* counters, const uint32_t* type_raw, bool simple, bool pair, uint32_t sm_count,
+                           cudaStream_t stream) {
   // The fewer queries, the more of the 227 KB of shared memory each open list gets (a spilled level costs an L2
   // round trip per pop): one query per SM -> 13 824 entries on chip; 4 per SM -> 3 456; 8 -> 1 472; 16 -> 736.
+  // Up to four queries per SM run as warp PAIRS (search warp + heap warp, see OpenList): the SM has issue slots
+  // to spare there, and a lone search is bound by one warp's dependent instruction chain.
   const uint32_t per_sm = (std::min(q.n, arena.n_slots) + sm_count - 1) / sm_count;
-#define LMB_WARP_LAUNCH_S(HS, WPB, BPS, L)                                                                       \
-  do {                                                                                                           \
-    if (simple) launch_warp_t<HS, WPB, BPS, L, true>(nav, arena, q, pool, counters, type_raw, sm_count, stream);   \
-    else launch_warp_t<HS, WPB, BPS, L, false>(nav, arena, q, pool, counters, type_raw, sm_count, stream);         \
+  const bool use_pair = pair && per_sm <= 4;
+#define LMB_WARP_LAUNCH_P(HS, WPB, BPS, L, P)                                                                      \
+  do {                                                                                                             \
+    if (simple) launch_warp_t<HS, WPB, BPS, L, true, P>(nav, arena, q, pool, counters, type_raw, sm_count, stream);  \
+    else launch_warp_t<HS, WPB, BPS, L, false, P>(nav, arena, q, pool, counters, type_raw, sm_count, stream);        \
   } while (0)
-#define LMB_WARP_LAUNCH(L)                                  \
-  do {                                                      \
-    if (per_sm <= 1) LMB_WARP_LAUNCH_S(13824, 1, 1, L);      \
-    else if (per_sm <= 4) LMB_WARP_LAUNCH_S(3456, 4, 1, L);  \
-    else if (per_sm <= 8) LMB_WARP_LAUNCH_S(1472, 4, 2, L);  \
-    else LMB_WARP_LAUNCH_S(736, 4, 4, L);                    \
+#define LMB_WARP_LAUNCH(L)                                                \
+  do {                                                                    \
+    if (per_sm <= 1 && use_pair) LMB_WARP_LAUNCH_P(13632, 1, 1, L, true);  \
+    else if (per_sm <= 1) LMB_WARP_LAUNCH_P(13824, 1, 1, L, false);        \
+    else if (per_sm <= 4 && use_pair) LMB_WARP_LAUNCH_P(3264, 4, 1, L, true); \
+    else if (per_sm <= 4) LMB_WARP_LAUNCH_P(3456, 4, 1, L, false);         \
+    else if (per_sm <= 8) LMB_WARP_LAUNCH_P(1472, 4, 2, L, false);         \
+    else LMB_WARP_LAUNCH_P(736, 4, 4, L, false);                           \
   } while (0)
   if (arena.layout == 1) LMB_WARP_LAUNCH(1);
   else if (arena.layout == 2) LMB_WARP_LAUNCH(2);
   else if (arena.layout == 3) LMB_WARP_LAUNCH(3);
   else LMB_WARP_LAUNCH(0);
 #undef LMB_WARP_LAUNCH
-#undef LMB_WARP_LAUNCH_S
+#undef LMB_WARP_LAUNCH_P
+  return use_pair ? 3u : 2u;
 }
 
 }  // namespace lmb

@@ -1,5 +1,5 @@
-"""Single-search latency and small-batch throughput of the two A* kernel families (k_astar_warp.cu: one
-query per warp; k_astar.cu: one query per thread) on a forest (256-room maze) and an open field
+"""Single-search latency and small-batch throughput of the A* kernel families (k_astar_warp.cu: a search warp +
+a heap warp per query up to 4 queries per SM, one warp per query; k_astar.cu: one query per thread) on a forest (256-room maze) and an open field
 (256 x 256 quads of 8 m, antipodal queries).  Prints one JSON line per (mesh, kernel, batch).
 Usage: python scripts/astar_latency.py [maze] [field] [tiled]"""
 import json
@@ -34,11 +34,13 @@ def run(kind):
     else:
         mesh = None
         flat = synth.tiled_archipelago_flat(8, 128)
-    for name, flags in (("warp", _abi.CONFIG_ASTAR_WARP_ONLY), ("thread", _abi.CONFIG_ASTAR_THREAD_ONLY)):
+    kernels = (("pair", _abi.CONFIG_ASTAR_WARP_ONLY), ("warp", _abi.CONFIG_ASTAR_WARP_ONLY | _abi.CONFIG_ASTAR_NO_PAIR),
+               ("thread", _abi.CONFIG_ASTAR_THREAD_ONLY))
+    for name, flags in kernels:
         gpu = NativeBackend(max_agents=1024, flags=flags)
         gpu.navdata_upload(flat)
         opts = synth.default_options()
-        for nq in (1, 16, 148, 1184, 2368):
+        for nq in (1, 16, 148, 592) if name == "pair" else (1, 16, 148, 592, 1184, 2368):
             rng = np.random.Generator(np.random.PCG64(1000 + nq))
             if mesh is not None:
                 sn, sp, en, ep = queries(kind, mesh, nq, rng)

@@ -1,5 +1,5 @@
 """One batch of long A* queries through one kernel family, for `ncu --set full --import-source on`:
-  python scripts/profile_single.py <maze|field> <warp|thread> <n_queries> [rooms]
+  python scripts/profile_single.py <maze|field> <pair|warp|thread> <n_queries> [rooms]
 The first call sizes the arena; profile the second launch (ncu --launch-skip 1 -k regex:k_astar)."""
 import sys
 sys.path.insert(0, ".")
@@ -14,7 +14,8 @@ if kind == "maze":
 else:
     mesh = synth.grid_mesh(256, 256, cell=8.0)
 flat = synth.single_island_flat(mesh)
-flags = _abi.CONFIG_ASTAR_WARP_ONLY if kernel == "warp" else _abi.CONFIG_ASTAR_THREAD_ONLY
+flags = {"pair": _abi.CONFIG_ASTAR_WARP_ONLY, "warp": _abi.CONFIG_ASTAR_WARP_ONLY | _abi.CONFIG_ASTAR_NO_PAIR,
+         "thread": _abi.CONFIG_ASTAR_THREAD_ONLY}[kernel]
 gpu = NativeBackend(max_agents=1024, flags=flags)
 gpu.navdata_upload(flat)
 rng = np.random.Generator(np.random.PCG64(1000 + nq))

@@ -71,7 +71,8 @@ def test_constants_match_header():
                         ("LMB_CONFIG_ASTAR_WARP_ONLY", _abi.CONFIG_ASTAR_WARP_ONLY),
                         ("LMB_CONFIG_ASTAR_NO_FOREST", _abi.CONFIG_ASTAR_NO_FOREST),
                         ("LMB_CONFIG_NO_L2_WINDOW", _abi.CONFIG_NO_L2_WINDOW),
-                        ("LMB_CONFIG_ASTAR_SMALL_HEAP", _abi.CONFIG_ASTAR_SMALL_HEAP)]:
+                        ("LMB_CONFIG_ASTAR_SMALL_HEAP", _abi.CONFIG_ASTAR_SMALL_HEAP),
+                        ("LMB_CONFIG_ASTAR_NO_PAIR", _abi.CONFIG_ASTAR_NO_PAIR)]:
         m = re.search(rf"#define {name} (\d+)u", text)
         assert m and int(m.group(1)) == value, name
 
@@ -173,5 +174,5 @@ def test_error_paths_of_the_round_2_entry_points():
     out = gpu.agents_download()
     np.testing.assert_array_equal(moved, (ag["position"] + out["desired_velocity"] * np.float32(0.1)).astype(np.float32))
     t = gpu.step_timings()
-    assert t.astar_launch_kind in (1, 2, 3) and t.allgather_ms >= 0.0
+    assert 1 <= t.astar_launch_kind <= 7 and t.allgather_ms >= 0.0
     gpu.close()

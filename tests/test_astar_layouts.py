@@ -13,14 +13,16 @@ pytestmark = pytest.mark.gpu
 NAMES = ["success", "explored", "begin", "nodes", "portals"]
 
 
-KERNELS = [pytest.param(0, id="warp-per-query"),
+KERNELS = [pytest.param(0, id="warp-pair-per-query"),
+           pytest.param(_abi.CONFIG_ASTAR_NO_PAIR, id="warp-per-query"),
            pytest.param(_abi.CONFIG_ASTAR_THREAD_ONLY, id="thread-per-query")]
 
 
 @pytest.fixture(params=KERNELS)
 def kernel(request):
-    """Small batches go to the warp-per-query kernel (k_astar_warp.cu) by default; THREAD_ONLY keeps them on
-    the thread-per-query kernel (k_astar.cu).  Every layout test runs on both."""
+    """Small batches go to the warp kernel (k_astar_warp.cu) by default — a search warp plus a heap warp per query
+    up to four queries per SM, one warp per query (NO_PAIR forces it) beyond; THREAD_ONLY keeps them on the
+    thread-per-query kernel (k_astar.cu).  Every layout test runs on all three."""
     return request.param
 
 
@@ -174,7 +176,8 @@ def test_dense_best_slot_reuse_and_arena_retry(capfd, kernel):
     assert err.count("arena:") >= 2 and "compact best" not in err
 
 
-@pytest.mark.parametrize("shape", [0, _abi.CONFIG_ASTAR_THREAD_ONLY, _abi.CONFIG_ASTAR_LARGE_SHAPES])
+@pytest.mark.parametrize("shape", [0, _abi.CONFIG_ASTAR_NO_PAIR, _abi.CONFIG_ASTAR_THREAD_ONLY,
+                                   _abi.CONFIG_ASTAR_LARGE_SHAPES])
 @pytest.mark.parametrize("mesh_kind", ["grid", "maze", "forest"])
 def test_open_list_spill_overflow_and_retry(mesh_kind, shape, capfd):
     """the spill region of a slot must hold heap_cap entries for the SMALLEST number of shared-memory

@@ -37,13 +37,14 @@ def maze256():
     return mesh, synth.single_island_flat(mesh)
 
 
-@pytest.mark.parametrize("shape", ["warp", "thread", "large"])
+@pytest.mark.parametrize("shape", ["pair", "warp", "thread", "large"])
 def test_find_paths_on_the_256_room_maze(maze256, shape):
     """300 queries on the bench's own mesh (131 071 polygons, searches of ~65 000 explored nodes) through
-    each kernel family: warp-per-query, thread-per-query small-batch shapes, and the large-batch shape the
+    each kernel family: warp pair per query, warp-per-query, thread-per-query small-batch shapes, and the large-batch shape the
     bench launches (<16, 40, 5, quad, forest, SIMPLE>) on 192 slots."""
     mesh, flat = maze256
-    flags = {"warp": 0, "thread": _abi.CONFIG_ASTAR_THREAD_ONLY, "large": _abi.CONFIG_ASTAR_LARGE_SHAPES}[shape]
+    flags = {"pair": 0, "warp": _abi.CONFIG_ASTAR_NO_PAIR, "thread": _abi.CONFIG_ASTAR_THREAD_ONLY,
+             "large": _abi.CONFIG_ASTAR_LARGE_SHAPES}[shape]
     gpu, cpu = _backends(flat, flags=flags, astar_slots=192 if shape == "large" else 0)
     rng = np.random.Generator(np.random.PCG64(256))
     nq = 300
@@ -83,7 +84,8 @@ def test_full_step_on_the_256_room_maze(maze256):
     cpu.close()
 
 
-@pytest.mark.parametrize("kernel", [0, _abi.CONFIG_ASTAR_THREAD_ONLY, _abi.CONFIG_ASTAR_LARGE_SHAPES])
+@pytest.mark.parametrize("kernel", [0, _abi.CONFIG_ASTAR_NO_PAIR, _abi.CONFIG_ASTAR_THREAD_ONLY,
+                                    _abi.CONFIG_ASTAR_LARGE_SHAPES])
 @pytest.mark.parametrize("layout", ["hashed", "dense"])
 def test_tiled_typed_multi_island_world(kernel, layout):
     """BASELINE config 4 in small: 3 x 3 islands of 32 x 32 quads, type costs {1, 2, 5}, boundary links.
