@@ -263,21 +263,17 @@ struct __align__(16) PairBox {
   uint4 root;           // the root after the pushes (the entry the heap warp then pops)
   uint32_t n, flags;    // batch size; MORE: the expansion goes on, no pop yet; STOP: the query is over; EXIT
   uint32_t len, pad;    // open-list length after the pushes
-  uint32_t rslot;       // record-cache slot that holds the root's records, or LMB_NONE
   uint32_t next_len;    // open-list length before the pushes (after the pop) ...
-  uint32_t pad2[2];
+  uint32_t pad2[3];
   uint4 next;           // ... and its root then: what a pushed entry has to beat to be the next root
 };
-// The search warp of a pair has no pop to hide the L2 round trip of the root's records behind, so the records are
-// fetched a step ahead (cp.async into staging slots, like the staging of the single-warp kernel), by whichever
-// warp is idle at the time:
-//   * the heap warp knows the root-to-be as soon as its pop ends — a whole expansion ahead — and fetches that
-//     state's records into slot 0 / 1 (alternating: the search warp may be reading the other);
-//   * the search warp, idle while its batch is being pushed, checks whether one of the entries is about to take
-//     the root (sift_up passes every ancestor the entry is not <= to) and fetches that one into slot 2.
-// The heap warp publishes the slot with the root.  Records are immutable; anything else (special states, CSR ids,
-// a wrong guess) is a miss and the search warp fetches and waits as before.
-constexpr uint32_t REC_CACHE = 3;
+// The search warp of a pair has no pop to hide the L2 round trip of the root's records behind.  It is idle while
+// the heap warp pushes its batch, and it can tell what the root will be then: the entry of the batch that passes
+// every ancestor (sift_up stops at the first ancestor the entry is <= to) or else the root the pop left behind.
+// It fetches that state's records in the idle window (cp.async into a staging slot, like the single-warp
+// kernel's staging), so they are there or nearly there when the root is published.  Records are immutable; a
+// wrong guess, a special state or CSR ids are a miss: fetch and wait as before.
+constexpr uint32_t REC_CACHE = 1;
 struct __align__(16) RecSlot {
   LaneStage lane[32];
 };
@@ -325,7 +321,6 @@ struct OpenList<HS, true> {  // the search warp's end of the mailbox
   PairBox* box;
   uint32_t id, lane, n, len_x;
   uint4 root;
-  uint32_t rslot;
   __device__ __forceinline__ void init(uint4*, uint4*, uint32_t lane_, PairBox* box_, uint32_t id_) {
     box = box_, id = id_, lane = lane_, n = 0, len_x = 0;
   }
@@ -349,7 +344,6 @@ struct OpenList<HS, true> {  // the search warp's end of the mailbox
     pair_sync(id);
     n = 0;
     root = box->root;
-    rslot = box->rslot;
     const uint32_t l = box->len;
     len_x = l ? l - 1u : 0u;
     s = root.w;
@@ -395,16 +389,12 @@ __device__ __forceinline__ void issue_records(LaneStage* dst, const RecSource& s
   cp_async_4(&dst[lane].dist, src.edge_dist + ((size_t)st << src.kshift) + le);
 }
 
-// The heap warp of a pair: pushes the batches it is handed, publishes the root, pops it — and keeps the record
-// cache (REC_CACHE) a node ahead of the search warp.
+// The heap warp of a pair: pushes the batches it is handed, publishes the root, pops it, publishes what the pop
+// left at the root.
 template <uint32_t HS>
-__device__ __forceinline__ void heap_warp_loop(uint4* sm, uint4* gm, PairBox* box, uint32_t id, uint32_t lane,
-                                               const RecSource src, RecSlot* cache) {
+__device__ __forceinline__ void heap_warp_loop(uint4* sm, uint4* gm, PairBox* box, uint32_t id, uint32_t lane) {
   WarpHeap<HS> heap;
   heap.init(sm, gm, lane);
-  const bool pf = src.kshift != 0;  // padded ids: a state's records are one aligned run
-  uint32_t a_state = LMB_NONE, a_slot = LMB_NONE;  // the root-to-be whose records were fetched, and where to
-  uint32_t root_slot = LMB_NONE;                   // the slot named for the current root (being read)
   if (lane == 0) box->next_len = 0;
   for (;;) {
     pair_sync(id);
@@ -417,30 +407,11 @@ __device__ __forceinline__ void heap_warp_loop(uint4* sm, uint4* gm, PairBox* bo
     }
     for (uint32_t k = 0; k < n; k++) heap.push(box->e[k]);
     const bool more = flags & BOX_MORE;
-    if (!more) {
-      const uint4 root = heap.sm[0];
-      root_slot = (heap.len != 0 && root.w == a_state) ? a_slot : LMB_NONE;
-      if (root_slot != LMB_NONE) cp_async_wait_all();  // the fetch is complete before the slot is named
-      if (lane == 0) box->root = root, box->len = heap.len, box->rslot = root_slot;
-    }
+    if (!more && lane == 0) box->root = heap.sm[0], box->len = heap.len;
     pair_sync(id);
-    if (!more && heap.len != 0) {
-      heap.pop();
-      if (pf && heap.len != 0) {
-        const uint32_t a = heap.sm[0].w;  // the next root unless a successor of this expansion beats it
-        if (a >= src.n_ids) {
-          a_state = a_slot = LMB_NONE;
-        } else if (a != a_state || a_slot == LMB_NONE) {
-          a_state = a;
-          a_slot = root_slot == LMB_NONE ? 0u : root_slot ^ 1u;
-          cp_async_wait_all();  // an earlier fetch into that slot that was never named (a node old: no wait in practice)
-          issue_records(cache[a_slot].lane, src, a, lane);
-        }
-      }
-    }
+    if (!more && heap.len != 0) heap.pop();
     if (lane == 0) box->next = heap.sm[0], box->next_len = heap.len;
   }
-  cp_async_wait_all();
 }
 
 // key under which two states collide physically in a layout's table (never for the dense array)
@@ -494,7 +465,7 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
                          (size_t)warp * REC_CACHE;
   if (PAIR && ((threadIdx.x >> 5) & 1u)) {
     heap_warp_loop<HS>(s_heap + (size_t)warp * HS, reinterpret_cast<uint4*>(slot_base + arena.heap_offset), box, 1u + warp,
-                       lane, RecSource{nav.edges, nav.edge_dist, arena.kshift, arena.n_ids}, cache);
+                       lane);
     return;
   }
   BestStore<LAYOUT> bs;
@@ -641,22 +612,21 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
     while (status == 1) {
       // ---- peek the root, issue this expansion's loads, then pop ----
       uint32_t s = 0;
-      uint32_t x_cand = LMB_NONE;  // (pair) the entry handed over that is about to take the root: records -> slot 2
+      uint32_t x_pred = LMB_NONE;  // (pair) the state expected at the root after the pushes: records -> the slot
       auto idle = [&](const PairBox* bx, uint32_t n_batch) {
-        if (!kshift || n_batch == 0) return;
+        if (!kshift) return;
         uint4 ref = bx->next;
         bool have = bx->next_len != 0;
+        uint32_t pred = have ? ref.w : LMB_NONE;
         for (uint32_t k = 0; k < n_batch; k++) {
           const uint4 e = bx->e[k];
-          if (!have || !rev_le4(e, ref)) ref = e, have = true, x_cand = e.w;
+          if (!have || !rev_le4(e, ref)) ref = e, have = true, pred = e.w;
         }
-        if (x_cand >= ST_LINK0) {
-          x_cand = LMB_NONE;
-          return;
-        }
-        cp_async_wait_all();  // the previous fetch into this slot
-        issue_records(cache[2].lane, rec_src, x_cand, lane);
+        if (pred >= ST_LINK0) return;  // a special state, or an empty open list
+        cp_async_wait_all();           // a wrong guess of the previous node may still be landing in the slot
+        issue_records(cache[0].lane, rec_src, pred, lane);
         cp_async_commit();
+        x_pred = pred;
       };
       if (!heap.peek(s, idle)) break;
       const bool is_edge = s < ST_LINK0;
@@ -670,7 +640,7 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
       __syncwarp();  // nobody still reads the previous expansion's staging slots
       const LaneStage* rs = stage_w->lane;  // where the root's records are staged
       if constexpr (PAIR) {
-        // records: in the slot the heap warp names (fetched a node ahead, complete), else fetched now
+        // records: fetched in the idle window if the guess was right, else fetched now
         bool fetched = false;
         if (LAYOUT != 3) {
           if (lane == 0) stage_root_probe<LAYOUT>(bs, s, &stage_w->root);
@@ -679,11 +649,9 @@ k_astar_warp(DevNav nav, AStarArena arena, AStarQueries q, PathPool pool, AStarC
         if (preloaded) {
           first = s & ~kmask;
           cnt = kmask + 1u;
-          if (s == x_cand) {
-            rs = cache[2].lane;
+          if (s == x_pred) {
+            rs = cache[0].lane;
             fetched = true;
-          } else if (heap.rslot != LMB_NONE) {
-            rs = cache[heap.rslot].lane;
           } else {
             issue_records(stage_w->lane, rec_src, s, lane);
             fetched = true;
@@ -985,9 +953,9 @@ uint32_t launch_astar_warp(const DevNav& nav, const AStarArena& arena, const ASt
   } while (0)
 #define LMB_WARP_LAUNCH(L)                                                \
   do {                                                                    \
-    if (per_sm <= 1 && use_pair) LMB_WARP_LAUNCH_P(13632, 1, 1, L, true);  \
+    if (per_sm <= 1 && use_pair) LMB_WARP_LAUNCH_P(13760, 1, 1, L, true);  \
     else if (per_sm <= 1) LMB_WARP_LAUNCH_P(13824, 1, 1, L, false);        \
-    else if (per_sm <= 4 && use_pair) LMB_WARP_LAUNCH_P(3264, 4, 1, L, true); \
+    else if (per_sm <= 4 && use_pair) LMB_WARP_LAUNCH_P(3392, 4, 1, L, true); \
     else if (per_sm <= 4) LMB_WARP_LAUNCH_P(3456, 4, 1, L, false);         \
     else if (per_sm <= 8) LMB_WARP_LAUNCH_P(1472, 4, 2, L, false);         \
     else LMB_WARP_LAUNCH_P(736, 4, 4, L, false);                           \

@@ -1183,18 +1183,25 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
                             cudaStream_t stream) {
   if (!chunk_n) return;
-  // Few agents: spread them over the SMs in small blocks.  One thread walks its agent's scratch serially (flood
-  // heap, cone list, loop nodes: tens of thousands of dependent accesses on a fine mesh), so what it needs is its
-  // ~25 KB of scratch in ITS SM's L1 — 64 agents per block put 1.5 MB behind one L1 and left 146 SMs idle
-  // (config 1, 100 agents: 3.3 ms of a 3.6 ms frame).
+  // Few agents: small blocks, down to ONE agent per block (= per warp).  One thread walks its agent's scratch
+  // serially (flood heap, cone list, loop nodes: tens of thousands of dependent instructions on a fine mesh) and
+  // the agents of a warp diverge — their instruction streams run one after the other (3.4 of 8 lanes active per
+  // instruction at 8 agents per warp) — so while the GPU has warp slots to spare, every agent gets a warp of its
+  // own: a block holds 1 agent up to 8 agents per SM, 2 up to 16, ... 64 beyond 256 per SM.  Measured
+  // (scripts/small_frame.py, 64 x 64 grid): 100 agents 1.48 -> 0.62 ms, 1 000 1.66 -> 0.75, 4 000 3.18 -> 1.98;
+  // from 16 000 agents on the old and new sizes agree.
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
+#ifndef LMB_AVOID_MIN_THREADS
+#define LMB_AVOID_MIN_THREADS 1
+#define LMB_AVOID_SPREAD 32
+#endif
   uint32_t threads = 64;
-  while (threads > 8 && (uint64_t)chunk_n * 8 <= (uint64_t)sm_count * threads * 4) threads >>= 1;
+  while (threads > LMB_AVOID_MIN_THREADS && (uint64_t)chunk_n * 8 <= (uint64_t)sm_count * threads * LMB_AVOID_SPREAD) threads >>= 1;
   k_avoidance<<<blocks_for(chunk_n, threads), threads, 0, stream>>>(nav, ag, o, delta_time, first_agent_global, chunk_begin,
                                                           chunk_n, n_records, records, n_characters, char_records,
                                                           grid, scratch, max_radius_bits, staged_moves, dbg);

@@ -7,12 +7,13 @@ from landmass_b200 import _abi, synth
 from landmass_b200._native import NativeBackend
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+lib = sys.argv[2] if len(sys.argv) > 2 else None  # an alternative liblandmass_b200.so (A/B of kernel variants)
 mesh = synth.grid_mesh(64, 64)
 flat = synth.single_island_flat(mesh)
 ag = synth.make_agents(mesh, n)
 opts = synth.default_options()
 for flags, name in ((0, "full step"), (_abi.CONFIG_NO_AVOIDANCE, "without avoidance")):
-    gpu = NativeBackend(max_agents=n, flags=flags)
+    gpu = NativeBackend(max_agents=n, flags=flags, lib_path=lib)
     gpu.navdata_upload(flat)
     a = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in ag.items()}
     rows = []
