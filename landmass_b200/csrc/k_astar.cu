@@ -887,17 +887,19 @@ uint32_t launch_astar(const DevNav& nav, const AStarArena& arena, const AStarQue
   uint32_t kind = 1;
   // LMB_CONFIG_ASTAR_LARGE_SHAPES: tests run the large-batch shapes (the benchmarked ones) at sizes the oracle can check
   const bool force_large = flags & LMB_CONFIG_ASTAR_LARGE_SHAPES;
-  // Small batches finish with their longest search: up to 16 queries per SM go to the warp-per-query kernel
-  // (k_astar_warp.cu), whose single-search latency is several times lower.
-  // (measured, scripts/astar_latency.py: on a forest the warp kernel wins up to 16 queries per SM; with large
-  // open lists it wins while a query's open list fits in its share of shared memory — up to 4 per SM — and the
-  // thread-per-query shapes are ahead again beyond that)
-  const uint32_t warp_max = (arena.layout == 3 ? 16u : 4u) * (uint32_t)sm_count;
+  // Small batches finish with their longest search: up to 16 queries per SM go to the warp kernels
+  // (k_astar_warp.cu: a search warp + a heap warp per query), whose single-search latency is several times lower.
+  // (measured, scripts/astar_latency.py, us per explored node of the longest search at 1 / 4 / 8 / 16 queries per
+  // SM: maze 0.79 / 0.87 / 0.91 / 1.12-1.16 against 1.05 / 1.08 / 1.12 / 1.35 thread-per-query; open field
+  // 1.11 / 1.30 / 1.51 / 2.03 against 1.83 / 1.93 / 1.96 / 3.56.  Without the heap warp — LMB_CONFIG_ASTAR_NO_PAIR
+  // — a query's open list has to fit its share of shared memory for the warp kernel to win: up to 4 per SM off a
+  // forest.)
+  const bool pair = !(flags & LMB_CONFIG_ASTAR_NO_PAIR);
+  const uint32_t warp_max = (arena.layout == 3 || pair ? 16u : 4u) * (uint32_t)sm_count;
   const bool warp = (flags & LMB_CONFIG_ASTAR_WARP_ONLY) ||
                     (!force_large && !(flags & LMB_CONFIG_ASTAR_THREAD_ONLY) && q.n <= warp_max);
   if (warp) {
-    kind = launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, !(flags & LMB_CONFIG_ASTAR_NO_PAIR),
-                             (uint32_t)sm_count, stream) == 3u ? 4u : 2u;
+    kind = launch_astar_warp(nav, arena, q, pool, counters, type_raw, simple, pair, (uint32_t)sm_count, stream) == 3u ? 4u : 2u;
   } else if (!force_large && q.n <= 8u * (uint32_t)sm_count)
     LMB_ASTAR_LAUNCH(1, 1536, 2);  // few queries: one per warp, the whole open list on chip
   else if (!force_large && q.n <= 32u * (uint32_t)sm_count)

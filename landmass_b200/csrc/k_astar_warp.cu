@@ -15,8 +15,9 @@
 //   * open list: the exact `BinaryHeap<Reverse<NodeRef>>` emulation of k_astar_common.cuh, but
 //       - `sift_down_to_bottom` picks the greater child independently of the hole, so its path is a
 //         function of the heap alone: 31 lanes evaluate the winner bits of a five-level subtree at
-//         once (two 16-byte shared-memory reads each), a ballot publishes them, and the path is
-//         walked five levels per round with ALU operations only;
+//         once (two 16-byte shared-memory reads each) and a ballot publishes them; a node lies on the
+//         path when every ancestor's bit points its way, which each lane checks against two precomputed
+//         masks, and a second ballot IS the path: five levels per round, no walk;
 //       - the moves along the path are one parallel step (lane k moves the entry of level k), and the
 //         `sift_up` that follows is ONE ballot over the path entries (stop at the first ancestor the
 //         hole element is <= to, scanning upward: the highest set bit);
@@ -26,10 +27,17 @@
 //     consumed after it, like in k_astar.cu;
 //   * walk: the back-pointer chain is followed through a 128-node window held in registers (four
 //     nodes per lane, moved by shuffles); a dependent memory round trip is paid only when the chain
-//     leaves the window.
+//     leaves the window;
+//   * two warps per query (PAIR, the default): `pop` needs nothing from the expansion and the expansion
+//     only the root's identity, so a HEAP warp owns the open list — it publishes the root, pops it, and
+//     pushes the batch of successors it is handed — while the SEARCH warp expands the root; a mailbox in
+//     shared memory and one named barrier (bar.sync id, 64) between them.  The search warp spends the push
+//     phase guessing the next root (the batch entry that passes every ancestor, else the root the pop
+//     left) and fetching its records.
 //
-// One warp runs one query at a time and pulls the next from the batch's queue; 1, 4, 8 or 16 warps per SM
-// with 13 824 / 3 456 / 1 472 / 736 open-list entries per query in shared memory (in-place spill beyond that).
+// A query unit (warp or pair) runs one query at a time and pulls the next from the batch's queue; 1, 4, 8
+// or 16 units per SM with ~13 800 / 3 400 / 1 500 / 700 open-list entries per query in shared memory
+// (in-place spill beyond that).
 #include <algorithm>
 
 #include "k_astar_common.cuh"
@@ -941,11 +949,12 @@ uint32_t launch_astar_warp(const DevNav& nav, const AStarArena& arena, const ASt
                            AStarCounters* counters, const uint32_t* type_raw, bool simple, bool pair, uint32_t sm_count,
                            cudaStream_t stream) {
   // The fewer queries, the more of the 227 KB of shared memory each open list gets (a spilled level costs an L2
-  // round trip per pop): one query per SM -> 13 824 entries on chip; 4 per SM -> 3 456; 8 -> 1 472; 16 -> 736.
-  // Up to four queries per SM run as warp PAIRS (search warp + heap warp, see OpenList): the SM has issue slots
-  // to spare there, and a lone search is bound by one warp's dependent instruction chain.
+  // round trip per pop): one query per SM -> ~13 800 entries on chip; 4 per SM -> ~3 400; 8 -> ~1 500; 16 -> ~700.
+  // Every shape exists as one warp per query and as a warp PAIR per query (search warp + heap warp, see OpenList):
+  // a lone search is bound by one warp's dependent instruction chain, and up to 16 queries per SM the SM has the
+  // issue slots for a second warp each.
   const uint32_t per_sm = (std::min(q.n, arena.n_slots) + sm_count - 1) / sm_count;
-  const bool use_pair = pair && per_sm <= 4;
+  const bool use_pair = pair;
 #define LMB_WARP_LAUNCH_P(HS, WPB, BPS, L, P)                                                                      \
   do {                                                                                                             \
     if (simple) launch_warp_t<HS, WPB, BPS, L, true, P>(nav, arena, q, pool, counters, type_raw, sm_count, stream);  \
@@ -957,7 +966,9 @@ uint32_t launch_astar_warp(const DevNav& nav, const AStarArena& arena, const ASt
     else if (per_sm <= 1) LMB_WARP_LAUNCH_P(13824, 1, 1, L, false);        \
     else if (per_sm <= 4 && use_pair) LMB_WARP_LAUNCH_P(3392, 4, 1, L, true); \
     else if (per_sm <= 4) LMB_WARP_LAUNCH_P(3456, 4, 1, L, false);         \
+    else if (per_sm <= 8 && use_pair) LMB_WARP_LAUNCH_P(1600, 4, 2, L, true); \
     else if (per_sm <= 8) LMB_WARP_LAUNCH_P(1472, 4, 2, L, false);         \
+    else if (use_pair) LMB_WARP_LAUNCH_P(704, 4, 4, L, true);              \
     else LMB_WARP_LAUNCH_P(736, 4, 4, L, false);                           \
   } while (0)
   if (arena.layout == 1) LMB_WARP_LAUNCH(1);

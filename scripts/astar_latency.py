@@ -40,7 +40,7 @@ def run(kind):
         gpu = NativeBackend(max_agents=1024, flags=flags)
         gpu.navdata_upload(flat)
         opts = synth.default_options()
-        for nq in (1, 16, 148, 592) if name == "pair" else (1, 16, 148, 592, 1184, 2368):
+        for nq in (1, 16, 148, 592, 1184) if name == "pair" else (1, 16, 148, 592, 1184, 2368):
             rng = np.random.Generator(np.random.PCG64(1000 + nq))
             if mesh is not None:
                 sn, sp, en, ep = queries(kind, mesh, nq, rng)

@@ -264,3 +264,39 @@ def test_large_batch_shapes_against_the_oracle(case):
     assert g[0].all()
     gpu.close()
     cpu.close()
+
+
+@pytest.mark.parametrize("pair", [pytest.param(0, id="warp-pair"), pytest.param(_abi.CONFIG_ASTAR_NO_PAIR, id="one-warp")])
+@pytest.mark.parametrize("case", ["maze", "grid_types", "loopy_maze_hashed"])
+def test_every_warp_kernel_launch_shape_against_the_oracle(case, pair):
+    """k_astar_warp.cu picks its launch shape by queries per SM — 1, up to 4, up to 8, up to 16 units per SM, each
+    unit one warp or a search warp + heap warp pair, with less shared memory per open list every step.
+    LMB_CONFIG_ASTAR_WARP_ONLY keeps batches of every size on it: 100 / 500 / 1 100 / 2 300 queries against the
+    oracle, on a forest (no best_estimates), a typed grid (dense) and a maze with cycles under the hashed layout."""
+    rng = np.random.Generator(np.random.PCG64(99))
+    flags = _abi.CONFIG_ASTAR_WARP_ONLY | pair
+    if case == "maze":
+        mesh = synth.maze_mesh(20)
+        flat = synth.single_island_flat(mesh)
+    elif case == "grid_types":
+        types = (np.add.outer(np.arange(24) // 4, np.arange(24) // 4) % 3).astype(np.uint32)
+        mesh = synth.grid_mesh(24, 24, types=types)
+        flat = dict(synth.single_island_flat(mesh))
+        flat["n_type_costs"] = 3
+        flat["type_cost_index"] = np.array([0, 1, 2], dtype=np.uint32)
+        flat["type_cost_value"] = np.array([1.0, 2.5, 0.5], dtype=np.float32)
+    else:
+        mesh = synth.loopy_maze_mesh(20, 60)
+        flat = synth.single_island_flat(mesh)
+        flags |= _abi.CONFIG_ASTAR_HASHED
+    gpu, cpu = backends(flat, flags=flags)
+    for nq in (100, 500, 1100, 2300):
+        sp, sn = synth.random_points_on_mesh(mesh, nq, rng)
+        ep, en = synth.random_points_on_mesh(mesh, nq, rng)
+        g = gpu.find_paths(sn, sp, en, ep, path_capacity=1 << 21)
+        c = cpu.find_paths(sn, sp, en, ep, path_capacity=1 << 21)
+        for a, b, name in zip(g, c, NAMES):
+            assert np.array_equal(a, b), (nq, name)
+        assert gpu.query_timings().astar_launch_kind == (2 if pair else 4)
+    gpu.close()
+    cpu.close()
