@@ -1190,6 +1190,9 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
   // own: a block holds 1 agent up to 8 agents per SM, 2 up to 16, ... 64 beyond 256 per SM.  Measured
   // (scripts/small_frame.py, 64 x 64 grid): 100 agents 1.48 -> 0.62 ms, 1 000 1.66 -> 0.75, 4 000 3.18 -> 1.98;
   // from 16 000 agents on the old and new sizes agree.
+  // (measured and not kept: ONE persistent launch for all chunks, warps taking 32 agents at a time off a counter —
+  // config 3 3.27 -> 3.31 ms per M agents, 16 000 agents on the 64 x 64 grid 12.4 -> 16.8 ms: the chunk tails were
+  // not the cost, and the loop around the body cost 120 bytes more stack)
   static int sm_count = 0;
   if (!sm_count) {
     int dev = 0;
