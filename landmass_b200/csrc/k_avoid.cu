@@ -728,10 +728,16 @@ __global__ void __launch_bounds__(64, 14)
 k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_t first_agent_global,
             uint32_t chunk_begin, uint32_t chunk_n, uint32_t n_records, const AvoidRecord* records,
             uint32_t n_characters, const AvoidRecord* char_records, AvoidGrid grid, AvoidScratch scratch,
-            const uint32_t* max_radius_bits, float* out_move, AvoidDebug dbg) {
+            const uint32_t* max_radius_bits, float* out_move, AvoidDebug dbg, bool cell_order) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= chunk_n) return;
-  const uint32_t i = chunk_begin + t;        // local dense agent index
+  uint32_t i = chunk_begin + t;  // local dense agent index
+  if (cell_order) {
+    // every record is this rank's own: take the agents in the grid's cell order, so that the threads of a warp
+    // stand next to each other — the same candidate rows (L1 hits) and about the same number of neighbours
+    if (i >= grid.cell_start[(size_t)grid.nx * grid.ny]) return;  // positions beyond the valid records
+    i = grid.sorted_rec[i].valid;                                   // (the word carries the record's index)
+  }
   const uint32_t gi = first_agent_global + i;  // index into the (gathered) record array
   const AvoidRecord me = records[gi];
   if (!me.valid) return;
@@ -1183,6 +1189,7 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
                             cudaStream_t stream) {
   if (!chunk_n) return;
+  const bool cell_order = first_agent_global == 0 && n_records == ag.n && ag.n >= 8192;
   // Few agents: small blocks, down to ONE agent per block (= per warp).  One thread walks its agent's scratch
   // serially (flood heap, cone list, loop nodes: tens of thousands of dependent instructions on a fine mesh) and
   // the agents of a warp diverge — their instruction streams run one after the other (3.4 of 8 lanes active per
@@ -1207,7 +1214,7 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
   while (threads > LMB_AVOID_MIN_THREADS && (uint64_t)chunk_n * 8 <= (uint64_t)sm_count * threads * LMB_AVOID_SPREAD) threads >>= 1;
   k_avoidance<<<blocks_for(chunk_n, threads), threads, 0, stream>>>(nav, ag, o, delta_time, first_agent_global, chunk_begin,
                                                           chunk_n, n_records, records, n_characters, char_records,
-                                                          grid, scratch, max_radius_bits, staged_moves, dbg);
+                                                          grid, scratch, max_radius_bits, staged_moves, dbg, cell_order);
 }
 
 }  // namespace lmb

@@ -349,11 +349,65 @@ k_repath_decide(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool,
 }
 
 // Post-A* bookkeeping (lib.rs:406-421) + phase C (lib.rs:426-523).
+// ---- processing order of k_follow -----------------------------------------------------------------------
+// The funnel scans the corridor from the agent to the first corner — on open ground to the corridor's end — so an
+// agent's work is its remaining corridor length, anything from 0 to thousands of nodes, and a warp of agents in
+// index order runs as long as its longest (config 3: 9 of 32 lanes active per instruction).  A counting sort by
+// half-octave length bucket, longest first, gives warps of like lengths.
+__device__ __forceinline__ uint32_t follow_bucket(uint32_t remaining) {
+  if (remaining == 0) return 0;
+  const uint32_t l = 31u - __clz(remaining);
+  const uint32_t half = l ? (remaining >> (l - 1u)) & 1u : 0u;
+  const uint32_t b = 1u + 2u * l + half;
+  return b < FOLLOW_BUCKETS ? b : FOLLOW_BUCKETS - 1u;
+}
+__global__ void k_follow_order_count(AgentArrays ag, PathPool pool, AStarQueries q, FollowScratch scratch, uint8_t* key8,
+                                     uint32_t* hist) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t key = FOLLOW_BUCKETS;  // no agent
+  if (i < ag.n) {
+    uint32_t remaining = 0;
+    const uint32_t qi = scratch.query_of_agent[i];
+    if (qi != LMB_NONE) {
+      if (q.out_success[qi]) remaining = q.out_path_len[qi];
+    } else if (pool.slot_path_len[ag.slot[i]]) {
+      const uint32_t fs = scratch.follow_start[i], fe = scratch.follow_end[i];
+      if (fs != LMB_NONE && fe != LMB_NONE && fe >= fs) remaining = fe - fs + 1u;
+    }
+    key = follow_bucket(remaining);
+    key8[i] = (uint8_t)key;
+  }
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
+  if (key < FOLLOW_BUCKETS && (threadIdx.x & 31u) == (uint32_t)__ffs(peers) - 1u) atomicAdd(hist + key, __popc(peers));
+}
+// hist[b] -> first position of bucket b with the LONGEST bucket first, into hist[FOLLOW_BUCKETS + b] (the cursors)
+__global__ void k_follow_order_offsets(uint32_t* hist) {
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int b = (int)FOLLOW_BUCKETS - 1; b >= 0; b--) {
+      hist[FOLLOW_BUCKETS + b] = run;
+      run += hist[b];
+    }
+  }
+}
+__global__ void k_follow_order_scatter(uint32_t n, const uint8_t* key8, uint32_t* hist, uint32_t* order) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t key = i < n ? key8[i] : FOLLOW_BUCKETS;
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
+  const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+  uint32_t base = 0;
+  if (key < FOLLOW_BUCKETS && lane == leader) base = atomicAdd(hist + FOLLOW_BUCKETS + key, __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (key < FOLLOW_BUCKETS) order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
 __global__ void __launch_bounds__(128)
 k_follow(DevNav nav, AgentArrays ag, AgentPersist persist, PathPool pool, AStarQueries q,
          FollowScratch scratch) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ag.n) return;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ag.n) return;
+  const uint32_t i = scratch.order ? scratch.order[t] : t;
   const uint32_t s = ag.slot[i];
   uint32_t follow_start = scratch.follow_start[i], follow_end = scratch.follow_end[i];
   const uint32_t qi = scratch.query_of_agent[i];
@@ -745,6 +799,14 @@ void launch_follow(const DevNav& nav, const AgentArrays& ag, const AgentPersist&
                    const PathPool& pool, const AStarQueries& q, const FollowScratch& scratch,
                    cudaStream_t stream) {
   if (ag.n) k_follow<<<blocks_for(ag.n, 128), 128, 0, stream>>>(nav, ag, persist, pool, q, scratch);
+}
+void launch_follow_order(const AgentArrays& ag, const PathPool& pool, const AStarQueries& q, const FollowScratch& scratch,
+                         uint8_t* key8, uint32_t* hist, uint32_t* order, cudaStream_t stream) {
+  if (!ag.n) return;
+  cudaMemsetAsync(hist, 0, 2 * FOLLOW_BUCKETS * sizeof(uint32_t), stream);
+  k_follow_order_count<<<blocks_for(ag.n, 256), 256, 0, stream>>>(ag, pool, q, scratch, key8, hist);
+  k_follow_order_offsets<<<1, 32, 0, stream>>>(hist);
+  k_follow_order_scatter<<<blocks_for(ag.n, 256), 256, 0, stream>>>(ag.n, key8, hist, order);
 }
 void launch_gather_outputs(const AgentArrays& ag, const AgentPersist& persist, float* out_velocity,
                            uint32_t* out_state, uint32_t* out_link_id, float* out_link_start,

@@ -1408,6 +1408,15 @@ int32_t lmb_step_begin_impl(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
 
   // phase C
   nvtxRangePushA("lmb:phaseC follow");
+  // from a few thousand agents on, k_follow takes them longest corridor first (three small launches)
+  if (n >= 8192) {
+    CUDA_TRY(ctx, ctx->d_follow_order.reserve(n));
+    CUDA_TRY(ctx, ctx->d_follow_key.reserve(n));
+    CUDA_TRY(ctx, ctx->d_follow_hist.reserve(2 * FOLLOW_BUCKETS));
+    launch_follow_order(ag, make_pool(ctx), q, scratch, ctx->d_follow_key.p, ctx->d_follow_hist.p, ctx->d_follow_order.p, s);
+    scratch.order = ctx->d_follow_order.p;
+    T.kernel_launches += 3;
+  }
   launch_follow(ctx->nav, ag, persist, make_pool(ctx), q, scratch, s);
   nvtxRangePop();
   T.kernel_launches += n ? 1 : 0;

@@ -149,7 +149,10 @@ struct FollowScratch {
   uint32_t* waypoint_kind;   // [n]
   uint32_t* waypoint_link;   // [n] animation link id of an AnimationLink step
   float* waypoint_points;    // [n*6] point (or link start point) xyz, link end point xyz
+  // k_follow's processing order (longest remaining corridor first, k_follow_order_*), or nullptr = by index
+  const uint32_t* order;     // [n]
 };
+constexpr uint32_t FOLLOW_BUCKETS = 64;
 
 void launch_reset_slots(const AgentArrays& ag, const AgentPersist& persist, const PathPool& pool,
                         cudaStream_t stream);
@@ -159,6 +162,10 @@ void launch_repath_decide(const DevNav& nav, const AgentArrays& ag, const AgentP
 void launch_follow(const DevNav& nav, const AgentArrays& ag, const AgentPersist& persist,
                    const PathPool& pool, const AStarQueries& q, const FollowScratch& scratch,
                    cudaStream_t stream);
+// order[] = the agents sorted by the length of corridor the funnel may scan, longest first (counting sort over
+// half-octave buckets); key8 [n] bytes, hist [2 * FOLLOW_BUCKETS] words.  Three launches.
+void launch_follow_order(const AgentArrays& ag, const PathPool& pool, const AStarQueries& q, const FollowScratch& scratch,
+                         uint8_t* key8, uint32_t* hist, uint32_t* order, cudaStream_t stream);
 void launch_gather_outputs(const AgentArrays& ag, const AgentPersist& persist, float* out_velocity,
                            uint32_t* out_state, uint32_t* out_link_id, float* out_link_start,
                            float* out_link_end, cudaStream_t stream);

@@ -111,13 +111,16 @@ def _abi_state(name):
     return int(AgentState[name])
 
 
-@pytest.mark.parametrize("mesh_kind,n", [("grid", 1500), ("maze", 800)])
+@pytest.mark.parametrize("mesh_kind,n", [("grid", 1500), ("maze", 800), ("grid64", 9000)])
 def test_full_step_with_avoidance(mesh_kind, n):
     """All four phases.  Velocities within 1e-4 relative (north_star tolerance); states,
-    pathing results and paths exact.  ORCA parity is CUDA-vs-oracle (dodgy_2d source absent)."""
-    mesh = synth.grid_mesh(24, 24) if mesh_kind == "grid" else synth.maze_mesh(10)
+    pathing results and paths exact.  ORCA parity is CUDA-vs-oracle (dodgy_2d source absent).
+    The 9 000-agent case is above the sizes from which k_follow takes the agents longest corridor first and
+    k_avoidance in the grid's cell order."""
+    mesh = {"grid": lambda: synth.grid_mesh(24, 24), "maze": lambda: synth.maze_mesh(10),
+            "grid64": lambda: synth.grid_mesh(64, 64)}[mesh_kind]()
     flat = synth.single_island_flat(mesh)
-    gpu, cpu = backends(flat)
+    gpu, cpu = backends(flat, max_agents=max(4096, n))
     ag = synth.make_agents(mesh, n)   # dense: many neighbours per agent, borders nearby
     opts = synth.default_options()
     ch = {"n": 3,
@@ -125,7 +128,7 @@ def test_full_step_with_avoidance(mesh_kind, n):
           "velocity": np.array([[0.5, 0.0, 0.0], [0.0, -0.5, 0.0], [0.0, 0.0, 0.0]], dtype=np.float32),
           "radius": np.array([0.6, 0.4, 1.0], dtype=np.float32)}
     dt = 1.0 / 30.0
-    for frame in range(4):
+    for frame in range(2 if n > 5000 else 4):
         og = gpu.step(ag, ch, opts, dt)
         oc = cpu.step(ag, ch, opts, dt)
         assert np.array_equal(og["state"], oc["state"]), f"frame {frame}: states"
