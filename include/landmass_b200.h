@@ -243,6 +243,8 @@ typedef struct lmb_pathing_result {
 #define LMB_CONFIG_ASTAR_SMALL_HEAP 1024u  /* start with a 64-entry open list per query: forces the in-place spill,
                                               its overflow (status 7) and the doubling retry at test sizes */
 #define LMB_CONFIG_ASTAR_NO_PAIR 2048u     /* warp-per-query launches never use a second (heap) warp per query */
+#define LMB_CONFIG_ORDER_ALWAYS 4096u      /* k_follow / k_avoidance take the agents in their work order (longest corridor
+                                              first / grid cell order) at every size, not only from 8192 agents on */
 
 typedef struct lmb_config {
   uint32_t struct_size;

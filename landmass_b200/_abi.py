@@ -50,6 +50,7 @@ CONFIG_ASTAR_NO_FOREST = 256
 CONFIG_NO_L2_WINDOW = 512
 CONFIG_ASTAR_SMALL_HEAP = 1024
 CONFIG_ASTAR_NO_PAIR = 2048
+CONFIG_ORDER_ALWAYS = 4096
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)

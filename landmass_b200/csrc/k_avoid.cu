@@ -728,15 +728,17 @@ __global__ void __launch_bounds__(64, 14)
 k_avoidance(DevNav nav, AgentArrays ag, lmb_options o, float delta_time, uint32_t first_agent_global,
             uint32_t chunk_begin, uint32_t chunk_n, uint32_t n_records, const AvoidRecord* records,
             uint32_t n_characters, const AvoidRecord* char_records, AvoidGrid grid, AvoidScratch scratch,
-            const uint32_t* max_radius_bits, float* out_move, AvoidDebug dbg, bool cell_order) {
+            const uint32_t* max_radius_bits, float* out_move, AvoidDebug dbg, AvoidOrder ord) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= chunk_n) return;
   uint32_t i = chunk_begin + t;  // local dense agent index
-  if (cell_order) {
-    // every record is this rank's own: take the agents in the grid's cell order, so that the threads of a warp
-    // stand next to each other — the same candidate rows (L1 hits) and about the same number of neighbours
+  if (ord.mode == 1) {
+    // every record is this rank's own: the agents in the grid's cell order (AvoidOrder)
     if (i >= grid.cell_start[(size_t)grid.nx * grid.ny]) return;  // positions beyond the valid records
     i = grid.sorted_rec[i].valid;                                   // (the word carries the record's index)
+  } else if (ord.mode == 2) {
+    if (i >= ord.pos[n_records]) return;
+    i = ord.order[i];
   }
   const uint32_t gi = first_agent_global + i;  // index into the (gathered) record array
   const AvoidRecord me = records[gi];
@@ -1174,6 +1176,27 @@ void launch_avoid_grid(uint32_t n_records, const AvoidRecord* records, AvoidGrid
   if (n_records) k_grid_fill<<<blocks_for(n_records, 256), 256, 0, stream>>>(grid, n_records, records);
 }
 
+// AvoidOrder mode 2: this rank's records [first, first + n) picked out of the cell order
+__global__ void k_order_flags(AvoidGrid g, uint32_t n_records, uint32_t first, uint32_t n, uint32_t* flags) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n_records) return;
+  const uint32_t n_sorted = g.cell_start[(size_t)g.nx * g.ny];
+  flags[p] = (p < n_sorted && g.sorted_rec[p].valid - first < n) ? 1u : 0u;
+}
+__global__ void k_order_scatter(AvoidGrid g, uint32_t n_records, uint32_t first, const uint32_t* flags, const uint32_t* pos,
+                                uint32_t* order) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_records || !flags[p]) return;
+  order[pos[p]] = g.sorted_rec[p].valid - first;
+}
+void launch_avoid_order(const AvoidGrid& grid, uint32_t n_records, uint32_t first, uint32_t n, const AvoidOrder& ord,
+                        cudaStream_t stream) {
+  if (ord.mode != 2 || !n_records) return;
+  k_order_flags<<<blocks_for(n_records + 1, 256), 256, 0, stream>>>(grid, n_records, first, n, ord.flags);
+  launch_exclusive_scan(ord.flags, ord.pos, n_records + 1, ord.scan_tmp, stream);
+  k_order_scatter<<<blocks_for(n_records, 256), 256, 0, stream>>>(grid, n_records, first, ord.flags, ord.pos, ord.order);
+}
+
 void launch_stage_moves(const AgentArrays& ag, const AgentPersist& persist, float* staged, cudaStream_t stream) {
   if (ag.n) k_stage_moves<<<blocks_for(ag.n, 256), 256, 0, stream>>>(ag, persist, staged);
 }
@@ -1187,9 +1210,8 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
                             const AvoidRecord* char_records, const AvoidGrid& grid, const AvoidScratch& scratch,
                             const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
-                            cudaStream_t stream) {
+                            const AvoidOrder& ord, cudaStream_t stream) {
   if (!chunk_n) return;
-  const bool cell_order = first_agent_global == 0 && n_records == ag.n && ag.n >= 8192;
   // Few agents: small blocks, down to ONE agent per block (= per warp).  One thread walks its agent's scratch
   // serially (flood heap, cone list, loop nodes: tens of thousands of dependent instructions on a fine mesh) and
   // the agents of a warp diverge — their instruction streams run one after the other (3.4 of 8 lanes active per
@@ -1214,7 +1236,7 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
   while (threads > LMB_AVOID_MIN_THREADS && (uint64_t)chunk_n * 8 <= (uint64_t)sm_count * threads * LMB_AVOID_SPREAD) threads >>= 1;
   k_avoidance<<<blocks_for(chunk_n, threads), threads, 0, stream>>>(nav, ag, o, delta_time, first_agent_global, chunk_begin,
                                                           chunk_n, n_records, records, n_characters, char_records,
-                                                          grid, scratch, max_radius_bits, staged_moves, dbg, cell_order);
+                                                          grid, scratch, max_radius_bits, staged_moves, dbg, ord);
 }
 
 }  // namespace lmb

@@ -1409,7 +1409,7 @@ int32_t lmb_step_begin_impl(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
   // phase C
   nvtxRangePushA("lmb:phaseC follow");
   // from a few thousand agents on, k_follow takes them longest corridor first (three small launches)
-  if (n >= 8192) {
+  if (n >= 8192 || (n && (ctx->cfg.flags & LMB_CONFIG_ORDER_ALWAYS))) {
     CUDA_TRY(ctx, ctx->d_follow_order.reserve(n));
     CUDA_TRY(ctx, ctx->d_follow_key.reserve(n));
     CUDA_TRY(ctx, ctx->d_follow_hist.reserve(2 * FOLLOW_BUCKETS));

@@ -18,7 +18,9 @@ void launch_avoidance_chunk(const DevNav& nav, const AgentArrays& ag, const lmb_
                             uint32_t n_records, const AvoidRecord* records, uint32_t n_characters,
                             const AvoidRecord* char_records, const AvoidGrid& grid, const AvoidScratch& scratch,
                             const uint32_t* max_radius_bits, float* staged_moves, const AvoidDebug& dbg,
-                            cudaStream_t stream);
+                            const AvoidOrder& ord, cudaStream_t stream);
+void launch_avoid_order(const AvoidGrid& grid, uint32_t n_records, uint32_t first, uint32_t n, const AvoidOrder& ord,
+                        cudaStream_t stream);
 }  // namespace lmb
 
 AgentArrays lmb_make_agent_arrays(lmb_ctx* ctx);
@@ -118,10 +120,29 @@ int32_t lmb_avoidance_solve(lmb_ctx* ctx, const lmb_options* o, float dt, uint32
       dbg.lines = ctx->d_dbg_lines.p;
       dbg.lines_per_row = ctx->dbg_lines_per_row;
     }
+    // processing order (AvoidOrder): cell order from a few thousand agents on
+    AvoidOrder ord{};
+    if (n >= 8192 || (ctx->cfg.flags & LMB_CONFIG_ORDER_ALWAYS)) {
+      if (n_total == n && first == 0) {
+        ord.mode = 1;
+      } else {
+        ord.mode = 2;
+        CUDA_TRY(ctx, ctx->d_avoid_flags.reserve((size_t)n_total + 1));
+        CUDA_TRY(ctx, ctx->d_avoid_pos.reserve((size_t)n_total + 1));
+        CUDA_TRY(ctx, ctx->d_avoid_order.reserve(n));
+        CUDA_TRY(ctx, ctx->d_avoid_scan.reserve(exclusive_scan_tmp_words(n_total + 1)));
+        ord.flags = ctx->d_avoid_flags.p;
+        ord.pos = ctx->d_avoid_pos.p;
+        ord.order = ctx->d_avoid_order.p;
+        ord.scan_tmp = ctx->d_avoid_scan.p;
+        launch_avoid_order(grid, n_total, first, n, ord, s);
+        ctx->timings.kernel_launches += 4;
+      }
+    }
     launch_stage_moves(ag, persist, staged, s);
     for (uint32_t b = 0; b < n; b += chunk) {
       launch_avoidance_chunk(ctx->nav, ag, *o, dt, first, b, std::min(chunk, n - b), n_total, ctx->d_records.p,
-                             ctx->n_chars, ctx->d_char_records.p, grid, sc, max_radius_bits, staged, dbg, s);
+                             ctx->n_chars, ctx->d_char_records.p, grid, sc, max_radius_bits, staged, dbg, ord, s);
       ctx->timings.kernel_launches += 1;
     }
     launch_commit_moves(ag, persist, staged, sc.overflow, s);

@@ -127,7 +127,7 @@ struct lmb_ctx {
       d_q_success, d_q_explored, d_q_path_off, d_q_path_len, d_retry_list;
   DevBuf<float> d_q_start_point, d_q_end_point;
   DevBuf<uint32_t> d_follow_start, d_follow_end, d_presult, d_query_of_agent, d_waypoint_kind, d_waypoint_link;
-  DevBuf<uint32_t> d_follow_order, d_follow_hist;
+  DevBuf<uint32_t> d_follow_order, d_follow_hist, d_avoid_flags, d_avoid_pos, d_avoid_order, d_avoid_scan;
   DevBuf<uint8_t> d_follow_key;
   DevBuf<float> d_waypoint_points, d_path_endpoints;
   uint32_t* h_small = nullptr;  // pinned scratch (n_repath etc.)

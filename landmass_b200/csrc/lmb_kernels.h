@@ -204,6 +204,18 @@ struct AvoidGrid {
   uint32_t capacity_cells;
 };
 
+// The order in which k_avoidance takes a rank's agents: by index (mode 0), or in the grid's cell order, so that the
+// threads of a warp stand next to each other (the same candidate rows, about as many neighbours).  Mode 1: every
+// record is the rank's own and the cell-ordered record copies ARE the order; mode 2 (agents sharded over ranks):
+// the rank's own records picked out of the cell order (flags, scan, scatter).
+struct AvoidOrder {
+  uint32_t mode;
+  uint32_t* flags;   // [n_records + 1]
+  uint32_t* pos;     // [n_records + 1] exclusive scan of flags; pos[n_records] = how many
+  uint32_t* order;   // [n_agents] local dense agent indices
+  uint32_t* scan_tmp;
+};
+
 struct AvoidScratch {
   // per-agent variable-length scratch, sized by `per_agent_*`
   uint8_t* base;

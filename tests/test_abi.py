@@ -72,7 +72,8 @@ def test_constants_match_header():
                         ("LMB_CONFIG_ASTAR_NO_FOREST", _abi.CONFIG_ASTAR_NO_FOREST),
                         ("LMB_CONFIG_NO_L2_WINDOW", _abi.CONFIG_NO_L2_WINDOW),
                         ("LMB_CONFIG_ASTAR_SMALL_HEAP", _abi.CONFIG_ASTAR_SMALL_HEAP),
-                        ("LMB_CONFIG_ASTAR_NO_PAIR", _abi.CONFIG_ASTAR_NO_PAIR)]:
+                        ("LMB_CONFIG_ASTAR_NO_PAIR", _abi.CONFIG_ASTAR_NO_PAIR),
+                        ("LMB_CONFIG_ORDER_ALWAYS", _abi.CONFIG_ORDER_ALWAYS)]:
         m = re.search(rf"#define {name} (\d+)u", text)
         assert m and int(m.group(1)) == value, name
 

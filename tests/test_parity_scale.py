@@ -134,8 +134,12 @@ def _wrap(ptr, nbytes):
     return torch.as_tensor(_Buf(), device=torch.device("cuda", 0))
 
 
+@pytest.mark.parametrize("order", [pytest.param(0, id="index-order"), pytest.param(_abi.CONFIG_ORDER_ALWAYS, id="work-order")])
 @pytest.mark.parametrize("world_kind", ["maze", "tiled"])
-def test_sharded_step_on_the_gpu_equals_the_single_context_step(world_kind):
+def test_sharded_step_on_the_gpu_equals_the_single_context_step(world_kind, order):
+    """`order`: from 8192 agents on k_follow takes a rank's agents longest corridor first and k_avoidance in the
+    grid's cell order — with sharded agents through a flag / scan / scatter over the gathered records;
+    LMB_CONFIG_ORDER_ALWAYS runs those paths at this size (results do not depend on the order)."""
     import torch
 
     from landmass_b200._native import NativeBackend
@@ -153,8 +157,8 @@ def test_sharded_step_on_the_gpu_equals_the_single_context_step(world_kind):
     opts = synth.default_options()
     world = 2
     ranges = [sharded.shard_range(n, world, r) for r in range(world)]
-    ranks = [NativeBackend(max_agents=n, device=0) for _ in range(world)]
-    single = NativeBackend(max_agents=n, device=0)
+    ranks = [NativeBackend(max_agents=n, device=0, flags=order) for _ in range(world)]
+    single = NativeBackend(max_agents=n, device=0, flags=order)
     cpu = OracleBackend()
     for b in ranks + [single, cpu]:
         b.navdata_upload(flat)
