@@ -1,6 +1,6 @@
 """Builds the round-2 files under profiles/ from the ncu reports and bench lines a GPU run left in gpurun_out/.
 
-  python scripts/make_r02_profiles.py <final bundle dir> <single-search dir v2> <single-search dir v1> <cfg3 dir> <objs dir>
+  python scripts/make_r02_profiles.py <final bundle dir> <single-search dir v2> <single-search dir v1> <cfg3 dir> <objs dir> [final objs subdir]
 
 Every number in profiles/r02_*.md comes out of an .ncu-rep through `ncu -i ... --page raw/source --csv`
 (scripts/ncu_lines.py joins the source page with `nvdisasm -g` line info of the object that was profiled)."""
@@ -13,6 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 final, single2, single1, cfg3, objs = sys.argv[1:6]
+final_objs = sys.argv[6] if len(sys.argv) > 6 else "final"  # objects (and sources) of the build the final bundle ran
 P = os.path.join(ROOT, "profiles")
 
 
@@ -104,6 +105,19 @@ with open(os.path.join(P, "r02_ncu_astar_single.md"), "w") as f:
     f.write("\nThread kernel, maze (`k_astar.cu:295` = the pin behind the pop: the same L2 round trip of the records):\n\n")
     f.write(lines(os.path.join(single1, "ncu_thread_maze1.ncu-rep"), os.path.join(objs, "r2d", "k_astar.o"), "k_astar<",
                   "k_astarILj1ELj1536ELj2ELj2ELi3ELb1E"))
+    pair = os.path.join(final, "ncu_pair_maze1.ncu-rep")
+    if os.path.exists(pair):
+        f.write("\n## Two warps per query (search warp + heap warp), the final kernel\n\n"
+                "`... python scripts/profile_single.py maze pair 1`: both warps of the pair are in the one capture (64 threads), so "
+                "'warp instructions' counts both and every percentage below is of the two warps together.  `barrier` stalls are "
+                "the hand-overs: the search warp waiting for the pushes (the line after the second `bar.sync` of `peek`), the heap "
+                "warp waiting for the batch (`heap_warp_loop`, first read of the mailbox).\n\n")
+        f.write(table([("warp pair (maze)", pair)]))
+        hdr, units, rows = raw(pair)
+        inst = float(rows[0][hdr.index("smsp__inst_executed.sum")])
+        f.write(f"\nPer explored node: {inst / 86725:.0f} warp instructions over the two warps.  Top source lines by stall samples:\n\n")
+        f.write(lines(pair, os.path.join(objs, final_objs, "k_astar_warp.o"), "k_astar_warp",
+                      "k_astar_warpILj13760ELj1ELj1ELi3ELb1ELb1E", 20))
 
 # ---- loaded ----
 rep = os.path.join(final, "ncu_astar_loaded.ncu-rep")
@@ -136,13 +150,14 @@ if os.path.exists(a):
     with open(os.path.join(P, "r02_ncu_avoid_follow_cfg3.md"), "w") as f:
         f.write("# ncu --set full of `k_avoidance` (one 131 072-agent chunk) and `k_follow` (1 M agents) at config 3\n\n"
                 "`ncu --set full -k regex:k_avoidance|k_follow --launch-skip 4 --launch-count 1 python bench.py --config 3 "
-                "--steps 3 --warmup 2` (open field, 1 M agents, steady frame; scratch interleaved by agent, portal table).\n\n")
+                "--steps 3 --warmup 2` (open field, 1 M agents, steady frame; scratch interleaved by agent, portal table, agents "
+                "taken in cell order / longest corridor first).\n\n")
         f.write(table([("k_avoidance", a), ("k_follow", fo)]))
         f.write("\nk_avoidance, top source lines by stall samples (`lmb_device.cuh:29-32` = the first use of a gathered "
-                "neighbour record, `k_avoid.cu:1049-1054` = `select_next`, the scan of the candidate list in the agent's "
+                "neighbour record, the `k_avoid.cu` lines around 1060 = `select_next`, the scan of the candidate list in the agent's "
                 "interleaved scratch that yields the neighbours in (distance^2, index) order, `k_avoid.cu:53` = a `Strided` "
                 "scratch access):\n\n")
-        f.write(lines(a, os.path.join(objs, "final", "k_avoid.o"), "k_avoidance", "k_avoidance", 12))
+        f.write(lines(a, os.path.join(objs, final_objs, "k_avoid.o"), "k_avoidance", "k_avoidance", 12))
 
 # ---- plain copies ----
 for src, dst in (("ncu_launches_bench.csv", "r02_ncu_launches_bench.csv"), ("ncu_dram_bench.csv", "r02_ncu_dram_bench.csv"),
@@ -164,6 +179,16 @@ with open(os.path.join(P, "r02_configs.jsonl"), "w") as f:
             f.write(json.dumps(d) + "\n")
 if os.path.exists(os.path.join(final, "latency.jsonl")):
     shutil.copy(os.path.join(final, "latency.jsonl"), os.path.join(P, "r02_astar_latency.jsonl"))
+    # the 1 M-polygon tiled world takes five GPU-minutes: its rows may come from an earlier run (R02_TILED_LATENCY)
+    extra = os.environ.get("R02_TILED_LATENCY")
+    have_tiled = any('"tiled"' in l for l in open(os.path.join(P, "r02_astar_latency.jsonl")))
+    if extra and os.path.exists(extra) and not have_tiled:
+        with open(os.path.join(P, "r02_astar_latency.jsonl"), "a") as f:
+            for l in open(extra):
+                if '"mesh": "tiled"' in l:
+                    d = json.loads(l)
+                    d["note"] = "measured one commit before the final pair kernel (prefetch by the heap warp)"
+                    f.write(json.dumps(d) + "\n")
 print("profiles written")
 
 
@@ -236,7 +261,7 @@ with open(os.path.join(P, "r02_README.md"), "w") as f:
     f.write("| `r02_ncu_astar_loaded.md`, `_raw.csv` | `ncu --set full` of a fully loaded `k_astar<16,40,5,quad,forest,SIMPLE>` launch "
             "on a capturable arena, with the per-line stall table |\n"
             "| `r02_ncu_astar_single.md` | `ncu --set full` of ONE search: warp kernel before / after `cp.async` staging, thread kernel, "
-            "open field; the false scoreboard wait |\n"
+            "open field; the false scoreboard wait; the final warp-pair kernel |\n"
             "| `r02_ncu_avoid_follow_cfg3.md` | `ncu --set full` of `k_avoidance` and `k_follow` at config 3 (1 M agents) |\n")
     try:
         agg = launch_shares()
