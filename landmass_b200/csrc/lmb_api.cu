@@ -205,8 +205,8 @@ static void arena_layout(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_ca
 
 // (Re)allocates an A* arena: `slots` query slots.
 static int32_t setup_arena_into(lmb_ctx* ctx, AStarArena& a, DevBuf<uint8_t>& buf, uint32_t node_cap,
-                                uint32_t heap_cap, uint32_t slots, const char* what) {
-  arena_layout(ctx, node_cap, heap_cap, ctx->best_layout, a);
+                                uint32_t heap_cap, uint32_t slots, int layout, const char* what) {
+  arena_layout(ctx, node_cap, heap_cap, layout, a);
   a.n_slots = slots;
   a.base = nullptr;
   const size_t bytes = a.slot_stride * (size_t)slots;
@@ -226,7 +226,7 @@ static int32_t setup_arena_into(lmb_ctx* ctx, AStarArena& a, DevBuf<uint8_t>& bu
 
 static int32_t setup_arena(lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap, uint32_t slots) {
   ctx->d_arena.release();
-  return setup_arena_into(ctx, ctx->arena, ctx->d_arena, node_cap, heap_cap, slots, "arena");
+  return setup_arena_into(ctx, ctx->arena, ctx->d_arena, node_cap, heap_cap, slots, ctx->best_layout, "arena");
 }
 
 static size_t arena_slot_bytes(const lmb_ctx* ctx, uint32_t node_cap, uint32_t heap_cap) {
@@ -257,6 +257,38 @@ static int32_t ensure_arena(lmb_ctx* ctx, uint32_t n_queries) {
   if (per_slot * slots > budget) slots = (uint32_t)std::max<size_t>(budget / per_slot, 32);
   if (ctx->arena.base && ctx->arena.n_slots >= slots) return LMB_OK;
   return setup_arena(ctx, ctx->arena_node_cap, ctx->arena_heap_cap, slots);
+}
+
+// Side arena (dense slots) of the small batches of a mesh whose main arena is hashed.  The hashed layout is for
+// thousands of searches in flight on a mesh too large for a dense array each; the few hundred re-plans of a steady
+// frame can afford 4 bytes per state and slot, and a dense probe is one plain load into an array whose touched
+// part stays in L2 (1 M-polygon world, 100 000 agents: steady frame 291 -> 220 ms; forcing dense for every batch
+// instead doubles frame 0, 7.6 -> 16.2 s).  Returns false when it does not fit the byte budget.
+static const uint32_t SIDE_SLOTS_PER_SM = 4;
+static bool ensure_side_arena(lmb_ctx* ctx, uint32_t n_queries, int32_t* status) {
+  *status = LMB_OK;
+  const uint32_t want = std::max<uint32_t>((n_queries + 31u) / 32u * 32u, 64u);
+  if (!ctx->side_node_cap) {
+    const uint32_t n_states = ctx->n_ids + ctx->nav.n_links + 2;
+    ctx->side_node_cap = std::max<uint32_t>(ctx->arena_node_cap, std::min<uint32_t>(n_states / 8 + 1024, 1u << 20));
+    ctx->side_heap_cap = ctx->arena_heap_cap;
+  }
+  AStarArena probe{};
+  arena_layout(ctx, ctx->side_node_cap, ctx->side_heap_cap, 0, probe);
+  if (ctx->side_arena.base && ctx->side_arena.n_slots >= want && ctx->side_arena.node_cap == ctx->side_node_cap &&
+      ctx->side_arena.heap_cap == ctx->side_heap_cap)
+    return true;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  free_b += ctx->d_side_arena.cap;
+  const size_t budget = ctx->cfg.scratch_bytes ? (size_t)ctx->cfg.scratch_bytes / 4 : std::min<size_t>(free_b / 4, (size_t)16 << 30);
+  const uint32_t slots = std::max(want, ctx->side_arena.base ? ctx->side_arena.n_slots : 0u);
+  if (probe.slot_stride * (size_t)slots > budget) return false;
+  ctx->d_side_arena.release();
+  ctx->side_arena = AStarArena{};
+  *status = setup_arena_into(ctx, ctx->side_arena, ctx->d_side_arena, ctx->side_node_cap, ctx->side_heap_cap, slots, 0,
+                             "side arena");
+  return *status == LMB_OK;
 }
 
 int32_t lmb_navdata_upload(lmb_ctx* ctx, const lmb_navdata_desc* d) { return lmb_navdata_update(ctx, d, nullptr); }
@@ -686,6 +718,9 @@ int32_t lmb_navdata_update(lmb_ctx* ctx, const lmb_navdata_desc* d, const lmb_na
     }
     ctx->arena = AStarArena{};
     ctx->d_arena.release();
+    ctx->side_arena = AStarArena{};
+    ctx->d_side_arena.release();
+    ctx->side_node_cap = ctx->side_heap_cap = 0;
   }
 
   // ---- path pool: drop all paths ----
@@ -812,14 +847,21 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     int32_t st = prepare_pool(ctx, n, &needed);
     if (st != LMB_OK) return st;
   }
-  {
+  bool side = ctx->best_layout == 2 && n <= SIDE_SLOTS_PER_SM * ctx->sm_count &&
+              !(ctx->cfg.flags & (LMB_CONFIG_ASTAR_HASHED | LMB_CONFIG_ASTAR_LARGE_SHAPES));
+  if (side) {
+    int32_t st = LMB_OK;
+    side = ensure_side_arena(ctx, n, &st);
+    if (st != LMB_OK) return st;
+  }
+  if (!side) {
     int32_t st = ensure_arena(ctx, n);
     if (st != LMB_OK) return st;
   }
   unsigned long long done_total = 0, nodes_total = 0, explored_total = 0, heap_max_total = 0;
   const uint32_t* list = nullptr;
   uint32_t n_run = n;
-  if (q.slot && n > ctx->arena.n_slots) {
+  if (!side && q.slot && n > ctx->arena.n_slots) {
     // more queries than can run at once: start the (probably) longest searches first
     CUDA_TRY(ctx, ctx->d_query_order.reserve(n));
     launch_order_queries(n, q.slot, ctx->d_slot_cost_hint.p, (uint32_t)std::max(ctx->explored_estimate, 1.0),
@@ -829,7 +871,7 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     list = ctx->d_query_order.p;
   }
   std::vector<uint32_t> h_status;
-  const AStarArena* cur = &ctx->arena;  // the arena of the next launch
+  const AStarArena* cur = side ? &ctx->side_arena : &ctx->arena;  // the arena of the next launch
   for (int iter = 0; iter < 24; iter++) {
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(AStarCounters), s));
     AStarQueries qq = q;
@@ -837,7 +879,7 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
     qq.list = list;
     ctx->timings.astar_launch_kind |= launch_astar(ctx->nav, *cur, qq, make_pool(ctx), ctx->d_counters.p,
                                                    ctx->d_type_raw.p, ctx->big_heap, ctx->cfg.flags,
-                                                   ctx->best_layout == 3 ? ctx->cfg.astar_shape : 0u, s);
+                                                   cur->layout == 3 ? ctx->cfg.astar_shape : 0u, s);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters.p, sizeof(AStarCounters),
                                   cudaMemcpyDeviceToHost, s));
@@ -873,11 +915,33 @@ static int32_t run_astar(lmb_ctx* ctx, AStarQueries q) {
       if (st != LMB_OK) return st;
     }
     if (rd) ctx->best_layout = 0;  // compact best_estimates overflowed: dense from now on
-    if (ra || rh || rd) {
+    if (side && (ra || rh)) {
+      // the side arena's node list / open-list spill: double what overflowed; back to the main arena if that
+      // no longer fits
+      if (ra) ctx->side_node_cap = cur->node_cap * 2;
+      if (rh) ctx->side_heap_cap = AT_HEAP_SM + (cur->heap_cap - AT_HEAP_SM) * 2;
+      int32_t st = LMB_OK;
+      side = ensure_side_arena(ctx, n, &st);
+      if (st != LMB_OK) return st;
+      if (!side) {
+        st = ensure_arena(ctx, n);
+        if (st != LMB_OK) return st;
+        cur = &ctx->arena;
+      }
+    } else if (ra || rh || rd) {
       // node list / hashed table (ra) or open-list spill (rh) too small: double what overflowed
       uint32_t node_cap = cur->node_cap, heap_cap = cur->heap_cap;
       if (ra) node_cap *= 2;
       if (rh) heap_cap = AT_HEAP_SM + (heap_cap - AT_HEAP_SM) * 2;
+      if (ra && ctx->best_layout == 2 && !(ctx->cfg.flags & LMB_CONFIG_ASTAR_HASHED)) {
+        // The hashed table holds 8 bytes for at least twice the node list; once that is no smaller than the dense
+        // array (4 bytes per state) the searches are not local after all: dense from now on — smaller slots AND
+        // one plain load per probe (1 M-polygon world, searches of 1.3-3.4 M nodes: 80-160 MB -> 25-49 MB per
+        // slot, 1.74 -> 1.32 us per explored node alone, 2.74 -> 1.34 at one search per SM).
+        AStarArena h{};
+        arena_layout(ctx, std::max(ctx->arena_node_cap, node_cap), std::max(ctx->arena_heap_cap, heap_cap), 2, h);
+        if (h.best_bytes >= (size_t)h.n_states * 4) ctx->best_layout = 0;
+      }
       // Resize the arena for good (the slot count follows the byte budget).  Measured alternative,
       // rejected: a side arena of fat slots for the few searches that overflow, keeping the lean
       // main arena — the same searches overflow again next frame and are then searched twice.

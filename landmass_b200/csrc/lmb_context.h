@@ -88,6 +88,10 @@ struct lmb_ctx {
   DevBuf<uint8_t> d_arena;
   uint32_t kshift = 0, n_ids = 0;              // edge-record id space (see EdgeRec)
   uint32_t arena_node_cap = 0, arena_heap_cap = 0;
+  // Small batches on a mesh whose main arena is hashed run on a side arena of dense slots (run_astar)
+  AStarArena side_arena{};
+  DevBuf<uint8_t> d_side_arena;
+  uint32_t side_node_cap = 0, side_heap_cap = 0;
   bool big_heap = false;                       // launch shape for large open lists (k_astar.cu)
   int best_layout = 0;                         // best_estimates layout (k_astar_common.cuh): 0 dense, 1 compact, 2 hashed, 3 none (forest)
   bool nav_is_forest = false;

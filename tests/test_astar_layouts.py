@@ -300,3 +300,59 @@ def test_every_warp_kernel_launch_shape_against_the_oracle(case, pair):
         assert gpu.query_timings().astar_launch_kind == (2 if pair else 4)
     gpu.close()
     cpu.close()
+
+
+BIG_TILED_POINTS = np.array([[100.5, 100.5, 0], [100.5, 500.5, 0], [300.5, 200.5, 0], [650.5, 300.5, 0],
+                             [20.5, 400.5, 0], [22.5, 410.5, 0], [10.5, 10.5, 0], [300.5, 300.5, 0]], dtype=np.float32)
+
+
+def test_hashed_layout_turns_dense_when_searches_are_not_local(capfd):
+    """A mesh of more than 2^21 states starts with the hashed best_estimates (a search is expected to touch a small
+    part of it).  Far-reaching searches make the node list — and with it the table — grow; once the table is no
+    smaller than the dense array the context goes dense for good.  6 x 6 islands of 128 x 128 quads, 2.4 M states;
+    LARGE_SHAPES keeps the four queries on the main arena (small batches would take the dense side arena)."""
+    flat = synth.tiled_archipelago_flat(6, 128)
+    gpu, cpu = backends(flat, flags=_abi.CONFIG_DEBUG_LOG | _abi.CONFIG_ASTAR_LARGE_SHAPES, astar_slots=32)
+    opts = synth.default_options()
+    p, nodes = gpu.sample_points(BIG_TILED_POINTS, opts)
+    sn, sp, en, ep = nodes[0::2], p[0::2], nodes[1::2], p[1::2]
+    g = assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 22)
+    assert g[0].all() and g[1].max() > 300_000
+    err = capfd.readouterr().err
+    assert "hashed best" in err and "dense best" in err and "side arena" not in err, err
+    assert err.rindex("dense best") > err.rindex("hashed best")
+    # and it stays dense: the same queries again, no reallocation
+    assert_same_paths(gpu, cpu, sn, sp, en, ep, cap=1 << 22)
+    assert "best" not in capfd.readouterr().err
+    gpu.close()
+    cpu.close()
+
+
+def test_small_batches_on_a_hashed_mesh_take_the_dense_side_arena(capfd):
+    """The hashed layout is for thousands of searches in flight; up to four queries per SM run on a side arena of
+    dense slots instead (a plain load per probe), larger batches on the hashed main arena.  Same world as above."""
+    flat = synth.tiled_archipelago_flat(6, 128)
+    gpu, cpu = backends(flat, flags=_abi.CONFIG_DEBUG_LOG)
+    opts = synth.default_options()
+    p, nodes = gpu.sample_points(BIG_TILED_POINTS, opts)
+    g = assert_same_paths(gpu, cpu, nodes[0::2], p[0::2], nodes[1::2], p[1::2], cap=1 << 22)
+    assert g[0].all() and g[1].max() > 300_000
+    err = capfd.readouterr().err
+    assert "side arena" in err and "dense best" in err and "hashed best" not in err, err
+    # 700 short queries: the main arena, hashed
+    rng = np.random.Generator(np.random.PCG64(5))
+    a = np.zeros((700, 3), dtype=np.float32)
+    a[:, :2] = rng.uniform(40.0, 720.0, size=(700, 2))
+    b = a.copy()
+    b[:, :2] += rng.uniform(-25.0, 25.0, size=(700, 2))
+    pa, na = gpu.sample_points(a, opts)
+    pb, nb = gpu.sample_points(b, opts)
+    g = assert_same_paths(gpu, cpu, na, pa, nb, pb, cap=1 << 22)
+    assert g[0].all()
+    err = capfd.readouterr().err
+    assert "hashed best" in err and "side arena" not in err, err
+    # ... and small batches keep using the side arena without reallocating it
+    assert_same_paths(gpu, cpu, nodes[0::2], p[0::2], nodes[1::2], p[1::2], cap=1 << 22)
+    assert "arena" not in capfd.readouterr().err
+    gpu.close()
+    cpu.close()
