@@ -374,6 +374,9 @@ struct OpenList<HS, true> {  // the search warp's end of the mailbox
     __syncwarp();
     if (lane == 0) box->n = 0, box->flags = flags;
     pair_sync(id);
+    // STOP: a second barrier, so that the header of the next query's first batch cannot be written before the heap
+    // warp has read this one (every other header is written after the second barrier of its predecessor)
+    if (flags & BOX_STOP) pair_sync(id);
     n = 0, len_x = 0;
   }
   __device__ __forceinline__ void stop() { signal(BOX_STOP); }
@@ -411,6 +414,7 @@ __device__ __forceinline__ void heap_warp_loop(uint4* sm, uint4* gm, PairBox* bo
     if (flags & BOX_STOP) {
       heap.len = 0;
       if (lane == 0) box->next_len = 0;
+      pair_sync(id);  // (see OpenList::signal)
       continue;
     }
     for (uint32_t k = 0; k < n; k++) heap.push(box->e[k]);
