@@ -246,6 +246,8 @@ with open(os.path.join(P, "r02_README.md"), "w") as f:
             "(`_file` names the run) |\n"
             "| `r02_astar_latency.jsonl` | `scripts/astar_latency.py maze field tiled`: microseconds per explored node of the longest "
             "search per kernel family, 1 ... 2368 queries |\n"
+            "| `r02_layout_latency.jsonl` | `scripts/layout_latency.py`: dense against hashed `best_estimates` on the 1 M-polygon "
+            "tiled world, warp-pair kernel, 1 and 148 queries (what the dense side arena of small batches buys) |\n"
             "| `r02_ncu_launches_bench.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none -c 400` of `bench.py --steps 2 "
             "--warmup 1`: every kernel launch of the bench (cold-cache, serialised: compare shares) |\n")
     try:
