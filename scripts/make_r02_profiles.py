@@ -246,6 +246,9 @@ with open(os.path.join(P, "r02_README.md"), "w") as f:
             "(`_file` names the run) |\n"
             "| `r02_astar_latency.jsonl` | `scripts/astar_latency.py maze field tiled`: microseconds per explored node of the longest "
             "search per kernel family, 1 ... 2368 queries |\n"
+            "| `r02_ncu_dram_field.csv` | `ncu --replay-mode application --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
+            "gpu__time_duration.sum -k regex:k_astar python scripts/profile_grid_loaded.py`: DRAM bytes of loaded open-field "
+            "launches (12 000 antipodal queries on the 256x256 field of 8 m quads, 4 736 slots; 338.7 M explored nodes per launch) |\n"
             "| `r02_layout_latency.jsonl` | `scripts/layout_latency.py`: dense against hashed `best_estimates` on the 1 M-polygon "
             "tiled world, warp-pair kernel, 1 and 148 queries (what the dense side arena of small batches buys) |\n"
             "| `r02_ncu_launches_bench.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none -c 400` of `bench.py --steps 2 "
